@@ -1,0 +1,185 @@
+/* sdf2mesh_b200.h -- C ABI of libsdf2mesh_b200.so: the B200-native replacement for the
+ * SDF -> dual-contoured quad mesh path of WilstonOreo/sdf2mesh.
+ *
+ * The reference has no plugin/FFI seam: the path is inlined in `run()`
+ * (/root/reference/src/bin/sdf2mesh/main.rs:177-364).  This header is the seam a Rust `extern "C"`
+ * block, the C++ CLI (cli/sdf2mesh.cpp) and the Python host (sdf2mesh_b200/)
+ * all bind.  Every entry point names the reference interface it replaces.
+ *
+ * Conventions: every call returns an s2m_status (0 = ok); on failure s2m_last_error() returns a
+ * thread-local human-readable message (NVRTC log, CUDA error, parse error with line:col).  Handles
+ * are opaque.  One host thread drives one s2m_ctx at a time; at most one begin()..finish() pair is
+ * outstanding per ctx.  There is no CPU fallback: without a CUDA device s2m_ctx_create fails.
+ * Plain pointers and sizes only; no C++/torch types.
+ */
+#ifndef SDF2MESH_B200_H_
+#define SDF2MESH_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum s2m_status {
+  S2M_OK = 0,
+  S2M_ERR_INVALID_ARG = 1,
+  S2M_ERR_IO = 2,
+  S2M_ERR_PARSE = 3,       /* reference: ShaderProcessingError::ParseErrors  (shadertoy.rs:70-80) */
+  S2M_ERR_VALIDATION = 4,  /* reference: ShaderProcessingError::ValidationError / wgpu validation panic */
+  S2M_ERR_MISSING_SDF = 5, /* reference: ShaderProcessingError::MissingSdf(name) */
+  S2M_ERR_SHADER = 6,      /* reference: ShaderProcessingError::ShaderError(msg) */
+  S2M_ERR_NVRTC = 7,       /* reference: driver shader compile failure inside create_shader_module */
+  S2M_ERR_CUDA = 8,
+  S2M_ERR_NO_DEVICE = 9,
+  S2M_ERR_OOM = 10,
+  S2M_ERR_UNSUPPORTED = 11,
+  S2M_ERR_STATE = 12
+} s2m_status;
+
+const char* s2m_last_error(void);
+const char* s2m_version(void);
+void s2m_free(void* p); /* frees strings returned through char** out-parameters */
+
+/* ------------------------------------------------------------------ shader source (host only)
+ * s2m_shader mirrors `Sdf3DShader` (/root/reference/src/shader.rs:35-40): an opaque holder of ONE
+ * assembled source string plus how to lower it. */
+typedef struct s2m_shader s2m_shader;
+
+typedef enum s2m_source_kind {
+  S2M_SRC_SDF3D = 0,         /* text of a .sdf3d file: WGSL + `use`/`include` lines (shader.rs:159-203) */
+  S2M_SRC_GLSL_FRAGMENT = 1, /* GLSL fragment shader containing `float <sdf>(vec3)` (shader.rs:73-104) */
+  S2M_SRC_WGSL = 2,          /* already-assembled WGSL (no directive processing) */
+  S2M_SRC_CUDA = 3           /* CUDA C++ defining `float sdf3d(vec3 p)` inside namespace s2m_user (diagnostic) */
+} s2m_source_kind;
+
+/* Sdf3DShader::from_path (shader.rs:44): never fails on IO; an unreadable file is reported through
+ * s2m_shader_log() and yields an empty source, like the reference's log::error!. */
+int s2m_shader_from_path(const char* path, s2m_shader** out);
+/* Sdf3DShader::from_glsl_fragment_shader (shader.rs:73): S2M_ERR_PARSE / S2M_ERR_MISSING_SDF / S2M_ERR_SHADER. */
+int s2m_shader_from_glsl_fragment_shader(const char* path, const char* sdf_name, s2m_shader** out);
+/* Same two constructors from memory.  include_dir: directory `include "f";` resolves against
+ * (NULL = current working directory, as the reference does). */
+int s2m_shader_from_source(const char* text, size_t len, int kind, const char* sdf_name,
+                           const char* include_dir, s2m_shader** out);
+/* Sdf3DShader::add_to_source (shader.rs:155) */
+int s2m_shader_add_to_source(s2m_shader* s, const char* text);
+/* the `source` field: assembled WGSL (for GLSL input: WGSL regenerated from the IR) */
+const char* s2m_shader_source(const s2m_shader* s);
+/* Sdf3DShader::write_to_file (shader.rs:206); what --debug-wgsl writes (main.rs:223-225) */
+int s2m_shader_write_to_file(const s2m_shader* s, const char* path);
+/* info/warn/error lines the reference would have sent to `log` (module names, include errors) */
+const char* s2m_shader_log(const s2m_shader* s);
+/* lower to CUDA C++ without compiling (returns malloc'd text; S2M_ERR_PARSE/VALIDATION/MISSING_SDF) */
+int s2m_shader_lower_to_cuda(const s2m_shader* s, char** cuda_out);
+void s2m_shader_free(s2m_shader* s);
+
+/* WGSL text munging used by the GLSL / ShaderToy path (shadertoy.rs:169-352); results malloc'd. */
+int s2m_glsl_to_wgsl(const char* glsl, char** wgsl_out);                                /* convert_glsl_to_wgsl :169 */
+int s2m_wgsl_remove_function(const char* wgsl, const char* fn_prefix, char** out);      /* :251 */
+int s2m_wgsl_has_function(const char* wgsl, const char* fn_name, int* found);           /* :208, :295 */
+int s2m_wgsl_rename_function(const char* wgsl, const char* old_name, const char* new_name, char** out); /* :316 */
+
+/* ------------------------------------------------------------------ device context */
+typedef struct s2m_ctx s2m_ctx;
+/* replaces wgpu Instance/Adapter/Device/Queue setup (main.rs:180-196) */
+int s2m_ctx_create(int device_ordinal, s2m_ctx** out);
+void s2m_ctx_destroy(s2m_ctx* ctx);
+int s2m_ctx_device_info(const s2m_ctx* ctx, char* name, size_t name_len, int* sm_count, uint64_t* total_mem);
+
+/* ------------------------------------------------------------------ module = compiled SDF
+ * replaces Sdf3DShader::create_shader_module (shader.rs:220) + create_compute_pipeline (main.rs:283-290):
+ * front-end -> CUDA C++ -> NVRTC (sm_100a, --fmad=false) -> cubin -> cuModuleLoadData.
+ * ctx may be NULL: compile to cubin only (no device needed; used by CPU-side tests). */
+typedef struct s2m_module s2m_module;
+#define S2M_COMPILE_ALLOW_FMA 1u /* let ptxas contract a*b+c (faster, NOT bit-identical to the oracle) */
+int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32_t flags, s2m_module** out);
+const char* s2m_module_log(const s2m_module* m);         /* NVRTC log */
+const char* s2m_module_cuda_source(const s2m_module* m); /* what NVRTC compiled */
+int s2m_module_cubin(const s2m_module* m, const void** data, size_t* size);
+double s2m_module_compile_ms(const s2m_module* m, int which); /* 0 front-end, 1 NVRTC, 2 load */
+void s2m_module_free(s2m_module* m);
+
+/* ------------------------------------------------------------------ meshing
+ * s2m_mesh_params mirrors the AppState uniform (main.rs:28-33; dualcontour.wgsl:133-141):
+ * bb_min.xyz, bb_max.xyz, eps (= bb_max.w), dims.xyz.  dims.w (z_slice_idx) disappears: there is
+ * no per-slice loop. */
+#define S2M_MESH_ALL_SLICES 1u      /* scan all res_z slices, label = z (default reproduces the reference's
+                                       one-slice readback lag: slices 0..res_z-2, label = z+1) */
+#define S2M_MESH_NO_NORMALS 2u      /* skip sdf3d_normal (normals only reach the PLY writer) */
+#define S2M_MESH_EXACT_DENSE 4u     /* reference-cost mode: every cell is a candidate (8 evaluations per cell) */
+#define S2M_MESH_KEEP_CANDIDATES 8u /* keep the candidate key list in the result (tests) */
+
+typedef struct s2m_mesh_params {
+  uint32_t struct_size; /* sizeof(s2m_mesh_params) */
+  float bb_min[3];
+  float bb_max[3];
+  float eps;
+  uint32_t dims[3];
+  uint32_t flags;
+  uint32_t z_begin, z_end;     /* z-slab of true cell slices [z_begin, z_end); 0,0 = whole grid */
+  float tau_voxels;            /* candidate band half-width in voxels; 0 = default (0.5) */
+  uint64_t slab_budget_bytes;  /* max bytes of corner slab resident at once; 0 = default */
+} s2m_mesh_params;
+
+/* AppState::from(&Arguments) (main.rs:139-175): resolution 0 -> 256, rounded UP to a power of two
+ * (*rounded = 1 if it was changed); bounds <= 0 or NaN -> 2; cube centred on the origin
+ * (lib.rs:115-118); eps = 1e-4. */
+int s2m_params_from_cli(uint32_t resolution, float bounds, s2m_mesh_params* out, int* rounded);
+
+typedef struct s2m_timings {
+  float k1_slab_ms, k2_classify_ms, k3_compact_ms, k4_vertices_ms, k4_quads_ms;
+  float d2h_ms;        /* device->pinned host copies not hidden behind kernels */
+  float total_ms;      /* first launch -> everything resident in pinned host memory (CUDA events) */
+  double host_wall_ms; /* same span by the host clock */
+  uint32_t launches;   /* kernel launches issued */
+  uint32_t chunks;     /* slab chunks */
+} s2m_timings;
+
+typedef struct s2m_result s2m_result;
+typedef struct s2m_result_info {
+  uint64_t n_vertices;       /* own vertices (halo slice excluded) */
+  uint64_t n_halo_vertices;  /* vertices of slice z_begin-1, recomputed locally to name them in quads */
+  uint64_t n_quads;          /* valid quads */
+  uint64_t n_invalid_quads;  /* reference: "Invalid quad" warnings (mesh.rs:270-278) */
+  uint64_t n_candidates;
+  /* library-owned pinned host memory, valid until s2m_result_free */
+  const float* positions;      /* 3 * n_vertices */
+  const float* normals;        /* 3 * n_vertices (zeros with S2M_MESH_NO_NORMALS) */
+  const uint64_t* cell_keys;   /* n_vertices: x | y<<16 | label<<32  (mesh.rs:224-226) */
+  const uint8_t* sign_nibbles; /* n_vertices: bit0 s100, bit1 s010, bit2 s001, bit3 s000 (main.rs:338-339) */
+  const uint64_t* quads;       /* 4 * n_quads global vertex indices, after Quad::swap, reference order */
+  const uint64_t* candidates;  /* n_candidates keys (true z) if S2M_MESH_KEEP_CANDIDATES, else NULL */
+  s2m_timings timings;
+} s2m_result_info;
+
+/* replaces main.rs:298-356 (slice loop) + VertexList (mesh.rs:229-265): K1 slab, K2 classify,
+ * K3 compact, K4a vertices; vertices land in pinned host memory. */
+int s2m_mesh_begin(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, s2m_result** out);
+/* replaces VertexList::fetch_triangle_indices (mesh.rs:267-324): K4b quads with
+ * index = local + global_vertex_base (the exclusive prefix of n_vertices over lower z-slabs,
+ * obtained by the caller from an allgather across ranks; 0 on one GPU). */
+int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base);
+/* begin + finish(0) */
+int s2m_mesh_run(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, s2m_result** out);
+int s2m_result_get(const s2m_result* r, s2m_result_info* out);
+void s2m_result_free(s2m_result* r);
+
+/* TriangleMesh::write_to_file (mesh.rs:182): by extension, case-insensitive: .stl -> ASCII STL
+ * (mesh.rs:167), .ply -> ASCII PLY (mesh.rs:198); unknown extension logs an error and returns OK
+ * like the reference.  Valid for single-slab results (indices are positions in this result). */
+int s2m_result_write_mesh(const s2m_result* r, const char* path);
+int s2m_result_write_stl_binary(const s2m_result* r, const char* path);
+
+/* diagnostics */
+int s2m_eval_points(s2m_ctx* ctx, s2m_module* m, const float* xyz, uint64_t n, float* out);
+/* one corner plane of K1's slab: (dims[1]+1) x (dims[0]+1) floats, row-major */
+int s2m_debug_slab_plane(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, uint32_t plane, float* out);
+/* relative K1 cost of `planes` equal-thickness z bands (for balancing z-slabs across GPUs) */
+int s2m_cost_probe(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, uint32_t planes, double* cost_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDF2MESH_B200_H_ */

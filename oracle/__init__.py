@@ -1,0 +1,119 @@
+"""CPU oracle bindings -- TEST INFRASTRUCTURE ONLY (see oracle/oracle.cpp).
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs; never from sdf2mesh_b200/.
+"""
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+SDF_IDS = {"torus": 0, "martin_cube": 1, "p_key": 2, "mandelbulb": 3, "naga_sphere": 4}
+FLAG_ALL_SLICES = 1
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "sdf_examples.h")]
+    srcs.append(os.path.join(_HERE, "..", "sdf2mesh_b200", "csrc", "s2m_math.h"))
+    stale = force or not os.path.exists(so) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(build())
+        L.oracle_mesh_run.restype = ctypes.c_void_p
+        L.oracle_mesh_run.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_float, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+        L.oracle_mesh_counts.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
+        L.oracle_mesh_copy.argtypes = [ctypes.c_void_p] * 6
+        L.oracle_mesh_free.argtypes = [ctypes.c_void_p]
+        L.oracle_write_stl.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.oracle_write_ply.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.oracle_eval.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.oracle_axis_coords.argtypes = [ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_rust_f32.restype = ctypes.c_char_p
+        L.oracle_rust_f32.argtypes = [ctypes.c_float]
+        _LIB = L
+    return _LIB
+
+
+@dataclass
+class OracleMesh:
+    positions: np.ndarray   # (N,3) f32
+    normals: np.ndarray     # (N,3) f32
+    keys: np.ndarray        # (N,) u64   x | y<<16 | label<<32   (mesh.rs:224-226)
+    nibbles: np.ndarray     # (N,) u8    bit0 s100, bit1 s010, bit2 s001, bit3 s000
+    quads: np.ndarray       # (Q,4) u64  after swap, emission order, valid only
+    n_invalid_quads: int
+    seconds_cells: float
+    seconds_quads: float
+    _handle: int = 0
+
+    def free(self):
+        if self._handle:
+            lib().oracle_mesh_free(self._handle)
+            self._handle = 0
+
+    def write_stl(self, path):
+        assert lib().oracle_write_stl(self._handle, str(path).encode()) == 0
+
+    def write_ply(self, path):
+        assert lib().oracle_write_ply(self._handle, str(path).encode()) == 0
+
+
+def cube_bounds(b: float):
+    """lib.rs:115-118 Bounds3D::cube(a, 0): v = a*0.5 (f32); min = 0 - v, max = 0 + v."""
+    v = np.float32(b) * np.float32(0.5)
+    return (np.zeros(3, np.float32) - v).astype(np.float32), (np.zeros(3, np.float32) + v).astype(np.float32)
+
+
+def mesh_run(sdf, res, bounds=2.0, eps=1e-4, flags=0, z_begin=0, z_end=0, threads=0, bmin=None, bmax=None) -> OracleMesh:
+    L = lib()
+    sid = SDF_IDS[sdf] if isinstance(sdf, str) else int(sdf)
+    res3 = np.array([res] * 3 if np.isscalar(res) else res, dtype=np.uint32)
+    if bmin is None:
+        bmin, bmax = cube_bounds(bounds)
+    bmin = np.ascontiguousarray(bmin, np.float32)
+    bmax = np.ascontiguousarray(bmax, np.float32)
+    h = L.oracle_mesh_run(sid, res3.ctypes.data, bmin.ctypes.data, bmax.ctypes.data, ctypes.c_float(eps),
+                          flags, z_begin, z_end, threads)
+    nv, nq, ninv = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    sc, sq = ctypes.c_double(), ctypes.c_double()
+    L.oracle_mesh_counts(h, ctypes.byref(nv), ctypes.byref(nq), ctypes.byref(ninv), ctypes.byref(sc), ctypes.byref(sq))
+    pos = np.empty((nv.value, 3), np.float32)
+    nrm = np.empty((nv.value, 3), np.float32)
+    keys = np.empty(nv.value, np.uint64)
+    nib = np.empty(nv.value, np.uint8)
+    quads = np.empty((nq.value, 4), np.uint64)
+    L.oracle_mesh_copy(h, pos.ctypes.data, nrm.ctypes.data, keys.ctypes.data, nib.ctypes.data, quads.ctypes.data)
+    return OracleMesh(pos, nrm, keys, nib, quads, ninv.value, sc.value, sq.value, h)
+
+
+def eval_points(sdf, pts) -> np.ndarray:
+    sid = SDF_IDS[sdf] if isinstance(sdf, str) else int(sdf)
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    out = np.empty(pts.shape[0], np.float32)
+    lib().oracle_eval(sid, pts.ctypes.data, out.ctypes.data, pts.shape[0])
+    return out
+
+
+def axis_coords(res, bmin, bmax):
+    a = np.empty(res, np.float32)
+    b = np.empty(res, np.float32)
+    lib().oracle_axis_coords(res, ctypes.c_float(bmin), ctypes.c_float(bmax), a.ctypes.data, b.ctypes.data)
+    return a, b
+
+
+def rust_f32(x) -> str:
+    return lib().oracle_rust_f32(ctypes.c_float(x)).decode()

@@ -1,0 +1,696 @@
+// engine.cpp -- device context, NVRTC JIT and the meshing pipeline behind the C ABI
+// (include/sdf2mesh_b200.h).  Replaces the wgpu device / pipeline / per-slice texture readback /
+// host mesh assembly of the reference:
+//   /root/reference/src/bin/sdf2mesh/main.rs:180-196 (device), :229-290 (module, pipeline),
+//   :298-356 (slice loop), /root/reference/src/texture.rs (storage textures + MAP_READ staging),
+//   /root/reference/src/mesh.rs:213-341 (VertexList -> quads).
+//
+// Data layout in HBM (all owned by the ctx and reused across runs):
+//   slab        f32 [planes][res_y+1][pitch_x]   corner values, variant-A coordinates, chunked in z
+//   cand_mask   u32 [nz][res_y][words_x]          1 bit per cell: candidate
+//   word_prefix u32 [nz][res_y][words_x]          exclusive popcount prefix (rank table)
+//   cand_key    u64 [n_cand]                      x | y<<16 | z_true<<32, linear cell order
+//   cand_vrank  u32 [n_cand]                      vertex index or 0xffffffff
+//   vert_*      pos f32x3, nrm f32x3, key u64, nibble u8   [n_vertices]
+//   quads       u64 [n_quads][4]
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "kernels_static.h"
+
+namespace s2m_internal {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int status, const std::string& msg) { g_err = msg; return status; }
+}  // namespace s2m_internal
+using s2m_internal::fail;
+
+extern "C" const char* s2m_last_error(void) { return s2m_internal::g_err.c_str(); }
+extern "C" const char* s2m_version(void) { return "sdf2mesh_b200 0.1 (sm_100a)"; }
+extern "C" void s2m_free(void* p) { free(p); }
+
+// ------------------------------------------------------------------ driver API (dlopen'ed so the
+// library loads on machines without a GPU driver; the front-end and NVRTC work there)
+namespace {
+typedef int CUresult_t;
+typedef struct CUmod_st* CUmodule_t;
+typedef struct CUfunc_st* CUfunction_t;
+struct DriverApi {
+  void* handle = nullptr;
+  CUresult_t (*cuInit)(unsigned) = nullptr;
+  CUresult_t (*cuModuleLoadData)(CUmodule_t*, const void*) = nullptr;
+  CUresult_t (*cuModuleUnload)(CUmodule_t) = nullptr;
+  CUresult_t (*cuModuleGetFunction)(CUfunction_t*, CUmodule_t, const char*) = nullptr;
+  CUresult_t (*cuLaunchKernel)(CUfunction_t, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                               cudaStream_t, void**, void**) = nullptr;
+  CUresult_t (*cuGetErrorString)(CUresult_t, const char**) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+DriverApi& driver() {
+  static DriverApi d;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    d.handle = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!d.handle) { d.why = std::string("cannot load libcuda.so.1: ") + dlerror(); return; }
+#define S2M_SYM(name, sym)                                                        \
+  d.name = reinterpret_cast<decltype(d.name)>(dlsym(d.handle, sym));              \
+  if (!d.name) { d.why = std::string("libcuda.so.1 lacks ") + sym; return; }
+    S2M_SYM(cuInit, "cuInit")
+    S2M_SYM(cuModuleLoadData, "cuModuleLoadData")
+    S2M_SYM(cuModuleUnload, "cuModuleUnload")
+    S2M_SYM(cuModuleGetFunction, "cuModuleGetFunction")
+    S2M_SYM(cuLaunchKernel, "cuLaunchKernel")
+    S2M_SYM(cuGetErrorString, "cuGetErrorString")
+#undef S2M_SYM
+    d.ok = true;
+  });
+  return d;
+}
+std::string cu_err(CUresult_t r) {
+  const char* s = nullptr;
+  if (driver().cuGetErrorString) driver().cuGetErrorString(r, &s);
+  return s ? s : ("CUresult " + std::to_string(r));
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail(e__ == cudaErrorMemoryAllocation ? S2M_ERR_OOM : S2M_ERR_CUDA,                         \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                                  \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return S2M_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + (bytes >> 4) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      want = bytes;
+    }
+    if (e != cudaSuccess) { p = nullptr; return fail(S2M_ERR_OOM, "cudaMalloc(" + std::to_string(bytes) + " B): " + cudaGetErrorString(e)); }
+    cap = want;
+    return S2M_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBlock { void* p; size_t cap; bool used; };
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+// ------------------------------------------------------------------ ctx
+struct s2m_ctx {
+  int device = 0;
+  cudaDeviceProp prop{};
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  DevBuf slab, cand_mask, word_prefix, cand_key, cand_vrank, status, counters;
+  DevBuf v_pos, v_nrm, v_key, v_nib, quads, scratch;
+  std::vector<PinnedBlock> pinned;
+  unsigned long long* h_counters = nullptr;  // pinned, 16 words
+  cudaEvent_t ev[16]{};
+  bool busy = false;  // a begin() without finish()/free() is outstanding
+
+  void* lease_pinned(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    PinnedBlock* best = nullptr;
+    for (auto& b : pinned)
+      if (!b.used && b.cap >= bytes && (!best || b.cap < best->cap)) best = &b;
+    if (best && best->cap <= bytes * 4 + (1u << 20)) { best->used = true; return best->p; }
+    void* p = nullptr;
+    size_t want = bytes + (bytes >> 3);
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      // drop idle blocks and retry with the exact size
+      for (auto it = pinned.begin(); it != pinned.end();)
+        if (!it->used) { cudaFreeHost(it->p); it = pinned.erase(it); } else ++it;
+      want = bytes;
+      if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    pinned.push_back({p, want, true});
+    return p;
+  }
+  void release_pinned(void* p) {
+    for (auto& b : pinned) if (b.p == p) b.used = false;
+  }
+};
+
+enum Counter { C_NCAND = 0, C_NVERT = 1, C_NHALO = 2, C_NQUAD = 3, C_NINVALID = 4, C_TICKET0 = 5, C_TICKET1 = 6, C_TICKET2 = 7, C_COUNT = 16 };
+
+extern "C" int s2m_ctx_create(int device_ordinal, s2m_ctx** out) {
+  if (!out) return fail(S2M_ERR_INVALID_ARG, "s2m_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(S2M_ERR_NO_DEVICE, std::string("no CUDA device (this engine has no CPU fallback): ") +
+                                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  }
+  if (device_ordinal < 0 || device_ordinal >= n) return fail(S2M_ERR_INVALID_ARG, "device ordinal out of range");
+  if (!driver().ok) return fail(S2M_ERR_NO_DEVICE, driver().why);
+  CUDA_TRY(cudaSetDevice(device_ordinal));
+  CUDA_TRY(cudaFree(0));  // create the primary context the driver-API calls will use
+  std::unique_ptr<s2m_ctx> c(new s2m_ctx());
+  c->device = device_ordinal;
+  CUDA_TRY(cudaGetDeviceProperties(&c->prop, device_ordinal));
+  if (c->prop.major < 10)
+    return fail(S2M_ERR_NO_DEVICE, std::string("device '") + c->prop.name + "' is sm_" + std::to_string(c->prop.major) +
+                                       std::to_string(c->prop.minor) + "; this library only carries sm_100a code");
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), C_COUNT * 8, cudaHostAllocDefault));
+  int st = c->counters.ensure(C_COUNT * 8);
+  if (st) return st;
+  *out = c.release();
+  return S2M_OK;
+}
+
+extern "C" void s2m_ctx_destroy(s2m_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (DevBuf* b : {&c->slab, &c->cand_mask, &c->word_prefix, &c->cand_key, &c->cand_vrank, &c->status, &c->counters,
+                    &c->v_pos, &c->v_nrm, &c->v_key, &c->v_nib, &c->quads, &c->scratch})
+    b->release();
+  for (auto& b : c->pinned) cudaFreeHost(b.p);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+extern "C" int s2m_ctx_device_info(const s2m_ctx* c, char* name, size_t name_len, int* sm_count, uint64_t* total_mem) {
+  if (!c) return fail(S2M_ERR_INVALID_ARG, "ctx is NULL");
+  if (name && name_len) { strncpy(name, c->prop.name, name_len - 1); name[name_len - 1] = 0; }
+  if (sm_count) *sm_count = c->prop.multiProcessorCount;
+  if (total_mem) *total_mem = c->prop.totalGlobalMem;
+  return S2M_OK;
+}
+
+// ------------------------------------------------------------------ module
+struct s2m_module {
+  std::string cuda_source, log;
+  std::vector<char> cubin;
+  CUmodule_t mod = nullptr;
+  CUfunction_t k1 = nullptr, k4 = nullptr, k_eval = nullptr, k_probe = nullptr;
+  s2m_ctx* ctx = nullptr;
+  double ms_frontend = 0, ms_nvrtc = 0, ms_load = 0;
+};
+
+extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32_t flags, s2m_module** out) {
+  using namespace s2m_internal;
+  if (!shader || !out) return fail(S2M_ERR_INVALID_ARG, "s2m_module_compile: NULL argument");
+  *out = nullptr;
+  std::unique_ptr<s2m_module> m(new s2m_module());
+  m->ctx = ctx;
+  double t0 = now_ms();
+  std::string user, err;
+  if (shader->kind == S2M_SRC_CUDA) {
+    user = shader->source;
+  } else {
+    int st = s2m_frontend::lower_to_cuda(*shader, &user, &err);
+    if (st != S2M_OK) return fail(st, err);
+  }
+  double t1 = now_ms();
+  m->ms_frontend = t1 - t0;
+  m->cuda_source = std::string("#include \"s2m_sdf3d_lib.h\"\n#include \"s2m_scan.cuh\"\n") +
+                   "namespace s2m_user {\nusing namespace s2m;\n" + user + "\n}  // namespace s2m_user\n" +
+                   "#include \"kernels_jit.cuh\"\n";
+  nvrtcProgram prog = nullptr;
+  const char* hdr_src[] = {kSrcMathH, kSrcVecH, kSrcSdfLibH, kSrcScanCuh, kSrcKernelsJit};
+  const char* hdr_name[] = {"s2m_math.h", "s2m_vec.h", "s2m_sdf3d_lib.h", "s2m_scan.cuh", "kernels_jit.cuh"};
+  nvrtcResult r = nvrtcCreateProgram(&prog, m->cuda_source.c_str(), "sdf_module.cu", 5, hdr_src, hdr_name);
+  if (r != NVRTC_SUCCESS) return fail(S2M_ERR_NVRTC, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r));
+  std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+  opts.push_back((flags & S2M_COMPILE_ALLOW_FMA) ? "--fmad=true" : "--fmad=false");
+  r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+  size_t ls = 0;
+  nvrtcGetProgramLogSize(prog, &ls);
+  if (ls > 1) { m->log.resize(ls); nvrtcGetProgramLog(prog, &m->log[0]); }
+  if (r != NVRTC_SUCCESS) {
+    std::string msg = std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + m->log;
+    nvrtcDestroyProgram(&prog);
+    return fail(S2M_ERR_NVRTC, msg);
+  }
+  size_t cs = 0;
+  nvrtcGetCUBINSize(prog, &cs);
+  m->cubin.resize(cs);
+  nvrtcGetCUBIN(prog, m->cubin.data());
+  nvrtcDestroyProgram(&prog);
+  double t2 = now_ms();
+  m->ms_nvrtc = t2 - t1;
+  if (ctx) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUresult_t cr = driver().cuModuleLoadData(&m->mod, m->cubin.data());
+    if (cr) return fail(S2M_ERR_CUDA, "cuModuleLoadData: " + cu_err(cr));
+    struct { CUfunction_t* f; const char* n; } fns[] = {
+        {&m->k1, "s2m_k1_slab"}, {&m->k4, "s2m_k4_vertices"}, {&m->k_eval, "s2m_k_eval"}, {&m->k_probe, "s2m_k_cost_probe"}};
+    for (auto& f : fns) {
+      cr = driver().cuModuleGetFunction(f.f, m->mod, f.n);
+      if (cr) return fail(S2M_ERR_CUDA, std::string("cuModuleGetFunction(") + f.n + "): " + cu_err(cr));
+    }
+    m->ms_load = now_ms() - t2;
+  }
+  *out = m.release();
+  return S2M_OK;
+}
+
+extern "C" const char* s2m_module_log(const s2m_module* m) { return m ? m->log.c_str() : ""; }
+extern "C" const char* s2m_module_cuda_source(const s2m_module* m) { return m ? m->cuda_source.c_str() : ""; }
+extern "C" int s2m_module_cubin(const s2m_module* m, const void** data, size_t* size) {
+  if (!m || !data || !size) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
+  *data = m->cubin.data(); *size = m->cubin.size();
+  return S2M_OK;
+}
+extern "C" double s2m_module_compile_ms(const s2m_module* m, int which) {
+  if (!m) return 0;
+  return which == 0 ? m->ms_frontend : (which == 1 ? m->ms_nvrtc : m->ms_load);
+}
+extern "C" void s2m_module_free(s2m_module* m) {
+  if (!m) return;
+  if (m->mod && m->ctx) { cudaSetDevice(m->ctx->device); driver().cuModuleUnload(m->mod); }
+  delete m;
+}
+
+// ------------------------------------------------------------------ grid bookkeeping
+namespace {
+struct GridDev {  // must match S2mGrid in kernels_jit.cuh
+  float bmin[3];
+  float size[3];
+  float eps;
+  unsigned res[3];
+  unsigned pitch_x;
+  unsigned rows;
+  unsigned long long plane_stride;
+};
+struct VertexOutDev {  // must match S2mVertexOut
+  float* pos; float* nrm; unsigned long long* key; unsigned char* nibble; unsigned* cand_vrank;
+  unsigned long long* status; unsigned* ticket; unsigned long long* n_vertices; unsigned long long* n_halo;
+};
+
+int make_grid(const s2m_mesh_params* p, GridDev* g) {
+  if (!p) return fail(S2M_ERR_INVALID_ARG, "params is NULL");
+  if (p->struct_size != sizeof(s2m_mesh_params)) return fail(S2M_ERR_INVALID_ARG, "s2m_mesh_params.struct_size mismatch");
+  for (int a = 0; a < 3; ++a) {
+    if (p->dims[a] < 2 || p->dims[a] > 65535u)
+      return fail(S2M_ERR_INVALID_ARG, "dims must be in [2, 65535] (cell coordinates are u16 in the reference key, mesh.rs:214)");
+    g->bmin[a] = p->bb_min[a];
+    volatile float v = (float)(p->dims[a] - 1u);      // dualcontour.wgsl:23
+    volatile float extent = p->bb_max[a] - p->bb_min[a];
+    g->size[a] = extent / v;                          // :24
+    g->res[a] = p->dims[a];
+  }
+  g->eps = p->eps;
+  g->pitch_x = (p->dims[0] + 1u + 31u) & ~31u;
+  g->rows = p->dims[1] + 1u;
+  g->plane_stride = (unsigned long long)g->pitch_x * g->rows;
+  return S2M_OK;
+}
+
+int launch(CUfunction_t f, dim3 grid, dim3 block, cudaStream_t st, void** args, const char* name) {
+  CUresult_t r = driver().cuLaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, st, args, nullptr);
+  if (r) return fail(S2M_ERR_CUDA, std::string("cuLaunchKernel(") + name + "): " + cu_err(r));
+  return S2M_OK;
+}
+}  // namespace
+
+// ------------------------------------------------------------------ result
+struct s2m_result {
+  s2m_ctx* ctx = nullptr;
+  s2m_module* mod = nullptr;
+  s2m_mesh_params params{};
+  GridDev grid{};
+  uint32_t z_first = 0, nz = 0, label_add = 0, halo = 0, words_x = 0;
+  uint64_t n_cand = 0, n_vert_total = 0, n_halo = 0, n_quads = 0, n_invalid = 0;
+  float* h_pos = nullptr; float* h_nrm = nullptr; uint64_t* h_key = nullptr; uint8_t* h_nib = nullptr;
+  uint64_t* h_quads = nullptr; uint64_t* h_cand = nullptr;
+  s2m_timings t{};
+  double wall0 = 0;
+  bool finished = false;
+};
+
+extern "C" void s2m_result_free(s2m_result* r) {
+  if (!r) return;
+  if (r->ctx) {
+    for (void* p : {(void*)r->h_pos, (void*)r->h_nrm, (void*)r->h_key, (void*)r->h_nib, (void*)r->h_quads, (void*)r->h_cand})
+      if (p) r->ctx->release_pinned(p);
+    if (!r->finished) r->ctx->busy = false;
+  }
+  delete r;
+}
+
+extern "C" int s2m_params_from_cli(uint32_t resolution, float bounds, s2m_mesh_params* out, int* rounded) {
+  if (!out) return fail(S2M_ERR_INVALID_ARG, "out is NULL");
+  memset(out, 0, sizeof *out);
+  out->struct_size = sizeof *out;
+  uint32_t res = resolution ? resolution : 256u;  // main.rs:141
+  int r = 0;
+  if (__builtin_popcount(res) > 1) {             // main.rs:142-148: 2 << ilog2(res)
+    res = 2u << (31 - __builtin_clz(res));
+    r = 1;
+  }
+  if (rounded) *rounded = r;
+  float b = (bounds > 0.0f) ? bounds : 2.0f;     // main.rs:150 unwrap_or(2.0)
+  volatile float v = b * 0.5f;                   // lib.rs:115-118
+  for (int a = 0; a < 3; ++a) { out->bb_min[a] = 0.0f - v; out->bb_max[a] = 0.0f + v; out->dims[a] = res; }
+  out->eps = 0.0001f;                            // main.rs:165
+  return S2M_OK;
+}
+
+extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_result** out) {
+  if (!c || !m || !p || !out) return fail(S2M_ERR_INVALID_ARG, "s2m_mesh_begin: NULL argument");
+  *out = nullptr;
+  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (c->busy) return fail(S2M_ERR_STATE, "a previous s2m_mesh_begin on this ctx has not been finished or freed");
+  CUDA_TRY(cudaSetDevice(c->device));
+  std::unique_ptr<s2m_result> r(new s2m_result());
+  r->ctx = c; r->mod = m; r->params = *p;
+  int st = make_grid(p, &r->grid);
+  if (st) return st;
+  const GridDev& g = r->grid;
+  const bool all = p->flags & S2M_MESH_ALL_SLICES;
+  const uint32_t zlast = all ? g.res[2] : g.res[2] - 1u;  // the last slice is never read back
+  uint32_t zb = p->z_begin, ze = p->z_end;
+  if (zb == 0 && ze == 0) ze = zlast;
+  ze = std::min(ze, zlast);
+  if (zb > ze) zb = ze;
+  r->label_add = all ? 0u : 1u;
+  r->halo = (zb > 0 && zb < ze) ? 1u : 0u;
+  r->z_first = zb - r->halo;
+  r->nz = ze - r->z_first;
+  r->words_x = (g.res[0] + 31u) / 32u;
+  const float min_size = std::min(g.size[0], std::min(g.size[1], g.size[2]));
+  const float tau = (p->tau_voxels > 0.0f ? p->tau_voxels : 0.5f) * min_size;
+
+  c->busy = true;
+  struct BusyGuard { s2m_ctx* c; bool keep = false; ~BusyGuard() { if (!keep) c->busy = false; } } guard{c};
+  r->wall0 = now_ms();
+  cudaStream_t s = c->stream;
+  unsigned long long* d_cnt = c->counters.as<unsigned long long>();
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, C_COUNT * 8, s));
+  CUDA_TRY(cudaEventRecord(c->ev[0], s));
+  uint32_t launches = 0, chunks = 0;
+
+  const unsigned long long words_per_slice = (unsigned long long)g.res[1] * r->words_x;
+  const unsigned long long n_words = words_per_slice * r->nz;
+  if (r->nz > 0) {
+    if ((st = c->cand_mask.ensure((n_words + 16) * 4))) return st;
+    if ((st = c->word_prefix.ensure((n_words + 16) * 4))) return st;
+  }
+  // ---- K1 + K2 over z-chunks of the slab
+  if (r->nz > 0 && !(p->flags & S2M_MESH_EXACT_DENSE)) {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const unsigned long long plane_bytes = g.plane_stride * 4ull;
+    unsigned long long budget = p->slab_budget_bytes ? p->slab_budget_bytes
+                                                     : std::min<unsigned long long>((unsigned long long)(free_b + c->slab.cap) / 2, 64ull << 30);
+    unsigned long long max_planes = std::max<unsigned long long>(2, budget / plane_bytes);
+    const uint32_t zc = (uint32_t)std::min<unsigned long long>(r->nz, max_planes - 1);
+    if ((st = c->slab.ensure((unsigned long long)(zc + 1) * plane_bytes))) return st;
+    for (uint32_t z0 = 0; z0 < r->nz; z0 += zc) {
+      const uint32_t nzc = std::min(zc, r->nz - z0);
+      GridDev gd = g;
+      float* slab = c->slab.as<float>();
+      unsigned first_plane = r->z_first + z0, n_planes = nzc + 1;
+      void* a1[] = {&gd, &slab, &first_plane, &n_planes};
+      dim3 grid1((g.pitch_x + 127u) / 128u, (g.rows + 7u) / 8u, n_planes);
+      if (chunks == 0) CUDA_TRY(cudaEventRecord(c->ev[1], s));
+      if ((st = launch(m->k1, grid1, dim3(32, 8, 1), s, a1, "s2m_k1_slab"))) return st;
+      S2mK2Args a2{};
+      a2.slab = slab; a2.pitch_x = g.pitch_x; a2.plane_stride = g.plane_stride;
+      a2.res_x = g.res[0]; a2.res_y = g.res[1]; a2.nz_chunk = nzc; a2.tau = tau;
+      a2.cand_mask = c->cand_mask.as<uint32_t>() + words_per_slice * z0;
+      a2.words_x = r->words_x; a2.total = d_cnt + C_NCAND;
+      if (chunks == 0) CUDA_TRY(cudaEventRecord(c->ev[2], s));
+      int e2 = s2m_launch_k2(&a2, s);
+      if (e2) return fail(S2M_ERR_CUDA, std::string("k2_classify launch: ") + cudaGetErrorString((cudaError_t)e2));
+      launches += 2; ++chunks;
+    }
+  } else if (r->nz > 0) {
+    // reference-cost mode: every cell is a candidate
+    std::vector<uint32_t> row(r->words_x, 0xffffffffu);
+    if (g.res[0] % 32u) row.back() = (1u << (g.res[0] % 32u)) - 1u;
+    std::vector<uint32_t> host(n_words);
+    for (unsigned long long i = 0; i < n_words; i += r->words_x) memcpy(&host[i], row.data(), r->words_x * 4);
+    CUDA_TRY(cudaMemcpyAsync(c->cand_mask.p, host.data(), n_words * 4, cudaMemcpyHostToDevice, s));
+    unsigned long long nc = (unsigned long long)g.res[0] * g.res[1] * r->nz;
+    CUDA_TRY(cudaMemcpyAsync(d_cnt + C_NCAND, &nc, 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(c->ev[1], s));
+    CUDA_TRY(cudaEventRecord(c->ev[2], s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+  } else {
+    CUDA_TRY(cudaEventRecord(c->ev[1], s));
+    CUDA_TRY(cudaEventRecord(c->ev[2], s));
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[3], s));
+  r->t.chunks = chunks;
+  // ---- sync #1: candidate count sizes everything downstream
+  CUDA_TRY(cudaMemcpyAsync(c->h_counters, d_cnt, 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  r->n_cand = c->h_counters[0];
+  if (r->n_cand >= 0xffffffffull) return fail(S2M_ERR_UNSUPPORTED, "more than 2^32-1 candidate cells in one slab; split it with z_begin/z_end");
+
+  const unsigned k3_tiles = r->nz ? s2m_k3_tiles(n_words) : 0;
+  const unsigned k4_tiles = (unsigned)((r->n_cand + 127) / 128);
+  const size_t status_words = (size_t)k3_tiles + k4_tiles + 8;
+  if ((st = c->status.ensure(status_words * 8))) return st;
+  if ((st = c->cand_key.ensure((r->n_cand + 1) * 8))) return st;
+  if ((st = c->cand_vrank.ensure((r->n_cand + 1) * 4))) return st;
+  if ((st = c->v_pos.ensure((r->n_cand + 1) * 12))) return st;
+  if ((st = c->v_nrm.ensure((r->n_cand + 1) * 12))) return st;
+  if ((st = c->v_key.ensure((r->n_cand + 1) * 8))) return st;
+  if ((st = c->v_nib.ensure(r->n_cand + 16))) return st;
+  CUDA_TRY(cudaMemsetAsync(c->status.p, 0, status_words * 8, s));
+  // ---- K3
+  CUDA_TRY(cudaEventRecord(c->ev[4], s));
+  if (k3_tiles) {
+    S2mK3Args a3{};
+    a3.cand_mask = c->cand_mask.as<uint32_t>(); a3.n_words = n_words; a3.words_x = r->words_x; a3.res_y = g.res[1];
+    a3.z_offset = r->z_first; a3.word_prefix = c->word_prefix.as<uint32_t>(); a3.cand_key = c->cand_key.as<unsigned long long>();
+    a3.status = c->status.as<unsigned long long>(); a3.ticket = reinterpret_cast<unsigned*>(d_cnt + C_TICKET0);
+    int e3 = s2m_launch_k3(&a3, s);
+    if (e3) return fail(S2M_ERR_CUDA, std::string("k3_compact launch: ") + cudaGetErrorString((cudaError_t)e3));
+    ++launches;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[5], s));
+  // ---- K4a
+  if (k4_tiles) {
+    GridDev gd = g;
+    const unsigned long long* ck = c->cand_key.as<unsigned long long>();
+    unsigned long long nc = r->n_cand;
+    unsigned label_add = r->label_add, halo_below = r->halo ? (r->z_first + 1u) : 0u;
+    unsigned want_normals = (p->flags & S2M_MESH_NO_NORMALS) ? 0u : 1u;
+    VertexOutDev vo{c->v_pos.as<float>(), c->v_nrm.as<float>(), c->v_key.as<unsigned long long>(), c->v_nib.as<unsigned char>(),
+                    c->cand_vrank.as<unsigned>(), c->status.as<unsigned long long>() + k3_tiles,
+                    reinterpret_cast<unsigned*>(d_cnt + C_TICKET1), d_cnt + C_NVERT, d_cnt + C_NHALO};
+    void* a4[] = {&gd, &ck, &nc, &label_add, &halo_below, &want_normals, &vo};
+    if ((st = launch(m->k4, dim3(k4_tiles), dim3(128), s, a4, "s2m_k4_vertices"))) return st;
+    ++launches;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[6], s));
+  // ---- sync #2: vertex counts
+  CUDA_TRY(cudaMemcpyAsync(c->h_counters, d_cnt, C_COUNT * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  r->n_vert_total = c->h_counters[C_NVERT];
+  r->n_halo = c->h_counters[C_NHALO];
+  const uint64_t n_own = r->n_vert_total - r->n_halo;
+  // ---- vertices -> pinned host (copy stream; overlaps the quad kernel)
+  r->h_pos = (float*)c->lease_pinned(n_own * 12);
+  r->h_nrm = (float*)c->lease_pinned(n_own * 12);
+  r->h_key = (uint64_t*)c->lease_pinned(n_own * 8);
+  r->h_nib = (uint8_t*)c->lease_pinned(n_own);
+  if (!r->h_pos || !r->h_nrm || !r->h_key || !r->h_nib) return fail(S2M_ERR_OOM, "cudaHostAlloc for vertex output failed");
+  if (p->flags & S2M_MESH_KEEP_CANDIDATES) {
+    r->h_cand = (uint64_t*)c->lease_pinned(r->n_cand * 8);
+    if (!r->h_cand) return fail(S2M_ERR_OOM, "cudaHostAlloc for candidate list failed");
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[7], s));
+  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev[7], 0));
+  if (n_own) {
+    CUDA_TRY(cudaMemcpyAsync(r->h_pos, c->v_pos.as<float>() + 3 * r->n_halo, n_own * 12, cudaMemcpyDeviceToHost, c->copy_stream));
+    if (p->flags & S2M_MESH_NO_NORMALS) memset(r->h_nrm, 0, n_own * 12);
+    else CUDA_TRY(cudaMemcpyAsync(r->h_nrm, c->v_nrm.as<float>() + 3 * r->n_halo, n_own * 12, cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r->h_key, c->v_key.as<unsigned long long>() + r->n_halo, n_own * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(r->h_nib, c->v_nib.as<unsigned char>() + r->n_halo, n_own, cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  if (r->h_cand && r->n_cand)
+    CUDA_TRY(cudaMemcpyAsync(r->h_cand, c->cand_key.p, r->n_cand * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+  CUDA_TRY(cudaEventRecord(c->ev[8], c->copy_stream));
+  r->t.launches = launches;
+  guard.keep = true;
+  *out = r.release();
+  return S2M_OK;
+}
+
+extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
+  if (!r || !r->ctx) return fail(S2M_ERR_INVALID_ARG, "s2m_mesh_finish: NULL result");
+  if (r->finished) return fail(S2M_ERR_STATE, "s2m_mesh_finish called twice");
+  s2m_ctx* c = r->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  unsigned long long* d_cnt = c->counters.as<unsigned long long>();
+  const uint64_t n_own = r->n_vert_total - r->n_halo;
+  const unsigned tiles = s2m_k4b_tiles(n_own);
+  int st;
+  if ((st = c->quads.ensure((size_t)n_own * 3 * 32 + 64))) return st;
+  if ((st = c->scratch.ensure(((size_t)tiles + 8) * 8))) return st;
+  CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, ((size_t)tiles + 8) * 8, s));
+  CUDA_TRY(cudaEventRecord(c->ev[9], s));
+  if (tiles) {
+    S2mK4bArgs a{};
+    a.vert_key = c->v_key.as<unsigned long long>(); a.vert_nibble = c->v_nib.as<unsigned char>();
+    a.n_vertices = r->n_vert_total; a.n_halo = r->n_halo;
+    a.cand_mask = c->cand_mask.as<uint32_t>(); a.word_prefix = c->word_prefix.as<uint32_t>(); a.cand_vrank = c->cand_vrank.as<uint32_t>();
+    a.words_x = r->words_x; a.res_y = r->grid.res[1]; a.z_first = r->z_first; a.label_add = r->label_add;
+    a.index_offset = (long long)global_vertex_base - (long long)r->n_halo;
+    a.quads = c->quads.as<unsigned long long>(); a.status = c->scratch.as<unsigned long long>();
+    a.ticket = reinterpret_cast<unsigned*>(d_cnt + C_TICKET2); a.n_quads = d_cnt + C_NQUAD; a.n_invalid = d_cnt + C_NINVALID;
+    int e = s2m_launch_k4b(&a, s);
+    if (e) return fail(S2M_ERR_CUDA, std::string("k4_quads launch: ") + cudaGetErrorString((cudaError_t)e));
+    r->t.launches += 1;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[10], s));
+  // ---- sync #3: quad counts
+  CUDA_TRY(cudaMemcpyAsync(c->h_counters, d_cnt, C_COUNT * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  r->n_quads = c->h_counters[C_NQUAD];
+  r->n_invalid = c->h_counters[C_NINVALID];
+  r->h_quads = (uint64_t*)c->lease_pinned(r->n_quads * 32);
+  if (!r->h_quads) return fail(S2M_ERR_OOM, "cudaHostAlloc for quad output failed");
+  if (r->n_quads) CUDA_TRY(cudaMemcpyAsync(r->h_quads, c->quads.p, r->n_quads * 32, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamWaitEvent(s, c->ev[8], 0));  // the vertex copies are part of the end-to-end span
+  CUDA_TRY(cudaEventRecord(c->ev[11], s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+  r->t.host_wall_ms = now_ms() - r->wall0;
+  auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
+  // single-chunk runs time K1 and K2 separately; chunked runs report their sum under k1 (interleaved)
+  if (r->t.chunks <= 1) { r->t.k1_slab_ms = el(1, 2); r->t.k2_classify_ms = el(2, 3); }
+  else { r->t.k1_slab_ms = el(1, 3); r->t.k2_classify_ms = 0; }
+  r->t.k3_compact_ms = el(4, 5);
+  r->t.k4_vertices_ms = el(5, 6);
+  r->t.k4_quads_ms = el(9, 10);
+  float d2h_v = el(7, 8), d2h_q = el(10, 11);
+  r->t.d2h_ms = d2h_v + d2h_q;
+  r->t.total_ms = el(0, 11);
+  r->finished = true;
+  c->busy = false;
+  return S2M_OK;
+}
+
+extern "C" int s2m_mesh_run(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_result** out) {
+  int st = s2m_mesh_begin(c, m, p, out);
+  if (st) return st;
+  st = s2m_mesh_finish(*out, 0);
+  if (st) { s2m_result_free(*out); *out = nullptr; }
+  return st;
+}
+
+extern "C" int s2m_result_get(const s2m_result* r, s2m_result_info* o) {
+  if (!r || !o) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
+  memset(o, 0, sizeof *o);
+  o->n_vertices = r->n_vert_total - r->n_halo;
+  o->n_halo_vertices = r->n_halo;
+  o->n_quads = r->n_quads;
+  o->n_invalid_quads = r->n_invalid;
+  o->n_candidates = r->n_cand;
+  o->positions = r->h_pos; o->normals = r->h_nrm; o->cell_keys = r->h_key; o->sign_nibbles = r->h_nib;
+  o->quads = r->h_quads; o->candidates = r->h_cand;
+  o->timings = r->t;
+  return S2M_OK;
+}
+
+// ------------------------------------------------------------------ diagnostics
+extern "C" int s2m_eval_points(s2m_ctx* c, s2m_module* m, const float* xyz, uint64_t n, float* out) {
+  if (!c || !m || !xyz || !out) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
+  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (n == 0) return S2M_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  DevBuf in, o;
+  int st;
+  if ((st = in.ensure(n * 12))) return st;
+  if ((st = o.ensure(n * 4))) { in.release(); return st; }
+  cudaStream_t s = c->stream;
+  cudaError_t e = cudaMemcpyAsync(in.p, xyz, n * 12, cudaMemcpyHostToDevice, s);
+  const float* pin = in.as<float>(); float* pout = o.as<float>(); unsigned long long nn = n;
+  void* args[] = {&pin, &pout, &nn};
+  if (e == cudaSuccess) st = launch(m->k_eval, dim3((unsigned)((n + 255) / 256)), dim3(256), s, args, "s2m_k_eval");
+  if (e == cudaSuccess && !st) e = cudaMemcpyAsync(out, o.p, n * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && !st) e = cudaStreamSynchronize(s);
+  in.release(); o.release();
+  if (st) return st;
+  if (e != cudaSuccess) return fail(S2M_ERR_CUDA, std::string("s2m_eval_points: ") + cudaGetErrorString(e));
+  return S2M_OK;
+}
+
+extern "C" int s2m_debug_slab_plane(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, uint32_t plane, float* out) {
+  if (!c || !m || !p || !out) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
+  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (c->busy) return fail(S2M_ERR_STATE, "ctx is busy");
+  GridDev g;
+  int st = make_grid(p, &g);
+  if (st) return st;
+  if (plane > g.res[2]) return fail(S2M_ERR_INVALID_ARG, "plane out of range");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if ((st = c->slab.ensure(g.plane_stride * 4))) return st;
+  float* slab = c->slab.as<float>();
+  unsigned first_plane = plane, n_planes = 1;
+  void* a1[] = {&g, &slab, &first_plane, &n_planes};
+  if ((st = launch(m->k1, dim3((g.pitch_x + 127u) / 128u, (g.rows + 7u) / 8u, 1), dim3(32, 8, 1), c->stream, a1, "s2m_k1_slab"))) return st;
+  CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)(g.res[0] + 1) * 4, slab, (size_t)g.pitch_x * 4, (size_t)(g.res[0] + 1) * 4, g.rows,
+                             cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return S2M_OK;
+}
+
+extern "C" int s2m_cost_probe(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, uint32_t planes, double* cost_out) {
+  if (!c || !m || !p || !cost_out || planes == 0) return fail(S2M_ERR_INVALID_ARG, "bad argument");
+  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  GridDev g;
+  int st = make_grid(p, &g);
+  if (st) return st;
+  CUDA_TRY(cudaSetDevice(c->device));
+  DevBuf buf;
+  if ((st = buf.ensure((size_t)planes * 8 + 64))) return st;
+  cudaStream_t s = c->stream;
+  cudaError_t e = cudaMemsetAsync(buf.p, 0, (size_t)planes * 8 + 64, s);
+  unsigned probe = 64, pl = planes;
+  unsigned long long* cyc = buf.as<unsigned long long>();
+  float* sink = reinterpret_cast<float*>(cyc + planes);
+  void* args[] = {&g, &probe, &pl, &cyc, &sink};
+  if (e == cudaSuccess) st = launch(m->k_probe, dim3(planes), dim3(256), s, args, "s2m_k_cost_probe");
+  std::vector<unsigned long long> h(planes);
+  if (e == cudaSuccess && !st) e = cudaMemcpyAsync(h.data(), cyc, (size_t)planes * 8, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && !st) e = cudaStreamSynchronize(s);
+  buf.release();
+  if (st) return st;
+  if (e != cudaSuccess) return fail(S2M_ERR_CUDA, std::string("s2m_cost_probe: ") + cudaGetErrorString(e));
+  for (uint32_t i = 0; i < planes; ++i) cost_out[i] = (double)h[i];
+  return S2M_OK;
+}

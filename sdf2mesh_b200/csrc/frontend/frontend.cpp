@@ -1,0 +1,39 @@
+// frontend.cpp -- front-end entry points.
+#include "frontend.h"
+
+#include "parse.h"
+
+namespace s2m_frontend {
+
+int lower_to_cuda(const s2m_shader& sh, std::string* cuda, std::string* err) {
+  try {
+    if (sh.kind == S2M_SRC_CUDA) { *cuda = sh.source; return S2M_OK; }
+    Module m;
+    parse_wgsl(sh.source, sh.builtin_functions, &m);
+    *cuda = emit_cuda(m);
+    return S2M_OK;
+  } catch (const FrontendError& e) {
+    *err = e.what();
+    return e.status;
+  } catch (const std::exception& e) {
+    *err = std::string("front-end: ") + e.what();
+    return S2M_ERR_SHADER;
+  }
+}
+
+int glsl_to_wgsl(const std::string& glsl, std::string* wgsl, std::string* err) {
+  try {
+    Module m;
+    parse_glsl(glsl, &m);
+    *wgsl = emit_wgsl(m);
+    return S2M_OK;
+  } catch (const FrontendError& e) {
+    *err = e.what();
+    return e.status;
+  } catch (const std::exception& e) {
+    *err = std::string("front-end: ") + e.what();
+    return S2M_ERR_SHADER;
+  }
+}
+
+}  // namespace s2m_frontend

@@ -1,0 +1,13 @@
+// parse.h -- parser and writer entry points (internal to the front-end).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "ir.h"
+
+namespace s2m_frontend {
+void parse_wgsl(const std::string& src, const std::vector<std::string>& builtin_fns, Module* out);
+void parse_glsl(const std::string& src, Module* out);
+std::string emit_cuda(const Module& m);
+std::string emit_wgsl(const Module& m);
+}  // namespace s2m_frontend

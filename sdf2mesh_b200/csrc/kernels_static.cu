@@ -1,0 +1,309 @@
+// kernels_static.cu -- the SDF-independent kernels, compiled ahead of time for sm_100a.
+//
+// K2  k2_classify   replaces the per-cell sign tests + host pixel scan that decide where the
+//                   surface is (/root/reference/src/bin/sdf2mesh/dualcontour.wgsl:57-69, :119-128;
+//                   /root/reference/src/bin/sdf2mesh/main.rs:327-344) by a conservative CANDIDATE
+//                   test on the once-per-corner slab: a cell is a candidate unless all 8 corners
+//                   are > +tau or all 8 are < -tau.  Exact reference arithmetic is then re-run on
+//                   candidates only (K4a).  Corner classes are formed once per corner, packed with
+//                   __ballot_sync into row bitmasks staged in shared memory, and combined per cell
+//                   with word-wide AND/shift; counts with __popc.
+// K3  k3_compact    single-pass decoupled look-back exclusive scan of the candidate bitmask:
+//                   writes the per-word rank table and the compact candidate list in linear cell
+//                   order == the reference's VertexList order (mesh.rs:224-245).
+// K4b k4_quads      replaces VertexList::fetch_triangle_indices + vertex_index + Quad::swap /
+//                   is_valid (/root/reference/src/mesh.rs:267-331, /root/reference/src/lib.rs:187-211):
+//                   3 edge tests per vertex, neighbour ranks by bitmask rank lookup instead of binary
+//                   search, stable single-pass emission of 64-bit-index quads.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels_static.h"
+#include "s2m_scan.cuh"
+
+namespace {
+
+constexpr int K2_TX_WORDS = 4;   // 128 cells in x per CTA
+constexpr int K2_TY = 16;        // cell rows per CTA
+constexpr int K2_ZT = 16;        // cell slices marched per CTA
+
+__device__ __forceinline__ uint32_t pair_x(const uint32_t* row, int i) {
+  // bit b of the result: corner (32*i + b) AND corner (32*i + b + 1)
+  return row[i] & ((row[i] >> 1) | (row[i + 1] << 31));
+}
+
+__global__ void __launch_bounds__(256)
+k2_classify(const float* __restrict__ slab, uint32_t pitch_x, unsigned long long plane_stride,
+            uint32_t res_x, uint32_t res_y, uint32_t nz_chunk, float tau,
+            uint32_t* __restrict__ cand_mask, uint32_t words_x, unsigned long long* __restrict__ total) {
+  __shared__ uint32_t sP[2][K2_TY + 1][K2_TX_WORDS + 1];
+  __shared__ uint32_t sN[2][K2_TY + 1][K2_TX_WORDS + 1];
+  __shared__ unsigned s_red[8];
+  const uint32_t x0 = blockIdx.x * (32u * K2_TX_WORDS);
+  const uint32_t y0 = blockIdx.y * K2_TY;
+  const uint32_t zt0 = blockIdx.z * K2_ZT;
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  unsigned count = 0;
+
+  for (uint32_t k = 0; k <= (uint32_t)K2_ZT; ++k) {
+    const uint32_t plane = zt0 + k;
+    if (plane > nz_chunk) break;  // uniform across the block
+    const int buf = (int)(k & 1u);
+    const float* pl = slab + (unsigned long long)plane * plane_stride;
+    for (uint32_t row = warp; row <= (uint32_t)K2_TY; row += 8u) {
+      const uint32_t y = y0 + row;
+      const bool yok = y <= res_y;
+      const float* rp = pl + (unsigned long long)y * pitch_x;
+      float v[K2_TX_WORDS];
+#pragma unroll
+      for (int i = 0; i < K2_TX_WORDS; ++i) {
+        const uint32_t x = x0 + 32u * i + lane;
+        v[i] = (yok && x <= res_x) ? __ldg(rp + x) : __int_as_float(0x7fc00000);
+      }
+      const uint32_t xh = x0 + 32u * K2_TX_WORDS;
+      float vh = __int_as_float(0x7fc00000);
+      if (lane == 0 && yok && xh <= res_x) vh = __ldg(rp + xh);
+#pragma unroll
+      for (int i = 0; i < K2_TX_WORDS; ++i) {
+        const uint32_t pw = __ballot_sync(0xffffffffu, v[i] > tau);
+        const uint32_t nw = __ballot_sync(0xffffffffu, v[i] < -tau);
+        if (lane == 0) { sP[buf][row][i] = pw; sN[buf][row][i] = nw; }
+      }
+      if (lane == 0) { sP[buf][row][K2_TX_WORDS] = vh > tau ? 1u : 0u; sN[buf][row][K2_TX_WORDS] = vh < -tau ? 1u : 0u; }
+    }
+    __syncthreads();
+    if (k >= 1) {
+      const uint32_t z = zt0 + k - 1;  // cell slice inside the chunk (z < nz_chunk because plane <= nz_chunk)
+      for (uint32_t idx = threadIdx.x; idx < (uint32_t)(K2_TY * K2_TX_WORDS); idx += blockDim.x) {
+        const uint32_t row = idx / K2_TX_WORDS;
+        const int i = (int)(idx % K2_TX_WORDS);
+        const uint32_t y = y0 + row;
+        const uint32_t xw = x0 / 32u + (uint32_t)i;
+        if (y < res_y && xw < words_x) {
+          const uint32_t allp = pair_x(sP[buf ^ 1][row], i) & pair_x(sP[buf ^ 1][row + 1], i) &
+                                pair_x(sP[buf][row], i) & pair_x(sP[buf][row + 1], i);
+          const uint32_t alln = pair_x(sN[buf ^ 1][row], i) & pair_x(sN[buf ^ 1][row + 1], i) &
+                                pair_x(sN[buf][row], i) & pair_x(sN[buf][row + 1], i);
+          uint32_t cand = ~(allp | alln);
+          const uint32_t xb = xw * 32u;
+          if (xb + 32u > res_x) cand &= (1u << (res_x - xb)) - 1u;  // cells beyond the grid
+          cand_mask[((unsigned long long)z * res_y + y) * words_x + xw] = cand;
+          count += (unsigned)__popc(cand);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+  if (lane == 0) s_red[warp] = count;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    if (t) atomicAdd(total, (unsigned long long)t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K3
+constexpr int K3_THREADS = 256;
+constexpr int K3_WORDS_PER_THREAD = 16;  // 4 x uint4
+constexpr int K3_TILE_WORDS = K3_THREADS * K3_WORDS_PER_THREAD;
+
+__global__ void __launch_bounds__(K3_THREADS)
+k3_compact(const uint32_t* __restrict__ cand_mask, unsigned long long n_words, uint32_t words_x, uint32_t res_y,
+           uint32_t z_offset, uint32_t* __restrict__ word_prefix, unsigned long long* __restrict__ cand_key,
+           unsigned long long* status, unsigned* ticket) {
+  __shared__ unsigned s_scan[33];
+  __shared__ unsigned s_tile;
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned tile = s_tile;
+  const unsigned long long w0 = (unsigned long long)tile * K3_TILE_WORDS + (unsigned long long)threadIdx.x * K3_WORDS_PER_THREAD;
+  uint32_t m[K3_WORDS_PER_THREAD];
+  if (w0 + K3_WORDS_PER_THREAD <= n_words) {
+    const uint4* p = reinterpret_cast<const uint4*>(cand_mask + w0);
+#pragma unroll
+    for (int q = 0; q < K3_WORDS_PER_THREAD / 4; ++q) {
+      const uint4 t = __ldg(p + q);
+      m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < K3_WORDS_PER_THREAD; ++q) m[q] = (w0 + q < n_words) ? cand_mask[w0 + q] : 0u;
+  }
+  unsigned mine = 0;
+#pragma unroll
+  for (int q = 0; q < K3_WORDS_PER_THREAD; ++q) mine += (unsigned)__popc(m[q]);
+  unsigned total = 0;
+  const unsigned local = s2m_block_exclusive_scan(mine, s_scan, &total);
+  if (threadIdx.x < 32) {
+    unsigned long long b = s2m_lookback_warp(status, tile, (unsigned long long)total, 0ull);
+    if (threadIdx.x == 0) s_base = b;
+  }
+  __syncthreads();
+  unsigned long long run = s_base + local;
+  uint32_t pre[K3_WORDS_PER_THREAD];
+#pragma unroll
+  for (int q = 0; q < K3_WORDS_PER_THREAD; ++q) {
+    const unsigned long long w = w0 + q;
+    pre[q] = (uint32_t)run;
+    uint32_t bits = m[q];
+    if (bits && w < n_words) {
+      const unsigned long long rowi = w / words_x;
+      const uint32_t xw = (uint32_t)(w - rowi * words_x);
+      const uint32_t z = (uint32_t)(rowi / res_y);
+      const uint32_t y = (uint32_t)(rowi - (unsigned long long)z * res_y);
+      const unsigned long long hi = ((unsigned long long)y << 16) | ((unsigned long long)(z + z_offset) << 32);
+      while (bits) {
+        const int b = __ffs((int)bits) - 1;
+        bits &= bits - 1u;
+        cand_key[run++] = hi | (unsigned long long)(xw * 32u + (uint32_t)b);
+      }
+    }
+  }
+  if (w0 + K3_WORDS_PER_THREAD <= n_words) {
+    uint4* o = reinterpret_cast<uint4*>(word_prefix + w0);
+#pragma unroll
+    for (int q = 0; q < K3_WORDS_PER_THREAD / 4; ++q) o[q] = make_uint4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < K3_WORDS_PER_THREAD; ++q) if (w0 + q < n_words) word_prefix[w0 + q] = pre[q];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K4b
+struct QuadParams {
+  const unsigned long long* vert_key;   // label keys
+  const unsigned char* vert_nibble;
+  unsigned long long n_vertices;        // including halo vertices
+  unsigned long long n_halo;            // leading vertices that belong to the previous slab
+  const uint32_t* cand_mask;
+  const uint32_t* word_prefix;
+  const uint32_t* cand_vrank;
+  uint32_t words_x, res_y;
+  uint32_t z_first;       // true z of the first slice present in cand_mask
+  uint32_t label_add;     // label = true z + label_add
+  long long index_offset; // global index = local vertex index + index_offset
+  unsigned long long* quads;  // 4 per quad
+  unsigned long long* status;
+  unsigned* ticket;
+  unsigned long long* n_quads;
+  unsigned long long* n_invalid;
+};
+
+constexpr uint32_t MISSING32 = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t rank_of(const QuadParams& p, int x, int y, int z_true) {
+  // vertex index (local) of cell (x, y, z_true) or MISSING32.  z_true may be z_first-1 -> missing.
+  if (x < 0 || y < 0 || z_true < (int)p.z_first) return MISSING32;
+  const unsigned long long w = ((unsigned long long)(z_true - (int)p.z_first) * p.res_y + (unsigned)y) * p.words_x + ((unsigned)x >> 5);
+  const uint32_t m = __ldg(p.cand_mask + w);
+  const uint32_t bit = 1u << (x & 31);
+  if (!(m & bit)) return MISSING32;
+  const uint32_t c = __ldg(p.word_prefix + w) + (uint32_t)__popc(m & (bit - 1u));
+  return __ldg(p.cand_vrank + c);
+}
+
+__global__ void __launch_bounds__(256)
+k4_quads(QuadParams p) {
+  __shared__ unsigned s_scan[33];
+  __shared__ unsigned s_tile;
+  __shared__ unsigned long long s_base;
+  __shared__ unsigned s_inv[8];
+  if (threadIdx.x == 0) s_tile = atomicAdd(p.ticket, 1u);
+  __syncthreads();
+  const unsigned tile = s_tile;
+  const unsigned long long n_own = p.n_vertices - p.n_halo;
+  const unsigned long long i = (unsigned long long)tile * blockDim.x + threadIdx.x;  // own vertex ordinal
+  uint32_t q[3][4];
+  unsigned nvalid = 0, ninvalid = 0;
+  if (i < n_own) {
+    const unsigned long long vi = i + p.n_halo;
+    const unsigned long long key = p.vert_key[vi];
+    const int x = (int)(key & 0xffffu), y = (int)((key >> 16) & 0xffffu);
+    const uint32_t label = (uint32_t)(key >> 32);
+    const int z = (int)(label - p.label_add);  // true z
+    const unsigned nib = p.vert_nibble[vi];
+    const bool s100 = nib & 1u, s010 = nib & 2u, s001 = nib & 4u, s000 = nib & 8u;
+    const uint32_t self = (uint32_t)vi;
+    // mesh.rs:286-296  X-edge quad.  The z guard is on the LABEL; a slice below the
+    // first scanned one does not exist in the list -> MISSING -> invalid quad, as in the reference.
+    auto emit = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool swap) {
+      if (a == MISSING32 || b == MISSING32 || c == MISSING32 || d == MISSING32) { ++ninvalid; return; }
+      uint32_t* o = q[nvalid++];
+      if (swap) { o[0] = d; o[1] = c; o[2] = b; o[3] = a; } else { o[0] = a; o[1] = b; o[2] = c; o[3] = d; }
+    };
+    const bool have_below = (z - 1) >= 0;  // a true slice z-1 exists in the grid
+    if (s100 != s000 && y > 0 && label > 0)
+      emit(have_below ? rank_of(p, x, y - 1, z - 1) : MISSING32, have_below ? rank_of(p, x, y, z - 1) : MISSING32,
+           self, rank_of(p, x, y - 1, z), s100);
+    if (s010 != s000 && x > 0 && label > 0)
+      emit(have_below ? rank_of(p, x - 1, y, z - 1) : MISSING32, have_below ? rank_of(p, x, y, z - 1) : MISSING32,
+           self, rank_of(p, x - 1, y, z), !s010);
+    if (s001 != s000 && x > 0 && y > 0)
+      emit(rank_of(p, x - 1, y - 1, z), rank_of(p, x, y - 1, z), self, rank_of(p, x - 1, y, z), s001);
+  }
+  unsigned total = 0;
+  const unsigned local = s2m_block_exclusive_scan(nvalid, s_scan, &total);
+  if (threadIdx.x < 32) {
+    unsigned long long b = s2m_lookback_warp(p.status, tile, (unsigned long long)total, 0ull);
+    if (threadIdx.x == 0) s_base = b;
+  }
+  unsigned inv = ninvalid;
+  for (int o = 16; o > 0; o >>= 1) inv += __shfl_xor_sync(0xffffffffu, inv, o);
+  if ((threadIdx.x & 31u) == 0) s_inv[threadIdx.x >> 5] = inv;
+  __syncthreads();
+  unsigned long long at = s_base + local;
+  for (unsigned k = 0; k < nvalid; ++k, ++at) {
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(p.quads + 4ull * at);
+    dst[0] = make_ulonglong2((unsigned long long)((long long)q[k][0] + p.index_offset), (unsigned long long)((long long)q[k][1] + p.index_offset));
+    dst[1] = make_ulonglong2((unsigned long long)((long long)q[k][2] + p.index_offset), (unsigned long long)((long long)q[k][3] + p.index_offset));
+  }
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < 8; ++w) t += s_inv[w];
+    if (t) atomicAdd(p.n_invalid, (unsigned long long)t);
+    if ((unsigned long long)(tile + 1) * blockDim.x >= n_own) *p.n_quads = s_base + total;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ launchers
+extern "C" int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream) {
+  dim3 grid((a->res_x + 32 * K2_TX_WORDS - 1) / (32 * K2_TX_WORDS), (a->res_y + K2_TY - 1) / K2_TY,
+            (a->nz_chunk + K2_ZT - 1) / K2_ZT);
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
+  k2_classify<<<grid, 256, 0, stream>>>(a->slab, a->pitch_x, a->plane_stride, a->res_x, a->res_y, a->nz_chunk, a->tau,
+                                        a->cand_mask, a->words_x, a->total);
+  return (int)cudaGetLastError();
+}
+
+extern "C" unsigned s2m_k3_tiles(unsigned long long n_words) {
+  return (unsigned)((n_words + K3_TILE_WORDS - 1) / K3_TILE_WORDS);
+}
+
+extern "C" int s2m_launch_k3(const S2mK3Args* a, cudaStream_t stream) {
+  const unsigned tiles = s2m_k3_tiles(a->n_words);
+  if (!tiles) return 0;
+  k3_compact<<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->n_words, a->words_x, a->res_y, a->z_offset,
+                                               a->word_prefix, a->cand_key, a->status, a->ticket);
+  return (int)cudaGetLastError();
+}
+
+extern "C" unsigned s2m_k4b_tiles(unsigned long long n_own) { return (unsigned)((n_own + 255) / 256); }
+
+extern "C" int s2m_launch_k4b(const S2mK4bArgs* a, cudaStream_t stream) {
+  const unsigned long long n_own = a->n_vertices - a->n_halo;
+  const unsigned tiles = s2m_k4b_tiles(n_own);
+  if (!tiles) return 0;
+  QuadParams p;
+  p.vert_key = a->vert_key; p.vert_nibble = a->vert_nibble; p.n_vertices = a->n_vertices; p.n_halo = a->n_halo;
+  p.cand_mask = a->cand_mask; p.word_prefix = a->word_prefix; p.cand_vrank = a->cand_vrank;
+  p.words_x = a->words_x; p.res_y = a->res_y; p.z_first = a->z_first; p.label_add = a->label_add;
+  p.index_offset = a->index_offset; p.quads = a->quads; p.status = a->status; p.ticket = a->ticket;
+  p.n_quads = a->n_quads; p.n_invalid = a->n_invalid;
+  k4_quads<<<tiles, 256, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}

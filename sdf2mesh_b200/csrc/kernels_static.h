@@ -1,0 +1,59 @@
+/* kernels_static.h -- host-callable launchers of the ahead-of-time compiled kernels. */
+#ifndef S2M_KERNELS_STATIC_H_
+#define S2M_KERNELS_STATIC_H_
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct S2mK2Args {
+  const float* slab;              /* chunk plane 0 */
+  uint32_t pitch_x;
+  unsigned long long plane_stride;
+  uint32_t res_x, res_y;          /* cells */
+  uint32_t nz_chunk;              /* cell slices in this chunk; planes 0..nz_chunk are present */
+  float tau;
+  uint32_t* cand_mask;            /* first word of the chunk's first slice */
+  uint32_t words_x;
+  unsigned long long* total;      /* candidate counter (accumulates) */
+} S2mK2Args;
+
+typedef struct S2mK3Args {
+  const uint32_t* cand_mask;
+  unsigned long long n_words;
+  uint32_t words_x, res_y;
+  uint32_t z_offset;              /* true z of slice 0 of the mask */
+  uint32_t* word_prefix;
+  unsigned long long* cand_key;
+  unsigned long long* status;     /* >= s2m_k3_tiles(n_words) zeroed words */
+  unsigned* ticket;               /* zeroed */
+} S2mK3Args;
+
+typedef struct S2mK4bArgs {
+  const unsigned long long* vert_key;
+  const unsigned char* vert_nibble;
+  unsigned long long n_vertices, n_halo;
+  const uint32_t* cand_mask;
+  const uint32_t* word_prefix;
+  const uint32_t* cand_vrank;
+  uint32_t words_x, res_y, z_first, label_add;
+  long long index_offset;
+  unsigned long long* quads;
+  unsigned long long* status;     /* >= s2m_k4b_tiles(n_own) zeroed words */
+  unsigned* ticket;               /* zeroed */
+  unsigned long long* n_quads;
+  unsigned long long* n_invalid;  /* accumulates */
+} S2mK4bArgs;
+
+int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream);
+unsigned s2m_k3_tiles(unsigned long long n_words);
+int s2m_launch_k3(const S2mK3Args* a, cudaStream_t stream);
+unsigned s2m_k4b_tiles(unsigned long long n_own);
+int s2m_launch_k4b(const S2mK4bArgs* a, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

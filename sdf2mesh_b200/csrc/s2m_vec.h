@@ -1,0 +1,255 @@
+/* s2m_vec.h -- vector types and component-wise builtins for SDF code lowered from WGSL / GLSL.
+ *
+ * The emitter (frontend/emit_cuda.cpp) lowers naga-shaped IR to C++ that uses these types; the
+ * same text compiles under NVRTC (device, --fmad=false) and g++ (tests, -ffp-contract=off), so
+ * every expression is evaluated op-by-op in IEEE f32 in the order the shader wrote it.
+ *
+ * Pinned semantics for what WGSL/GLSL leave to the driver:
+ *   dot = products summed left to right; length = sqrt(dot(v,v)); normalize = v / length(v);
+ *   distance(a,b) = length(a-b); cross per the usual formula (a.y*b.z - a.z*b.y, ...);
+ *   reflect(i,n) = i - 2*dot(n,i)*n.
+ */
+#ifndef S2M_VEC_H_
+#define S2M_VEC_H_
+#include "s2m_math.h"
+
+namespace s2m {
+
+struct vec2 { float x, y; };
+struct vec3 { float x, y, z; };
+struct vec4 { float x, y, z, w; };
+struct ivec2 { int x, y; };
+struct ivec3 { int x, y, z; };
+struct ivec4 { int x, y, z, w; };
+struct bvec2 { bool x, y; };
+struct bvec3 { bool x, y, z; };
+struct bvec4 { bool x, y, z, w; };
+
+S2M_HD vec2 mk2(float x, float y) { vec2 v; v.x = x; v.y = y; return v; }
+S2M_HD vec3 mk3(float x, float y, float z) { vec3 v; v.x = x; v.y = y; v.z = z; return v; }
+S2M_HD vec4 mk4(float x, float y, float z, float w) { vec4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+S2M_HD ivec2 mki2(int x, int y) { ivec2 v; v.x = x; v.y = y; return v; }
+S2M_HD ivec3 mki3(int x, int y, int z) { ivec3 v; v.x = x; v.y = y; v.z = z; return v; }
+S2M_HD ivec4 mki4(int x, int y, int z, int w) { ivec4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+S2M_HD bvec2 mkb2(bool x, bool y) { bvec2 v; v.x = x; v.y = y; return v; }
+S2M_HD bvec3 mkb3(bool x, bool y, bool z) { bvec3 v; v.x = x; v.y = y; v.z = z; return v; }
+S2M_HD bvec4 mkb4(bool x, bool y, bool z, bool w) { bvec4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+
+
+/* mixed-argument constructors: vec3(v2, s), vec4(v3, s), vec4(v2, v2), ... and splats */
+S2M_HD vec3 mk3(const vec2& a, float b) { return mk3(a.x, a.y, b); }
+S2M_HD vec3 mk3(float a, const vec2& b) { return mk3(a, b.x, b.y); }
+S2M_HD vec4 mk4(const vec3& a, float b) { return mk4(a.x, a.y, a.z, b); }
+S2M_HD vec4 mk4(float a, const vec3& b) { return mk4(a, b.x, b.y, b.z); }
+S2M_HD vec4 mk4(const vec2& a, const vec2& b) { return mk4(a.x, a.y, b.x, b.y); }
+S2M_HD vec4 mk4(const vec2& a, float b, float c) { return mk4(a.x, a.y, b, c); }
+S2M_HD vec4 mk4(float a, const vec2& b, float c) { return mk4(a, b.x, b.y, c); }
+S2M_HD vec4 mk4(float a, float b, const vec2& c) { return mk4(a, b, c.x, c.y); }
+S2M_HD ivec3 mki3(const ivec2& a, int b) { return mki3(a.x, a.y, b); }
+S2M_HD ivec3 mki3(int a, const ivec2& b) { return mki3(a, b.x, b.y); }
+S2M_HD ivec4 mki4(const ivec3& a, int b) { return mki4(a.x, a.y, a.z, b); }
+S2M_HD ivec4 mki4(const ivec2& a, const ivec2& b) { return mki4(a.x, a.y, b.x, b.y); }
+S2M_HD vec2 splat2(float a) { return mk2(a, a); }
+S2M_HD vec3 splat3(float a) { return mk3(a, a, a); }
+S2M_HD vec4 splat4(float a) { return mk4(a, a, a, a); }
+S2M_HD ivec2 splati2(int a) { return mki2(a, a); }
+S2M_HD ivec3 splati3(int a) { return mki3(a, a, a); }
+S2M_HD ivec4 splati4(int a) { return mki4(a, a, a, a); }
+S2M_HD bvec2 splatb2(bool a) { return mkb2(a, a); }
+S2M_HD bvec3 splatb3(bool a) { return mkb3(a, a, a); }
+S2M_HD bvec4 splatb4(bool a) { return mkb4(a, a, a, a); }
+
+/* component access by index (swizzles are lowered to these) */
+S2M_HD float cget(const vec2& v, int i) { return i == 0 ? v.x : v.y; }
+S2M_HD float cget(const vec3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+S2M_HD float cget(const vec4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+S2M_HD int cget(const ivec2& v, int i) { return i == 0 ? v.x : v.y; }
+S2M_HD int cget(const ivec3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+S2M_HD int cget(const ivec4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+S2M_HD bool cget(const bvec2& v, int i) { return i == 0 ? v.x : v.y; }
+S2M_HD bool cget(const bvec3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+S2M_HD bool cget(const bvec4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+S2M_HD void cset(vec2& v, int i, float f) { if (i == 0) v.x = f; else v.y = f; }
+S2M_HD void cset(vec3& v, int i, float f) { if (i == 0) v.x = f; else if (i == 1) v.y = f; else v.z = f; }
+S2M_HD void cset(vec4& v, int i, float f) { if (i == 0) v.x = f; else if (i == 1) v.y = f; else if (i == 2) v.z = f; else v.w = f; }
+S2M_HD void cset(ivec2& v, int i, int f) { if (i == 0) v.x = f; else v.y = f; }
+S2M_HD void cset(ivec3& v, int i, int f) { if (i == 0) v.x = f; else if (i == 1) v.y = f; else v.z = f; }
+S2M_HD void cset(ivec4& v, int i, int f) { if (i == 0) v.x = f; else if (i == 1) v.y = f; else if (i == 2) v.z = f; else v.w = f; }
+
+
+/* multi-component swizzle reads: swz3(v, 0, 2, 1) == v.xzy */
+S2M_HD vec2 swz2(const vec2& v, int a, int b) { return mk2(cget(v, a), cget(v, b)); }
+S2M_HD vec2 swz2(const vec3& v, int a, int b) { return mk2(cget(v, a), cget(v, b)); }
+S2M_HD vec2 swz2(const vec4& v, int a, int b) { return mk2(cget(v, a), cget(v, b)); }
+S2M_HD vec3 swz3(const vec2& v, int a, int b, int c) { return mk3(cget(v, a), cget(v, b), cget(v, c)); }
+S2M_HD vec3 swz3(const vec3& v, int a, int b, int c) { return mk3(cget(v, a), cget(v, b), cget(v, c)); }
+S2M_HD vec3 swz3(const vec4& v, int a, int b, int c) { return mk3(cget(v, a), cget(v, b), cget(v, c)); }
+S2M_HD vec4 swz4(const vec2& v, int a, int b, int c, int d) { return mk4(cget(v, a), cget(v, b), cget(v, c), cget(v, d)); }
+S2M_HD vec4 swz4(const vec3& v, int a, int b, int c, int d) { return mk4(cget(v, a), cget(v, b), cget(v, c), cget(v, d)); }
+S2M_HD vec4 swz4(const vec4& v, int a, int b, int c, int d) { return mk4(cget(v, a), cget(v, b), cget(v, c), cget(v, d)); }
+S2M_HD ivec2 swz2(const ivec2& v, int a, int b) { return mki2(cget(v, a), cget(v, b)); }
+S2M_HD ivec2 swz2(const ivec3& v, int a, int b) { return mki2(cget(v, a), cget(v, b)); }
+S2M_HD ivec2 swz2(const ivec4& v, int a, int b) { return mki2(cget(v, a), cget(v, b)); }
+S2M_HD ivec3 swz3(const ivec3& v, int a, int b, int c) { return mki3(cget(v, a), cget(v, b), cget(v, c)); }
+S2M_HD ivec3 swz3(const ivec4& v, int a, int b, int c) { return mki3(cget(v, a), cget(v, b), cget(v, c)); }
+
+/* ---- arithmetic: vec op vec, vec op scalar, scalar op vec, unary minus */
+#define S2M_VEC_BINOP(OP)                                                                             \
+  S2M_HD vec2 operator OP(const vec2& a, const vec2& b) { return mk2(a.x OP b.x, a.y OP b.y); }       \
+  S2M_HD vec3 operator OP(const vec3& a, const vec3& b) { return mk3(a.x OP b.x, a.y OP b.y, a.z OP b.z); } \
+  S2M_HD vec4 operator OP(const vec4& a, const vec4& b) { return mk4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); } \
+  S2M_HD vec2 operator OP(const vec2& a, float b) { return mk2(a.x OP b, a.y OP b); }                 \
+  S2M_HD vec3 operator OP(const vec3& a, float b) { return mk3(a.x OP b, a.y OP b, a.z OP b); }       \
+  S2M_HD vec4 operator OP(const vec4& a, float b) { return mk4(a.x OP b, a.y OP b, a.z OP b, a.w OP b); } \
+  S2M_HD vec2 operator OP(float a, const vec2& b) { return mk2(a OP b.x, a OP b.y); }                 \
+  S2M_HD vec3 operator OP(float a, const vec3& b) { return mk3(a OP b.x, a OP b.y, a OP b.z); }       \
+  S2M_HD vec4 operator OP(float a, const vec4& b) { return mk4(a OP b.x, a OP b.y, a OP b.z, a OP b.w); }
+S2M_VEC_BINOP(+)
+S2M_VEC_BINOP(-)
+S2M_VEC_BINOP(*)
+S2M_VEC_BINOP(/)
+#undef S2M_VEC_BINOP
+S2M_HD vec2 operator-(const vec2& a) { return mk2(-a.x, -a.y); }
+S2M_HD vec3 operator-(const vec3& a) { return mk3(-a.x, -a.y, -a.z); }
+S2M_HD vec4 operator-(const vec4& a) { return mk4(-a.x, -a.y, -a.z, -a.w); }
+
+#define S2M_IVEC_BINOP(OP)                                                                            \
+  S2M_HD ivec2 operator OP(const ivec2& a, const ivec2& b) { return mki2(a.x OP b.x, a.y OP b.y); }   \
+  S2M_HD ivec3 operator OP(const ivec3& a, const ivec3& b) { return mki3(a.x OP b.x, a.y OP b.y, a.z OP b.z); } \
+  S2M_HD ivec4 operator OP(const ivec4& a, const ivec4& b) { return mki4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); } \
+  S2M_HD ivec2 operator OP(const ivec2& a, int b) { return mki2(a.x OP b, a.y OP b); }                \
+  S2M_HD ivec3 operator OP(const ivec3& a, int b) { return mki3(a.x OP b, a.y OP b, a.z OP b); }      \
+  S2M_HD ivec4 operator OP(const ivec4& a, int b) { return mki4(a.x OP b, a.y OP b, a.z OP b, a.w OP b); }
+S2M_IVEC_BINOP(+)
+S2M_IVEC_BINOP(-)
+S2M_IVEC_BINOP(*)
+#undef S2M_IVEC_BINOP
+
+/* ---- conversions */
+S2M_HD vec2 to_f(const ivec2& v) { return mk2((float)v.x, (float)v.y); }
+S2M_HD vec3 to_f(const ivec3& v) { return mk3((float)v.x, (float)v.y, (float)v.z); }
+S2M_HD vec4 to_f(const ivec4& v) { return mk4((float)v.x, (float)v.y, (float)v.z, (float)v.w); }
+S2M_HD ivec2 to_i(const vec2& v) { return mki2(s2m_f2int(v.x), s2m_f2int(v.y)); }
+S2M_HD ivec3 to_i(const vec3& v) { return mki3(s2m_f2int(v.x), s2m_f2int(v.y), s2m_f2int(v.z)); }
+S2M_HD ivec4 to_i(const vec4& v) { return mki4(s2m_f2int(v.x), s2m_f2int(v.y), s2m_f2int(v.z), s2m_f2int(v.w)); }
+
+/* ---- component-wise maps of the scalar builtins in s2m_math.h */
+#define S2M_MAP1(NAME, FN)                                                              \
+  S2M_HD float NAME(float a) { return FN(a); }                                          \
+  S2M_HD vec2 NAME(const vec2& a) { return mk2(FN(a.x), FN(a.y)); }                     \
+  S2M_HD vec3 NAME(const vec3& a) { return mk3(FN(a.x), FN(a.y), FN(a.z)); }            \
+  S2M_HD vec4 NAME(const vec4& a) { return mk4(FN(a.x), FN(a.y), FN(a.z), FN(a.w)); }
+S2M_MAP1(f_abs, s2m_abs)       S2M_MAP1(f_sign, s2m_sign)     S2M_MAP1(f_floor, s2m_floor)
+S2M_MAP1(f_ceil, s2m_ceil)     S2M_MAP1(f_trunc, s2m_trunc)   S2M_MAP1(f_round, s2m_round)
+S2M_MAP1(f_fract, s2m_fract)   S2M_MAP1(f_sqrt, s2m_sqrt)     S2M_MAP1(f_inversesqrt, s2m_inversesqrt)
+S2M_MAP1(f_sin, s2m_sin)       S2M_MAP1(f_cos, s2m_cos)       S2M_MAP1(f_tan, s2m_tan)
+S2M_MAP1(f_asin, s2m_asin)     S2M_MAP1(f_acos, s2m_acos)     S2M_MAP1(f_atan, s2m_atan)
+S2M_MAP1(f_sinh, s2m_sinh)     S2M_MAP1(f_cosh, s2m_cosh)     S2M_MAP1(f_tanh, s2m_tanh)
+S2M_MAP1(f_exp, s2m_exp)       S2M_MAP1(f_exp2, s2m_exp2)     S2M_MAP1(f_log, s2m_log)
+S2M_MAP1(f_log2, s2m_log2)     S2M_MAP1(f_radians, s2m_radians) S2M_MAP1(f_degrees, s2m_degrees)
+#undef S2M_MAP1
+S2M_HD float s2m__saturate(float a) { return s2m_clamp(a, 0.0f, 1.0f); }
+S2M_HD float f_saturate(float a) { return s2m__saturate(a); }
+S2M_HD vec2 f_saturate(const vec2& a) { return mk2(s2m__saturate(a.x), s2m__saturate(a.y)); }
+S2M_HD vec3 f_saturate(const vec3& a) { return mk3(s2m__saturate(a.x), s2m__saturate(a.y), s2m__saturate(a.z)); }
+S2M_HD vec4 f_saturate(const vec4& a) { return mk4(s2m__saturate(a.x), s2m__saturate(a.y), s2m__saturate(a.z), s2m__saturate(a.w)); }
+
+/* two-operand maps; the scalar-broadcast forms are GLSL's (min(vec,float), pow is vec/vec only) */
+#define S2M_MAP2(NAME, FN)                                                                              \
+  S2M_HD float NAME(float a, float b) { return FN(a, b); }                                              \
+  S2M_HD vec2 NAME(const vec2& a, const vec2& b) { return mk2(FN(a.x, b.x), FN(a.y, b.y)); }            \
+  S2M_HD vec3 NAME(const vec3& a, const vec3& b) { return mk3(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z)); } \
+  S2M_HD vec4 NAME(const vec4& a, const vec4& b) { return mk4(FN(a.x, b.x), FN(a.y, b.y), FN(a.z, b.z), FN(a.w, b.w)); } \
+  S2M_HD vec2 NAME(const vec2& a, float b) { return mk2(FN(a.x, b), FN(a.y, b)); }                      \
+  S2M_HD vec3 NAME(const vec3& a, float b) { return mk3(FN(a.x, b), FN(a.y, b), FN(a.z, b)); }          \
+  S2M_HD vec4 NAME(const vec4& a, float b) { return mk4(FN(a.x, b), FN(a.y, b), FN(a.z, b), FN(a.w, b)); } \
+  S2M_HD vec2 NAME(float a, const vec2& b) { return mk2(FN(a, b.x), FN(a, b.y)); }                      \
+  S2M_HD vec3 NAME(float a, const vec3& b) { return mk3(FN(a, b.x), FN(a, b.y), FN(a, b.z)); }          \
+  S2M_HD vec4 NAME(float a, const vec4& b) { return mk4(FN(a, b.x), FN(a, b.y), FN(a, b.z), FN(a, b.w)); }
+S2M_MAP2(f_min, s2m_min)   S2M_MAP2(f_max, s2m_max)   S2M_MAP2(f_pow, s2m_pow)   S2M_MAP2(f_atan2, s2m_atan2)
+S2M_MAP2(f_step, s2m_step) S2M_MAP2(f_mod, s2m_mod_floor) S2M_MAP2(f_rem, s2m_fmod_trunc)
+#undef S2M_MAP2
+
+S2M_HD int i_min(int a, int b) { return a < b ? a : b; }
+S2M_HD int i_max(int a, int b) { return a > b ? a : b; }
+S2M_HD int i_abs(int a) { return a < 0 ? -a : a; }
+S2M_HD int i_clamp(int x, int lo, int hi) { return i_min(i_max(x, lo), hi); }
+
+S2M_HD float f_clamp(float x, float lo, float hi) { return s2m_clamp(x, lo, hi); }
+S2M_HD vec2 f_clamp(const vec2& x, const vec2& lo, const vec2& hi) { return mk2(s2m_clamp(x.x, lo.x, hi.x), s2m_clamp(x.y, lo.y, hi.y)); }
+S2M_HD vec3 f_clamp(const vec3& x, const vec3& lo, const vec3& hi) { return mk3(s2m_clamp(x.x, lo.x, hi.x), s2m_clamp(x.y, lo.y, hi.y), s2m_clamp(x.z, lo.z, hi.z)); }
+S2M_HD vec4 f_clamp(const vec4& x, const vec4& lo, const vec4& hi) { return mk4(s2m_clamp(x.x, lo.x, hi.x), s2m_clamp(x.y, lo.y, hi.y), s2m_clamp(x.z, lo.z, hi.z), s2m_clamp(x.w, lo.w, hi.w)); }
+S2M_HD vec2 f_clamp(const vec2& x, float lo, float hi) { return mk2(s2m_clamp(x.x, lo, hi), s2m_clamp(x.y, lo, hi)); }
+S2M_HD vec3 f_clamp(const vec3& x, float lo, float hi) { return mk3(s2m_clamp(x.x, lo, hi), s2m_clamp(x.y, lo, hi), s2m_clamp(x.z, lo, hi)); }
+S2M_HD vec4 f_clamp(const vec4& x, float lo, float hi) { return mk4(s2m_clamp(x.x, lo, hi), s2m_clamp(x.y, lo, hi), s2m_clamp(x.z, lo, hi), s2m_clamp(x.w, lo, hi)); }
+
+S2M_HD float f_mix(float a, float b, float t) { return s2m_mix(a, b, t); }
+S2M_HD vec2 f_mix(const vec2& a, const vec2& b, const vec2& t) { return mk2(s2m_mix(a.x, b.x, t.x), s2m_mix(a.y, b.y, t.y)); }
+S2M_HD vec3 f_mix(const vec3& a, const vec3& b, const vec3& t) { return mk3(s2m_mix(a.x, b.x, t.x), s2m_mix(a.y, b.y, t.y), s2m_mix(a.z, b.z, t.z)); }
+S2M_HD vec4 f_mix(const vec4& a, const vec4& b, const vec4& t) { return mk4(s2m_mix(a.x, b.x, t.x), s2m_mix(a.y, b.y, t.y), s2m_mix(a.z, b.z, t.z), s2m_mix(a.w, b.w, t.w)); }
+S2M_HD vec2 f_mix(const vec2& a, const vec2& b, float t) { return mk2(s2m_mix(a.x, b.x, t), s2m_mix(a.y, b.y, t)); }
+S2M_HD vec3 f_mix(const vec3& a, const vec3& b, float t) { return mk3(s2m_mix(a.x, b.x, t), s2m_mix(a.y, b.y, t), s2m_mix(a.z, b.z, t)); }
+S2M_HD vec4 f_mix(const vec4& a, const vec4& b, float t) { return mk4(s2m_mix(a.x, b.x, t), s2m_mix(a.y, b.y, t), s2m_mix(a.z, b.z, t), s2m_mix(a.w, b.w, t)); }
+
+S2M_HD float f_smoothstep(float lo, float hi, float x) { return s2m_smoothstep(lo, hi, x); }
+S2M_HD vec2 f_smoothstep(const vec2& lo, const vec2& hi, const vec2& x) { return mk2(s2m_smoothstep(lo.x, hi.x, x.x), s2m_smoothstep(lo.y, hi.y, x.y)); }
+S2M_HD vec3 f_smoothstep(const vec3& lo, const vec3& hi, const vec3& x) { return mk3(s2m_smoothstep(lo.x, hi.x, x.x), s2m_smoothstep(lo.y, hi.y, x.y), s2m_smoothstep(lo.z, hi.z, x.z)); }
+S2M_HD vec4 f_smoothstep(const vec4& lo, const vec4& hi, const vec4& x) { return mk4(s2m_smoothstep(lo.x, hi.x, x.x), s2m_smoothstep(lo.y, hi.y, x.y), s2m_smoothstep(lo.z, hi.z, x.z), s2m_smoothstep(lo.w, hi.w, x.w)); }
+S2M_HD vec2 f_smoothstep(float lo, float hi, const vec2& x) { return mk2(s2m_smoothstep(lo, hi, x.x), s2m_smoothstep(lo, hi, x.y)); }
+S2M_HD vec3 f_smoothstep(float lo, float hi, const vec3& x) { return mk3(s2m_smoothstep(lo, hi, x.x), s2m_smoothstep(lo, hi, x.y), s2m_smoothstep(lo, hi, x.z)); }
+S2M_HD vec4 f_smoothstep(float lo, float hi, const vec4& x) { return mk4(s2m_smoothstep(lo, hi, x.x), s2m_smoothstep(lo, hi, x.y), s2m_smoothstep(lo, hi, x.z), s2m_smoothstep(lo, hi, x.w)); }
+
+S2M_HD float f_fma(float a, float b, float c) { return s2m_fma(a, b, c); }
+S2M_HD vec2 f_fma(const vec2& a, const vec2& b, const vec2& c) { return mk2(s2m_fma(a.x, b.x, c.x), s2m_fma(a.y, b.y, c.y)); }
+S2M_HD vec3 f_fma(const vec3& a, const vec3& b, const vec3& c) { return mk3(s2m_fma(a.x, b.x, c.x), s2m_fma(a.y, b.y, c.y), s2m_fma(a.z, b.z, c.z)); }
+S2M_HD vec4 f_fma(const vec4& a, const vec4& b, const vec4& c) { return mk4(s2m_fma(a.x, b.x, c.x), s2m_fma(a.y, b.y, c.y), s2m_fma(a.z, b.z, c.z), s2m_fma(a.w, b.w, c.w)); }
+
+/* ---- geometric */
+S2M_HD float f_dot(float a, float b) { return a * b; }
+S2M_HD float f_dot(const vec2& a, const vec2& b) { return a.x * b.x + a.y * b.y; }
+S2M_HD float f_dot(const vec3& a, const vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+S2M_HD float f_dot(const vec4& a, const vec4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+S2M_HD float f_length(float a) { return s2m_abs(a); }
+S2M_HD float f_length(const vec2& a) { return s2m_sqrt(f_dot(a, a)); }
+S2M_HD float f_length(const vec3& a) { return s2m_sqrt(f_dot(a, a)); }
+S2M_HD float f_length(const vec4& a) { return s2m_sqrt(f_dot(a, a)); }
+S2M_HD float f_distance(float a, float b) { return s2m_abs(a - b); }
+S2M_HD float f_distance(const vec2& a, const vec2& b) { return f_length(a - b); }
+S2M_HD float f_distance(const vec3& a, const vec3& b) { return f_length(a - b); }
+S2M_HD float f_distance(const vec4& a, const vec4& b) { return f_length(a - b); }
+S2M_HD vec2 f_normalize(const vec2& a) { return a / f_length(a); }
+S2M_HD vec3 f_normalize(const vec3& a) { return a / f_length(a); }
+S2M_HD vec4 f_normalize(const vec4& a) { return a / f_length(a); }
+S2M_HD vec3 f_cross(const vec3& a, const vec3& b) {
+  return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+S2M_HD vec2 f_reflect(const vec2& i, const vec2& n) { return i - (2.0f * f_dot(n, i)) * n; }
+S2M_HD vec3 f_reflect(const vec3& i, const vec3& n) { return i - (2.0f * f_dot(n, i)) * n; }
+
+/* ---- comparisons / selection */
+#define S2M_CMP(NAME, OP)                                                                                \
+  S2M_HD bvec2 NAME(const vec2& a, const vec2& b) { return mkb2(a.x OP b.x, a.y OP b.y); }               \
+  S2M_HD bvec3 NAME(const vec3& a, const vec3& b) { return mkb3(a.x OP b.x, a.y OP b.y, a.z OP b.z); }   \
+  S2M_HD bvec4 NAME(const vec4& a, const vec4& b) { return mkb4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); }
+S2M_CMP(v_lt, <) S2M_CMP(v_le, <=) S2M_CMP(v_gt, >) S2M_CMP(v_ge, >=) S2M_CMP(v_eq, ==) S2M_CMP(v_ne, !=)
+#undef S2M_CMP
+S2M_HD bool b_all(bool a) { return a; }
+S2M_HD bool b_all(const bvec2& a) { return a.x && a.y; }
+S2M_HD bool b_all(const bvec3& a) { return a.x && a.y && a.z; }
+S2M_HD bool b_all(const bvec4& a) { return a.x && a.y && a.z && a.w; }
+S2M_HD bool b_any(bool a) { return a; }
+S2M_HD bool b_any(const bvec2& a) { return a.x || a.y; }
+S2M_HD bool b_any(const bvec3& a) { return a.x || a.y || a.z; }
+S2M_HD bool b_any(const bvec4& a) { return a.x || a.y || a.z || a.w; }
+/* WGSL select(f, t, cond) */
+S2M_HD float f_select(float f, float t, bool c) { return c ? t : f; }
+S2M_HD int f_select(int f, int t, bool c) { return c ? t : f; }
+S2M_HD vec2 f_select(const vec2& f, const vec2& t, bool c) { return c ? t : f; }
+S2M_HD vec3 f_select(const vec3& f, const vec3& t, bool c) { return c ? t : f; }
+S2M_HD vec4 f_select(const vec4& f, const vec4& t, bool c) { return c ? t : f; }
+S2M_HD vec2 f_select(const vec2& f, const vec2& t, const bvec2& c) { return mk2(c.x ? t.x : f.x, c.y ? t.y : f.y); }
+S2M_HD vec3 f_select(const vec3& f, const vec3& t, const bvec3& c) { return mk3(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z); }
+S2M_HD vec4 f_select(const vec4& f, const vec4& t, const bvec4& c) { return mk4(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z, c.w ? t.w : f.w); }
+
+}  // namespace s2m
+#endif /* S2M_VEC_H_ */
