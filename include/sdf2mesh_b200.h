@@ -131,6 +131,7 @@ int s2m_params_from_cli(uint32_t resolution, float bounds, s2m_mesh_params* out,
 typedef struct s2m_timings {
   float k1_slab_ms, k2_classify_ms, k3_compact_ms, k4_vertices_ms, k4_quads_ms;
   float d2h_ms;        /* device->pinned host copies not hidden behind kernels */
+  float device_ms;     /* first launch -> last kernel finished, results resident in HBM (CUDA events) */
   float total_ms;      /* first launch -> everything resident in pinned host memory (CUDA events) */
   double host_wall_ms; /* same span by the host clock */
   uint32_t launches;   /* kernel launches issued */

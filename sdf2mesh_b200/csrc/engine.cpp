@@ -598,6 +598,7 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   r->t.k4_quads_ms = el(9, 10);
   float d2h_v = el(7, 8), d2h_q = el(10, 11);
   r->t.d2h_ms = d2h_v + d2h_q;
+  r->t.device_ms = el(0, 10);
   r->t.total_ms = el(0, 11);
   r->finished = true;
   c->busy = false;

@@ -1,4 +1,315 @@
+// emit_wgsl.cpp -- IR -> WGSL text.  Plays the role of naga::back::wgsl::Writer in
+// convert_glsl_to_wgsl (/root/reference/src/shadertoy.rs:169-194): the GLSL front-end's module is
+// written out as WGSL, which is what the reference then munges (remove `fn main_1(`, `fn main(`,
+// `@fragment`), extends with sdf3d_normal + the sdf3d wrapper (shader.rs:84-98) and compiles.  It is
+// also what --debug-wgsl shows for --glsl inputs.  The text is naga-shaped (typed literals, params
+// copied into locals, out-params as ptr<function,T>, `fn main_1()` + `@fragment fn main()`), not
+// byte-identical to naga's output.
+#include <cmath>
+#include <cstdio>
+#include <map>
+#include <set>
+#include <sstream>
+
 #include "parse.h"
+
 namespace s2m_frontend {
-std::string emit_wgsl(const Module&) { throw FrontendError(11, "WGSL writer not built yet"); }
-}
+
+namespace {
+
+class WgslWriter {
+ public:
+  explicit WgslWriter(const Module& m) : m_(m) {}
+
+  std::string run() {
+    for (const auto& v : m_.vars) used_.insert(v->name);
+    for (const auto& f : m_.functions) used_.insert(f->name);
+    for (const Var* g : m_.globals) {
+      if (g->storage == Var::ModuleConst && g->has_const) {
+        out_ << "const " << g->name << ": " << type_name(g->ty) << " = " << const_lit(g->cval) << ";\n";
+      } else {
+        out_ << "var<private> " << g->name << ": " << type_name(g->ty);
+        auto it = m_.global_init.find(g);
+        if (it != m_.global_init.end()) out_ << " = " << expr(*it->second);
+        out_ << ";\n";
+      }
+    }
+    if (!m_.globals.empty()) out_ << "\n";
+    for (const auto& f : m_.functions) {
+      if (f->is_entry || !f->body) continue;
+      function(*f);
+      out_ << "\n";
+    }
+    // naga's shape for an empty GLSL `void main() {}`
+    out_ << "fn main_1() {\n    return;\n}\n\n@fragment \nfn main() {\n    main_1();\n    return;\n}\n";
+    return out_.str();
+  }
+
+ private:
+  const Module& m_;
+  std::ostringstream out_;
+  std::set<std::string> used_;
+  std::map<const Var*, std::string> rename_;  // params copied into a mutable local
+  int tmp_ = 0;
+
+  static std::string type_name(const Type& t) {
+    const char* s = t.sk == Sk::F32 ? "f32" : t.sk == Sk::I32 ? "i32" : t.sk == Sk::U32 ? "u32" : "bool";
+    if (t.is_void()) return "void";
+    if (t.is_scalar()) return s;
+    return "vec" + std::to_string(t.n) + "<" + s + ">";
+  }
+  std::string fresh(const std::string& base) {
+    for (int i = 1;; ++i) {
+      std::string n = base + "_" + std::to_string(i);
+      if (!used_.count(n)) { used_.insert(n); return n; }
+    }
+  }
+  static std::string float_lit(double v) {
+    const float f = (float)v;
+    if (f != f) return "(0f / 0f)";
+    if (std::isinf(f)) return f > 0 ? "(1f / 0f)" : "(-1f / 0f)";
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.9g", (double)f);
+    return std::string(buf) + "f";
+  }
+  static std::string scalar_lit(const ConstVal& cv, int c) {
+    switch (cv.ty.sk) {
+      case Sk::F32: return float_lit(cv.f[c]);
+      case Sk::I32: return cv.i[c] == INT32_MIN ? "(-2147483647i - 1i)" : std::to_string((int32_t)cv.i[c]) + "i";
+      case Sk::U32: return std::to_string((uint32_t)cv.i[c]) + "u";
+      case Sk::Bool: return cv.i[c] ? "true" : "false";
+      default: throw FrontendError(4, "internal: abstract literal in the WGSL writer");
+    }
+  }
+  static std::string const_lit(const ConstVal& cv) {
+    if (cv.ty.is_scalar()) return scalar_lit(cv, 0);
+    std::string s = type_name(cv.ty) + "(";
+    for (int c = 0; c < cv.ty.n; ++c) s += (c ? ", " : "") + scalar_lit(cv, c);
+    return s + ")";
+  }
+  std::string var_name(const Var* v) {
+    auto it = rename_.find(v);
+    if (it != rename_.end()) return it->second;
+    if (v->by_ref && v->storage == Var::Param) return "(*" + v->name + ")";
+    return v->name;
+  }
+  static std::string wgsl_builtin(const std::string& canon) {
+    if (canon == "inversesqrt") return "inverseSqrt";
+    return canon;
+  }
+
+  std::string splat_to(const Expr& a, int n) {
+    std::string s = expr(a);
+    if (n > 1 && a.ty.is_scalar()) return type_name(Type::vec(a.ty.sk, n)) + "(" + s + ")";
+    return s;
+  }
+
+  std::string expr(const Expr& e) {
+    switch (e.k) {
+      case Expr::Lit: return scalar_lit(e.lit, 0);
+      case Expr::VarRef: return var_name(e.var);
+      case Expr::Unary: {
+        const char* o = e.op == Op::Neg ? "-" : e.op == Op::Not ? "!" : "~";
+        return std::string(o) + "(" + expr(*e.args[0]) + ")";
+      }
+      case Expr::Binary: {
+        static const std::map<Op, const char*> ops = {
+            {Op::Add, "+"}, {Op::Sub, "-"}, {Op::Mul, "*"}, {Op::Div, "/"}, {Op::Rem, "%"}, {Op::And, "&&"}, {Op::Or, "||"},
+            {Op::BitAnd, "&"}, {Op::BitOr, "|"}, {Op::BitXor, "^"}, {Op::Shl, "<<"}, {Op::Shr, ">>"}, {Op::Lt, "<"},
+            {Op::Le, "<="}, {Op::Gt, ">"}, {Op::Ge, ">="}, {Op::Eq, "=="}, {Op::Ne, "!="}};
+        return "(" + expr(*e.args[0]) + " " + ops.at(e.op) + " " + expr(*e.args[1]) + ")";
+      }
+      case Expr::Ternary:  // both sides are pure expressions here
+        return "select(" + expr(*e.args[2]) + ", " + expr(*e.args[1]) + ", " + expr(*e.args[0]) + ")";
+      case Expr::Call: {
+        std::string name = e.callee;
+        if (name.compare(0, 2, "i_") == 0) name = name.substr(2);
+        int n = 1;
+        for (const ExprP& a : e.args) n = std::max(n, a->ty.n);
+        if (name == "mod") {  // GLSL mod(x, y) = x - y * floor(x / y)
+          const std::string x = splat_to(*e.args[0], n), y = splat_to(*e.args[1], n);
+          return "(" + x + " - " + y + " * floor(" + x + " / " + y + "))";
+        }
+        std::string s = wgsl_builtin(name) + "(";
+        for (size_t i = 0; i < e.args.size(); ++i) {
+          const bool keep_scalar = (name == "mix" && i == 2) || name == "dot" || name == "length" || name == "distance" || name == "select" || name == "any" || name == "all";
+          s += (i ? ", " : "") + (keep_scalar ? expr(*e.args[i]) : splat_to(*e.args[i], n));
+        }
+        return s + ")";
+      }
+      case Expr::UserCall: {
+        std::string s = e.fn->name + "(";
+        for (size_t i = 0; i < e.args.size(); ++i) {
+          s += i ? ", " : "";
+          if (e.fn->params[i]->by_ref) {
+            const Expr& a = *e.args[i];
+            if (a.k == Expr::VarRef && a.var->by_ref && a.var->storage == Var::Param && !rename_.count(a.var)) s += a.var->name;  // forward the pointer
+            else s += "&" + expr(a);
+          } else s += expr(*e.args[i]);
+        }
+        return s + ")";
+      }
+      case Expr::Construct: {
+        if (e.args.empty()) return type_name(e.ty) + "()";
+        std::string s = type_name(e.ty) + "(";
+        for (size_t i = 0; i < e.args.size(); ++i) s += (i ? ", " : "") + expr(*e.args[i]);
+        return s + ")";
+      }
+      case Expr::Swizzle: {
+        std::string s = expr(*e.args[0]) + ".";
+        for (int i = 0; i < e.nswz; ++i) s += "xyzw"[e.swz[i]];
+        return s;
+      }
+      case Expr::Convert: return type_name(e.ty) + "(" + expr(*e.args[0]) + ")";
+      case Expr::AddrOf: return "&" + expr(*e.args[0]);
+      case Expr::Deref: return "(*" + expr(*e.args[0]) + ")";
+    }
+    return "";
+  }
+
+  void indent(int d) { for (int i = 0; i < d; ++i) out_ << "    "; }
+
+  void function(const Function& f) {
+    rename_.clear();
+    out_ << "fn " << f.name << "(";
+    for (size_t i = 0; i < f.params.size(); ++i) {
+      const Var* p = f.params[i];
+      out_ << (i ? ", " : "") << p->name << ": ";
+      if (p->by_ref) out_ << "ptr<function, " << type_name(p->ty) << ">";
+      else out_ << type_name(p->ty);
+    }
+    out_ << ")";
+    if (!f.ret.is_void()) out_ << " -> " << type_name(f.ret);
+    out_ << " {\n";
+    // WGSL parameters are immutable: copy the ones the GLSL body assigns to (naga does this for all)
+    for (const Var* p : f.params) {
+      if (p->by_ref || !p->written) continue;
+      const std::string local = fresh(p->name);
+      indent(1);
+      out_ << "var " << local << ": " << type_name(p->ty) << " = " << p->name << ";\n";
+      rename_[p] = local;
+    }
+    for (const StmtP& s : f.body->body) stmt(*s, 1);
+    out_ << "}\n";
+  }
+
+  void block(const Stmt& s, int d) {
+    out_ << "{\n";
+    for (const StmtP& c : s.body) stmt(*c, d + 1);
+    indent(d);
+    out_ << "}";
+  }
+
+  // assignment without indentation / terminator; multi-component swizzle stores are expanded
+  void assign(const Stmt& s, int d, bool in_header) {
+    const Expr& lhs = *s.a;
+    if (lhs.k == Expr::Swizzle && lhs.nswz > 1) {
+      if (in_header) throw FrontendError(11, "unsupported: swizzle assignment in a for header");
+      const Expr& base = *lhs.args[0];
+      bool identity = lhs.nswz == base.ty.n;
+      for (int i = 0; i < lhs.nswz; ++i) identity = identity && lhs.swz[i] == i;
+      if (identity) { out_ << expr(base) << " = " << expr(*s.b) << ";"; return; }
+      const std::string t = fresh("_e");
+      out_ << "{\n";
+      indent(d + 1);
+      out_ << "let " << t << " = " << expr(*s.b) << ";\n";
+      for (int i = 0; i < lhs.nswz; ++i) {
+        indent(d + 1);
+        out_ << expr(base) << "." << "xyzw"[lhs.swz[i]] << " = " << t << "." << "xyzw"[i] << ";\n";
+      }
+      indent(d);
+      out_ << "}";
+      return;
+    }
+    out_ << expr(lhs) << " = " << expr(*s.b);
+    if (!in_header) out_ << ";";
+  }
+
+  void header_stmt(const Stmt& s, int d) {
+    if (s.k == Stmt::Assign) assign(s, d, true);
+    else if (s.k == Stmt::CallStmt) out_ << expr(*s.a);
+    else if (s.k == Stmt::VarDecl) {
+      out_ << "var " << s.var->name << ": " << type_name(s.var->ty);
+      if (s.a) out_ << " = " << expr(*s.a);
+    } else throw FrontendError(11, "unsupported statement in a for header");
+  }
+
+  void stmt(const Stmt& s, int d) {
+    indent(d);
+    switch (s.k) {
+      case Stmt::Block: block(s, d); out_ << "\n"; break;
+      case Stmt::VarDecl:
+        out_ << (s.var->immutable && s.a ? "let " : "var ") << s.var->name << ": " << type_name(s.var->ty);
+        if (s.a) out_ << " = " << expr(*s.a);
+        out_ << ";\n";
+        break;
+      case Stmt::Assign: assign(s, d, false); out_ << "\n"; break;
+      case Stmt::CallStmt: out_ << expr(*s.a) << ";\n"; break;
+      case Stmt::Return:
+        if (s.a) out_ << "return " << expr(*s.a) << ";\n"; else out_ << "return;\n";
+        break;
+      case Stmt::Break: out_ << "break;\n"; break;
+      case Stmt::Continue: out_ << "continue;\n"; break;
+      case Stmt::Discard: out_ << "discard;\n"; break;
+      case Stmt::If: emit_if(s, d); out_ << "\n"; break;
+      case Stmt::For:
+        out_ << "for (";
+        if (s.init) header_stmt(*s.init, d);
+        out_ << "; ";
+        if (s.a) out_ << expr(*s.a);
+        out_ << "; ";
+        if (s.cont) header_stmt(*s.cont, d);
+        out_ << ") ";
+        block(*s.body[0], d);
+        out_ << "\n";
+        break;
+      case Stmt::While:
+        out_ << "while " << expr(*s.a) << " ";
+        block(*s.body[0], d);
+        out_ << "\n";
+        break;
+      case Stmt::DoWhile:
+        out_ << "loop {\n";
+        for (const StmtP& c : s.body[0]->body) stmt(*c, d + 1);
+        indent(d + 1);
+        out_ << "continuing {\n";
+        indent(d + 2);
+        out_ << "break if !(" << expr(*s.a) << ");\n";
+        indent(d + 1);
+        out_ << "}\n";
+        indent(d);
+        out_ << "}\n";
+        break;
+      case Stmt::Loop:
+        out_ << "loop {\n";
+        for (const StmtP& c : s.body[0]->body) stmt(*c, d + 1);
+        if (s.cont || s.break_if) {
+          indent(d + 1);
+          out_ << "continuing {\n";
+          if (s.cont) for (const StmtP& c : s.cont->body) stmt(*c, d + 2);
+          if (s.break_if) { indent(d + 2); out_ << "break if " << expr(*s.break_if) << ";\n"; }
+          indent(d + 1);
+          out_ << "}\n";
+        }
+        indent(d);
+        out_ << "}\n";
+        break;
+    }
+  }
+
+  void emit_if(const Stmt& s, int d) {
+    out_ << "if " << expr(*s.a) << " ";
+    block(*s.then_s, d);
+    if (s.else_s) {
+      out_ << " else ";
+      if (s.else_s->k == Stmt::If) emit_if(*s.else_s, d);
+      else block(*s.else_s, d);
+    }
+  }
+};
+
+}  // namespace
+
+std::string emit_wgsl(const Module& m) { return WgslWriter(m).run(); }
+
+}  // namespace s2m_frontend

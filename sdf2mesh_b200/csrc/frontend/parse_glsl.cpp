@@ -1,4 +1,499 @@
+// parse_glsl.cpp -- GLSL (fragment shader) front-end: the subset ShaderToy-style SDF code uses.
+// Replaces naga's glsl::Frontend behind convert_glsl_to_wgsl (/root/reference/src/shadertoy.rs:169-194).
 #include "parse.h"
+#include "parser_base.h"
+
 namespace s2m_frontend {
-void parse_glsl(const std::string&, Module*) { throw FrontendError(11, "GLSL front-end not built yet"); }
+
+namespace {
+
+class GlslParser : public ParserBase {
+ public:
+  explicit GlslParser(Module* m) : ParserBase(Lang::Glsl, m) {}
+
+  void parse(const std::string& src) {
+    LexOptions lo;
+    lo.glsl = true;
+    toks = Lexer(src, lo).run();
+    push_scope();
+    bool have_main = false;
+    while (peek().k != Token::End) {
+      if (accept(";")) continue;
+      parse_external_declaration(&have_main);
+    }
+    if (!have_main) throw FrontendError(3, "parse error: GLSL shader has no entry point `void main()`");
+  }
+
+ private:
+  static bool type_from_name(const std::string& s, Type* t) {
+    if (s == "void") { *t = Type::void_(); return true; }
+    if (s == "float") { *t = Type::scalar(Sk::F32); return true; }
+    if (s == "int") { *t = Type::scalar(Sk::I32); return true; }
+    if (s == "uint") { *t = Type::scalar(Sk::U32); return true; }
+    if (s == "bool") { *t = Type::scalar(Sk::Bool); return true; }
+    if (s.size() == 4 && s.compare(0, 3, "vec") == 0 && s[3] >= '2' && s[3] <= '4') { *t = Type::vec(Sk::F32, s[3] - '0'); return true; }
+    if (s.size() == 5 && s.compare(1, 3, "vec") == 0 && s[4] >= '2' && s[4] <= '4') {
+      const Sk sk = s[0] == 'i' ? Sk::I32 : s[0] == 'u' ? Sk::U32 : s[0] == 'b' ? Sk::Bool : Sk::F32;
+      if (s[0] == 'i' || s[0] == 'u' || s[0] == 'b') { *t = Type::vec(sk, s[4] - '0'); return true; }
+    }
+    return false;
+  }
+  bool at_type() const {
+    if (peek().k != Token::Ident) return false;
+    Type t;
+    const std::string& s = peek().text;
+    return type_from_name(s, &t) || s.compare(0, 3, "mat") == 0 || s == "double" || s.compare(0, 4, "dvec") == 0 || s.compare(0, 7, "sampler") == 0;
+  }
+  Type parse_type() {
+    const std::string s = expect_ident("a type");
+    Type t;
+    if (type_from_name(s, &t)) return t;
+    b.unsupported("GLSL type '" + s + "'");
+  }
+
+  struct Qualifiers { bool is_const = false, uniform = false, in = false, out = false, inout = false; };
+  Qualifiers parse_qualifiers() {
+    Qualifiers q;
+    for (;;) {
+      if (accept_ident("const")) q.is_const = true;
+      else if (accept_ident("uniform")) q.uniform = true;
+      else if (accept_ident("in")) q.in = true;
+      else if (accept_ident("out")) q.out = true;
+      else if (accept_ident("inout")) q.inout = true;
+      else if (accept_ident("highp") || accept_ident("mediump") || accept_ident("lowp") || accept_ident("flat") ||
+               accept_ident("smooth") || accept_ident("noperspective") || accept_ident("centroid") || accept_ident("invariant") ||
+               accept_ident("precise")) {}
+      else if (is_ident("layout")) {
+        advance();
+        expect("(");
+        int depth = 1;
+        while (depth > 0 && peek().k != Token::End) { if (is_punct("(")) ++depth; if (is_punct(")")) --depth; advance(); }
+      } else break;
+    }
+    return q;
+  }
+
+  void parse_external_declaration(bool* have_main) {
+    b.cur_line = peek().line;
+    if (accept_ident("precision")) { while (!is_punct(";") && peek().k != Token::End) advance(); expect(";"); return; }
+    if (is_ident("struct")) b.unsupported("struct declarations");
+    Qualifiers q = parse_qualifiers();
+    if (is_ident("buffer") || is_ident("shared")) b.unsupported("storage qualifier " + peek().text);
+    if (accept(";")) return;  // e.g. `layout(...) in;`
+    Type ty = parse_type();
+    const std::string name = expect_ident("a name");
+    if (is_punct("(")) { parse_function(ty, name, have_main); return; }
+    // global variable(s)
+    std::string n = name;
+    for (;;) {
+      if (is_punct("[")) b.unsupported("arrays");
+      ExprP init;
+      if (accept("=")) init = parse_assignment_expr();
+      declare_global(q, ty, n, init);
+      if (!accept(",")) break;
+      n = expect_ident("a name");
+    }
+    expect(";");
+  }
+
+  void declare_global(const Qualifiers& q, Type ty, const std::string& name, ExprP init) {
+    if (ty.is_void()) b.error("variable of type void");
+    const bool resource = q.uniform || q.in || q.out;
+    if (resource) init = nullptr;
+    if (init) init = b.coerce(init, ty, "initializer");
+    Var* v = declare(name, ty, q.is_const ? Var::ModuleConst : Var::Global);
+    v->immutable = q.is_const || q.uniform || q.in;
+    if (init) {
+      ConstVal cv;
+      if (b.const_eval(*init, &cv)) { v->has_const = true; v->cval = cv; }
+      mod->global_init[v] = init;
+    } else {
+      if (q.is_const) b.error("const '" + name + "' needs an initializer");
+      v->has_const = true;
+      v->cval.ty = ty;
+    }
+    mod->globals.push_back(v);
+  }
+
+  void parse_function(Type ret, const std::string& name, bool* have_main) {
+    std::vector<Var*> params;
+    expect("(");
+    if (is_ident("void") && is_punct(")", 1)) advance();
+    while (!is_punct(")")) {
+      Qualifiers q = parse_qualifiers();
+      Type t = parse_type();
+      if (t.is_void()) b.error("parameter of type void");
+      std::string pn = "_p" + std::to_string(params.size());
+      if (peek().k == Token::Ident) pn = advance().text;
+      if (is_punct("[")) b.unsupported("array parameters");
+      Var* v = mod->new_var();
+      v->name = pn; v->ty = t; v->storage = Var::Param;
+      v->immutable = q.is_const;
+      v->by_ref = q.out || q.inout;
+      params.push_back(v);
+      if (!accept(",")) break;
+    }
+    expect(")");
+    Function* fn = nullptr;
+    auto it = functions.find(name);
+    if (it != functions.end()) {
+      fn = it->second;
+      bool same = fn->params.size() == params.size() && fn->ret == ret;
+      for (size_t i = 0; same && i < params.size(); ++i) same = fn->params[i]->ty == params[i]->ty && fn->params[i]->by_ref == params[i]->by_ref;
+      if (!same) b.unsupported("overloaded function '" + name + "'");
+      if (fn->body && is_punct("{")) b.error("redefinition of function '" + name + "'");
+    } else {
+      if (lookup(name) && scopes.size() == 1 && scopes[0].count(name)) b.error("'" + name + "' redeclared as a function");
+      mod->functions.emplace_back(new Function());
+      fn = mod->functions.back().get();
+      fn->name = name; fn->ret = ret; fn->line = peek().line;
+      functions[name] = fn;
+    }
+    if (accept(";")) { if (fn->params.empty()) fn->params = params; return; }  // prototype
+    fn->params = params;
+    if (name == "main") {
+      *have_main = true;
+      fn->is_entry = true;
+      skip_braces();  // the fragment entry point is discarded by the caller (shader.rs:84-86)
+      return;
+    }
+    if (name == "mainImage") {  // ShaderToy image entry: never part of the SDF; keep the signature only
+      fn->is_entry = false;
+      skip_braces();
+      fn->body = mk_stmt(Stmt::Block);
+      return;
+    }
+    cur_fn = fn;
+    push_scope();
+    for (Var* p : params) {
+      if (scopes.back().count(p->name)) b.error("duplicate parameter '" + p->name + "'");
+      scopes.back()[p->name] = p;
+    }
+    fn->body = parse_compound(false);
+    pop_scope();
+    cur_fn = nullptr;
+  }
+
+  // ---------------------------------------------------------------- statements
+  StmtP parse_compound(bool new_scope) {
+    expect("{");
+    StmtP blk = mk_stmt(Stmt::Block);
+    if (new_scope) push_scope();
+    while (!is_punct("}")) {
+      if (peek().k == Token::End) perr("unterminated block");
+      parse_statement_into(blk);
+    }
+    expect("}");
+    if (new_scope) pop_scope();
+    return blk;
+  }
+  // a statement used as a loop / if body: always returns a Block
+  StmtP parse_body() {
+    if (is_punct("{")) return parse_compound(true);
+    StmtP blk = mk_stmt(Stmt::Block);
+    push_scope();
+    parse_statement_into(blk);
+    pop_scope();
+    return blk;
+  }
+
+  void parse_declaration_into(StmtP blk) {
+    Qualifiers q = parse_qualifiers();
+    Type ty = parse_type();
+    if (ty.is_void()) b.error("variable of type void");
+    for (;;) {
+      const std::string name = expect_ident("a variable name");
+      if (is_punct("[")) b.unsupported("arrays");
+      ExprP init;
+      if (accept("=")) init = b.coerce(parse_assignment_expr(), ty, "initializer");
+      Var* v = declare(name, ty, Var::Local);
+      v->immutable = q.is_const;
+      if (q.is_const && !init) b.error("const '" + name + "' needs an initializer");
+      StmtP s = mk_stmt(Stmt::VarDecl);
+      s->var = v; s->a = init;
+      blk->body.push_back(s);
+      if (!accept(",")) break;
+    }
+  }
+
+  // expression statement without ';' : assignment, ++/--, call
+  StmtP parse_expression_statement() {
+    if (is_punct("++") || is_punct("--")) {
+      const bool inc = advance().text == "++";
+      ExprP lhs = parse_unary();
+      return make_assign(lhs, b.binary(inc ? Op::Add : Op::Sub, lhs, one_for(lhs)));
+    }
+    ExprP lhs = parse_unary();
+    if (is_punct("=")) {
+      advance();
+      return make_assign(lhs, parse_assignment_expr());
+    }
+    if (peek().k == Token::Punct) {
+      const std::string p = peek().text;
+      if (p == "+=" || p == "-=" || p == "*=" || p == "/=" || p == "%=" || p == "&=" || p == "|=" || p == "^=" || p == "<<=" || p == ">>=") {
+        advance();
+        ExprP rhs = parse_assignment_expr();
+        return make_assign(lhs, b.binary(compound_op(p), lhs, rhs));
+      }
+      if (p == "++" || p == "--") {
+        advance();
+        return make_assign(lhs, b.binary(p == "++" ? Op::Add : Op::Sub, lhs, one_for(lhs)));
+      }
+    }
+    if (lhs->k == Expr::UserCall || lhs->k == Expr::Call) {
+      StmtP s = mk_stmt(Stmt::CallStmt);
+      s->a = lhs;
+      return s;
+    }
+    perr("expected a statement (expression statements without effect are not supported)");
+  }
+  ExprP one_for(const ExprP& lhs) {
+    if (lhs->ty.is_float()) return b.lit_float(1.0, Sk::F32);
+    return b.lit_int(1, lhs->ty.sk);
+  }
+
+  ExprP parse_condition() {
+    ExprP c = parse_expr();
+    if (!c->ty.is_bool() || !c->ty.is_scalar()) b.error("condition must be a bool, found " + c->ty.str());
+    return c;
+  }
+
+  void parse_statement_into(StmtP blk) {
+    b.cur_line = peek().line;
+    if (accept(";")) return;
+    if (is_punct("{")) { blk->body.push_back(parse_compound(true)); return; }
+    if (is_ident("const") || is_ident("highp") || is_ident("mediump") || is_ident("lowp") || (at_type() && peek(1).k == Token::Ident)) {
+      parse_declaration_into(blk);
+      expect(";");
+      return;
+    }
+    if (accept_ident("return")) {
+      StmtP s = mk_stmt(Stmt::Return);
+      if (!is_punct(";")) {
+        if (cur_fn->ret.is_void()) b.error("return with a value in a void function");
+        s->a = b.coerce(parse_expr(), cur_fn->ret, "return");
+      } else if (!cur_fn->ret.is_void()) b.error("return without a value");
+      expect(";");
+      blk->body.push_back(s);
+      return;
+    }
+    if (accept_ident("if")) { blk->body.push_back(parse_if()); return; }
+    if (accept_ident("for")) {
+      StmtP s = mk_stmt(Stmt::For);
+      push_scope();
+      expect("(");
+      if (!is_punct(";")) {
+        if (at_type() && peek(1).k == Token::Ident) {
+          StmtP tmp = mk_stmt(Stmt::Block);
+          parse_declaration_into(tmp);
+          if (tmp->body.size() != 1) b.unsupported("several declarators in a for-init");
+          s->init = tmp->body[0];
+        } else s->init = parse_expression_statement();
+      }
+      expect(";");
+      if (!is_punct(";")) s->a = parse_condition();
+      expect(";");
+      if (!is_punct(")")) {
+        s->cont = parse_expression_statement();
+        if (is_punct(",")) b.unsupported("comma operator in a for header");
+      }
+      expect(")");
+      ++loop_depth;
+      s->body.push_back(parse_body());
+      --loop_depth;
+      pop_scope();
+      blk->body.push_back(s);
+      return;
+    }
+    if (accept_ident("while")) {
+      StmtP s = mk_stmt(Stmt::While);
+      expect("(");
+      s->a = parse_condition();
+      expect(")");
+      ++loop_depth;
+      s->body.push_back(parse_body());
+      --loop_depth;
+      blk->body.push_back(s);
+      return;
+    }
+    if (accept_ident("do")) {
+      StmtP s = mk_stmt(Stmt::DoWhile);
+      ++loop_depth;
+      s->body.push_back(parse_body());
+      --loop_depth;
+      if (!accept_ident("while")) perr("expected 'while' after do body");
+      expect("(");
+      s->a = parse_condition();
+      expect(")");
+      expect(";");
+      blk->body.push_back(s);
+      return;
+    }
+    if (accept_ident("break")) { if (!loop_depth) b.error("break outside of a loop"); expect(";"); blk->body.push_back(mk_stmt(Stmt::Break)); return; }
+    if (accept_ident("continue")) { if (!loop_depth) b.error("continue outside of a loop"); expect(";"); blk->body.push_back(mk_stmt(Stmt::Continue)); return; }
+    if (accept_ident("discard")) { expect(";"); blk->body.push_back(mk_stmt(Stmt::Discard)); return; }
+    if (is_ident("switch")) b.unsupported("switch statements");
+    StmtP s = parse_expression_statement();
+    expect(";");
+    blk->body.push_back(s);
+  }
+
+  StmtP parse_if() {
+    StmtP s = mk_stmt(Stmt::If);
+    expect("(");
+    s->a = parse_condition();
+    expect(")");
+    s->then_s = parse_body();
+    if (accept_ident("else")) {
+      if (accept_ident("if")) s->else_s = parse_if();
+      else s->else_s = parse_body();
+    }
+    return s;
+  }
+
+  // ---------------------------------------------------------------- expressions
+  ExprP parse_expr() { return parse_assignment_expr(); }
+  ExprP parse_assignment_expr() {  // assignments inside expressions are not supported; this is the ?: level
+    ExprP c = parse_binary(0);
+    if (accept("?")) {
+      ExprP t = parse_assignment_expr();
+      expect(":");
+      ExprP f = parse_assignment_expr();
+      return b.ternary(c, t, f);
+    }
+    if (is_punct("=") || is_punct("+=") || is_punct("-=") || is_punct("*=") || is_punct("/="))
+      b.unsupported("assignment used as an expression");
+    return c;
+  }
+  static int prec_of(const std::string& p) {
+    if (p == "||") return 1;
+    if (p == "^^") return 2;
+    if (p == "&&") return 3;
+    if (p == "|") return 4;
+    if (p == "^") return 5;
+    if (p == "&") return 6;
+    if (p == "==" || p == "!=") return 7;
+    if (p == "<" || p == ">" || p == "<=" || p == ">=") return 8;
+    if (p == "<<" || p == ">>") return 9;
+    if (p == "+" || p == "-") return 10;
+    if (p == "*" || p == "/" || p == "%") return 11;
+    return -1;
+  }
+  ExprP parse_binary(int min_prec) {
+    ExprP lhs = parse_unary();
+    for (;;) {
+      if (peek().k != Token::Punct) break;
+      std::string p = peek().text;
+      if (p == "^" && is_punct("^", 1)) b.unsupported("^^ operator");
+      const int prec = prec_of(p);
+      if (prec < 0 || prec < min_prec) break;
+      advance();
+      ExprP rhs = parse_binary(prec + 1);
+      Op op = p == "||" ? Op::Or : p == "&&" ? Op::And : p == "|" ? Op::BitOr : p == "^" ? Op::BitXor : p == "&" ? Op::BitAnd
+              : p == "==" ? Op::Eq : p == "!=" ? Op::Ne : p == "<" ? Op::Lt : p == ">" ? Op::Gt : p == "<=" ? Op::Le : p == ">=" ? Op::Ge
+              : p == "<<" ? Op::Shl : p == ">>" ? Op::Shr : p == "+" ? Op::Add : p == "-" ? Op::Sub : p == "*" ? Op::Mul : p == "/" ? Op::Div : Op::Rem;
+      if (op == Op::Rem && (lhs->ty.is_float() || rhs->ty.is_float())) b.error("% needs integer operands in GLSL (use mod())");
+      lhs = b.binary(op, lhs, rhs);
+    }
+    return lhs;
+  }
+  ExprP parse_unary() {
+    b.cur_line = peek().line;
+    if (accept("-")) return b.unary(Op::Neg, parse_unary());
+    if (accept("+")) return parse_unary();
+    if (accept("!")) return b.unary(Op::Not, parse_unary());
+    if (accept("~")) return b.unary(Op::BitNot, parse_unary());
+    if (is_punct("++") || is_punct("--")) b.unsupported("++/-- inside an expression");
+    ExprP e = parse_postfix(parse_primary());
+    if (is_punct("++") || is_punct("--")) {
+      // allowed only when the whole statement is `x++;` -- handled by the caller; elsewhere reject
+      if (!(is_punct(";", 1) || is_punct(")", 1))) b.unsupported("++/-- inside an expression");
+    }
+    return e;
+  }
+  ExprP parse_postfix(ExprP e) {
+    for (;;) {
+      if (accept(".")) {
+        const std::string m = expect_ident("a member name");
+        if (is_punct("(")) b.unsupported("method call ." + m + "()");
+        e = b.swizzle(e, m);
+        continue;
+      }
+      if (is_punct("[")) {
+        advance();
+        ExprP idx = parse_expr();
+        expect("]");
+        ConstVal cv;
+        if (!e->ty.is_vector()) b.unsupported("indexing of non-vector values");
+        if (!idx->ty.is_int() || !b.const_eval(*idx, &cv)) b.unsupported("dynamic vector indexing");
+        if (cv.i[0] < 0 || cv.i[0] >= e->ty.n) b.error("vector index out of range");
+        e = b.swizzle(e, std::string(1, "xyzw"[cv.i[0]]));
+        continue;
+      }
+      break;
+    }
+    return e;
+  }
+  std::vector<ExprP> parse_args() {
+    std::vector<ExprP> args;
+    expect("(");
+    if (is_ident("void") && is_punct(")", 1)) advance();
+    while (!is_punct(")")) {
+      args.push_back(parse_assignment_expr());
+      if (!accept(",")) break;
+    }
+    expect(")");
+    return args;
+  }
+  ExprP parse_primary() {
+    const Token& t = peek();
+    b.cur_line = t.line;
+    if (t.k == Token::Float) { advance(); return b.lit_float(t.fval, Sk::F32); }
+    if (t.k == Token::Int) {
+      advance();
+      if (t.suffix == 'f') return b.lit_float((double)t.ival, Sk::F32);
+      return b.lit_int(t.ival, t.suffix == 'u' ? Sk::U32 : Sk::I32);
+    }
+    if (accept("(")) {
+      ExprP e = parse_expr();
+      expect(")");
+      return e;
+    }
+    if (t.k != Token::Ident) perr("expected an expression");
+    const std::string name = t.text;
+    if (name == "true" || name == "false") { advance(); return b.lit_bool(name == "true"); }
+    Type ty;
+    if (is_punct("(", 1) && (type_from_name(name, &ty) || name.compare(0, 3, "mat") == 0)) {
+      if (name.compare(0, 3, "mat") == 0) b.unsupported("matrix types (" + name + ")");
+      advance();
+      std::vector<ExprP> args = parse_args();
+      return b.construct(ty, false, args);
+    }
+    if (is_punct("(", 1)) {
+      // a local variable cannot be called; functions and builtins share one namespace
+      advance();
+      std::vector<ExprP> args = parse_args();
+      auto it = functions.find(name);
+      if (it != functions.end()) {
+        if (it->second->is_entry) b.error("main() cannot be called");
+        return b.call_user(it->second, args);
+      }
+      if (name == "texture" || name == "texelFetch" || name == "textureLod") b.unsupported("texture sampling (" + name + ")");
+      ExprP e = b.call_builtin(name, args);
+      if (!e) b.error("unknown function '" + name + "'");
+      return e;
+    }
+    if (Var* v = lookup(name)) { advance(); return b.var_ref(v); }
+    if (name.compare(0, 3, "gl_") == 0) b.unsupported("built-in variable " + name);
+    b.error("unknown identifier '" + name + "'");
+  }
+};
+
+}  // namespace
+
+void parse_glsl(const std::string& src, Module* out) {
+  GlslParser p(out);
+  p.parse(src);
 }
+
+}  // namespace s2m_frontend

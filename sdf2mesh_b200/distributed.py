@@ -1,0 +1,89 @@
+"""Multi-GPU z-slab decomposition: one process per GPU, no data-path collective.
+
+Rank g meshes true cell slices [z_g, z_{g+1}) and recomputes the single slice z_g - 1 locally (its
+one-plane corner halo) so it can name that slice's vertices in its quads.  The only exchange is
+one all-gather of the per-slab vertex counts (8 bytes per rank, NCCL over NVLink when the backend
+is nccl) whose exclusive prefix is the slab's global vertex base.  The
+reference has no multi-device path at all (one adapter, one queue: main.rs:180-196).
+"""
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+
+def n_scanned_slices(res_z: int, all_slices: bool) -> int:
+    """slices the reference's loop actually reads back: res_z - 1 unless ALL_SLICES"""
+    return res_z if all_slices else res_z - 1
+
+
+def partition_slices(n_slices: int, world: int, cost: Optional[Sequence[float]] = None) -> List[int]:
+    """Boundaries b[0..world] with b[0] = 0, b[world] = n_slices, non-decreasing.
+
+    cost: relative cost of equal-thickness z bands (any length >= 1, e.g. from s2m_cost_probe);
+    None = equal thickness.  Slab g gets ~1/world of the total cost (for the mandelbulb
+    the work is concentrated in r <= 2, so equal thickness starves the outer ranks).
+    """
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    if cost is None or len(cost) == 0 or not np.isfinite(np.sum(cost)) or np.sum(cost) <= 0:
+        return [int(round(n_slices * g / world)) for g in range(world + 1)]
+    c = np.asarray(cost, np.float64)
+    c = np.maximum(c, c.max() * 1e-3)  # every band costs something (launch + memory traffic)
+    # piecewise-linear cumulative cost over slice index
+    edges = np.linspace(0.0, float(n_slices), len(c) + 1)
+    cum = np.concatenate([[0.0], np.cumsum(c)])
+    targets = cum[-1] * np.arange(world + 1) / world
+    b = np.interp(targets, cum, edges)
+    out = [int(round(x)) for x in b]
+    out[0], out[-1] = 0, n_slices
+    for i in range(1, len(out)):
+        out[i] = min(max(out[i], out[i - 1]), n_slices)
+    return out
+
+
+def exclusive_bases(counts: Sequence[int]) -> List[int]:
+    out, acc = [], 0
+    for c in counts:
+        out.append(acc)
+        acc += int(c)
+    return out
+
+
+def allgather_counts(local_count: int, device=None) -> List[int]:
+    """one all-gather of a single int64 per rank over torch.distributed (nccl or gloo)"""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return [int(local_count)]
+    t = torch.tensor([int(local_count)], dtype=torch.int64, device=device if device is not None else "cpu")
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [int(x.item()) for x in out]
+
+
+def broadcast_boundaries(bounds: Optional[List[int]], world: int, device=None) -> List[int]:
+    """rank 0 decides the partition (its cost probe); everyone uses the same one"""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return list(bounds)
+    t = torch.zeros(world + 1, dtype=torch.int64, device=device if device is not None else "cpu")
+    if dist.get_rank() == 0:
+        t[:] = torch.tensor(bounds, dtype=torch.int64)
+    dist.broadcast(t, 0)
+    return [int(x) for x in t.tolist()]
+
+
+def mesh_slab(ctx, module, params, z_begin: int, z_end: int, gather=allgather_counts, rank: int = 0, device=None):
+    """Mesh one z-slab and return (MeshResult, global_vertex_base, all_counts).
+
+    begin() runs K1..K4a and yields the local vertex count; the all-gather turns counts into the
+    global base; finish(base) emits quads with global 64-bit indices.
+    """
+    from . import engine
+    params.z_begin, params.z_end = int(z_begin), int(z_end)
+    res = engine.mesh_begin(ctx, module, params)
+    counts = gather(res.info().n_vertices, device) if gather is allgather_counts else gather(res.info().n_vertices)
+    base = exclusive_bases(counts)[rank]
+    res.finish(base)
+    return res, base, counts

@@ -1,0 +1,193 @@
+"""Context / Module / meshing calls over the C ABI (the path main.rs:177-364 inlines in `run()`)."""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi
+from ._capi import MeshParams, ResultInfo, check, lib
+
+
+class Context:
+    """One CUDA device (replaces wgpu Instance/Adapter/Device/Queue, main.rs:180-196)."""
+
+    def __init__(self, device: int = 0):
+        self._h = ctypes.c_void_p()
+        check(lib().s2m_ctx_create(device, ctypes.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().s2m_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_info(self):
+        name = ctypes.create_string_buffer(256)
+        sms = ctypes.c_int()
+        mem = ctypes.c_uint64()
+        check(lib().s2m_ctx_device_info(self._h, name, 256, ctypes.byref(sms), ctypes.byref(mem)))
+        return name.value.decode(), sms.value, mem.value
+
+
+class Module:
+    """A compiled SDF (replaces create_shader_module + create_compute_pipeline)."""
+
+    def __init__(self, shader, ctx: Context = None, flags: int = 0):
+        self._h = ctypes.c_void_p()
+        self.ctx = ctx
+        self._shader = shader
+        check(lib().s2m_module_compile(ctx._h if ctx is not None else None, shader._h, flags, ctypes.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                lib().s2m_module_free(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    @property
+    def log(self) -> str:
+        return lib().s2m_module_log(self._h).decode("utf-8", "replace")
+
+    @property
+    def cuda_source(self) -> str:
+        return lib().s2m_module_cuda_source(self._h).decode("utf-8", "replace")
+
+    @property
+    def cubin_size(self) -> int:
+        data = ctypes.c_void_p()
+        size = ctypes.c_size_t()
+        check(lib().s2m_module_cubin(self._h, ctypes.byref(data), ctypes.byref(size)))
+        return size.value
+
+    def compile_ms(self):
+        return tuple(lib().s2m_module_compile_ms(self._h, i) for i in range(3))
+
+    def eval_points(self, pts) -> np.ndarray:
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        out = np.empty(pts.shape[0], np.float32)
+        check(lib().s2m_eval_points(self.ctx._h, self._h, pts.ctypes.data, pts.shape[0], out.ctypes.data))
+        return out
+
+
+def params_from_cli(resolution=None, bounds=None, flags: int = 0):
+    """AppState::from(&Arguments), main.rs:139-175.  Returns (MeshParams, rounded: bool)."""
+    p = MeshParams()
+    rounded = ctypes.c_int()
+    check(lib().s2m_params_from_cli(resolution or 0, float(bounds) if bounds else 0.0, ctypes.byref(p), ctypes.byref(rounded)))
+    p.flags = flags
+    return p, bool(rounded.value)
+
+
+def make_params(dims, bb_min, bb_max, eps=1e-4, flags=0, z_begin=0, z_end=0, tau_voxels=0.0, slab_budget_bytes=0):
+    p = MeshParams()
+    p.struct_size = ctypes.sizeof(MeshParams)
+    d = [dims] * 3 if np.isscalar(dims) else list(dims)
+    for a in range(3):
+        p.bb_min[a] = float(bb_min[a])
+        p.bb_max[a] = float(bb_max[a])
+        p.dims[a] = int(d[a])
+    p.eps = eps
+    p.flags = flags
+    p.z_begin, p.z_end = z_begin, z_end
+    p.tau_voxels = tau_voxels
+    p.slab_budget_bytes = slab_budget_bytes
+    return p
+
+
+def _view(ptr, n, dtype, shape=None):
+    if n == 0 or not ptr:
+        a = np.empty(0, dtype)
+    else:
+        a = np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
+    return a.reshape(shape) if shape else a
+
+
+@dataclass
+class MeshData:
+    """Numpy views into the library's pinned host memory (valid until MeshResult.free())."""
+    positions: np.ndarray
+    normals: np.ndarray
+    keys: np.ndarray
+    nibbles: np.ndarray
+    quads: np.ndarray
+    candidates: np.ndarray
+    n_invalid_quads: int
+    n_halo_vertices: int
+    n_candidates: int
+    timings: dict
+
+
+class MeshResult:
+    def __init__(self, handle, ctx):
+        self._h = handle
+        self._ctx = ctx  # keep the context alive while views exist
+
+    def finish(self, global_vertex_base: int = 0):
+        check(lib().s2m_mesh_finish(self._h, global_vertex_base))
+        return self
+
+    def info(self) -> ResultInfo:
+        i = ResultInfo()
+        check(lib().s2m_result_get(self._h, ctypes.byref(i)))
+        return i
+
+    def data(self) -> MeshData:
+        i = self.info()
+        nv, nq = i.n_vertices, i.n_quads
+        t = {f[0]: getattr(i.timings, f[0]) for f in _capi.Timings._fields_}
+        return MeshData(
+            _view(i.positions, nv * 3, np.float32, (-1, 3)), _view(i.normals, nv * 3, np.float32, (-1, 3)),
+            _view(i.cell_keys, nv, np.uint64), _view(i.sign_nibbles, nv, np.uint8),
+            _view(i.quads, nq * 4, np.uint64, (-1, 4)),
+            _view(i.candidates, i.n_candidates if i.candidates else 0, np.uint64),
+            i.n_invalid_quads, i.n_halo_vertices, i.n_candidates, t)
+
+    def write_mesh(self, path):
+        """TriangleMesh::write_to_file (mesh.rs:182): .stl / .ply by extension."""
+        check(lib().s2m_result_write_mesh(self._h, str(path).encode()))
+
+    def write_stl_binary(self, path):
+        check(lib().s2m_result_write_stl_binary(self._h, str(path).encode()))
+
+    def free(self):
+        if getattr(self, "_h", None):
+            lib().s2m_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def mesh_begin(ctx: Context, module: Module, params: MeshParams) -> MeshResult:
+    h = ctypes.c_void_p()
+    check(lib().s2m_mesh_begin(ctx._h, module._h, ctypes.byref(params), ctypes.byref(h)))
+    return MeshResult(h, ctx)
+
+
+def mesh_run(ctx: Context, module: Module, params: MeshParams) -> MeshResult:
+    h = ctypes.c_void_p()
+    check(lib().s2m_mesh_run(ctx._h, module._h, ctypes.byref(params), ctypes.byref(h)))
+    return MeshResult(h, ctx)
+
+
+def debug_slab_plane(ctx: Context, module: Module, params: MeshParams, plane: int) -> np.ndarray:
+    out = np.empty((params.dims[1] + 1, params.dims[0] + 1), np.float32)
+    check(lib().s2m_debug_slab_plane(ctx._h, module._h, ctypes.byref(params), plane, out.ctypes.data))
+    return out
+
+
+def cost_probe(ctx: Context, module: Module, params: MeshParams, planes: int) -> np.ndarray:
+    out = np.empty(planes, np.float64)
+    check(lib().s2m_cost_probe(ctx._h, module._h, ctypes.byref(params), planes, out.ctypes.data))
+    return out

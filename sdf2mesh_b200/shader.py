@@ -1,0 +1,113 @@
+"""Sdf3DShader -- host-side mirror of /root/reference/src/shader.rs:35-225.
+
+Same constructor names, argument meaning and error behaviour as the reference; the only change is
+what `create_shader_module` returns: a CUDA module (front-end -> CUDA C++ -> NVRTC for sm_100a)
+instead of a wgpu::ShaderModule.
+"""
+import ctypes
+
+from . import _capi
+from ._capi import check, lib
+
+
+class WgslShaderCode:
+    """String-level WGSL helpers (/root/reference/src/shadertoy.rs:196-249)."""
+
+    def __init__(self, text: str):
+        self.text = text
+
+    @classmethod
+    def from_glsl(cls, glsl: str) -> "WgslShaderCode":
+        return cls(convert_glsl_to_wgsl(glsl))
+
+    def remove_function(self, function_name: str) -> None:
+        out = ctypes.c_void_p()
+        check(lib().s2m_wgsl_remove_function(self.text.encode(), function_name.encode(), ctypes.byref(out)))
+        self.text = _capi.take_string(out)
+
+    def has_function(self, function_name: str) -> bool:
+        found = ctypes.c_int()
+        check(lib().s2m_wgsl_has_function(self.text.encode(), function_name.encode(), ctypes.byref(found)))
+        return bool(found.value)
+
+    def rename_function(self, old: str, new: str) -> None:
+        out = ctypes.c_void_p()
+        check(lib().s2m_wgsl_rename_function(self.text.encode(), old.encode(), new.encode(), ctypes.byref(out)))
+        self.text = _capi.take_string(out)
+
+    def remove_line(self, line: str) -> None:
+        self.text = "".join(l + "\n" for l in self.text.splitlines() if l.strip() != line.strip())
+
+    def add_line(self, line: str) -> None:
+        self.text += line + "\n"
+
+    def __str__(self):
+        return self.text
+
+
+def convert_glsl_to_wgsl(glsl: str) -> str:
+    """shadertoy.rs:169 convert_glsl_to_wgsl."""
+    out = ctypes.c_void_p()
+    check(lib().s2m_glsl_to_wgsl(glsl.encode(), ctypes.byref(out)))
+    return _capi.take_string(out)
+
+
+class Sdf3DShader:
+    def __init__(self, handle=None):
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                lib().s2m_shader_free(self._h)
+            except Exception:
+                pass
+            self._h = None
+
+    # --- constructors -------------------------------------------------------------------
+    @classmethod
+    def from_path(cls, path) -> "Sdf3DShader":
+        """shader.rs:44.  Like the reference this never raises on IO errors (see .log)."""
+        h = ctypes.c_void_p()
+        check(lib().s2m_shader_from_path(str(path).encode(), ctypes.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_glsl_fragment_shader(cls, path, sdf: str = "sdf") -> "Sdf3DShader":
+        """shader.rs:73.  Raises S2mError(PARSE | VALIDATION | MISSING_SDF | SHADER)."""
+        h = ctypes.c_void_p()
+        check(lib().s2m_shader_from_glsl_fragment_shader(str(path).encode(), sdf.encode(), ctypes.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_source(cls, text: str, kind: int = _capi.SRC_SDF3D, sdf: str = "sdf", include_dir=None) -> "Sdf3DShader":
+        h = ctypes.c_void_p()
+        raw = text.encode()
+        check(lib().s2m_shader_from_source(raw, len(raw), kind, sdf.encode(),
+                                           None if include_dir is None else str(include_dir).encode(), ctypes.byref(h)))
+        return cls(h)
+
+    # --- reference API ------------------------------------------------------------------
+    def add_to_source(self, source: str) -> None:
+        check(lib().s2m_shader_add_to_source(self._h, source.encode()))
+
+    def write_to_file(self, path) -> None:
+        check(lib().s2m_shader_write_to_file(self._h, str(path).encode()))
+
+    @property
+    def source(self) -> str:
+        return lib().s2m_shader_source(self._h).decode("utf-8", "replace")
+
+    @property
+    def log(self) -> str:
+        return lib().s2m_shader_log(self._h).decode("utf-8", "replace")
+
+    def lower_to_cuda(self) -> str:
+        out = ctypes.c_void_p()
+        check(lib().s2m_shader_lower_to_cuda(self._h, ctypes.byref(out)))
+        return _capi.take_string(out)
+
+    def create_shader_module(self, ctx=None, flags: int = 0):
+        """shader.rs:220.  ctx=None compiles to a cubin without loading it (no GPU needed)."""
+        from .engine import Module
+        return Module(self, ctx, flags)

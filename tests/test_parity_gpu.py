@@ -1,0 +1,215 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden digests.
+
+Bar: bit-exact keys (active cell set + order), sign nibbles, quad connectivity and invalid-quad
+count; vertex positions and normals bit-exact as well (NaN == NaN), which is stricter than the
+1e-4 voxel tolerance north_star asks for.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import sdf2mesh_b200 as s2m
+from tests.conftest import ROOT, load_example_shader
+from tests.support.digest import f32_equal, mesh_digests
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "digests.json")))
+_modules = {}
+
+
+def module_for(ctx, name):
+    if name not in _modules:
+        _modules[name] = load_example_shader(name).create_shader_module(ctx)
+    return _modules[name]
+
+
+def assert_same(d, o, what=""):
+    assert len(d.keys) == len(o.keys), f"{what}: vertex count {len(d.keys)} vs oracle {len(o.keys)}"
+    assert np.array_equal(d.keys, o.keys), f"{what}: active cell set / order differs"
+    assert np.array_equal(d.nibbles, o.nibbles), f"{what}: sign nibbles differ"
+    assert d.n_invalid_quads == o.n_invalid_quads, f"{what}: invalid quads {d.n_invalid_quads} vs {o.n_invalid_quads}"
+    assert np.array_equal(d.quads, o.quads), f"{what}: quad connectivity differs"
+    eq = f32_equal(d.positions, o.positions)
+    assert eq.all(), f"{what}: {np.count_nonzero(~eq)} position components differ"
+    eq = f32_equal(d.normals, o.normals)
+    assert eq.all(), f"{what}: {np.count_nonzero(~eq)} normal components differ"
+
+
+CASES = [("torus", 32, 2.0), ("torus", 128, 2.0), ("martin_cube", 64, 2.0), ("martin_cube", 128, 2.0),
+         ("p_key", 64, 2.0), ("p_key", 128, 20.0), ("mandelbulb", 64, 5.0), ("mandelbulb", 128, 5.0)]
+
+
+@pytest.mark.parametrize("name,res,bounds", CASES)
+def test_mesh_matches_oracle(ctx, name, res, bounds):
+    p, _ = s2m.params_from_cli(res, bounds)
+    r = s2m.mesh_run(ctx, module_for(ctx, name), p)
+    o = oracle.mesh_run(name, res, bounds)
+    try:
+        assert_same(r.data(), o, f"{name} {res}^3")
+    finally:
+        r.free()
+        o.free()
+
+
+@pytest.mark.parametrize("key", sorted(GOLDEN))
+def test_mesh_matches_golden_digest(ctx, key):
+    name, r_, b_, f_ = key.rsplit("_", 3)
+    if name == "naga_sphere":
+        pytest.skip("covered by test_frontend_gpu")
+    res, bounds, flags = int(r_[1:]), float(b_[1:]), int(f_[1:])
+    p, _ = s2m.params_from_cli(res, bounds, flags=s2m.MESH_ALL_SLICES if flags & 1 else 0)
+    r = s2m.mesh_run(ctx, module_for(ctx, name), p)
+    d = r.data()
+    got = mesh_digests(d.positions, d.normals, d.keys, d.nibbles, d.quads, d.n_invalid_quads)
+    r.free()
+    assert got == GOLDEN[key]
+
+
+def test_golden_npz_fixture(ctx):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "torus_r32_b2.npz"))
+    p, _ = s2m.params_from_cli(32, 2.0)
+    r = s2m.mesh_run(ctx, module_for(ctx, "torus"), p)
+    d = r.data()
+    assert np.array_equal(d.keys, g["keys"]) and np.array_equal(d.quads, g["quads"]) and np.array_equal(d.nibbles, g["nibbles"])
+    assert f32_equal(d.positions, g["positions"]).all() and f32_equal(d.normals, g["normals"]).all()
+    r.free()
+
+
+@pytest.mark.parametrize("name,bounds", [("torus", 2.0), ("martin_cube", 2.5), ("p_key", 20.0), ("mandelbulb", 5.0)])
+def test_sdf_values_bit_exact(ctx, name, bounds):
+    """device SDF == hand-transcribed oracle SDF, bit for bit, on random points"""
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(-bounds / 2, bounds / 2, (300000, 3)).astype(np.float32)
+    dev = module_for(ctx, name).eval_points(pts)
+    ref = oracle.eval_points(name, pts)
+    eq = f32_equal(dev, ref)
+    assert eq.all(), f"{np.count_nonzero(~eq)} of {len(pts)} values differ"
+
+
+def test_slab_plane_matches_oracle(ctx):
+    """K1: corner values at the variant-A coordinates fl(bmin + fl(size*j))"""
+    res, bounds = 100, 2.0  # not a power of two: exercises the padded pitch
+    bmin, bmax = oracle.cube_bounds(bounds)
+    p = s2m.make_params(res, bmin, bmax)
+    size = (np.float32(bmax[0]) - np.float32(bmin[0])) / np.float32(res - 1)
+    coords = (np.float32(bmin[0]) + size * np.arange(res + 1, dtype=np.float32)).astype(np.float32)
+    for plane in (0, 37, res):
+        got = s2m.debug_slab_plane(ctx, module_for(ctx, "torus"), p, plane)
+        X, Y = np.meshgrid(coords, coords)
+        pts = np.stack([X, Y, np.full_like(X, coords[plane])], -1).reshape(-1, 3)
+        ref = oracle.eval_points("torus", pts).reshape(res + 1, res + 1)
+        assert f32_equal(got, ref).all()
+
+
+def test_exact_dense_mode_equals_default(ctx):
+    """reference-cost mode (every cell evaluated with the reference's 8 corners) == candidate mode"""
+    for name, res, bounds in [("torus", 48, 2.0), ("mandelbulb", 64, 5.0)]:
+        p, _ = s2m.params_from_cli(res, bounds)
+        a = s2m.mesh_run(ctx, module_for(ctx, name), p)
+        p.flags = s2m.MESH_EXACT_DENSE
+        b = s2m.mesh_run(ctx, module_for(ctx, name), p)
+        da, db = a.data(), b.data()
+        n = p.dims[0]  # the CLI rounds the resolution up to a power of two (main.rs:142-148)
+        assert db.n_candidates == n * n * (n - 1)
+        assert np.array_equal(da.keys, db.keys) and np.array_equal(da.quads, db.quads)
+        assert f32_equal(da.positions, db.positions).all()
+        a.free()
+        b.free()
+
+
+def test_all_slices_flag(ctx):
+    p, _ = s2m.params_from_cli(64, 2.0, flags=s2m.MESH_ALL_SLICES)
+    r = s2m.mesh_run(ctx, module_for(ctx, "torus"), p)
+    o = oracle.mesh_run("torus", 64, 2.0, flags=oracle.FLAG_ALL_SLICES)
+    assert_same(r.data(), o, "torus all-slices")
+    r.free()
+    o.free()
+
+
+def test_non_cubic_grid_and_small_chunks(ctx):
+    """dims differ per axis, resolution not a multiple of 32, slab forced into many z-chunks"""
+    dims = (70, 45, 33)
+    bmin = np.array([-1.0, -0.6, -0.5], np.float32)
+    bmax = np.array([1.0, 0.7, 0.5], np.float32)
+    o = oracle.mesh_run("torus", dims, bmin=bmin, bmax=bmax)
+    for budget in (0, 71 * 46 * 4 * 3 + 4096):  # default, and ~3 planes per chunk
+        p = s2m.make_params(dims, bmin, bmax, slab_budget_bytes=budget)
+        r = s2m.mesh_run(ctx, module_for(ctx, "torus"), p)
+        d = r.data()
+        if budget:
+            assert d.timings["chunks"] > 4
+        assert_same(d, o, f"non-cubic budget={budget}")
+        r.free()
+    o.free()
+
+
+def test_empty_and_degenerate(ctx):
+    """no surface inside the box -> empty mesh; tiny grid works"""
+    p = s2m.make_params(16, [5, 5, 5], [6, 6, 6])
+    r = s2m.mesh_run(ctx, module_for(ctx, "torus"), p)
+    d = r.data()
+    assert len(d.keys) == 0 and len(d.quads) == 0 and d.n_invalid_quads == 0
+    r.free()
+    p, _ = s2m.params_from_cli(2, 2.0)
+    r = s2m.mesh_run(ctx, module_for(ctx, "torus"), p)
+    o = oracle.mesh_run("torus", 2, 2.0)
+    assert_same(r.data(), o, "2^3")
+    r.free()
+    o.free()
+
+
+@pytest.mark.parametrize("name,res,bounds,splits", [("torus", 64, 2.0, [0, 20, 31, 50, 63]), ("mandelbulb", 96, 5.0, [0, 48, 95])])
+def test_z_slabs_reassemble(ctx, name, res, bounds, splits):
+    """z-slab decomposition (what N ranks do): per-slab results with halo recompute + global
+    vertex offsets concatenate to exactly the single-slab result"""
+    p, _ = s2m.params_from_cli(res, bounds)
+    full = s2m.mesh_run(ctx, module_for(ctx, name), p)
+    df = full.data()
+    keys, quads, pos, ninv = [], [], [], 0
+    base = 0
+    for zb, ze in zip(splits[:-1], splits[1:]):
+        p.z_begin, p.z_end = zb, ze
+        r = s2m.mesh_begin(ctx, module_for(ctx, name), p)
+        n_own = r.info().n_vertices
+        r.finish(base)
+        d = r.data()
+        keys.append(d.keys.copy()); quads.append(d.quads.copy()); pos.append(d.positions.copy())
+        ninv += d.n_invalid_quads
+        base += n_own
+        r.free()
+    assert np.array_equal(np.concatenate(keys), df.keys)
+    assert np.array_equal(np.concatenate(quads), df.quads)
+    assert f32_equal(np.concatenate(pos), df.positions).all()
+    assert ninv == df.n_invalid_quads
+    full.free()
+
+
+def test_bigger_sizes_properties(ctx):
+    """size-independent properties at a size the oracle would not finish quickly: sorted unique keys,
+    quads reference existing vertices, every quad's 4 cells are the right neighbours, determinism"""
+    p, _ = s2m.params_from_cli(512, 5.0)
+    m = module_for(ctx, "mandelbulb")
+    r = s2m.mesh_run(ctx, m, p)
+    d = r.data()
+    k = d.keys
+    assert len(k) > 400000
+    assert np.all(k[1:] > k[:-1])
+    q = d.quads
+    assert q.max() < len(k)
+    x = (k & 0xFFFF).astype(np.int64); y = ((k >> 16) & 0xFFFF).astype(np.int64); z = (k >> 32).astype(np.int64)
+    cx, cy, cz = x[q], y[q], z[q]
+    # the four cells of a quad span a 2x2x1 block
+    span = (cx.max(1) - cx.min(1)) + (cy.max(1) - cy.min(1)) + (cz.max(1) - cz.min(1))
+    assert np.all(span == 2)
+    r2 = s2m.mesh_run(ctx, m, p)
+    d2 = r2.data()
+    assert np.array_equal(d2.keys, k) and np.array_equal(d2.quads, q) and f32_equal(d2.positions, d.positions).all()
+    key = "mandelbulb_r512_b5_f0"
+    if key in GOLDEN:
+        assert mesh_digests(d.positions, d.normals, d.keys, d.nibbles, d.quads, d.n_invalid_quads) == GOLDEN[key]
+    r.free()
+    r2.free()
