@@ -63,11 +63,12 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+            threading.Thread(target=lambda: [self.lines.append((time.perf_counter(), l)) for l in self.proc.stdout], daemon=True).start()
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_from=0.0, t_to=float("inf")):
+        """summarise the samples taken inside [t_from, t_to] (perf_counter clock)"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -77,7 +78,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for ts, l in self.lines:
+            if ts < t_from or ts > t_to + 0.15:
+                continue
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -201,37 +204,44 @@ def main():
     def step():
         r, base, counts = dist_util.mesh_slab(ctx, module, params, zb, ze, rank=rank, device=dev)
         i = r.info()
-        out = (i.n_vertices, i.n_quads, i.n_invalid_quads, {k[0]: getattr(i.timings, k[0]) for k in s2m._capi.Timings._fields_}, sum(counts))
+        out = (i.n_vertices, i.n_quads, i.n_invalid_quads, {k[0]: getattr(i.timings, k[0]) for k in s2m._capi.Timings._fields_}, sum(counts), i.n_candidates)
         r.free()
         return out
 
+    # nvidia-smi is started BEFORE the warm-up: its start-up stalls the driver for tens of ms
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.5)
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     t_start = time.perf_counter()
     stats = []
     for _ in range(args.steps):
         stats.append(step())
     barrier()
-    wall = time.perf_counter() - t_start
-    clocks = sampler.stop()
+    t_end = time.perf_counter()
+    wall = t_end - t_start
+    if wall < 0.35:
+        time.sleep(0.35 - wall)  # let at least a couple of 100 ms samples land
+    clocks = sampler.stop(t_start, t_end)
 
     dev_ms = sum(s[3]["device_ms"] for s in stats)
     tot_ms = sum(s[3]["total_ms"] for s in stats)
     launches = sum(s[3]["launches"] for s in stats)
     nv, nq, ninv = stats[-1][0], stats[-1][1], stats[-1][2]
+    ncand = stats[-1][5]
     d2h_bytes = nv * 33 + nq * 32
     per = {k: sum(s[3][k] for s in stats) / args.steps for k in ("k1_slab_ms", "k2_classify_ms", "k3_compact_ms", "k4_vertices_ms", "k4_quads_ms", "d2h_ms")}
     if world > 1:
-        t = torch.tensor([wall, dev_ms, tot_ms, float(nv), float(nq), float(ninv), float(launches), float(d2h_bytes)] + [per[k] for k in sorted(per)],
+        t = torch.tensor([wall, dev_ms, tot_ms, float(nv), float(nq), float(ninv), float(launches), float(d2h_bytes), float(ncand)] + [per[k] for k in sorted(per)],
                          dtype=torch.float64, device=dev)
         mx = t.clone(); torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
         sm = t.clone(); torch.distributed.all_reduce(sm, op=torch.distributed.ReduceOp.SUM)
         wall, dev_ms, tot_ms = mx[0].item(), mx[1].item(), mx[2].item()
         nv, nq, ninv, launches, d2h_bytes = int(sm[3].item()), int(sm[4].item()), int(sm[5].item()), int(sm[6].item()), int(sm[7].item())
-        per = {k: mx[8 + i].item() for i, k in enumerate(sorted(per))}
+        ncand = int(sm[8].item())
+        per = {k: mx[9 + i].item() for i, k in enumerate(sorted(per))}
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
@@ -256,7 +266,7 @@ def main():
         "config": {"workload": wl, "sdf": f, "resolution": res, "bounds": bounds, "mode": "faithful (slices 0..R-2)" if not (args.flags & 1) else "all slices",
                    "parallelism": f"z-slabs x{world}" + ("" if world == 1 else (" equal" if args.no_balance else " cost-balanced")), "z_boundaries": bounds_z,
                    "l2": "no L2 flush needed: the corner slab alone is %.1f GB per step, far larger than the 126 MB L2" % (k1_bytes / 1e9)},
-        "mesh": {"vertices": nv, "quads": nq, "invalid_quads": ninv, "triangles": 2 * nq, "Mtriangles_per_s": 2 * nq * args.steps / wall / 1e6},
+        "mesh": {"candidates": ncand, "vertices": nv, "quads": nq, "invalid_quads": ninv, "triangles": 2 * nq, "Mtriangles_per_s": 2 * nq * args.steps / wall / 1e6},
         "e2e": {"value": e2e, "unit": "Gvoxel/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": launches,
         "clocks": clocks,

@@ -120,6 +120,18 @@ struct PinnedBlock { void* p; size_t cap; bool used; };
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+// S2M_TRACE=1: host-clock timestamps of the pipeline phases on stderr
+struct Trace {
+  bool on;
+  double t0, last;
+  Trace() : on(getenv("S2M_TRACE") != nullptr), t0(now_ms()), last(t0) {}
+  void mark(const char* what) {
+    if (!on) return;
+    const double t = now_ms();
+    fprintf(stderr, "[s2m trace] %-28s +%8.3f ms (at %8.3f)\n", what, t - last, t - t0);
+    last = t;
+  }
+};
 }  // namespace
 
 // ------------------------------------------------------------------ ctx
@@ -408,6 +420,7 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
   const float min_size = std::min(g.size[0], std::min(g.size[1], g.size[2]));
   const float tau = (p->tau_voxels > 0.0f ? p->tau_voxels : 0.5f) * min_size;
 
+  Trace tr;
   c->busy = true;
   struct BusyGuard { s2m_ctx* c; bool keep = false; ~BusyGuard() { if (!keep) c->busy = false; } } guard{c};
   r->wall0 = now_ms();
@@ -425,14 +438,21 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
   }
   // ---- K1 + K2 over z-chunks of the slab
   if (r->nz > 0 && !(p->flags & S2M_MESH_EXACT_DENSE)) {
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    tr.mark("setup");
+    // No cudaMemGetInfo here: it costs 0.1-3.5 ms per call on a B200 and the answer only matters
+    // the first time.  Default budget: a third of the device (<= 64 GiB), halved on OOM.
     const unsigned long long plane_bytes = g.plane_stride * 4ull;
     unsigned long long budget = p->slab_budget_bytes ? p->slab_budget_bytes
-                                                     : std::min<unsigned long long>((unsigned long long)(free_b + c->slab.cap) / 2, 64ull << 30);
-    unsigned long long max_planes = std::max<unsigned long long>(2, budget / plane_bytes);
-    const uint32_t zc = (uint32_t)std::min<unsigned long long>(r->nz, max_planes - 1);
-    if ((st = c->slab.ensure((unsigned long long)(zc + 1) * plane_bytes))) return st;
+                                                     : std::min<unsigned long long>((unsigned long long)c->prop.totalGlobalMem / 3, 64ull << 30);
+    uint32_t zc = 0;
+    for (;;) {
+      unsigned long long max_planes = std::max<unsigned long long>(2, budget / plane_bytes);
+      zc = (uint32_t)std::min<unsigned long long>(r->nz, max_planes - 1);
+      st = c->slab.ensure((unsigned long long)(zc + 1) * plane_bytes);
+      if (st == S2M_OK) break;
+      if (st != S2M_ERR_OOM || zc <= 1) return st;
+      budget = (unsigned long long)(zc + 1) * plane_bytes / 2;
+    }
     for (uint32_t z0 = 0; z0 < r->nz; z0 += zc) {
       const uint32_t nzc = std::min(zc, r->nz - z0);
       GridDev gd = g;
@@ -469,11 +489,13 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
     CUDA_TRY(cudaEventRecord(c->ev[2], s));
   }
   CUDA_TRY(cudaEventRecord(c->ev[3], s));
+  tr.mark("K1+K2 launched");
   r->t.chunks = chunks;
   // ---- sync #1: candidate count sizes everything downstream
   CUDA_TRY(cudaMemcpyAsync(c->h_counters, d_cnt, 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   r->n_cand = c->h_counters[0];
+  tr.mark("sync #1 (candidates)");
   if (r->n_cand >= 0xffffffffull) return fail(S2M_ERR_UNSUPPORTED, "more than 2^32-1 candidate cells in one slab; split it with z_begin/z_end");
 
   const unsigned k3_tiles = r->nz ? s2m_k3_tiles(n_words) : 0;
@@ -514,12 +536,14 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
     ++launches;
   }
   CUDA_TRY(cudaEventRecord(c->ev[6], s));
+  tr.mark("K3+K4a launched");
   // ---- sync #2: vertex counts
   CUDA_TRY(cudaMemcpyAsync(c->h_counters, d_cnt, C_COUNT * 8, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   r->n_vert_total = c->h_counters[C_NVERT];
   r->n_halo = c->h_counters[C_NHALO];
   const uint64_t n_own = r->n_vert_total - r->n_halo;
+  tr.mark("sync #2 (vertices)");
   // ---- vertices -> pinned host (copy stream; overlaps the quad kernel)
   r->h_pos = (float*)c->lease_pinned(n_own * 12);
   r->h_nrm = (float*)c->lease_pinned(n_own * 12);
@@ -543,6 +567,7 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
     CUDA_TRY(cudaMemcpyAsync(r->h_cand, c->cand_key.p, r->n_cand * 8, cudaMemcpyDeviceToHost, c->copy_stream));
   CUDA_TRY(cudaEventRecord(c->ev[8], c->copy_stream));
   r->t.launches = launches;
+  tr.mark("vertex copies queued");
   guard.keep = true;
   *out = r.release();
   return S2M_OK;
@@ -552,6 +577,7 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   if (!r || !r->ctx) return fail(S2M_ERR_INVALID_ARG, "s2m_mesh_finish: NULL result");
   if (r->finished) return fail(S2M_ERR_STATE, "s2m_mesh_finish called twice");
   s2m_ctx* c = r->ctx;
+  Trace tr;
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   unsigned long long* d_cnt = c->counters.as<unsigned long long>();
@@ -581,6 +607,7 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   CUDA_TRY(cudaStreamSynchronize(s));
   r->n_quads = c->h_counters[C_NQUAD];
   r->n_invalid = c->h_counters[C_NINVALID];
+  tr.mark("finish: sync #3 (quads)");
   r->h_quads = (uint64_t*)c->lease_pinned(r->n_quads * 32);
   if (!r->h_quads) return fail(S2M_ERR_OOM, "cudaHostAlloc for quad output failed");
   if (r->n_quads) CUDA_TRY(cudaMemcpyAsync(r->h_quads, c->quads.p, r->n_quads * 32, cudaMemcpyDeviceToHost, s));
@@ -588,6 +615,7 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   CUDA_TRY(cudaEventRecord(c->ev[11], s));
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+  tr.mark("finish: copies done");
   r->t.host_wall_ms = now_ms() - r->wall0;
   auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
   // single-chunk runs time K1 and K2 separately; chunked runs report their sum under k1 (interleaved)

@@ -42,6 +42,11 @@ class WgslParser : public ParserBase {
     if (s == "bool") { *sk = Sk::Bool; return true; }
     return false;
   }
+  // closes a template list; splits a `>>` token in two (`ptr<function, vec4<f32>>`)
+  void expect_close_angle() {
+    if (is_punct(">>")) { toks[pos].text = ">"; return; }
+    expect(">");
+  }
   // Parses a type.  *infer is set when the scalar kind was left to inference (`vec3` without <T>).
   Type parse_type(bool* infer = nullptr, bool* is_ptr = nullptr) {
     if (infer) *infer = false;
@@ -59,7 +64,7 @@ class WgslParser : public ParserBase {
       if (accept("<")) {
         const std::string el = expect_ident("a scalar type");
         if (!scalar_kind(el, &sk)) perr("unknown vector component type " + el);
-        expect(">");
+        expect_close_angle();
         return Type::vec(sk, n);
       }
       if (infer) { *infer = true; return Type::vec(Sk::F32, n); }
@@ -71,7 +76,7 @@ class WgslParser : public ParserBase {
       expect(",");
       Type t = parse_type();
       if (accept(",")) expect_ident("an access mode");
-      expect(">");
+      expect_close_angle();
       if (!is_ptr) b.unsupported("pointer types outside of function parameters");
       *is_ptr = true;
       return t;

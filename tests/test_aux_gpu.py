@@ -1,0 +1,115 @@
+"""GPU tests for the pieces around the four kernels: device math == host math bit for bit, writers
+byte-identical to the oracle's restatement of mesh.rs, candidate classification, cost probe."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import sdf2mesh_b200 as s2m
+from tests.conftest import ROOT, load_example_shader
+from tests.support.digest import f32_equal
+
+pytestmark = pytest.mark.gpu
+
+# sdf3d(p): p.z selects the function, p.x / p.y are the operands -- runs s2m_math.h on the device
+MATH_CUDA = open(os.path.join(ROOT, "tests", "support", "math_dispatch.h")).read().replace('#include "s2m_math.h"', "").replace("#pragma once", "") + """
+S2M_HD float sdf3d(vec3 p) {
+  const int fn = (int)p.z;
+  return fn >= 100 ? s2m_dispatch2(fn, p.x, p.y) : s2m_dispatch1(fn, p.x);
+}
+"""
+
+
+@pytest.fixture(scope="module")
+def host_math(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("math") / "libmath_host.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-I", os.path.join(ROOT, "sdf2mesh_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "support", "math_host.cpp"), "-o", so])
+    return ctypes.CDLL(so)
+
+
+def test_device_math_is_bit_identical_to_host_math(ctx, host_math):
+    """the premise of bit-exact parity: every pinned function gives the same bits on sm_100a and x86"""
+    mod = s2m.Sdf3DShader.from_source(MATH_CUDA, s2m.SRC_CUDA).create_shader_module(ctx)
+    rng = np.random.default_rng(11)
+    n = 200_000
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, -1.0, 0.5, 2.0, 1e-45, -1e-45, 1.17549435e-38, 3.4028235e38, 88.72, 88.73,
+                        -103.9, -104.1, 105615.0, 105616.0, 1e9, 1e30, 0.70710678, 1.41421356], np.float32)
+    xs = np.concatenate([special, rng.uniform(-30, 30, n), 10 ** rng.uniform(-45, 38, n), -(10 ** rng.uniform(-45, 38, n)),
+                         rng.uniform(-1, 1, n), rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32)]).astype(np.float32)
+    for fn in range(19):
+        pts = np.stack([xs, np.zeros_like(xs), np.full_like(xs, fn)], 1)
+        dev = mod.eval_points(pts)
+        host = np.empty_like(xs)
+        host_math.s2m_host_map1(fn, xs.ctypes.data_as(ctypes.c_void_p), host.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(xs.size))
+        eq = f32_equal(dev, host)
+        assert eq.all(), f"fn {fn}: {np.count_nonzero(~eq)} mismatches, first at x={xs[~eq][0]!r}: dev={dev[~eq][0]!r} host={host[~eq][0]!r}"
+    a = np.concatenate([np.repeat(special, len(special)), rng.uniform(-4, 4, n), 10 ** rng.uniform(-20, 20, n)]).astype(np.float32)
+    b = np.concatenate([np.tile(special, len(special)), rng.uniform(-10, 10, n), rng.uniform(-3, 3, n)]).astype(np.float32)
+    for fn in range(100, 108):
+        pts = np.stack([a, b, np.full_like(a, fn)], 1)
+        dev = mod.eval_points(pts)
+        host = np.empty_like(a)
+        host_math.s2m_host_map2(fn, a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p), host.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(a.size))
+        eq = f32_equal(dev, host)
+        assert eq.all(), f"fn {fn}: {np.count_nonzero(~eq)} mismatches, first at ({a[~eq][0]!r}, {b[~eq][0]!r}): dev={dev[~eq][0]!r} host={host[~eq][0]!r}"
+
+
+@pytest.mark.parametrize("name,res,bounds", [("torus", 32, 2.0), ("mandelbulb", 64, 5.0)])
+def test_writers_byte_identical(ctx, tmp_path, name, res, bounds):
+    """ASCII STL / PLY from the library == the oracle's restatement of mesh.rs, byte for byte"""
+    p, _ = s2m.params_from_cli(res, bounds)
+    r = s2m.mesh_run(ctx, load_example_shader(name).create_shader_module(ctx), p)
+    o = oracle.mesh_run(name, res, bounds)
+    for ext in ("stl", "PLY"):
+        mine, ref = tmp_path / f"mine.{ext}", tmp_path / f"ref.{ext}"
+        r.write_mesh(mine)
+        (o.write_stl if ext == "stl" else o.write_ply)(ref)
+        assert mine.read_bytes() == ref.read_bytes()
+    r.write_mesh(tmp_path / "mesh.xyz")  # unknown extension: logged, not an error, no file (mesh.rs:193)
+    assert not (tmp_path / "mesh.xyz").exists()
+    r.write_stl_binary(tmp_path / "b.stl")
+    raw = (tmp_path / "b.stl").read_bytes()
+    nq = len(r.data().quads)
+    assert len(raw) == 84 + 50 * 2 * nq and int.from_bytes(raw[80:84], "little") == 2 * nq
+    tri0 = np.frombuffer(raw[84:84 + 48], np.float32).reshape(4, 3)
+    q0 = r.data().quads[0]
+    assert f32_equal(tri0[1], r.data().positions[q0[2]]).all() and f32_equal(tri0[3], r.data().positions[q0[0]]).all()
+    r.free()
+    o.free()
+
+
+def test_candidates_are_a_superset_and_match_numpy(ctx):
+    """K2+K3: candidate set == cells whose 8 slab corners are not all > tau / all < -tau, in linear order"""
+    res, bounds = 40, 2.0
+    bmin, bmax = oracle.cube_bounds(bounds)
+    p = s2m.make_params(res, bmin, bmax, flags=s2m.MESH_KEEP_CANDIDATES)
+    mod = load_example_shader("torus").create_shader_module(ctx)
+    r = s2m.mesh_run(ctx, mod, p)
+    d = r.data()
+    slab = np.stack([s2m.debug_slab_plane(ctx, mod, p, z) for z in range(res + 1)])  # [z][y][x]
+    size = (np.float32(bmax[0]) - np.float32(bmin[0])) / np.float32(res - 1)
+    tau = np.float32(0.5) * size
+    P, N = slab > tau, slab < -tau
+
+    def all8(m):
+        return (m[:-1, :-1, :-1] & m[:-1, :-1, 1:] & m[:-1, 1:, :-1] & m[:-1, 1:, 1:] & m[1:, :-1, :-1] & m[1:, :-1, 1:] & m[1:, 1:, :-1] & m[1:, 1:, 1:])
+
+    cand = ~(all8(P) | all8(N))
+    cand = cand[:res - 1]  # faithful mode scans slices 0..res-2
+    z, y, x = np.nonzero(cand)
+    want = x.astype(np.uint64) | (y.astype(np.uint64) << np.uint64(16)) | (z.astype(np.uint64) << np.uint64(32))
+    assert np.array_equal(d.candidates, want)
+    vert = (d.keys - (np.uint64(1) << np.uint64(32)))
+    assert np.isin(vert, d.candidates).all()
+    r.free()
+
+
+def test_cost_probe(ctx):
+    p, _ = s2m.params_from_cli(256, 5.0)
+    cost = s2m.cost_probe(ctx, load_example_shader("mandelbulb").create_shader_module(ctx), p, 32)
+    assert len(cost) == 32 and np.all(cost > 0)
+    assert cost[12:20].mean() > 2 * cost[[0, 1, 30, 31]].mean(), "the mandelbulb's cost is concentrated around z = 0"

@@ -1,0 +1,82 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol include/*.h declares,
+fails loudly (no CPU fallback) when asked for a device that is not there, and can still JIT every
+example SDF to an sm_100a cubin."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import sdf2mesh_b200 as s2m
+from sdf2mesh_b200 import _capi
+from tests.conftest import EXAMPLE_INPUTS, ROOT, load_example_shader
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "sdf2mesh_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(s2m_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(built):
+    names = header_functions()
+    assert len(names) >= 30
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/sdf2mesh_b200.h but not exported"
+        assert n in _capi.SYMBOLS, f"{n} has no ctypes prototype in sdf2mesh_b200/_capi.py"
+    assert sorted(_capi.SYMBOLS) == names, "ctypes table and header disagree"
+
+
+def test_struct_layouts_match_header(built):
+    """compile a tiny C program against the header and compare sizeof/offsetof with ctypes"""
+    src = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "sdf2mesh_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(s2m_mesh_params), offsetof(s2m_mesh_params, dims), offsetof(s2m_mesh_params, slab_budget_bytes),
+         sizeof(s2m_timings), sizeof(s2m_result_info), offsetof(s2m_result_info, timings));
+  return 0;
+}'''
+    import tempfile
+    d = tempfile.mkdtemp()
+    open(os.path.join(d, "t.c"), "w").write(src)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+    got = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    P, T, R = _capi.MeshParams, _capi.Timings, _capi.ResultInfo
+    assert got == [ctypes.sizeof(P), P.dims.offset, P.slab_budget_bytes.offset, ctypes.sizeof(T), ctypes.sizeof(R), R.timings.offset]
+
+
+def test_no_gpu_means_loud_failure(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Context(0)
+    assert e.value.kind == "NO_DEVICE" and "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("name", sorted(EXAMPLE_INPUTS))
+def test_examples_jit_to_sm100a_cubin(built, name, tmp_path):
+    m = load_example_shader(name).create_shader_module(None)  # NVRTC needs no device
+    assert m.cubin_size > 10000
+    data, size = ctypes.c_void_p(), ctypes.c_size_t()
+    _capi.check(_capi.lib().s2m_module_cubin(m._h, ctypes.byref(data), ctypes.byref(size)))
+    cubin = tmp_path / "m.cubin"
+    cubin.write_bytes(ctypes.string_at(data, size.value))
+    out = subprocess.run(["cuobjdump", "-elf", str(cubin)], capture_output=True, text=True).stdout
+    assert "sm_100" in out or "SM100" in out.upper() or "EF_CUDA_SM100" in out
+    for k in ("s2m_k1_slab", "s2m_k4_vertices", "s2m_k_eval"):
+        assert k in out
+
+
+def test_params_from_cli(built):
+    """AppState::from(&Arguments): defaults 256 / 2.0, power-of-two rounding UP (main.rs:141-150)"""
+    p, r = s2m.params_from_cli(None, None)
+    assert list(p.dims) == [256, 256, 256] and not r and list(p.bb_min) == [-1, -1, -1] and list(p.bb_max) == [1, 1, 1]
+    assert abs(p.eps - 1e-4) < 1e-10
+    for res, want in [(128, 128), (100, 128), (129, 256), (3, 4), (2048, 2048), (2049, 4096)]:
+        p, r = s2m.params_from_cli(res, 5.0)
+        assert p.dims[0] == want and r == (res != want) and p.bb_max[2] == 2.5

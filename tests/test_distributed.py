@@ -1,0 +1,64 @@
+"""Host-side multi-GPU logic on CPU: partitioning, count exchange (gloo, world_size 2), offsets."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from sdf2mesh_b200 import distributed as D
+
+
+def test_partition_equal():
+    assert D.partition_slices(2047, 1) == [0, 2047]
+    b = D.partition_slices(2047, 8)
+    assert b[0] == 0 and b[-1] == 2047 and all(x <= y for x, y in zip(b, b[1:]))
+    assert max(y - x for x, y in zip(b, b[1:])) - min(y - x for x, y in zip(b, b[1:])) <= 1
+
+
+def test_partition_cost_weighted():
+    cost = np.ones(128)
+    cost[32:96] = 20.0  # all the work in the middle half
+    b = D.partition_slices(1024, 4, cost)
+    assert b[0] == 0 and b[-1] == 1024 and all(x <= y for x, y in zip(b, b[1:]))
+    widths = [y - x for x, y in zip(b, b[1:])]
+    assert widths[0] > widths[1] and widths[3] > widths[2], "outer slabs must be thicker than inner ones"
+    edges = np.linspace(0, 1024, 129)
+    cum = np.concatenate([[0], np.cumsum(cost)])
+    per = np.diff(np.interp(b, edges, cum))
+    assert per.max() / per.min() < 1.15
+    assert D.partition_slices(10, 4, [0, 0, 0]) == D.partition_slices(10, 4)  # degenerate cost -> equal
+
+
+def test_exclusive_bases_and_slice_count():
+    assert D.exclusive_bases([5, 0, 7]) == [0, 5, 5]
+    assert D.n_scanned_slices(2048, False) == 2047 and D.n_scanned_slices(2048, True) == 2048
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    counts = D.allgather_counts(1000 * (rank + 1) + 7)
+    bounds = D.broadcast_boundaries([0, 300, 511] if rank == 0 else None, world)
+    q.put((rank, counts, D.exclusive_bases(counts)[rank], bounds))
+    dist.destroy_process_group()
+
+
+def test_count_exchange_gloo_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0] == (0, [1007, 2007], 0, [0, 300, 511])
+    assert out[1] == (1, [1007, 2007], 1007, [0, 300, 511])

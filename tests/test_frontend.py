@@ -1,0 +1,324 @@
+"""Front-end tests (no GPU): .sdf3d preprocessing, WGSL / GLSL lowering, WGSL text munging.
+
+Emitted CUDA C++ is compiled with g++ (tests/support/host_eval.py) and evaluated on the CPU; the
+hand-transcribed SDFs in oracle/sdf_examples.h are the independent answer."""
+import os
+import textwrap
+
+import numpy as np
+import pytest
+
+import oracle
+import sdf2mesh_b200 as s2m
+from tests.conftest import EXAMPLES, load_example_shader
+from tests.support import host_eval
+from tests.support.digest import f32_equal
+
+REF_EXAMPLES = "/root/reference/examples"
+RNG = np.random.default_rng(3)
+
+
+def points(bounds, n=100_000):
+    return RNG.uniform(-bounds / 2, bounds / 2, (n, 3)).astype(np.float32)
+
+
+@pytest.mark.parametrize("name,bounds", [("torus", 2.0), ("martin_cube", 2.5), ("p_key", 20.0), ("mandelbulb", 5.0)])
+def test_examples_lower_bit_exact(built, name, bounds):
+    cuda = load_example_shader(name).lower_to_cuda()
+    pts = points(bounds)
+    assert f32_equal(host_eval.eval_points(cuda, pts), oracle.eval_points(name, pts)).all()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="reference checkout not present")
+@pytest.mark.parametrize("name,f,bounds", [("torus", "torus.sdf3d", 2.0), ("martin_cube", "martin_cube.sdf3d", 2.5),
+                                           ("p_key", "p_key.sdf3d", 20.0), ("mandelbulb", "mandelmesh.frag", 5.0)])
+def test_our_examples_equal_reference_examples(built, name, f, bounds):
+    """examples/ holds re-typed equivalents of the reference inputs; same values at every point"""
+    path = os.path.join(REF_EXAMPLES, f)
+    ref = s2m.Sdf3DShader.from_glsl_fragment_shader(path, "sdf") if f.endswith(".frag") else s2m.Sdf3DShader.from_path(path)
+    pts = points(bounds, 50_000)
+    a = host_eval.eval_points(ref.lower_to_cuda(), pts)
+    b = host_eval.eval_points(load_example_shader(name).lower_to_cuda(), pts)
+    assert f32_equal(a, b).all()
+
+
+# --- the reference's own three unit tests (/root/reference/src/shadertoy.rs:354-453), restated -----
+NAGA_WGSL = textwrap.dedent("""\
+    fn mainImage(fragColor: ptr<function, vec4<f32>>, fragCoord: vec2<f32>) {
+        var fragCoord_1: vec2<f32>;
+
+        fragCoord_1 = fragCoord;
+        return;
+    }
+
+    fn main_1() {
+        return;
+    }
+
+    @fragment
+    fn main() {
+        main_1();
+        return;
+    }
+    """)
+
+
+def test_remove_function(built):
+    w = s2m.WgslShaderCode("        \n" + NAGA_WGSL)
+    w.remove_function("fn main_1()")
+    assert "fn mainImage(fragColor" in w.text and "fn main_1()" not in w.text
+    w.remove_function("fn main(")
+    assert "fn mainImage(fragColor" in w.text and "fn main()" not in w.text
+    w.remove_function("fn mainImage(")
+    assert w.text.strip() == "@fragment"
+    with pytest.raises(s2m.S2mError) as e:
+        w.remove_function("fn nope(")
+    assert e.value.kind == "SHADER" and "not found in shader" in str(e.value)
+
+
+def test_rename_function(built):
+    w = s2m.WgslShaderCode("fn normal(p_4: vec3<f32>, epsilon: f32) -> vec3<f32>")
+    w.rename_function("normal", "sdf3d_normal")
+    assert "fn sdf3d_normal(p_4: vec3<f32>, epsilon: f32) -> vec3<f32>" in w.text
+
+
+NAGA_TEST_GLSL = "#version 450 core\n" + """
+        layout(binding=0) uniform vec3      iResolution;           // viewport resolution (in pixels)
+		layout(binding=0) uniform float     iTime;                 // shader playback time (in seconds)
+		layout(binding=0) uniform float     iTimeDelta;            // render time (in seconds)
+		layout(binding=0) uniform int       iFrame;                // shader playback frame
+		layout(binding=0) uniform vec4      iChannelTime;          // channel playback time (in seconds)
+		layout(binding=0) uniform vec4      iMouse;                // mouse pixel coords. xy: current (if MLB down), zw: click
+		layout(binding=0) uniform vec4      iDate;                 // (year, month, day, time in seconds)
+		layout(binding=0) uniform float     iSampleRate;           // sound sample rate (i.e., 44100)
+""" + """
+vec3 c = vec3(0.0, 0.0, 0.0);
+const float r = 1.0;
+float distance_from_sphere(vec3 p, vec3 c, float r)
+{
+    return distance(p, c) - r;
+}
+
+float sdf3d(vec3 p)
+{
+    float sphere_0 = distance_from_sphere(p, c, r);
+
+    // set displacement
+    float displacement = sin(5.0 * p.x) * sin(5.0 * p.y) * sin(5.0 * p.z) * 0.25 * sin(2.f * iTime);
+
+    return sphere_0 + displacement;
+}
+
+vec3 sdf3d_normal(in vec3 p, in float epsilon)
+{
+    const vec3 small_step = vec3(epsilon, 0.0, 0.0);
+
+    float gradient_x = sdf3d(p + small_step.xyy) - sdf3d(p - small_step.xyy);
+    float gradient_y = sdf3d(p + small_step.yxy) - sdf3d(p - small_step.yxy);
+    float gradient_z = sdf3d(p + small_step.yyx) - sdf3d(p - small_step.yyx);
+
+    vec3 normal = vec3(gradient_x, gradient_y, gradient_z);
+
+    return normalize(normal);
+}
+
+void mainImage( out vec4 fragColor, in vec2 fragCoord ) {}
+
+""" + " void main() {}"
+
+
+def test_naga_shader_converts_and_evaluates(built):
+    """the reference's test only checks that conversion succeeds; here the result is also evaluated"""
+    wgsl = s2m.convert_glsl_to_wgsl(NAGA_TEST_GLSL)
+    assert "fn sdf3d(" in wgsl and "fn main_1(" in wgsl and "@fragment" in wgsl and "fn mainImage(" in wgsl
+    w = s2m.WgslShaderCode(wgsl)
+    w.remove_function("fn main_1(")
+    w.remove_function("fn main(")
+    w.remove_line("@fragment")
+    cuda = s2m.Sdf3DShader.from_source(w.text, s2m.SRC_WGSL).lower_to_cuda()
+    pts = points(2.5, 50_000)
+    assert f32_equal(host_eval.eval_points(cuda, pts), oracle.eval_points("naga_sphere", pts)).all()
+
+
+# --- .sdf3d directive semantics (/root/reference/src/shader.rs:159-203) ----------------------------
+def test_use_directives(built, tmp_path):
+    src = 'use sdf3d::*;\nuse nonexistent::module;\n  use "sdf::op";\nfn sdf3d(p: vec3f) -> f32 { return sdf3d_sphere(p, 1.0); }\n'
+    sh = s2m.Sdf3DShader.from_source(src)
+    assert "fn sdf3d_box(" in sh.source and "fn sdf3d_normal(" in sh.source and "fn sdf_op_smooth_union(" in sh.source
+    assert "nonexistent" not in sh.source, "unknown modules are dropped silently (shader.rs:170-180)"
+    assert sh.log.count("INFO ") == 3 and "INFO nonexistent::module" in sh.log
+    assert sh.source.index("fn sdf3d_torus(") < sh.source.index("fn sdf3d_normal("), "sdf3d::* = primitives then normal"
+    # only lines ending in ';' are directives; `used = 1.0;` is swallowed as a `use` line like in the reference
+    sh2 = s2m.Sdf3DShader.from_source("use sdf3d::primitives\nused = 1.0;\nkeep me\n")
+    assert sh2.source == "use sdf3d::primitives\nkeep me\n"
+
+
+def test_include_directive(built, tmp_path):
+    (tmp_path / "lib.wgsl").write_text("fn helper(x: f32) -> f32 { return x * 2.0; }\n")
+    (tmp_path / "main.sdf3d").write_text('include "lib.wgsl";\ninclude "missing.wgsl";\nfn sdf3d(p: vec3f) -> f32 { return helper(p.x); }\n')
+    cwd = os.getcwd()
+    os.chdir(tmp_path)  # includes resolve against the CWD, not the including file (shader.rs:181-191)
+    try:
+        sh = s2m.Sdf3DShader.from_path("main.sdf3d")
+    finally:
+        os.chdir(cwd)
+    assert "fn helper(" in sh.source and 'ERROR Could not include "missing.wgsl"' in sh.log
+    vals = host_eval.eval_points(sh.lower_to_cuda(), np.array([[1.5, 0, 0]], np.float32))
+    assert vals[0] == 3.0
+    # unreadable top-level file: no exception, empty source, logged (shader.rs:44, :197-199)
+    bad = s2m.Sdf3DShader.from_path(str(tmp_path / "nope.sdf3d"))
+    assert bad.source == "" and "ERROR Could not include" in bad.log
+
+
+def test_write_to_file_and_add_to_source(built, tmp_path):
+    sh = s2m.Sdf3DShader.from_path(os.path.join(EXAMPLES, "torus.sdf3d"))
+    before = sh.source
+    sh.write_to_file(tmp_path / "debug.wgsl")  # --debug-wgsl (main.rs:223-225)
+    assert (tmp_path / "debug.wgsl").read_text() == before
+    sh.add_to_source("// tail\n")
+    assert sh.source == before + "// tail\n"
+
+
+# --- errors ------------------------------------------------------------------------------------
+def test_glsl_missing_sdf(built, tmp_path):
+    f = tmp_path / "x.frag"
+    f.write_text("#version 450 core\nfloat other(vec3 p) { return p.x; }\nvoid main() {}\n")
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_glsl_fragment_shader(f, "sdf")
+    assert e.value.kind == "MISSING_SDF"
+    ok = s2m.Sdf3DShader.from_glsl_fragment_shader(f, "other")  # --glsl-sdf
+    assert "fn sdf3d(p: vec3<f32>) -> f32 { return other(p); }" in ok.source
+    f.write_text("#version 450 core\nfloat sdf(vec3 p) { return p.x; }\n")
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_glsl_fragment_shader(f, "sdf")  # no main(): naga rejects it too
+    assert e.value.kind == "PARSE"
+
+
+@pytest.mark.parametrize("src,kind", [
+    ("fn sdf3d(p: vec3f) -> f32 { return p.x +; }", "PARSE"),
+    ("fn sdf3d(p: vec3f) -> f32 { return q.x; }", "VALIDATION"),
+    ("fn sdf3d(p: vec3f) -> f32 { return p; }", "VALIDATION"),
+    ("fn sdf3d(p: vec3f) -> f32 { let a: i32 = 1.5; return p.x; }", "VALIDATION"),
+    ("fn sdf3d(p: vec3f) -> f32 { return p.x + 1i; }", "VALIDATION"),
+    ("fn other(p: vec3f) -> f32 { return p.x; }", "MISSING_SDF"),
+    ("fn sdf3d(p: vec2f) -> f32 { return p.x; }", "MISSING_SDF"),
+    ("struct S { a: f32 }\nfn sdf3d(p: vec3f) -> f32 { return p.x; }", "UNSUPPORTED"),
+])
+def test_wgsl_errors(built, src, kind):
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_source(src).lower_to_cuda()
+    assert e.value.kind == kind
+
+
+def test_nvrtc_error_is_reported(built):
+    sh = s2m.Sdf3DShader.from_source("float sdf3d(vec3 p) { return undefined_symbol(p); }", s2m.SRC_CUDA)
+    with pytest.raises(s2m.S2mError) as e:
+        sh.create_shader_module(None)
+    assert e.value.kind == "NVRTC" and "undefined_symbol" in str(e.value)
+
+
+# --- semantics -----------------------------------------------------------------------------------
+def run_wgsl(src, pts):
+    return host_eval.eval_points(s2m.Sdf3DShader.from_source(src).lower_to_cuda(), np.asarray(pts, np.float32))
+
+
+def test_abstract_float_constants_fold_in_f64(built):
+    """module consts are abstract floats: K*0.1 is folded in f64 and rounded once (naga), which differs
+    from f32(K)*f32(0.45) for K = 3"""
+    src = "const K = 3.0;\nfn sdf3d(p: vec3f) -> f32 { return p.x - K*0.45; }"
+    v = run_wgsl(src, [[8.0, 0, 0]])[0]
+    assert v == np.float32(8.0) - np.float32(3.0 * 0.45)
+    assert np.float32(3.0 * 0.45) != np.float32(3.0) * np.float32(0.45)
+    src2 = "const K: f32 = 3.0;\nfn sdf3d(p: vec3f) -> f32 { return p.x - K*0.45; }"  # concrete: f32 arithmetic
+    assert run_wgsl(src2, [[8.0, 0, 0]])[0] == np.float32(8.0) - np.float32(3.0) * np.float32(0.45)
+
+
+def test_wgsl_control_flow_and_swizzles(built):
+    src = textwrap.dedent("""\
+        fn fold(p: vec3f) -> vec3f {
+            var q = p;
+            for (var i = 0; i < 3; i++) {
+                q = abs(q) - vec3f(0.5);
+                if (q.x < q.y) { let t = q.x; q.x = q.y; q.y = t; }
+                q.z *= 1.5;
+            }
+            return q;
+        }
+        fn sdf3d(p: vec3f) -> f32 {
+            var acc = 0.0;
+            var i: u32 = 0u;
+            loop {
+                if (i >= 4u) { break; }
+                acc += f32(i) * 0.25;
+                continuing { i = i + 1u; }
+            }
+            let q = fold(p).zyx;
+            var k = 0;
+            while (k < 2) { k += 1; if (k == 1) { continue; } acc -= 1.0; }
+            return select(length(q.xy), max(q.x, q.z), p.y > 0.0) + acc + f32(k);
+        }""")
+    pts = points(3.0, 2000)
+
+    def ref(p):
+        q = p.astype(np.float32).copy()
+        for _ in range(3):
+            q = (np.abs(q) - np.float32(0.5)).astype(np.float32)
+            if q[0] < q[1]:
+                q[0], q[1] = q[1], q[0]
+            q[2] = np.float32(q[2] * np.float32(1.5))
+        acc = np.float32(0)
+        for i in range(4):
+            acc = np.float32(acc + np.float32(i) * np.float32(0.25))
+        q = q[::-1]
+        acc = np.float32(acc - np.float32(1.0))
+        a = np.float32(np.sqrt(np.float32(np.float32(q[0] * q[0]) + np.float32(q[1] * q[1]))))
+        b = max(q[0], q[2])
+        return np.float32(np.float32((b if p[1] > 0 else a) + acc) + np.float32(2))
+
+    got = run_wgsl(src, pts)
+    want = np.array([ref(p) for p in pts], np.float32)
+    assert f32_equal(got, want).all()
+
+
+def test_glsl_features(built, tmp_path):
+    glsl = textwrap.dedent("""\
+        #version 450 core
+        #define PI 3.14159265
+        #define SQ(x) ((x)*(x))
+        uniform float iTime;
+        const float R = 0.75;
+        float helper(in vec3 p, out float extra) { extra = p.y * 2.0; return length(p) - R; }
+        float sdf(vec3 p) {
+            float e;
+            float d = helper(p, e);
+            int n = 0;
+            do { n++; d += 0.125; } while (n < 2);
+            vec2 w = vec2(d, e);
+            w.yx = w.xy;
+            float s = (p.z > 0.0) ? SQ(w.x) : mod(w.y, 0.5);
+            return s + sin(PI * iTime) + float(n) + max(vec3(p.x, 1, 2), 0.5).x;
+        }
+        void main() {}
+        """)
+    f = tmp_path / "t.frag"
+    f.write_text(glsl)
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(f, "sdf")
+    pts = points(3.0, 2000)
+
+    def ref(p):
+        p = p.astype(np.float32)
+        e = np.float32(p[1] * np.float32(2))
+        d = np.float32(np.sqrt(np.float32(np.float32(np.float32(p[0] * p[0]) + np.float32(p[1] * p[1])) + np.float32(p[2] * p[2]))) - np.float32(0.75))
+        d = np.float32(np.float32(d + np.float32(0.125)) + np.float32(0.125))
+        w = np.array([e, d], np.float32)  # w.yx = w.xy  ->  w = (old y, old x) = (e, d)
+        if p[2] > 0:
+            s = np.float32(w[0] * w[0])
+        else:
+            y = w[1]
+            s = np.float32(y - np.float32(np.float32(0.5) * np.floor(np.float32(y / np.float32(0.5)))))
+        out = np.float32(np.float32(np.float32(s + np.float32(0.0)) + np.float32(2)) + max(p[0], np.float32(0.5)))
+        return out
+
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+    want = np.array([ref(p) for p in pts], np.float32)
+    assert f32_equal(got, want).all()

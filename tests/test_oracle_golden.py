@@ -1,0 +1,88 @@
+"""The CPU oracle against its own committed known-answer set, plus structural invariants.
+
+There are no reference-owned golden vectors for this path: the digests under
+tests/golden/ were produced by this oracle (make_golden.py) -- this test pins the oracle against
+regressions and against the independently derived counts in SURVEY.md / BASELINE.md."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from tests.conftest import ROOT
+from tests.support.digest import f32_equal, mesh_digests
+
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "digests.json")))
+SMALL = [k for k in sorted(GOLDEN) if int(k.rsplit("_", 3)[1][1:]) <= 128]
+
+
+@pytest.mark.parametrize("key", SMALL)
+def test_oracle_reproduces_digest(key):
+    name, r_, b_, f_ = key.rsplit("_", 3)
+    m = oracle.mesh_run(name, int(r_[1:]), float(b_[1:]), flags=int(f_[1:]))
+    assert mesh_digests(m.positions, m.normals, m.keys, m.nibbles, m.quads, m.n_invalid_quads) == GOLDEN[key]
+    m.free()
+
+
+def test_survey_probe_counts():
+    """vertex counts the survey derived independently with a numpy probe"""
+    assert GOLDEN["torus_r128_b2_f0"]["n_vertices"] == 23248
+    assert GOLDEN["mandelbulb_r128_b5_f0"]["n_vertices"] == 21208
+    assert GOLDEN["mandelbulb_r256_b5_f0"]["n_vertices"] == 104232
+    assert GOLDEN["p_key_r64_b2_f0"]["n_vertices"] == 64 * 64  # one plane z = -0.75
+
+
+def test_npz_fixture_matches_oracle():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "torus_r32_b2.npz"))
+    m = oracle.mesh_run("torus", 32, 2.0)
+    assert np.array_equal(m.keys, g["keys"]) and np.array_equal(m.quads, g["quads"]) and np.array_equal(m.nibbles, g["nibbles"])
+    assert f32_equal(m.positions, g["positions"]).all() and f32_equal(m.normals, g["normals"]).all()
+    m.free()
+
+
+def test_structure_invariants():
+    m = oracle.mesh_run("mandelbulb", 64, 5.0)
+    k = m.keys
+    assert np.all(k[1:] > k[:-1]), "vertex order must be ascending key order (mesh.rs:224-226, SURVEY F10)"
+    z = (k >> np.uint64(32)).astype(np.int64)
+    assert z.min() >= 1 and z.max() <= 63, "faithful mode labels slices 1..R-1 (SURVEY F3)"
+    assert m.quads.max() < len(k)
+    # vertices lie inside their cell (within rounding)
+    size = np.float32(5.0) / np.float32(63)
+    x = (k & np.uint64(0xFFFF)).astype(np.float32)
+    lo = np.float32(-2.5) + size * x
+    assert np.all(m.positions[:, 0] >= lo - 1e-5) and np.all(m.positions[:, 0] <= lo + size + 1e-5)
+    m.free()
+
+
+def test_all_slices_mode_is_superset():
+    a = oracle.mesh_run("torus", 32, 2.0)
+    b = oracle.mesh_run("torus", 32, 2.0, flags=oracle.FLAG_ALL_SLICES)
+    shift = np.uint64(1) << np.uint64(32)
+    assert set((a.keys - shift).tolist()) <= set(b.keys.tolist())
+    a.free()
+    b.free()
+
+
+def test_rust_f32_display():
+    cases = {1.0: "1", 0.1: "0.1", -0.0: "-0", 1e30: "1000000000000000000000000000000", 1e-10: "0.0000000001",
+             3.4028235e38: "340282350000000000000000000000000000000", 123456.789: "123456.79", 16777216.0: "16777216",
+             0.30000001192092896: "0.3", -2.5: "-2.5", 1.17549435e-38: "0.000000000000000000000000000000000000011754944"}
+    for v, s in cases.items():
+        assert oracle.rust_f32(v) == s
+    assert oracle.rust_f32(float("nan")) == "NaN" and oracle.rust_f32(float("inf")) == "inf" and oracle.rust_f32(float("-inf")) == "-inf"
+
+
+def test_stl_ply_text_shape(tmp_path):
+    m = oracle.mesh_run("torus", 16, 2.0)
+    m.write_stl(tmp_path / "t.stl")
+    m.write_ply(tmp_path / "t.ply")
+    stl = open(tmp_path / "t.stl").read().split("\n")
+    assert stl[0] == "solid" and stl[-2] == "endsolid" and stl[1].startswith("facet normal ") and stl[2] == "\touter loop"
+    assert stl[3].startswith("\t\tvertex ") and stl[6] == "\tendloop" and stl[7] == "endfacet"
+    assert (len(stl) - 3) == 7 * 2 * len(m.quads)
+    ply = open(tmp_path / "t.ply").read().split("\n")
+    assert ply[:3] == ["ply", "format ascii 1.0", "comment written by rust-sdf"]
+    assert ply[3] == f"element vertex {len(m.keys)}" and ply[10] == f"element face {2 * len(m.quads)}" and ply[12] == "end_header"
+    m.free()
