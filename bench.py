@@ -148,8 +148,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="mandelmesh2048", choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-slices", type=int, default=8, help="z-slices per step of the CPU reference sample")
-    ap.add_argument("--cpu-baseline-slices", type=int, default=16)
+    ap.add_argument("--ref-slices", type=int, default=64, help="z-slices per step of the CPU reference sample")
+    ap.add_argument("--cpu-baseline-slices", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-balance", action="store_true", help="equal-thickness z-slabs instead of cost-balanced")
     ap.add_argument("--flags", type=int, default=0, help="extra S2M_MESH_* flags")

@@ -1,0 +1,213 @@
+// sdf2mesh -- command-line front end with the reference's flag surface
+// (/root/reference/src/bin/sdf2mesh/main.rs:95-137 `Arguments`, :177-364 `run`, :366-376 `main`),
+// driving libsdf2mesh_b200.so through its C ABI.  Same flags, same defaults, same input priority
+// (shadertoy > sdf > glsl, main.rs:200-221), same power-of-two rounding with a warning, same log
+// lines ("Reading SDF from ...", module names, "Mesh has N vertices.", "Mesh written to ...").
+// Additions: --device, --all-slices, --exact-dense, --no-normals, --binary-stl, --stats.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+
+#include "../include/sdf2mesh_b200.h"
+
+namespace {
+
+void log_line(const char* level, const std::string& msg) {
+  using namespace std::chrono;
+  const auto now = system_clock::now();
+  const std::time_t t = system_clock::to_time_t(now);
+  const long ns = (long)(duration_cast<nanoseconds>(now.time_since_epoch()).count() % 1000000000LL);
+  char buf[64];
+  std::tm tm{};
+  gmtime_r(&t, &tm);
+  strftime(buf, sizeof buf, "%Y-%m-%dT%H:%M:%S", &tm);
+  fprintf(stderr, "[%s.%09ldZ %-5s sdf2mesh] %s\n", buf, ns, level, msg.c_str());  // env_logger, nanosecond timestamps (main.rs:370-373)
+}
+void info(const std::string& m) { log_line("INFO", m); }
+void warn(const std::string& m) { log_line("WARN", m); }
+void error(const std::string& m) { log_line("ERROR", m); }
+
+[[noreturn]] void die(const std::string& what) {
+  // the reference unwrap()s / expect()s here and panics
+  error(what + ": " + s2m_last_error());
+  exit(101);
+}
+
+void usage(FILE* f) {
+  fputs(
+      "sdf2mesh\n\n"
+      "Usage: sdf2mesh [OPTIONS] --mesh <MESH>\n\n"
+      "Options:\n"
+      "  -i, --sdf <SDF>                      Input SDF file\n"
+      "      --shadertoy-id <SHADERTOY_ID>    Input ShaderToy shader ID\n"
+      "      --shadertoy-sdf <SHADERTOY_SDF>  ShaderToy SDF name [default: sdf]\n"
+      "      --glsl <GLSL>                    Input GLSL fragment shader\n"
+      "      --glsl-sdf <GLSL_SDF>            GLSL SDF name [default: sdf]\n"
+      "  -0, --mesh <MESH>                    Output mesh file (supports STL and PLY output)\n"
+      "      --debug-wgsl <DEBUG_WGSL>        Output WGSL file for debugging\n"
+      "      --debug-png <DEBUG_PNG>          Write PNG images for debugging (not available: there are no per-slice textures)\n"
+      "  -r, --resolution <RESOLUTION>        Grid resolution. Default: 256\n"
+      "  -b, --bounds <BOUNDS>                Size of bounding box. Default: 2\n"
+      "      --device <N>                     CUDA device ordinal [default: 0]\n"
+      "      --all-slices                     Mesh every z-slice (the reference never reads back the last one)\n"
+      "      --exact-dense                    Evaluate all 8 corners of every cell, like the reference (slow)\n"
+      "      --no-normals                     Skip vertex normals (only PLY output uses them)\n"
+      "      --binary-stl                     Write binary instead of ASCII STL\n"
+      "      --debug-cuda <FILE>              Write the generated CUDA C++ for debugging\n"
+      "      --stats                          Print per-kernel timings\n"
+      "  -h, --help                           Print help\n"
+      "  -V, --version                        Print version\n",
+      f);
+}
+
+struct Args {
+  std::string sdf, shadertoy_id, shadertoy_sdf = "sdf", glsl, glsl_sdf = "sdf", mesh, debug_wgsl, debug_png, debug_cuda;
+  unsigned resolution = 0;
+  float bounds = 0.0f;
+  int device = 0;
+  bool all_slices = false, exact_dense = false, no_normals = false, binary_stl = false, stats = false;
+};
+
+bool take_value(int argc, char** argv, int& i, const char* longf, const char* shortf, std::string* out) {
+  const std::string a = argv[i];
+  const std::string l = std::string("--") + longf;
+  if (a == l || (shortf && a == shortf)) {
+    if (i + 1 >= argc) { fprintf(stderr, "error: a value is required for '%s <%s>' but none was supplied\n", l.c_str(), longf); exit(2); }
+    *out = argv[++i];
+    return true;
+  }
+  if (a.compare(0, l.size() + 1, l + "=") == 0) { *out = a.substr(l.size() + 1); return true; }
+  if (shortf && a.size() > 2 && a.compare(0, 2, shortf) == 0) { *out = a.substr(2); return true; }
+  return false;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  Args a;
+  bool have_mesh = false;
+  for (int i = 1; i < argc; ++i) {
+    std::string v;
+    const std::string s = argv[i];
+    if (s == "-h" || s == "--help") { usage(stdout); return 0; }
+    if (s == "-V" || s == "--version") { printf("sdf2mesh (%s)\n", s2m_version()); return 0; }
+    if (take_value(argc, argv, i, "sdf", "-i", &a.sdf)) continue;
+    if (take_value(argc, argv, i, "shadertoy-id", nullptr, &a.shadertoy_id)) continue;
+    if (take_value(argc, argv, i, "shadertoy-sdf", nullptr, &a.shadertoy_sdf)) continue;
+    if (take_value(argc, argv, i, "glsl", nullptr, &a.glsl)) continue;
+    if (take_value(argc, argv, i, "glsl-sdf", nullptr, &a.glsl_sdf)) continue;
+    if (take_value(argc, argv, i, "mesh", "-0", &a.mesh)) { have_mesh = true; continue; }
+    if (take_value(argc, argv, i, "debug-wgsl", nullptr, &a.debug_wgsl)) continue;
+    if (take_value(argc, argv, i, "debug-png", nullptr, &a.debug_png)) continue;
+    if (take_value(argc, argv, i, "debug-cuda", nullptr, &a.debug_cuda)) continue;
+    if (take_value(argc, argv, i, "resolution", "-r", &v)) {
+      char* end = nullptr;
+      const long long n = strtoll(v.c_str(), &end, 10);
+      if (!end || *end || n < 0 || n > 0xffffffffLL) { fprintf(stderr, "error: invalid value '%s' for '--resolution <RESOLUTION>'\n", v.c_str()); return 2; }
+      a.resolution = (unsigned)n;
+      continue;
+    }
+    if (take_value(argc, argv, i, "bounds", "-b", &v)) {
+      char* end = nullptr;
+      a.bounds = strtof(v.c_str(), &end);
+      if (!end || *end) { fprintf(stderr, "error: invalid value '%s' for '--bounds <BOUNDS>'\n", v.c_str()); return 2; }
+      continue;
+    }
+    if (take_value(argc, argv, i, "device", nullptr, &v)) { a.device = atoi(v.c_str()); continue; }
+    if (s == "--all-slices") { a.all_slices = true; continue; }
+    if (s == "--exact-dense") { a.exact_dense = true; continue; }
+    if (s == "--no-normals") { a.no_normals = true; continue; }
+    if (s == "--binary-stl") { a.binary_stl = true; continue; }
+    if (s == "--stats") { a.stats = true; continue; }
+    fprintf(stderr, "error: unexpected argument '%s' found\n\n", s.c_str());
+    usage(stderr);
+    return 2;
+  }
+  if (!have_mesh) {
+    fputs("error: the following required arguments were not provided:\n  --mesh <MESH>\n\n", stderr);
+    usage(stderr);
+    return 2;
+  }
+
+  // AppState::from(&args)  (main.rs:139-175)
+  s2m_mesh_params params;
+  int rounded = 0;
+  if (s2m_params_from_cli(a.resolution, a.bounds, &params, &rounded)) die("bad arguments");
+  if (rounded) warn("Resolution should be a power of 2 (actual resolution : " + std::to_string(params.dims[0]) + ")");
+  if (a.all_slices) params.flags |= S2M_MESH_ALL_SLICES;
+  if (a.exact_dense) params.flags |= S2M_MESH_EXACT_DENSE;
+  if (a.no_normals) params.flags |= S2M_MESH_NO_NORMALS;
+
+  s2m_ctx* ctx = nullptr;
+  if (s2m_ctx_create(a.device, &ctx)) die("no usable CUDA device");  // request_adapter/request_device .unwrap()
+
+  // input priority: shadertoy > sdf > glsl  (main.rs:200-221)
+  s2m_shader* shader = nullptr;
+  if (!a.shadertoy_id.empty()) {
+    info("Reading SDF from ShaderToy (shader ID " + a.shadertoy_id + ")");
+    error("the ShaderToy REST fetch is not part of this build (no network access); save the shader as a .frag file and use --glsl");
+    return 101;
+  } else if (!a.sdf.empty()) {
+    info("Reading SDF from " + a.sdf + "...");
+    if (s2m_shader_from_path(a.sdf.c_str(), &shader)) die("cannot read SDF");
+  } else if (!a.glsl.empty()) {
+    info("Reading SDF from GLSL fragment shader " + a.glsl + "...");
+    if (s2m_shader_from_glsl_fragment_shader(a.glsl.c_str(), a.glsl_sdf.c_str(), &shader)) die("cannot convert GLSL shader");
+  } else {
+    if (s2m_shader_from_source("", 0, S2M_SRC_SDF3D, nullptr, nullptr, &shader)) die("empty shader");  // Sdf3DShader::default()
+  }
+  {  // forward what the reference logs while assembling the source
+    std::string lg = s2m_shader_log(shader);
+    size_t p = 0;
+    while (p < lg.size()) {
+      size_t e = lg.find('\n', p);
+      if (e == std::string::npos) e = lg.size();
+      const std::string line = lg.substr(p, e - p);
+      if (line.compare(0, 5, "INFO ") == 0) info(line.substr(5));
+      else if (line.compare(0, 6, "ERROR ") == 0) error(line.substr(6));
+      else if (!line.empty()) info(line);
+      p = e + 1;
+    }
+  }
+  if (!a.debug_wgsl.empty() && s2m_shader_write_to_file(shader, a.debug_wgsl.c_str())) die("cannot write --debug-wgsl file");
+  if (!a.debug_png.empty()) warn("--debug-png is ignored: this engine has no per-slice textures to dump");
+
+  s2m_module* module = nullptr;
+  if (s2m_module_compile(ctx, shader, 0, &module)) die("shader module creation failed");
+  if (!a.debug_cuda.empty()) {
+    FILE* f = fopen(a.debug_cuda.c_str(), "wb");
+    if (f) { fputs(s2m_module_cuda_source(module), f); fclose(f); }
+  }
+  info("CUDA context set up.");
+
+  s2m_result* result = nullptr;
+  if (s2m_mesh_run(ctx, module, &params, &result)) die("meshing failed");
+  s2m_result_info ri;
+  s2m_result_get(result, &ri);
+  info("Mesh has " + std::to_string(ri.n_vertices) + " vertices.");
+  if (ri.n_invalid_quads) warn(std::to_string(ri.n_invalid_quads) + " invalid quads. Mesh will not be water-tight!");
+  if (a.stats) {
+    const s2m_timings& t = ri.timings;
+    const double vox = (double)params.dims[0] * params.dims[1] * params.dims[2];
+    fprintf(stderr, "stats: %llu candidates, %llu vertices, %llu quads | front-end %.1f ms, NVRTC %.1f ms | K1 %.3f K2 %.3f K3 %.3f K4a %.3f K4b %.3f d2h %.3f total %.3f ms (%u launches, %u chunks) | %.2f Gvoxel/s\n",
+            (unsigned long long)ri.n_candidates, (unsigned long long)ri.n_vertices, (unsigned long long)ri.n_quads,
+            s2m_module_compile_ms(module, 0), s2m_module_compile_ms(module, 1), t.k1_slab_ms, t.k2_classify_ms, t.k3_compact_ms,
+            t.k4_vertices_ms, t.k4_quads_ms, t.d2h_ms, t.total_ms, t.launches, t.chunks, vox / (t.total_ms * 1e-3) / 1e9);
+  }
+  int st;
+  const std::string& m = a.mesh;
+  const bool is_stl = m.size() >= 4 && strcasecmp(m.c_str() + m.size() - 4, ".stl") == 0;
+  if (a.binary_stl && is_stl) st = s2m_result_write_stl_binary(result, m.c_str());
+  else st = s2m_result_write_mesh(result, m.c_str());
+  if (st) error(std::string("Could not write mesh to ") + s2m_last_error() + "!");  // main.rs:359-361 (and it carries on)
+  info("Mesh written to " + a.mesh);
+
+  s2m_result_free(result);
+  s2m_module_free(module);
+  s2m_shader_free(shader);
+  s2m_ctx_destroy(ctx);
+  return 0;
+}
