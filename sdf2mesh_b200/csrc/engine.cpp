@@ -321,6 +321,23 @@ struct GridDev {  // must match S2mGrid in kernels_jit.cuh
   unsigned rows;
   unsigned long long plane_stride;
 };
+struct SlabViewDev {  // must match S2mSlabView
+  const float* slab;
+  unsigned first_plane;
+  unsigned n_planes;
+};
+// K1 block shape (bx, by), bx*by = 256; S2M_K1_BLOCK=8x32 overrides the default for experiments
+void k1_block_shape(unsigned* bx, unsigned* by) {
+  static unsigned sx = 0, sy = 0;
+  if (!sx) {
+    sx = 32; sy = 8;
+    if (const char* e = getenv("S2M_K1_BLOCK")) {
+      unsigned a = 0, b = 0;
+      if (sscanf(e, "%ux%u", &a, &b) == 2 && a && b && a * b <= 1024 && (a * b) % 32 == 0) { sx = a; sy = b; }
+    }
+  }
+  *bx = sx; *by = sy;
+}
 struct VertexOutDev {  // must match S2mVertexOut
   float* pos; float* nrm; unsigned long long* key; unsigned char* nibble; unsigned* cand_vrank;
   unsigned long long* status; unsigned* ticket; unsigned long long* n_vertices; unsigned long long* n_halo;
@@ -359,6 +376,7 @@ struct s2m_result {
   s2m_mesh_params params{};
   GridDev grid{};
   uint32_t z_first = 0, nz = 0, label_add = 0, halo = 0, words_x = 0;
+  uint32_t slab_first_plane = 0, slab_n_planes = 0;
   uint64_t n_cand = 0, n_vert_total = 0, n_halo = 0, n_quads = 0, n_invalid = 0;
   float* h_pos = nullptr; float* h_nrm = nullptr; uint64_t* h_key = nullptr; uint8_t* h_nib = nullptr;
   uint64_t* h_quads = nullptr; uint64_t* h_cand = nullptr;
@@ -459,9 +477,12 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
       float* slab = c->slab.as<float>();
       unsigned first_plane = r->z_first + z0, n_planes = nzc + 1;
       void* a1[] = {&gd, &slab, &first_plane, &n_planes};
-      dim3 grid1((g.pitch_x + 127u) / 128u, (g.rows + 7u) / 8u, n_planes);
+      unsigned bx, by;
+      k1_block_shape(&bx, &by);
+      dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by - 1u) / by, n_planes);
       if (chunks == 0) CUDA_TRY(cudaEventRecord(c->ev[1], s));
-      if ((st = launch(m->k1, grid1, dim3(32, 8, 1), s, a1, "s2m_k1_slab"))) return st;
+      if ((st = launch(m->k1, grid1, dim3(bx, by, 1), s, a1, "s2m_k1_slab"))) return st;
+      r->slab_first_plane = first_plane; r->slab_n_planes = n_planes;  // what stays resident for K4a
       S2mK2Args a2{};
       a2.slab = slab; a2.pitch_x = g.pitch_x; a2.plane_stride = g.plane_stride;
       a2.res_x = g.res[0]; a2.res_y = g.res[1]; a2.nz_chunk = nzc; a2.tau = tau;
@@ -531,7 +552,8 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
     VertexOutDev vo{c->v_pos.as<float>(), c->v_nrm.as<float>(), c->v_key.as<unsigned long long>(), c->v_nib.as<unsigned char>(),
                     c->cand_vrank.as<unsigned>(), c->status.as<unsigned long long>() + k3_tiles,
                     reinterpret_cast<unsigned*>(d_cnt + C_TICKET1), d_cnt + C_NVERT, d_cnt + C_NHALO};
-    void* a4[] = {&gd, &ck, &nc, &label_add, &halo_below, &want_normals, &vo};
+    SlabViewDev sv{c->slab.as<float>(), r->slab_first_plane, r->slab_n_planes};
+    void* a4[] = {&gd, &ck, &nc, &label_add, &halo_below, &want_normals, &sv, &vo};
     if ((st = launch(m->k4, dim3(k4_tiles), dim3(128), s, a4, "s2m_k4_vertices"))) return st;
     ++launches;
   }
@@ -691,7 +713,9 @@ extern "C" int s2m_debug_slab_plane(s2m_ctx* c, s2m_module* m, const s2m_mesh_pa
   float* slab = c->slab.as<float>();
   unsigned first_plane = plane, n_planes = 1;
   void* a1[] = {&g, &slab, &first_plane, &n_planes};
-  if ((st = launch(m->k1, dim3((g.pitch_x + 127u) / 128u, (g.rows + 7u) / 8u, 1), dim3(32, 8, 1), c->stream, a1, "s2m_k1_slab"))) return st;
+  unsigned bx, by;
+  k1_block_shape(&bx, &by);
+  if ((st = launch(m->k1, dim3((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by - 1u) / by, 1), dim3(bx, by, 1), c->stream, a1, "s2m_k1_slab"))) return st;
   CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)(g.res[0] + 1) * 4, slab, (size_t)g.pitch_x * 4, (size_t)(g.res[0] + 1) * 4, g.rows,
                              cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));

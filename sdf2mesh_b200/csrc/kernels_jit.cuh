@@ -30,25 +30,16 @@ __device__ __forceinline__ float s2m_sdf(float x, float y, float z) {
 }
 __device__ __noinline__ float s2m_sdf_call(float x, float y, float z) { return s2m_sdf(x, y, z); }
 
-/* sdf3d_normal.wgsl:4-10:  v1*f(p+v1*eps) + v2*f(p+v2*eps) + v3*f(p+v3*eps) + v4*f(p+v4*eps) */
-__device__ __forceinline__ void s2m_sdf3d_normal(const float p[3], float eps, float n[3]) {
-  const float v[4][3] = {{1.0f, -1.0f, -1.0f}, {-1.0f, -1.0f, 1.0f}, {-1.0f, 1.0f, -1.0f}, {1.0f, 1.0f, 1.0f}};
-  n[0] = n[1] = n[2] = 0.0f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    float f = s2m_sdf_call(p[0] + v[k][0] * eps, p[1] + v[k][1] * eps, p[2] + v[k][2] * eps);
-    if (k == 0) { n[0] = v[k][0] * f; n[1] = v[k][1] * f; n[2] = v[k][2] * f; }
-    else { n[0] = n[0] + v[k][0] * f; n[1] = n[1] + v[k][1] * f; n[2] = n[2] + v[k][2] * f; }
-  }
-}
-
 /* ------------------------------------------------------------------------------------------ K1 */
-/* Block (32,8): a warp covers 128 consecutive x corners of one row, a thread 4 of them (one
- * float4 store, 512 B contiguous per warp).  grid = (pitch_x/128, ceil(rows/8), planes). */
+/* A thread evaluates 4 consecutive x corners and stores one float4.  The block shape is chosen by
+ * the host: blockDim = (bx, by) with bx*by = 256.  A warp is 32 consecutive threads, x fastest, so
+ * its footprint is (4*min(bx,32)) x (32/min(bx,32)) corners: (32,8) = 128x1 rows (512 B contiguous
+ * per warp), (8,32) = 32x4 tiles (one full 128 B line per row) -- more compact, less divergence
+ * in SDFs whose cost varies in space.  grid = (ceil(pitch_x/(4*bx)), ceil(rows/by), planes). */
 extern "C" __global__ void __launch_bounds__(256)
 s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned n_planes) {
-  const unsigned x4 = (blockIdx.x * 32u + threadIdx.x) * 4u;
-  const unsigned y = blockIdx.y * 8u + threadIdx.y;
+  const unsigned x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+  const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
   const unsigned pz = blockIdx.z;
   if (x4 >= g.pitch_x || y >= g.rows || pz >= n_planes) return;
   const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
@@ -79,36 +70,118 @@ struct S2mVertexOut {
   unsigned long long* n_halo;      /* out: vertices whose true z < halo_below */
 };
 
-/* One thread per candidate cell.  cand_key = x | y<<16 | z_true<<32 (z_true relative to the grid).
- * label_add = 1 in faithful mode (the reference labels slice z as z+1), else 0. */
-extern "C" __global__ void __launch_bounds__(128)
+/* the part of K1's slab that is still resident when K4a runs (n_planes = 0: none) */
+struct S2mSlabView {
+  const float* slab;
+  unsigned first_plane;
+  unsigned n_planes;
+};
+
+#define S2M_K4_THREADS 128
+
+/* Distribute `count` work items per lane over the lanes of a warp: returns the warp total and
+ * writes the inclusive prefix to inc[lane] (shared memory, 32 entries per warp). */
+__device__ __forceinline__ unsigned s2m_warp_items(unsigned count, unsigned* inc) {
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned v = count;
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= (unsigned)o) v += n;
+  }
+  inc[lane] = v;
+  __syncwarp();
+  return __shfl_sync(0xffffffffu, v, 31);
+}
+/* owner lane of work item `item`: first lane whose inclusive prefix exceeds it */
+__device__ __forceinline__ unsigned s2m_item_owner(const unsigned* inc, unsigned item) {
+  unsigned lo = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1)
+    if (inc[lo + step - 1] <= item) lo += step;
+  return lo;
+}
+
+/* One thread per candidate cell; SDF evaluations are pooled per warp and dealt out evenly.
+ *
+ * The reference evaluates the 8 corners of a cell at (min | min+size) per axis
+ * (dualcontour.wgsl:22-43).  Corner 000 is always at the slab's own coordinates, and a corner with
+ * a `max` coordinate is too whenever fl(min + size) == the next corner's min bit for bit (true for
+ * 17-95 % of indices).  Those values are read back from K1's slab (same function, same
+ * arguments, same bits); only the rest -- 2.5 of 8 on average at 2048^3 -- are evaluated, and those
+ * evaluations plus the 4 normal taps of cells that get a vertex are spread over all 32 lanes.
+ *
+ * cand_key = x | y<<16 | z_true<<32.  label_add = 1 in faithful mode, else 0. */
+extern "C" __global__ void __launch_bounds__(S2M_K4_THREADS)
 s2m_k4_vertices(S2mGrid g, const unsigned long long* __restrict__ cand_key, unsigned long long n_cand,
-                unsigned label_add, unsigned halo_below, unsigned want_normals, S2mVertexOut out) {
+                unsigned label_add, unsigned halo_below, unsigned want_normals, S2mSlabView sv, S2mVertexOut out) {
   __shared__ unsigned s_scan[33];
   __shared__ unsigned s_tile;
   __shared__ unsigned long long s_base;
+  __shared__ unsigned s_inc[S2M_K4_THREADS];        /* per warp: inclusive item prefix */
+  __shared__ unsigned s_mask[S2M_K4_THREADS];       /* per lane: which corners / taps need an evaluation */
+  __shared__ float s_co[S2M_K4_THREADS][6];         /* per lane: cmin.xyz, cmax.xyz  (later: pos.xyz) */
+  __shared__ float s_val[S2M_K4_THREADS][8];        /* per lane: evaluated corner values / tap values */
   if (threadIdx.x == 0) s_tile = atomicAdd(out.ticket, 1u);
   __syncthreads();
   const unsigned tile = s_tile;
   const unsigned long long c = (unsigned long long)tile * blockDim.x + threadIdx.x;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned wbase = threadIdx.x & ~31u;          /* first thread of this warp */
+  unsigned* inc = s_inc + wbase;
 
   bool has_vertex = false;
   float pos[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 0.f};
-  unsigned nib = 0;
+  float cmin[3] = {0.f, 0.f, 0.f}, cmax[3] = {0.f, 0.f, 0.f};
+  float d[8];
+  unsigned nib = 0, need = 0;
   unsigned cx = 0, cy = 0, cz = 0;
-  if (c < n_cand) {
+  const bool live = c < n_cand;
+  if (live) {
     const unsigned long long key = cand_key[c];
     cx = (unsigned)(key & 0xffffu); cy = (unsigned)((key >> 16) & 0xffffu); cz = (unsigned)(key >> 32);
     /* cell_bounds, dualcontour.wgsl:22-27 */
-    float cmin[3], cmax[3];
     cmin[0] = g.bmin[0] + g.size[0] * (float)cx; cmax[0] = cmin[0] + g.size[0];
     cmin[1] = g.bmin[1] + g.size[1] * (float)cy; cmax[1] = cmin[1] + g.size[1];
     cmin[2] = g.bmin[2] + g.size[2] * (float)cz; cmax[2] = cmin[2] + g.size[2];
-    /* cell_new :29-43 -- the reference's own 8 corner positions */
-    float d[8];
+    /* does the reference's `max` coordinate coincide with the slab coordinate of the next corner? */
+    const bool mx = cmax[0] == g.bmin[0] + g.size[0] * (float)(cx + 1u);
+    const bool my = cmax[1] == g.bmin[1] + g.size[1] * (float)(cy + 1u);
+    const bool mz = cmax[2] == g.bmin[2] + g.size[2] * (float)(cz + 1u);
+    const bool p0 = cz >= sv.first_plane && cz - sv.first_plane < sv.n_planes;          /* plane cz resident */
+    const bool p1 = cz + 1u >= sv.first_plane && cz + 1u - sv.first_plane < sv.n_planes; /* plane cz+1 resident */
 #pragma unroll
-    for (int k = 0; k < 8; ++k)  /* 8 call sites of one out-of-line copy of the SDF */
-      d[k] = s2m_sdf_call((k & 1) ? cmax[0] : cmin[0], (k & 2) ? cmax[1] : cmin[1], (k & 4) ? cmax[2] : cmin[2]);
+    for (int k = 0; k < 8; ++k) {
+      const bool ok = ((k & 1) ? mx : true) && ((k & 2) ? my : true) && ((k & 4) ? (mz && p1) : p0);
+      if (ok) {
+        const unsigned long long at = (unsigned long long)(cz + ((k >> 2) & 1) - sv.first_plane) * g.plane_stride +
+                                      (unsigned long long)(cy + ((k >> 1) & 1)) * g.pitch_x + (cx + (k & 1));
+        d[k] = __ldg(sv.slab + at);
+      } else {
+        d[k] = 0.0f;
+        need |= 1u << k;
+      }
+    }
+  }
+  /* ---- pooled corner evaluations: cell_new :29-43, the reference's own 8 corner positions */
+  s_mask[threadIdx.x] = need;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { s_co[threadIdx.x][a] = cmin[a]; s_co[threadIdx.x][3 + a] = cmax[a]; }
+  {
+    const unsigned total = s2m_warp_items((unsigned)__popc(need), inc);
+    for (unsigned item = lane; item < total; item += 32u) {
+      const unsigned o = s2m_item_owner(inc, item);
+      const unsigned j = item - (o ? inc[o - 1] : 0u);
+      const unsigned k = __fns(s_mask[wbase + o], 0u, (int)j + 1);
+      const float* co = s_co[wbase + o];
+      s_val[wbase + o][k] = s2m_sdf_call((k & 1u) ? co[3] : co[0], (k & 2u) ? co[4] : co[1], (k & 4u) ? co[5] : co[2]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (need & (1u << k)) d[k] = s_val[threadIdx.x][k];
+    __syncwarp();
+  }
+  if (live) {
     /* cell_fetch_interpolated_pos :86-131.  Edge e joins corners ea[e] -> eb[e]; the crossing
      * parameter goes into axis ax[e]; the other two coordinates are the corner bits of ea[e]. */
     const int ea[12] = {0, 2, 1, 3, 0, 4, 1, 5, 0, 4, 2, 6};
@@ -134,13 +207,33 @@ s2m_k4_vertices(S2mGrid g, const unsigned long long* __restrict__ cand_key, unsi
       pos[0] = cmin[0] + (cmax[0] - cmin[0]) * avg[0] / count;
       pos[1] = cmin[1] + (cmax[1] - cmin[1]) * avg[1] / count;
       pos[2] = cmin[2] + (cmax[2] - cmin[2]) * avg[2] / count;
-      if (want_normals) {
-        float n[3];
-        s2m_sdf3d_normal(pos, g.eps, n);
-        const float len = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);  /* normalize :171 */
-        nrm[0] = n[0] / len; nrm[1] = n[1] / len; nrm[2] = n[2] / len;
-      }
       nib = (d[1] > 0.0f ? 1u : 0u) | (d[2] > 0.0f ? 2u : 0u) | (d[4] > 0.0f ? 4u : 0u) | (d[0] > 0.0f ? 8u : 0u);
+    }
+  }
+  /* ---- pooled normal taps: sdf3d_normal.wgsl:4-10
+   *      v1*f(p+v1*eps) + v2*f(p+v2*eps) + v3*f(p+v3*eps) + v4*f(p+v4*eps), then normalize (:171) */
+  if (want_normals) {
+    const float v[4][3] = {{1.0f, -1.0f, -1.0f}, {-1.0f, -1.0f, 1.0f}, {-1.0f, 1.0f, -1.0f}, {1.0f, 1.0f, 1.0f}};
+    s_co[threadIdx.x][0] = pos[0]; s_co[threadIdx.x][1] = pos[1]; s_co[threadIdx.x][2] = pos[2];
+    const unsigned total = s2m_warp_items(has_vertex ? 4u : 0u, inc);
+    for (unsigned item = lane; item < total; item += 32u) {
+      const unsigned o = s2m_item_owner(inc, item);
+      const unsigned k = item - (o ? inc[o - 1] : 0u);
+      const float* p = s_co[wbase + o];
+      const float sx = (k == 0u || k == 3u) ? 1.0f : -1.0f, sy = (k >= 2u) ? 1.0f : -1.0f, sz = (k == 1u || k == 3u) ? 1.0f : -1.0f;
+      s_val[wbase + o][k] = s2m_sdf_call(p[0] + sx * g.eps, p[1] + sy * g.eps, p[2] + sz * g.eps);
+    }
+    __syncwarp();
+    if (has_vertex) {
+      float n[3];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float f = s_val[threadIdx.x][k];
+        if (k == 0) { n[0] = v[k][0] * f; n[1] = v[k][1] * f; n[2] = v[k][2] * f; }
+        else { n[0] = n[0] + v[k][0] * f; n[1] = n[1] + v[k][1] * f; n[2] = n[2] + v[k][2] * f; }
+      }
+      const float len = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      nrm[0] = n[0] / len; nrm[1] = n[1] / len; nrm[2] = n[2] / len;
     }
   }
   /* stable compaction: block scan + decoupled look-back for the tile's base */
@@ -152,7 +245,7 @@ s2m_k4_vertices(S2mGrid g, const unsigned long long* __restrict__ cand_key, unsi
   }
   __syncthreads();
   const unsigned long long vi = s_base + local;
-  if (c < n_cand) out.cand_vrank[c] = has_vertex ? (unsigned)vi : 0xffffffffu;
+  if (live) out.cand_vrank[c] = has_vertex ? (unsigned)vi : 0xffffffffu;
   if (has_vertex) {
     out.pos[3 * vi + 0] = pos[0]; out.pos[3 * vi + 1] = pos[1]; out.pos[3 * vi + 2] = pos[2];
     out.nrm[3 * vi + 0] = nrm[0]; out.nrm[3 * vi + 1] = nrm[1]; out.nrm[3 * vi + 2] = nrm[2];

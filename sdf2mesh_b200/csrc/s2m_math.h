@@ -13,8 +13,9 @@
  *   - g++ for tests/ that check accuracy against libm (double)
  * so the device and the oracle agree bit-for-bit on every SDF value (NaN payloads excepted).
  *
- * Accuracy (measured by tests/test_math.py against libm in double): <= 2 ulp for
- * sin cos tan asin acos atan atan2 exp exp2 log log2 pow on their usual domains.
+ * Accuracy (measured by tests/test_math.py against libm in double): <= 2.4 ulp for
+ * sin cos tan asin acos atan atan2 exp exp2 log log2 pow on their usual domains; pow with an
+ * integer exponent |n| <= 8 is a multiplication chain (<= 5 ulp).
  *
  * C99 / C++ / CUDA compatible.  No includes on the device (NVRTC has no libc headers).
  */
@@ -122,7 +123,11 @@ S2M_HD unsigned s2m_f2uint(float x) {
 
 /* ------------------------------------------------------------------ trigonometric range reduction */
 /* Fast path |x| <= 105615: 3-term Cody-Waite with FMA.  r = x - j*pi/2, *q = j mod 4. */
-S2M_HD float s2m__trig_red_slow(float x, int* q);
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+__host__ __device__ __noinline__ float s2m__trig_red_slow(float x, int* q);
+#else
+static float s2m__trig_red_slow(float x, int* q);
+#endif
 
 S2M_HD float s2m__trig_red(float x, int* q) {
   if (s2m_abs(x) > 105615.0f) return s2m__trig_red_slow(x, q);
@@ -134,11 +139,28 @@ S2M_HD float s2m__trig_red(float x, int* q) {
   return r;
 }
 
-/* Slow path: Payne-Hanek with integer arithmetic (inf/NaN -> NaN). */
-S2M_HD float s2m__trig_red_slow(float x, int* q) {
-  /* 2/pi = 0.A2F9836E 4E441529 FC2757D1 F534DDC0 DB629599 3C439041 FE5163AB ... (hex) */
-  const unsigned tw[9] = {0u, 0xa2f9836eu, 0x4e441529u, 0xfc2757d1u, 0xf534ddc0u,
-                          0xdb629599u, 0x3c439041u, 0xfe5163abu, 0xdebbc561u};
+/* 2/pi = 0.A2F9836E 4E441529 FC2757D1 F534DDC0 DB629599 3C439041 FE5163AB ... (hex), one leading zero word */
+#define S2M_TWO_OVER_PI_WORDS {0u, 0xa2f9836eu, 0x4e441529u, 0xfc2757d1u, 0xf534ddc0u, 0xdb629599u, 0x3c439041u, 0xfe5163abu, 0xdebbc561u}
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+static __constant__ unsigned s2m__two_over_pi_dev[9] = S2M_TWO_OVER_PI_WORDS;
+#endif
+#if !defined(__CUDA_ARCH__)
+static const unsigned s2m__two_over_pi_host[9] = S2M_TWO_OVER_PI_WORDS;
+#endif
+
+/* Slow path: Payne-Hanek with integer arithmetic (inf/NaN -> NaN).  Out of line on the device:
+ * it is cold, and inlining it at every sin/cos call site only bloats the SDF kernels. */
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+__host__ __device__ __noinline__
+#else
+static
+#endif
+float s2m__trig_red_slow(float x, int* q) {
+#if defined(__CUDA_ARCH__)
+  const unsigned* tw = s2m__two_over_pi_dev;
+#else
+  const unsigned* tw = s2m__two_over_pi_host;
+#endif
   int ia = s2m_f2i(x) & 0x7fffffff;
   *q = 0;
   if (ia >= 0x7f800000) return s2m_nan();
@@ -431,6 +453,22 @@ S2M_HD float s2m_pow(float a, float b) {
   if (b == 0.0f || a == 1.0f) return 1.0f;
   if (s2m_isnan(a) || s2m_isnan(b)) return s2m_nan();
   float aa = s2m_abs(a), ab = s2m_abs(b);
+  /* Integer exponents up to 8 in magnitude: exponentiation by squaring (<= 5 multiplications,
+   * <= 5 ulp measured; handles signs, zeros and infinities by itself).  This is the strength reduction
+   * shader compilers apply to pow(x, 8.0); when b is a compile-time constant it folds to the
+   * bare multiplication chain. */
+  if (ab <= 8.0f && truncf(b) == b) {
+    int n = (int)ab;
+    float r = 1.0f, p = a;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) {
+      if (n & (1 << i)) r = r * p;
+      p = p * p;
+    }
+    return b < 0.0f ? 1.0f / r : r;
+  }
   int b_int = (ab >= 8388608.0f) || (truncf(b) == b);
   int b_odd = b_int && (ab < 16777216.0f) && ((((int)truncf(ab)) & 1) != 0) && (ab >= 1.0f);
   if (ab == s2m_inf()) {
