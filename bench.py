@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-balance", action="store_true", help="equal-thickness z-slabs instead of cost-balanced")
     ap.add_argument("--flags", type=int, default=0, help="extra S2M_MESH_* flags")
+    ap.add_argument("--slab-budget-gb", type=float, default=0.0, help="bytes of corner slab resident at once (0 = engine default, 4 GiB chunks)")
     args = ap.parse_args()
     wl = args.workload
     if args.impl == "reference":
@@ -182,6 +183,7 @@ def main():
     module = shader.create_shader_module(ctx)
     jit_ms = (time.perf_counter() - t0) * 1e3
     params, _ = s2m.params_from_cli(res, bounds, flags=args.flags)
+    params.slab_budget_bytes = int(args.slab_budget_gb * (1 << 30))
     n_slices = dist_util.n_scanned_slices(res, bool(args.flags & s2m.MESH_ALL_SLICES))
 
     # z-slab partition (rank 0 probes the per-band cost, everyone uses its answer)
@@ -202,7 +204,11 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        r, base, counts = dist_util.mesh_slab(ctx, module, params, zb, ze, rank=rank, device=dev)
+        if world == 1:
+            r = s2m.mesh_run(ctx, module, params)  # one slab: quads are emitted and copied chunk by chunk
+            counts = [r.info().n_vertices]
+        else:
+            r, base, counts = dist_util.mesh_slab(ctx, module, params, zb, ze, rank=rank, device=dev)
         i = r.info()
         out = (i.n_vertices, i.n_quads, i.n_invalid_quads, {k[0]: getattr(i.timings, k[0]) for k in s2m._capi.Timings._fields_}, sum(counts), i.n_candidates)
         r.free()

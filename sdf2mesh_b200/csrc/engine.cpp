@@ -111,6 +111,22 @@ struct DevBuf {
     cap = want;
     return S2M_OK;
   }
+  // grow, keeping the first `used` bytes (device-to-device copy on `st`)
+  int ensure_preserve(size_t bytes, size_t used, cudaStream_t st) {
+    if (bytes <= cap) return S2M_OK;
+    if (!p || used == 0) return ensure(bytes);
+    void* np = nullptr;
+    size_t want = bytes + bytes / 2 + 256;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMalloc(&np, want); }
+    if (e != cudaSuccess) return fail(S2M_ERR_OOM, "cudaMalloc(" + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
+    e = cudaMemcpyAsync(np, p, used, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(np); return fail(S2M_ERR_CUDA, std::string("grow copy: ") + cudaGetErrorString(e)); }
+    cudaFree(p);
+    p = np; cap = want;
+    return S2M_OK;
+  }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -144,6 +160,8 @@ struct s2m_ctx {
   std::vector<PinnedBlock> pinned;
   unsigned long long* h_counters = nullptr;  // pinned, 16 words
   cudaEvent_t ev[16]{};
+  std::vector<cudaEvent_t> ev_pool;   // per-launch timing events, grown on demand
+  uint64_t hint_nv = 0, hint_nq = 0;  // output sizes of the previous run (pinned capacity guess)
   bool busy = false;  // a begin() without finish()/free() is outstanding
 
   void* lease_pinned(size_t bytes) {
@@ -212,6 +230,7 @@ extern "C" void s2m_ctx_destroy(s2m_ctx* c) {
   for (auto& b : c->pinned) cudaFreeHost(b.p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : c->ev_pool) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -261,6 +280,11 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   if (r != NVRTC_SUCCESS) return fail(S2M_ERR_NVRTC, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r));
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   opts.push_back((flags & S2M_COMPILE_ALLOW_FMA) ? "--fmad=true" : "--fmad=false");
+  std::string unroll_opt;
+  if (const char* e = getenv("S2M_K1_UNROLL")) {  // experiment knob, see kernels_jit.cuh
+    unroll_opt = std::string("-DS2M_K1_UNROLL=") + (atoi(e) == 1 ? "1" : "4");
+    opts.push_back(unroll_opt.c_str());
+  }
   r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);
@@ -330,7 +354,7 @@ struct SlabViewDev {  // must match S2mSlabView
 void k1_block_shape(unsigned* bx, unsigned* by) {
   static unsigned sx = 0, sy = 0;
   if (!sx) {
-    sx = 32; sy = 8;
+    sx = 8; sy = 32;
     if (const char* e = getenv("S2M_K1_BLOCK")) {
       unsigned a = 0, b = 0;
       if (sscanf(e, "%ux%u", &a, &b) == 2 && a && b && a * b <= 1024 && (a * b) % 32 == 0) { sx = a; sy = b; }
@@ -376,12 +400,17 @@ struct s2m_result {
   s2m_mesh_params params{};
   GridDev grid{};
   uint32_t z_first = 0, nz = 0, label_add = 0, halo = 0, words_x = 0;
-  uint32_t slab_first_plane = 0, slab_n_planes = 0;
   uint64_t n_cand = 0, n_vert_total = 0, n_halo = 0, n_quads = 0, n_invalid = 0;
   float* h_pos = nullptr; float* h_nrm = nullptr; uint64_t* h_key = nullptr; uint8_t* h_nib = nullptr;
   uint64_t* h_quads = nullptr; uint64_t* h_cand = nullptr;
+  uint64_t cap_v = 0, cap_q = 0;   // capacity (elements) of the pinned vertex / quad blocks
+  bool streamed = false;           // vertex (and quad) chunks were copied while later chunks computed
+  bool quads_done = false;         // K4b ran inside begin (single-slab s2m_mesh_run)
   s2m_timings t{};
   double wall0 = 0;
+  size_t ev_used = 0;              // events taken from the ctx pool by this run
+  struct Span { int kind; size_t e0, e1; };  // kind: 0 K1, 1 K2, 2 K3, 3 K4a, 4 K4b, 5 copy
+  std::vector<Span> spans;
   bool finished = false;
 };
 
@@ -413,18 +442,121 @@ extern "C" int s2m_params_from_cli(uint32_t resolution, float bounds, s2m_mesh_p
   return S2M_OK;
 }
 
-extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_result** out) {
+namespace {
+
+// One z-chunk of the pipeline.  Slices are local to the slab: slice 0 == true slice r->z_first.
+struct Chunk { uint32_t z0, nzc; };
+
+size_t take_event(s2m_ctx* c, s2m_result* r) {
+  if (r->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  return r->ev_used++;
+}
+#define SPAN_BEGIN(kind_, stream_) \
+  const size_t span_e0__ = take_event(c, r); CUDA_TRY(cudaEventRecord(c->ev_pool[span_e0__], stream_)); const int span_kind__ = kind_
+#define SPAN_END(stream_) \
+  do { const size_t e1__ = take_event(c, r); CUDA_TRY(cudaEventRecord(c->ev_pool[e1__], stream_)); r->spans.push_back({span_kind__, span_e0__, e1__}); } while (0)
+
+int ensure_pinned_outputs(s2m_ctx* c, s2m_result* r, uint64_t need_v, uint64_t need_q, bool want_quads) {
+  if (need_v > r->cap_v || !r->h_pos) {
+    for (void* p : {(void*)r->h_pos, (void*)r->h_nrm, (void*)r->h_key, (void*)r->h_nib}) if (p) c->release_pinned(p);
+    r->h_pos = (float*)c->lease_pinned(need_v * 12);
+    r->h_nrm = (float*)c->lease_pinned(need_v * 12);
+    r->h_key = (uint64_t*)c->lease_pinned(need_v * 8);
+    r->h_nib = (uint8_t*)c->lease_pinned(need_v);
+    if (!r->h_pos || !r->h_nrm || !r->h_key || !r->h_nib) return fail(S2M_ERR_OOM, "cudaHostAlloc for vertex output failed");
+    r->cap_v = need_v;
+  }
+  if (want_quads && (need_q > r->cap_q || !r->h_quads)) {
+    if (r->h_quads) c->release_pinned(r->h_quads);
+    r->h_quads = (uint64_t*)c->lease_pinned(need_q * 32);
+    if (!r->h_quads) return fail(S2M_ERR_OOM, "cudaHostAlloc for quad output failed");
+    r->cap_q = need_q;
+  }
+  return S2M_OK;
+}
+
+// device -> pinned host copies of vertices [v0, v1) (indices include the halo) and quads [q0, q1)
+int copy_out(s2m_ctx* c, s2m_result* r, cudaStream_t st, uint64_t v0, uint64_t v1, uint64_t q0, uint64_t q1) {
+  v0 = std::max<uint64_t>(v0, r->n_halo);
+  if (v1 > v0) {
+    const uint64_t n = v1 - v0, h = v0 - r->n_halo;
+    CUDA_TRY(cudaMemcpyAsync(r->h_pos + 3 * h, c->v_pos.as<float>() + 3 * v0, n * 12, cudaMemcpyDeviceToHost, st));
+    if (!(r->params.flags & S2M_MESH_NO_NORMALS))
+      CUDA_TRY(cudaMemcpyAsync(r->h_nrm + 3 * h, c->v_nrm.as<float>() + 3 * v0, n * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(r->h_key + h, c->v_key.as<unsigned long long>() + v0, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(r->h_nib + h, c->v_nib.as<unsigned char>() + v0, n, cudaMemcpyDeviceToHost, st));
+  }
+  if (q1 > q0) CUDA_TRY(cudaMemcpyAsync(r->h_quads + 4 * q0, c->quads.as<unsigned long long>() + 4 * q0, (q1 - q0) * 32, cudaMemcpyDeviceToHost, st));
+  return S2M_OK;
+}
+
+int launch_k4b(s2m_ctx* c, s2m_result* r, cudaStream_t s, uint64_t v_begin, uint64_t v_end, uint64_t quad_base, long long index_offset) {
+  unsigned long long* d_cnt = c->counters.as<unsigned long long>();
+  v_begin = std::max<uint64_t>(v_begin, r->n_halo);
+  if (v_end <= v_begin) return S2M_OK;
+  const unsigned tiles = s2m_k4b_tiles(v_end - v_begin);
+  int st;
+  if ((st = c->quads.ensure_preserve((size_t)(quad_base + (v_end - v_begin) * 3) * 32 + 64, (size_t)quad_base * 32, s))) return st;
+  if ((st = c->scratch.ensure(((size_t)tiles + 8) * 8 + 64))) return st;
+  CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, ((size_t)tiles + 8) * 8 + 64, s));
+  S2mK4bArgs a{};
+  a.vert_key = c->v_key.as<unsigned long long>(); a.vert_nibble = c->v_nib.as<unsigned char>();
+  a.v_begin = v_begin; a.v_end = v_end; a.quad_base = quad_base;
+  a.cand_mask = c->cand_mask.as<uint32_t>(); a.word_prefix = c->word_prefix.as<uint32_t>(); a.cand_vrank = c->cand_vrank.as<uint32_t>();
+  a.words_x = r->words_x; a.res_y = r->grid.res[1]; a.z_first = r->z_first; a.label_add = r->label_add;
+  a.index_offset = index_offset;
+  a.quads = c->quads.as<unsigned long long>(); a.status = c->scratch.as<unsigned long long>() + 1;
+  a.ticket = reinterpret_cast<unsigned*>(c->scratch.p); a.n_quads = d_cnt + C_NQUAD; a.n_invalid = d_cnt + C_NINVALID;
+  SPAN_BEGIN(4, s);
+  int e = s2m_launch_k4b(&a, s);
+  if (e) return fail(S2M_ERR_CUDA, std::string("k4_quads launch: ") + cudaGetErrorString((cudaError_t)e));
+  SPAN_END(s);
+  r->t.launches += 1;
+  return S2M_OK;
+}
+
+int read_counters(s2m_ctx* c, cudaStream_t s) {
+  CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, C_COUNT * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return S2M_OK;
+}
+
+void finalize_timings(s2m_ctx* c, s2m_result* r) {
+  float acc[6] = {0, 0, 0, 0, 0, 0};
+  for (const auto& sp : r->spans) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev_pool[sp.e0], c->ev_pool[sp.e1]);
+    acc[sp.kind] += ms;
+  }
+  r->t.k1_slab_ms = acc[0]; r->t.k2_classify_ms = acc[1]; r->t.k3_compact_ms = acc[2];
+  r->t.k4_vertices_ms = acc[3]; r->t.k4_quads_ms = acc[4]; r->t.d2h_ms = acc[5];
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); r->t.device_ms = ms;
+  cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]); r->t.total_ms = ms;
+}
+
+// The pipeline.  For every z-chunk: K1 slab -> K2 classify -> [count] -> K3 compact -> K4a vertices
+// -> [count] -> (K4b quads -> [count]) -> async copy of the chunk's vertices (and quads) into pinned
+// host memory on the copy stream, overlapping the next chunk's kernels.  [count] = the host reads
+// 8 bytes to size the next launch.
+int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fuse_quads, s2m_result** out) {
   if (!c || !m || !p || !out) return fail(S2M_ERR_INVALID_ARG, "s2m_mesh_begin: NULL argument");
   *out = nullptr;
   if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
   if (c->busy) return fail(S2M_ERR_STATE, "a previous s2m_mesh_begin on this ctx has not been finished or freed");
   CUDA_TRY(cudaSetDevice(c->device));
-  std::unique_ptr<s2m_result> r(new s2m_result());
+  std::unique_ptr<s2m_result> rp(new s2m_result());
+  s2m_result* r = rp.get();
   r->ctx = c; r->mod = m; r->params = *p;
   int st = make_grid(p, &r->grid);
   if (st) return st;
   const GridDev& g = r->grid;
   const bool all = p->flags & S2M_MESH_ALL_SLICES;
+  const bool dense = p->flags & S2M_MESH_EXACT_DENSE;
   const uint32_t zlast = all ? g.res[2] : g.res[2] - 1u;  // the last slice is never read back
   uint32_t zb = p->z_begin, ze = p->z_end;
   if (zb == 0 && ze == 0) ze = zlast;
@@ -435,6 +567,7 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
   r->z_first = zb - r->halo;
   r->nz = ze - r->z_first;
   r->words_x = (g.res[0] + 31u) / 32u;
+  if (r->halo) fuse_quads = false;  // a halo means there are lower slabs: the global vertex base comes later
   const float min_size = std::min(g.size[0], std::min(g.size[1], g.size[2]));
   const float tau = (p->tau_voxels > 0.0f ? p->tau_voxels : 0.5f) * min_size;
 
@@ -446,7 +579,6 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
   unsigned long long* d_cnt = c->counters.as<unsigned long long>();
   CUDA_TRY(cudaMemsetAsync(d_cnt, 0, C_COUNT * 8, s));
   CUDA_TRY(cudaEventRecord(c->ev[0], s));
-  uint32_t launches = 0, chunks = 0;
 
   const unsigned long long words_per_slice = (unsigned long long)g.res[1] * r->words_x;
   const unsigned long long n_words = words_per_slice * r->nz;
@@ -454,145 +586,193 @@ extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
     if ((st = c->cand_mask.ensure((n_words + 16) * 4))) return st;
     if ((st = c->word_prefix.ensure((n_words + 16) * 4))) return st;
   }
-  // ---- K1 + K2 over z-chunks of the slab
-  if (r->nz > 0 && !(p->flags & S2M_MESH_EXACT_DENSE)) {
-    tr.mark("setup");
-    // No cudaMemGetInfo here: it costs 0.1-3.5 ms per call on a B200 and the answer only matters
-    // the first time.  Default budget: a third of the device (<= 64 GiB), halved on OOM.
-    const unsigned long long plane_bytes = g.plane_stride * 4ull;
-    unsigned long long budget = p->slab_budget_bytes ? p->slab_budget_bytes
-                                                     : std::min<unsigned long long>((unsigned long long)c->prop.totalGlobalMem / 3, 64ull << 30);
+  // ---- chunk plan: bounded slab, and enough chunks that the copies hide behind later chunks
+  std::vector<Chunk> chunks;
+  const unsigned long long plane_bytes = g.plane_stride * 4ull;
+  if (r->nz > 0) {
+    unsigned long long budget = p->slab_budget_bytes ? p->slab_budget_bytes : (4ull << 30);
     uint32_t zc = 0;
     for (;;) {
-      unsigned long long max_planes = std::max<unsigned long long>(2, budget / plane_bytes);
+      const unsigned long long max_planes = std::max<unsigned long long>(2, budget / plane_bytes);
       zc = (uint32_t)std::min<unsigned long long>(r->nz, max_planes - 1);
+      if (dense) break;
       st = c->slab.ensure((unsigned long long)(zc + 1) * plane_bytes);
       if (st == S2M_OK) break;
       if (st != S2M_ERR_OOM || zc <= 1) return st;
       budget = (unsigned long long)(zc + 1) * plane_bytes / 2;
     }
-    for (uint32_t z0 = 0; z0 < r->nz; z0 += zc) {
-      const uint32_t nzc = std::min(zc, r->nz - z0);
+    const uint32_t n_chunks = (r->nz + zc - 1) / zc;
+    const uint32_t even = (r->nz + n_chunks - 1) / n_chunks;  // equal chunks instead of a short last one
+    for (uint32_t z0 = 0; z0 < r->nz; z0 += even) chunks.push_back({z0, std::min(even, r->nz - z0)});
+  }
+  r->t.chunks = (uint32_t)chunks.size();
+  // pinned output sized from the previous run on this ctx (if any): lets chunk copies start early
+  const bool can_stream = c->hint_nv > 0;
+  if (can_stream) {
+    if ((st = ensure_pinned_outputs(c, r, c->hint_nv + c->hint_nv / 32 + 4096, c->hint_nq + c->hint_nq / 32 + 4096, fuse_quads))) return st;
+    r->streamed = true;
+  }
+  tr.mark("setup");
+
+  uint64_t cand_done = 0, vert_done = 0, quad_done = 0;
+  std::vector<uint32_t> dense_row;
+  for (size_t ci = 0; ci < chunks.size(); ++ci) {
+    const Chunk ch = chunks[ci];
+    const unsigned long long chunk_words = words_per_slice * ch.nzc;
+    uint32_t* mask_chunk = c->cand_mask.as<uint32_t>() + words_per_slice * ch.z0;
+    unsigned slab_first_plane = 0, slab_n_planes = 0;
+    if (!dense) {
+      // ---- K1
       GridDev gd = g;
       float* slab = c->slab.as<float>();
-      unsigned first_plane = r->z_first + z0, n_planes = nzc + 1;
+      unsigned first_plane = r->z_first + ch.z0, n_planes = ch.nzc + 1;
       void* a1[] = {&gd, &slab, &first_plane, &n_planes};
       unsigned bx, by;
       k1_block_shape(&bx, &by);
       dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by - 1u) / by, n_planes);
-      if (chunks == 0) CUDA_TRY(cudaEventRecord(c->ev[1], s));
-      if ((st = launch(m->k1, grid1, dim3(bx, by, 1), s, a1, "s2m_k1_slab"))) return st;
-      r->slab_first_plane = first_plane; r->slab_n_planes = n_planes;  // what stays resident for K4a
+      {
+        SPAN_BEGIN(0, s);
+        if ((st = launch(m->k1, grid1, dim3(bx, by, 1), s, a1, "s2m_k1_slab"))) return st;
+        SPAN_END(s);
+      }
+      slab_first_plane = first_plane; slab_n_planes = n_planes;
+      // ---- K2
       S2mK2Args a2{};
       a2.slab = slab; a2.pitch_x = g.pitch_x; a2.plane_stride = g.plane_stride;
-      a2.res_x = g.res[0]; a2.res_y = g.res[1]; a2.nz_chunk = nzc; a2.tau = tau;
-      a2.cand_mask = c->cand_mask.as<uint32_t>() + words_per_slice * z0;
-      a2.words_x = r->words_x; a2.total = d_cnt + C_NCAND;
-      if (chunks == 0) CUDA_TRY(cudaEventRecord(c->ev[2], s));
-      int e2 = s2m_launch_k2(&a2, s);
-      if (e2) return fail(S2M_ERR_CUDA, std::string("k2_classify launch: ") + cudaGetErrorString((cudaError_t)e2));
-      launches += 2; ++chunks;
+      a2.res_x = g.res[0]; a2.res_y = g.res[1]; a2.nz_chunk = ch.nzc; a2.tau = tau;
+      a2.cand_mask = mask_chunk; a2.words_x = r->words_x; a2.total = d_cnt + C_NCAND;
+      {
+        SPAN_BEGIN(1, s);
+        int e2 = s2m_launch_k2(&a2, s);
+        if (e2) return fail(S2M_ERR_CUDA, std::string("k2_classify launch: ") + cudaGetErrorString((cudaError_t)e2));
+        SPAN_END(s);
+      }
+      r->t.launches += 2;
+    } else {
+      // reference-cost mode: every cell of the chunk is a candidate
+      if (dense_row.empty()) {
+        dense_row.assign(r->words_x, 0xffffffffu);
+        if (g.res[0] % 32u) dense_row.back() = (1u << (g.res[0] % 32u)) - 1u;
+      }
+      std::vector<uint32_t> host(chunk_words);
+      for (unsigned long long i = 0; i < chunk_words; i += r->words_x) memcpy(&host[i], dense_row.data(), r->words_x * 4);
+      CUDA_TRY(cudaMemcpyAsync(mask_chunk, host.data(), chunk_words * 4, cudaMemcpyHostToDevice, s));
+      const unsigned long long nc = cand_done + (unsigned long long)g.res[0] * g.res[1] * ch.nzc;
+      CUDA_TRY(cudaMemcpyAsync(d_cnt + C_NCAND, &nc, 8, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
     }
-  } else if (r->nz > 0) {
-    // reference-cost mode: every cell is a candidate
-    std::vector<uint32_t> row(r->words_x, 0xffffffffu);
-    if (g.res[0] % 32u) row.back() = (1u << (g.res[0] % 32u)) - 1u;
-    std::vector<uint32_t> host(n_words);
-    for (unsigned long long i = 0; i < n_words; i += r->words_x) memcpy(&host[i], row.data(), r->words_x * 4);
-    CUDA_TRY(cudaMemcpyAsync(c->cand_mask.p, host.data(), n_words * 4, cudaMemcpyHostToDevice, s));
-    unsigned long long nc = (unsigned long long)g.res[0] * g.res[1] * r->nz;
-    CUDA_TRY(cudaMemcpyAsync(d_cnt + C_NCAND, &nc, 8, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaEventRecord(c->ev[1], s));
-    CUDA_TRY(cudaEventRecord(c->ev[2], s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-  } else {
-    CUDA_TRY(cudaEventRecord(c->ev[1], s));
-    CUDA_TRY(cudaEventRecord(c->ev[2], s));
+    // ---- [count] candidates of this chunk
+    if ((st = read_counters(c, s))) return st;
+    const uint64_t cand_total = c->h_counters[C_NCAND];
+    const uint64_t n_cand = cand_total - cand_done;
+    if (cand_total >= 0xffffffffull) return fail(S2M_ERR_UNSUPPORTED, "more than 2^32-1 candidate cells in one slab; split it with z_begin/z_end");
+    const unsigned k3_tiles = s2m_k3_tiles(chunk_words);
+    const unsigned k4_tiles = (unsigned)((n_cand + 127) / 128);
+    const size_t status_words = (size_t)k3_tiles + k4_tiles + 16;
+    if ((st = c->status.ensure(status_words * 8))) return st;
+    if ((st = c->cand_key.ensure_preserve((cand_total + 1) * 8, cand_done * 8, s))) return st;
+    if ((st = c->cand_vrank.ensure_preserve((cand_total + 1) * 4, cand_done * 4, s))) return st;
+    if ((st = c->v_pos.ensure_preserve((vert_done + n_cand + 1) * 12, vert_done * 12, s))) return st;
+    if ((st = c->v_nrm.ensure_preserve((vert_done + n_cand + 1) * 12, vert_done * 12, s))) return st;
+    if ((st = c->v_key.ensure_preserve((vert_done + n_cand + 1) * 8, vert_done * 8, s))) return st;
+    if ((st = c->v_nib.ensure_preserve(vert_done + n_cand + 16, vert_done, s))) return st;
+    CUDA_TRY(cudaMemsetAsync(c->status.p, 0, status_words * 8, s));
+    unsigned long long* status = c->status.as<unsigned long long>();
+    unsigned* tickets = reinterpret_cast<unsigned*>(status);  // words 0..1: tickets; 2..: tile status
+    // ---- K3
+    {
+      S2mK3Args a3{};
+      a3.cand_mask = mask_chunk; a3.n_words = chunk_words; a3.words_x = r->words_x; a3.res_y = g.res[1];
+      a3.z_offset = r->z_first + ch.z0; a3.word_prefix = c->word_prefix.as<uint32_t>() + words_per_slice * ch.z0;
+      a3.cand_key = c->cand_key.as<unsigned long long>(); a3.base = cand_done;
+      a3.status = status + 2; a3.ticket = tickets;
+      SPAN_BEGIN(2, s);
+      int e3 = s2m_launch_k3(&a3, s);
+      if (e3) return fail(S2M_ERR_CUDA, std::string("k3_compact launch: ") + cudaGetErrorString((cudaError_t)e3));
+      SPAN_END(s);
+      r->t.launches += 1;
+    }
+    // ---- K4a
+    if (k4_tiles) {
+      GridDev gd = g;
+      const unsigned long long* ck = c->cand_key.as<unsigned long long>() + cand_done;
+      unsigned long long nc = n_cand, vbase = vert_done;
+      unsigned label_add = r->label_add, halo_below = r->halo ? (r->z_first + 1u) : 0u;
+      unsigned want_normals = (p->flags & S2M_MESH_NO_NORMALS) ? 0u : 1u;
+      SlabViewDev sv{c->slab.as<float>(), slab_first_plane, slab_n_planes};
+      VertexOutDev vo{c->v_pos.as<float>(), c->v_nrm.as<float>(), c->v_key.as<unsigned long long>(), c->v_nib.as<unsigned char>(),
+                      c->cand_vrank.as<unsigned>() + cand_done, status + 2 + k3_tiles, tickets + 1, d_cnt + C_NVERT, d_cnt + C_NHALO};
+      void* a4[] = {&gd, &ck, &nc, &vbase, &label_add, &halo_below, &want_normals, &sv, &vo};
+      SPAN_BEGIN(3, s);
+      if ((st = launch(m->k4, dim3(k4_tiles), dim3(128), s, a4, "s2m_k4_vertices"))) return st;
+      SPAN_END(s);
+      r->t.launches += 1;
+    }
+    // ---- [count] vertices so far
+    uint64_t vert_total = vert_done;
+    if (k4_tiles) {
+      if ((st = read_counters(c, s))) return st;
+      vert_total = c->h_counters[C_NVERT];
+      r->n_halo = c->h_counters[C_NHALO];
+    }
+    // ---- K4b (single-slab runs only: the global vertex base is 0)
+    uint64_t quad_total = quad_done;
+    if (fuse_quads && vert_total > vert_done) {
+      if ((st = launch_k4b(c, r, s, vert_done, vert_total, quad_done, 0))) return st;
+      if ((st = read_counters(c, s))) return st;
+      quad_total = c->h_counters[C_NQUAD];
+    }
+    // ---- copy this chunk's output while the next chunk computes
+    if (r->streamed) {
+      const uint64_t own = vert_total - std::min<uint64_t>(vert_total, r->n_halo);
+      if (own > r->cap_v || (fuse_quads && quad_total > r->cap_q)) {
+        r->streamed = false;  // the hint was too small: everything is copied at the end instead
+      } else {
+        const size_t e = take_event(c, r);
+        CUDA_TRY(cudaEventRecord(c->ev_pool[e], s));
+        CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_pool[e], 0));
+        SPAN_BEGIN(5, c->copy_stream);
+        if ((st = copy_out(c, r, c->copy_stream, vert_done, vert_total, quad_done, fuse_quads ? quad_total : quad_done))) return st;
+        SPAN_END(c->copy_stream);
+      }
+    }
+    cand_done = cand_total; vert_done = vert_total; quad_done = quad_total;
+    tr.mark("chunk done");
   }
-  CUDA_TRY(cudaEventRecord(c->ev[3], s));
-  tr.mark("K1+K2 launched");
-  r->t.chunks = chunks;
-  // ---- sync #1: candidate count sizes everything downstream
-  CUDA_TRY(cudaMemcpyAsync(c->h_counters, d_cnt, 8, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  r->n_cand = c->h_counters[0];
-  tr.mark("sync #1 (candidates)");
-  if (r->n_cand >= 0xffffffffull) return fail(S2M_ERR_UNSUPPORTED, "more than 2^32-1 candidate cells in one slab; split it with z_begin/z_end");
-
-  const unsigned k3_tiles = r->nz ? s2m_k3_tiles(n_words) : 0;
-  const unsigned k4_tiles = (unsigned)((r->n_cand + 127) / 128);
-  const size_t status_words = (size_t)k3_tiles + k4_tiles + 8;
-  if ((st = c->status.ensure(status_words * 8))) return st;
-  if ((st = c->cand_key.ensure((r->n_cand + 1) * 8))) return st;
-  if ((st = c->cand_vrank.ensure((r->n_cand + 1) * 4))) return st;
-  if ((st = c->v_pos.ensure((r->n_cand + 1) * 12))) return st;
-  if ((st = c->v_nrm.ensure((r->n_cand + 1) * 12))) return st;
-  if ((st = c->v_key.ensure((r->n_cand + 1) * 8))) return st;
-  if ((st = c->v_nib.ensure(r->n_cand + 16))) return st;
-  CUDA_TRY(cudaMemsetAsync(c->status.p, 0, status_words * 8, s));
-  // ---- K3
-  CUDA_TRY(cudaEventRecord(c->ev[4], s));
-  if (k3_tiles) {
-    S2mK3Args a3{};
-    a3.cand_mask = c->cand_mask.as<uint32_t>(); a3.n_words = n_words; a3.words_x = r->words_x; a3.res_y = g.res[1];
-    a3.z_offset = r->z_first; a3.word_prefix = c->word_prefix.as<uint32_t>(); a3.cand_key = c->cand_key.as<unsigned long long>();
-    a3.status = c->status.as<unsigned long long>(); a3.ticket = reinterpret_cast<unsigned*>(d_cnt + C_TICKET0);
-    int e3 = s2m_launch_k3(&a3, s);
-    if (e3) return fail(S2M_ERR_CUDA, std::string("k3_compact launch: ") + cudaGetErrorString((cudaError_t)e3));
-    ++launches;
-  }
-  CUDA_TRY(cudaEventRecord(c->ev[5], s));
-  // ---- K4a
-  if (k4_tiles) {
-    GridDev gd = g;
-    const unsigned long long* ck = c->cand_key.as<unsigned long long>();
-    unsigned long long nc = r->n_cand;
-    unsigned label_add = r->label_add, halo_below = r->halo ? (r->z_first + 1u) : 0u;
-    unsigned want_normals = (p->flags & S2M_MESH_NO_NORMALS) ? 0u : 1u;
-    VertexOutDev vo{c->v_pos.as<float>(), c->v_nrm.as<float>(), c->v_key.as<unsigned long long>(), c->v_nib.as<unsigned char>(),
-                    c->cand_vrank.as<unsigned>(), c->status.as<unsigned long long>() + k3_tiles,
-                    reinterpret_cast<unsigned*>(d_cnt + C_TICKET1), d_cnt + C_NVERT, d_cnt + C_NHALO};
-    SlabViewDev sv{c->slab.as<float>(), r->slab_first_plane, r->slab_n_planes};
-    void* a4[] = {&gd, &ck, &nc, &label_add, &halo_below, &want_normals, &sv, &vo};
-    if ((st = launch(m->k4, dim3(k4_tiles), dim3(128), s, a4, "s2m_k4_vertices"))) return st;
-    ++launches;
-  }
-  CUDA_TRY(cudaEventRecord(c->ev[6], s));
-  tr.mark("K3+K4a launched");
-  // ---- sync #2: vertex counts
-  CUDA_TRY(cudaMemcpyAsync(c->h_counters, d_cnt, C_COUNT * 8, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  r->n_vert_total = c->h_counters[C_NVERT];
-  r->n_halo = c->h_counters[C_NHALO];
+  r->n_cand = cand_done;
+  r->n_vert_total = vert_done;
   const uint64_t n_own = r->n_vert_total - r->n_halo;
-  tr.mark("sync #2 (vertices)");
-  // ---- vertices -> pinned host (copy stream; overlaps the quad kernel)
-  r->h_pos = (float*)c->lease_pinned(n_own * 12);
-  r->h_nrm = (float*)c->lease_pinned(n_own * 12);
-  r->h_key = (uint64_t*)c->lease_pinned(n_own * 8);
-  r->h_nib = (uint8_t*)c->lease_pinned(n_own);
-  if (!r->h_pos || !r->h_nrm || !r->h_key || !r->h_nib) return fail(S2M_ERR_OOM, "cudaHostAlloc for vertex output failed");
+  if (fuse_quads) {
+    r->quads_done = true;
+    r->n_quads = quad_done;
+    if ((st = read_counters(c, s))) return st;
+    r->n_invalid = c->h_counters[C_NINVALID];
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[1], s));  // device_ms: every kernel of begin() has finished
+  // ---- whatever has not been streamed is copied now
+  if (!r->streamed) {
+    if ((st = ensure_pinned_outputs(c, r, n_own, fuse_quads ? r->n_quads : 0, fuse_quads))) return st;
+    SPAN_BEGIN(5, s);
+    if ((st = copy_out(c, r, s, 0, r->n_vert_total, 0, fuse_quads ? r->n_quads : 0))) return st;
+    SPAN_END(s);
+  }
+  if (p->flags & S2M_MESH_NO_NORMALS) memset(r->h_nrm, 0, n_own * 12);
   if (p->flags & S2M_MESH_KEEP_CANDIDATES) {
     r->h_cand = (uint64_t*)c->lease_pinned(r->n_cand * 8);
     if (!r->h_cand) return fail(S2M_ERR_OOM, "cudaHostAlloc for candidate list failed");
+    if (r->n_cand) CUDA_TRY(cudaMemcpyAsync(r->h_cand, c->cand_key.p, r->n_cand * 8, cudaMemcpyDeviceToHost, s));
   }
-  CUDA_TRY(cudaEventRecord(c->ev[7], s));
-  CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev[7], 0));
-  if (n_own) {
-    CUDA_TRY(cudaMemcpyAsync(r->h_pos, c->v_pos.as<float>() + 3 * r->n_halo, n_own * 12, cudaMemcpyDeviceToHost, c->copy_stream));
-    if (p->flags & S2M_MESH_NO_NORMALS) memset(r->h_nrm, 0, n_own * 12);
-    else CUDA_TRY(cudaMemcpyAsync(r->h_nrm, c->v_nrm.as<float>() + 3 * r->n_halo, n_own * 12, cudaMemcpyDeviceToHost, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(r->h_key, c->v_key.as<unsigned long long>() + r->n_halo, n_own * 8, cudaMemcpyDeviceToHost, c->copy_stream));
-    CUDA_TRY(cudaMemcpyAsync(r->h_nib, c->v_nib.as<unsigned char>() + r->n_halo, n_own, cudaMemcpyDeviceToHost, c->copy_stream));
-  }
-  if (r->h_cand && r->n_cand)
-    CUDA_TRY(cudaMemcpyAsync(r->h_cand, c->cand_key.p, r->n_cand * 8, cudaMemcpyDeviceToHost, c->copy_stream));
-  CUDA_TRY(cudaEventRecord(c->ev[8], c->copy_stream));
-  r->t.launches = launches;
-  tr.mark("vertex copies queued");
+  c->hint_nv = n_own;
+  tr.mark("begin done");
   guard.keep = true;
-  *out = r.release();
+  *out = rp.release();
   return S2M_OK;
+}
+
+}  // namespace
+
+extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_result** out) {
+  return mesh_begin_impl(c, m, p, false, out);
 }
 
 extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
@@ -602,61 +782,41 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   Trace tr;
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
-  unsigned long long* d_cnt = c->counters.as<unsigned long long>();
-  const uint64_t n_own = r->n_vert_total - r->n_halo;
-  const unsigned tiles = s2m_k4b_tiles(n_own);
   int st;
-  if ((st = c->quads.ensure((size_t)n_own * 3 * 32 + 64))) return st;
-  if ((st = c->scratch.ensure(((size_t)tiles + 8) * 8))) return st;
-  CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, ((size_t)tiles + 8) * 8, s));
-  CUDA_TRY(cudaEventRecord(c->ev[9], s));
-  if (tiles) {
-    S2mK4bArgs a{};
-    a.vert_key = c->v_key.as<unsigned long long>(); a.vert_nibble = c->v_nib.as<unsigned char>();
-    a.n_vertices = r->n_vert_total; a.n_halo = r->n_halo;
-    a.cand_mask = c->cand_mask.as<uint32_t>(); a.word_prefix = c->word_prefix.as<uint32_t>(); a.cand_vrank = c->cand_vrank.as<uint32_t>();
-    a.words_x = r->words_x; a.res_y = r->grid.res[1]; a.z_first = r->z_first; a.label_add = r->label_add;
-    a.index_offset = (long long)global_vertex_base - (long long)r->n_halo;
-    a.quads = c->quads.as<unsigned long long>(); a.status = c->scratch.as<unsigned long long>();
-    a.ticket = reinterpret_cast<unsigned*>(d_cnt + C_TICKET2); a.n_quads = d_cnt + C_NQUAD; a.n_invalid = d_cnt + C_NINVALID;
-    int e = s2m_launch_k4b(&a, s);
-    if (e) return fail(S2M_ERR_CUDA, std::string("k4_quads launch: ") + cudaGetErrorString((cudaError_t)e));
-    r->t.launches += 1;
+  if (!r->quads_done) {
+    // ---- K4b over all own vertices with the global base, then the quad copy
+    if ((st = launch_k4b(c, r, s, 0, r->n_vert_total, 0, (long long)global_vertex_base - (long long)r->n_halo))) return st;
+    CUDA_TRY(cudaEventRecord(c->ev[1], s));
+    if ((st = read_counters(c, s))) return st;
+    r->n_quads = c->h_counters[C_NQUAD];
+    r->n_invalid = c->h_counters[C_NINVALID];
+    if ((st = ensure_pinned_outputs(c, r, r->cap_v, r->n_quads, true))) return st;
+    SPAN_BEGIN(5, s);
+    if ((st = copy_out(c, r, s, 0, 0, 0, r->n_quads))) return st;
+    SPAN_END(s);
+    r->quads_done = true;
+  } else if (global_vertex_base != 0) {
+    return fail(S2M_ERR_STATE, "quads were already emitted with base 0 (s2m_mesh_run); use s2m_mesh_begin for multi-slab runs");
   }
-  CUDA_TRY(cudaEventRecord(c->ev[10], s));
-  // ---- sync #3: quad counts
-  CUDA_TRY(cudaMemcpyAsync(c->h_counters, d_cnt, C_COUNT * 8, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
-  r->n_quads = c->h_counters[C_NQUAD];
-  r->n_invalid = c->h_counters[C_NINVALID];
-  tr.mark("finish: sync #3 (quads)");
-  r->h_quads = (uint64_t*)c->lease_pinned(r->n_quads * 32);
-  if (!r->h_quads) return fail(S2M_ERR_OOM, "cudaHostAlloc for quad output failed");
-  if (r->n_quads) CUDA_TRY(cudaMemcpyAsync(r->h_quads, c->quads.p, r->n_quads * 32, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamWaitEvent(s, c->ev[8], 0));  // the vertex copies are part of the end-to-end span
-  CUDA_TRY(cudaEventRecord(c->ev[11], s));
+  c->hint_nq = r->n_quads;
+  {  // everything (both streams) done -> total span
+    const size_t e = take_event(c, r);
+    CUDA_TRY(cudaEventRecord(c->ev_pool[e], c->copy_stream));
+    CUDA_TRY(cudaStreamWaitEvent(s, c->ev_pool[e], 0));
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[2], s));
   CUDA_TRY(cudaStreamSynchronize(s));
   CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
   tr.mark("finish: copies done");
   r->t.host_wall_ms = now_ms() - r->wall0;
-  auto el = [&](int a, int b) { float ms = 0; cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]); return ms; };
-  // single-chunk runs time K1 and K2 separately; chunked runs report their sum under k1 (interleaved)
-  if (r->t.chunks <= 1) { r->t.k1_slab_ms = el(1, 2); r->t.k2_classify_ms = el(2, 3); }
-  else { r->t.k1_slab_ms = el(1, 3); r->t.k2_classify_ms = 0; }
-  r->t.k3_compact_ms = el(4, 5);
-  r->t.k4_vertices_ms = el(5, 6);
-  r->t.k4_quads_ms = el(9, 10);
-  float d2h_v = el(7, 8), d2h_q = el(10, 11);
-  r->t.d2h_ms = d2h_v + d2h_q;
-  r->t.device_ms = el(0, 10);
-  r->t.total_ms = el(0, 11);
+  finalize_timings(c, r);
   r->finished = true;
   c->busy = false;
   return S2M_OK;
 }
 
 extern "C" int s2m_mesh_run(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_result** out) {
-  int st = s2m_mesh_begin(c, m, p, out);
+  int st = mesh_begin_impl(c, m, p, true, out);
   if (st) return st;
   st = s2m_mesh_finish(*out, 0);
   if (st) { s2m_result_free(*out); *out = nullptr; }

@@ -15,6 +15,10 @@
  *     s2m_k_cost_probe per-z-plane evaluation cost estimate used to balance multi-GPU z-slabs.
  */
 
+#ifndef S2M_K1_UNROLL
+#define S2M_K1_UNROLL 4
+#endif
+
 struct S2mGrid {
   float bmin[3];
   float size[3];      /* (bmax - bmin) / f32(res - 1), computed on the host in f32 (IEEE division) */
@@ -44,15 +48,22 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   if (x4 >= g.pitch_x || y >= g.rows || pz >= n_planes) return;
   const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
   const float cy = g.bmin[1] + g.size[1] * (float)y;
-  float v[4];
+  /* S2M_K1_UNROLL=1 keeps ONE inlined copy of the SDF in the kernel (4x less code: the mandelbulb
+   * kernel otherwise overflows the instruction cache, ncu: stall_no_instruction); 4 = unrolled. */
+  float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+#if S2M_K1_UNROLL == 1
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int k = 0; k < 4; ++k) {
     const unsigned x = x4 + (unsigned)k;
-    v[k] = (x <= g.res[0]) ? s2m_sdf(g.bmin[0] + g.size[0] * (float)x, cy, cz) : 0.0f;
+    const float val = (x <= g.res[0]) ? s2m_sdf(g.bmin[0] + g.size[0] * (float)x, cy, cz) : 0.0f;
+    if (k == 0) v0 = val; else if (k == 1) v1 = val; else if (k == 2) v2 = val; else v3 = val;
   }
   float4* dst = reinterpret_cast<float4*>(slab + (unsigned long long)pz * g.plane_stride +
                                           (unsigned long long)y * g.pitch_x + x4);
-  *dst = make_float4(v[0], v[1], v[2], v[3]);
+  *dst = make_float4(v0, v1, v2, v3);
 }
 
 /* ------------------------------------------------------------------------------------------ K4a */
@@ -110,10 +121,11 @@ __device__ __forceinline__ unsigned s2m_item_owner(const unsigned* inc, unsigned
  * arguments, same bits); only the rest -- 2.5 of 8 on average at 2048^3 -- are evaluated, and those
  * evaluations plus the 4 normal taps of cells that get a vertex are spread over all 32 lanes.
  *
- * cand_key = x | y<<16 | z_true<<32.  label_add = 1 in faithful mode, else 0. */
+ * cand_key = x | y<<16 | z_true<<32 (this launch's slice of the list; cand_vrank likewise).
+ * vert_base = vertices emitted by earlier chunks.  label_add = 1 in faithful mode. */
 extern "C" __global__ void __launch_bounds__(S2M_K4_THREADS)
 s2m_k4_vertices(S2mGrid g, const unsigned long long* __restrict__ cand_key, unsigned long long n_cand,
-                unsigned label_add, unsigned halo_below, unsigned want_normals, S2mSlabView sv, S2mVertexOut out) {
+                unsigned long long vert_base, unsigned label_add, unsigned halo_below, unsigned want_normals, S2mSlabView sv, S2mVertexOut out) {
   __shared__ unsigned s_scan[33];
   __shared__ unsigned s_tile;
   __shared__ unsigned long long s_base;
@@ -240,7 +252,7 @@ s2m_k4_vertices(S2mGrid g, const unsigned long long* __restrict__ cand_key, unsi
   unsigned total = 0;
   const unsigned local = s2m_block_exclusive_scan(has_vertex ? 1u : 0u, s_scan, &total);
   if (threadIdx.x < 32) {
-    unsigned long long b = s2m_lookback_warp(out.status, tile, (unsigned long long)total, 0ull);
+    unsigned long long b = s2m_lookback_warp(out.status, tile, (unsigned long long)total, vert_base);
     if (threadIdx.x == 0) s_base = b;
   }
   __syncthreads();

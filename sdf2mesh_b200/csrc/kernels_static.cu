@@ -112,7 +112,7 @@ constexpr int K3_TILE_WORDS = K3_THREADS * K3_WORDS_PER_THREAD;
 __global__ void __launch_bounds__(K3_THREADS)
 k3_compact(const uint32_t* __restrict__ cand_mask, unsigned long long n_words, uint32_t words_x, uint32_t res_y,
            uint32_t z_offset, uint32_t* __restrict__ word_prefix, unsigned long long* __restrict__ cand_key,
-           unsigned long long* status, unsigned* ticket) {
+           unsigned long long base, unsigned long long* status, unsigned* ticket) {
   __shared__ unsigned s_scan[33];
   __shared__ unsigned s_tile;
   __shared__ unsigned long long s_base;
@@ -121,7 +121,9 @@ k3_compact(const uint32_t* __restrict__ cand_mask, unsigned long long n_words, u
   const unsigned tile = s_tile;
   const unsigned long long w0 = (unsigned long long)tile * K3_TILE_WORDS + (unsigned long long)threadIdx.x * K3_WORDS_PER_THREAD;
   uint32_t m[K3_WORDS_PER_THREAD];
-  if (w0 + K3_WORDS_PER_THREAD <= n_words) {
+  // a chunk's region starts at a multiple of the per-slice word count, which need not be 16-byte aligned
+  const bool vec_ok = ((reinterpret_cast<unsigned long long>(cand_mask) | reinterpret_cast<unsigned long long>(word_prefix)) & 15ull) == 0ull;
+  if (vec_ok && w0 + K3_WORDS_PER_THREAD <= n_words) {
     const uint4* p = reinterpret_cast<const uint4*>(cand_mask + w0);
 #pragma unroll
     for (int q = 0; q < K3_WORDS_PER_THREAD / 4; ++q) {
@@ -138,7 +140,7 @@ k3_compact(const uint32_t* __restrict__ cand_mask, unsigned long long n_words, u
   unsigned total = 0;
   const unsigned local = s2m_block_exclusive_scan(mine, s_scan, &total);
   if (threadIdx.x < 32) {
-    unsigned long long b = s2m_lookback_warp(status, tile, (unsigned long long)total, 0ull);
+    unsigned long long b = s2m_lookback_warp(status, tile, (unsigned long long)total, base);
     if (threadIdx.x == 0) s_base = b;
   }
   __syncthreads();
@@ -162,7 +164,7 @@ k3_compact(const uint32_t* __restrict__ cand_mask, unsigned long long n_words, u
       }
     }
   }
-  if (w0 + K3_WORDS_PER_THREAD <= n_words) {
+  if (vec_ok && w0 + K3_WORDS_PER_THREAD <= n_words) {
     uint4* o = reinterpret_cast<uint4*>(word_prefix + w0);
 #pragma unroll
     for (int q = 0; q < K3_WORDS_PER_THREAD / 4; ++q) o[q] = make_uint4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
@@ -176,8 +178,8 @@ k3_compact(const uint32_t* __restrict__ cand_mask, unsigned long long n_words, u
 struct QuadParams {
   const unsigned long long* vert_key;   // label keys
   const unsigned char* vert_nibble;
-  unsigned long long n_vertices;        // including halo vertices
-  unsigned long long n_halo;            // leading vertices that belong to the previous slab
+  unsigned long long v_begin, v_end;    // vertices handled by this launch
+  unsigned long long quad_base;         // quads emitted before this launch
   const uint32_t* cand_mask;
   const uint32_t* word_prefix;
   const uint32_t* cand_vrank;
@@ -214,12 +216,12 @@ k4_quads(QuadParams p) {
   if (threadIdx.x == 0) s_tile = atomicAdd(p.ticket, 1u);
   __syncthreads();
   const unsigned tile = s_tile;
-  const unsigned long long n_own = p.n_vertices - p.n_halo;
-  const unsigned long long i = (unsigned long long)tile * blockDim.x + threadIdx.x;  // own vertex ordinal
+  const unsigned long long n_own = p.v_end - p.v_begin;
+  const unsigned long long i = (unsigned long long)tile * blockDim.x + threadIdx.x;  // vertex ordinal in this launch
   uint32_t q[3][4];
   unsigned nvalid = 0, ninvalid = 0;
   if (i < n_own) {
-    const unsigned long long vi = i + p.n_halo;
+    const unsigned long long vi = i + p.v_begin;
     const unsigned long long key = p.vert_key[vi];
     const int x = (int)(key & 0xffffu), y = (int)((key >> 16) & 0xffffu);
     const uint32_t label = (uint32_t)(key >> 32);
@@ -247,7 +249,7 @@ k4_quads(QuadParams p) {
   unsigned total = 0;
   const unsigned local = s2m_block_exclusive_scan(nvalid, s_scan, &total);
   if (threadIdx.x < 32) {
-    unsigned long long b = s2m_lookback_warp(p.status, tile, (unsigned long long)total, 0ull);
+    unsigned long long b = s2m_lookback_warp(p.status, tile, (unsigned long long)total, p.quad_base);
     if (threadIdx.x == 0) s_base = b;
   }
   unsigned inv = ninvalid;
@@ -288,18 +290,18 @@ extern "C" int s2m_launch_k3(const S2mK3Args* a, cudaStream_t stream) {
   const unsigned tiles = s2m_k3_tiles(a->n_words);
   if (!tiles) return 0;
   k3_compact<<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->n_words, a->words_x, a->res_y, a->z_offset,
-                                               a->word_prefix, a->cand_key, a->status, a->ticket);
+                                               a->word_prefix, a->cand_key, a->base, a->status, a->ticket);
   return (int)cudaGetLastError();
 }
 
 extern "C" unsigned s2m_k4b_tiles(unsigned long long n_own) { return (unsigned)((n_own + 255) / 256); }
 
 extern "C" int s2m_launch_k4b(const S2mK4bArgs* a, cudaStream_t stream) {
-  const unsigned long long n_own = a->n_vertices - a->n_halo;
+  const unsigned long long n_own = a->v_end - a->v_begin;
   const unsigned tiles = s2m_k4b_tiles(n_own);
   if (!tiles) return 0;
   QuadParams p;
-  p.vert_key = a->vert_key; p.vert_nibble = a->vert_nibble; p.n_vertices = a->n_vertices; p.n_halo = a->n_halo;
+  p.vert_key = a->vert_key; p.vert_nibble = a->vert_nibble; p.v_begin = a->v_begin; p.v_end = a->v_end; p.quad_base = a->quad_base;
   p.cand_mask = a->cand_mask; p.word_prefix = a->word_prefix; p.cand_vrank = a->cand_vrank;
   p.words_x = a->words_x; p.res_y = a->res_y; p.z_first = a->z_first; p.label_add = a->label_add;
   p.index_offset = a->index_offset; p.quads = a->quads; p.status = a->status; p.ticket = a->ticket;

@@ -25,8 +25,9 @@ typedef struct S2mK3Args {
   unsigned long long n_words;
   uint32_t words_x, res_y;
   uint32_t z_offset;              /* true z of slice 0 of the mask */
-  uint32_t* word_prefix;
-  unsigned long long* cand_key;
+  uint32_t* word_prefix;          /* same region as cand_mask */
+  unsigned long long* cand_key;   /* GLOBAL list: entry `base + local rank` is written */
+  unsigned long long base;        /* candidates in earlier chunks */
   unsigned long long* status;     /* >= s2m_k3_tiles(n_words) zeroed words */
   unsigned* ticket;               /* zeroed */
 } S2mK3Args;
@@ -34,16 +35,17 @@ typedef struct S2mK3Args {
 typedef struct S2mK4bArgs {
   const unsigned long long* vert_key;
   const unsigned char* vert_nibble;
-  unsigned long long n_vertices, n_halo;
+  unsigned long long v_begin, v_end; /* vertices to emit quads for (local indices, halo excluded by the caller) */
+  unsigned long long quad_base;      /* quads emitted by earlier launches */
   const uint32_t* cand_mask;
   const uint32_t* word_prefix;
   const uint32_t* cand_vrank;
   uint32_t words_x, res_y, z_first, label_add;
   long long index_offset;
   unsigned long long* quads;
-  unsigned long long* status;     /* >= s2m_k4b_tiles(n_own) zeroed words */
+  unsigned long long* status;     /* >= s2m_k4b_tiles(v_end - v_begin) zeroed words */
   unsigned* ticket;               /* zeroed */
-  unsigned long long* n_quads;
+  unsigned long long* n_quads;    /* out: quad_base + quads of this launch */
   unsigned long long* n_invalid;  /* accumulates */
 } S2mK4bArgs;
 

@@ -29,6 +29,8 @@ CASES = [
     ("naga_sphere", 64, 2.5, 0),
 ]
 BIG = [("torus", 512, 2.0, 0), ("martin_cube", 512, 2.0, 0), ("mandelbulb", 512, 5.0, 0), ("p_key", 512, 20.0, 0)]
+# headline sizes: minutes of CPU on 16 cores; run on the GPU box's host (`--huge`), output copied back
+HUGE = [("mandelbulb", 1024, 5.0, 0), ("mandelbulb", 2048, 5.0, 0), ("p_key", 1024, 20.0, 0)]
 
 
 def key(c):
@@ -38,7 +40,9 @@ def key(c):
 def main():
     path = os.path.join(HERE, "digests.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
-    cases = CASES + (BIG if "--big" in sys.argv else [])
+    if "--out" in sys.argv:
+        path = sys.argv[sys.argv.index("--out") + 1]
+    cases = CASES + (BIG if "--big" in sys.argv else []) + (HUGE if "--huge" in sys.argv else [])
     for c in cases:
         if key(c) in out and "--force" not in sys.argv:
             continue

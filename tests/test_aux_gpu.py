@@ -113,3 +113,37 @@ def test_cost_probe(ctx):
     cost = s2m.cost_probe(ctx, load_example_shader("mandelbulb").create_shader_module(ctx), p, 32)
     assert len(cost) == 32 and np.all(cost > 0)
     assert cost[12:20].mean() > 2 * cost[[0, 1, 30, 31]].mean(), "the mandelbulb's cost is concentrated around z = 0"
+
+
+def test_cli_binary_end_to_end(ctx, tmp_path):
+    """the sdf2mesh executable with the reference's flags: same STL bytes as the oracle, same log lines"""
+    exe = os.path.join(ROOT, "sdf2mesh_b200", "sdf2mesh")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    out = tmp_path / "torus.stl"
+    dbg = tmp_path / "debug.wgsl"
+    p = subprocess.run([exe, "--sdf", os.path.join(ROOT, "examples", "torus.sdf3d"), "--resolution", "30", "--bounds", "2", "--mesh", str(out),
+                        "--debug-wgsl", str(dbg), "--stats"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "Reading SDF from" in p.stderr and "Resolution should be a power of 2 (actual resolution : 32)" in p.stderr
+    assert "INFO  sdf2mesh] sdf3d::*" in p.stderr and "Mesh written to" in p.stderr
+    o = oracle.mesh_run("torus", 32, 2.0)
+    assert f"Mesh has {len(o.keys)} vertices." in p.stderr
+    ref = tmp_path / "ref.stl"
+    o.write_stl(ref)
+    assert out.read_bytes() == ref.read_bytes()
+    assert "fn sdf3d_torus(" in dbg.read_text() and "fn sdf3d(p: vec3f)" in dbg.read_text()
+    # GLSL input, PLY output, short flags
+    ply = tmp_path / "m.ply"
+    p = subprocess.run([exe, "--glsl", os.path.join(ROOT, "examples", "mandelmesh.frag"), "-r", "64", "-b", "5", "-0", str(ply)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    o2 = oracle.mesh_run("mandelbulb", 64, 5.0)
+    refp = tmp_path / "ref.ply"
+    o2.write_ply(refp)
+    assert ply.read_bytes() == refp.read_bytes()
+    # missing required flag / bad GLSL sdf name
+    assert subprocess.run([exe, "-i", "x.sdf3d"], capture_output=True).returncode == 2
+    p = subprocess.run([exe, "--glsl", os.path.join(ROOT, "examples", "mandelmesh.frag"), "--glsl-sdf", "nope", "-0", str(ply)], capture_output=True, text=True)
+    assert p.returncode == 101 and "Missing SDF function" in p.stderr
+    o.free()
+    o2.free()
