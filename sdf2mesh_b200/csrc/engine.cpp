@@ -213,7 +213,7 @@ extern "C" int s2m_ctx_create(int device_ordinal, s2m_ctx** out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
-  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), C_COUNT * 8, cudaHostAllocDefault));
+  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), C_COUNT * 8, cudaHostAllocMapped | cudaHostAllocPortable));
   int st = c->counters.ensure(C_COUNT * 8);
   if (st) return st;
   *out = c.release();
@@ -520,7 +520,9 @@ int launch_k4b(s2m_ctx* c, s2m_result* r, cudaStream_t s, uint64_t v_begin, uint
 }
 
 int read_counters(s2m_ctx* c, cudaStream_t s) {
-  CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, C_COUNT * 8, cudaMemcpyDeviceToHost, s));
+  // not a cudaMemcpy: see k_publish in kernels_static.cu
+  int e = s2m_launch_publish(c->counters.as<unsigned long long>(), c->h_counters, C_COUNT, s);
+  if (e) return fail(S2M_ERR_CUDA, std::string("k_publish launch: ") + cudaGetErrorString((cudaError_t)e));
   CUDA_TRY(cudaStreamSynchronize(s));
   return S2M_OK;
 }
@@ -534,6 +536,15 @@ void finalize_timings(s2m_ctx* c, s2m_result* r) {
   }
   r->t.k1_slab_ms = acc[0]; r->t.k2_classify_ms = acc[1]; r->t.k3_compact_ms = acc[2];
   r->t.k4_vertices_ms = acc[3]; r->t.k4_quads_ms = acc[4]; r->t.d2h_ms = acc[5];
+  if (getenv("S2M_TRACE")) {  // device timeline: when each span started / ended relative to the first launch
+    static const char* names[6] = {"K1", "K2", "K3", "K4a", "K4b", "copy"};
+    for (const auto& sp : r->spans) {
+      float t0 = 0, t1 = 0;
+      cudaEventElapsedTime(&t0, c->ev[0], c->ev_pool[sp.e0]);
+      cudaEventElapsedTime(&t1, c->ev[0], c->ev_pool[sp.e1]);
+      fprintf(stderr, "[s2m timeline] %-4s %9.3f -> %9.3f ms (%7.3f)\n", names[sp.kind], t0, t1, t1 - t0);
+    }
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); r->t.device_ms = ms;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]); r->t.total_ms = ms;

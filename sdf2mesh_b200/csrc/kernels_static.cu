@@ -270,9 +270,22 @@ k4_quads(QuadParams p) {
   }
 }
 
+// Copies a few counters into mapped pinned host memory with plain stores, so that the host can read
+// them after an event WITHOUT a cudaMemcpy: a D2H memcpy would queue on the copy engine behind the
+// bulk vertex/quad copies of the previous chunk and stall the pipeline for milliseconds.
+__global__ void k_publish(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst_host, unsigned n) {
+  if (threadIdx.x < n) dst_host[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ launchers
+extern "C" int s2m_launch_publish(const unsigned long long* src, unsigned long long* dst_host, unsigned n, cudaStream_t stream) {
+  k_publish<<<1, 32, 0, stream>>>(src, dst_host, n);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream) {
   dim3 grid((a->res_x + 32 * K2_TX_WORDS - 1) / (32 * K2_TX_WORDS), (a->res_y + K2_TY - 1) / K2_TY,
             (a->nz_chunk + K2_ZT - 1) / K2_ZT);

@@ -49,6 +49,7 @@ typedef struct S2mK4bArgs {
   unsigned long long* n_invalid;  /* accumulates */
 } S2mK4bArgs;
 
+int s2m_launch_publish(const unsigned long long* src, unsigned long long* dst_host, unsigned n, cudaStream_t stream); /* n <= 32 */
 int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream);
 unsigned s2m_k3_tiles(unsigned long long n_words);
 int s2m_launch_k3(const S2mK3Args* a, cudaStream_t stream);
