@@ -208,15 +208,20 @@ S2M_HD float s2m__cos_poly(float r) {
   p = s2m_fma(p, s, -0.5f);
   return s2m_fma(p, s, 1.0f);
 }
+/* Branch-free: both polynomials are always evaluated and selected by the quadrant.  sin(x) and
+ * cos(x) of the same argument then share the reduction and both polynomials after CSE, and lanes
+ * in different quadrants do not diverge.  (Same values as selecting before evaluating.) */
 S2M_HD float s2m_sin(float x) {
   int q; float r = s2m__trig_red(x, &q);
-  float v = (q & 1) ? s2m__cos_poly(r) : s2m__sin_poly(r);
+  const float sp = s2m__sin_poly(r), cp = s2m__cos_poly(r);
+  const float v = (q & 1) ? cp : sp;
   return (q & 2) ? -v : v;
 }
 S2M_HD float s2m_cos(float x) {
   int q; float r = s2m__trig_red(x, &q);
+  const float sp = s2m__sin_poly(r), cp = s2m__cos_poly(r);
   q += 1;
-  float v = (q & 1) ? s2m__cos_poly(r) : s2m__sin_poly(r);
+  const float v = (q & 1) ? cp : sp;
   return (q & 2) ? -v : v;
 }
 S2M_HD float s2m_tan(float x) {
@@ -248,14 +253,11 @@ S2M_HD float s2m__atan_poly(float t) { /* 0 <= t <= 1 */
   return s2m_fma(p * s, t, t);
 }
 S2M_HD float s2m_atan(float x) {
-  float a = s2m_abs(x);
-  float r;
-  if (a > 1.0f) {
-    r = s2m__atan_poly(1.0f / a);        /* 1/inf = 0 -> pi/2 */
-    r = s2m_fma(1.0f, 1.570796371e+00f, -r) + (-4.371138829e-08f);
-  } else {
-    r = s2m__atan_poly(a);               /* NaN flows through */
-  }
+  const float a = s2m_abs(x);
+  const bool big = a > 1.0f;                     /* NaN: false, flows through the polynomial */
+  const float t = big ? 1.0f / a : a;            /* 1/inf = 0 -> pi/2 */
+  float r = s2m__atan_poly(t);
+  if (big) r = s2m_fma(1.0f, 1.570796371e+00f, -r) + (-4.371138829e-08f);
   return s2m_i2f(s2m_f2i(r) | (s2m_f2i(x) & (int)0x80000000));
 }
 S2M_HD float s2m_atan2(float y, float x) {
@@ -284,16 +286,12 @@ S2M_HD float s2m__asin_poly(float x, float s) { /* x + x*s*P(s) */
   return s2m_fma(p * s, x, x);
 }
 S2M_HD float s2m_asin(float x) {
-  float a = s2m_abs(x);
-  float r;
-  if (a > 0.5f) {                /* asin(a) = pi/2 - 2*asin(sqrt((1-a)/2)); a>1 -> NaN via sqrt */
-    float z = s2m_fma(a, -0.5f, 0.5f);
-    float y = s2m_sqrt(z);
-    r = s2m__asin_poly(y, z);
-    r = s2m_fma(r, -2.0f, 1.570796371e+00f) + (-4.371138829e-08f);
-  } else {
-    r = s2m__asin_poly(a, a * a);
-  }
+  const float a = s2m_abs(x);
+  const bool big = a > 0.5f;   /* asin(a) = pi/2 - 2*asin(sqrt((1-a)/2)); a > 1 -> NaN via sqrt */
+  const float z = big ? s2m_fma(a, -0.5f, 0.5f) : a * a;
+  const float y = big ? s2m_sqrt(z) : a;
+  float r = s2m__asin_poly(y, z);
+  if (big) r = s2m_fma(r, -2.0f, 1.570796371e+00f) + (-4.371138829e-08f);
   return s2m_i2f(s2m_f2i(r) | (s2m_f2i(x) & (int)0x80000000));
 }
 S2M_HD float s2m_acos(float x) {
