@@ -110,6 +110,7 @@ void s2m_module_free(s2m_module* m);
 #define S2M_MESH_NO_NORMALS 2u      /* skip sdf3d_normal (normals only reach the PLY writer) */
 #define S2M_MESH_EXACT_DENSE 4u     /* reference-cost mode: every cell is a candidate (8 evaluations per cell) */
 #define S2M_MESH_KEEP_CANDIDATES 8u /* keep the candidate key list in the result (tests) */
+#define S2M_MESH_CLASSIFY_FROM_SLAB 16u /* K2 re-reads the f32 slab through shared memory instead of K1's class bit planes */
 
 typedef struct s2m_mesh_params {
   uint32_t struct_size; /* sizeof(s2m_mesh_params) */

@@ -16,7 +16,7 @@ STATUS_NAMES = {
 }
 SRC_SDF3D, SRC_GLSL_FRAGMENT, SRC_WGSL, SRC_CUDA = 0, 1, 2, 3
 COMPILE_ALLOW_FMA = 1
-MESH_ALL_SLICES, MESH_NO_NORMALS, MESH_EXACT_DENSE, MESH_KEEP_CANDIDATES = 1, 2, 4, 8
+MESH_ALL_SLICES, MESH_NO_NORMALS, MESH_EXACT_DENSE, MESH_KEEP_CANDIDATES, MESH_CLASSIFY_FROM_SLAB = 1, 2, 4, 8, 16
 
 
 class S2mError(RuntimeError):

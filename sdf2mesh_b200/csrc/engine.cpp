@@ -155,7 +155,7 @@ struct s2m_ctx {
   int device = 0;
   cudaDeviceProp prop{};
   cudaStream_t stream = nullptr, copy_stream = nullptr;
-  DevBuf slab, cand_mask, word_prefix, cand_key, cand_vrank, status, counters;
+  DevBuf slab, cls, cand_mask, word_prefix, cand_key, cand_vrank, status, counters;
   DevBuf v_pos, v_nrm, v_key, v_nib, quads, scratch;
   std::vector<PinnedBlock> pinned;
   unsigned long long* h_counters = nullptr;  // pinned, 16 words
@@ -224,7 +224,7 @@ extern "C" void s2m_ctx_destroy(s2m_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&c->slab, &c->cand_mask, &c->word_prefix, &c->cand_key, &c->cand_vrank, &c->status, &c->counters,
+  for (DevBuf* b : {&c->slab, &c->cls, &c->cand_mask, &c->word_prefix, &c->cand_key, &c->cand_vrank, &c->status, &c->counters,
                     &c->v_pos, &c->v_nrm, &c->v_key, &c->v_nib, &c->quads, &c->scratch})
     b->release();
   for (auto& b : c->pinned) cudaFreeHost(b.p);
@@ -357,7 +357,7 @@ void k1_block_shape(unsigned* bx, unsigned* by) {
     sx = 8; sy = 32;
     if (const char* e = getenv("S2M_K1_BLOCK")) {
       unsigned a = 0, b = 0;
-      if (sscanf(e, "%ux%u", &a, &b) == 2 && a && b && a * b <= 1024 && (a * b) % 32 == 0) { sx = a; sy = b; }
+      if (sscanf(e, "%ux%u", &a, &b) == 2 && a && b && a * b <= 256 && (a * b) % 32 == 0 && a % 8 == 0) { sx = a; sy = b; }
     }
   }
   *bx = sx; *by = sy;
@@ -637,7 +637,15 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       GridDev gd = g;
       float* slab = c->slab.as<float>();
       unsigned first_plane = r->z_first + ch.z0, n_planes = ch.nzc + 1;
-      void* a1[] = {&gd, &slab, &first_plane, &n_planes};
+      const bool from_slab = p->flags & S2M_MESH_CLASSIFY_FROM_SLAB;
+      unsigned cls_words = g.pitch_x / 32u;
+      void* cls = nullptr;
+      if (!from_slab) {
+        if ((st = c->cls.ensure((size_t)n_planes * g.rows * cls_words * 8 + 64))) return st;
+        cls = c->cls.p;
+      }
+      float tau_arg = tau;
+      void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words};
       unsigned bx, by;
       k1_block_shape(&bx, &by);
       dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by - 1u) / by, n_planes);
@@ -652,9 +660,10 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       a2.slab = slab; a2.pitch_x = g.pitch_x; a2.plane_stride = g.plane_stride;
       a2.res_x = g.res[0]; a2.res_y = g.res[1]; a2.nz_chunk = ch.nzc; a2.tau = tau;
       a2.cand_mask = mask_chunk; a2.words_x = r->words_x; a2.total = d_cnt + C_NCAND;
+      a2.cls = cls; a2.cls_words = cls_words;
       {
         SPAN_BEGIN(1, s);
-        int e2 = s2m_launch_k2(&a2, s);
+        int e2 = from_slab ? s2m_launch_k2(&a2, s) : s2m_launch_k2_bits(&a2, s);
         if (e2) return fail(S2M_ERR_CUDA, std::string("k2_classify launch: ") + cudaGetErrorString((cudaError_t)e2));
         SPAN_END(s);
       }
@@ -882,8 +891,10 @@ extern "C" int s2m_debug_slab_plane(s2m_ctx* c, s2m_module* m, const s2m_mesh_pa
   CUDA_TRY(cudaSetDevice(c->device));
   if ((st = c->slab.ensure(g.plane_stride * 4))) return st;
   float* slab = c->slab.as<float>();
-  unsigned first_plane = plane, n_planes = 1;
-  void* a1[] = {&g, &slab, &first_plane, &n_planes};
+  unsigned first_plane = plane, n_planes = 1, cls_words = 0;
+  float tau_arg = 0.0f;
+  void* cls = nullptr;
+  void* a1[] = {&g, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words};
   unsigned bx, by;
   k1_block_shape(&bx, &by);
   if ((st = launch(m->k1, dim3((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by - 1u) / by, 1), dim3(bx, by, 1), c->stream, a1, "s2m_k1_slab"))) return st;

@@ -41,15 +41,19 @@ __device__ __noinline__ float s2m_sdf_call(float x, float y, float z) { return s
  * per warp), (8,32) = 32x4 tiles (one full 128 B line per row) -- more compact, less divergence
  * in SDFs whose cost varies in space.  grid = (ceil(pitch_x/(4*bx)), ceil(rows/by), planes). */
 extern "C" __global__ void __launch_bounds__(256)
-s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned n_planes) {
+s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned n_planes,
+            float tau, uint2* __restrict__ cls, unsigned cls_words) {
   const unsigned x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
   const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
   const unsigned pz = blockIdx.z;
-  if (x4 >= g.pitch_x || y >= g.rows || pz >= n_planes) return;
+  /* no early return: all 32 lanes take part in the shuffles below.  Groups of 8 lanes cover 32
+   * consecutive corners of one row (blockDim.x is a multiple of 8, pitch_x of 32), so a group is
+   * active or inactive as a whole. */
+  const bool active = x4 < g.pitch_x && y < g.rows && pz < n_planes;
   const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
   const float cy = g.bmin[1] + g.size[1] * (float)y;
-  /* S2M_K1_UNROLL=1 keeps ONE inlined copy of the SDF in the kernel (4x less code: the mandelbulb
-   * kernel otherwise overflows the instruction cache, ncu: stall_no_instruction); 4 = unrolled. */
+  /* S2M_K1_UNROLL=1 keeps ONE inlined copy of the SDF in the kernel (4x less code); 4 = unrolled
+   * (lets independent evaluations overlap; faster for the mandelbulb, measured). */
   float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
 #if S2M_K1_UNROLL == 1
 #pragma unroll 1
@@ -58,12 +62,26 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
 #endif
   for (int k = 0; k < 4; ++k) {
     const unsigned x = x4 + (unsigned)k;
-    const float val = (x <= g.res[0]) ? s2m_sdf(g.bmin[0] + g.size[0] * (float)x, cy, cz) : 0.0f;
+    const float val = (active && x <= g.res[0]) ? s2m_sdf(g.bmin[0] + g.size[0] * (float)x, cy, cz) : 0.0f;
     if (k == 0) v0 = val; else if (k == 1) v1 = val; else if (k == 2) v2 = val; else v3 = val;
   }
-  float4* dst = reinterpret_cast<float4*>(slab + (unsigned long long)pz * g.plane_stride +
-                                          (unsigned long long)y * g.pitch_x + x4);
-  *dst = make_float4(v0, v1, v2, v3);
+  const unsigned long long row = (unsigned long long)pz * g.rows + y;
+  if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(v0, v1, v2, v3);
+  /* Corner classes for K2: P = value > +tau, N = value < -tau (NaN and the |v| <= tau band are
+   * neither), one bit per corner, 32 corners per word, words (P,N) interleaved:
+   * cls[plane][row][x/32] = (P word, N word).  0.25 B per corner instead of K2 re-reading 4 B. */
+  if (cls != nullptr) {
+    const unsigned lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31u;
+    const unsigned sh = 4u * (lane & 7u);
+    unsigned pw = ((v0 > tau ? 1u : 0u) | (v1 > tau ? 2u : 0u) | (v2 > tau ? 4u : 0u) | (v3 > tau ? 8u : 0u)) << sh;
+    unsigned nw = ((v0 < -tau ? 1u : 0u) | (v1 < -tau ? 2u : 0u) | (v2 < -tau ? 4u : 0u) | (v3 < -tau ? 8u : 0u)) << sh;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      pw |= __shfl_xor_sync(0xffffffffu, pw, o);
+      nw |= __shfl_xor_sync(0xffffffffu, nw, o);
+    }
+    if (active && (lane & 7u) == 0u) cls[row * cls_words + (x4 >> 5)] = make_uint2(pw, nw);
+  }
 }
 
 /* ------------------------------------------------------------------------------------------ K4a */

@@ -104,6 +104,54 @@ k2_classify(const float* __restrict__ slab, uint32_t pitch_x, unsigned long long
   }
 }
 
+// K2 (default): the same candidate test on the corner-class bit planes K1 wrote next to the slab
+// (P = v > tau, N = v < -tau; cls[plane][row][x/32] = (P word, N word)).  One thread owns one
+// 32-cell word of one cell row and marches through the chunk's slices, keeping the previous
+// plane's "both rows, both x-neighbours" masks in registers.  0.25 B/voxel read instead of 4.
+__global__ void __launch_bounds__(256)
+k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t rows, uint32_t res_x, uint32_t res_y,
+                 uint32_t nz_chunk, uint32_t* __restrict__ cand_mask, uint32_t words_x, unsigned long long* __restrict__ total) {
+  __shared__ unsigned s_red[8];
+  const uint32_t xw = blockIdx.x * 32u + (threadIdx.x & 31u);
+  const uint32_t y = blockIdx.y * 8u + (threadIdx.x >> 5);
+  const uint32_t zt0 = blockIdx.z * K2_ZT;
+  const bool live = xw < words_x && y < res_y;
+  unsigned count = 0;
+  uint32_t prevP = 0, prevN = 0;
+  for (uint32_t k = 0; k <= (uint32_t)K2_ZT; ++k) {
+    const uint32_t plane = zt0 + k;
+    if (plane > nz_chunk) break;
+    uint32_t curP = 0, curN = 0;
+    if (live) {
+      const uint2* r0 = cls + ((unsigned long long)plane * rows + y) * cls_words + xw;
+      const uint2* r1 = r0 + cls_words;
+      const bool has_next = xw + 1u < cls_words;
+      const uint2 a = __ldg(r0), c = __ldg(r1);
+      const uint2 b = has_next ? __ldg(r0 + 1) : make_uint2(0u, 0u);
+      const uint2 d = has_next ? __ldg(r1 + 1) : make_uint2(0u, 0u);
+      curP = (a.x & ((a.x >> 1) | (b.x << 31))) & (c.x & ((c.x >> 1) | (d.x << 31)));
+      curN = (a.y & ((a.y >> 1) | (b.y << 31))) & (c.y & ((c.y >> 1) | (d.y << 31)));
+      if (k >= 1) {
+        const uint32_t z = plane - 1u;
+        uint32_t cand = ~((prevP & curP) | (prevN & curN));
+        const uint32_t xb = xw * 32u;
+        if (xb + 32u > res_x) cand &= (1u << (res_x - xb)) - 1u;
+        cand_mask[((unsigned long long)z * res_y + y) * words_x + xw] = cand;
+        count += (unsigned)__popc(cand);
+      }
+    }
+    prevP = curP; prevN = curN;
+  }
+  for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+  if ((threadIdx.x & 31u) == 0) s_red[threadIdx.x >> 5] = count;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = 0;
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    if (t) atomicAdd(total, (unsigned long long)t);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ K3
 constexpr int K3_THREADS = 256;
 constexpr int K3_WORDS_PER_THREAD = 16;  // 4 x uint4
@@ -292,6 +340,14 @@ extern "C" int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream) {
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
   k2_classify<<<grid, 256, 0, stream>>>(a->slab, a->pitch_x, a->plane_stride, a->res_x, a->res_y, a->nz_chunk, a->tau,
                                         a->cand_mask, a->words_x, a->total);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int s2m_launch_k2_bits(const S2mK2Args* a, cudaStream_t stream) {
+  dim3 grid((a->words_x + 31u) / 32u, (a->res_y + 7u) / 8u, (a->nz_chunk + K2_ZT - 1) / K2_ZT);
+  if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
+  k2_classify_bits<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint2*>(a->cls), a->cls_words, a->res_y + 1u, a->res_x, a->res_y, a->nz_chunk,
+                                              a->cand_mask, a->words_x, a->total);
   return (int)cudaGetLastError();
 }
 

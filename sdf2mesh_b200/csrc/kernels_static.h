@@ -18,6 +18,8 @@ typedef struct S2mK2Args {
   uint32_t* cand_mask;            /* first word of the chunk's first slice */
   uint32_t words_x;
   unsigned long long* total;      /* candidate counter (accumulates) */
+  const void* cls;                /* s2m_launch_k2_bits: corner-class planes written by K1 (uint2 per 32 corners) */
+  uint32_t cls_words;             /* class words per row */
 } S2mK2Args;
 
 typedef struct S2mK3Args {
@@ -50,7 +52,8 @@ typedef struct S2mK4bArgs {
 } S2mK4bArgs;
 
 int s2m_launch_publish(const unsigned long long* src, unsigned long long* dst_host, unsigned n, cudaStream_t stream); /* n <= 32 */
-int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream);
+int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream);      /* classify from the f32 slab */
+int s2m_launch_k2_bits(const S2mK2Args* a, cudaStream_t stream); /* classify from K1's class bit planes */
 unsigned s2m_k3_tiles(unsigned long long n_words);
 int s2m_launch_k3(const S2mK3Args* a, cudaStream_t stream);
 unsigned s2m_k4b_tiles(unsigned long long n_own);

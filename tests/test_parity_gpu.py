@@ -213,3 +213,23 @@ def test_bigger_sizes_properties(ctx):
         assert mesh_digests(d.positions, d.normals, d.keys, d.nibbles, d.quads, d.n_invalid_quads) == GOLDEN[key]
     r.free()
     r2.free()
+
+
+@pytest.mark.parametrize("name,dims,bmin,bmax", [
+    ("torus", (70, 45, 33), [-1.0, -0.6, -0.5], [1.0, 0.7, 0.5]),
+    ("mandelbulb", (96, 96, 96), [-2.5, -2.5, -2.5], [2.5, 2.5, 2.5]),
+    ("p_key", (64, 64, 64), [-1, -1, -1], [1, 1, 1]),
+    ("torus", (31, 33, 2), [-1, -1, -0.1], [1, 1, 0.1]),
+])
+def test_classify_paths_agree(ctx, name, dims, bmin, bmax):
+    """K2 from K1's class bit planes (default) == K2 re-reading the f32 slab through shared memory"""
+    out = []
+    for flags in (s2m.MESH_KEEP_CANDIDATES, s2m.MESH_KEEP_CANDIDATES | s2m.MESH_CLASSIFY_FROM_SLAB):
+        for budget in (0, (dims[0] + 32) * (dims[1] + 1) * 4 * 5):
+            p = s2m.make_params(dims, bmin, bmax, flags=flags, slab_budget_bytes=budget)
+            r = s2m.mesh_run(ctx, module_for(ctx, name), p)
+            d = r.data()
+            out.append((d.candidates.copy(), d.keys.copy(), d.quads.copy()))
+            r.free()
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and np.array_equal(o[1], out[0][1]) and np.array_equal(o[2], out[0][2])
