@@ -1,6 +1,8 @@
 // frontend.cpp -- front-end entry points.
 #include "frontend.h"
 
+#include <cstdlib>
+
 #include "parse.h"
 
 namespace s2m_frontend {
@@ -10,6 +12,7 @@ int lower_to_cuda(const s2m_shader& sh, std::string* cuda, std::string* err) {
     if (sh.kind == S2M_SRC_CUDA) { *cuda = sh.source; return S2M_OK; }
     Module m;
     parse_wgsl(sh.source, sh.builtin_functions, &m);
+    if (!getenv("S2M_NO_IR_OPT")) optimize_module(m);
     *cuda = emit_cuda(m);
     return S2M_OK;
   } catch (const FrontendError& e) {

@@ -8,6 +8,7 @@
 namespace s2m_frontend {
 void parse_wgsl(const std::string& src, const std::vector<std::string>& builtin_fns, Module* out);
 void parse_glsl(const std::string& src, Module* out);
+int optimize_module(Module& m);  // returns the number of rewrites applied
 std::string emit_cuda(const Module& m);
 std::string emit_wgsl(const Module& m);
 }  // namespace s2m_frontend

@@ -68,19 +68,18 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   const unsigned long long row = (unsigned long long)pz * g.rows + y;
   if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(v0, v1, v2, v3);
   /* Corner classes for K2: P = value > +tau, N = value < -tau (NaN and the |v| <= tau band are
-   * neither), one bit per corner, 32 corners per word, words (P,N) interleaved:
-   * cls[plane][row][x/32] = (P word, N word).  0.25 B per corner instead of K2 re-reading 4 B. */
+   * neither).  One byte per thread: low nibble = P of its 4 corners, high nibble = N.  8 lanes
+   * (32 corners of a row) make one 64-bit word, cls[plane][row][x/32] = (lanes 0-3, lanes 4-7):
+   * 0.25 B per corner instead of K2 re-reading 4 B.  Two shuffles per thread. */
   if (cls != nullptr) {
     const unsigned lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31u;
-    const unsigned sh = 4u * (lane & 7u);
-    unsigned pw = ((v0 > tau ? 1u : 0u) | (v1 > tau ? 2u : 0u) | (v2 > tau ? 4u : 0u) | (v3 > tau ? 8u : 0u)) << sh;
-    unsigned nw = ((v0 < -tau ? 1u : 0u) | (v1 < -tau ? 2u : 0u) | (v2 < -tau ? 4u : 0u) | (v3 < -tau ? 8u : 0u)) << sh;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      pw |= __shfl_xor_sync(0xffffffffu, pw, o);
-      nw |= __shfl_xor_sync(0xffffffffu, nw, o);
-    }
-    if (active && (lane & 7u) == 0u) cls[row * cls_words + (x4 >> 5)] = make_uint2(pw, nw);
+    unsigned w = ((v0 > tau ? 1u : 0u) | (v1 > tau ? 2u : 0u) | (v2 > tau ? 4u : 0u) | (v3 > tau ? 8u : 0u) |
+                  (v0 < -tau ? 16u : 0u) | (v1 < -tau ? 32u : 0u) | (v2 < -tau ? 64u : 0u) | (v3 < -tau ? 128u : 0u))
+                 << (8u * (lane & 3u));
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    if (active && (lane & 3u) == 0u)
+      reinterpret_cast<unsigned*>(cls)[(row * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u)] = w;
   }
 }
 

@@ -322,3 +322,24 @@ def test_glsl_features(built, tmp_path):
     got = host_eval.eval_points(sh.lower_to_cuda(), pts)
     want = np.array([ref(p) for p in pts], np.float32)
     assert f32_equal(got, want).all()
+
+
+def test_continue_to_break_rewrite(built, monkeypatch):
+    """IR optimisation (frontend/optimize.cpp): an idempotent `P; if (c) continue;` loop prefix that does
+    not depend on the loop counter turns `continue` into `break`; anything else is left alone, and the
+    values never change"""
+    ok = "fn sdf3d(p: vec3f) -> f32 { var r = 0.0; var z = p; for (var i = 0; i < 6; i++) { r = length(z); if (r > 2.0) { continue; } z = z * 1.7 + p; } return r; }"
+    acc = "fn sdf3d(p: vec3f) -> f32 { var r = 0.0; var z = p; for (var i = 0; i < 6; i++) { r = r + length(z); if (r > 2.0) { continue; } z = z * 1.7 + p; } return r; }"
+    cnt = "fn sdf3d(p: vec3f) -> f32 { var r = 0.0; var z = p; for (var i = 0; i < 6; i++) { r = length(z) + f32(i); if (r > 2.0) { continue; } z = z * 1.7 + p; } return r; }"
+    outer = "fn sdf3d(p: vec3f) -> f32 { var r = 0.0; var z = p; var i = 0; for (; i < 6; i++) { r = length(z); if (r > 2.0) { continue; } z = z * 1.7 + p; } return r + f32(i); }"
+    pts = points(4.0, 5000)
+    for src, rewritten in ((ok, True), (acc, False), (cnt, False), (outer, False)):
+        monkeypatch.delenv("S2M_NO_IR_OPT", raising=False)
+        opt = s2m.Sdf3DShader.from_source(src).lower_to_cuda()
+        monkeypatch.setenv("S2M_NO_IR_OPT", "1")
+        plain = s2m.Sdf3DShader.from_source(src).lower_to_cuda()
+        assert "continue;" in plain and "break;" not in plain
+        assert ("break;" in opt) == rewritten
+        assert f32_equal(host_eval.eval_points(opt, pts), host_eval.eval_points(plain, pts)).all()
+    monkeypatch.delenv("S2M_NO_IR_OPT", raising=False)
+    assert "break;" in load_example_shader("mandelbulb").lower_to_cuda()
