@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (example file, kind, oracle sdf, resolution, bounds)
     "mandelmesh2048": ("mandelmesh.frag", "glsl", "mandelbulb", 2048, 5.0),
+    "mandelmesh4096": ("mandelmesh.frag", "glsl", "mandelbulb", 4096, 5.0),  # beyond the reference's 2048 limit (BASELINE config 5)
     "mandelmesh1024": ("mandelmesh.frag", "glsl", "mandelbulb", 1024, 5.0),
     "mandelmesh512": ("mandelmesh.frag", "glsl", "mandelbulb", 512, 5.0),
     "torus2048": ("torus.sdf3d", "sdf3d", "torus", 2048, 2.0),
@@ -261,7 +262,8 @@ def main():
     planes = (ze - max(zb - 1, 0)) + 1 if world > 1 else n_slices + 1
     k1_bytes = 4.0 * (res + 1) * (res + 1) * planes
     k1_s = per["k1_slab_ms"] * 1e-3
-    k2_bytes = k1_bytes + (res * res * (planes - 1)) / 8.0
+    # K2 reads K1's corner-class planes (8 B per 32 corners) and writes 1 bit per cell
+    k2_bytes = (res + 1.0) * (((res + 1 + 31) // 32) * 8.0) * planes + (res * res * (planes - 1)) / 8.0
     full, early, frac_in = FLOPS_PER_EVAL.get(osdf, (100.0, 100.0, 1.0))
     flops = (res + 1.0) ** 2 * planes * (frac_in * full + (1 - frac_in) * early)
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
@@ -279,7 +281,8 @@ def main():
         "jit_ms": jit_ms,
         "roofline": {"kernel": "s2m_k1_slab", "bound": "hbm", "achieved": k1_bytes / k1_s / 1e9 if k1_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (k1_bytes / k1_s / 1e9 / hbm_peak) if k1_s > 0 else None, "traffic": None, "peak_source": peak_src,
-                     "note": "K1 is FP32/issue bound for this SDF, not HBM bound; see fp32",
+                     "note": "K1 is FP32/issue bound for this SDF, not HBM bound (ncu: issue slots ~90 % busy, DRAM ~5 %); see fp32. "
+                             "achieved = 4 B per corner written (SURVEY 8d) / K1 time",
                      "fp32": {"achieved_tflops_source_level": flops / k1_s / 1e12 if k1_s > 0 else None, "peak_tflops_nominal": fp32_peak,
                               "frac": flops / k1_s / 1e12 / fp32_peak if k1_s > 0 else None}},
         "kernels": {"k1_slab": {"ms": per["k1_slab_ms"], "GBps": k1_bytes / k1_s / 1e9 if k1_s > 0 else None},

@@ -16,6 +16,7 @@ std::string Type::str() const {
   const char* s = sk == Sk::Bool ? "bool" : sk == Sk::I32 ? "i32" : sk == Sk::U32 ? "u32" : sk == Sk::F32 ? "f32"
                   : sk == Sk::AInt ? "abstract-int" : "abstract-float";
   if (k == Scalar) return s;
+  if (k == Matrix) return "mat" + std::to_string(n) + "x" + std::to_string(n) + "<f32>";
   return "vec" + std::to_string(n) + "<" + s + ">";
 }
 
@@ -100,6 +101,8 @@ ConstVal convert_cv(const ConstVal& v, Sk sk) {
 }  // namespace
 
 bool Builder::const_eval(const Expr& e, ConstVal* out) const {
+  if (e.ty.is_matrix()) return false;
+  for (const ExprP& a : e.args) if (a && a->ty.is_matrix()) return false;
   switch (e.k) {
     case Expr::Lit: *out = e.lit; return true;
     case Expr::VarRef:
@@ -338,6 +341,35 @@ ExprP Builder::binary(Op op, ExprP a, ExprP b) {
     return e;
   }
   if (a->ty.is_bool() || b->ty.is_bool()) error("arithmetic on bool operands");
+  if (a->ty.is_matrix() || b->ty.is_matrix()) {
+    // linear algebra: mat*vec, vec*mat, mat*mat, mat*scalar, scalar*mat, mat/scalar, mat+-mat
+    if (a->ty.is_abstract()) a = concretize(a);
+    if (b->ty.is_abstract()) b = concretize(b);
+    if (lang == Lang::Glsl) {
+      if (a->ty.is_int() && !a->ty.is_matrix()) a = convert_sk(a, Sk::F32);
+      if (b->ty.is_int() && !b->ty.is_matrix()) b = convert_sk(b, Sk::F32);
+    }
+    if (a->ty.sk != Sk::F32 || b->ty.sk != Sk::F32) error("matrix arithmetic needs f32 operands, found " + a->ty.str() + " and " + b->ty.str());
+    Type rt;
+    const bool am = a->ty.is_matrix(), bm = b->ty.is_matrix();
+    if (op == Op::Mul) {
+      if (am && bm) { if (a->ty.n != b->ty.n) error("matrix size mismatch"); rt = a->ty; }
+      else if (am && b->ty.is_vector()) { if (a->ty.n != b->ty.n) error("matrix * vector size mismatch"); rt = b->ty; }
+      else if (bm && a->ty.is_vector()) { if (a->ty.n != b->ty.n) error("vector * matrix size mismatch"); rt = a->ty; }
+      else if (am && b->ty.is_scalar()) rt = a->ty;
+      else if (bm && a->ty.is_scalar()) rt = b->ty;
+      else error("bad operands for *: " + a->ty.str() + " and " + b->ty.str());
+    } else if (op == Op::Add || op == Op::Sub) {
+      if (!(am && bm && a->ty.n == b->ty.n)) error("matrix +/- needs two matrices of the same size");
+      rt = a->ty;
+    } else if (op == Op::Div) {
+      if (!(am && b->ty.is_scalar())) error("matrix / needs a scalar divisor");
+      rt = a->ty;
+    } else error("operator not defined for matrices");
+    ExprP e = mk(Expr::Binary, rt);
+    e->op = op; e->args = {a, b};
+    return e;
+  }
   // shapes
   int n = 1;
   if (a->ty.is_vector() && b->ty.is_vector()) {
@@ -378,6 +410,7 @@ ExprP Builder::ternary(ExprP c, ExprP t, ExprP f) {
 
 ExprP Builder::swizzle(ExprP base, const std::string& comps) {
   if (base->ty.is_void()) error("swizzle of void");
+  if (base->ty.is_matrix()) error("matrices have no named members; use m[i]");
   if (comps.empty() || comps.size() > 4) error("bad swizzle ." + comps);
   static const char* sets[] = {"xyzw", "rgba", "stpq"};
   int idx[4];
@@ -405,8 +438,34 @@ ExprP Builder::swizzle(ExprP base, const std::string& comps) {
   return e;
 }
 
+ExprP Builder::matrix_column(ExprP base, int col) {
+  if (!base->ty.is_matrix()) error("column access on a non-matrix");
+  if (col < 0 || col >= base->ty.n) error("matrix column index out of range");
+  ExprP e = mk(Expr::Swizzle, Type::vec(Sk::F32, base->ty.n));
+  e->args.push_back(base);
+  e->nswz = 1;
+  e->swz[0] = col;
+  return e;
+}
+
 ExprP Builder::construct(Type target, bool infer_sk, std::vector<ExprP> args) {
   for (const ExprP& a : args) if (a->ty.is_void()) error("void constructor argument");
+  if (target.is_matrix()) {
+    const int n = target.n;
+    for (ExprP& a : args) {
+      if (a->ty.is_matrix()) { if (args.size() != 1 || a->ty.n != n) unsupported("matrix constructor from a matrix of another size"); return a; }
+      if (a->ty.is_abstract() || (lang == Lang::Glsl && a->ty.is_int())) a = convert_sk(a, Sk::F32);
+      if (a->ty.sk != Sk::F32) error("matrix constructor needs f32 components, found " + a->ty.str());
+    }
+    int total = 0;
+    for (const ExprP& a : args) total += a->ty.n;
+    const bool diag = args.size() == 1 && args[0]->ty.is_scalar();
+    if (!diag && !args.empty() && total != n * n) error("mat" + std::to_string(n) + " constructor has " + std::to_string(total) + " components");
+    if (diag && lang != Lang::Glsl) error("WGSL has no diagonal matrix constructor");
+    ExprP e = mk(Expr::Construct, target);
+    e->args = args;
+    return e;
+  }
   if (target.is_scalar()) {
     if (args.empty()) return target.is_float() ? lit_float(0, target.sk) : lit_int(0, target.sk);
     if (args.size() != 1) error("scalar constructor takes one argument");
@@ -482,6 +541,7 @@ const BuiltinInfo kBuiltins[] = {
     {"dot", "dot", 2, 's', 3},       {"cross", "cross", 2, 'x', 3},   {"reflect", "reflect", 2, 'r', 3},
     {"clamp", "clamp", 3, 'n', 3},   {"mix", "mix", 3, 'm', 3},       {"smoothstep", "smoothstep", 3, 'm', 3}, {"fma", "fma", 3, 'm', 3},
     {"select", "select", 3, 'S', 1}, {"any", "any", 1, 'b', 3},       {"all", "all", 1, 'b', 3},
+    {"transpose", "transpose", 1, 'T', 3}, {"determinant", "determinant", 1, 'D', 3},
 };
 }  // namespace
 
@@ -503,6 +563,11 @@ ExprP Builder::call_builtin(const std::string& name, std::vector<ExprP> args) {
   }
   for (const ExprP& a : args) if (a->ty.is_void()) error("void argument to " + name + "()");
   auto call = [&](Type ty) { ExprP e = mk(Expr::Call, ty); e->callee = bi->canon; e->args = args; return e; };
+  if (bi->kind == 'T' || bi->kind == 'D') {
+    if (!args[0]->ty.is_matrix()) error(name + "() needs a matrix");
+    return call(bi->kind == 'T' ? args[0]->ty : Type::scalar(Sk::F32));
+  }
+  for (const ExprP& a : args) if (a->ty.is_matrix()) error("matrix argument to " + name + "()");
   if (bi->kind == 'b') {
     if (!args[0]->ty.is_bool()) error(name + "() needs a bool vector");
     return call(Type::scalar(Sk::Bool));

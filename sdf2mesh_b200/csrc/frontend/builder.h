@@ -28,6 +28,7 @@ class Builder {
   ExprP binary(Op op, ExprP a, ExprP b);
   ExprP ternary(ExprP c, ExprP t, ExprP f);
   ExprP swizzle(ExprP base, const std::string& comps);
+  ExprP matrix_column(ExprP base, int col);  // m[i]
   ExprP construct(Type target, bool infer_sk, std::vector<ExprP> args);  // vecN(...) / scalar casts
   ExprP call_builtin(const std::string& name, std::vector<ExprP> args);  // returns null if not a builtin
   ExprP call_user(Function* fn, std::vector<ExprP> args);

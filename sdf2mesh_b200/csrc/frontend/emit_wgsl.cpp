@@ -55,6 +55,7 @@ class WgslWriter {
   static std::string type_name(const Type& t) {
     const char* s = t.sk == Sk::F32 ? "f32" : t.sk == Sk::I32 ? "i32" : t.sk == Sk::U32 ? "u32" : "bool";
     if (t.is_void()) return "void";
+    if (t.is_matrix()) return "mat" + std::to_string(t.n) + "x" + std::to_string(t.n) + "<f32>";
     if (t.is_scalar()) return s;
     return "vec" + std::to_string(t.n) + "<" + s + ">";
   }
@@ -151,11 +152,19 @@ class WgslWriter {
       }
       case Expr::Construct: {
         if (e.args.empty()) return type_name(e.ty) + "()";
+        if (e.ty.is_matrix() && e.args.size() == 1 && e.args[0]->ty.is_scalar()) {  // GLSL diagonal constructor
+          const std::string d = expr(*e.args[0]);
+          std::string m = type_name(e.ty) + "(";
+          for (int c = 0; c < e.ty.n; ++c)
+            for (int r = 0; r < e.ty.n; ++r) m += std::string(c || r ? ", " : "") + (c == r ? d : "0f");
+          return m + ")";
+        }
         std::string s = type_name(e.ty) + "(";
         for (size_t i = 0; i < e.args.size(); ++i) s += (i ? ", " : "") + expr(*e.args[i]);
         return s + ")";
       }
       case Expr::Swizzle: {
+        if (e.args[0]->ty.is_matrix()) return expr(*e.args[0]) + "[" + std::to_string(e.swz[0]) + "]";
         std::string s = expr(*e.args[0]) + ".";
         for (int i = 0; i < e.nswz; ++i) s += "xyzw"[e.swz[i]];
         return s;

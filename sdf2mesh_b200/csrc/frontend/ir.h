@@ -12,15 +12,17 @@ namespace s2m_frontend {
 enum class Sk : uint8_t { Bool, I32, U32, F32, AInt, AFloat };  // A* = WGSL abstract numerics
 
 struct Type {
-  enum K : uint8_t { Void, Scalar, Vector } k = Void;
+  enum K : uint8_t { Void, Scalar, Vector, Matrix } k = Void;  // Matrix: n x n of f32, column-major
   Sk sk = Sk::F32;
   int n = 1;  // vector width
   static Type scalar(Sk s) { Type t; t.k = Scalar; t.sk = s; t.n = 1; return t; }
   static Type vec(Sk s, int n) { Type t; t.k = n == 1 ? Scalar : Vector; t.sk = s; t.n = n; return t; }
+  static Type mat(int n) { Type t; t.k = Matrix; t.sk = Sk::F32; t.n = n; return t; }
   static Type void_() { return Type(); }
   bool is_void() const { return k == Void; }
   bool is_scalar() const { return k == Scalar; }
   bool is_vector() const { return k == Vector; }
+  bool is_matrix() const { return k == Matrix; }
   bool is_abstract() const { return !is_void() && (sk == Sk::AInt || sk == Sk::AFloat); }
   bool is_float() const { return !is_void() && (sk == Sk::F32 || sk == Sk::AFloat); }
   bool is_int() const { return !is_void() && (sk == Sk::I32 || sk == Sk::U32 || sk == Sk::AInt); }

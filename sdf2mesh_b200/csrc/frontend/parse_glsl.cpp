@@ -32,6 +32,8 @@ class GlslParser : public ParserBase {
     if (s == "uint") { *t = Type::scalar(Sk::U32); return true; }
     if (s == "bool") { *t = Type::scalar(Sk::Bool); return true; }
     if (s.size() == 4 && s.compare(0, 3, "vec") == 0 && s[3] >= '2' && s[3] <= '4') { *t = Type::vec(Sk::F32, s[3] - '0'); return true; }
+    if (s.size() == 4 && s.compare(0, 3, "mat") == 0 && s[3] >= '2' && s[3] <= '4') { *t = Type::mat(s[3] - '0'); return true; }
+    if (s.size() == 6 && s.compare(0, 3, "mat") == 0 && s[4] == 'x' && s[3] == s[5] && s[3] >= '2' && s[3] <= '4') { *t = Type::mat(s[3] - '0'); return true; }
     if (s.size() == 5 && s.compare(1, 3, "vec") == 0 && s[4] >= '2' && s[4] <= '4') {
       const Sk sk = s[0] == 'i' ? Sk::I32 : s[0] == 'u' ? Sk::U32 : s[0] == 'b' ? Sk::Bool : Sk::F32;
       if (s[0] == 'i' || s[0] == 'u' || s[0] == 'b') { *t = Type::vec(sk, s[4] - '0'); return true; }
@@ -424,10 +426,11 @@ class GlslParser : public ParserBase {
         ExprP idx = parse_expr();
         expect("]");
         ConstVal cv;
-        if (!e->ty.is_vector()) b.unsupported("indexing of non-vector values");
-        if (!idx->ty.is_int() || !b.const_eval(*idx, &cv)) b.unsupported("dynamic vector indexing");
-        if (cv.i[0] < 0 || cv.i[0] >= e->ty.n) b.error("vector index out of range");
-        e = b.swizzle(e, std::string(1, "xyzw"[cv.i[0]]));
+        if (!e->ty.is_vector() && !e->ty.is_matrix()) b.unsupported("indexing of non-vector values");
+        if (!idx->ty.is_int() || !b.const_eval(*idx, &cv)) b.unsupported("dynamic vector / matrix indexing");
+        if (cv.i[0] < 0 || cv.i[0] >= e->ty.n) b.error("index out of range");
+        if (e->ty.is_matrix()) e = b.matrix_column(e, (int)cv.i[0]);
+        else e = b.swizzle(e, std::string(1, "xyzw"[cv.i[0]]));
         continue;
       }
       break;
@@ -464,7 +467,7 @@ class GlslParser : public ParserBase {
     if (name == "true" || name == "false") { advance(); return b.lit_bool(name == "true"); }
     Type ty;
     if (is_punct("(", 1) && (type_from_name(name, &ty) || name.compare(0, 3, "mat") == 0)) {
-      if (name.compare(0, 3, "mat") == 0) b.unsupported("matrix types (" + name + ")");
+      if (!type_from_name(name, &ty)) b.unsupported("matrix type " + name + " (only square matrices)");
       advance();
       std::vector<ExprP> args = parse_args();
       return b.construct(ty, false, args);

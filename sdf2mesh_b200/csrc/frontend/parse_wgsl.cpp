@@ -32,7 +32,8 @@ class WgslParser : public ParserBase {
   // ---------------------------------------------------------------- types
   bool is_type_name(const std::string& s) const {
     static const std::set<std::string> names = {"f32", "i32", "u32", "bool", "vec2", "vec3", "vec4", "vec2f", "vec3f", "vec4f",
-                                                "vec2i", "vec3i", "vec4i", "vec2u", "vec3u", "vec4u", "vec2h", "vec3h", "vec4h", "f16"};
+                                                "vec2i", "vec3i", "vec4i", "vec2u", "vec3u", "vec4u", "vec2h", "vec3h", "vec4h", "f16",
+                                                "mat2x2", "mat3x3", "mat4x4", "mat2x2f", "mat3x3f", "mat4x4f"};
     return names.count(s) || aliases_.count(s);
   }
   static bool scalar_kind(const std::string& s, Sk* sk) {
@@ -81,7 +82,16 @@ class WgslParser : public ParserBase {
       *is_ptr = true;
       return t;
     }
-    if (name.compare(0, 3, "mat") == 0) b.unsupported("matrix types (" + name + ")");
+    if (name.compare(0, 3, "mat") == 0) {
+      if (name.size() >= 6 && name[4] == 'x' && name[3] == name[5] && name[3] >= '2' && name[3] <= '4' && (name.size() == 6 || (name.size() == 7 && name[6] == 'f'))) {
+        if (name.size() == 6 && accept("<")) {
+          if (expect_ident("a scalar type") != "f32") b.unsupported("non-f32 matrices");
+          expect_close_angle();
+        }
+        return Type::mat(name[3] - '0');
+      }
+      b.unsupported("matrix type " + name + " (only square f32 matrices)");
+    }
     if (name == "array") b.unsupported("array types");
     if (name == "atomic" || name.compare(0, 7, "texture") == 0 || name == "sampler") b.unsupported("type " + name);
     b.unsupported("user-defined type '" + name + "'");
@@ -513,10 +523,11 @@ class WgslParser : public ParserBase {
         ExprP idx = parse_expr();
         expect("]");
         ConstVal cv;
-        if (!e->ty.is_vector()) b.unsupported("indexing of non-vector values");
-        if (!idx->ty.is_int() || !b.const_eval(*idx, &cv)) b.unsupported("dynamic vector indexing");
-        if (cv.i[0] < 0 || cv.i[0] >= e->ty.n) b.error("vector index out of range");
-        e = b.swizzle(e, std::string(1, "xyzw"[cv.i[0]]));
+        if (!e->ty.is_vector() && !e->ty.is_matrix()) b.unsupported("indexing of non-vector values");
+        if (!idx->ty.is_int() || !b.const_eval(*idx, &cv)) b.unsupported("dynamic vector / matrix indexing");
+        if (cv.i[0] < 0 || cv.i[0] >= e->ty.n) b.error("index out of range");
+        if (e->ty.is_matrix()) e = b.matrix_column(e, (int)cv.i[0]);
+        else e = b.swizzle(e, std::string(1, "xyzw"[cv.i[0]]));
         continue;
       }
       break;

@@ -226,6 +226,64 @@ S2M_HD vec3 f_cross(const vec3& a, const vec3& b) {
 S2M_HD vec2 f_reflect(const vec2& i, const vec2& n) { return i - (2.0f * f_dot(n, i)) * n; }
 S2M_HD vec3 f_reflect(const vec3& i, const vec3& n) { return i - (2.0f * f_dot(n, i)) * n; }
 
+
+/* ---- square matrices, column-major (c0 = first column), as in WGSL / GLSL.
+ * Pinned: (M*v)_i = sum_j M[j][i]*v[j], summed left to right; v*M = (dot(v,M[0]), dot(v,M[1]), ...);
+ * (A*B)[j] = A*B[j]. */
+struct mat2 { vec2 c0, c1; };
+struct mat3 { vec3 c0, c1, c2; };
+struct mat4 { vec4 c0, c1, c2, c3; };
+S2M_HD mat2 mkm2(const vec2& a, const vec2& b) { mat2 m; m.c0 = a; m.c1 = b; return m; }
+S2M_HD mat3 mkm3(const vec3& a, const vec3& b, const vec3& c) { mat3 m; m.c0 = a; m.c1 = b; m.c2 = c; return m; }
+S2M_HD mat4 mkm4(const vec4& a, const vec4& b, const vec4& c, const vec4& d) { mat4 m; m.c0 = a; m.c1 = b; m.c2 = c; m.c3 = d; return m; }
+S2M_HD mat2 mkm2(float a, float b, float c, float d) { return mkm2(mk2(a, b), mk2(c, d)); }
+S2M_HD mat3 mkm3(float a, float b, float c, float d, float e, float f, float g, float h, float i) { return mkm3(mk3(a, b, c), mk3(d, e, f), mk3(g, h, i)); }
+S2M_HD mat4 mkm4(float a, float b, float c, float d, float e, float f, float g, float h, float i, float j, float k, float l, float m, float n, float o, float p) {
+  return mkm4(mk4(a, b, c, d), mk4(e, f, g, h), mk4(i, j, k, l), mk4(m, n, o, p));
+}
+S2M_HD mat2 diagm2(float s) { return mkm2(s, 0.0f, 0.0f, s); }
+S2M_HD mat3 diagm3(float s) { return mkm3(s, 0.0f, 0.0f, 0.0f, s, 0.0f, 0.0f, 0.0f, s); }
+S2M_HD mat4 diagm4(float s) { return mkm4(s, 0.0f, 0.0f, 0.0f, 0.0f, s, 0.0f, 0.0f, 0.0f, 0.0f, s, 0.0f, 0.0f, 0.0f, 0.0f, s); }
+S2M_HD vec2 operator*(const mat2& m, const vec2& v) { return mk2(m.c0.x * v.x + m.c1.x * v.y, m.c0.y * v.x + m.c1.y * v.y); }
+S2M_HD vec3 operator*(const mat3& m, const vec3& v) {
+  return mk3(m.c0.x * v.x + m.c1.x * v.y + m.c2.x * v.z, m.c0.y * v.x + m.c1.y * v.y + m.c2.y * v.z, m.c0.z * v.x + m.c1.z * v.y + m.c2.z * v.z);
+}
+S2M_HD vec4 operator*(const mat4& m, const vec4& v) {
+  return mk4(m.c0.x * v.x + m.c1.x * v.y + m.c2.x * v.z + m.c3.x * v.w, m.c0.y * v.x + m.c1.y * v.y + m.c2.y * v.z + m.c3.y * v.w,
+             m.c0.z * v.x + m.c1.z * v.y + m.c2.z * v.z + m.c3.z * v.w, m.c0.w * v.x + m.c1.w * v.y + m.c2.w * v.z + m.c3.w * v.w);
+}
+S2M_HD vec2 operator*(const vec2& v, const mat2& m) { return mk2(f_dot(v, m.c0), f_dot(v, m.c1)); }
+S2M_HD vec3 operator*(const vec3& v, const mat3& m) { return mk3(f_dot(v, m.c0), f_dot(v, m.c1), f_dot(v, m.c2)); }
+S2M_HD vec4 operator*(const vec4& v, const mat4& m) { return mk4(f_dot(v, m.c0), f_dot(v, m.c1), f_dot(v, m.c2), f_dot(v, m.c3)); }
+S2M_HD mat2 operator*(const mat2& a, const mat2& b) { return mkm2(a * b.c0, a * b.c1); }
+S2M_HD mat3 operator*(const mat3& a, const mat3& b) { return mkm3(a * b.c0, a * b.c1, a * b.c2); }
+S2M_HD mat4 operator*(const mat4& a, const mat4& b) { return mkm4(a * b.c0, a * b.c1, a * b.c2, a * b.c3); }
+S2M_HD mat2 operator*(const mat2& a, float s) { return mkm2(a.c0 * s, a.c1 * s); }
+S2M_HD mat3 operator*(const mat3& a, float s) { return mkm3(a.c0 * s, a.c1 * s, a.c2 * s); }
+S2M_HD mat4 operator*(const mat4& a, float s) { return mkm4(a.c0 * s, a.c1 * s, a.c2 * s, a.c3 * s); }
+S2M_HD mat2 operator*(float s, const mat2& a) { return mkm2(s * a.c0, s * a.c1); }
+S2M_HD mat3 operator*(float s, const mat3& a) { return mkm3(s * a.c0, s * a.c1, s * a.c2); }
+S2M_HD mat4 operator*(float s, const mat4& a) { return mkm4(s * a.c0, s * a.c1, s * a.c2, s * a.c3); }
+S2M_HD mat2 operator/(const mat2& a, float s) { return mkm2(a.c0 / s, a.c1 / s); }
+S2M_HD mat3 operator/(const mat3& a, float s) { return mkm3(a.c0 / s, a.c1 / s, a.c2 / s); }
+S2M_HD mat4 operator/(const mat4& a, float s) { return mkm4(a.c0 / s, a.c1 / s, a.c2 / s, a.c3 / s); }
+S2M_HD mat2 operator+(const mat2& a, const mat2& b) { return mkm2(a.c0 + b.c0, a.c1 + b.c1); }
+S2M_HD mat3 operator+(const mat3& a, const mat3& b) { return mkm3(a.c0 + b.c0, a.c1 + b.c1, a.c2 + b.c2); }
+S2M_HD mat4 operator+(const mat4& a, const mat4& b) { return mkm4(a.c0 + b.c0, a.c1 + b.c1, a.c2 + b.c2, a.c3 + b.c3); }
+S2M_HD mat2 operator-(const mat2& a, const mat2& b) { return mkm2(a.c0 - b.c0, a.c1 - b.c1); }
+S2M_HD mat3 operator-(const mat3& a, const mat3& b) { return mkm3(a.c0 - b.c0, a.c1 - b.c1, a.c2 - b.c2); }
+S2M_HD mat4 operator-(const mat4& a, const mat4& b) { return mkm4(a.c0 - b.c0, a.c1 - b.c1, a.c2 - b.c2, a.c3 - b.c3); }
+S2M_HD mat2 operator-(const mat2& a) { return mkm2(-a.c0, -a.c1); }
+S2M_HD mat3 operator-(const mat3& a) { return mkm3(-a.c0, -a.c1, -a.c2); }
+S2M_HD mat4 operator-(const mat4& a) { return mkm4(-a.c0, -a.c1, -a.c2, -a.c3); }
+S2M_HD mat2 f_transpose(const mat2& m) { return mkm2(m.c0.x, m.c1.x, m.c0.y, m.c1.y); }
+S2M_HD mat3 f_transpose(const mat3& m) { return mkm3(m.c0.x, m.c1.x, m.c2.x, m.c0.y, m.c1.y, m.c2.y, m.c0.z, m.c1.z, m.c2.z); }
+S2M_HD mat4 f_transpose(const mat4& m) {
+  return mkm4(m.c0.x, m.c1.x, m.c2.x, m.c3.x, m.c0.y, m.c1.y, m.c2.y, m.c3.y, m.c0.z, m.c1.z, m.c2.z, m.c3.z, m.c0.w, m.c1.w, m.c2.w, m.c3.w);
+}
+S2M_HD float f_determinant(const mat2& m) { return m.c0.x * m.c1.y - m.c1.x * m.c0.y; }
+S2M_HD float f_determinant(const mat3& m) { return f_dot(m.c0, f_cross(m.c1, m.c2)); }
+
 /* ---- comparisons / selection */
 #define S2M_CMP(NAME, OP)                                                                                \
   S2M_HD bvec2 NAME(const vec2& a, const vec2& b) { return mkb2(a.x OP b.x, a.y OP b.y); }               \

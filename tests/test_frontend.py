@@ -343,3 +343,71 @@ def test_continue_to_break_rewrite(built, monkeypatch):
         assert f32_equal(host_eval.eval_points(opt, pts), host_eval.eval_points(plain, pts)).all()
     monkeypatch.delenv("S2M_NO_IR_OPT", raising=False)
     assert "break;" in load_example_shader("mandelbulb").lower_to_cuda()
+
+
+def test_matrices(built, tmp_path):
+    """mat2/mat3 (GLSL) and mat2x2f/mat3x3<f32> (WGSL): constructors, m*v, v*m, m*m, m[i], transpose"""
+    glsl = textwrap.dedent("""\
+        #version 450 core
+        mat2 rot(float a) { float c = cos(a), s = sin(a); return mat2(c, -s, s, c); }
+        float sdf(vec3 p) {
+            p.xz *= rot(0.7);
+            p.xy = rot(-0.3) * p.xy;
+            mat3 m = mat3(vec3(1.0, 0.5, 0.0), vec3(0.0, 1.0, 0.25), vec3(0.1, 0.0, 1.0));
+            vec3 q = transpose(m) * p + m[1] * 0.5;
+            mat3 mm = m * mat3(2.0);
+            return length(q * mm) - determinant(m);
+        }
+        void main() {}
+        """)
+    f = tmp_path / "m.frag"
+    f.write_text(glsl)
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(f, "sdf")
+    assert "mat2x2<f32>" in sh.source and "mat3x3<f32>" in sh.source
+    pts = points(3.0, 1000)
+    F = np.float32
+
+    def rot(a):
+        c, s = F(np.cos(F(a))), F(np.sin(F(a)))
+        return np.array([[c, -s], [s, c]], F)  # columns: (c,-s), (s,c)
+
+    def mv(cols, v):  # sum_j cols[j]*v[j], left to right, f32
+        acc = cols[0] * v[0]
+        for j in range(1, len(v)):
+            acc = (acc + cols[j] * v[j]).astype(F)
+        return acc.astype(F)
+
+    def vm(v, cols):
+        out = []
+        for c in cols:
+            acc = F(v[0] * c[0])
+            for j in range(1, len(v)):
+                acc = F(acc + F(v[j] * c[j]))
+            out.append(acc)
+        return np.array(out, F)
+
+    def ref(p):
+        p = p.astype(F).copy()
+        r1 = rot(0.7)
+        p[[0, 2]] = vm(p[[0, 2]], r1)           # p.xz = p.xz * rot
+        p[[0, 1]] = mv(rot(-0.3), p[[0, 1]])    # p.xy = rot * p.xy
+        m = np.array([[1.0, 0.5, 0.0], [0.0, 1.0, 0.25], [0.1, 0.0, 1.0]], F)  # m[j] = column j
+        mt = m.T.copy()                          # transpose: columns of mt = rows of m
+        q = (mv(mt, p) + m[1] * F(0.5)).astype(F)
+        two = np.diag(np.full(3, 2.0, F)).astype(F)
+        mm = np.array([mv(m, two[j]) for j in range(3)], F)
+        v = vm(q, mm)
+        ln = F(np.sqrt(F(F(F(v[0] * v[0]) + F(v[1] * v[1])) + F(v[2] * v[2]))))
+        cr = np.array([F(F(m[1][1] * m[2][2]) - F(m[1][2] * m[2][1])), F(F(m[1][2] * m[2][0]) - F(m[1][0] * m[2][2])),
+                       F(F(m[1][0] * m[2][1]) - F(m[1][1] * m[2][0]))], F)
+        det = F(F(F(m[0][0] * cr[0]) + F(m[0][1] * cr[1])) + F(m[0][2] * cr[2]))
+        return F(ln - det)
+
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+    want = np.array([ref(p) for p in pts], F)
+    # cos/sin here are the engine's pinned functions; numpy's may differ in the last ulp
+    assert np.allclose(got, want, rtol=2e-6, atol=2e-6)
+    wgsl = "fn sdf3d(p: vec3f) -> f32 { let m = mat2x2f(vec2f(0.0, 1.0), vec2f(-1.0, 0.0)); let n = mat2x2<f32>(1.0, 2.0, 3.0, 4.0); let q = (m * n) * p.xy; return q.x + n[1].y + (p.xy * m).y; }"
+    v = run_wgsl(wgsl, [[1.0, 2.0, 0.0]])[0]
+    # m*n columns: m*(1,2) = (-2,1), m*(3,4) = (-4,3);  (m*n)*(1,2) = (-2-8, 1+6) = (-10, 7);  (p.xy*m).y = dot((1,2),(-1,0)) = -1
+    assert v == np.float32(-10.0 + 4.0 - 1.0)

@@ -233,3 +233,31 @@ def test_classify_paths_agree(ctx, name, dims, bmin, bmax):
             r.free()
     for o in out[1:]:
         assert np.array_equal(o[0], out[0][0]) and np.array_equal(o[1], out[0][1]) and np.array_equal(o[2], out[0][2])
+
+
+def test_4096_cubed_properties(ctx):
+    """BASELINE config 5: 4096^3 (beyond the reference's 2048 texture limit) on ONE GPU, chunked slab.
+    No oracle at this size (~20 CPU-minutes): structural properties + determinism of the counts."""
+    p, _ = s2m.params_from_cli(4096, 5.0, flags=s2m.MESH_NO_NORMALS)
+    m = module_for(ctx, "mandelbulb")
+    r = s2m.mesh_run(ctx, m, p)
+    d = r.data()
+    k = d.keys
+    assert len(k) > 30_000_000 and d.timings["chunks"] > 8
+    assert np.all(k[1:] > k[:-1])
+    z = (k >> np.uint64(32)).astype(np.int64)
+    assert z.min() >= 1 and z.max() <= 4095
+    q = d.quads
+    assert int(q.max()) < len(k)
+    sel = np.random.default_rng(0).integers(0, len(q), 2_000_000)
+    qs = q[sel]
+    x = (k & np.uint64(0xFFFF)).astype(np.int64); y = ((k >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.int64)
+    cx, cy, cz = x[qs], y[qs], z[qs]
+    span = (cx.max(1) - cx.min(1)) + (cy.max(1) - cy.min(1)) + (cz.max(1) - cz.min(1))
+    assert np.all(span == 2)
+    counts = (len(k), len(q), d.n_invalid_quads)
+    r.free()
+    r = s2m.mesh_run(ctx, m, p)
+    d = r.data()
+    assert (len(d.keys), len(d.quads), d.n_invalid_quads) == counts
+    r.free()
