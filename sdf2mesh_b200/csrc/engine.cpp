@@ -915,7 +915,7 @@ extern "C" int s2m_cost_probe(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
   if ((st = buf.ensure((size_t)planes * 8 + 64))) return st;
   cudaStream_t s = c->stream;
   cudaError_t e = cudaMemsetAsync(buf.p, 0, (size_t)planes * 8 + 64, s);
-  unsigned probe = 64, pl = planes;
+  unsigned probe = 128, pl = planes;
   unsigned long long* cyc = buf.as<unsigned long long>();
   float* sink = reinterpret_cast<float*>(cyc + planes);
   void* args[] = {&g, &probe, &pl, &cyc, &sink};

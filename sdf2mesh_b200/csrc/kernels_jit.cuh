@@ -293,20 +293,26 @@ extern "C" __global__ void s2m_k_eval(const float* __restrict__ pts, float* __re
 }
 
 /* Coarse cost probe: block b evaluates a (probe x probe) lattice of plane z_b of a `planes`-plane
- * coarse grid and records the SM cycles it took (max over warps), a proxy for per-slice K1 cost. */
+ * coarse grid; every warp adds the SM cycles it spent (issue time including divergence), so the
+ * per-plane sums are proportional to K1's work per z-slice. */
 extern "C" __global__ void __launch_bounds__(256)
 s2m_k_cost_probe(S2mGrid g, unsigned probe, unsigned planes, unsigned long long* __restrict__ cycles, float* __restrict__ sink) {
   const unsigned pz = blockIdx.x;
   const float fz = g.bmin[2] + (g.size[2] * (float)g.res[2]) * ((float)pz + 0.5f) / (float)planes;
-  const long long t0 = clock64();
   float acc = 0.0f;
-  for (unsigned i = threadIdx.x; i < probe * probe; i += blockDim.x) {
-    const unsigned ix = i % probe, iy = i / probe;
-    const float fx = g.bmin[0] + (g.size[0] * (float)g.res[0]) * ((float)ix + 0.5f) / (float)probe;
-    const float fy = g.bmin[1] + (g.size[1] * (float)g.res[1]) * ((float)iy + 0.5f) / (float)probe;
-    acc += s2m_sdf(fx, fy, fz);
+  /* a warp covers a compact 8x4 patch per step, like K1's warps */
+  const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const unsigned tiles_x = (probe + 7u) / 8u, tiles_y = (probe + 3u) / 4u;
+  const long long t0 = clock64();
+  for (unsigned t = warp; t < tiles_x * tiles_y; t += blockDim.x >> 5) {
+    const unsigned ix = (t % tiles_x) * 8u + (lane & 7u), iy = (t / tiles_x) * 4u + (lane >> 3);
+    if (ix < probe && iy < probe) {
+      const float fx = g.bmin[0] + (g.size[0] * (float)g.res[0]) * ((float)ix + 0.5f) / (float)probe;
+      const float fy = g.bmin[1] + (g.size[1] * (float)g.res[1]) * ((float)iy + 0.5f) / (float)probe;
+      acc += s2m_sdf(fx, fy, fz);
+    }
   }
   const long long t1 = clock64();
-  atomicMax(cycles + pz, (unsigned long long)(t1 - t0));
+  if (lane == 0) atomicAdd(cycles + pz, (unsigned long long)(t1 - t0));
   if (acc == 123.456f) sink[0] = acc;
 }
