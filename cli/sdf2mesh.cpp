@@ -140,6 +140,7 @@ int main(int argc, char** argv) {
   if (a.all_slices) params.flags |= S2M_MESH_ALL_SLICES;
   if (a.exact_dense) params.flags |= S2M_MESH_EXACT_DENSE;
   if (a.no_normals) params.flags |= S2M_MESH_NO_NORMALS;
+  params.flags |= S2M_MESH_KEEP_INVALID;  // so that the reference's per-quad warnings can be printed
 
   s2m_ctx* ctx = nullptr;
   if (s2m_ctx_create(a.device, &ctx)) die("no usable CUDA device");  // request_adapter/request_device .unwrap()
@@ -188,7 +189,16 @@ int main(int argc, char** argv) {
   s2m_result_info ri;
   s2m_result_get(result, &ri);
   info("Mesh has " + std::to_string(ri.n_vertices) + " vertices.");
-  if (ri.n_invalid_quads) warn(std::to_string(ri.n_invalid_quads) + " invalid quads. Mesh will not be water-tight!");
+  {  // mesh.rs:276: one warning per invalid quad, with u32::MAX for a missing corner
+    const uint64_t shown = ri.n_invalid_records < 64 ? ri.n_invalid_records : 64;
+    for (uint64_t i = 0; i < shown; ++i) {
+      const uint64_t* q = ri.invalid_records + 6 * i + 2;
+      std::string s = "Invalid quad: Quad(";
+      for (int k = 0; k < 4; ++k) s += (k ? ", " : "") + (q[k] == UINT64_MAX ? std::string("4294967295") : std::to_string(q[k]));
+      warn(s + "). Mesh will not be water-tight!");
+    }
+    if (ri.n_invalid_quads > shown) warn("... " + std::to_string(ri.n_invalid_quads - shown) + " more invalid quads. Mesh will not be water-tight!");
+  }
   if (a.stats) {
     const s2m_timings& t = ri.timings;
     const double vox = (double)params.dims[0] * params.dims[1] * params.dims[2];

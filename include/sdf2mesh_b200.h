@@ -110,6 +110,7 @@ void s2m_module_free(s2m_module* m);
 #define S2M_MESH_NO_NORMALS 2u      /* skip sdf3d_normal (normals only reach the PLY writer) */
 #define S2M_MESH_EXACT_DENSE 4u     /* reference-cost mode: every cell is a candidate (8 evaluations per cell) */
 #define S2M_MESH_KEEP_CANDIDATES 8u /* keep the candidate key list in the result (tests) */
+#define S2M_MESH_KEEP_INVALID 32u    /* keep the list of invalid quads (which cell, which edge, which corner is missing) */
 #define S2M_MESH_CLASSIFY_FROM_SLAB 16u /* K2 re-reads the f32 slab through shared memory instead of K1's class bit planes */
 
 typedef struct s2m_mesh_params {
@@ -153,6 +154,11 @@ typedef struct s2m_result_info {
   const uint8_t* sign_nibbles; /* n_vertices: bit0 s100, bit1 s010, bit2 s001, bit3 s000 (main.rs:338-339) */
   const uint64_t* quads;       /* 4 * n_quads global vertex indices, after Quad::swap, reference order */
   const uint64_t* candidates;  /* n_candidates keys (true z) if S2M_MESH_KEEP_CANDIDATES, else NULL */
+  /* S2M_MESH_KEEP_INVALID: the quads the reference reports as "Invalid quad: Quad(..)" (mesh.rs:270-278),
+   * 6 u64 per record: cell key, edge (0 = X, 1 = Y, 2 = Z), q0..q3 after Quad::swap with
+   * UINT64_MAX for a missing vertex; sorted by (key, edge) = the reference's order.  At most 2^20. */
+  const uint64_t* invalid_records;
+  uint64_t n_invalid_records;
   s2m_timings timings;
 } s2m_result_info;
 

@@ -38,6 +38,8 @@ def lib():
         L.oracle_mesh_counts.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 5
         L.oracle_mesh_copy.argtypes = [ctypes.c_void_p] * 6
         L.oracle_mesh_free.argtypes = [ctypes.c_void_p]
+        L.oracle_mesh_invalid.restype = ctypes.c_uint64
+        L.oracle_mesh_invalid.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_write_stl.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.oracle_write_ply.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.oracle_eval.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
@@ -64,6 +66,14 @@ class OracleMesh:
         if self._handle:
             lib().oracle_mesh_free(self._handle)
             self._handle = 0
+
+    def invalid_records(self) -> np.ndarray:
+        """(n, 6) u64: key, edge, q0..q3 (UINT64_MAX = missing), in the reference's warning order"""
+        n = lib().oracle_mesh_invalid(self._handle, None)
+        out = np.empty((n, 6), np.uint64)
+        if n:
+            lib().oracle_mesh_invalid(self._handle, out.ctypes.data)
+        return out
 
     def write_stl(self, path):
         assert lib().oracle_write_stl(self._handle, str(path).encode()) == 0

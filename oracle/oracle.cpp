@@ -51,6 +51,7 @@ struct Mesh {
   std::vector<Item> items;
   std::vector<uint64_t> quads;  // 4 per quad, after swap, emission order (valid quads only)
   uint64_t n_invalid = 0;
+  std::vector<uint64_t> invalid;  // 6 per invalid quad: key, edge (0 X, 1 Y, 2 Z), q0..q3 after swap (MISSING = ~0)
   double seconds_cells = 0, seconds_quads = 0;
 };
 
@@ -154,21 +155,30 @@ inline uint64_t vertex_index(const std::vector<Item>& v, uint16_t x, uint16_t y,
 
 // mesh.rs:267-324 + lib.rs:190-211
 void assemble_quads(Mesh& m) {
+  uint64_t cur_key = 0, cur_edge = 0;
   auto push = [&](uint64_t q0, uint64_t q1, uint64_t q2, uint64_t q3, bool swap) {
     uint64_t q[4] = {q0, q1, q2, q3};
     if (swap) { std::swap(q[0], q[3]); std::swap(q[1], q[2]); }
     if (q[0] != MISSING && q[1] != MISSING && q[2] != MISSING && q[3] != MISSING) m.quads.insert(m.quads.end(), q, q + 4);
-    else m.n_invalid++;
+    else {
+      m.n_invalid++;  // mesh.rs:276 log::warn!("Invalid quad: {:?}. Mesh will not be water-tight!", quad)
+      const uint64_t rec[6] = {cur_key, cur_edge, q[0], q[1], q[2], q[3]};
+      m.invalid.insert(m.invalid.end(), rec, rec + 6);
+    }
   };
   const std::vector<Item>& v = m.items;
   for (size_t i = 0; i < v.size(); ++i) {
     const Item& it = v[i];
     bool s100 = it.nibble & 1, s010 = it.nibble & 2, s001 = it.nibble & 4, s000 = it.nibble & 8;
     uint16_t x = it.x, y = it.y, z = it.z;
+    cur_key = it.key();
+    cur_edge = 0;
     if (s100 != s000 && y > 0 && z > 0)
       push(vertex_index(v, x, y - 1, z - 1), vertex_index(v, x, y, z - 1), vertex_index(v, x, y, z), vertex_index(v, x, y - 1, z), s100);
+    cur_edge = 1;
     if (s010 != s000 && x > 0 && z > 0)
       push(vertex_index(v, x - 1, y, z - 1), vertex_index(v, x, y, z - 1), vertex_index(v, x, y, z), vertex_index(v, x - 1, y, z), !s010);
+    cur_edge = 2;
     if (s001 != s000 && x > 0 && y > 0)
       push(vertex_index(v, x - 1, y - 1, z), vertex_index(v, x, y - 1, z), vertex_index(v, x, y, z), vertex_index(v, x - 1, y, z), s001);
   }
@@ -290,6 +300,12 @@ void oracle_mesh_copy(void* h, float* pos, float* nrm, uint64_t* keys, uint8_t* 
     nibbles[i] = it.nibble;
   }
   if (!m->quads.empty()) memcpy(quads, m->quads.data(), m->quads.size() * 8);
+}
+
+uint64_t oracle_mesh_invalid(void* h, uint64_t* out) {  // out may be NULL: returns the record count
+  Mesh* m = (Mesh*)h;
+  if (out && !m->invalid.empty()) memcpy(out, m->invalid.data(), m->invalid.size() * 8);
+  return m->invalid.size() / 6;
 }
 
 void oracle_mesh_free(void* h) { delete (Mesh*)h; }

@@ -17,6 +17,7 @@ STATUS_NAMES = {
 SRC_SDF3D, SRC_GLSL_FRAGMENT, SRC_WGSL, SRC_CUDA = 0, 1, 2, 3
 COMPILE_ALLOW_FMA = 1
 MESH_ALL_SLICES, MESH_NO_NORMALS, MESH_EXACT_DENSE, MESH_KEEP_CANDIDATES, MESH_CLASSIFY_FROM_SLAB = 1, 2, 4, 8, 16
+MESH_KEEP_INVALID = 32
 
 
 class S2mError(RuntimeError):
@@ -64,6 +65,7 @@ class ResultInfo(ctypes.Structure):
         ("positions", ctypes.POINTER(ctypes.c_float)), ("normals", ctypes.POINTER(ctypes.c_float)),
         ("cell_keys", ctypes.POINTER(ctypes.c_uint64)), ("sign_nibbles", ctypes.POINTER(ctypes.c_uint8)),
         ("quads", ctypes.POINTER(ctypes.c_uint64)), ("candidates", ctypes.POINTER(ctypes.c_uint64)),
+        ("invalid_records", ctypes.POINTER(ctypes.c_uint64)), ("n_invalid_records", ctypes.c_uint64),
         ("timings", Timings),
     ]
 

@@ -156,7 +156,7 @@ struct s2m_ctx {
   cudaDeviceProp prop{};
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   DevBuf slab, cls, cand_mask, word_prefix, cand_key, cand_vrank, status, counters;
-  DevBuf v_pos, v_nrm, v_key, v_nib, quads, scratch;
+  DevBuf v_pos, v_nrm, v_key, v_nib, quads, scratch, invalid;
   std::vector<PinnedBlock> pinned;
   unsigned long long* h_counters = nullptr;  // pinned, 16 words
   cudaEvent_t ev[16]{};
@@ -188,7 +188,8 @@ struct s2m_ctx {
   }
 };
 
-enum Counter { C_NCAND = 0, C_NVERT = 1, C_NHALO = 2, C_NQUAD = 3, C_NINVALID = 4, C_TICKET0 = 5, C_TICKET1 = 6, C_TICKET2 = 7, C_COUNT = 16 };
+enum Counter { C_NCAND = 0, C_NVERT = 1, C_NHALO = 2, C_NQUAD = 3, C_NINVALID = 4, C_TICKET0 = 5, C_TICKET1 = 6, C_TICKET2 = 7, C_INVALID_CURSOR = 8, C_COUNT = 16 };
+constexpr unsigned long long kInvalidCapacity = 1ull << 20;
 
 extern "C" int s2m_ctx_create(int device_ordinal, s2m_ctx** out) {
   if (!out) return fail(S2M_ERR_INVALID_ARG, "s2m_ctx_create: out is NULL");
@@ -225,7 +226,7 @@ extern "C" void s2m_ctx_destroy(s2m_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (DevBuf* b : {&c->slab, &c->cls, &c->cand_mask, &c->word_prefix, &c->cand_key, &c->cand_vrank, &c->status, &c->counters,
-                    &c->v_pos, &c->v_nrm, &c->v_key, &c->v_nib, &c->quads, &c->scratch})
+                    &c->v_pos, &c->v_nrm, &c->v_key, &c->v_nib, &c->quads, &c->scratch, &c->invalid})
     b->release();
   for (auto& b : c->pinned) cudaFreeHost(b.p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -402,7 +403,8 @@ struct s2m_result {
   uint32_t z_first = 0, nz = 0, label_add = 0, halo = 0, words_x = 0;
   uint64_t n_cand = 0, n_vert_total = 0, n_halo = 0, n_quads = 0, n_invalid = 0;
   float* h_pos = nullptr; float* h_nrm = nullptr; uint64_t* h_key = nullptr; uint8_t* h_nib = nullptr;
-  uint64_t* h_quads = nullptr; uint64_t* h_cand = nullptr;
+  uint64_t* h_quads = nullptr; uint64_t* h_cand = nullptr; uint64_t* h_invalid = nullptr;
+  uint64_t n_invalid_records = 0;
   uint64_t cap_v = 0, cap_q = 0;   // capacity (elements) of the pinned vertex / quad blocks
   bool streamed = false;           // vertex (and quad) chunks were copied while later chunks computed
   bool quads_done = false;         // K4b ran inside begin (single-slab s2m_mesh_run)
@@ -417,7 +419,7 @@ struct s2m_result {
 extern "C" void s2m_result_free(s2m_result* r) {
   if (!r) return;
   if (r->ctx) {
-    for (void* p : {(void*)r->h_pos, (void*)r->h_nrm, (void*)r->h_key, (void*)r->h_nib, (void*)r->h_quads, (void*)r->h_cand})
+    for (void* p : {(void*)r->h_pos, (void*)r->h_nrm, (void*)r->h_key, (void*)r->h_nib, (void*)r->h_quads, (void*)r->h_cand, (void*)r->h_invalid})
       if (p) r->ctx->release_pinned(p);
     if (!r->finished) r->ctx->busy = false;
   }
@@ -511,6 +513,10 @@ int launch_k4b(s2m_ctx* c, s2m_result* r, cudaStream_t s, uint64_t v_begin, uint
   a.index_offset = index_offset;
   a.quads = c->quads.as<unsigned long long>(); a.status = c->scratch.as<unsigned long long>() + 1;
   a.ticket = reinterpret_cast<unsigned*>(c->scratch.p); a.n_quads = d_cnt + C_NQUAD; a.n_invalid = d_cnt + C_NINVALID;
+  if (r->params.flags & S2M_MESH_KEEP_INVALID) {
+    if ((st = c->invalid.ensure(kInvalidCapacity * 48))) return st;
+    a.invalid_records = c->invalid.as<unsigned long long>(); a.invalid_cursor = d_cnt + C_INVALID_CURSOR; a.invalid_capacity = kInvalidCapacity;
+  }
   SPAN_BEGIN(4, s);
   int e = s2m_launch_k4b(&a, s);
   if (e) return fail(S2M_ERR_CUDA, std::string("k4_quads launch: ") + cudaGetErrorString((cudaError_t)e));
@@ -819,6 +825,20 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
     return fail(S2M_ERR_STATE, "quads were already emitted with base 0 (s2m_mesh_run); use s2m_mesh_begin for multi-slab runs");
   }
   c->hint_nq = r->n_quads;
+  if (r->params.flags & S2M_MESH_KEEP_INVALID) {
+    if ((st = read_counters(c, s))) return st;
+    r->n_invalid_records = std::min<uint64_t>(c->h_counters[C_INVALID_CURSOR], kInvalidCapacity);
+    r->h_invalid = (uint64_t*)c->lease_pinned(r->n_invalid_records * 48 + 48);
+    if (!r->h_invalid) return fail(S2M_ERR_OOM, "cudaHostAlloc for the invalid-quad list failed");
+    if (r->n_invalid_records) {
+      CUDA_TRY(cudaMemcpyAsync(r->h_invalid, c->invalid.p, r->n_invalid_records * 48, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      // the device appends in completion order; the reference reports them in (vertex, edge) order
+      struct Rec { uint64_t v[6]; };
+      Rec* recs = reinterpret_cast<Rec*>(r->h_invalid);
+      std::sort(recs, recs + r->n_invalid_records, [](const Rec& x, const Rec& y) { return x.v[0] != y.v[0] ? x.v[0] < y.v[0] : x.v[1] < y.v[1]; });
+    }
+  }
   {  // everything (both streams) done -> total span
     const size_t e = take_event(c, r);
     CUDA_TRY(cudaEventRecord(c->ev_pool[e], c->copy_stream));
@@ -853,6 +873,7 @@ extern "C" int s2m_result_get(const s2m_result* r, s2m_result_info* o) {
   o->n_candidates = r->n_cand;
   o->positions = r->h_pos; o->normals = r->h_nrm; o->cell_keys = r->h_key; o->sign_nibbles = r->h_nib;
   o->quads = r->h_quads; o->candidates = r->h_cand;
+  o->invalid_records = r->h_invalid; o->n_invalid_records = r->n_invalid_records;
   o->timings = r->t;
   return S2M_OK;
 }

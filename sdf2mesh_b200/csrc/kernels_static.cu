@@ -256,6 +256,9 @@ struct QuadParams {
   unsigned* ticket;
   unsigned long long* n_quads;
   unsigned long long* n_invalid;
+  unsigned long long* invalid_records;
+  unsigned long long* invalid_cursor;
+  unsigned long long invalid_capacity;
 };
 
 constexpr uint32_t MISSING32 = 0xffffffffu;
@@ -295,20 +298,33 @@ k4_quads(QuadParams p) {
     const uint32_t self = (uint32_t)vi;
     // mesh.rs:286-296  X-edge quad.  The z guard is on the LABEL; a slice below the
     // first scanned one does not exist in the list -> MISSING -> invalid quad, as in the reference.
-    auto emit = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool swap) {
-      if (a == MISSING32 || b == MISSING32 || c == MISSING32 || d == MISSING32) { ++ninvalid; return; }
+    auto emit = [&](uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool swap, unsigned edge) {
+      if (a == MISSING32 || b == MISSING32 || c == MISSING32 || d == MISSING32) {
+        ++ninvalid;
+        if (p.invalid_records) {  // rare: a handful per million vertices
+          const unsigned long long slot = atomicAdd(p.invalid_cursor, 1ull);
+          if (slot < p.invalid_capacity) {
+            uint32_t o[4] = {a, b, c, d};
+            if (swap) { o[0] = d; o[1] = c; o[2] = b; o[3] = a; }
+            unsigned long long* rec = p.invalid_records + 6ull * slot;
+            rec[0] = key; rec[1] = edge;
+            for (int t = 0; t < 4; ++t) rec[2 + t] = o[t] == MISSING32 ? ~0ull : (unsigned long long)((long long)o[t] + p.index_offset);
+          }
+        }
+        return;
+      }
       uint32_t* o = q[nvalid++];
       if (swap) { o[0] = d; o[1] = c; o[2] = b; o[3] = a; } else { o[0] = a; o[1] = b; o[2] = c; o[3] = d; }
     };
     const bool have_below = (z - 1) >= 0;  // a true slice z-1 exists in the grid
     if (s100 != s000 && y > 0 && label > 0)
       emit(have_below ? rank_of(p, x, y - 1, z - 1) : MISSING32, have_below ? rank_of(p, x, y, z - 1) : MISSING32,
-           self, rank_of(p, x, y - 1, z), s100);
+           self, rank_of(p, x, y - 1, z), s100, 0u);
     if (s010 != s000 && x > 0 && label > 0)
       emit(have_below ? rank_of(p, x - 1, y, z - 1) : MISSING32, have_below ? rank_of(p, x, y, z - 1) : MISSING32,
-           self, rank_of(p, x - 1, y, z), !s010);
+           self, rank_of(p, x - 1, y, z), !s010, 1u);
     if (s001 != s000 && x > 0 && y > 0)
-      emit(rank_of(p, x - 1, y - 1, z), rank_of(p, x, y - 1, z), self, rank_of(p, x - 1, y, z), s001);
+      emit(rank_of(p, x - 1, y - 1, z), rank_of(p, x, y - 1, z), self, rank_of(p, x - 1, y, z), s001, 2u);
   }
   unsigned total = 0;
   const unsigned local = s2m_block_exclusive_scan(nvalid, s_scan, &total);
@@ -391,6 +407,7 @@ extern "C" int s2m_launch_k4b(const S2mK4bArgs* a, cudaStream_t stream) {
   p.words_x = a->words_x; p.res_y = a->res_y; p.z_first = a->z_first; p.label_add = a->label_add;
   p.index_offset = a->index_offset; p.quads = a->quads; p.status = a->status; p.ticket = a->ticket;
   p.n_quads = a->n_quads; p.n_invalid = a->n_invalid;
+  p.invalid_records = a->invalid_records; p.invalid_cursor = a->invalid_cursor; p.invalid_capacity = a->invalid_capacity;
   k4_quads<<<tiles, 256, 0, stream>>>(p);
   return (int)cudaGetLastError();
 }

@@ -49,6 +49,9 @@ typedef struct S2mK4bArgs {
   unsigned* ticket;               /* zeroed */
   unsigned long long* n_quads;    /* out: quad_base + quads of this launch */
   unsigned long long* n_invalid;  /* accumulates */
+  unsigned long long* invalid_records; /* optional: 6 u64 per invalid quad (key, edge, q0..q3), unordered */
+  unsigned long long* invalid_cursor;  /* optional: record counter (accumulates) */
+  unsigned long long invalid_capacity;
 } S2mK4bArgs;
 
 int s2m_launch_publish(const unsigned long long* src, unsigned long long* dst_host, unsigned n, cudaStream_t stream); /* n <= 32 */

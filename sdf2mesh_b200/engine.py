@@ -119,6 +119,7 @@ class MeshData:
     nibbles: np.ndarray
     quads: np.ndarray
     candidates: np.ndarray
+    invalid_records: np.ndarray  # (n, 6) u64: key, edge, q0..q3 (UINT64_MAX = missing); needs MESH_KEEP_INVALID
     n_invalid_quads: int
     n_halo_vertices: int
     n_candidates: int
@@ -148,6 +149,7 @@ class MeshResult:
             _view(i.cell_keys, nv, np.uint64), _view(i.sign_nibbles, nv, np.uint8),
             _view(i.quads, nq * 4, np.uint64, (-1, 4)),
             _view(i.candidates, i.n_candidates if i.candidates else 0, np.uint64),
+            _view(i.invalid_records, i.n_invalid_records * 6 if i.invalid_records else 0, np.uint64, (-1, 6)),
             i.n_invalid_quads, i.n_halo_vertices, i.n_candidates, t)
 
     def write_mesh(self, path):

@@ -261,3 +261,18 @@ def test_4096_cubed_properties(ctx):
     d = r.data()
     assert (len(d.keys), len(d.quads), d.n_invalid_quads) == counts
     r.free()
+
+
+@pytest.mark.parametrize("name,res,bounds", [("torus", 64, 1.0), ("mandelbulb", 256, 3.0)])
+def test_invalid_quad_records(ctx, name, res, bounds):
+    """f4: which quads the reference would report as invalid (mesh.rs:270-278), in its order"""
+    p, _ = s2m.params_from_cli(res, bounds, flags=s2m.MESH_KEEP_INVALID)
+    r = s2m.mesh_run(ctx, module_for(ctx, name), p)
+    o = oracle.mesh_run(name, res, bounds)
+    d = r.data()
+    want = o.invalid_records()
+    assert d.n_invalid_quads == o.n_invalid_quads == len(want) and len(want) > 0
+    assert np.array_equal(d.invalid_records, want)
+    assert_same(d, o, f"{name} with invalid quads")
+    r.free()
+    o.free()
