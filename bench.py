@@ -204,12 +204,23 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    phase = [0.0, 0.0, 0.0]  # this rank's begin / all-gather wait / finish, ms
+
     def step():
         if world == 1:
             r = s2m.mesh_run(ctx, module, params)  # one slab: quads are emitted and copied chunk by chunk
             counts = [r.info().n_vertices]
         else:
-            r, base, counts = dist_util.mesh_slab(ctx, module, params, zb, ze, rank=rank, device=dev)
+            # same sequence as distributed.mesh_slab, with the three phases timed on this rank
+            params.z_begin, params.z_end = zb, ze
+            t0 = time.perf_counter()
+            r = s2m.mesh_begin(ctx, module, params)
+            t1 = time.perf_counter()
+            counts = dist_util.allgather_counts(r.info().n_vertices, dev)
+            t2 = time.perf_counter()
+            r.finish(dist_util.exclusive_bases(counts)[rank])
+            t3 = time.perf_counter()
+            phase[0] += (t1 - t0) * 1e3; phase[1] += (t2 - t1) * 1e3; phase[2] += (t3 - t2) * 1e3
         i = r.info()
         out = (i.n_vertices, i.n_quads, i.n_invalid_quads, {k[0]: getattr(i.timings, k[0]) for k in s2m._capi.Timings._fields_}, sum(counts), i.n_candidates)
         r.free()
@@ -222,6 +233,7 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    phase[:] = [0.0, 0.0, 0.0]
     t_start = time.perf_counter()
     stats = []
     for _ in range(args.steps):
@@ -240,7 +252,13 @@ def main():
     ncand = stats[-1][5]
     d2h_bytes = nv * 33 + nq * 32
     per = {k: sum(s[3][k] for s in stats) / args.steps for k in ("k1_slab_ms", "k2_classify_ms", "k3_compact_ms", "k4_vertices_ms", "k4_quads_ms", "d2h_ms")}
+    per_rank = None
     if world > 1:
+        mine = {"rank": rank, "slices": [zb, ze], "wall_ms_per_step": 1000.0 * wall / args.steps, "device_ms": dev_ms / args.steps,
+                "vertices": int(nv), "candidates": int(ncand), "begin_ms": round(phase[0] / args.steps, 3),
+                "allgather_wait_ms": round(phase[1] / args.steps, 3), "finish_ms": round(phase[2] / args.steps, 3), **{k: round(v, 3) for k, v in per.items()}}
+        per_rank = [None] * world
+        torch.distributed.all_gather_object(per_rank, mine)
         t = torch.tensor([wall, dev_ms, tot_ms, float(nv), float(nq), float(ninv), float(launches), float(d2h_bytes), float(ncand)] + [per[k] for k in sorted(per)],
                          dtype=torch.float64, device=dev)
         mx = t.clone(); torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
@@ -277,6 +295,7 @@ def main():
         "mesh": {"candidates": ncand, "vertices": nv, "quads": nq, "invalid_quads": ninv, "triangles": 2 * nq, "Mtriangles_per_s": 2 * nq * args.steps / wall / 1e6},
         "e2e": {"value": e2e, "unit": "Gvoxel/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": launches,
+        "per_rank": per_rank,
         "clocks": clocks,
         "jit_ms": jit_ms,
         "roofline": {"kernel": "s2m_k1_slab", "bound": "hbm", "achieved": k1_bytes / k1_s / 1e9 if k1_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
