@@ -44,6 +44,7 @@ void usage(FILE* f) {
       "  -i, --sdf <SDF>                      Input SDF file\n"
       "      --shadertoy-id <SHADERTOY_ID>    Input ShaderToy shader ID\n"
       "      --shadertoy-sdf <SHADERTOY_SDF>  ShaderToy SDF name [default: sdf]\n"
+      "      --shadertoy-file <FILE>          ShaderToy image-pass code saved to a file (offline stand-in for --shadertoy-id)\n"
       "      --glsl <GLSL>                    Input GLSL fragment shader\n"
       "      --glsl-sdf <GLSL_SDF>            GLSL SDF name [default: sdf]\n"
       "  -0, --mesh <MESH>                    Output mesh file (supports STL and PLY output)\n"
@@ -64,7 +65,7 @@ void usage(FILE* f) {
 }
 
 struct Args {
-  std::string sdf, shadertoy_id, shadertoy_sdf = "sdf", glsl, glsl_sdf = "sdf", mesh, debug_wgsl, debug_png, debug_cuda;
+  std::string sdf, shadertoy_id, shadertoy_file, shadertoy_sdf = "sdf", glsl, glsl_sdf = "sdf", mesh, debug_wgsl, debug_png, debug_cuda;
   unsigned resolution = 0;
   float bounds = 0.0f;
   int device = 0;
@@ -97,6 +98,7 @@ int main(int argc, char** argv) {
     if (take_value(argc, argv, i, "sdf", "-i", &a.sdf)) continue;
     if (take_value(argc, argv, i, "shadertoy-id", nullptr, &a.shadertoy_id)) continue;
     if (take_value(argc, argv, i, "shadertoy-sdf", nullptr, &a.shadertoy_sdf)) continue;
+    if (take_value(argc, argv, i, "shadertoy-file", nullptr, &a.shadertoy_file)) continue;
     if (take_value(argc, argv, i, "glsl", nullptr, &a.glsl)) continue;
     if (take_value(argc, argv, i, "glsl-sdf", nullptr, &a.glsl_sdf)) continue;
     if (take_value(argc, argv, i, "mesh", "-0", &a.mesh)) { have_mesh = true; continue; }
@@ -151,6 +153,16 @@ int main(int argc, char** argv) {
     info("Reading SDF from ShaderToy (shader ID " + a.shadertoy_id + ")");
     error("the ShaderToy REST fetch is not part of this build (no network access); save the shader as a .frag file and use --glsl");
     return 101;
+  } else if (!a.shadertoy_file.empty()) {
+    info("Reading SDF from ShaderToy code in " + a.shadertoy_file + "...");
+    FILE* f = fopen(a.shadertoy_file.c_str(), "rb");
+    if (!f) { error("cannot open " + a.shadertoy_file); return 101; }
+    std::string code;
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) code.append(buf, n);
+    fclose(f);
+    if (s2m_shader_from_shadertoy_source(code.data(), code.size(), a.shadertoy_sdf.c_str(), &shader)) die("cannot convert ShaderToy shader");
   } else if (!a.sdf.empty()) {
     info("Reading SDF from " + a.sdf + "...");
     if (s2m_shader_from_path(a.sdf.c_str(), &shader)) die("cannot read SDF");

@@ -63,6 +63,11 @@ int s2m_shader_from_glsl_fragment_shader(const char* path, const char* sdf_name,
  * (NULL = current working directory, as the reference does). */
 int s2m_shader_from_source(const char* text, size_t len, int kind, const char* sdf_name,
                            const char* include_dir, s2m_shader** out);
+/* Sdf3DShader::from_shadertoy_api (shader.rs:110-144) without the REST fetch (no network here):
+ * `code` is the GLSL of the shader's image pass as ShaderToy serves it (mainImage + helpers); it is
+ * wrapped with the ShaderToy uniform block and an empty main() (shadertoy.rs:141-167), converted,
+ * and main_1 / main / mainImage are removed.  Same errors as the GLSL constructor. */
+int s2m_shader_from_shadertoy_source(const char* code, size_t len, const char* sdf_name, s2m_shader** out);
 /* Sdf3DShader::add_to_source (shader.rs:155) */
 int s2m_shader_add_to_source(s2m_shader* s, const char* text);
 /* the `source` field: assembled WGSL (for GLSL input: WGSL regenerated from the IR) */

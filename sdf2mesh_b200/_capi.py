@@ -82,6 +82,7 @@ SYMBOLS = {
     "s2m_shader_from_path": (ctypes.c_int, [_S, _PP]),
     "s2m_shader_from_glsl_fragment_shader": (ctypes.c_int, [_S, _S, _PP]),
     "s2m_shader_from_source": (ctypes.c_int, [_S, ctypes.c_size_t, ctypes.c_int, _S, _S, _PP]),
+    "s2m_shader_from_shadertoy_source": (ctypes.c_int, [_S, ctypes.c_size_t, _S, _PP]),
     "s2m_shader_add_to_source": (ctypes.c_int, [_P, _S]),
     "s2m_shader_source": (_S, [_P]),
     "s2m_shader_write_to_file": (ctypes.c_int, [_P, _S]),

@@ -10,6 +10,7 @@ namespace {
 class GlslParser : public ParserBase {
  public:
   explicit GlslParser(Module* m) : ParserBase(Lang::Glsl, m) {}
+  std::map<std::string, std::vector<Function*>> overloads_;
 
   void parse(const std::string& src) {
     LexOptions lo;
@@ -136,20 +137,27 @@ class GlslParser : public ParserBase {
       if (!accept(",")) break;
     }
     expect(")");
+    // GLSL allows overloading: functions with the same name are distinguished by parameter types.
+    // The first keeps its name, later ones are emitted as name_1, name_2, ... (like naga).
     Function* fn = nullptr;
-    auto it = functions.find(name);
-    if (it != functions.end()) {
-      fn = it->second;
-      bool same = fn->params.size() == params.size() && fn->ret == ret;
-      for (size_t i = 0; same && i < params.size(); ++i) same = fn->params[i]->ty == params[i]->ty && fn->params[i]->by_ref == params[i]->by_ref;
-      if (!same) b.unsupported("overloaded function '" + name + "'");
+    std::vector<Function*>& set = overloads_[name];
+    for (Function* f : set) {
+      bool same = f->params.size() == params.size();
+      for (size_t i = 0; same && i < params.size(); ++i) same = f->params[i]->ty == params[i]->ty && f->params[i]->by_ref == params[i]->by_ref;
+      if (same) { fn = f; break; }
+    }
+    if (fn) {
+      if (fn->ret != ret) b.error("function '" + name + "' redeclared with a different return type");
       if (fn->body && is_punct("{")) b.error("redefinition of function '" + name + "'");
     } else {
-      if (lookup(name) && scopes.size() == 1 && scopes[0].count(name)) b.error("'" + name + "' redeclared as a function");
+      if (scopes[0].count(name)) b.error("'" + name + "' redeclared as a function");
       mod->functions.emplace_back(new Function());
       fn = mod->functions.back().get();
-      fn->name = name; fn->ret = ret; fn->line = peek().line;
-      functions[name] = fn;
+      fn->name = name;
+      for (int k = 1; functions.count(fn->name) || scopes[0].count(fn->name); ++k) fn->name = name + "_" + std::to_string(k);
+      fn->ret = ret; fn->line = peek().line;
+      functions[fn->name] = fn;
+      set.push_back(fn);
     }
     if (accept(";")) { if (fn->params.empty()) fn->params = params; return; }  // prototype
     fn->params = params;
@@ -476,10 +484,29 @@ class GlslParser : public ParserBase {
       // a local variable cannot be called; functions and builtins share one namespace
       advance();
       std::vector<ExprP> args = parse_args();
-      auto it = functions.find(name);
-      if (it != functions.end()) {
-        if (it->second->is_entry) b.error("main() cannot be called");
-        return b.call_user(it->second, args);
+      auto ov = overloads_.find(name);
+      if (ov != overloads_.end() && !ov->second.empty()) {
+        Function* best = nullptr;
+        int best_score = -1;
+        for (Function* f : ov->second) {
+          if (f->params.size() != args.size()) continue;
+          int score = 0;
+          bool ok = true;
+          for (size_t i = 0; ok && i < args.size(); ++i) {
+            const Type& pt = f->params[i]->ty;
+            const Type& at = args[i]->ty;
+            if (pt == at) score += 2;
+            else if (!f->params[i]->by_ref && pt.k == at.k && pt.n == at.n && pt.sk == Sk::F32 && at.is_int()) score += 1;  // int -> float
+            else ok = false;
+          }
+          if (ok && score > best_score) { best = f; best_score = score; }
+        }
+        if (!best) {
+          if (ov->second.size() == 1) best = ov->second[0];  // let call_user report the precise mismatch
+          else b.error("no overload of '" + name + "' matches the argument types");
+        }
+        if (best->is_entry) b.error("main() cannot be called");
+        return b.call_user(best, args);
       }
       if (name == "texture" || name == "texelFetch" || name == "textureLod") b.unsupported("texture sampling (" + name + ")");
       ExprP e = b.call_builtin(name, args);

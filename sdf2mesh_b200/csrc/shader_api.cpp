@@ -253,7 +253,51 @@ int build_from_glsl(const std::string& glsl, const std::string& sdf, s2m_shader*
   return S2M_OK;
 }
 
+// Shader::default_uniform_block (shadertoy.rs:141-152): the ShaderToy inputs, all read as zero
+const char* kShaderToyUniforms =
+    "layout(binding=0) uniform vec3 iResolution;\n"
+    "layout(binding=0) uniform float iTime;\n"
+    "layout(binding=0) uniform float iTimeDelta;\n"
+    "layout(binding=0) uniform int iFrame;\n"
+    "layout(binding=0) uniform vec4 iChannelTime;\n"
+    "layout(binding=0) uniform vec4 iMouse;\n"
+    "layout(binding=0) uniform vec4 iDate;\n"
+    "layout(binding=0) uniform float iSampleRate;\n";
+
+// Sdf3DShader::from_shadertoy_api (shader.rs:110-144) minus the REST fetch: `code` is the text of
+// the shader's last render pass (shadertoy.rs:154-167 generate_wgsl_shader_code wraps it).
+int build_from_shadertoy(const std::string& code, const std::string& sdf, s2m_shader** out) {
+  const std::string glsl = std::string("#version 450 core\n") + kShaderToyUniforms + code + "\n void main() {}";
+  std::string wgsl, err;
+  int st = s2m_frontend::glsl_to_wgsl(glsl, &wgsl, &err);
+  if (st) return fail(st, err);
+  if ((st = remove_function(wgsl, "fn main_1(", &wgsl, &err))) return fail(st, err);
+  if ((st = remove_function(wgsl, "fn main(", &wgsl, &err))) return fail(st, err);
+  if ((st = remove_function(wgsl, "fn mainImage(", &wgsl, &err))) return fail(st, err);  // shader.rs:123
+  wgsl = remove_line(wgsl, "@fragment");
+  if (has_function(wgsl, sdf)) {
+    if (!has_function(wgsl, "sdf3d")) wgsl += "fn sdf3d(p: vec3<f32>) -> f32 { return " + sdf + "(p); }\n";
+  } else {
+    return fail(S2M_ERR_MISSING_SDF, "Missing SDF function `" + sdf + "` in shader");
+  }
+  wgsl += kModNormal; wgsl += "\n";  // shader.rs:139
+  s2m_shader* sh = new s2m_shader();
+  sh->kind = S2M_SRC_WGSL;
+  sh->source = wgsl;
+  sh->sdf_name = sdf;
+  sh->glsl = glsl;
+  sh->builtin_functions.push_back("sdf3d_normal");
+  *out = sh;
+  return S2M_OK;
+}
+
 }  // namespace
+
+extern "C" int s2m_shader_from_shadertoy_source(const char* code, size_t len, const char* sdf_name, s2m_shader** out) {
+  if (!code || !out) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
+  *out = nullptr;
+  return build_from_shadertoy(std::string(code, len), sdf_name && *sdf_name ? sdf_name : "sdf", out);
+}
 
 extern "C" int s2m_shader_from_path(const char* path, s2m_shader** out) {
   if (!path || !out) return fail(S2M_ERR_INVALID_ARG, "NULL argument");

@@ -87,6 +87,14 @@ class Sdf3DShader:
                                            None if include_dir is None else str(include_dir).encode(), ctypes.byref(h)))
         return cls(h)
 
+    @classmethod
+    def from_shadertoy_source(cls, code: str, sdf: str = "sdf") -> "Sdf3DShader":
+        """shader.rs:110 from_shadertoy_api without the network fetch: `code` is the image-pass GLSL."""
+        h = ctypes.c_void_p()
+        raw = code.encode()
+        check(lib().s2m_shader_from_shadertoy_source(raw, len(raw), sdf.encode(), ctypes.byref(h)))
+        return cls(h)
+
     # --- reference API ------------------------------------------------------------------
     def add_to_source(self, source: str) -> None:
         check(lib().s2m_shader_add_to_source(self._h, source.encode()))

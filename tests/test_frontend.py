@@ -411,3 +411,55 @@ def test_matrices(built, tmp_path):
     v = run_wgsl(wgsl, [[1.0, 2.0, 0.0]])[0]
     # m*n columns: m*(1,2) = (-2,1), m*(3,4) = (-4,3);  (m*n)*(1,2) = (-2-8, 1+6) = (-10, 7);  (p.xy*m).y = dot((1,2),(-1,0)) = -1
     assert v == np.float32(-10.0 + 4.0 - 1.0)
+
+
+SHADERTOY_CODE = """
+// a typical ShaderToy image pass: helpers, overloads, uniforms, mainImage
+#define PI 3.14159265
+float hash(float n) { return fract(sin(n) * 43758.5453); }
+float hash(vec2 p) { return hash(p.x + p.y * 57.0); }
+mat2 rot(float a) { float c = cos(a), s = sin(a); return mat2(c, -s, s, c); }
+float map(vec3 p) {
+    p.xz *= rot(0.4 + iTime);
+    vec3 q = abs(p) - vec3(0.6, 0.4, 0.5);
+    float box = length(max(q, 0.0)) + min(max(q.x, max(q.y, q.z)), 0.0);
+    return min(box, length(p - vec3(0.0, 0.7, 0.0)) - 0.35) + 0.0 * hash(p.xy) + 0.0 * hash(1.0);
+}
+void mainImage(out vec4 fragColor, in vec2 fragCoord) {
+    vec2 uv = fragCoord / iResolution.xy;
+    fragColor = vec4(uv, 0.5 + 0.5 * sin(iTime), 1.0);
+}
+"""
+
+
+def test_shadertoy_source_path(built):
+    """from_shadertoy_api minus the network: uniform block, mainImage removal, --shadertoy-sdf name"""
+    sh = s2m.Sdf3DShader.from_shadertoy_source(SHADERTOY_CODE, "map")
+    src = sh.source
+    assert "fn mainImage(" not in src and "fn main(" not in src and "@fragment" not in src
+    assert "fn hash(" in src and "fn hash_1(" in src, "GLSL overloads get distinct WGSL names"
+    assert "fn sdf3d(p: vec3<f32>) -> f32 { return map(p); }" in src and "fn sdf3d_normal(" in src
+    pts = points(3.0, 2000)
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+
+    def ref(p):
+        F = np.float32
+        a = F(0.4)
+        c, s_ = F(np.cos(a)), F(np.sin(a))
+        x = F(F(p[0] * c) + F(p[2] * F(-s_)))   # p.xz * mat2(c,-s,s,c): (dot(p.xz,(c,-s)), dot(p.xz,(s,c)))
+        z = F(F(p[0] * s_) + F(p[2] * c))
+        q = np.array([abs(x) - F(0.6), abs(p[1]) - F(0.4), abs(z) - F(0.5)], F)
+        m = np.maximum(q, F(0))
+        box = F(F(np.sqrt(F(F(F(m[0] * m[0]) + F(m[1] * m[1])) + F(m[2] * m[2])))) + min(max(q[0], max(q[1], q[2])), F(0)))
+        d = np.array([x, p[1] - F(0.7), z], F)
+        sph = F(F(np.sqrt(F(F(F(d[0] * d[0]) + F(d[1] * d[1])) + F(d[2] * d[2])))) - F(0.35))
+        return min(box, sph)
+
+    want = np.array([ref(p) for p in pts], np.float32)
+    assert np.allclose(got, want, rtol=3e-6, atol=3e-6)
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_shadertoy_source(SHADERTOY_CODE, "sdf")
+    assert e.value.kind == "MISSING_SDF"
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_shadertoy_source("float map(vec3 p) { return p.x; }", "map")  # no mainImage
+    assert e.value.kind == "SHADER" and "mainImage" in str(e.value)
