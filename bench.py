@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--cpu-baseline-slices", type=int, default=192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-balance", action="store_true", help="equal-thickness z-slabs instead of cost-balanced")
+    ap.add_argument("--no-rebalance", action="store_true", help="keep the cost-probe partition; do not refine it from warm-up step times")
     ap.add_argument("--flags", type=int, default=0, help="extra S2M_MESH_* flags")
     ap.add_argument("--slab-budget-gb", type=float, default=0.0, help="bytes of corner slab resident at once (0 = engine default, 4 GiB chunks)")
     args = ap.parse_args()
@@ -230,8 +231,16 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.5)
-    for _ in range(args.warmup):
+    for w in range(args.warmup):
         step()
+        if world > 1 and not args.no_balance and not args.no_rebalance and w < args.warmup - 1:
+            # refine the partition from what every rank's begin()+finish() took in this warm-up step
+            own = torch.tensor([phase[0] + phase[2]], dtype=torch.float64, device=dev)
+            allt = torch.zeros(world, dtype=torch.float64, device=dev)
+            torch.distributed.all_gather_into_tensor(allt, own)
+            bounds_z = dist_util.rebalance(bounds_z, allt.tolist())
+            zb, ze = bounds_z[rank], bounds_z[rank + 1]
+        phase[:] = [0.0, 0.0, 0.0]
     barrier()
     phase[:] = [0.0, 0.0, 0.0]
     t_start = time.perf_counter()
@@ -290,7 +299,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (analytic SDF, no random inputs)",
         "config": {"workload": wl, "sdf": f, "resolution": res, "bounds": bounds, "mode": "faithful (slices 0..R-2)" if not (args.flags & 1) else "all slices",
-                   "parallelism": f"z-slabs x{world}" + ("" if world == 1 else (" equal" if args.no_balance else " cost-balanced")), "z_boundaries": bounds_z,
+                   "parallelism": f"z-slabs x{world}" + ("" if world == 1 else (" equal" if args.no_balance else (" cost-probe" if args.no_rebalance else " cost-probe + refined from warm-up step times"))), "z_boundaries": bounds_z,
                    "l2": "no L2 flush needed: the corner slab alone is %.1f GB per step, far larger than the 126 MB L2" % (k1_bytes / 1e9)},
         "mesh": {"candidates": ncand, "vertices": nv, "quads": nq, "invalid_quads": ninv, "triangles": 2 * nq, "Mtriangles_per_s": 2 * nq * args.steps / wall / 1e6},
         "e2e": {"value": e2e, "unit": "Gvoxel/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": d2h_bytes},

@@ -49,16 +49,52 @@ def exclusive_bases(counts: Sequence[int]) -> List[int]:
     return out
 
 
+_GATHER_BUF = {}
+
+
 def allgather_counts(local_count: int, device=None) -> List[int]:
-    """one all-gather of a single int64 per rank over torch.distributed (nccl or gloo)"""
+    """one all-gather of a single int64 per rank over torch.distributed (nccl or gloo).
+
+    One collective into one tensor and one device->host read (a per-rank `.item()` costs a device
+    synchronisation each: 8 of them took 2 ms of a 12 ms step on 8 GPUs)."""
     import torch
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         return [int(local_count)]
-    t = torch.tensor([int(local_count)], dtype=torch.int64, device=device if device is not None else "cpu")
-    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
-    dist.all_gather(out, t)
-    return [int(x.item()) for x in out]
+    world = dist.get_world_size()
+    dev = device if device is not None else "cpu"
+    key = (str(dev), world)
+    if key not in _GATHER_BUF:
+        _GATHER_BUF[key] = (torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(world, dtype=torch.int64, device=dev))
+    src, dst = _GATHER_BUF[key]
+    src.fill_(int(local_count))
+    dist.all_gather_into_tensor(dst, src)
+    return [int(x) for x in dst.tolist()]
+
+
+def rebalance(bounds: Sequence[int], seconds: Sequence[float], damping: float = 1.0) -> List[int]:
+    """Refine z-slab boundaries from the time every rank actually took for its slab.
+
+    Model: inside rank g's current slab the cost per slice is constant (= seconds[g] / slices[g]).
+    The new boundaries cut the resulting piecewise-linear cumulative cost into equal parts.  Used
+    when the same SDF is meshed repeatedly (animation frames, bench warm-up steps): the coarse
+    `cost_probe` only sees SDF evaluation cost, not the vertex / quad work that follows it.
+    """
+    world = len(bounds) - 1
+    n = bounds[-1]
+    widths = np.diff(np.asarray(bounds, np.float64))
+    sec = np.asarray(seconds, np.float64)
+    if world < 2 or not np.all(np.isfinite(sec)) or sec.sum() <= 0 or np.any(widths <= 0):
+        return list(bounds)
+    cum = np.concatenate([[0.0], np.cumsum(sec)])
+    targets = cum[-1] * np.arange(world + 1) / world
+    nb = np.interp(targets, cum, np.asarray(bounds, np.float64))
+    nb = np.asarray(bounds, np.float64) + damping * (nb - np.asarray(bounds, np.float64))
+    out = [int(round(x)) for x in nb]
+    out[0], out[-1] = 0, n
+    for i in range(1, world + 1):
+        out[i] = min(max(out[i], out[i - 1] + 1), n - (world - i))
+    return out
 
 
 def broadcast_boundaries(bounds: Optional[List[int]], world: int, device=None) -> List[int]:

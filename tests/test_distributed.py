@@ -62,3 +62,18 @@ def test_count_exchange_gloo_world2():
         assert p.exitcode == 0
     assert out[0] == (0, [1007, 2007], 0, [0, 300, 511])
     assert out[1] == (1, [1007, 2007], 1007, [0, 300, 511])
+
+
+def test_rebalance_from_measured_times():
+    b = [0, 406, 678, 864, 1023, 1183, 1368, 1640, 2047]
+    t = [6.75, 8.3, 10.7, 10.3, 10.45, 10.1, 7.9, 6.8]
+    nb = D.rebalance(b, t)
+    assert nb[0] == 0 and nb[-1] == 2047 and all(x < y for x, y in zip(nb, nb[1:]))
+    rate = np.array(t) / np.diff(b)
+    pred = []
+    for g in range(8):
+        z = np.arange(nb[g], nb[g + 1])
+        pred.append(rate[np.searchsorted(b, z, side="right") - 1].sum())
+    assert max(pred) / min(pred) < 1.02 and max(pred) < max(t) * 0.9
+    assert D.rebalance([0, 10], [1.0]) == [0, 10]
+    assert D.rebalance(b, [0.0] * 8) == b
