@@ -11,7 +11,7 @@
 namespace s2m_frontend {
 
 struct Token {
-  enum K { End, Ident, Int, Float, Punct } k = End;
+  enum K { End, Ident, Int, Float, Punct, Directive } k = End;  // Directive: a GLSL '#...' line (text = the line)
   std::string text;     // identifier / punctuation / literal spelling
   double fval = 0;
   int64_t ival = 0;
@@ -40,10 +40,8 @@ class Lexer {
       raw.push_back(t);
       if (t.k == Token::End) break;
     }
-    if (!opt_.glsl || macros_.empty()) return raw;
-    std::vector<Token> out;
-    expand(raw, out, 0);
-    return out;
+    if (!opt_.glsl) return raw;
+    return preprocess(raw);
   }
 
  private:
@@ -80,52 +78,171 @@ class Lexer {
         } while (depth > 0);
         continue;
       }
-      if (opt_.glsl && peek() == '#' && at_line_start_) { directive(); continue; }
       break;
     }
   }
-  // handles #define (object- and function-like); ignores #version/#extension/#pragma/#line/precision
-  void directive() {
-    int l = line_, c = col_;
-    std::string text;
+  // reads a '#...' line (with backslash continuations) into one Directive token
+  Token directive() {
+    Token t;
+    t.k = Token::Directive; t.line = line_; t.col = col_;
     while (i_ < s_.size() && peek() != '\n') {
-      if (peek() == '\\' && peek(1) == '\n') { adv(); adv(); text += ' '; continue; }
-      text += peek();
+      if (peek() == '\\' && peek(1) == '\n') { adv(); adv(); t.text += ' '; continue; }
+      if (peek() == '/' && peek(1) == '/') { while (i_ < s_.size() && peek() != '\n') adv(); break; }
+      t.text += peek();
       adv();
     }
+    return t;
+  }
+
+  static std::string directive_name(const std::string& text, size_t* rest) {
     size_t p = 1;
     while (p < text.size() && isspace((unsigned char)text[p])) ++p;
     size_t q = p;
     while (q < text.size() && isalpha((unsigned char)text[q])) ++q;
-    const std::string name = text.substr(p, q - p);
-    if (name == "define") {
-      while (q < text.size() && isspace((unsigned char)text[q])) ++q;
-      size_t r = q;
-      while (r < text.size() && (isalnum((unsigned char)text[r]) || text[r] == '_')) ++r;
-      const std::string mname = text.substr(q, r - q);
-      if (mname.empty()) err("#define without a name", l, c);
-      Macro m;
-      if (r < text.size() && text[r] == '(') {
-        m.function_like = true;
-        ++r;
-        std::string cur;
-        for (; r < text.size() && text[r] != ')'; ++r) {
-          if (text[r] == ',') { m.params.push_back(cur); cur.clear(); }
-          else if (!isspace((unsigned char)text[r])) cur += text[r];
-        }
-        if (!cur.empty()) m.params.push_back(cur);
-        if (r < text.size()) ++r;
+    *rest = q;
+    return text.substr(p, q - p);
+  }
+
+  void define_macro(const Token& d, size_t q) {
+    const std::string& text = d.text;
+    while (q < text.size() && isspace((unsigned char)text[q])) ++q;
+    size_t r = q;
+    while (r < text.size() && (isalnum((unsigned char)text[r]) || text[r] == '_')) ++r;
+    const std::string mname = text.substr(q, r - q);
+    if (mname.empty()) err("#define without a name", d.line, d.col);
+    Macro m;
+    if (r < text.size() && text[r] == '(') {
+      m.function_like = true;
+      ++r;
+      std::string cur;
+      for (; r < text.size() && text[r] != ')'; ++r) {
+        if (text[r] == ',') { m.params.push_back(cur); cur.clear(); }
+        else if (!isspace((unsigned char)text[r])) cur += text[r];
       }
-      const std::string body = text.substr(r);
-      LexOptions o; o.glsl = false;
-      Lexer sub(body, o);
-      for (;;) { Token t = sub.next(); if (t.k == Token::End) break; t.line = l; t.col = c; m.body.push_back(t); }
-      macros_[mname] = m;
-    } else if (name == "if" || name == "ifdef" || name == "ifndef" || name == "else" || name == "elif" || name == "endif" ||
-               name == "undef" || name == "include") {
-      err("GLSL preprocessor directive #" + name + " is not supported", l, c);
+      if (!cur.empty()) m.params.push_back(cur);
+      if (r < text.size()) ++r;
     }
-    // #version, #extension, #pragma, #line: ignored
+    for (Token& t : lex_fragment(text.substr(r), d)) m.body.push_back(t);
+    macros_[mname] = m;
+  }
+
+  std::vector<Token> lex_fragment(const std::string& body, const Token& at) {
+    LexOptions o; o.glsl = false;
+    Lexer sub(body, o);
+    std::vector<Token> out;
+    for (;;) { Token t = sub.next(); if (t.k == Token::End) break; t.line = at.line; t.col = at.col; out.push_back(t); }
+    return out;
+  }
+
+  // ---- #if expression: integers, defined(X), ! - + * / % < > <= >= == != && || and parentheses
+  struct IfEval {
+    const std::vector<Token>& t;
+    size_t i = 0;
+    Lexer* lx;
+    const Token& at;
+    bool is(const char* p) const { return i < t.size() && t[i].k == Token::Punct && t[i].text == p; }
+    long long primary() {
+      if (i >= t.size()) lx->err("malformed #if expression", at.line, at.col);
+      if (is("(")) { ++i; long long v = lor(); if (!is(")")) lx->err("expected ')' in #if", at.line, at.col); ++i; return v; }
+      if (is("!")) { ++i; return !primary(); }
+      if (is("-")) { ++i; return -primary(); }
+      if (is("+")) { ++i; return primary(); }
+      const Token& k = t[i++];
+      if (k.k == Token::Int) return k.ival;
+      if (k.k == Token::Float) return (long long)k.fval;
+      if (k.k == Token::Ident) return 0;  // unknown identifiers evaluate to 0, as in cpp
+      lx->err("unexpected token '" + k.text + "' in #if", at.line, at.col);
+    }
+    long long mul() { long long v = primary(); while (is("*") || is("/") || is("%")) { const char o = t[i++].text[0]; long long r = primary(); v = o == '*' ? v * r : (r == 0 ? 0 : (o == '/' ? v / r : v % r)); } return v; }
+    long long add() { long long v = mul(); while (is("+") || is("-")) { const char o = t[i++].text[0]; long long r = mul(); v = o == '+' ? v + r : v - r; } return v; }
+    long long rel() { long long v = add(); while (is("<") || is(">") || is("<=") || is(">=")) { const std::string o = t[i++].text; long long r = add(); v = o == "<" ? v < r : o == ">" ? v > r : o == "<=" ? v <= r : v >= r; } return v; }
+    long long eq() { long long v = rel(); while (is("==") || is("!=")) { const bool e = t[i++].text == "=="; long long r = rel(); v = e ? v == r : v != r; } return v; }
+    long long land() { long long v = eq(); while (is("&&")) { ++i; long long r = eq(); v = v && r; } return v; }
+    long long lor() { long long v = land(); while (is("||")) { ++i; long long r = land(); v = v || r; } return v; }
+  };
+  bool eval_if(const Token& d, size_t q) {
+    std::vector<Token> toks = lex_fragment(d.text.substr(q), d);
+    // defined(X) / defined X  before macro expansion
+    std::vector<Token> pre;
+    for (size_t k = 0; k < toks.size(); ++k) {
+      if (toks[k].k == Token::Ident && toks[k].text == "defined") {
+        size_t j = k + 1;
+        const bool paren = j < toks.size() && toks[j].text == "(";
+        if (paren) ++j;
+        if (j >= toks.size() || toks[j].k != Token::Ident) err("malformed defined()", d.line, d.col);
+        Token v; v.k = Token::Int; v.ival = macros_.count(toks[j].text) ? 1 : 0; v.line = d.line; v.col = d.col;
+        pre.push_back(v);
+        k = paren ? j + 1 : j;
+        continue;
+      }
+      pre.push_back(toks[k]);
+    }
+    std::vector<Token> ex;
+    expand(pre, ex, 0);
+    IfEval ev{ex, 0, this, d};
+    const long long v = ev.lor();
+    if (ev.i != ex.size()) err("trailing tokens in #if expression", d.line, d.col);
+    return v != 0;
+  }
+
+  // Ordered pass over the raw tokens: conditionals, #define / #undef, macro expansion.
+  std::vector<Token> preprocess(const std::vector<Token>& raw) {
+    struct Cond { bool parent, taken, active; };
+    std::vector<Cond> stack;
+    std::vector<Token> out, pending;
+    auto active = [&] { return stack.empty() || stack.back().active; };
+    auto flush = [&] { if (!pending.empty()) { expand(pending, out, 0); pending.clear(); } };
+    for (const Token& t : raw) {
+      if (t.k != Token::Directive) {
+        if (t.k == Token::End) { flush(); out.push_back(t); break; }
+        if (active()) pending.push_back(t);
+        continue;
+      }
+      size_t q = 0;
+      const std::string name = directive_name(t.text, &q);
+      if (name == "ifdef" || name == "ifndef" || name == "if") {
+        flush();
+        bool v = false;
+        if (active()) {
+          if (name == "if") v = eval_if(t, q);
+          else {
+            std::vector<Token> id = lex_fragment(t.text.substr(q), t);
+            if (id.empty() || id[0].k != Token::Ident) err("#" + name + " needs an identifier", t.line, t.col);
+            v = macros_.count(id[0].text) > 0;
+            if (name == "ifndef") v = !v;
+          }
+        }
+        const bool par = active();
+        stack.push_back({par, par && v, par && v});
+      } else if (name == "elif" || name == "else") {
+        flush();
+        if (stack.empty()) err("#" + name + " without #if", t.line, t.col);
+        Cond& c = stack.back();
+        bool v = name == "else" ? true : (c.parent && !c.taken ? eval_if(t, q) : false);
+        c.active = c.parent && !c.taken && v;
+        if (c.active) c.taken = true;
+      } else if (name == "endif") {
+        flush();
+        if (stack.empty()) err("#endif without #if", t.line, t.col);
+        stack.pop_back();
+      } else if (!active()) {
+        continue;
+      } else if (name == "define") {
+        flush();
+        define_macro(t, q);
+      } else if (name == "undef") {
+        flush();
+        std::vector<Token> id = lex_fragment(t.text.substr(q), t);
+        if (!id.empty()) macros_.erase(id[0].text);
+      } else if (name == "include") {
+        err("#include is not supported in GLSL input", t.line, t.col);
+      } else if (name == "error") {
+        err("#error" + t.text.substr(q), t.line, t.col);
+      }
+      // #version, #extension, #pragma, #line: ignored
+    }
+    if (!stack.empty()) err("unterminated #if", raw.back().line, raw.back().col);
+    return out;
   }
 
   void expand(const std::vector<Token>& in, std::vector<Token>& out, int depth) {
@@ -173,6 +290,7 @@ class Lexer {
     Token t;
     t.line = line_; t.col = col_;
     if (i_ >= s_.size()) { t.k = Token::End; return t; }
+    if (opt_.glsl && peek() == '#' && at_line_start_) return directive();
     const char c = peek();
     if (isalpha((unsigned char)c) || c == '_') {
       while (isalnum((unsigned char)peek()) || peek() == '_') { t.text += peek(); adv(); }

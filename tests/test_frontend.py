@@ -463,3 +463,39 @@ def test_shadertoy_source_path(built):
     with pytest.raises(s2m.S2mError) as e:
         s2m.Sdf3DShader.from_shadertoy_source("float map(vec3 p) { return p.x; }", "map")  # no mainImage
     assert e.value.kind == "SHADER" and "mainImage" in str(e.value)
+
+
+def test_glsl_preprocessor_conditionals(built, tmp_path):
+    glsl = textwrap.dedent("""\
+        #version 450 core
+        #define QUALITY 2
+        #define USE_SPHERE
+        #if QUALITY > 1 && defined(USE_SPHERE)
+        #define RADIUS 0.75
+        #elif QUALITY == 1
+        #define RADIUS 0.5
+        #else
+        #define RADIUS 0.25
+        #endif
+        #ifdef NOT_DEFINED
+        this is not GLSL and must be skipped
+        #endif
+        #ifndef NOT_DEFINED
+        #define OFFSET 0.125   // trailing comment
+        #endif
+        #undef QUALITY
+        #if defined QUALITY
+        #define OFFSET 100.0
+        #endif
+        float sdf(vec3 p) { return length(p) - RADIUS + OFFSET; }
+        void main() {}
+        """)
+    f = tmp_path / "pp.frag"
+    f.write_text(glsl)
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(f, "sdf")
+    v = host_eval.eval_points(sh.lower_to_cuda(), np.array([[2.0, 0.0, 0.0]], np.float32))[0]
+    assert v == np.float32(np.float32(2.0) - np.float32(0.75)) + np.float32(0.125)
+    f.write_text("#version 450 core\n#if 1\nfloat sdf(vec3 p) { return p.x; }\nvoid main() {}\n")
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_glsl_fragment_shader(f, "sdf")
+    assert e.value.kind == "PARSE" and "unterminated #if" in str(e.value)
