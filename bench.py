@@ -190,9 +190,11 @@ def main():
 
     # z-slab partition (rank 0 probes the per-band cost, everyone uses its answer)
     bounds_z = None
+    cost = None
     if world > 1:
+        if not args.no_balance:
+            cost = dist_util.broadcast_floats(s2m.cost_probe(ctx, module, params, 128) if rank == 0 else None, 128, dev)
         if rank == 0:
-            cost = None if args.no_balance else s2m.cost_probe(ctx, module, params, 128)
             bounds_z = dist_util.partition_slices(n_slices, world, cost)
         bounds_z = dist_util.broadcast_boundaries(bounds_z, world, dev)
     else:
@@ -233,12 +235,14 @@ def main():
     time.sleep(0.5)
     for w in range(args.warmup):
         step()
-        if world > 1 and not args.no_balance and not args.no_rebalance and w < args.warmup - 1:
-            # refine the partition from what every rank's begin()+finish() took in this warm-up step
+        if world > 1 and not args.no_balance and not args.no_rebalance and w == 1 and args.warmup >= 3:
+            # One refinement, from the second warm-up step (the first one pays for allocations, and
+            # the step after the refinement pays for re-allocations): what every rank's
+            # begin()+finish() took, spread inside its slab according to the probe profile.
             own = torch.tensor([phase[0] + phase[2]], dtype=torch.float64, device=dev)
             allt = torch.zeros(world, dtype=torch.float64, device=dev)
             torch.distributed.all_gather_into_tensor(allt, own)
-            bounds_z = dist_util.rebalance(bounds_z, allt.tolist())
+            bounds_z = dist_util.rebalance(bounds_z, allt.tolist(), cost)
             zb, ze = bounds_z[rank], bounds_z[rank + 1]
         phase[:] = [0.0, 0.0, 0.0]
     barrier()

@@ -72,29 +72,58 @@ def allgather_counts(local_count: int, device=None) -> List[int]:
     return [int(x) for x in dst.tolist()]
 
 
-def rebalance(bounds: Sequence[int], seconds: Sequence[float], damping: float = 1.0) -> List[int]:
+def _band_density(n_slices: int, cost: Optional[Sequence[float]]) -> np.ndarray:
+    """relative cost of every slice from a coarse band profile (uniform if there is none)"""
+    if cost is None or len(cost) == 0 or not np.isfinite(np.sum(cost)) or np.sum(cost) <= 0:
+        return np.ones(n_slices)
+    c = np.asarray(cost, np.float64)
+    c = np.maximum(c, c.max() * 1e-3)
+    centres = (np.arange(len(c)) + 0.5) * n_slices / len(c)
+    return np.interp(np.arange(n_slices) + 0.5, centres, c)
+
+
+def rebalance(bounds: Sequence[int], seconds: Sequence[float], cost: Optional[Sequence[float]] = None,
+              damping: float = 1.0) -> List[int]:
     """Refine z-slab boundaries from the time every rank actually took for its slab.
 
-    Model: inside rank g's current slab the cost per slice is constant (= seconds[g] / slices[g]).
-    The new boundaries cut the resulting piecewise-linear cumulative cost into equal parts.  Used
-    when the same SDF is meshed repeatedly (animation frames, bench warm-up steps): the coarse
-    `cost_probe` only sees SDF evaluation cost, not the vertex / quad work that follows it.
+    Model: the cost of slice z is shape(z) * corr_g for z in rank g's current slab, where shape is
+    the coarse probe profile (`cost`, uniform if None) and corr_g = seconds[g] / sum(shape over the
+    slab) absorbs what the probe cannot see (vertex and quad work, copies).  The new boundaries cut
+    the cumulative model cost into equal parts.  Meant for repeated meshing of the same SDF
+    (animation frames, bench warm-up): measure one steady-state step, refine once.
     """
     world = len(bounds) - 1
-    n = bounds[-1]
-    widths = np.diff(np.asarray(bounds, np.float64))
+    n = int(bounds[-1])
     sec = np.asarray(seconds, np.float64)
-    if world < 2 or not np.all(np.isfinite(sec)) or sec.sum() <= 0 or np.any(widths <= 0):
-        return list(bounds)
-    cum = np.concatenate([[0.0], np.cumsum(sec)])
+    widths = np.diff(np.asarray(bounds))
+    if world < 2 or not np.all(np.isfinite(sec)) or sec.sum() <= 0 or np.any(widths <= 0) or np.any(sec <= 0):
+        return [int(b) for b in bounds]
+    dens = _band_density(n, cost)
+    for g in range(world):
+        sl = slice(int(bounds[g]), int(bounds[g + 1]))
+        dens[sl] *= sec[g] / dens[sl].sum()
+    cum = np.concatenate([[0.0], np.cumsum(dens)])
     targets = cum[-1] * np.arange(world + 1) / world
-    nb = np.interp(targets, cum, np.asarray(bounds, np.float64))
+    nb = np.interp(targets, cum, np.arange(n + 1, dtype=np.float64))
     nb = np.asarray(bounds, np.float64) + damping * (nb - np.asarray(bounds, np.float64))
     out = [int(round(x)) for x in nb]
     out[0], out[-1] = 0, n
     for i in range(1, world + 1):
         out[i] = min(max(out[i], out[i - 1] + 1), n - (world - i))
     return out
+
+
+def broadcast_floats(values: Optional[Sequence[float]], count: int, device=None) -> List[float]:
+    """rank 0's `values` (length `count`) on every rank"""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return list(values)
+    t = torch.zeros(count, dtype=torch.float64, device=device if device is not None else "cpu")
+    if dist.get_rank() == 0:
+        t[:] = torch.tensor(list(values), dtype=torch.float64)
+    dist.broadcast(t, 0)
+    return t.tolist()
 
 
 def broadcast_boundaries(bounds: Optional[List[int]], world: int, device=None) -> List[int]:

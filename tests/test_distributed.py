@@ -77,3 +77,14 @@ def test_rebalance_from_measured_times():
     assert max(pred) / min(pred) < 1.02 and max(pred) < max(t) * 0.9
     assert D.rebalance([0, 10], [1.0]) == [0, 10]
     assert D.rebalance(b, [0.0] * 8) == b
+    # with a probe profile the cost inside a slab follows the profile; the fastest ranks (the outer
+    # slabs) get more slices, the slowest (middle) fewer
+    z = (np.arange(128) + 0.5) / 128 * 2 - 1
+    profile = 1.0 + 20.0 * np.exp(-(z / 0.35) ** 2)
+    b0 = D.partition_slices(2047, 8, profile)
+    t2 = [6.75, 8.3, 10.7, 10.3, 10.45, 10.1, 7.9, 6.8]
+    with_profile = D.rebalance(b0, t2, profile)
+    uniform = D.rebalance(b0, t2)
+    assert with_profile[1] > b0[1] and uniform[1] > b0[1]
+    assert with_profile[4] - with_profile[3] < b0[4] - b0[3]
+    assert all(x < y for x, y in zip(with_profile, with_profile[1:]))
