@@ -3,13 +3,20 @@
 // driving libsdf2mesh_b200.so through its C ABI.  Same flags, same defaults, same input priority
 // (shadertoy > sdf > glsl, main.rs:200-221), same power-of-two rounding with a warning, same log
 // lines ("Reading SDF from ...", module names, "Mesh has N vertices.", "Mesh written to ...").
-// Additions: --device, --all-slices, --exact-dense, --no-normals, --binary-stl, --stats.
+// Additions: --device, --gpus, --all-slices, --exact-dense, --no-normals, --binary-stl, --stats,
+// --shadertoy-file, --debug-cuda.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../include/sdf2mesh_b200.h"
 
@@ -53,6 +60,7 @@ void usage(FILE* f) {
       "  -r, --resolution <RESOLUTION>        Grid resolution. Default: 256\n"
       "  -b, --bounds <BOUNDS>                Size of bounding box. Default: 2\n"
       "      --device <N>                     CUDA device ordinal [default: 0]\n"
+      "      --gpus <N>                       Split the grid into N z-slabs, one GPU (and host thread) each [default: 1]\n"
       "      --all-slices                     Mesh every z-slice (the reference never reads back the last one)\n"
       "      --exact-dense                    Evaluate all 8 corners of every cell, like the reference (slow)\n"
       "      --no-normals                     Skip vertex normals (only PLY output uses them)\n"
@@ -68,7 +76,7 @@ struct Args {
   std::string sdf, shadertoy_id, shadertoy_file, shadertoy_sdf = "sdf", glsl, glsl_sdf = "sdf", mesh, debug_wgsl, debug_png, debug_cuda;
   unsigned resolution = 0;
   float bounds = 0.0f;
-  int device = 0;
+  int device = 0, gpus = 1;
   bool all_slices = false, exact_dense = false, no_normals = false, binary_stl = false, stats = false;
 };
 
@@ -83,6 +91,143 @@ bool take_value(int argc, char** argv, int& i, const char* longf, const char* sh
   if (a.compare(0, l.size() + 1, l + "=") == 0) { *out = a.substr(l.size() + 1); return true; }
   if (shortf && a.size() > 2 && a.compare(0, 2, shortf) == 0) { *out = a.substr(2); return true; }
   return false;
+}
+
+
+// builds the shader from the arguments (input priority: shadertoy > sdf > glsl, main.rs:200-221)
+s2m_shader* load_shader(const Args& a, bool quiet) {
+  s2m_shader* shader = nullptr;
+  if (!a.shadertoy_id.empty()) {
+    if (!quiet) info("Reading SDF from ShaderToy (shader ID " + a.shadertoy_id + ")");
+    error("the ShaderToy REST fetch is not part of this build (no network access); save the shader's code to a file and use --shadertoy-file");
+    exit(101);
+  } else if (!a.shadertoy_file.empty()) {
+    if (!quiet) info("Reading SDF from ShaderToy code in " + a.shadertoy_file + "...");
+    FILE* f = fopen(a.shadertoy_file.c_str(), "rb");
+    if (!f) { error("cannot open " + a.shadertoy_file); exit(101); }
+    std::string code;
+    char buf[4096];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) code.append(buf, n);
+    fclose(f);
+    if (s2m_shader_from_shadertoy_source(code.data(), code.size(), a.shadertoy_sdf.c_str(), &shader)) die("cannot convert ShaderToy shader");
+  } else if (!a.sdf.empty()) {
+    if (!quiet) info("Reading SDF from " + a.sdf + "...");
+    if (s2m_shader_from_path(a.sdf.c_str(), &shader)) die("cannot read SDF");
+  } else if (!a.glsl.empty()) {
+    if (!quiet) info("Reading SDF from GLSL fragment shader " + a.glsl + "...");
+    if (s2m_shader_from_glsl_fragment_shader(a.glsl.c_str(), a.glsl_sdf.c_str(), &shader)) die("cannot convert GLSL shader");
+  } else {
+    if (s2m_shader_from_source("", 0, S2M_SRC_SDF3D, nullptr, nullptr, &shader)) die("empty shader");  // Sdf3DShader::default()
+  }
+  if (!quiet) {  // forward what the reference logs while assembling the source
+    std::string lg = s2m_shader_log(shader);
+    size_t p = 0;
+    while (p < lg.size()) {
+      size_t e = lg.find('\n', p);
+      if (e == std::string::npos) e = lg.size();
+      const std::string line = lg.substr(p, e - p);
+      if (line.compare(0, 5, "INFO ") == 0) info(line.substr(5));
+      else if (line.compare(0, 6, "ERROR ") == 0) error(line.substr(6));
+      else if (!line.empty()) info(line);
+      p = e + 1;
+    }
+  }
+  return shader;
+}
+
+// --gpus N: one host thread + one context per GPU, contiguous z-slabs balanced with the cost probe,
+// vertex counts exchanged in-process (the multi-process form of the same protocol, over NCCL, is
+// sdf2mesh_b200/distributed.py), one output file written from all parts.
+int run_multi_gpu(const Args& a, s2m_mesh_params params) {
+  const int n = a.gpus;
+  s2m_shader* shader = load_shader(a, false);
+  if (!a.debug_wgsl.empty() && s2m_shader_write_to_file(shader, a.debug_wgsl.c_str())) die("cannot write --debug-wgsl file");
+  const uint32_t n_slices = (params.flags & S2M_MESH_ALL_SLICES) ? params.dims[2] : params.dims[2] - 1;
+  std::vector<s2m_ctx*> ctx(n, nullptr);
+  std::vector<s2m_module*> mod(n, nullptr);
+  std::vector<s2m_result*> res(n, nullptr);
+  std::vector<uint64_t> counts(n, 0);
+  std::vector<uint32_t> bounds(n + 1, 0);
+  std::vector<std::string> errors(n);
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0, generation = 0;
+  auto barrier = [&] {
+    std::unique_lock<std::mutex> lk(mu);
+    const int gen = generation;
+    if (++arrived == n) { arrived = 0; ++generation; cv.notify_all(); }
+    else cv.wait(lk, [&] { return generation != gen; });
+  };
+  std::atomic<bool> failed{false};
+  auto worker = [&](int g) {
+    auto fail_here = [&](const char* what) { errors[g] = std::string(what) + ": " + s2m_last_error(); failed = true; };
+    if (s2m_ctx_create(a.device + g, &ctx[g])) fail_here("no usable CUDA device");
+    else if (s2m_module_compile(ctx[g], shader, 0, &mod[g])) fail_here("shader module creation failed");
+    if (g == 0 && !failed) {
+      const uint32_t bands = 128;
+      std::vector<double> cost(bands, 1.0);
+      if (s2m_cost_probe(ctx[0], mod[0], &params, bands, cost.data())) std::fill(cost.begin(), cost.end(), 1.0);
+      double total = 0, mx = 0;
+      for (double c : cost) mx = std::max(mx, c);
+      for (double& c : cost) { c = std::max(c, mx * 1e-3); total += c; }
+      double acc = 0;
+      int next = 1;
+      for (uint32_t b = 0; b < bands && next < n; ++b) {
+        const double before = acc;
+        acc += cost[b];
+        while (next < n && acc >= total * next / n) {
+          const double frac = cost[b] > 0 ? (total * next / n - before) / cost[b] : 0.0;
+          bounds[next] = (uint32_t)((b + frac) * n_slices / bands + 0.5);
+          ++next;
+        }
+      }
+      bounds[n] = n_slices;
+      for (int k = 1; k <= n; ++k) bounds[k] = std::min(std::max(bounds[k], bounds[k - 1] + 1), n_slices - (uint32_t)(n - k));
+    }
+    barrier();
+    if (failed) return;
+    s2m_mesh_params p = params;
+    p.z_begin = bounds[g]; p.z_end = bounds[g + 1];
+    if (s2m_mesh_begin(ctx[g], mod[g], &p, &res[g])) fail_here("meshing failed");
+    else {
+      s2m_result_info ri;
+      s2m_result_get(res[g], &ri);
+      counts[g] = ri.n_vertices;
+    }
+    barrier();  // the "all-gather": every slab's vertex count is now visible to every thread
+    if (failed) return;
+    int64_t base = 0;
+    for (int k = 0; k < g; ++k) base += (int64_t)counts[k];
+    if (s2m_mesh_finish(res[g], base)) fail_here("quad emission failed");
+  };
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> threads;
+  for (int g = 0; g < n; ++g) threads.emplace_back(worker, g);
+  for (auto& t : threads) t.join();
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (failed) {
+    for (int g = 0; g < n; ++g) if (!errors[g].empty()) error("GPU " + std::to_string(a.device + g) + ": " + errors[g]);
+    return 101;
+  }
+  info("CUDA contexts set up on " + std::to_string(n) + " GPUs.");
+  uint64_t nv = 0, nq = 0, ninv = 0;
+  for (int g = 0; g < n; ++g) {
+    s2m_result_info ri;
+    s2m_result_get(res[g], &ri);
+    nv += ri.n_vertices; nq += ri.n_quads; ninv += ri.n_invalid_quads;
+    if (a.stats)
+      fprintf(stderr, "stats: GPU %d slices [%u, %u): %llu vertices, %llu quads, device %.3f ms\n", a.device + g, bounds[g], bounds[g + 1],
+              (unsigned long long)ri.n_vertices, (unsigned long long)ri.n_quads, ri.timings.device_ms);
+  }
+  info("Mesh has " + std::to_string(nv) + " vertices.");
+  if (ninv) warn(std::to_string(ninv) + " invalid quads. Mesh will not be water-tight!");
+  if (a.stats) fprintf(stderr, "stats: %llu quads; JIT + meshing on %d GPUs took %.1f ms wall\n", (unsigned long long)nq, n, ms);
+  if (s2m_write_mesh_parts(res.data(), n, a.mesh.c_str(), a.binary_stl ? 1 : 0)) error(std::string("Could not write mesh to ") + s2m_last_error() + "!");
+  info("Mesh written to " + a.mesh);
+  for (int g = 0; g < n; ++g) { s2m_result_free(res[g]); s2m_module_free(mod[g]); s2m_ctx_destroy(ctx[g]); }
+  s2m_shader_free(shader);
+  return 0;
 }
 
 }  // namespace
@@ -119,6 +264,7 @@ int main(int argc, char** argv) {
       continue;
     }
     if (take_value(argc, argv, i, "device", nullptr, &v)) { a.device = atoi(v.c_str()); continue; }
+    if (take_value(argc, argv, i, "gpus", nullptr, &v)) { a.gpus = std::max(1, atoi(v.c_str())); continue; }
     if (s == "--all-slices") { a.all_slices = true; continue; }
     if (s == "--exact-dense") { a.exact_dense = true; continue; }
     if (s == "--no-normals") { a.no_normals = true; continue; }
@@ -144,47 +290,12 @@ int main(int argc, char** argv) {
   if (a.no_normals) params.flags |= S2M_MESH_NO_NORMALS;
   params.flags |= S2M_MESH_KEEP_INVALID;  // so that the reference's per-quad warnings can be printed
 
+  if (a.gpus > 1) return run_multi_gpu(a, params);
+
   s2m_ctx* ctx = nullptr;
   if (s2m_ctx_create(a.device, &ctx)) die("no usable CUDA device");  // request_adapter/request_device .unwrap()
 
-  // input priority: shadertoy > sdf > glsl  (main.rs:200-221)
-  s2m_shader* shader = nullptr;
-  if (!a.shadertoy_id.empty()) {
-    info("Reading SDF from ShaderToy (shader ID " + a.shadertoy_id + ")");
-    error("the ShaderToy REST fetch is not part of this build (no network access); save the shader as a .frag file and use --glsl");
-    return 101;
-  } else if (!a.shadertoy_file.empty()) {
-    info("Reading SDF from ShaderToy code in " + a.shadertoy_file + "...");
-    FILE* f = fopen(a.shadertoy_file.c_str(), "rb");
-    if (!f) { error("cannot open " + a.shadertoy_file); return 101; }
-    std::string code;
-    char buf[4096];
-    size_t n;
-    while ((n = fread(buf, 1, sizeof buf, f)) > 0) code.append(buf, n);
-    fclose(f);
-    if (s2m_shader_from_shadertoy_source(code.data(), code.size(), a.shadertoy_sdf.c_str(), &shader)) die("cannot convert ShaderToy shader");
-  } else if (!a.sdf.empty()) {
-    info("Reading SDF from " + a.sdf + "...");
-    if (s2m_shader_from_path(a.sdf.c_str(), &shader)) die("cannot read SDF");
-  } else if (!a.glsl.empty()) {
-    info("Reading SDF from GLSL fragment shader " + a.glsl + "...");
-    if (s2m_shader_from_glsl_fragment_shader(a.glsl.c_str(), a.glsl_sdf.c_str(), &shader)) die("cannot convert GLSL shader");
-  } else {
-    if (s2m_shader_from_source("", 0, S2M_SRC_SDF3D, nullptr, nullptr, &shader)) die("empty shader");  // Sdf3DShader::default()
-  }
-  {  // forward what the reference logs while assembling the source
-    std::string lg = s2m_shader_log(shader);
-    size_t p = 0;
-    while (p < lg.size()) {
-      size_t e = lg.find('\n', p);
-      if (e == std::string::npos) e = lg.size();
-      const std::string line = lg.substr(p, e - p);
-      if (line.compare(0, 5, "INFO ") == 0) info(line.substr(5));
-      else if (line.compare(0, 6, "ERROR ") == 0) error(line.substr(6));
-      else if (!line.empty()) info(line);
-      p = e + 1;
-    }
-  }
+  s2m_shader* shader = load_shader(a, false);
   if (!a.debug_wgsl.empty() && s2m_shader_write_to_file(shader, a.debug_wgsl.c_str())) die("cannot write --debug-wgsl file");
   if (!a.debug_png.empty()) warn("--debug-png is ignored: this engine has no per-slice textures to dump");
 

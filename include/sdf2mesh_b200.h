@@ -164,6 +164,9 @@ typedef struct s2m_result_info {
    * UINT64_MAX for a missing vertex; sorted by (key, edge) = the reference's order.  At most 2^20. */
   const uint64_t* invalid_records;
   uint64_t n_invalid_records;
+  const float* halo_positions;   /* 3 * n_halo_vertices: positions of the recomputed slice below this slab (vertex
+                                    global_vertex_base - n_halo_vertices + j), so a slab can be written on its own */
+  int64_t global_vertex_base;    /* what s2m_mesh_finish was given (0 for s2m_mesh_run) */
   s2m_timings timings;
 } s2m_result_info;
 
@@ -181,9 +184,14 @@ void s2m_result_free(s2m_result* r);
 
 /* TriangleMesh::write_to_file (mesh.rs:182): by extension, case-insensitive: .stl -> ASCII STL
  * (mesh.rs:167), .ply -> ASCII PLY (mesh.rs:198); unknown extension logs an error and returns OK
- * like the reference.  Valid for single-slab results (indices are positions in this result). */
+ * like the reference.  A z-slab result (s2m_mesh_begin/finish with a halo) can be written as STL on
+ * its own (it carries the halo positions its quads refer to); PLY needs the whole mesh. */
 int s2m_result_write_mesh(const s2m_result* r, const char* path);
 int s2m_result_write_stl_binary(const s2m_result* r, const char* path);
+/* The same writers over several z-slab results held by ONE process (e.g. one host thread per GPU),
+ * given in z order with consecutive global vertex bases: one STL / PLY file for the whole mesh.
+ * binary_stl != 0 writes binary STL for a .stl path. */
+int s2m_write_mesh_parts(const s2m_result* const* parts, int n_parts, const char* path, int binary_stl);
 
 /* diagnostics */
 int s2m_eval_points(s2m_ctx* ctx, s2m_module* m, const float* xyz, uint64_t n, float* out);

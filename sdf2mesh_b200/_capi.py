@@ -66,6 +66,7 @@ class ResultInfo(ctypes.Structure):
         ("cell_keys", ctypes.POINTER(ctypes.c_uint64)), ("sign_nibbles", ctypes.POINTER(ctypes.c_uint8)),
         ("quads", ctypes.POINTER(ctypes.c_uint64)), ("candidates", ctypes.POINTER(ctypes.c_uint64)),
         ("invalid_records", ctypes.POINTER(ctypes.c_uint64)), ("n_invalid_records", ctypes.c_uint64),
+        ("halo_positions", ctypes.POINTER(ctypes.c_float)), ("global_vertex_base", ctypes.c_int64),
         ("timings", Timings),
     ]
 
@@ -110,6 +111,7 @@ SYMBOLS = {
     "s2m_result_free": (None, [_P]),
     "s2m_result_write_mesh": (ctypes.c_int, [_P, _S]),
     "s2m_result_write_stl_binary": (ctypes.c_int, [_P, _S]),
+    "s2m_write_mesh_parts": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _S, ctypes.c_int]),
     "s2m_eval_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_uint64, _P]),
     "s2m_debug_slab_plane": (ctypes.c_int, [_P, _P, ctypes.POINTER(MeshParams), ctypes.c_uint32, _P]),
     "s2m_cost_probe": (ctypes.c_int, [_P, _P, ctypes.POINTER(MeshParams), ctypes.c_uint32, _P]),

@@ -403,7 +403,8 @@ struct s2m_result {
   uint32_t z_first = 0, nz = 0, label_add = 0, halo = 0, words_x = 0;
   uint64_t n_cand = 0, n_vert_total = 0, n_halo = 0, n_quads = 0, n_invalid = 0;
   float* h_pos = nullptr; float* h_nrm = nullptr; uint64_t* h_key = nullptr; uint8_t* h_nib = nullptr;
-  uint64_t* h_quads = nullptr; uint64_t* h_cand = nullptr; uint64_t* h_invalid = nullptr;
+  uint64_t* h_quads = nullptr; uint64_t* h_cand = nullptr; uint64_t* h_invalid = nullptr; float* h_halo_pos = nullptr;
+  int64_t global_base = 0;
   uint64_t n_invalid_records = 0;
   uint64_t cap_v = 0, cap_q = 0;   // capacity (elements) of the pinned vertex / quad blocks
   bool streamed = false;           // vertex (and quad) chunks were copied while later chunks computed
@@ -419,7 +420,7 @@ struct s2m_result {
 extern "C" void s2m_result_free(s2m_result* r) {
   if (!r) return;
   if (r->ctx) {
-    for (void* p : {(void*)r->h_pos, (void*)r->h_nrm, (void*)r->h_key, (void*)r->h_nib, (void*)r->h_quads, (void*)r->h_cand, (void*)r->h_invalid})
+    for (void* p : {(void*)r->h_pos, (void*)r->h_nrm, (void*)r->h_key, (void*)r->h_nib, (void*)r->h_quads, (void*)r->h_cand, (void*)r->h_invalid, (void*)r->h_halo_pos})
       if (p) r->ctx->release_pinned(p);
     if (!r->finished) r->ctx->busy = false;
   }
@@ -788,6 +789,11 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
     if (!r->h_cand) return fail(S2M_ERR_OOM, "cudaHostAlloc for candidate list failed");
     if (r->n_cand) CUDA_TRY(cudaMemcpyAsync(r->h_cand, c->cand_key.p, r->n_cand * 8, cudaMemcpyDeviceToHost, s));
   }
+  if (r->n_halo) {  // the halo slice's positions, so that this slab's triangles can be written without the slab below
+    r->h_halo_pos = (float*)c->lease_pinned(r->n_halo * 12);
+    if (!r->h_halo_pos) return fail(S2M_ERR_OOM, "cudaHostAlloc for halo positions failed");
+    CUDA_TRY(cudaMemcpyAsync(r->h_halo_pos, c->v_pos.p, r->n_halo * 12, cudaMemcpyDeviceToHost, s));
+  }
   c->hint_nv = n_own;
   tr.mark("begin done");
   guard.keep = true;
@@ -809,6 +815,7 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   int st;
+  r->global_base = global_vertex_base;
   if (!r->quads_done) {
     // ---- K4b over all own vertices with the global base, then the quad copy
     if ((st = launch_k4b(c, r, s, 0, r->n_vert_total, 0, (long long)global_vertex_base - (long long)r->n_halo))) return st;
@@ -874,6 +881,7 @@ extern "C" int s2m_result_get(const s2m_result* r, s2m_result_info* o) {
   o->positions = r->h_pos; o->normals = r->h_nrm; o->cell_keys = r->h_key; o->sign_nibbles = r->h_nib;
   o->quads = r->h_quads; o->candidates = r->h_cand;
   o->invalid_records = r->h_invalid; o->n_invalid_records = r->n_invalid_records;
+  o->halo_positions = r->h_halo_pos; o->global_vertex_base = r->global_base;
   o->timings = r->t;
   return S2M_OK;
 }

@@ -129,14 +129,23 @@ __host__ __device__ __noinline__ float s2m__trig_red_slow(float x, int* q);
 static float s2m__trig_red_slow(float x, int* q);
 #endif
 
-S2M_HD float s2m__trig_red(float x, int* q) {
-  if (s2m_abs(x) > 105615.0f) return s2m__trig_red_slow(x, q);
-  float j = s2m_fma(x, 6.366197467e-01f, 12582912.0f) - 12582912.0f; /* rint(x*2/pi) */
+/* Fast reduction (Cody-Waite, 3 fma): valid for |x| <= 105615; straight-line, so that sin(x) and
+ * cos(x) of one argument share it (and both polynomials) after CSE.  Larger arguments, inf and NaN
+ * are patched afterwards by the callers through the out-of-line Payne-Hanek path.  The quadrant is
+ * read from the low mantissa bits of the 1.5*2^23-biased product instead of a float->int convert. */
+#define S2M__TRIG_FAST_MAX 105615.0f
+S2M_HD float s2m__trig_red_fast(float x, int* q) {
+  float jm = s2m_fma(x, 6.366197467e-01f, 12582912.0f);
+  float j = jm - 12582912.0f; /* rint(x*2/pi) */
   float r = s2m_fma(j, -1.570796371e+00f, x);
   r = s2m_fma(j, 4.371138829e-08f, r);
   r = s2m_fma(j, 1.715124510e-15f, r);
-  *q = ((int)j) & 3;
+  *q = s2m_f2i(jm) & 3;
   return r;
+}
+S2M_HD float s2m__trig_red(float x, int* q) {
+  if (s2m_abs(x) > S2M__TRIG_FAST_MAX) return s2m__trig_red_slow(x, q);
+  return s2m__trig_red_fast(x, q);
 }
 
 /* 2/pi = 0.A2F9836E 4E441529 FC2757D1 F534DDC0 DB629599 3C439041 FE5163AB ... (hex), one leading zero word */
@@ -208,21 +217,35 @@ S2M_HD float s2m__cos_poly(float r) {
   p = s2m_fma(p, s, -0.5f);
   return s2m_fma(p, s, 1.0f);
 }
-/* Branch-free: both polynomials are always evaluated and selected by the quadrant.  sin(x) and
- * cos(x) of the same argument then share the reduction and both polynomials after CSE, and lanes
- * in different quadrants do not diverge.  (Same values as selecting before evaluating.) */
-S2M_HD float s2m_sin(float x) {
-  int q; float r = s2m__trig_red(x, &q);
+/* Branch-lean: both polynomials are always evaluated on the fast reduction and selected by the
+ * quadrant; sin(x) and cos(x) of the same argument then share everything but the selects after CSE,
+ * and lanes in different quadrants do not diverge.  Big arguments take the cold out-of-line path.
+ * (Same values as reducing first and selecting before evaluating.) */
+S2M_HD float s2m__sincos_sel(float r, int q) {
   const float sp = s2m__sin_poly(r), cp = s2m__cos_poly(r);
   const float v = (q & 1) ? cp : sp;
   return (q & 2) ? -v : v;
 }
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+__host__ __device__ __noinline__
+#else
+static
+#endif
+float s2m__sincos_slow(float x, int dq) { /* |x| > S2M__TRIG_FAST_MAX, inf, NaN */
+  int q; float r = s2m__trig_red_slow(x, &q);
+  return s2m__sincos_sel(r, q + dq);
+}
+S2M_HD float s2m_sin(float x) {
+  int q; float r = s2m__trig_red_fast(x, &q);
+  float v = s2m__sincos_sel(r, q);
+  if (s2m_abs(x) > S2M__TRIG_FAST_MAX) v = s2m__sincos_slow(x, 0);
+  return v;
+}
 S2M_HD float s2m_cos(float x) {
-  int q; float r = s2m__trig_red(x, &q);
-  const float sp = s2m__sin_poly(r), cp = s2m__cos_poly(r);
-  q += 1;
-  const float v = (q & 1) ? cp : sp;
-  return (q & 2) ? -v : v;
+  int q; float r = s2m__trig_red_fast(x, &q);
+  float v = s2m__sincos_sel(r, q + 1);
+  if (s2m_abs(x) > S2M__TRIG_FAST_MAX) v = s2m__sincos_slow(x, 1);
+  return v;
 }
 S2M_HD float s2m_tan(float x) {
   int q; float r = s2m__trig_red(x, &q);

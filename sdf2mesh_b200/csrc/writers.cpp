@@ -58,17 +58,49 @@ void rust_f32(float f, std::string& out) {
   }
 }
 
-struct MeshView {
+// One or more z-slab results, in z order, addressed by global vertex index.
+struct Part {
   s2m_result_info i;
-  bool ok = false;
+  int64_t base;   // global index of this part's first own vertex
+};
+struct Parts {
+  std::vector<Part> parts;
+  uint64_t n_vertices = 0, n_quads = 0;
+  // position of global vertex g as seen from part `hint` (its own vertices, its halo, or another part)
+  const float* pos(uint64_t g, size_t hint) const {
+    const Part& h = parts[hint];
+    const int64_t gi = (int64_t)g;
+    if (gi >= h.base && gi < h.base + (int64_t)h.i.n_vertices) return h.i.positions + 3 * (gi - h.base);
+    const int64_t hb = h.base - (int64_t)h.i.n_halo_vertices;
+    if (gi >= hb && gi < h.base && h.i.halo_positions) return h.i.halo_positions + 3 * (gi - hb);
+    for (const Part& p : parts)
+      if (gi >= p.base && gi < p.base + (int64_t)p.i.n_vertices) return p.i.positions + 3 * (gi - p.base);
+    return nullptr;
+  }
 };
 
-int get_view(const s2m_result* r, MeshView* v) {
-  if (!r) return fail(S2M_ERR_INVALID_ARG, "result is NULL");
-  int st = s2m_result_get(r, &v->i);
-  if (st) return st;
-  if (v->i.n_halo_vertices != 0) return fail(S2M_ERR_STATE, "mesh writers need a single-slab result (this one is a z-slab with a halo)");
-  if (v->i.n_quads && !v->i.quads) return fail(S2M_ERR_STATE, "s2m_mesh_finish has not been called");
+int get_parts(const s2m_result* const* rs, int n, Parts* out, bool whole_mesh) {
+  if (!rs || n <= 0) return fail(S2M_ERR_INVALID_ARG, "no results to write");
+  for (int k = 0; k < n; ++k) {
+    if (!rs[k]) return fail(S2M_ERR_INVALID_ARG, "result is NULL");
+    Part p;
+    int st = s2m_result_get(rs[k], &p.i);
+    if (st) return st;
+    if (p.i.n_quads && !p.i.quads) return fail(S2M_ERR_STATE, "s2m_mesh_finish has not been called");
+    p.base = p.i.global_vertex_base;
+    if (k > 0 && p.base != out->parts.back().base + (int64_t)out->parts.back().i.n_vertices)
+      return fail(S2M_ERR_STATE, "parts must be consecutive z-slabs with consecutive global vertex bases");
+    out->parts.push_back(p);
+    out->n_vertices += p.i.n_vertices;
+    out->n_quads += p.i.n_quads;
+  }
+  if (whole_mesh && out->parts.front().base != 0) return fail(S2M_ERR_STATE, "this format needs the whole mesh (first part must start at vertex 0)");
+  // every quad index must resolve
+  for (size_t k = 0; k < out->parts.size(); ++k) {
+    const Part& p = out->parts[k];
+    for (uint64_t q = 0; q < 4 * p.i.n_quads; ++q)
+      if (!out->pos(p.i.quads[q], k)) return fail(S2M_ERR_STATE, "a quad refers to a vertex outside the given parts");
+  }
   return S2M_OK;
 }
 
@@ -107,54 +139,61 @@ inline void tri_normal(const float* p0, const float* p1, const float* p2, float 
   n[2] = a[0] * b[1] - a[1] * b[0];
 }
 
-int write_stl_ascii(const MeshView& v, const char* path) {
+int write_stl_ascii(const Parts& v, const char* path) {
   FILE* f = fopen(path, "wb");
   if (!f) return fail(S2M_ERR_IO, std::string("cannot create ") + path + ": " + strerror(errno));
   fputs("solid\n", f);
-  const s2m_result_info& m = v.i;
-  int st = parallel_write(f, m.n_quads, 1u << 15, [&](uint64_t b, uint64_t e, std::string& out) {
-    for (uint64_t q = b; q < e; ++q)
-      for (int t = 0; t < 2; ++t) {
-        uint64_t tri[3];
-        tri_of_quad(m.quads + 4 * q, t, tri);
-        const float* p0 = m.positions + 3 * tri[0];
-        const float* p1 = m.positions + 3 * tri[1];
-        const float* p2 = m.positions + 3 * tri[2];
-        float n[3];
-        tri_normal(p0, p1, p2, n);
-        out += "facet normal ";
-        rust_f32(n[0], out); out += ' '; rust_f32(n[1], out); out += ' '; rust_f32(n[2], out);
-        out += "\n\touter loop\n";
-        for (const float* p : {p0, p1, p2}) {
-          out += "\t\tvertex ";
-          rust_f32(p[0], out); out += ' '; rust_f32(p[1], out); out += ' '; rust_f32(p[2], out);
-          out += '\n';
+  int st = S2M_OK;
+  for (size_t k = 0; k < v.parts.size() && st == S2M_OK; ++k) {
+    const s2m_result_info& m = v.parts[k].i;
+    st = parallel_write(f, m.n_quads, 1u << 15, [&](uint64_t b, uint64_t e, std::string& out) {
+      for (uint64_t q = b; q < e; ++q)
+        for (int t = 0; t < 2; ++t) {
+          uint64_t tri[3];
+          tri_of_quad(m.quads + 4 * q, t, tri);
+          const float* p0 = v.pos(tri[0], k);
+          const float* p1 = v.pos(tri[1], k);
+          const float* p2 = v.pos(tri[2], k);
+          float n[3];
+          tri_normal(p0, p1, p2, n);
+          out += "facet normal ";
+          rust_f32(n[0], out); out += ' '; rust_f32(n[1], out); out += ' '; rust_f32(n[2], out);
+          out += "\n\touter loop\n";
+          for (const float* p : {p0, p1, p2}) {
+            out += "\t\tvertex ";
+            rust_f32(p[0], out); out += ' '; rust_f32(p[1], out); out += ' '; rust_f32(p[2], out);
+            out += '\n';
+          }
+          out += "\tendloop\nendfacet\n";
         }
-        out += "\tendloop\nendfacet\n";
-      }
-  });
+    });
+  }
   fputs("endsolid\n", f);
   if (fclose(f) != 0 && st == S2M_OK) st = fail(S2M_ERR_IO, std::string("close failed for ") + path);
   return st;
 }
 
-int write_ply_ascii(const MeshView& v, const char* path) {
+int write_ply_ascii(const Parts& v, const char* path) {
   FILE* f = fopen(path, "wb");
   if (!f) return fail(S2M_ERR_IO, std::string("cannot create ") + path + ": " + strerror(errno));
-  const s2m_result_info& m = v.i;
   fprintf(f, "ply\nformat ascii 1.0\ncomment written by rust-sdf\n");
   fprintf(f, "element vertex %llu\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\n",
-          (unsigned long long)m.n_vertices);
-  fprintf(f, "element face %llu\nproperty list uchar int vertex_index\nend_header\n", (unsigned long long)(2 * m.n_quads));
-  int st = parallel_write(f, m.n_vertices, 1u << 16, [&](uint64_t b, uint64_t e, std::string& out) {
-    for (uint64_t i = b; i < e; ++i) {
-      const float* p = m.positions + 3 * i;
-      const float* n = m.normals + 3 * i;
-      rust_f32(p[0], out); out += ' '; rust_f32(p[1], out); out += ' '; rust_f32(p[2], out); out += ' ';
-      rust_f32(n[0], out); out += ' '; rust_f32(n[1], out); out += ' '; rust_f32(n[2], out); out += '\n';
-    }
-  });
-  if (st == S2M_OK)
+          (unsigned long long)v.n_vertices);
+  fprintf(f, "element face %llu\nproperty list uchar int vertex_index\nend_header\n", (unsigned long long)(2 * v.n_quads));
+  int st = S2M_OK;
+  for (size_t k = 0; k < v.parts.size() && st == S2M_OK; ++k) {
+    const s2m_result_info& m = v.parts[k].i;
+    st = parallel_write(f, m.n_vertices, 1u << 16, [&](uint64_t b, uint64_t e, std::string& out) {
+      for (uint64_t i = b; i < e; ++i) {
+        const float* p = m.positions + 3 * i;
+        const float* n = m.normals + 3 * i;
+        rust_f32(p[0], out); out += ' '; rust_f32(p[1], out); out += ' '; rust_f32(p[2], out); out += ' ';
+        rust_f32(n[0], out); out += ' '; rust_f32(n[1], out); out += ' '; rust_f32(n[2], out); out += '\n';
+      }
+    });
+  }
+  for (size_t k = 0; k < v.parts.size() && st == S2M_OK; ++k) {
+    const s2m_result_info& m = v.parts[k].i;
     st = parallel_write(f, m.n_quads, 1u << 16, [&](uint64_t b, uint64_t e, std::string& out) {
       char buf[128];
       for (uint64_t q = b; q < e; ++q)
@@ -165,62 +204,81 @@ int write_ply_ascii(const MeshView& v, const char* path) {
           out.append(buf, (size_t)n);
         }
     });
+  }
   if (fclose(f) != 0 && st == S2M_OK) st = fail(S2M_ERR_IO, std::string("close failed for ") + path);
   return st;
 }
 
-}  // namespace
-
-extern "C" int s2m_result_write_mesh(const s2m_result* r, const char* path) {
-  if (!path) return fail(S2M_ERR_INVALID_ARG, "path is NULL");
-  MeshView v;
-  int st = get_view(r, &v);
-  if (st) return st;
-  for (uint64_t i = 0; i < 4 * v.i.n_quads; ++i)
-    if (v.i.quads[i] >= v.i.n_vertices) return fail(S2M_ERR_STATE, "quad index outside this result (a non-zero global vertex base was used)");
-  std::string p(path), ext;
-  size_t slash = p.find_last_of('/');
-  size_t dot = p.find_last_of('.');
-  if (dot != std::string::npos && (slash == std::string::npos || dot > slash) && dot != (slash == std::string::npos ? 0 : slash + 1)) ext = p.substr(dot + 1);
-  for (char& c : ext) c = (char)toupper((unsigned char)c);
-  if (ext == "STL") return write_stl_ascii(v, path);
-  if (ext == "PLY") return write_ply_ascii(v, path);
-  fprintf(stderr, "ERROR Unknown file extension: %s\n", ext.c_str());  // mesh.rs:193; the reference still returns Ok
-  return S2M_OK;
-}
-
-extern "C" int s2m_result_write_stl_binary(const s2m_result* r, const char* path) {
-  if (!path) return fail(S2M_ERR_INVALID_ARG, "path is NULL");
-  MeshView v;
-  int st = get_view(r, &v);
-  if (st) return st;
-  const s2m_result_info& m = v.i;
-  if (2 * m.n_quads > 0xffffffffull) return fail(S2M_ERR_UNSUPPORTED, "binary STL holds at most 2^32-1 triangles");
+int write_stl_binary(const Parts& v, const char* path) {
+  if (2 * v.n_quads > 0xffffffffull) return fail(S2M_ERR_UNSUPPORTED, "binary STL holds at most 2^32-1 triangles");
   FILE* f = fopen(path, "wb");
   if (!f) return fail(S2M_ERR_IO, std::string("cannot create ") + path + ": " + strerror(errno));
   char header[80];
   memset(header, 0, sizeof header);
   snprintf(header, sizeof header, "sdf2mesh_b200 binary STL");
-  const uint32_t ntri = (uint32_t)(2 * m.n_quads);
+  const uint32_t ntri = (uint32_t)(2 * v.n_quads);
   fwrite(header, 1, 80, f);
   fwrite(&ntri, 4, 1, f);
-  st = parallel_write(f, m.n_quads, 1u << 16, [&](uint64_t b, uint64_t e, std::string& out) {
-    out.resize((size_t)(e - b) * 100);
-    char* o = &out[0];
-    for (uint64_t q = b; q < e; ++q)
-      for (int t = 0; t < 2; ++t) {
-        uint64_t tri[3];
-        tri_of_quad(m.quads + 4 * q, t, tri);
-        const float* p[3] = {m.positions + 3 * tri[0], m.positions + 3 * tri[1], m.positions + 3 * tri[2]};
-        float n[3];
-        tri_normal(p[0], p[1], p[2], n);
-        const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-        if (len > 0.0f) { n[0] /= len; n[1] /= len; n[2] /= len; } else { n[0] = n[1] = n[2] = 0.0f; }
-        memcpy(o, n, 12); o += 12;
-        for (int k = 0; k < 3; ++k) { memcpy(o, p[k], 12); o += 12; }
-        o[0] = o[1] = 0; o += 2;
-      }
-  });
+  int st = S2M_OK;
+  for (size_t k = 0; k < v.parts.size() && st == S2M_OK; ++k) {
+    const s2m_result_info& m = v.parts[k].i;
+    st = parallel_write(f, m.n_quads, 1u << 16, [&](uint64_t b, uint64_t e, std::string& out) {
+      out.resize((size_t)(e - b) * 100);
+      char* o = &out[0];
+      for (uint64_t q = b; q < e; ++q)
+        for (int t = 0; t < 2; ++t) {
+          uint64_t tri[3];
+          tri_of_quad(m.quads + 4 * q, t, tri);
+          const float* p[3] = {v.pos(tri[0], k), v.pos(tri[1], k), v.pos(tri[2], k)};
+          float n[3];
+          tri_normal(p[0], p[1], p[2], n);
+          const float len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+          if (len > 0.0f) { n[0] /= len; n[1] /= len; n[2] /= len; } else { n[0] = n[1] = n[2] = 0.0f; }
+          memcpy(o, n, 12); o += 12;
+          for (int c = 0; c < 3; ++c) { memcpy(o, p[c], 12); o += 12; }
+          o[0] = o[1] = 0; o += 2;
+        }
+    });
+  }
   if (fclose(f) != 0 && st == S2M_OK) st = fail(S2M_ERR_IO, std::string("close failed for ") + path);
   return st;
+}
+
+std::string upper_extension(const char* path) {  // Path::extension().to_ascii_uppercase() (mesh.rs:183-188)
+  std::string p(path), ext;
+  size_t slash = p.find_last_of('/');
+  size_t dot = p.find_last_of('.');
+  if (dot != std::string::npos && (slash == std::string::npos || dot > slash) && dot != (slash == std::string::npos ? 0 : slash + 1)) ext = p.substr(dot + 1);
+  for (char& c : ext) c = (char)toupper((unsigned char)c);
+  return ext;
+}
+
+int write_parts(const s2m_result* const* rs, int n, const char* path, int binary_stl) {
+  if (!path) return fail(S2M_ERR_INVALID_ARG, "path is NULL");
+  const std::string ext = upper_extension(path);
+  if (ext != "STL" && ext != "PLY") {
+    fprintf(stderr, "ERROR Unknown file extension: %s\n", ext.c_str());  // mesh.rs:193; the reference still returns Ok
+    return S2M_OK;
+  }
+  Parts v;
+  int st = get_parts(rs, n, &v, ext == "PLY");
+  if (st) return st;
+  if (ext == "PLY") return write_ply_ascii(v, path);
+  return binary_stl ? write_stl_binary(v, path) : write_stl_ascii(v, path);
+}
+
+}  // namespace
+
+extern "C" int s2m_result_write_mesh(const s2m_result* r, const char* path) { return write_parts(&r, 1, path, 0); }
+
+extern "C" int s2m_result_write_stl_binary(const s2m_result* r, const char* path) {
+  if (!path) return fail(S2M_ERR_INVALID_ARG, "path is NULL");
+  Parts v;
+  int st = get_parts(&r, 1, &v, false);
+  if (st) return st;
+  return write_stl_binary(v, path);
+}
+
+extern "C" int s2m_write_mesh_parts(const s2m_result* const* parts, int n_parts, const char* path, int binary_stl) {
+  return write_parts(parts, n_parts, path, binary_stl);
 }

@@ -171,6 +171,12 @@ class MeshResult:
             pass
 
 
+def write_mesh_parts(parts, path, binary_stl: bool = False):
+    """one STL / PLY file from several z-slab results held by this process, in z order"""
+    arr = (ctypes.c_void_p * len(parts))(*[p._h for p in parts])
+    check(lib().s2m_write_mesh_parts(arr, len(parts), str(path).encode(), 1 if binary_stl else 0))
+
+
 def mesh_begin(ctx: Context, module: Module, params: MeshParams) -> MeshResult:
     h = ctypes.c_void_p()
     check(lib().s2m_mesh_begin(ctx._h, module._h, ctypes.byref(params), ctypes.byref(h)))

@@ -147,3 +147,61 @@ def test_cli_binary_end_to_end(ctx, tmp_path):
     assert p.returncode == 101 and "Missing SDF function" in p.stderr
     o.free()
     o2.free()
+
+
+@pytest.mark.parametrize("name,res,bounds,splits", [("torus", 32, 2.0, [0, 9, 20, 31]), ("mandelbulb", 64, 5.0, [0, 30, 31, 50, 63])])
+def test_z_slab_parts_write_the_same_file(ctx, tmp_path, name, res, bounds, splits):
+    """s2m_write_mesh_parts over z-slab results (what a multi-GPU job holds) == the single-result file,
+    and an STL written from one slab alone (its halo supplies the vertices below) is that slab's
+    facets of the whole file"""
+    p, _ = s2m.params_from_cli(res, bounds)
+    m = load_example_shader(name).create_shader_module(ctx)
+    full = s2m.mesh_run(ctx, m, p)
+    parts, base = [], 0
+    for zb, ze in zip(splits[:-1], splits[1:]):
+        p.z_begin, p.z_end = zb, ze
+        r = s2m.mesh_begin(ctx, m, p)
+        n_own = r.info().n_vertices
+        r.finish(base)
+        assert r.info().global_vertex_base == base
+        base += n_own
+        parts.append(r)
+    for ext in ("stl", "ply"):
+        a, b = tmp_path / f"full.{ext}", tmp_path / f"parts.{ext}"
+        full.write_mesh(a)
+        s2m.write_mesh_parts(parts, b)
+        assert a.read_bytes() == b.read_bytes()
+    s2m.write_mesh_parts(parts, tmp_path / "pb.stl", binary_stl=True)
+    full.write_stl_binary(tmp_path / "fb.stl")
+    assert (tmp_path / "pb.stl").read_bytes() == (tmp_path / "fb.stl").read_bytes()
+    # each slab on its own: facet text concatenates to the body of the whole file
+    whole = (tmp_path / "full.stl").read_text().splitlines(keepends=True)
+    body = []
+    for k, r in enumerate(parts):
+        f = tmp_path / f"slab{k}.stl"
+        r.write_mesh(f)
+        lines = f.read_text().splitlines(keepends=True)
+        assert lines[0] == whole[0] and lines[-1] == whole[-1]
+        body += lines[1:-1]
+    assert body == whole[1:-1]
+    with pytest.raises(s2m.S2mError):  # a PLY needs every vertex: one interior slab is not a mesh
+        s2m.write_mesh_parts(parts[1:2], tmp_path / "bad.ply")
+    for r in parts:
+        r.free()
+    full.free()
+
+
+def test_cli_multi_gpu_threads(ctx, tmp_path):
+    """sdf2mesh --gpus N (one host thread + context per GPU, in-process count exchange): same bytes"""
+    import torch
+    exe = os.path.join(ROOT, "sdf2mesh_b200", "sdf2mesh")
+    n = torch.cuda.device_count()
+    if not os.path.exists(exe) or n < 2:
+        pytest.skip("needs the CLI and 2 GPUs")
+    n = min(n, 4)
+    one, many = tmp_path / "one.ply", tmp_path / "many.ply"
+    args = [exe, "--glsl", os.path.join(ROOT, "examples", "mandelmesh.frag"), "-r", "128", "-b", "5"]
+    assert subprocess.run(args + ["-0", str(one)], capture_output=True).returncode == 0
+    p = subprocess.run(args + ["-0", str(many), "--gpus", str(n), "--stats"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert one.read_bytes() == many.read_bytes()

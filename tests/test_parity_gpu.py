@@ -263,7 +263,7 @@ def test_4096_cubed_properties(ctx):
     r.free()
 
 
-@pytest.mark.parametrize("name,res,bounds", [("torus", 64, 1.0), ("mandelbulb", 256, 3.0)])
+@pytest.mark.parametrize("name,res,bounds", [("torus", 64, 1.0), ("mandelbulb", 128, 2.0)])
 def test_invalid_quad_records(ctx, name, res, bounds):
     """f4: which quads the reference would report as invalid (mesh.rs:270-278), in its order"""
     p, _ = s2m.params_from_cli(res, bounds, flags=s2m.MESH_KEEP_INVALID)
