@@ -142,6 +142,14 @@ def run_reference_arm(args, wl):
     print(json.dumps(line))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE s2m_k1_slab launch (a 229-plane z-chunk of the
+# default 4 GiB slab budget) from the ncu --set full capture summarised in profiles/r01c_k1_2048_full.md.
+# Algorithmic bytes of that launch: 229 * 2049^2 * 4 B = 3.846 GB of corner values (+ 0.244 GB of
+# corner-class planes that save K2 from re-reading the slab) -> no wasted DRAM traffic.
+K1_TRAFFIC = {"mandelmesh2048": {"bytes_per_launch": 4.0910e9, "algorithmic_bytes_per_launch": 3.8457e9, "launches_per_step": 9,
+                                 "source": "profiles/r01c_k1_2048_full.md"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -298,6 +306,7 @@ def main():
     full, early, frac_in = FLOPS_PER_EVAL.get(osdf, (100.0, 100.0, 1.0))
     flops = (res + 1.0) ** 2 * planes * (frac_in * full + (1 - frac_in) * early)
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+    traffic_known = wl in K1_TRAFFIC and world == 1 and not args.slab_budget_gb
     line = {
         "metric": "Gvoxels/s end-to-end SDF->quads", "value": value, "unit": "Gvoxel/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -312,7 +321,7 @@ def main():
         "clocks": clocks,
         "jit_ms": jit_ms,
         "roofline": {"kernel": "s2m_k1_slab", "bound": "hbm", "achieved": k1_bytes / k1_s / 1e9 if k1_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": (k1_bytes / k1_s / 1e9 / hbm_peak) if k1_s > 0 else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (k1_bytes / k1_s / 1e9 / hbm_peak) if k1_s > 0 else None, "traffic": K1_TRAFFIC[wl]["bytes_per_launch"] if traffic_known else None, "traffic_detail": K1_TRAFFIC[wl] if traffic_known else None, "peak_source": peak_src,
                      "note": "K1 is FP32/issue bound for this SDF, not HBM bound (ncu: issue slots ~90 % busy, DRAM ~5 %); see fp32. "
                              "achieved = 4 B per corner written (SURVEY 8d) / K1 time",
                      "fp32": {"achieved_tflops_source_level": flops / k1_s / 1e12 if k1_s > 0 else None, "peak_tflops_nominal": fp32_peak,

@@ -376,15 +376,6 @@ S2M_HD float s2m_exp2(float a) {
   return s2m__scale2(r, (int)j);
 }
 
-/* splits a finite positive float into m in [2/3,4/3) and integer exponent i (as float) */
-S2M_HD float s2m__frexp23(float a, float* i) {
-  float bias = 0.0f;
-  int ia = s2m_f2i(a);
-  if (ia < 0x00800000) { a = a * 8388608.0f; bias = -23.0f; ia = s2m_f2i(a); }
-  int e = (ia - 0x3f2aaaab) & (int)0xff800000;
-  *i = s2m_fma((float)e, 1.192092896e-07f, bias);
-  return s2m_i2f(ia - e);
-}
 S2M_HD float s2m__log1p_poly(float f) { /* log1p(f) - f + f*f/2 = f^3 L(f),  |f| <= 1/3 */
   float p = -1.289160103e-01f;
   p = s2m_fma(p, f, 1.398446709e-01f);
@@ -396,32 +387,52 @@ S2M_HD float s2m__log1p_poly(float f) { /* log1p(f) - f + f*f/2 = f^3 L(f),  |f|
   p = s2m_fma(p, f, 3.333321512e-01f);
   return p;
 }
-S2M_HD float s2m_log(float a) {
-  int ia = s2m_f2i(a);
-  if ((ia & 0x7fffffff) == 0) return -s2m_inf();
-  if (ia < 0) return s2m_nan();
-  if (ia >= 0x7f800000) return a + a; /* +inf, NaN */
-  float i; float m = s2m__frexp23(a, &i);
-  float f = m - 1.0f;
-  float s = f * f;
+/* log / log2 of a normal positive finite float (bias = exponent correction of a pre-scaled denormal) */
+S2M_HD float s2m__log_norm(float a, float bias) {
+  const int ia = s2m_f2i(a);
+  const int e = (ia - 0x3f2aaaab) & (int)0xff800000;   /* m = a / 2^i in [2/3, 4/3) */
+  const float i = s2m_fma((float)e, 1.192092896e-07f, bias);
+  const float f = s2m_i2f(ia - e) - 1.0f;
+  const float s = f * f;
   float r = s2m_fma(s2m__log1p_poly(f) * f, s, i * -1.904654212e-09f);
   r = s2m_fma(-0.5f, s, r);
   r = r + f;
   return s2m_fma(i, 6.931471825e-01f, r);
 }
-S2M_HD float s2m_log2(float a) {
-  int ia = s2m_f2i(a);
-  if ((ia & 0x7fffffff) == 0) return -s2m_inf();
-  if (ia < 0) return s2m_nan();
-  if (ia >= 0x7f800000) return a + a;
-  float i; float m = s2m__frexp23(a, &i);
-  float f = m - 1.0f;
-  float s = f * f;
+S2M_HD float s2m__log2_norm(float a, float bias) {
+  const int ia = s2m_f2i(a);
+  const int e = (ia - 0x3f2aaaab) & (int)0xff800000;
+  const float i = s2m_fma((float)e, 1.192092896e-07f, bias);
+  const float f = s2m_i2f(ia - e) - 1.0f;
+  const float s = f * f;
   float r = s2m_fma(s2m__log1p_poly(f) * f, s, -0.5f * s);   /* log1p(f) - f */
   /* (f + r) * log2(e) with log2(e) = hi + lo */
   float t = s2m_fma(f, 1.925963034e-08f, r * 1.442695022e+00f);
   t = s2m_fma(f, 1.442695022e+00f, t);
   return t + i;
+}
+/* zero, negative, denormal, inf, NaN: one cold out-of-line path behind a single range test */
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+__host__ __device__ __noinline__
+#else
+static
+#endif
+float s2m__log_special(float a, int base2) {
+  const int ia = s2m_f2i(a);
+  if ((ia & 0x7fffffff) == 0) return -s2m_inf();
+  if (ia < 0) return s2m_nan();
+  if (ia >= 0x7f800000) return a + a; /* +inf, NaN */
+  a = a * 8388608.0f;                 /* denormal */
+  return base2 ? s2m__log2_norm(a, -23.0f) : s2m__log_norm(a, -23.0f);
+}
+#define S2M__LOG_IS_SPECIAL(a) ((unsigned)(s2m_f2i(a) - 0x00800000) >= 0x7f000000u)
+S2M_HD float s2m_log(float a) {
+  if (S2M__LOG_IS_SPECIAL(a)) return s2m__log_special(a, 0);
+  return s2m__log_norm(a, 0.0f);
+}
+S2M_HD float s2m_log2(float a) {
+  if (S2M__LOG_IS_SPECIAL(a)) return s2m__log_special(a, 1);
+  return s2m__log2_norm(a, 0.0f);
 }
 
 /* log(a) as a double-float hi:lo (a finite, positive); relative error ~1e-9. */
@@ -471,13 +482,11 @@ S2M_HD float s2m__pow_pos(float a, float b) { /* a finite > 0, b finite */
 }
 /* C99 powf semantics (a superset of WGSL/GLSL pow, which leave a < 0 undefined). */
 S2M_HD float s2m_pow(float a, float b) {
-  if (b == 0.0f || a == 1.0f) return 1.0f;
-  if (s2m_isnan(a) || s2m_isnan(b)) return s2m_nan();
-  float aa = s2m_abs(a), ab = s2m_abs(b);
+  const float ab = s2m_abs(b);
   /* Integer exponents up to 8 in magnitude: exponentiation by squaring (<= 5 multiplications,
-   * <= 5 ulp measured; handles signs, zeros and infinities by itself).  This is the strength reduction
-   * shader compilers apply to pow(x, 8.0); when b is a compile-time constant it folds to the
-   * bare multiplication chain. */
+   * <= 5 ulp measured; handles signs, zeros, infinities, a == 1, b == 0 and NaN a by itself, so it
+   * comes before the special-case tests).  This is the strength reduction shader compilers apply
+   * to pow(x, 8.0); when b is a compile-time constant it folds to the bare multiplication chain. */
   if (ab <= 8.0f && truncf(b) == b) {
     int n = (int)ab;
     float r = 1.0f, p = a;
@@ -490,6 +499,9 @@ S2M_HD float s2m_pow(float a, float b) {
     }
     return b < 0.0f ? 1.0f / r : r;
   }
+  if (a == 1.0f) return 1.0f;
+  if (s2m_isnan(a) || s2m_isnan(b)) return s2m_nan();
+  const float aa = s2m_abs(a);
   int b_int = (ab >= 8388608.0f) || (truncf(b) == b);
   int b_odd = b_int && (ab < 16777216.0f) && ((((int)truncf(ab)) & 1) != 0) && (ab >= 1.0f);
   if (ab == s2m_inf()) {
