@@ -9,7 +9,19 @@
 // runs out.  `continue` is then equivalent to `break`, which skips the redundant re-evaluations.
 // examples/mandelmesh.frag has this shape (`r = length(z); if (r > 2.0) continue;`): for the 73 % of
 // grid corners outside the bailout radius it saves 4 of the 5 length() evaluations.
+//
+// pair_sin_cos: within a run of plain statements of one block, sin(e) and cos(e) of a structurally
+// identical pure scalar f32 expression e -- with none of e's variables written in between -- become
+//     vec2 _sc = sincos_pair(e);   ... _sc.x ... _sc.y ...
+// declared before the first of them.  s2m_sincos returns exactly s2m_sin(e) and s2m_cos(e) (one
+// argument reduction and one big-argument test instead of two); rotation code and the spherical
+// coordinates of examples/mandelmesh.frag have this shape.
+#include <cstring>
+#include <map>
 #include <set>
+
+#include <algorithm>
+#include <cstdio>
 
 #include "parse.h"
 
@@ -131,6 +143,163 @@ bool try_loop(Stmt& loop) {
   return changed;
 }
 
+// ---------------------------------------------------------------------------- pair_sin_cos
+bool expr_key(const Expr& e, std::string& key, std::set<const Var*>& reads) {  // false: not a pure, nameable expression
+  char buf[64];
+  switch (e.k) {
+    case Expr::Lit:
+      snprintf(buf, sizeof buf, "L%d:%d:%a:%lld;", (int)e.ty.sk, e.ty.n, e.lit.f[0], (long long)e.lit.i[0]);
+      if (e.ty.n != 1) return false;
+      key += buf;
+      return true;
+    case Expr::VarRef:
+      if (e.var->is_ptr || e.var->by_ref) return false;
+      reads.insert(e.var);
+      snprintf(buf, sizeof buf, "V%d;", e.var->id);
+      key += buf;
+      return true;
+    case Expr::Swizzle:
+      key += "S";
+      for (int k = 0; k < e.nswz; ++k) key += char('0' + e.swz[k]);
+      key += "(";
+      if (!expr_key(*e.args[0], key, reads)) return false;
+      key += ")";
+      return true;
+    case Expr::Unary: case Expr::Binary: case Expr::Call: case Expr::Construct: case Expr::Convert: case Expr::Ternary:
+      if (e.k == Expr::Call && (e.callee == "sin" || e.callee == "cos")) return false;  // keeps the hoisted declarations independent
+      snprintf(buf, sizeof buf, "E%d:%d:%d:%d:", (int)e.k, (int)e.op, (int)e.ty.sk, e.ty.n + 8 * (int)e.ty.k);
+      key += buf;
+      key += e.callee;
+      key += "(";
+      for (const ExprP& a : e.args) { if (!expr_key(*a, key, reads)) return false; key += ","; }
+      key += ")";
+      return true;
+    default: return false;  // UserCall, AddrOf, Deref
+  }
+}
+
+bool has_user_call(const Expr& e) {
+  if (e.k == Expr::UserCall) return true;
+  for (const ExprP& a : e.args) if (has_user_call(*a)) return true;
+  return false;
+}
+
+struct TrigGroup {
+  std::vector<Expr*> calls;
+  std::set<const Var*> reads;
+  size_t first_stmt = 0;
+  bool has_sin = false, has_cos = false;
+};
+
+struct TrigPairing {
+  Module& m;
+  int pairs = 0;
+  explicit TrigPairing(Module& mod) : m(mod) {}
+
+  bool no_globals = false;  // the statement being scanned calls user functions, which may write globals
+
+  void collect(Expr& e, size_t stmt_index, std::map<std::string, TrigGroup>& groups) {
+    for (ExprP& a : e.args) collect(*a, stmt_index, groups);
+    if (e.k != Expr::Call || (e.callee != "sin" && e.callee != "cos") || e.args.size() != 1) return;
+    if (!(e.ty == Type::scalar(Sk::F32)) || !(e.args[0]->ty == Type::scalar(Sk::F32))) return;
+    std::string key;
+    std::set<const Var*> reads;
+    if (!expr_key(*e.args[0], key, reads)) return;
+    if (no_globals)
+      for (const Var* v : reads) if (v->storage == Var::Global) return;
+    auto it = groups.find(key);
+    if (it == groups.end()) {
+      TrigGroup g;
+      g.reads = reads;
+      g.first_stmt = stmt_index;
+      it = groups.emplace(key, std::move(g)).first;
+    }
+    it->second.calls.push_back(&e);
+    (e.callee == "sin" ? it->second.has_sin : it->second.has_cos) = true;
+  }
+
+  // turns the group's calls into swizzles of one pair variable; returns the declaration to insert
+  StmtP materialize(TrigGroup& g) {
+    Var* v = m.new_var();
+    v->name = "_sc" + std::to_string(pairs++);
+    v->ty = Type::vec(Sk::F32, 2);
+    v->storage = Var::Local;
+    v->immutable = true;
+    ExprP call(new Expr());
+    call->k = Expr::Call;
+    call->callee = "sincos_pair";
+    call->ty = v->ty;
+    call->args.push_back(g.calls[0]->args[0]);
+    call->line = g.calls[0]->line;
+    StmtP decl(new Stmt());
+    decl->k = Stmt::VarDecl;
+    decl->var = v;
+    decl->a = call;
+    decl->line = call->line;
+    for (Expr* e : g.calls) {
+      const bool is_sin = e->callee == "sin";
+      ExprP ref(new Expr());
+      ref->k = Expr::VarRef;
+      ref->var = v;
+      ref->ty = v->ty;
+      e->k = Expr::Swizzle;
+      e->callee.clear();
+      e->args.assign(1, ref);
+      e->nswz = 1;
+      e->swz[0] = is_sin ? 0 : 1;
+    }
+    return decl;
+  }
+
+  void block(Stmt& b) {
+    std::map<std::string, TrigGroup> groups;
+    std::vector<std::pair<size_t, StmtP>> inserts;  // (before statement index, declaration)
+    auto finish = [&](TrigGroup& g) { if (g.has_sin && g.has_cos) inserts.emplace_back(g.first_stmt, materialize(g)); };
+    auto flush_all = [&] { for (auto& kv : groups) finish(kv.second); groups.clear(); };
+    auto invalidate = [&](const Var* v) {
+      for (auto it = groups.begin(); it != groups.end();) {
+        if (it->second.reads.count(v)) { finish(it->second); it = groups.erase(it); } else ++it;
+      }
+    };
+    for (size_t k = 0; k < b.body.size(); ++k) {
+      Stmt& st = *b.body[k];
+      const bool plain = st.k == Stmt::VarDecl || st.k == Stmt::Assign || st.k == Stmt::Return || st.k == Stmt::CallStmt;
+      if (!plain) { flush_all(); nested(st); continue; }
+      std::set<const Var*> rd;
+      bool impure = false;
+      if (st.a) reads_of(*st.a, rd, &impure);
+      if (st.b) reads_of(*st.b, rd, &impure);
+      if (impure) { flush_all(); continue; }  // a by-reference user call may write anything it is handed
+      no_globals = (st.a && has_user_call(*st.a)) || (st.b && has_user_call(*st.b));
+      if (no_globals) {  // ... and any call may write globals
+        std::set<const Var*> globals;
+        for (auto& kv : groups) for (const Var* v : kv.second.reads) if (v->storage == Var::Global) globals.insert(v);
+        for (const Var* v : globals) invalidate(v);
+      }
+      if (st.k == Stmt::Assign) {
+        collect(*st.b, k, groups);
+        collect(*st.a, k, groups);  // index expressions on the left are reads too
+        bool partial;
+        if (const Var* v = assigned_var(*st.a, &partial)) invalidate(v); else flush_all();
+      } else {
+        if (st.a) collect(*st.a, k, groups);
+        if (st.k == Stmt::VarDecl) invalidate(st.var);
+      }
+    }
+    flush_all();
+    std::stable_sort(inserts.begin(), inserts.end(), [](const std::pair<size_t, StmtP>& x, const std::pair<size_t, StmtP>& y) { return x.first > y.first; });
+    for (auto& ins : inserts) b.body.insert(b.body.begin() + (long)ins.first, ins.second);
+  }
+
+  void nested(Stmt& s) {
+    if (s.k == Stmt::Block) { block(s); return; }
+    for (StmtP& c : s.body) nested(*c);
+    if (s.then_s) nested(*s.then_s);
+    if (s.else_s) nested(*s.else_s);
+    // for-init / continuing statements and loop conditions are left alone: they are re-evaluated
+  }
+};
+
 void walk(Stmt& s, int* count) {
   for (StmtP& c : s.body) walk(*c, count);
   if (s.then_s) walk(*s.then_s, count);
@@ -142,9 +311,13 @@ void walk(Stmt& s, int* count) {
 
 int optimize_module(Module& m) {
   int count = 0;
-  for (auto& f : m.functions)
-    if (f->body) walk(*f->body, &count);
-  return count;
+  TrigPairing pairing(m);
+  for (auto& f : m.functions) {
+    if (!f->body) continue;
+    walk(*f->body, &count);
+    pairing.nested(*f->body);
+  }
+  return count + pairing.pairs;
 }
 
 }  // namespace s2m_frontend

@@ -247,6 +247,26 @@ S2M_HD float s2m_cos(float x) {
   if (s2m_abs(x) > S2M__TRIG_FAST_MAX) v = s2m__sincos_slow(x, 1);
   return v;
 }
+/* sin and cos of one argument: one reduction, both polynomials, ONE cold big-argument test.  Same
+ * values as s2m_sin(x) and s2m_cos(x); the front-end pairs the calls (optimize.cpp: pair_sin_cos). */
+#if defined(__CUDACC__) || defined(__CUDACC_RTC__)
+__host__ __device__ __noinline__
+#else
+static
+#endif
+void s2m__sincos_slow2(float x, float* s, float* c) {
+  int q; float r = s2m__trig_red_slow(x, &q);
+  *s = s2m__sincos_sel(r, q);
+  *c = s2m__sincos_sel(r, q + 1);
+}
+S2M_HD void s2m_sincos(float x, float* s, float* c) {
+  int q; float r = s2m__trig_red_fast(x, &q);
+  const float sp = s2m__sin_poly(r), cp = s2m__cos_poly(r);
+  const float vs = (q & 1) ? cp : sp, vc = (q & 1) ? sp : cp;
+  *s = (q & 2) ? -vs : vs;
+  *c = ((q + 1) & 2) ? -vc : vc;
+  if (s2m_abs(x) > S2M__TRIG_FAST_MAX) s2m__sincos_slow2(x, s, c);
+}
 S2M_HD float s2m_tan(float x) {
   int q; float r = s2m__trig_red(x, &q);
   float s = r * r;

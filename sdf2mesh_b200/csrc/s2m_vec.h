@@ -142,6 +142,8 @@ S2M_HD ivec4 to_i(const vec4& v) { return mki4(s2m_f2int(v.x), s2m_f2int(v.y), s
 S2M_MAP1(f_abs, s2m_abs)       S2M_MAP1(f_sign, s2m_sign)     S2M_MAP1(f_floor, s2m_floor)
 S2M_MAP1(f_ceil, s2m_ceil)     S2M_MAP1(f_trunc, s2m_trunc)   S2M_MAP1(f_round, s2m_round)
 S2M_MAP1(f_fract, s2m_fract)   S2M_MAP1(f_sqrt, s2m_sqrt)     S2M_MAP1(f_inversesqrt, s2m_inversesqrt)
+/* (sin x, cos x) as a vec2: what optimize.cpp's pair_sin_cos rewrites sin(e) ... cos(e) into */
+S2M_HD vec2 f_sincos_pair(float x) { vec2 r; s2m_sincos(x, &r.x, &r.y); return r; }
 S2M_MAP1(f_sin, s2m_sin)       S2M_MAP1(f_cos, s2m_cos)       S2M_MAP1(f_tan, s2m_tan)
 S2M_MAP1(f_asin, s2m_asin)     S2M_MAP1(f_acos, s2m_acos)     S2M_MAP1(f_atan, s2m_atan)
 S2M_MAP1(f_sinh, s2m_sinh)     S2M_MAP1(f_cosh, s2m_cosh)     S2M_MAP1(f_tanh, s2m_tanh)

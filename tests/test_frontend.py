@@ -345,6 +345,32 @@ def test_continue_to_break_rewrite(built, monkeypatch):
     assert "break;" in load_example_shader("mandelbulb").lower_to_cuda()
 
 
+def test_sin_cos_pairing(built, monkeypatch):
+    """IR optimisation (frontend/optimize.cpp: pair_sin_cos): sin(e) / cos(e) of the same pure argument
+    become one sincos_pair(e) unless a variable of e is written in between; values never change"""
+    cases = [
+        # (source, number of pairs expected)
+        ("fn sdf3d(p: vec3f) -> f32 { let a = p.x * 40000.0; let s = sin(a); let c = cos(a); return s * p.y + c * p.z; }", 1),
+        ("fn sdf3d(p: vec3f) -> f32 { return sin(p.x * 3.0) * p.y + cos(p.x * 3.0) * p.z + sin(p.y) ; }", 1),
+        ("fn sdf3d(p: vec3f) -> f32 { var a = p.x; let s = sin(a); a = a + 1.0; let c = cos(a); return s + c; }", 0),
+        ("fn sdf3d(p: vec3f) -> f32 { var a = p.x; let s = sin(a); if (p.y > 0.0) { a = 2.0 * a; } let c = cos(a); return s + c; }", 0),
+        ("fn sdf3d(p: vec3f) -> f32 { var q = p; q.x = sin(q.y) + cos(q.y); q.y = cos(q.z) - sin(q.z) + cos(q.x) * sin(q.x); return length(q) - 1.0; }", 3),
+        ("fn rot(v: vec2f, a: f32) -> vec2f { return vec2f(cos(a) * v.x - sin(a) * v.y, sin(a) * v.x + cos(a) * v.y); } fn sdf3d(p: vec3f) -> f32 { let q = rot(p.xy, 1.0e6 * p.z); return length(vec3f(q, p.z)) - 1.0; }", 1),
+        ("fn sdf3d(p: vec3f) -> f32 { var acc = 0.0; for (var i = 0; i < 3; i++) { let a = p.x * f32(i + 1); acc = acc + sin(a) * cos(a); } return acc + sin(p.y) + cos(p.z); }", 1),
+    ]
+    pts = points(4.0, 4000)
+    for src, n_pairs in cases:
+        monkeypatch.delenv("S2M_NO_IR_OPT", raising=False)
+        opt = s2m.Sdf3DShader.from_source(src).lower_to_cuda()
+        monkeypatch.setenv("S2M_NO_IR_OPT", "1")
+        plain = s2m.Sdf3DShader.from_source(src).lower_to_cuda()
+        assert "f_sincos_pair" not in plain
+        assert opt.count("= f_sincos_pair(") == n_pairs, src
+        assert f32_equal(host_eval.eval_points(opt, pts), host_eval.eval_points(plain, pts)).all(), src
+    monkeypatch.delenv("S2M_NO_IR_OPT", raising=False)
+    assert load_example_shader("mandelbulb").lower_to_cuda().count("= f_sincos_pair(") == 2
+
+
 def test_matrices(built, tmp_path):
     """mat2/mat3 (GLSL) and mat2x2f/mat3x3<f32> (WGSL): constructors, m*v, v*m, m*m, m[i], transpose"""
     glsl = textwrap.dedent("""\
