@@ -3,7 +3,7 @@
 // driving libsdf2mesh_b200.so through its C ABI.  Same flags, same defaults, same input priority
 // (shadertoy > sdf > glsl, main.rs:200-221), same power-of-two rounding with a warning, same log
 // lines ("Reading SDF from ...", module names, "Mesh has N vertices.", "Mesh written to ...").
-// Additions: --device, --gpus, --all-slices, --exact-dense, --no-normals, --binary-stl, --stats,
+// Additions: --device, --gpus, --all-slices, --watertight, --exact-dense, --no-normals, --binary-stl, --stats,
 // --shadertoy-file, --debug-cuda.
 #include <chrono>
 #include <cstdio>
@@ -62,6 +62,7 @@ void usage(FILE* f) {
       "      --device <N>                     CUDA device ordinal [default: 0]\n"
       "      --gpus <N>                       Split the grid into N z-slabs, one GPU (and host thread) each [default: 1]\n"
       "      --all-slices                     Mesh every z-slice (the reference never reads back the last one)\n"
+      "      --watertight                     --all-slices plus consistent cell corners: no quads lost to rounding\n"
       "      --exact-dense                    Evaluate all 8 corners of every cell, like the reference (slow)\n"
       "      --no-normals                     Skip vertex normals (only PLY output uses them)\n"
       "      --binary-stl                     Write binary instead of ASCII STL\n"
@@ -77,7 +78,7 @@ struct Args {
   unsigned resolution = 0;
   float bounds = 0.0f;
   int device = 0, gpus = 1;
-  bool all_slices = false, exact_dense = false, no_normals = false, binary_stl = false, stats = false;
+  bool watertight = false, all_slices = false, exact_dense = false, no_normals = false, binary_stl = false, stats = false;
 };
 
 bool take_value(int argc, char** argv, int& i, const char* longf, const char* shortf, std::string* out) {
@@ -266,6 +267,7 @@ int main(int argc, char** argv) {
     if (take_value(argc, argv, i, "device", nullptr, &v)) { a.device = atoi(v.c_str()); continue; }
     if (take_value(argc, argv, i, "gpus", nullptr, &v)) { a.gpus = std::max(1, atoi(v.c_str())); continue; }
     if (s == "--all-slices") { a.all_slices = true; continue; }
+    if (s == "--watertight") { a.watertight = true; continue; }
     if (s == "--exact-dense") { a.exact_dense = true; continue; }
     if (s == "--no-normals") { a.no_normals = true; continue; }
     if (s == "--binary-stl") { a.binary_stl = true; continue; }
@@ -286,6 +288,7 @@ int main(int argc, char** argv) {
   if (s2m_params_from_cli(a.resolution, a.bounds, &params, &rounded)) die("bad arguments");
   if (rounded) warn("Resolution should be a power of 2 (actual resolution : " + std::to_string(params.dims[0]) + ")");
   if (a.all_slices) params.flags |= S2M_MESH_ALL_SLICES;
+  if (a.watertight) params.flags |= S2M_MESH_ALL_SLICES | S2M_MESH_CONSISTENT_CORNERS;
   if (a.exact_dense) params.flags |= S2M_MESH_EXACT_DENSE;
   if (a.no_normals) params.flags |= S2M_MESH_NO_NORMALS;
   params.flags |= S2M_MESH_KEEP_INVALID;  // so that the reference's per-quad warnings can be printed

@@ -116,6 +116,10 @@ void s2m_module_free(s2m_module* m);
 #define S2M_MESH_EXACT_DENSE 4u     /* reference-cost mode: every cell is a candidate (8 evaluations per cell) */
 #define S2M_MESH_KEEP_CANDIDATES 8u /* keep the candidate key list in the result (tests) */
 #define S2M_MESH_KEEP_INVALID 32u    /* keep the list of invalid quads (which cell, which edge, which corner is missing) */
+#define S2M_MESH_CONSISTENT_CORNERS 64u /* not the reference's arithmetic: a cell's max corner is the next cell's min corner
+                                          (bmin + size*(i+1) instead of min + size), so neighbouring cells agree on every
+                                          corner value and no quad is lost to 1-ulp disagreements.  With S2M_MESH_ALL_SLICES this is
+                                          the watertight mode (CLI --watertight). */
 #define S2M_MESH_CLASSIFY_FROM_SLAB 16u /* K2 re-reads the f32 slab through shared memory instead of K1's class bit planes */
 
 typedef struct s2m_mesh_params {

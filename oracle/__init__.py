@@ -15,6 +15,7 @@ _LIB = None
 
 SDF_IDS = {"torus": 0, "martin_cube": 1, "p_key": 2, "mandelbulb": 3, "naga_sphere": 4}
 FLAG_ALL_SLICES = 1
+FLAG_CONSISTENT_CORNERS = 64  # not the reference's arithmetic; mirrors S2M_MESH_CONSISTENT_CORNERS
 
 
 def build(force: bool = False) -> str:

@@ -61,16 +61,17 @@ struct Grid {
 };
 
 const uint32_t FLAG_ALL_SLICES = 1u;  // scan every slice, label = true z (no F3 lag)
+const uint32_t FLAG_CONSISTENT_CORNERS = 64u;  // NOT the reference: cell max = next cell's min (S2M_MESH_CONSISTENT_CORNERS)
 const uint64_t MISSING = ~0ull;
 
 // dualcontour.wgsl:22-27
-inline void cell_bounds(const Grid& g, int x, int y, int z, float cmin[3], float cmax[3]) {
+inline void cell_bounds(const Grid& g, int x, int y, int z, float cmin[3], float cmax[3], bool consistent = false) {
   const int pos[3] = {x, y, z};
   for (int a = 0; a < 3; ++a) {
     float v = (float)(g.res[a] - 1u);
     float size = (g.bmax[a] - g.bmin[a]) / v;
     cmin[a] = g.bmin[a] + size * (float)pos[a];
-    cmax[a] = cmin[a] + size;
+    cmax[a] = consistent ? g.bmin[a] + size * (float)(pos[a] + 1) : cmin[a] + size;
   }
 }
 
@@ -83,9 +84,9 @@ inline void cell_change(float a, float b, float x, float y, float z, float out[3
 
 // One invocation of the compute shader entry point (dualcontour.wgsl:161-180).
 // Returns true iff the host would accept the pixel (main.rs:331: p.3 > 0.0).
-inline bool run_cell(int sdf, const Grid& g, int x, int y, int z, Item& it) {
+inline bool run_cell(int sdf, const Grid& g, int x, int y, int z, Item& it, bool consistent = false) {
   float cmin[3], cmax[3];
-  cell_bounds(g, x, y, z, cmin, cmax);
+  cell_bounds(g, x, y, z, cmin, cmax, consistent);
   // cell_new :29-43
   float d[8];
   for (int c = 0; c < 8; ++c) {
@@ -263,7 +264,7 @@ void* oracle_mesh_run(int sdf, const uint32_t res[3], const float bmin[3], const
           rows[(size_t)y].clear();
           for (int x = 0; x < nx; ++x) {
             Item it;
-            if (run_cell(sdf, g, x, y, (int)z, it)) {
+            if (run_cell(sdf, g, x, y, (int)z, it, (flags & FLAG_CONSISTENT_CORNERS) != 0)) {
               it.z = (uint16_t)(all ? z : z + 1);
               rows[(size_t)y].push_back(it);
             }

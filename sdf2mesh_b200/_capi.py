@@ -18,6 +18,7 @@ SRC_SDF3D, SRC_GLSL_FRAGMENT, SRC_WGSL, SRC_CUDA = 0, 1, 2, 3
 COMPILE_ALLOW_FMA = 1
 MESH_ALL_SLICES, MESH_NO_NORMALS, MESH_EXACT_DENSE, MESH_KEEP_CANDIDATES, MESH_CLASSIFY_FROM_SLAB = 1, 2, 4, 8, 16
 MESH_KEEP_INVALID = 32
+MESH_CONSISTENT_CORNERS = 64
 
 
 class S2mError(RuntimeError):

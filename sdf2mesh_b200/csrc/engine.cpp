@@ -725,7 +725,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       const unsigned long long* ck = c->cand_key.as<unsigned long long>() + cand_done;
       unsigned long long nc = n_cand, vbase = vert_done;
       unsigned label_add = r->label_add, halo_below = r->halo ? (r->z_first + 1u) : 0u;
-      unsigned want_normals = (p->flags & S2M_MESH_NO_NORMALS) ? 0u : 1u;
+      unsigned want_normals = ((p->flags & S2M_MESH_NO_NORMALS) ? 0u : 1u) | ((p->flags & S2M_MESH_CONSISTENT_CORNERS) ? 2u : 0u);  // K4a's mode bits
       SlabViewDev sv{c->slab.as<float>(), slab_first_plane, slab_n_planes};
       VertexOutDev vo{c->v_pos.as<float>(), c->v_nrm.as<float>(), c->v_key.as<unsigned long long>(), c->v_nib.as<unsigned char>(),
                       c->cand_vrank.as<unsigned>() + cand_done, status + 2 + k3_tiles, tickets + 1, d_cnt + C_NVERT, d_cnt + C_NHALO};

@@ -55,15 +55,18 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   /* S2M_K1_UNROLL=1 keeps ONE inlined copy of the SDF in the kernel (4x less code); 4 = unrolled
    * (lets independent evaluations overlap; faster for the mandelbulb, measured). */
   float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+  /* One guard per thread, not per corner: a float4 whose first corner is inside the grid is
+   * evaluated whole (at most 3 corners past the last one per row, in the padding nobody reads). */
+  if (active && x4 <= g.res[0]) {
 #if S2M_K1_UNROLL == 1
 #pragma unroll 1
 #else
 #pragma unroll
 #endif
-  for (int k = 0; k < 4; ++k) {
-    const unsigned x = x4 + (unsigned)k;
-    const float val = (active && x <= g.res[0]) ? s2m_sdf(g.bmin[0] + g.size[0] * (float)x, cy, cz) : 0.0f;
-    if (k == 0) v0 = val; else if (k == 1) v1 = val; else if (k == 2) v2 = val; else v3 = val;
+    for (int k = 0; k < 4; ++k) {
+      const float val = s2m_sdf(g.bmin[0] + g.size[0] * (float)(x4 + (unsigned)k), cy, cz);
+      if (k == 0) v0 = val; else if (k == 1) v1 = val; else if (k == 2) v2 = val; else v3 = val;
+    }
   }
   const unsigned long long row = (unsigned long long)pz * g.rows + y;
   if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(v0, v1, v2, v3);
@@ -139,10 +142,13 @@ __device__ __forceinline__ unsigned s2m_item_owner(const unsigned* inc, unsigned
  * evaluations plus the 4 normal taps of cells that get a vertex are spread over all 32 lanes.
  *
  * cand_key = x | y<<16 | z_true<<32 (this launch's slice of the list; cand_vrank likewise).
- * vert_base = vertices emitted by earlier chunks.  label_add = 1 in faithful mode. */
+ * vert_base = vertices emitted by earlier chunks.  label_add = 1 in faithful mode.
+ * mode: bit 0 = compute normals, bit 1 = consistent corners. */
 extern "C" __global__ void __launch_bounds__(S2M_K4_THREADS)
 s2m_k4_vertices(S2mGrid g, const unsigned long long* __restrict__ cand_key, unsigned long long n_cand,
-                unsigned long long vert_base, unsigned label_add, unsigned halo_below, unsigned want_normals, S2mSlabView sv, S2mVertexOut out) {
+                unsigned long long vert_base, unsigned label_add, unsigned halo_below, unsigned mode, S2mSlabView sv, S2mVertexOut out) {
+  const unsigned want_normals = mode & 1u;
+  const bool consistent = (mode & 2u) != 0u;  /* S2M_MESH_CONSISTENT_CORNERS: a cell's max corner IS the next cell's min corner */
   __shared__ unsigned s_scan[33];
   __shared__ unsigned s_tile;
   __shared__ unsigned long long s_base;
@@ -169,13 +175,12 @@ s2m_k4_vertices(S2mGrid g, const unsigned long long* __restrict__ cand_key, unsi
     const unsigned long long key = cand_key[c];
     cx = (unsigned)(key & 0xffffu); cy = (unsigned)((key >> 16) & 0xffffu); cz = (unsigned)(key >> 32);
     /* cell_bounds, dualcontour.wgsl:22-27 */
-    cmin[0] = g.bmin[0] + g.size[0] * (float)cx; cmax[0] = cmin[0] + g.size[0];
-    cmin[1] = g.bmin[1] + g.size[1] * (float)cy; cmax[1] = cmin[1] + g.size[1];
-    cmin[2] = g.bmin[2] + g.size[2] * (float)cz; cmax[2] = cmin[2] + g.size[2];
+    const float nx = g.bmin[0] + g.size[0] * (float)(cx + 1u), ny = g.bmin[1] + g.size[1] * (float)(cy + 1u), nz = g.bmin[2] + g.size[2] * (float)(cz + 1u);
+    cmin[0] = g.bmin[0] + g.size[0] * (float)cx; cmax[0] = consistent ? nx : cmin[0] + g.size[0];
+    cmin[1] = g.bmin[1] + g.size[1] * (float)cy; cmax[1] = consistent ? ny : cmin[1] + g.size[1];
+    cmin[2] = g.bmin[2] + g.size[2] * (float)cz; cmax[2] = consistent ? nz : cmin[2] + g.size[2];
     /* does the reference's `max` coordinate coincide with the slab coordinate of the next corner? */
-    const bool mx = cmax[0] == g.bmin[0] + g.size[0] * (float)(cx + 1u);
-    const bool my = cmax[1] == g.bmin[1] + g.size[1] * (float)(cy + 1u);
-    const bool mz = cmax[2] == g.bmin[2] + g.size[2] * (float)(cz + 1u);
+    const bool mx = cmax[0] == nx, my = cmax[1] == ny, mz = cmax[2] == nz;
     const bool p0 = cz >= sv.first_plane && cz - sv.first_plane < sv.n_planes;          /* plane cz resident */
     const bool p1 = cz + 1u >= sv.first_plane && cz + 1u - sv.first_plane < sv.n_planes; /* plane cz+1 resident */
 #pragma unroll

@@ -276,3 +276,36 @@ def test_invalid_quad_records(ctx, name, res, bounds):
     assert_same(d, o, f"{name} with invalid quads")
     r.free()
     o.free()
+
+
+@pytest.mark.parametrize("name,res,bounds", [("torus", 64, 1.0), ("mandelbulb", 128, 5.0), ("p_key", 64, 20.0), ("martin_cube", 64, 2.0)])
+def test_consistent_corner_mode_matches_oracle(ctx, name, res, bounds):
+    """S2M_MESH_CONSISTENT_CORNERS (with ALL_SLICES: the CLI's --watertight): cell max corner = next
+    cell's min corner.  Not the reference's arithmetic, so the oracle carries the same switch."""
+    flags = s2m.MESH_ALL_SLICES | s2m.MESH_CONSISTENT_CORNERS
+    p, _ = s2m.params_from_cli(res, bounds, flags=flags)
+    r = s2m.mesh_run(ctx, module_for(ctx, name), p)
+    o = oracle.mesh_run(name, res, bounds, flags=oracle.FLAG_ALL_SLICES | oracle.FLAG_CONSISTENT_CORNERS)
+    try:
+        assert_same(r.data(), o, f"{name} {res}^3 consistent corners")
+    finally:
+        r.free()
+        o.free()
+
+
+def test_watertight_mode_closes_the_2048_mesh_cracks(ctx):
+    """at 1024^3 the faithful mandelbulb mesh loses quads to 1-ulp corner disagreements (F4) and the
+    slice lag (F3); the watertight mode loses none, and every mesh edge is then shared by an even
+    number of quads (closed surface inside the box)"""
+    m = module_for(ctx, "mandelbulb")
+    p, _ = s2m.params_from_cli(1024, 5.0, flags=s2m.MESH_ALL_SLICES | s2m.MESH_CONSISTENT_CORNERS | s2m.MESH_NO_NORMALS)
+    r = s2m.mesh_run(ctx, m, p)
+    d = r.data()
+    assert d.n_invalid_quads == 0 and len(d.quads) > 2_000_000
+    q = d.quads.astype(np.int64)
+    e = np.concatenate([np.stack([q[:, i], q[:, (i + 1) % 4]], 1) for i in range(4)])
+    e.sort(axis=1)
+    code = e[:, 0] * (len(d.keys) + 1) + e[:, 1]
+    _, counts = np.unique(code, return_counts=True)
+    assert (counts % 2 == 0).all() and (counts == 2).mean() > 0.99  # one vertex per cell: a few edges are shared by 4
+    r.free()
