@@ -13,6 +13,8 @@ namespace s2m_frontend {
 
 std::string Type::str() const {
   if (k == Void) return "void";
+  if (k == Struct) return sdef->name;
+  if (k == Array) return "array<" + adef->elem.str() + ", " + std::to_string(adef->len) + ">";
   const char* s = sk == Sk::Bool ? "bool" : sk == Sk::I32 ? "i32" : sk == Sk::U32 ? "u32" : sk == Sk::F32 ? "f32"
                   : sk == Sk::AInt ? "abstract-int" : "abstract-float";
   if (k == Scalar) return s;
@@ -65,7 +67,7 @@ ExprP Builder::var_ref(Var* v) {
 bool Builder::is_lvalue(const Expr& e) {
   if (e.k == Expr::VarRef) return !e.var->immutable && !e.var->is_ptr;
   if (e.k == Expr::Deref) return true;
-  if (e.k == Expr::Swizzle) return is_lvalue(*e.args[0]);
+  if (e.k == Expr::Swizzle || e.k == Expr::Member || e.k == Expr::Index) return is_lvalue(*e.args[0]);
   return false;
 }
 
@@ -100,13 +102,25 @@ ConstVal convert_cv(const ConstVal& v, Sk sk) {
 }
 }  // namespace
 
+bool Builder::is_const_expr(const Expr& e) const {
+  ConstVal cv;
+  if (const_eval(e, &cv)) return true;
+  if (e.k == Expr::VarRef) return e.var->storage == Var::ModuleConst;
+  if (e.k == Expr::Construct || e.k == Expr::Member || e.k == Expr::Index || e.k == Expr::Swizzle) {
+    for (const ExprP& a : e.args) if (!is_const_expr(*a)) return false;
+    return true;
+  }
+  return false;
+}
+
 bool Builder::const_eval(const Expr& e, ConstVal* out) const {
-  if (e.ty.is_matrix()) return false;
-  for (const ExprP& a : e.args) if (a && a->ty.is_matrix()) return false;
+  if (e.ty.is_matrix() || e.ty.is_aggregate() || e.k == Expr::Member || e.k == Expr::Index) return false;
+  for (const ExprP& a : e.args) if (a && (a->ty.is_matrix() || a->ty.is_aggregate())) return false;
   switch (e.k) {
     case Expr::Lit: *out = e.lit; return true;
     case Expr::VarRef:
-      if (e.var->has_const) { *out = e.var->cval; return true; }
+      // a mutable module-scope variable has a known INITIAL value, which is not a constant
+      if (e.var->has_const && (e.var->storage == Var::ModuleConst || e.var->immutable)) { *out = e.var->cval; return true; }
       return false;
     case Expr::Convert: {
       ConstVal a;
@@ -328,6 +342,7 @@ ExprP Builder::unary(Op op, ExprP a) {
 
 ExprP Builder::binary(Op op, ExprP a, ExprP b) {
   if (a->ty.is_void() || b->ty.is_void()) error("void operand");
+  if (a->ty.is_aggregate() || b->ty.is_aggregate()) error("operator not defined for " + (a->ty.is_aggregate() ? a->ty.str() : b->ty.str()));
   if (op == Op::And || op == Op::Or) {
     if (!a->ty.is_bool() || !b->ty.is_bool() || !a->ty.is_scalar() || !b->ty.is_scalar())
       error("logical operator needs bool operands, found " + a->ty.str() + " and " + b->ty.str());
@@ -399,6 +414,7 @@ ExprP Builder::binary(Op op, ExprP a, ExprP b) {
 
 ExprP Builder::ternary(ExprP c, ExprP t, ExprP f) {
   if (!c->ty.is_bool() || !c->ty.is_scalar()) error("?: condition must be a scalar bool");
+  if (t->ty.is_void() || f->ty.is_void()) error("void operand of ?:");
   if (t->ty != f->ty) {
     if (t->ty.is_abstract() || (lang == Lang::Glsl && f->ty.sk == Sk::F32 && t->ty.sk != Sk::F32)) t = coerce(t, f->ty, "?: operand");
     else f = coerce(f, t->ty, "?: operand");
@@ -408,8 +424,42 @@ ExprP Builder::ternary(ExprP c, ExprP t, ExprP f) {
   return e;
 }
 
+ExprP Builder::member(ExprP base, const std::string& name) {
+  if (!base->ty.is_struct()) return swizzle(base, name);
+  const int f = base->ty.sdef->field(name);
+  if (f < 0) error("struct " + base->ty.sdef->name + " has no member '" + name + "'");
+  ExprP e = mk(Expr::Member, base->ty.sdef->field_types[(size_t)f]);
+  e->args.push_back(base);
+  e->nswz = 1;
+  e->swz[0] = f;
+  return e;
+}
+
+ExprP Builder::index(ExprP base, ExprP idx) {
+  if (!(base->ty.is_vector() || base->ty.is_matrix() || base->ty.is_array())) error("cannot index a value of type " + base->ty.str());
+  idx = concretize(idx);
+  if (!idx->ty.is_scalar() || !(idx->ty.sk == Sk::I32 || idx->ty.sk == Sk::U32)) error("index must be an integer scalar, found " + idx->ty.str());
+  const int len = base->ty.is_array() ? base->ty.adef->len : base->ty.n;
+  ConstVal cv;
+  if (const_eval(*idx, &cv)) {
+    if (cv.i[0] < 0 || cv.i[0] >= len) error("index " + std::to_string(cv.i[0]) + " out of range for " + base->ty.str());
+    if (base->ty.is_matrix()) return matrix_column(base, (int)cv.i[0]);
+    if (base->ty.is_vector()) return swizzle(base, std::string(1, "xyzw"[cv.i[0]]));
+  }
+  const Type rt = base->ty.is_array() ? base->ty.adef->elem : base->ty.is_matrix() ? Type::vec(Sk::F32, base->ty.n) : Type::scalar(base->ty.sk);
+  ExprP e = mk(Expr::Index, rt);
+  e->args = {base, idx};
+  return e;
+}
+
+ExprP Builder::array_length(ExprP base) {
+  if (!base->ty.is_array()) error(".length() of a non-array");
+  return lit_int(base->ty.adef->len, Sk::I32);
+}
+
 ExprP Builder::swizzle(ExprP base, const std::string& comps) {
   if (base->ty.is_void()) error("swizzle of void");
+  if (base->ty.is_aggregate()) error(base->ty.str() + " has no member '" + comps + "'");
   if (base->ty.is_matrix()) error("matrices have no named members; use m[i]");
   if (comps.empty() || comps.size() > 4) error("bad swizzle ." + comps);
   static const char* sets[] = {"xyzw", "rgba", "stpq"};
@@ -450,6 +500,26 @@ ExprP Builder::matrix_column(ExprP base, int col) {
 
 ExprP Builder::construct(Type target, bool infer_sk, std::vector<ExprP> args) {
   for (const ExprP& a : args) if (a->ty.is_void()) error("void constructor argument");
+  if (target.is_struct()) {
+    const StructDef& d = *target.sdef;
+    if (!args.empty()) {  // S() is the zero value
+      if (args.size() != d.field_types.size()) error("constructor of " + d.name + " takes " + std::to_string(d.field_types.size()) + " arguments");
+      for (size_t i = 0; i < args.size(); ++i) args[i] = coerce(args[i], d.field_types[i], "struct constructor");
+    }
+    ExprP e = mk(Expr::Construct, target);
+    e->args = args;
+    return e;
+  }
+  if (target.is_array()) {
+    if (!args.empty()) {
+      if ((int)args.size() != target.adef->len) error("constructor of " + target.str() + " takes " + std::to_string(target.adef->len) + " elements");
+      for (ExprP& a : args) a = coerce(a, target.adef->elem, "array constructor");
+    }
+    ExprP e = mk(Expr::Construct, target);
+    e->args = args;
+    return e;
+  }
+  for (const ExprP& a : args) if (a->ty.is_aggregate()) error("cannot construct " + target.str() + " from " + a->ty.str());
   if (target.is_matrix()) {
     const int n = target.n;
     for (ExprP& a : args) {

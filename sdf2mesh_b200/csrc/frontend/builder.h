@@ -29,6 +29,10 @@ class Builder {
   ExprP ternary(ExprP c, ExprP t, ExprP f);
   ExprP swizzle(ExprP base, const std::string& comps);
   ExprP matrix_column(ExprP base, int col);  // m[i]
+  ExprP member(ExprP base, const std::string& name);   // struct field or vector swizzle
+  ExprP index(ExprP base, ExprP idx);                  // a[i], v[i], m[i] (constant or dynamic index)
+  ExprP array_length(ExprP base);                      // GLSL a.length()
+  Module* module = nullptr;                            // for interning array types
   ExprP construct(Type target, bool infer_sk, std::vector<ExprP> args);  // vecN(...) / scalar casts
   ExprP call_builtin(const std::string& name, std::vector<ExprP> args);  // returns null if not a builtin
   ExprP call_user(Function* fn, std::vector<ExprP> args);
@@ -41,6 +45,7 @@ class Builder {
   // Make e concrete: abstract float -> f32, abstract int -> i32 (WGSL default concretisation).
   ExprP concretize(ExprP e);
   bool const_eval(const Expr& e, ConstVal* out) const;
+  bool is_const_expr(const Expr& e) const;  // const_eval-able, or an aggregate built from such values
   static bool is_lvalue(const Expr& e);
 
  private:

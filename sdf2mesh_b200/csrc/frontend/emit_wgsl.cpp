@@ -24,9 +24,16 @@ class WgslWriter {
   std::string run() {
     for (const auto& v : m_.vars) used_.insert(v->name);
     for (const auto& f : m_.functions) used_.insert(f->name);
+    for (const auto& sd : m_.structs) {
+      out_ << "struct " << sd->name << " {\n";
+      for (size_t i = 0; i < sd->field_names.size(); ++i) out_ << "    " << sd->field_names[i] << ": " << type_name(sd->field_types[i]) << ",\n";
+      out_ << "}\n\n";
+    }
     for (const Var* g : m_.globals) {
       if (g->storage == Var::ModuleConst && g->has_const) {
         out_ << "const " << g->name << ": " << type_name(g->ty) << " = " << const_lit(g->cval) << ";\n";
+      } else if (g->storage == Var::ModuleConst && (g->ty.is_aggregate() || g->ty.is_matrix()) && m_.global_init.count(g)) {
+        out_ << "const " << g->name << ": " << type_name(g->ty) << " = " << expr(*m_.global_init.at(g)) << ";\n";
       } else {
         out_ << "var<private> " << g->name << ": " << type_name(g->ty);
         auto it = m_.global_init.find(g);
@@ -55,6 +62,8 @@ class WgslWriter {
   static std::string type_name(const Type& t) {
     const char* s = t.sk == Sk::F32 ? "f32" : t.sk == Sk::I32 ? "i32" : t.sk == Sk::U32 ? "u32" : "bool";
     if (t.is_void()) return "void";
+    if (t.is_struct()) return t.sdef->name;
+    if (t.is_array()) return "array<" + type_name(t.adef->elem) + ", " + std::to_string(t.adef->len) + ">";
     if (t.is_matrix()) return "mat" + std::to_string(t.n) + "x" + std::to_string(t.n) + "<f32>";
     if (t.is_scalar()) return s;
     return "vec" + std::to_string(t.n) + "<" + s + ">";
@@ -83,6 +92,7 @@ class WgslWriter {
     }
   }
   static std::string const_lit(const ConstVal& cv) {
+    if (cv.ty.is_aggregate() || cv.ty.is_matrix()) return type_name(cv.ty) + "()";  // zero value
     if (cv.ty.is_scalar()) return scalar_lit(cv, 0);
     std::string s = type_name(cv.ty) + "(";
     for (int c = 0; c < cv.ty.n; ++c) s += (c ? ", " : "") + scalar_lit(cv, c);
@@ -169,6 +179,8 @@ class WgslWriter {
         for (int i = 0; i < e.nswz; ++i) s += "xyzw"[e.swz[i]];
         return s;
       }
+      case Expr::Member: return expr(*e.args[0]) + "." + e.args[0]->ty.sdef->field_names[(size_t)e.swz[0]];
+      case Expr::Index: return expr(*e.args[0]) + "[" + expr(*e.args[1]) + "]";
       case Expr::Convert: return type_name(e.ty) + "(" + expr(*e.args[0]) + ")";
       case Expr::AddrOf: return "&" + expr(*e.args[0]);
       case Expr::Deref: return "(*" + expr(*e.args[0]) + ")";
@@ -289,6 +301,26 @@ class WgslWriter {
         indent(d);
         out_ << "}\n";
         break;
+      case Stmt::Switch: {
+        out_ << "switch " << expr(*s.a) << " {\n";
+        const bool uns = s.a->ty.sk == Sk::U32;
+        bool has_default = false;
+        for (const StmtP& c : s.body) {
+          indent(d + 1);
+          out_ << (c->case_values.empty() ? "default" : "case ");
+          for (size_t i = 0; i < c->case_values.size(); ++i) out_ << (i ? ", " : "") << (uns ? std::to_string((uint32_t)c->case_values[i]) + "u" : std::to_string((int32_t)c->case_values[i]) + "i");
+          if (c->is_default && !c->case_values.empty()) out_ << ", default";
+          has_default = has_default || c->is_default;
+          out_ << ": ";
+          block(*c->body[0], d + 1);
+          out_ << "\n";
+        }
+        if (!has_default) { indent(d + 1); out_ << "default: {\n"; indent(d + 1); out_ << "}\n"; }
+        indent(d);
+        out_ << "}\n";
+        break;
+      }
+      case Stmt::Case: throw FrontendError(4, "internal: case outside of a switch");
       case Stmt::Loop:
         out_ << "loop {\n";
         for (const StmtP& c : s.body[0]->body) stmt(*c, d + 1);

@@ -29,10 +29,14 @@ namespace s2m_frontend {
 
 namespace {
 
+// functions that (transitively) assign module-scope variables: calling one is a side effect
+thread_local const std::set<const Function*>* g_state_writers = nullptr;
+
 void reads_of(const Expr& e, std::set<const Var*>& out, bool* impure) {
   if (e.k == Expr::VarRef) out.insert(e.var);
   if (e.k == Expr::UserCall) {
     for (const Var* p : e.fn->params) if (p->by_ref) *impure = true;  // may write through the reference
+    if (g_state_writers && g_state_writers->count(e.fn)) *impure = true;
   }
   if (e.k == Expr::AddrOf) *impure = true;
   for (const ExprP& a : e.args) reads_of(*a, out, impure);
@@ -41,11 +45,20 @@ void reads_of(const Expr& e, std::set<const Var*>& out, bool* impure) {
 const Var* assigned_var(const Expr& lhs, bool* partial) {
   const Expr* e = &lhs;
   *partial = false;
-  while (e->k == Expr::Swizzle || e->k == Expr::Deref) {
-    if (e->k == Expr::Swizzle) *partial = true;
+  while (e->k == Expr::Swizzle || e->k == Expr::Deref || e->k == Expr::Member || e->k == Expr::Index) {
+    if (e->k != Expr::Deref) *partial = true;
     e = e->args[0].get();
   }
   return e->k == Expr::VarRef ? e->var : nullptr;
+}
+
+// variables read by the index expressions of an assignment target (a[i].x = ...)
+void lhs_index_reads(const Expr& lhs, std::set<const Var*>& out, bool* impure) {
+  const Expr* e = &lhs;
+  while (e->k == Expr::Swizzle || e->k == Expr::Deref || e->k == Expr::Member || e->k == Expr::Index) {
+    if (e->k == Expr::Index) reads_of(*e->args[1], out, impure);
+    e = e->args[0].get();
+  }
 }
 
 bool is_bare_continue(const Stmt& s) {
@@ -111,6 +124,7 @@ bool try_loop(Stmt& loop) {
         if (p.k == Stmt::VarDecl) { if (p.a) reads_of(*p.a, rd, &imp); }
         else {
           reads_of(*p.b, rd, &imp);
+          lhs_index_reads(*p.a, rd, &imp);
           bool partial = false;
           const Var* v = assigned_var(*p.a, &partial);
           if (!v || v->by_ref || v->storage == Var::Global) ok = false;
@@ -165,7 +179,12 @@ bool expr_key(const Expr& e, std::string& key, std::set<const Var*>& reads) {  /
       if (!expr_key(*e.args[0], key, reads)) return false;
       key += ")";
       return true;
-    case Expr::Unary: case Expr::Binary: case Expr::Call: case Expr::Construct: case Expr::Convert: case Expr::Ternary:
+    case Expr::Member:
+      key += "M" + std::to_string(e.swz[0]) + "(";
+      if (!expr_key(*e.args[0], key, reads)) return false;
+      key += ")";
+      return true;
+    case Expr::Unary: case Expr::Binary: case Expr::Call: case Expr::Construct: case Expr::Convert: case Expr::Ternary: case Expr::Index:
       if (e.k == Expr::Call && (e.callee == "sin" || e.callee == "cos")) return false;  // keeps the hoisted declarations independent
       snprintf(buf, sizeof buf, "E%d:%d:%d:%d:", (int)e.k, (int)e.op, (int)e.ty.sk, e.ty.n + 8 * (int)e.ty.k);
       key += buf;
@@ -309,8 +328,46 @@ void walk(Stmt& s, int* count) {
 
 }  // namespace
 
+void callees_of(const Expr& e, std::set<const Function*>& out) {
+  if (e.k == Expr::UserCall) out.insert(e.fn);
+  for (const ExprP& a : e.args) callees_of(*a, out);
+}
+void callees_of(const Stmt& s, std::set<const Function*>& out) {
+  if (s.a) callees_of(*s.a, out);
+  if (s.b) callees_of(*s.b, out);
+  if (s.break_if) callees_of(*s.break_if, out);
+  for (const StmtP& c : s.body) callees_of(*c, out);
+  if (s.init) callees_of(*s.init, out);
+  if (s.cont) callees_of(*s.cont, out);
+  if (s.then_s) callees_of(*s.then_s, out);
+  if (s.else_s) callees_of(*s.else_s, out);
+}
+
+std::set<const Function*> state_writers(const Module& m) {
+  std::set<const Function*> w;
+  std::map<const Function*, std::set<const Function*>> calls;
+  for (const auto& f : m.functions) {
+    if (!f->body) continue;
+    std::set<const Var*> written;
+    writes_anywhere(*f->body, written);
+    for (const Var* v : written) if (v->storage == Var::Global) w.insert(f.get());
+    callees_of(*f->body, calls[f.get()]);
+  }
+  for (bool changed = true; changed;) {
+    changed = false;
+    for (const auto& kv : calls)
+      if (!w.count(kv.first))
+        for (const Function* c : kv.second)
+          if (w.count(c)) { w.insert(kv.first); changed = true; break; }
+  }
+  return w;
+}
+
 int optimize_module(Module& m) {
   int count = 0;
+  const std::set<const Function*> writers = state_writers(m);
+  g_state_writers = &writers;
+  struct Reset { ~Reset() { g_state_writers = nullptr; } } reset;
   TrigPairing pairing(m);
   for (auto& f : m.functions) {
     if (!f->body) continue;

@@ -45,13 +45,68 @@ class GlslParser : public ParserBase {
     if (peek().k != Token::Ident) return false;
     Type t;
     const std::string& s = peek().text;
+    if (structs.count(s) && !lookup(s)) return true;
     return type_from_name(s, &t) || s.compare(0, 3, "mat") == 0 || s == "double" || s.compare(0, 4, "dvec") == 0 || s.compare(0, 7, "sampler") == 0;
   }
-  Type parse_type() {
+  // `[N]` / `[]` after a type or a declarator name.  *unsized is set for `[]` (length from the initializer).
+  Type parse_array_suffix(Type base, bool* unsized) {
+    if (unsized) *unsized = false;
+    if (!is_punct("[")) return base;
+    advance();
+    if (accept("]")) {
+      if (!unsized) b.error("array needs a length here");
+      *unsized = true;
+      if (is_punct("[")) b.unsupported("arrays of arrays");
+      return base;
+    }
+    const int len = array_len(parse_expr());
+    expect("]");
+    if (is_punct("[")) b.unsupported("arrays of arrays");
+    return mod->array_of(base, len);
+  }
+  Type parse_type(bool* unsized = nullptr) {
     const std::string s = expect_ident("a type");
     Type t;
-    if (type_from_name(s, &t)) return t;
-    b.unsupported("GLSL type '" + s + "'");
+    if (structs.count(s)) t = Type::struct_(structs[s]);
+    else if (!type_from_name(s, &t)) b.unsupported("GLSL type '" + s + "'");
+    return parse_array_suffix(t, unsized);
+  }
+  // declared type of one declarator: the base type plus the declarator's own array suffix;
+  // an unsized array takes its length from the initializer
+  Type declarator_type(Type base, bool base_unsized, ExprP* init, bool allow_init) {
+    bool unsized = base_unsized;
+    Type ty = base;
+    if (is_punct("[")) {
+      if (base.is_array() || base_unsized) b.unsupported("arrays of arrays");
+      ty = parse_array_suffix(base, &unsized);
+    }
+    if (allow_init && accept("=")) *init = parse_assignment_expr();
+    if (unsized) {
+      if (!*init || !(*init)->ty.is_array() || !((*init)->ty.adef->elem == base)) b.error("unsized array needs an array initializer of the same element type");
+      ty = (*init)->ty;
+    }
+    return ty;
+  }
+  void parse_struct() {  // struct Name { float a; vec3 b, c; float d[3]; };
+    advance();
+    StructDef* d = declare_struct(expect_ident("struct name"));
+    expect("{");
+    while (!is_punct("}")) {
+      parse_qualifiers();
+      bool unsized = false;
+      Type base = parse_type(&unsized);
+      if (unsized) b.error("unsized array member");
+      for (;;) {
+        const std::string fname = expect_ident("a member name");
+        add_field(d, fname, is_punct("[") ? parse_array_suffix(base, nullptr) : base);
+        if (!accept(",")) break;
+      }
+      expect(";");
+    }
+    expect("}");
+    if (d->field_names.empty()) b.error("struct " + d->name + " has no members");
+    if (!is_punct(";")) b.unsupported("variable declared together with its struct");
+    expect(";");
   }
 
   struct Qualifiers { bool is_const = false, uniform = false, in = false, out = false, inout = false; };
@@ -79,19 +134,23 @@ class GlslParser : public ParserBase {
   void parse_external_declaration(bool* have_main) {
     b.cur_line = peek().line;
     if (accept_ident("precision")) { while (!is_punct(";") && peek().k != Token::End) advance(); expect(";"); return; }
-    if (is_ident("struct")) b.unsupported("struct declarations");
+    if (is_ident("struct")) { parse_struct(); return; }
     Qualifiers q = parse_qualifiers();
     if (is_ident("buffer") || is_ident("shared")) b.unsupported("storage qualifier " + peek().text);
     if (accept(";")) return;  // e.g. `layout(...) in;`
-    Type ty = parse_type();
+    bool unsized = false;
+    Type base = parse_type(&unsized);
     const std::string name = expect_ident("a name");
-    if (is_punct("(")) { parse_function(ty, name, have_main); return; }
+    if (is_punct("(")) {
+      if (unsized) b.error("function returning an unsized array");
+      parse_function(base, name, have_main);
+      return;
+    }
     // global variable(s)
     std::string n = name;
     for (;;) {
-      if (is_punct("[")) b.unsupported("arrays");
       ExprP init;
-      if (accept("=")) init = parse_assignment_expr();
+      const Type ty = declarator_type(base, unsized, &init, true);
       declare_global(q, ty, n, init);
       if (!accept(",")) break;
       n = expect_ident("a name");
@@ -128,7 +187,7 @@ class GlslParser : public ParserBase {
       if (t.is_void()) b.error("parameter of type void");
       std::string pn = "_p" + std::to_string(params.size());
       if (peek().k == Token::Ident) pn = advance().text;
-      if (is_punct("[")) b.unsupported("array parameters");
+      if (is_punct("[")) { if (t.is_array()) b.unsupported("arrays of arrays"); t = parse_array_suffix(t, nullptr); }
       Var* v = mod->new_var();
       v->name = pn; v->ty = t; v->storage = Var::Param;
       v->immutable = q.is_const;
@@ -209,13 +268,14 @@ class GlslParser : public ParserBase {
 
   void parse_declaration_into(StmtP blk) {
     Qualifiers q = parse_qualifiers();
-    Type ty = parse_type();
-    if (ty.is_void()) b.error("variable of type void");
+    bool unsized = false;
+    Type base = parse_type(&unsized);
+    if (base.is_void()) b.error("variable of type void");
     for (;;) {
       const std::string name = expect_ident("a variable name");
-      if (is_punct("[")) b.unsupported("arrays");
       ExprP init;
-      if (accept("=")) init = b.coerce(parse_assignment_expr(), ty, "initializer");
+      const Type ty = declarator_type(base, unsized, &init, true);
+      if (init) init = b.coerce(init, ty, "initializer");
       Var* v = declare(name, ty, Var::Local);
       v->immutable = q.is_const;
       if (q.is_const && !init) b.error("const '" + name + "' needs an initializer");
@@ -272,7 +332,7 @@ class GlslParser : public ParserBase {
     b.cur_line = peek().line;
     if (accept(";")) return;
     if (is_punct("{")) { blk->body.push_back(parse_compound(true)); return; }
-    if (is_ident("const") || is_ident("highp") || is_ident("mediump") || is_ident("lowp") || (at_type() && peek(1).k == Token::Ident)) {
+    if (is_ident("const") || is_ident("highp") || is_ident("mediump") || is_ident("lowp") || (at_type() && (peek(1).k == Token::Ident || is_punct("[", 1)))) {
       parse_declaration_into(blk);
       expect(";");
       return;
@@ -293,7 +353,7 @@ class GlslParser : public ParserBase {
       push_scope();
       expect("(");
       if (!is_punct(";")) {
-        if (at_type() && peek(1).k == Token::Ident) {
+        if (at_type() && (peek(1).k == Token::Ident || is_punct("[", 1))) {
           StmtP tmp = mk_stmt(Stmt::Block);
           parse_declaration_into(tmp);
           if (tmp->body.size() != 1) b.unsupported("several declarators in a for-init");
@@ -339,13 +399,59 @@ class GlslParser : public ParserBase {
       blk->body.push_back(s);
       return;
     }
-    if (accept_ident("break")) { if (!loop_depth) b.error("break outside of a loop"); expect(";"); blk->body.push_back(mk_stmt(Stmt::Break)); return; }
+    if (accept_ident("break")) { if (!loop_depth && !switch_depth) b.error("break outside of a loop or switch"); expect(";"); blk->body.push_back(mk_stmt(Stmt::Break)); return; }
     if (accept_ident("continue")) { if (!loop_depth) b.error("continue outside of a loop"); expect(";"); blk->body.push_back(mk_stmt(Stmt::Continue)); return; }
     if (accept_ident("discard")) { expect(";"); blk->body.push_back(mk_stmt(Stmt::Discard)); return; }
-    if (is_ident("switch")) b.unsupported("switch statements");
+    if (accept_ident("switch")) { blk->body.push_back(parse_switch()); return; }
     StmtP s = parse_expression_statement();
     expect(";");
     blk->body.push_back(s);
+  }
+
+  static bool ends_flow(const Stmt& blk) {  // last statement leaves the case for good
+    if (blk.body.empty()) return false;
+    const Stmt::K k = blk.body.back()->k;
+    return k == Stmt::Break || k == Stmt::Return || k == Stmt::Continue || k == Stmt::Discard;
+  }
+  // switch (e) { case 1: case 2: ...; break; default: ... }  -- labels group into cases; a case
+  // that runs into the next label without break/return/continue/discard would fall through,
+  // which the IR (like WGSL) does not model.
+  StmtP parse_switch() {
+    StmtP sw = mk_stmt(Stmt::Switch);
+    expect("(");
+    sw->a = switch_selector(parse_expr());
+    expect(")");
+    expect("{");
+    ++switch_depth;
+    push_scope();
+    StmtP cur;
+    while (!is_punct("}")) {
+      if (peek().k == Token::End) perr("unterminated switch");
+      if (is_ident("case") || is_ident("default")) {
+        const bool starts_new = !cur || !cur->body[0]->body.empty();
+        if (starts_new) {
+          if (cur && !ends_flow(*cur->body[0])) b.unsupported("switch case that falls through into the next one");
+          cur = mk_stmt(Stmt::Case);
+          cur->body.push_back(mk_stmt(Stmt::Block));
+          sw->body.push_back(cur);
+        }
+        if (accept_ident("default")) cur->is_default = true;
+        else { advance(); cur->case_values.push_back(case_value(parse_binary(0), sw->a->ty)); }
+        expect(":");
+        continue;
+      }
+      if (!cur) perr("statement before the first case label");
+      parse_statement_into(cur->body[0]);
+    }
+    expect("}");
+    pop_scope();
+    --switch_depth;
+    for (const StmtP& c : sw->body) {  // the closing break of a case is implied by the IR
+      std::vector<StmtP>& bd = c->body[0]->body;
+      if (!bd.empty() && bd.back()->k == Stmt::Break) bd.pop_back();
+    }
+    check_cases(*sw);
+    return sw;
   }
 
   StmtP parse_if() {
@@ -425,20 +531,21 @@ class GlslParser : public ParserBase {
     for (;;) {
       if (accept(".")) {
         const std::string m = expect_ident("a member name");
-        if (is_punct("(")) b.unsupported("method call ." + m + "()");
-        e = b.swizzle(e, m);
+        if (is_punct("(")) {
+          if (m != "length" || !e->ty.is_array()) b.unsupported("method call ." + m + "()");
+          advance();
+          expect(")");
+          e = b.array_length(e);
+          continue;
+        }
+        e = b.member(e, m);
         continue;
       }
       if (is_punct("[")) {
         advance();
         ExprP idx = parse_expr();
         expect("]");
-        ConstVal cv;
-        if (!e->ty.is_vector() && !e->ty.is_matrix()) b.unsupported("indexing of non-vector values");
-        if (!idx->ty.is_int() || !b.const_eval(*idx, &cv)) b.unsupported("dynamic vector / matrix indexing");
-        if (cv.i[0] < 0 || cv.i[0] >= e->ty.n) b.error("index out of range");
-        if (e->ty.is_matrix()) e = b.matrix_column(e, (int)cv.i[0]);
-        else e = b.swizzle(e, std::string(1, "xyzw"[cv.i[0]]));
+        e = b.index(e, idx);
         continue;
       }
       break;
@@ -474,6 +581,23 @@ class GlslParser : public ParserBase {
     const std::string name = t.text;
     if (name == "true" || name == "false") { advance(); return b.lit_bool(name == "true"); }
     Type ty;
+    const bool type_like = (structs.count(name) && !lookup(name)) || type_from_name(name, &ty);
+    if (type_like && is_punct("[", 1)) {  // array constructor: float[3](a, b, c) / vec2[](a, b)
+      bool unsized = false;
+      Type at = parse_type(&unsized);
+      if (!is_punct("(")) perr("expected '(' after an array type");
+      std::vector<ExprP> args = parse_args();
+      if (unsized) {
+        if (args.empty()) b.error("cannot infer the length of an empty array constructor");
+        at = mod->array_of(at, (int)args.size());
+      }
+      return b.construct(at, false, args);
+    }
+    if (structs.count(name) && !lookup(name) && is_punct("(", 1)) {
+      advance();
+      std::vector<ExprP> args = parse_args();
+      return b.construct(Type::struct_(structs[name]), false, args);
+    }
     if (is_punct("(", 1) && (type_from_name(name, &ty) || name.compare(0, 3, "mat") == 0)) {
       if (!type_from_name(name, &ty)) b.unsupported("matrix type " + name + " (only square matrices)");
       advance();

@@ -17,15 +17,18 @@ class WgslParser : public ParserBase {
     toks = Lexer(src, lo).run();
     push_scope();
     collect_module_scope();
-    resolve_globals();
+    resolve_globals();      // constants, variables and struct bodies (order-independent)
+    resolve_signatures();
     for (auto& fb : fn_bodies_) parse_function_body(fb);
   }
 
  private:
   std::set<std::string> builtin_fns_;
-  struct GlobalDecl { size_t tok; bool done = false; };
+  struct GlobalDecl { size_t tok; bool done = false; StructDef* sdef = nullptr; };
   struct FnBody { Function* fn; size_t tok; };
   std::vector<GlobalDecl> global_decls_;
+  struct FnSig { Function* fn; size_t tok; };
+  std::vector<FnSig> fn_sigs_;             // token index of each non-entry function's `(`
   std::vector<FnBody> fn_bodies_;
   std::map<std::string, Type> aliases_;
 
@@ -34,7 +37,7 @@ class WgslParser : public ParserBase {
     static const std::set<std::string> names = {"f32", "i32", "u32", "bool", "vec2", "vec3", "vec4", "vec2f", "vec3f", "vec4f",
                                                 "vec2i", "vec3i", "vec4i", "vec2u", "vec3u", "vec4u", "vec2h", "vec3h", "vec4h", "f16",
                                                 "mat2x2", "mat3x3", "mat4x4", "mat2x2f", "mat3x3f", "mat4x4f"};
-    return names.count(s) || aliases_.count(s);
+    return names.count(s) || aliases_.count(s) || structs.count(s) || s == "array";
   }
   static bool scalar_kind(const std::string& s, Sk* sk) {
     if (s == "f32") { *sk = Sk::F32; return true; }
@@ -92,7 +95,15 @@ class WgslParser : public ParserBase {
       }
       b.unsupported("matrix type " + name + " (only square f32 matrices)");
     }
-    if (name == "array") b.unsupported("array types");
+    if (name == "array") {
+      if (!accept("<")) perr("array type needs an element type (array<T, N>)");
+      Type el = parse_type();
+      if (!accept(",")) b.unsupported("runtime-sized arrays");
+      const int len = array_len(parse_binary(9));  // additive level: `>` closes the template list
+      expect_close_angle();
+      return mod->array_of(el, len);
+    }
+    if (structs.count(name)) return Type::struct_(structs[name]);
     if (name == "atomic" || name.compare(0, 7, "texture") == 0 || name == "sampler") b.unsupported("type " + name);
     b.unsupported("user-defined type '" + name + "'");
   }
@@ -137,7 +148,14 @@ class WgslParser : public ParserBase {
         expect(";");
         continue;
       }
-      if (is_ident("struct")) b.unsupported("struct declarations");
+      if (is_ident("struct")) {
+        GlobalDecl gd{pos};
+        advance();
+        gd.sdef = declare_struct(expect_ident("struct name"));
+        global_decls_.push_back(gd);
+        skip_braces();
+        continue;
+      }
       if (is_ident("enable") || is_ident("requires") || is_ident("diagnostic")) {
         while (!is_punct(";") && peek().k != Token::End) advance();
         expect(";");
@@ -158,39 +176,50 @@ class WgslParser : public ParserBase {
     fn->name = name; fn->line = peek().line; fn->is_entry = entry;
     fn->builtin_lib = builtin_fns_.count(name) > 0 && name != "sdf3d_normal";
     functions[name] = fn;
-    expect("(");
-    while (!is_punct(")")) {
-      skip_attributes();
-      const std::string pn = expect_ident("parameter name");
-      expect(":");
-      skip_attributes();
-      if (entry) {  // entry-point signatures may use types we do not model; skip them
-        int depth = 0;
-        while (peek().k != Token::End && !(depth == 0 && (is_punct(",") || is_punct(")")))) {
-          if (is_punct("<") || is_punct("(")) ++depth;
-          if (is_punct(">") || is_punct(")")) --depth;
-          advance();
-        }
-      } else {
-        bool is_ptr = false;
-        Type t = parse_type(nullptr, &is_ptr);
-        Var* v = mod->new_var();
-        v->name = pn; v->ty = t; v->storage = Var::Param; v->immutable = true;
-        v->is_ptr = is_ptr; v->by_ref = is_ptr;
-        fn->params.push_back(v);
-      }
-      if (!accept(",")) break;
-    }
-    expect(")");
-    fn->ret = Type::void_();
-    if (accept("->")) {
-      skip_attributes();
-      if (entry) { while (!is_punct("{") && peek().k != Token::End) advance(); }
-      else fn->ret = parse_type();
-    }
+    // types in the signature may name structs / constants declared further down: parse it later
+    fn_sigs_.push_back({fn, pos});
+    while (!is_punct("{") && peek().k != Token::End) advance();
     if (!is_punct("{")) perr("expected function body");
     if (!entry) fn_bodies_.push_back({fn, pos});
     skip_braces();
+  }
+
+  void resolve_signatures() {
+    for (const FnSig& sg : fn_sigs_) {
+      pos = sg.tok;
+      Function* fn = sg.fn;
+      const bool entry = fn->is_entry;
+      b.cur_line = peek().line;
+      expect("(");
+      while (!is_punct(")")) {
+        skip_attributes();
+        const std::string pn = expect_ident("parameter name");
+        expect(":");
+        skip_attributes();
+        if (entry) {  // entry-point signatures may use types we do not model; skip them
+          int depth = 0;
+          while (peek().k != Token::End && !(depth == 0 && (is_punct(",") || is_punct(")")))) {
+            if (is_punct("<") || is_punct("(")) ++depth;
+            if (is_punct(">") || is_punct(")")) --depth;
+            advance();
+          }
+        } else {
+          bool is_ptr = false;
+          Type t = parse_type(nullptr, &is_ptr);
+          Var* v = mod->new_var();
+          v->name = pn; v->ty = t; v->storage = Var::Param; v->immutable = true;
+          v->is_ptr = is_ptr; v->by_ref = is_ptr;
+          fn->params.push_back(v);
+        }
+        if (!accept(",")) break;
+      }
+      expect(")");
+      fn->ret = Type::void_();
+      if (accept("->")) {
+        skip_attributes();
+        if (!entry) fn->ret = parse_type();
+      }
+    }
   }
 
   void resolve_globals() {
@@ -217,7 +246,26 @@ class WgslParser : public ParserBase {
     }
   }
 
-  void parse_global(GlobalDecl&) {
+  void parse_struct_body(StructDef* d) {  // struct Name { a: T, b: U, }
+    d->field_names.clear();
+    d->field_types.clear();
+    advance();  // struct
+    advance();  // name
+    expect("{");
+    while (!is_punct("}")) {
+      skip_attributes();
+      const std::string fname = expect_ident("a member name");
+      expect(":");
+      skip_attributes();
+      add_field(d, fname, parse_type());
+      if (!accept(",")) break;
+    }
+    expect("}");
+    if (d->field_names.empty()) b.error("struct " + d->name + " has no members");
+  }
+
+  void parse_global(GlobalDecl& g) {
+    if (g.sdef) { parse_struct_body(g.sdef); return; }
     bool resource = false;
     while (is_punct("@")) { resource = true; skip_attributes(); }
     b.cur_line = peek().line;
@@ -252,7 +300,8 @@ class WgslParser : public ParserBase {
     if (init) {
       ConstVal cv;
       if (b.const_eval(*init, &cv)) { v->has_const = true; v->cval = cv; }
-      else if (is_const) b.error("initializer of const '" + name + "' is not a constant expression");
+      else if (is_const && !(init->ty.is_matrix() || init->ty.is_aggregate()) ) b.error("initializer of const '" + name + "' is not a constant expression");
+      else if (is_const && !b.is_const_expr(*init)) b.error("initializer of const '" + name + "' is not a constant expression");
     } else {
       v->has_const = true;  // zero value
       v->cval.ty = ty;
@@ -311,9 +360,12 @@ class WgslParser : public ParserBase {
     v->immutable = kw != "var";
     if (kw == "const") {
       ConstVal cv;
-      if (!b.const_eval(*init, &cv)) b.error("initializer of const '" + name + "' is not a constant expression");
-      v->has_const = true; v->cval = cv;
-      return nullptr;  // folded at every use
+      if (b.const_eval(*init, &cv)) {
+        v->has_const = true; v->cval = cv;
+        return nullptr;  // folded at every use
+      }
+      if (!((init->ty.is_aggregate() || init->ty.is_matrix()) && b.is_const_expr(*init))) b.error("initializer of const '" + name + "' is not a constant expression");
+      // aggregate constants are not folded: they behave like `let`
     }
     StmtP s = mk_stmt(Stmt::VarDecl);
     s->var = v; s->a = init;
@@ -423,13 +475,44 @@ class WgslParser : public ParserBase {
       s->body.push_back(blk);
       return s;
     }
-    if (accept_ident("break")) { if (!loop_depth) b.error("break outside of a loop"); expect(";"); return mk_stmt(Stmt::Break); }
+    if (accept_ident("break")) { if (!loop_depth && !switch_depth) b.error("break outside of a loop or switch"); expect(";"); return mk_stmt(Stmt::Break); }
     if (accept_ident("continue")) { if (!loop_depth) b.error("continue outside of a loop"); expect(";"); return mk_stmt(Stmt::Continue); }
     if (accept_ident("discard")) { expect(";"); return mk_stmt(Stmt::Discard); }
-    if (is_ident("switch")) b.unsupported("switch statements");
+    if (accept_ident("switch")) return parse_switch();
     StmtP s = parse_simple_statement();
     expect(";");
     return s;
+  }
+
+  // switch e { case 1, 2: { } case 3 { } default: { } }   (`default` may also appear in a case list)
+  StmtP parse_switch() {
+    StmtP sw = mk_stmt(Stmt::Switch);
+    sw->a = switch_selector(parse_expr());
+    expect("{");
+    ++switch_depth;
+    while (!is_punct("}")) {
+      if (peek().k == Token::End) perr("unterminated switch");
+      StmtP c = mk_stmt(Stmt::Case);
+      if (accept_ident("default")) c->is_default = true;
+      else if (accept_ident("case")) {
+        for (;;) {
+          if (accept_ident("default")) c->is_default = true;
+          else c->case_values.push_back(case_value(parse_expr(), sw->a->ty));
+          if (!accept(",")) break;
+          if (is_punct(":") || is_punct("{")) break;  // trailing comma
+        }
+      } else perr("expected 'case' or 'default'");
+      accept(":");
+      c->body.push_back(parse_block());
+      sw->body.push_back(c);
+    }
+    expect("}");
+    --switch_depth;
+    check_cases(*sw);
+    bool has_default = false;
+    for (const StmtP& c : sw->body) has_default = has_default || c->is_default;
+    if (!has_default) b.error("switch needs a default clause");
+    return sw;
   }
 
   ExprP parse_condition() {
@@ -515,19 +598,15 @@ class WgslParser : public ParserBase {
       if (accept(".")) {
         const std::string m = expect_ident("a member name");
         if (e->k == Expr::VarRef && e->var->is_ptr) e = b.deref(e);  // p.x on a pointer parameter
-        e = b.swizzle(e, m);
+        e = b.member(e, m);
         continue;
       }
       if (is_punct("[")) {
         advance();
         ExprP idx = parse_expr();
         expect("]");
-        ConstVal cv;
-        if (!e->ty.is_vector() && !e->ty.is_matrix()) b.unsupported("indexing of non-vector values");
-        if (!idx->ty.is_int() || !b.const_eval(*idx, &cv)) b.unsupported("dynamic vector / matrix indexing");
-        if (cv.i[0] < 0 || cv.i[0] >= e->ty.n) b.error("index out of range");
-        if (e->ty.is_matrix()) e = b.matrix_column(e, (int)cv.i[0]);
-        else e = b.swizzle(e, std::string(1, "xyzw"[cv.i[0]]));
+        if (e->k == Expr::VarRef && e->var->is_ptr) e = b.deref(e);
+        e = b.index(e, idx);
         continue;
       }
       break;
@@ -573,6 +652,16 @@ class WgslParser : public ParserBase {
       advance();
       if (is_punct("(")) b.error("'" + name + "' is a variable, not a function");
       return b.var_ref(v);
+    }
+    if (name == "array" && is_punct("(", 1)) {  // array(a, b, c): element type and length inferred
+      advance();
+      std::vector<ExprP> args = parse_args();
+      if (args.empty()) b.error("cannot infer the type of an empty array constructor");
+      bool any_float = false;
+      const Expr* concrete = nullptr;
+      for (const ExprP& a : args) { if (!a->ty.is_abstract() && !concrete) concrete = a.get(); if (a->ty.is_float()) any_float = true; }
+      Type el = concrete ? concrete->ty : any_float ? args[0]->ty.with_sk(Sk::F32) : args[0]->ty.with_sk(Sk::I32);
+      return b.construct(mod->array_of(el, (int)args.size()), false, args);
     }
     if (is_type_name(name) && (is_punct("(", 1) || is_punct("<", 1))) {
       bool infer = false;

@@ -12,7 +12,7 @@ namespace s2m_frontend {
 
 class ParserBase {
  public:
-  ParserBase(Lang lang, Module* m) : b(lang), mod(m) {}
+  ParserBase(Lang lang, Module* m) : b(lang), mod(m) { b.module = m; }
 
  protected:
   Builder b;
@@ -21,8 +21,10 @@ class ParserBase {
   size_t pos = 0;
   std::vector<std::map<std::string, Var*>> scopes;   // innermost last; scopes[0] = module scope
   std::map<std::string, Function*> functions;
+  std::map<std::string, const StructDef*> structs;
   Function* cur_fn = nullptr;
   int loop_depth = 0;
+  int switch_depth = 0;
 
   const Token& peek(size_t o = 0) const { return toks[std::min(pos + o, toks.size() - 1)]; }
   const Token& advance() { const Token& t = toks[pos]; if (pos + 1 < toks.size()) ++pos; b.cur_line = t.line; return t; }
@@ -69,7 +71,7 @@ class ParserBase {
   }
   static void mark_written(const Expr& lhs) {
     const Expr* e = &lhs;
-    while (e->k == Expr::Swizzle || e->k == Expr::Deref || e->k == Expr::AddrOf) e = e->args[0].get();
+    while (e->k == Expr::Swizzle || e->k == Expr::Deref || e->k == Expr::AddrOf || e->k == Expr::Member || e->k == Expr::Index) e = e->args[0].get();
     if (e->k == Expr::VarRef) e->var->written = true;
   }
   StmtP mk_stmt(Stmt::K k) { StmtP s = std::make_shared<Stmt>(); s->k = k; s->line = b.cur_line; return s; }
@@ -86,6 +88,48 @@ class ParserBase {
     StmtP s = mk_stmt(Stmt::Assign);
     s->a = lhs; s->b = rhs;
     return s;
+  }
+  StructDef* declare_struct(const std::string& name) {
+    if (structs.count(name)) b.error("redefinition of struct '" + name + "'");
+    mod->structs.emplace_back(new StructDef());
+    mod->structs.back()->name = name;
+    structs[name] = mod->structs.back().get();
+    return mod->structs.back().get();
+  }
+  void add_field(StructDef* d, const std::string& fname, const Type& t) {
+    if (t.is_void()) b.error("struct member of type void");
+    if (d->field(fname) >= 0) b.error("duplicate member '" + fname + "' in struct " + d->name);
+    d->field_names.push_back(fname);
+    d->field_types.push_back(t);
+  }
+  // array length from a constant expression
+  int array_len(ExprP e) {
+    ConstVal cv;
+    e = b.concretize(e);
+    if (!e->ty.is_scalar() || !e->ty.is_int() || !b.const_eval(*e, &cv)) b.error("array length must be a constant integer expression");
+    if (cv.i[0] < 1 || cv.i[0] > 65536) b.error("array length " + std::to_string(cv.i[0]) + " out of range");
+    return (int)cv.i[0];
+  }
+  // selector of a switch: concrete i32 / u32 scalar
+  ExprP switch_selector(ExprP e) {
+    e = b.concretize(e);
+    if (!e->ty.is_scalar() || !(e->ty.sk == Sk::I32 || e->ty.sk == Sk::U32)) b.error("switch selector must be an integer scalar, found " + e->ty.str());
+    return e;
+  }
+  int64_t case_value(ExprP e, const Type& sel) {
+    e = b.coerce(e, sel, "case selector");
+    ConstVal cv;
+    if (!b.const_eval(*e, &cv)) b.error("case selector is not a constant expression");
+    return cv.i[0];
+  }
+  void check_cases(const Stmt& sw) {
+    std::set<int64_t> seen;
+    int defaults = 0;
+    for (const StmtP& c : sw.body) {
+      if (c->is_default) ++defaults;
+      for (int64_t v : c->case_values) if (!seen.insert(v).second) b.error("duplicate case value " + std::to_string(v));
+    }
+    if (defaults > 1) b.error("switch has more than one default");
   }
   static Op compound_op(const std::string& p) {
     switch (p[0]) {

@@ -311,5 +311,27 @@ S2M_HD vec2 f_select(const vec2& f, const vec2& t, const bvec2& c) { return mk2(
 S2M_HD vec3 f_select(const vec3& f, const vec3& t, const bvec3& c) { return mk3(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z); }
 S2M_HD vec4 f_select(const vec4& f, const vec4& t, const bvec4& c) { return mk4(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z, c.w ? t.w : f.w); }
 
+
+/* ---------------------------------------------------------------- arrays and dynamic indexing
+ * array<T, N> / T[N] of the shading languages.  An out-of-range index reads / writes the nearest
+ * valid element (the `Restrict` bounds-check policy wgpu applies by default). */
+template <class T, int N> struct s2m_array { T v[N]; };
+S2M_HD int s2m_clamp_index(int i, int n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); }
+S2M_HD int s2m_clamp_index(unsigned i, int n) { return i >= (unsigned)n ? n - 1 : (int)i; }
+template <class T, int N, class I> S2M_HD T& s2m_at(s2m_array<T, N>& a, I i) { return a.v[s2m_clamp_index(i, N)]; }
+template <class T, int N, class I> S2M_HD const T& s2m_at(const s2m_array<T, N>& a, I i) { return a.v[s2m_clamp_index(i, N)]; }
+#define S2M_VAT(V, T, N) \
+  template <class I> S2M_HD T& s2m_at(V& v, I i) { return (&v.x)[s2m_clamp_index(i, N)]; } \
+  template <class I> S2M_HD const T& s2m_at(const V& v, I i) { return (&v.x)[s2m_clamp_index(i, N)]; }
+S2M_VAT(vec2, float, 2) S2M_VAT(vec3, float, 3) S2M_VAT(vec4, float, 4)
+S2M_VAT(ivec2, int, 2) S2M_VAT(ivec3, int, 3) S2M_VAT(ivec4, int, 4)
+S2M_VAT(bvec2, bool, 2) S2M_VAT(bvec3, bool, 3) S2M_VAT(bvec4, bool, 4)
+#undef S2M_VAT
+#define S2M_MAT_AT(M, V, N) \
+  template <class I> S2M_HD V& s2m_at(M& m, I i) { return (&m.c0)[s2m_clamp_index(i, N)]; } \
+  template <class I> S2M_HD const V& s2m_at(const M& m, I i) { return (&m.c0)[s2m_clamp_index(i, N)]; }
+S2M_MAT_AT(mat2, vec2, 2) S2M_MAT_AT(mat3, vec3, 3) S2M_MAT_AT(mat4, vec4, 4)
+#undef S2M_MAT_AT
+
 }  // namespace s2m
 #endif /* S2M_VEC_H_ */

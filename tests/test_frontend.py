@@ -202,7 +202,16 @@ def test_glsl_missing_sdf(built, tmp_path):
     ("fn sdf3d(p: vec3f) -> f32 { return p.x + 1i; }", "VALIDATION"),
     ("fn other(p: vec3f) -> f32 { return p.x; }", "MISSING_SDF"),
     ("fn sdf3d(p: vec2f) -> f32 { return p.x; }", "MISSING_SDF"),
-    ("struct S { a: f32 }\nfn sdf3d(p: vec3f) -> f32 { return p.x; }", "UNSUPPORTED"),
+    ("fn sdf3d(p: vec3f) -> f32 { var t: texture_2d<f32>; return p.x; }", "UNSUPPORTED"),
+    ("struct S { a: f32 }\nfn sdf3d(p: vec3f) -> f32 { let s = S(1.0); return s.b; }", "VALIDATION"),
+    ("struct S { a: f32 }\nfn sdf3d(p: vec3f) -> f32 { let s = S(1.0, 2.0); return s.a; }", "VALIDATION"),
+    ("struct S { a: S }\nfn sdf3d(p: vec3f) -> f32 { return p.x; }", "VALIDATION"),
+    ("fn sdf3d(p: vec3f) -> f32 { let a = array<f32, 2>(1.0, 2.0); return a[2]; }", "VALIDATION"),
+    ("fn sdf3d(p: vec3f) -> f32 { let a = array<f32, 2>(1.0, 2.0, 3.0); return a[0]; }", "VALIDATION"),
+    ("fn sdf3d(p: vec3f) -> f32 { var a: array<f32>; return p.x; }", "UNSUPPORTED"),
+    ("fn sdf3d(p: vec3f) -> f32 { switch 1 { case 1: { return p.x; } } return 0.0; }", "VALIDATION"),
+    ("fn sdf3d(p: vec3f) -> f32 { switch 1 { case 1, 1: { return p.x; } default: { } } return 0.0; }", "VALIDATION"),
+    ("fn sdf3d(p: vec3f) -> f32 { switch p.x { default: { } } return 0.0; }", "VALIDATION"),
 ])
 def test_wgsl_errors(built, src, kind):
     with pytest.raises(s2m.S2mError) as e:
@@ -369,6 +378,124 @@ def test_sin_cos_pairing(built, monkeypatch):
         assert f32_equal(host_eval.eval_points(opt, pts), host_eval.eval_points(plain, pts)).all(), src
     monkeypatch.delenv("S2M_NO_IR_OPT", raising=False)
     assert load_example_shader("mandelbulb").lower_to_cuda().count("= f_sincos_pair(") == 2
+
+
+def test_mutable_globals_switch_structs_arrays(built, tmp_path):
+    """f2: module-scope variables that functions assign, switch, structs, fixed-size arrays and dynamic
+    indexing -- the same program in WGSL and in GLSL (through the GLSL -> WGSL -> CUDA route), checked
+    against a numpy transcription"""
+    wgsl = textwrap.dedent("""\
+        const N = 3;
+        struct Hit { d: f32, id: i32, }
+        struct Scene { spheres: array<vec4f, N>, best: Hit, }
+        const RADII = array<f32, N>(0.5, 0.25, 0.75);
+        var<private> evals: i32;
+        var<private> bias: f32 = 0.125;
+        fn closer(a: Hit, b: Hit) -> Hit { evals = evals + 1; if (a.d < b.d) { return a; } return b; }
+        fn make_scene() -> Scene {
+          var s: Scene;
+          for (var i = 0; i < N; i++) { s.spheres[i] = vec4f(f32(i) - 1.0, 0.0, 0.0, RADII[i]); }
+          s.best = Hit(1e9, -1);
+          return s;
+        }
+        fn weight(id: i32) -> f32 {
+          var w = 0.0;
+          switch id {
+            case 0: { w = 1.0; }
+            case 1, 2: { w = 2.0; if (id == 2) { break; } w = w + 0.5; }
+            default: { w = -1.0; }
+          }
+          return w;
+        }
+        fn sdf3d(p: vec3f) -> f32 {
+          var sc = make_scene();
+          for (var i = 0; i < N; i++) {
+            let sp = sc.spheres[i];
+            sc.best = closer(sc.best, Hit(length(p - sp.xyz) - sp.w, i));
+          }
+          bias = bias * f32(evals);
+          var v = p;
+          v[sc.best.id] = v[sc.best.id] * 2.0;
+          let m = mat3x3f(v, p, v + p);
+          let far = array(p.x, p.y, p.z)[sc.best.id + 7];    // out of range: nearest element
+          return sc.best.d + 0.001 * weight(sc.best.id) + 0.01 * m[sc.best.id].y + 0.0001 * v[2] + 0.00001 * far + bias;
+        }
+        """)
+    glsl = textwrap.dedent("""\
+        #version 450 core
+        const int N = 3;
+        struct Hit { float d; int id; };
+        struct Scene { vec4 spheres[N]; Hit best; };
+        const float RADII[N] = float[N](0.5, 0.25, 0.75);
+        int evals;
+        float bias = 0.125;
+        Hit closer(Hit a, Hit b) { evals++; if (a.d < b.d) return a; return b; }
+        void make_scene(out Scene s) {
+          for (int i = 0; i < N; i++) s.spheres[i] = vec4(float(i) - 1.0, 0.0, 0.0, RADII[i]);
+          s.best = Hit(1e9, -1);
+        }
+        float weight(int id) {
+          float w = 0.0;
+          switch (id) {
+            case 0: w = 1.0; break;
+            case 1:
+            case 2: w = 2.0; if (id == 2) break; w += 0.5; break;
+            default: w = -1.0;
+          }
+          return w;
+        }
+        float sdf(vec3 p) {
+          Scene sc;
+          make_scene(sc);
+          for (int i = 0; i < N; i++) {
+            vec4 sp = sc.spheres[i];
+            sc.best = closer(sc.best, Hit(length(p - sp.xyz) - sp.w, i));
+          }
+          bias *= float(evals);
+          vec3 v = p;
+          v[sc.best.id] *= 2.0;
+          mat3 m = mat3(v, p, v + p);
+          float far = float[](p.x, p.y, p.z)[sc.best.id + 7];
+          return sc.best.d + 0.001 * weight(sc.best.id) + 0.01 * m[sc.best.id].y + 0.0001 * v[2] + 0.00001 * far + bias;
+        }
+        void main() {}
+        """)
+    f = np.float32
+
+    def expect(p):
+        best_d, best_id = f(1e9), -1
+        for i, rad in enumerate((f(0.5), f(0.25), f(0.75))):
+            q = (p - np.array([f(i) - f(1), 0, 0], np.float32)).astype(np.float32)
+            d = f(np.sqrt(f(f(q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]))) - rad
+            if not (best_d < d):
+                best_d, best_id = f(d), i
+        bias = f(f(0.125) * f(3))
+        v = p.copy()
+        v[best_id] = v[best_id] * f(2)
+        m = [v, p, (v + p).astype(np.float32)]
+        w = (f(1.0), f(2.5), f(2.0))[best_id]
+        r = f(best_d + f(f(0.001) * w))
+        r = f(r + f(f(0.01) * m[best_id][1]))
+        r = f(r + f(f(0.0001) * v[2]))
+        r = f(r + f(f(0.00001) * p[2]))
+        return f(r + bias)
+
+    pts = points(4.0, 1500)
+    want = np.array([expect(p) for p in pts], np.float32)
+    frag = tmp_path / "agg.frag"
+    frag.write_text(glsl)
+    shaders = {"wgsl": s2m.Sdf3DShader.from_source(wgsl), "glsl": s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")}
+    for lang, sh in shaders.items():
+        cuda = sh.lower_to_cuda()
+        assert "struct S_Hit" in cuda and "struct S2mState" in cuda and "switch (" in cuda and "s2m_array<vec4, 3>" in cuda
+        assert f32_equal(host_eval.eval_points(cuda, pts), want).all(), lang
+        assert sh.create_shader_module(None).cubin_size > 0   # NVRTC accepts it for sm_100a
+    assert "struct Scene {" in shaders["glsl"].source and "var<private> evals: i32;" in shaders["glsl"].source
+    # GLSL fall-through between non-empty cases is not modelled
+    frag.write_text("#version 450\nfloat sdf(vec3 p) { float w = 0.0; switch (int(p.x)) { case 0: w = 1.0; case 1: w = 2.0; break; } return w; }\nvoid main() {}\n")
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    assert "falls through" in str(e.value)
 
 
 def test_matrices(built, tmp_path):

@@ -1,0 +1,87 @@
+"""GPU tests of the front-end: the CUDA C++ it emits gives the same bits when NVRTC compiles it for
+sm_100a (--fmad=false) as when g++ compiles the same text for the host (-ffp-contract=off), for
+programs that use every language feature the CPU-side tests cover; and the reference's own test
+shader (src/lib.rs test_naga) meshes to its golden digest."""
+import json
+import os
+import textwrap
+
+import numpy as np
+import pytest
+
+import sdf2mesh_b200 as s2m
+from tests.conftest import ROOT
+from tests.support import host_eval
+from tests.support.digest import f32_equal, mesh_digests
+from tests.test_frontend import NAGA_TEST_GLSL
+
+pytestmark = pytest.mark.gpu
+
+WGSL_PROGRAMS = {
+    "control_flow": """
+        fn fold(q: vec3f) -> vec3f { var v = abs(q); if (v.x < v.y) { v = v.yxz; } if (v.x < v.z) { v = v.zyx; } return v; }
+        fn sdf3d(p: vec3f) -> f32 {
+          var z = p; var acc = 0.0; var i = 0;
+          loop { if (i >= 6) { break; } z = fold(z) * 1.7 - vec3f(0.6, 0.2, 0.1); acc += sin(z.x * 3.0) * cos(z.x * 3.0);
+                 continuing { i++; break if length(z) > 20.0; } }
+          while (acc > 2.0) { acc = acc - 1.5; }
+          return length(z) * pow(1.7, -f32(i)) - 0.05 + 0.01 * acc;
+        }""",
+    "math_mix": """
+        fn sdf3d(p: vec3f) -> f32 {
+          let a = atan2(p.y, p.x); let r = length(p.xy);
+          let q = vec3f(r * cos(a * 3.0), r * sin(a * 3.0), p.z);
+          let e = exp(-abs(q.z)) + log(1.0 + r) + tanh(q.x) + sqrt(abs(q.y)) + asin(clamp(q.z * 0.3, -1.0, 1.0)) + acos(clamp(q.x * 0.2, -1.0, 1.0));
+          return smoothstep(0.0, 4.0, e) + fract(q.x) * 0.1 + mix(q.y, q.z, 0.25) * 0.01 + sign(q.x) * step(0.5, r) * 0.001 + pow(r + 0.5, 2.5) * 1e-3 + exp2(-r) + log2(r + 1.0);
+        }""",
+    "aggregates": """
+        const N = 3;
+        struct Hit { d: f32, id: i32, }
+        struct Scene { spheres: array<vec4f, N>, best: Hit, }
+        const RADII = array<f32, N>(0.5, 0.25, 0.75);
+        var<private> evals: i32;
+        fn closer(a: Hit, b: Hit) -> Hit { evals = evals + 1; if (a.d < b.d) { return a; } return b; }
+        fn sdf3d(p: vec3f) -> f32 {
+          var sc: Scene;
+          for (var i = 0; i < N; i++) { sc.spheres[i] = vec4f(f32(i) - 1.0, 0.0, 0.0, RADII[i]); }
+          sc.best = Hit(1e9, -1);
+          for (var i = 0; i < N; i++) { let sp = sc.spheres[i]; sc.best = closer(sc.best, Hit(length(p - sp.xyz) - sp.w, i)); }
+          var v = p;
+          v[sc.best.id] = v[sc.best.id] * 2.0;
+          var w = 0.0;
+          switch sc.best.id { case 0: { w = 1.0; } case 1, 2: { w = 2.0; } default: { w = -1.0; } }
+          let m = mat3x3f(v, p, v + p);
+          return sc.best.d + 0.001 * w + 0.01 * m[sc.best.id].y + 0.0001 * f32(evals);
+        }""",
+}
+
+
+@pytest.mark.parametrize("name", sorted(WGSL_PROGRAMS))
+def test_device_bits_equal_host_bits(ctx, name):
+    sh = s2m.Sdf3DShader.from_source(textwrap.dedent(WGSL_PROGRAMS[name]))
+    cuda = sh.lower_to_cuda()
+    rng = np.random.default_rng(11)
+    pts = rng.uniform(-3, 3, (200_000, 3)).astype(np.float32)
+    dev = sh.create_shader_module(ctx).eval_points(pts)
+    host = host_eval.eval_points(cuda, pts)
+    eq = f32_equal(dev, host)
+    assert eq.all(), f"{np.count_nonzero(~eq)} of {len(pts)} values differ"
+
+
+def test_naga_test_shader_meshes_to_its_golden_digest(ctx, tmp_path):
+    """the GLSL of the reference's only unit test (lib.rs test_naga), through GLSL -> WGSL -> CUDA -> mesh"""
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "digests.json")))
+    keys = [k for k in golden if k.startswith("naga_sphere_")]
+    assert keys
+    w = s2m.WgslShaderCode(s2m.convert_glsl_to_wgsl(NAGA_TEST_GLSL))
+    w.remove_function("fn main_1(")
+    w.remove_function("fn main(")
+    w.remove_line("@fragment")
+    m = s2m.Sdf3DShader.from_source(w.text, s2m.SRC_WGSL).create_shader_module(ctx)
+    for key in keys:
+        _, r_, b_, f_ = key.rsplit("_", 3)
+        p, _ = s2m.params_from_cli(int(r_[1:]), float(b_[1:]), flags=s2m.MESH_ALL_SLICES if int(f_[1:]) & 1 else 0)
+        r = s2m.mesh_run(ctx, m, p)
+        d = r.data()
+        assert mesh_digests(d.positions, d.normals, d.keys, d.nibbles, d.quads, d.n_invalid_quads) == golden[key]
+        r.free()

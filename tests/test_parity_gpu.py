@@ -59,7 +59,7 @@ def test_mesh_matches_oracle(ctx, name, res, bounds):
 def test_mesh_matches_golden_digest(ctx, key):
     name, r_, b_, f_ = key.rsplit("_", 3)
     if name == "naga_sphere":
-        pytest.skip("covered by test_frontend_gpu")
+        pytest.skip("covered by tests/test_frontend_gpu.py")
     res, bounds, flags = int(r_[1:]), float(b_[1:]), int(f_[1:])
     p, _ = s2m.params_from_cli(res, bounds, flags=s2m.MESH_ALL_SLICES if flags & 1 else 0)
     r = s2m.mesh_run(ctx, module_for(ctx, name), p)
