@@ -246,12 +246,15 @@ extern "C" int s2m_ctx_device_info(const s2m_ctx* c, char* name, size_t name_len
 }
 
 // ------------------------------------------------------------------ module
+constexpr unsigned kK1RowsDefault = 2;  // measured: mandelbulb K1 -0.6 %, torus K1 -7 %; +10-20 % NVRTC time
+
 struct s2m_module {
   std::string cuda_source, log;
   std::vector<char> cubin;
   CUmodule_t mod = nullptr;
   CUfunction_t k1 = nullptr, k4 = nullptr, k_eval = nullptr, k_probe = nullptr;
   s2m_ctx* ctx = nullptr;
+  unsigned k1_rows = 1;  // grid rows per K1 thread (S2M_K1_ROWS the kernels were compiled with)
   double ms_frontend = 0, ms_nvrtc = 0, ms_load = 0;
 };
 
@@ -286,6 +289,10 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
     unroll_opt = std::string("-DS2M_K1_UNROLL=") + (atoi(e) == 1 ? "1" : "4");
     opts.push_back(unroll_opt.c_str());
   }
+  m->k1_rows = kK1RowsDefault;
+  if (const char* e = getenv("S2M_K1_ROWS")) m->k1_rows = atoi(e) == 2 ? 2u : 1u;  // experiment knob
+  const std::string rows_opt = "-DS2M_K1_ROWS=" + std::to_string(m->k1_rows);
+  opts.push_back(rows_opt.c_str());
   r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);
@@ -655,7 +662,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words};
       unsigned bx, by;
       k1_block_shape(&bx, &by);
-      dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by - 1u) / by, n_planes);
+      dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), n_planes);
       {
         SPAN_BEGIN(0, s);
         if ((st = launch(m->k1, grid1, dim3(bx, by, 1), s, a1, "s2m_k1_slab"))) return st;
@@ -926,7 +933,7 @@ extern "C" int s2m_debug_slab_plane(s2m_ctx* c, s2m_module* m, const s2m_mesh_pa
   void* a1[] = {&g, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words};
   unsigned bx, by;
   k1_block_shape(&bx, &by);
-  if ((st = launch(m->k1, dim3((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by - 1u) / by, 1), dim3(bx, by, 1), c->stream, a1, "s2m_k1_slab"))) return st;
+  if ((st = launch(m->k1, dim3((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), 1), dim3(bx, by, 1), c->stream, a1, "s2m_k1_slab"))) return st;
   CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)(g.res[0] + 1) * 4, slab, (size_t)g.pitch_x * 4, (size_t)(g.res[0] + 1) * 4, g.rows,
                              cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));

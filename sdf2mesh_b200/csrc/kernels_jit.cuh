@@ -40,49 +40,79 @@ __device__ __noinline__ float s2m_sdf_call(float x, float y, float z) { return s
  * its footprint is (4*min(bx,32)) x (32/min(bx,32)) corners: (32,8) = 128x1 rows (512 B contiguous
  * per warp), (8,32) = 32x4 tiles (one full 128 B line per row) -- more compact, less divergence
  * in SDFs whose cost varies in space.  grid = (ceil(pitch_x/(4*bx)), ceil(rows/by), planes). */
+#ifndef S2M_K1_ROWS
+#define S2M_K1_ROWS 2   /* grid rows a thread evaluates (1 or 2): 2 amortises the index / class / store overhead */
+#endif
+
+__device__ __forceinline__ void s2m_k1_eval4(bool on, const float cx[4], float cy, float cz, float v[4]) {
+  v[0] = 0.0f; v[1] = 0.0f; v[2] = 0.0f; v[3] = 0.0f;
+  /* One guard per thread, not per corner: a float4 whose first corner is inside the grid is
+   * evaluated whole (at most 3 corners past the last one per row, in the padding nobody reads). */
+  if (on) {
+#if S2M_K1_UNROLL == 1
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) v[k] = s2m_sdf(cx[k], cy, cz);
+  }
+}
+/* corner classes of 4 values: low nibble P (value > tau), high nibble N (value < -tau) */
+__device__ __forceinline__ unsigned s2m_k1_class_byte(const float v[4], float tau) {
+  return (v[0] > tau ? 1u : 0u) | (v[1] > tau ? 2u : 0u) | (v[2] > tau ? 4u : 0u) | (v[3] > tau ? 8u : 0u) |
+         (v[0] < -tau ? 16u : 0u) | (v[1] < -tau ? 32u : 0u) | (v[2] < -tau ? 64u : 0u) | (v[3] < -tau ? 128u : 0u);
+}
+
 extern "C" __global__ void __launch_bounds__(256)
 s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned n_planes,
             float tau, uint2* __restrict__ cls, unsigned cls_words) {
   const unsigned x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
-  const unsigned y = blockIdx.y * blockDim.y + threadIdx.y;
+  const unsigned y = (blockIdx.y * blockDim.y + threadIdx.y) * (unsigned)S2M_K1_ROWS;
   const unsigned pz = blockIdx.z;
   /* no early return: all 32 lanes take part in the shuffles below.  Groups of 8 lanes cover 32
    * consecutive corners of one row (blockDim.x is a multiple of 8, pitch_x of 32), so a group is
    * active or inactive as a whole. */
   const bool active = x4 < g.pitch_x && y < g.rows && pz < n_planes;
   const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
-  const float cy = g.bmin[1] + g.size[1] * (float)y;
-  /* S2M_K1_UNROLL=1 keeps ONE inlined copy of the SDF in the kernel (4x less code); 4 = unrolled
-   * (lets independent evaluations overlap; faster for the mandelbulb, measured). */
-  float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
-  /* One guard per thread, not per corner: a float4 whose first corner is inside the grid is
-   * evaluated whole (at most 3 corners past the last one per row, in the padding nobody reads). */
-  if (active && x4 <= g.res[0]) {
-#if S2M_K1_UNROLL == 1
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
-    for (int k = 0; k < 4; ++k) {
-      const float val = s2m_sdf(g.bmin[0] + g.size[0] * (float)(x4 + (unsigned)k), cy, cz);
-      if (k == 0) v0 = val; else if (k == 1) v1 = val; else if (k == 2) v2 = val; else v3 = val;
-    }
-  }
+  const unsigned lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31u;
   const unsigned long long row = (unsigned long long)pz * g.rows + y;
-  if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(v0, v1, v2, v3);
+  /* S2M_K1_UNROLL=1 keeps ONE inlined copy of the SDF per row in the kernel (4x less code); 4 =
+   * unrolled (lets independent evaluations overlap; faster for the mandelbulb, measured). */
+  float cx[4], va[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) cx[k] = g.bmin[0] + g.size[0] * (float)(x4 + (unsigned)k);
+  const bool in_x = x4 <= g.res[0];
+  s2m_k1_eval4(active && in_x, cx, g.bmin[1] + g.size[1] * (float)y, cz, va);
+  if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(va[0], va[1], va[2], va[3]);
+#if S2M_K1_ROWS == 2
+  const bool active_b = active && y + 1u < g.rows;
+  float vb[4];
+  s2m_k1_eval4(active_b && in_x, cx, g.bmin[1] + g.size[1] * (float)(y + 1u), cz, vb);
+  if (active_b) *reinterpret_cast<float4*>(slab + (row + 1ull) * g.pitch_x + x4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+#endif
   /* Corner classes for K2: P = value > +tau, N = value < -tau (NaN and the |v| <= tau band are
-   * neither).  One byte per thread: low nibble = P of its 4 corners, high nibble = N.  8 lanes
-   * (32 corners of a row) make one 64-bit word, cls[plane][row][x/32] = (lanes 0-3, lanes 4-7):
-   * 0.25 B per corner instead of K2 re-reading 4 B.  Two shuffles per thread. */
+   * neither).  One byte per thread and row: low nibble = P of its 4 corners, high nibble = N.
+   * 8 lanes (32 corners of a row) make one 64-bit word, cls[plane][row][x/32] = (lanes 0-3,
+   * lanes 4-7): 0.25 B per corner instead of K2 re-reading 4 B.  Two shuffles per thread. */
   if (cls != nullptr) {
-    const unsigned lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31u;
-    unsigned w = ((v0 > tau ? 1u : 0u) | (v1 > tau ? 2u : 0u) | (v2 > tau ? 4u : 0u) | (v3 > tau ? 8u : 0u) |
-                  (v0 < -tau ? 16u : 0u) | (v1 < -tau ? 32u : 0u) | (v2 < -tau ? 64u : 0u) | (v3 < -tau ? 128u : 0u))
-                 << (8u * (lane & 3u));
+#if S2M_K1_ROWS == 1
+    unsigned w = s2m_k1_class_byte(va, tau) << (8u * (lane & 3u));
     w |= __shfl_xor_sync(0xffffffffu, w, 1);
     w |= __shfl_xor_sync(0xffffffffu, w, 2);
     if (active && (lane & 3u) == 0u)
       reinterpret_cast<unsigned*>(cls)[(row * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u)] = w;
+#else
+    /* both rows travel in one register: bytes (A even lane, A odd lane, B even lane, B odd lane)
+     * after the first exchange, then lane pairs (0,1) and (2,3) swap their 16-bit halves */
+    unsigned w = (s2m_k1_class_byte(va, tau) << (8u * (lane & 1u))) | (s2m_k1_class_byte(vb, tau) << (16u + 8u * (lane & 1u)));
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    const unsigned o = __shfl_xor_sync(0xffffffffu, w, 2);
+    const unsigned lo = (lane & 2u) ? o : w, hi = (lane & 2u) ? w : o;   /* lanes 0-1 of the quad, lanes 2-3 */
+    const unsigned wa = (lo & 0xffffu) | (hi << 16), wb = (lo >> 16) | (hi & 0xffff0000u);
+    const unsigned long long at = (row * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u);
+    if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = wa;
+    if (active_b && (lane & 3u) == 2u) reinterpret_cast<unsigned*>(cls)[at + 2ull * cls_words] = wb;
+#endif
   }
 }
 
