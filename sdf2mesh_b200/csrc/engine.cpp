@@ -154,8 +154,8 @@ struct Trace {
 struct s2m_ctx {
   int device = 0;
   cudaDeviceProp prop{};
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
-  DevBuf slab, cls, cand_mask, word_prefix, cand_key, cand_vrank, status, counters;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, prod_stream = nullptr;
+  DevBuf slab, cls, slab2, cls2, cand_mask, word_prefix, cand_key, cand_vrank, status, counters;
   DevBuf v_pos, v_nrm, v_key, v_nib, quads, scratch, invalid;
   std::vector<PinnedBlock> pinned;
   unsigned long long* h_counters = nullptr;  // pinned, 16 words
@@ -188,7 +188,9 @@ struct s2m_ctx {
   }
 };
 
-enum Counter { C_NCAND = 0, C_NVERT = 1, C_NHALO = 2, C_NQUAD = 3, C_NINVALID = 4, C_TICKET0 = 5, C_TICKET1 = 6, C_TICKET2 = 7, C_INVALID_CURSOR = 8, C_COUNT = 16 };
+enum Counter { C_NCAND = 0, C_NVERT = 1, C_NHALO = 2, C_NQUAD = 3, C_NINVALID = 4, C_TICKET0 = 5, C_TICKET1 = 6, C_TICKET2 = 7, C_INVALID_CURSOR = 8,
+               C_CHUNK_CAND0 = 9, C_CHUNK_CAND1 = 10 /* candidates of the chunk K2 classified into slab buffer 0 / 1 */, C_COUNT = 16 };
+enum CtxEvent { EV_BEGIN = 0, EV_KERNELS_DONE = 1, EV_ALL_DONE = 2, EV_PRODUCED0 = 4, EV_PRODUCED1 = 5, EV_CONSUMED0 = 6, EV_CONSUMED1 = 7 };
 constexpr unsigned long long kInvalidCapacity = 1ull << 20;
 
 extern "C" int s2m_ctx_create(int device_ordinal, s2m_ctx** out) {
@@ -211,7 +213,12 @@ extern "C" int s2m_ctx_create(int device_ordinal, s2m_ctx** out) {
   if (c->prop.major < 10)
     return fail(S2M_ERR_NO_DEVICE, std::string("device '") + c->prop.name + "' is sm_" + std::to_string(c->prop.major) +
                                        std::to_string(c->prop.minor) + "; this library only carries sm_100a code");
-  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // Two compute streams: K1/K2 of chunk c+1 (producer, low priority) run while K3/K4a/K4b of chunk c
+  // (consumer = the main stream, high priority) execute; see mesh_begin_impl.
+  int prio_least = 0, prio_greatest = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
+  CUDA_TRY(cudaStreamCreateWithPriority(&c->prod_stream, cudaStreamNonBlocking, prio_least));
   CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
   CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), C_COUNT * 8, cudaHostAllocMapped | cudaHostAllocPortable));
@@ -225,7 +232,7 @@ extern "C" void s2m_ctx_destroy(s2m_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&c->slab, &c->cls, &c->cand_mask, &c->word_prefix, &c->cand_key, &c->cand_vrank, &c->status, &c->counters,
+  for (DevBuf* b : {&c->slab, &c->cls, &c->slab2, &c->cls2, &c->cand_mask, &c->word_prefix, &c->cand_key, &c->cand_vrank, &c->status, &c->counters,
                     &c->v_pos, &c->v_nrm, &c->v_key, &c->v_nib, &c->quads, &c->scratch, &c->invalid})
     b->release();
   for (auto& b : c->pinned) cudaFreeHost(b.p);
@@ -234,6 +241,7 @@ extern "C" void s2m_ctx_destroy(s2m_ctx* c) {
   for (auto& ev : c->ev_pool) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->prod_stream) cudaStreamDestroy(c->prod_stream);
   delete c;
 }
 
@@ -631,6 +639,13 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
     for (uint32_t z0 = 0; z0 < r->nz; z0 += even) chunks.push_back({z0, std::min(even, r->nz - z0)});
   }
   r->t.chunks = (uint32_t)chunks.size();
+  // Two slab (and class-plane) buffers when there is more than one chunk: K1/K2 of chunk c+1 then run
+  // on the producer stream while the consumer stream works through K3/K4a/K4b of chunk c.
+  bool pipelined = !dense && chunks.size() > 1 && !getenv("S2M_NO_CHUNK_OVERLAP");
+  if (pipelined) {
+    const size_t max_planes = (size_t)chunks[0].nzc + 1;
+    if (c->slab2.ensure(max_planes * plane_bytes) != S2M_OK) { cudaGetLastError(); pipelined = false; }  // not enough memory: one buffer, no overlap
+  }
   // pinned output sized from the previous run on this ctx (if any): lets chunk copies start early
   const bool can_stream = c->hint_nv > 0;
   if (can_stream) {
@@ -641,47 +656,70 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
 
   uint64_t cand_done = 0, vert_done = 0, quad_done = 0;
   std::vector<uint32_t> dense_row;
+  cudaStream_t ps = pipelined ? c->prod_stream : s;   // producer stream (K1, K2)
+  if (pipelined) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_BEGIN], 0));  // after the counter reset
+  const bool from_slab = p->flags & S2M_MESH_CLASSIFY_FROM_SLAB;
+  const unsigned cls_words = g.pitch_x / 32u;
+  // K1 + K2 of chunk ci into slab buffer ci % 2 (buffer 0 when not pipelined)
+  auto produce = [&](size_t ci) -> int {
+    const Chunk ch = chunks[ci];
+    const int buf = pipelined ? (int)(ci & 1) : 0;
+    DevBuf& slab_buf = buf ? c->slab2 : c->slab;
+    DevBuf& cls_buf = buf ? c->cls2 : c->cls;
+    int st2;
+    GridDev gd = g;
+    float* slab = slab_buf.as<float>();
+    unsigned first_plane = r->z_first + ch.z0, n_planes = ch.nzc + 1;
+    unsigned cw = cls_words;
+    void* cls = nullptr;
+    if (!from_slab) {
+      if ((st2 = cls_buf.ensure((size_t)n_planes * g.rows * cls_words * 8 + 64))) return st2;
+      cls = cls_buf.p;
+    }
+    if (pipelined && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_CONSUMED0 + buf], 0));  // K4a of chunk ci-2 has read this buffer
+    CUDA_TRY(cudaMemsetAsync(d_cnt + C_CHUNK_CAND0 + buf, 0, 8, ps));
+    float tau_arg = tau;
+    void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw};
+    unsigned bx, by;
+    k1_block_shape(&bx, &by);
+    dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), n_planes);
+    {
+      SPAN_BEGIN(0, ps);
+      if ((st2 = launch(m->k1, grid1, dim3(bx, by, 1), ps, a1, "s2m_k1_slab"))) return st2;
+      SPAN_END(ps);
+    }
+    S2mK2Args a2{};
+    a2.slab = slab; a2.pitch_x = g.pitch_x; a2.plane_stride = g.plane_stride;
+    a2.res_x = g.res[0]; a2.res_y = g.res[1]; a2.nz_chunk = ch.nzc; a2.tau = tau;
+    a2.cand_mask = c->cand_mask.as<uint32_t>() + words_per_slice * ch.z0; a2.words_x = r->words_x; a2.total = d_cnt + C_CHUNK_CAND0 + buf;
+    a2.cls = cls; a2.cls_words = cls_words;
+    {
+      SPAN_BEGIN(1, ps);
+      int e2 = from_slab ? s2m_launch_k2(&a2, ps) : s2m_launch_k2_bits(&a2, ps);
+      if (e2) return fail(S2M_ERR_CUDA, std::string("k2_classify launch: ") + cudaGetErrorString((cudaError_t)e2));
+      SPAN_END(ps);
+    }
+    if (pipelined) CUDA_TRY(cudaEventRecord(c->ev[EV_PRODUCED0 + buf], ps));
+    r->t.launches += 2;
+    return S2M_OK;
+  };
+  if (!dense && !chunks.empty() && (st = produce(0))) return st;
   for (size_t ci = 0; ci < chunks.size(); ++ci) {
     const Chunk ch = chunks[ci];
+    const int buf = pipelined ? (int)(ci & 1) : 0;
     const unsigned long long chunk_words = words_per_slice * ch.nzc;
     uint32_t* mask_chunk = c->cand_mask.as<uint32_t>() + words_per_slice * ch.z0;
     unsigned slab_first_plane = 0, slab_n_planes = 0;
+    uint64_t cand_total = cand_done;
     if (!dense) {
-      // ---- K1
-      GridDev gd = g;
-      float* slab = c->slab.as<float>();
-      unsigned first_plane = r->z_first + ch.z0, n_planes = ch.nzc + 1;
-      const bool from_slab = p->flags & S2M_MESH_CLASSIFY_FROM_SLAB;
-      unsigned cls_words = g.pitch_x / 32u;
-      void* cls = nullptr;
-      if (!from_slab) {
-        if ((st = c->cls.ensure((size_t)n_planes * g.rows * cls_words * 8 + 64))) return st;
-        cls = c->cls.p;
-      }
-      float tau_arg = tau;
-      void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words};
-      unsigned bx, by;
-      k1_block_shape(&bx, &by);
-      dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), n_planes);
-      {
-        SPAN_BEGIN(0, s);
-        if ((st = launch(m->k1, grid1, dim3(bx, by, 1), s, a1, "s2m_k1_slab"))) return st;
-        SPAN_END(s);
-      }
-      slab_first_plane = first_plane; slab_n_planes = n_planes;
-      // ---- K2
-      S2mK2Args a2{};
-      a2.slab = slab; a2.pitch_x = g.pitch_x; a2.plane_stride = g.plane_stride;
-      a2.res_x = g.res[0]; a2.res_y = g.res[1]; a2.nz_chunk = ch.nzc; a2.tau = tau;
-      a2.cand_mask = mask_chunk; a2.words_x = r->words_x; a2.total = d_cnt + C_NCAND;
-      a2.cls = cls; a2.cls_words = cls_words;
-      {
-        SPAN_BEGIN(1, s);
-        int e2 = from_slab ? s2m_launch_k2(&a2, s) : s2m_launch_k2_bits(&a2, s);
-        if (e2) return fail(S2M_ERR_CUDA, std::string("k2_classify launch: ") + cudaGetErrorString((cudaError_t)e2));
-        SPAN_END(s);
-      }
-      r->t.launches += 2;
+      // the next chunk's K1/K2 are queued before this chunk's counts are waited for
+      if (pipelined && ci + 1 < chunks.size() && (st = produce(ci + 1))) return st;
+      if (pipelined) CUDA_TRY(cudaStreamWaitEvent(s, c->ev[EV_PRODUCED0 + buf], 0));
+      slab_first_plane = r->z_first + ch.z0; slab_n_planes = ch.nzc + 1;
+      // ---- [count] candidates of this chunk
+      if ((st = read_counters(c, s))) return st;
+      cand_total = cand_done + c->h_counters[C_CHUNK_CAND0 + buf];
+      if (!pipelined && ci + 1 < chunks.size()) { /* single buffer: the next K1 is issued after this chunk's K4a (below) */ }
     } else {
       // reference-cost mode: every cell of the chunk is a candidate
       if (dense_row.empty()) {
@@ -691,13 +729,9 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       std::vector<uint32_t> host(chunk_words);
       for (unsigned long long i = 0; i < chunk_words; i += r->words_x) memcpy(&host[i], dense_row.data(), r->words_x * 4);
       CUDA_TRY(cudaMemcpyAsync(mask_chunk, host.data(), chunk_words * 4, cudaMemcpyHostToDevice, s));
-      const unsigned long long nc = cand_done + (unsigned long long)g.res[0] * g.res[1] * ch.nzc;
-      CUDA_TRY(cudaMemcpyAsync(d_cnt + C_NCAND, &nc, 8, cudaMemcpyHostToDevice, s));
       CUDA_TRY(cudaStreamSynchronize(s));
+      cand_total = cand_done + (unsigned long long)g.res[0] * g.res[1] * ch.nzc;
     }
-    // ---- [count] candidates of this chunk
-    if ((st = read_counters(c, s))) return st;
-    const uint64_t cand_total = c->h_counters[C_NCAND];
     const uint64_t n_cand = cand_total - cand_done;
     if (cand_total >= 0xffffffffull) return fail(S2M_ERR_UNSUPPORTED, "more than 2^32-1 candidate cells in one slab; split it with z_begin/z_end");
     const unsigned k3_tiles = s2m_k3_tiles(chunk_words);
@@ -733,7 +767,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       unsigned long long nc = n_cand, vbase = vert_done;
       unsigned label_add = r->label_add, halo_below = r->halo ? (r->z_first + 1u) : 0u;
       unsigned want_normals = ((p->flags & S2M_MESH_NO_NORMALS) ? 0u : 1u) | ((p->flags & S2M_MESH_CONSISTENT_CORNERS) ? 2u : 0u);  // K4a's mode bits
-      SlabViewDev sv{c->slab.as<float>(), slab_first_plane, slab_n_planes};
+      SlabViewDev sv{(buf ? c->slab2 : c->slab).as<float>(), slab_first_plane, slab_n_planes};
       VertexOutDev vo{c->v_pos.as<float>(), c->v_nrm.as<float>(), c->v_key.as<unsigned long long>(), c->v_nib.as<unsigned char>(),
                       c->cand_vrank.as<unsigned>() + cand_done, status + 2 + k3_tiles, tickets + 1, d_cnt + C_NVERT, d_cnt + C_NHALO};
       void* a4[] = {&gd, &ck, &nc, &vbase, &label_add, &halo_below, &want_normals, &sv, &vo};
@@ -742,6 +776,8 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       SPAN_END(s);
       r->t.launches += 1;
     }
+    if (pipelined) CUDA_TRY(cudaEventRecord(c->ev[EV_CONSUMED0 + buf], s));  // slab buffer `buf` may be overwritten
+    else if (!dense && ci + 1 < chunks.size() && (st = produce(ci + 1))) return st;
     // ---- [count] vertices so far
     uint64_t vert_total = vert_done;
     if (k4_tiles) {
