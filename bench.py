@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--no-balance", action="store_true", help="equal-thickness z-slabs instead of cost-balanced")
     ap.add_argument("--no-rebalance", action="store_true", help="keep the cost-probe partition; do not refine it from warm-up step times")
     ap.add_argument("--flags", type=int, default=0, help="extra S2M_MESH_* flags")
+    ap.add_argument("--u64-quads", action="store_true", help="64-bit quad indices (default: u32, the reference's own index type)")
     ap.add_argument("--slab-budget-gb", type=float, default=0.0, help="bytes of corner slab resident at once (0 = engine default, 4 GiB chunks)")
     args = ap.parse_args()
     wl = args.workload
@@ -192,6 +193,8 @@ def main():
     shader = s2m.Sdf3DShader.from_glsl_fragment_shader(path, "sdf") if kind == "glsl" else s2m.Sdf3DShader.from_path(path)
     module = shader.create_shader_module(ctx)
     jit_ms = (time.perf_counter() - t0) * 1e3
+    if not args.u64_quads:
+        args.flags |= s2m.MESH_QUADS_U32
     params, _ = s2m.params_from_cli(res, bounds, flags=args.flags)
     params.slab_budget_bytes = int(args.slab_budget_gb * (1 << 30))
     n_slices = dist_util.n_scanned_slices(res, bool(args.flags & s2m.MESH_ALL_SLICES))
@@ -227,7 +230,7 @@ def main():
             t0 = time.perf_counter()
             r = s2m.mesh_begin(ctx, module, params)
             t1 = time.perf_counter()
-            counts = dist_util.allgather_counts(r.info().n_vertices, dev)
+            counts = dist_util.allgather_counts(r.info().n_vertices, dev, ctx)
             t2 = time.perf_counter()
             r.finish(dist_util.exclusive_bases(counts)[rank])
             t3 = time.perf_counter()
@@ -246,8 +249,10 @@ def main():
         if world > 1 and not args.no_balance and not args.no_rebalance and w == 1 and args.warmup >= 3:
             # One refinement, from the second warm-up step (the first one pays for allocations, and
             # the step after the refinement pays for re-allocations): what every rank's
-            # begin()+finish() took, spread inside its slab according to the probe profile.
-            own = torch.tensor([phase[0] + phase[2]], dtype=torch.float64, device=dev)
+            # begin() took, spread inside its slab according to the probe profile.
+            # The all-gather in the middle of a step waits for the slowest begin(), so begin() is what
+            # has to be equal across ranks (finish() is a quad copy, short and proportional to the vertices).
+            own = torch.tensor([phase[0]], dtype=torch.float64, device=dev)
             allt = torch.zeros(world, dtype=torch.float64, device=dev)
             torch.distributed.all_gather_into_tensor(allt, own)
             bounds_z = dist_util.rebalance(bounds_z, allt.tolist(), cost)
@@ -271,7 +276,7 @@ def main():
     launches = sum(s[3]["launches"] for s in stats)
     nv, nq, ninv = stats[-1][0], stats[-1][1], stats[-1][2]
     ncand = stats[-1][5]
-    d2h_bytes = nv * 33 + nq * 32
+    d2h_bytes = nv * 33 + nq * (32 if args.u64_quads else 16)
     per = {k: sum(s[3][k] for s in stats) / args.steps for k in ("k1_slab_ms", "k2_classify_ms", "k3_compact_ms", "k4_vertices_ms", "k4_quads_ms", "d2h_ms")}
     per_rank = None
     if world > 1:
@@ -312,6 +317,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (analytic SDF, no random inputs)",
         "config": {"workload": wl, "sdf": f, "resolution": res, "bounds": bounds, "mode": "faithful (slices 0..R-2)" if not (args.flags & 1) else "all slices",
+                   "quad_index": "u64" if args.u64_quads else "u32 (the reference's Quad(u32, u32, u32, u32))",
                    "parallelism": f"z-slabs x{world}" + ("" if world == 1 else (" equal" if args.no_balance else (" cost-probe" if args.no_rebalance else " cost-probe + refined from warm-up step times"))), "z_boundaries": bounds_z,
                    "l2": "no L2 flush needed: the corner slab alone is %.1f GB per step, far larger than the 126 MB L2" % (k1_bytes / 1e9)},
         "mesh": {"candidates": ncand, "vertices": nv, "quads": nq, "invalid_quads": ninv, "triangles": 2 * nq, "Mtriangles_per_s": 2 * nq * args.steps / wall / 1e6},

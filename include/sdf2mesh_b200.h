@@ -120,6 +120,9 @@ void s2m_module_free(s2m_module* m);
                                           (bmin + size*(i+1) instead of min + size), so neighbouring cells agree on every
                                           corner value and no quad is lost to 1-ulp disagreements.  With S2M_MESH_ALL_SLICES this is
                                           the watertight mode (CLI --watertight). */
+#define S2M_MESH_QUADS_U32 128u      /* quad indices as u32 -- the reference's own type (lib.rs Quad(u32, ..)) -- in
+                                       s2m_result_info.quads32 instead of u64 in .quads: half the bytes to copy and keep.
+                                       s2m_mesh_finish fails with S2M_ERR_UNSUPPORTED if an index would not fit. */
 #define S2M_MESH_CLASSIFY_FROM_SLAB 16u /* K2 re-reads the f32 slab through shared memory instead of K1's class bit planes */
 
 typedef struct s2m_mesh_params {
@@ -171,6 +174,7 @@ typedef struct s2m_result_info {
   const float* halo_positions;   /* 3 * n_halo_vertices: positions of the recomputed slice below this slab (vertex
                                     global_vertex_base - n_halo_vertices + j), so a slab can be written on its own */
   int64_t global_vertex_base;    /* what s2m_mesh_finish was given (0 for s2m_mesh_run) */
+  const uint32_t* quads32;       /* S2M_MESH_QUADS_U32: 4 * n_quads u32 indices, and .quads is NULL */
   s2m_timings timings;
 } s2m_result_info;
 
@@ -196,6 +200,13 @@ int s2m_result_write_stl_binary(const s2m_result* r, const char* path);
  * given in z order with consecutive global vertex bases: one STL / PLY file for the whole mesh.
  * binary_stl != 0 writes binary STL for a .stl path. */
 int s2m_write_mesh_parts(const s2m_result* const* parts, int n_parts, const char* path, int binary_stl);
+
+/* Reads n (<= 32) 64-bit words that live in device memory -- the output of the count all-gather --
+ * into host memory with a one-warp kernel writing through mapped pinned memory, on the caller's CUDA
+ * stream (cudaStream_t passed as void*; NULL = the ctx's own stream), then waits for that stream.
+ * A cudaMemcpy of these few bytes would queue on the copy engine behind the slab's vertex copy
+ * (measured: ~2 ms per step on 8 GPUs). */
+int s2m_read_device_words(s2m_ctx* ctx, const void* device_words, uint32_t n, uint64_t* out, void* cuda_stream);
 
 /* diagnostics */
 int s2m_eval_points(s2m_ctx* ctx, s2m_module* m, const float* xyz, uint64_t n, float* out);

@@ -19,6 +19,7 @@ COMPILE_ALLOW_FMA = 1
 MESH_ALL_SLICES, MESH_NO_NORMALS, MESH_EXACT_DENSE, MESH_KEEP_CANDIDATES, MESH_CLASSIFY_FROM_SLAB = 1, 2, 4, 8, 16
 MESH_KEEP_INVALID = 32
 MESH_CONSISTENT_CORNERS = 64
+MESH_QUADS_U32 = 128
 
 
 class S2mError(RuntimeError):
@@ -68,6 +69,7 @@ class ResultInfo(ctypes.Structure):
         ("quads", ctypes.POINTER(ctypes.c_uint64)), ("candidates", ctypes.POINTER(ctypes.c_uint64)),
         ("invalid_records", ctypes.POINTER(ctypes.c_uint64)), ("n_invalid_records", ctypes.c_uint64),
         ("halo_positions", ctypes.POINTER(ctypes.c_float)), ("global_vertex_base", ctypes.c_int64),
+        ("quads32", ctypes.POINTER(ctypes.c_uint32)),
         ("timings", Timings),
     ]
 
@@ -116,6 +118,7 @@ SYMBOLS = {
     "s2m_eval_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_uint64, _P]),
     "s2m_debug_slab_plane": (ctypes.c_int, [_P, _P, ctypes.POINTER(MeshParams), ctypes.c_uint32, _P]),
     "s2m_cost_probe": (ctypes.c_int, [_P, _P, ctypes.POINTER(MeshParams), ctypes.c_uint32, _P]),
+    "s2m_read_device_words": (ctypes.c_int, [_P, _P, ctypes.c_uint32, _P, _P]),
 }
 
 _lib = None

@@ -159,6 +159,7 @@ struct s2m_ctx {
   DevBuf v_pos, v_nrm, v_key, v_nib, quads, scratch, invalid;
   std::vector<PinnedBlock> pinned;
   unsigned long long* h_counters = nullptr;  // pinned, 16 words
+  unsigned long long* h_words = nullptr;     // pinned + mapped, 32 words (s2m_read_device_words)
   cudaEvent_t ev[16]{};
   std::vector<cudaEvent_t> ev_pool;   // per-launch timing events, grown on demand
   uint64_t hint_nv = 0, hint_nq = 0;  // output sizes of the previous run (pinned capacity guess)
@@ -222,6 +223,7 @@ extern "C" int s2m_ctx_create(int device_ordinal, s2m_ctx** out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto& ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
   CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counters), C_COUNT * 8, cudaHostAllocMapped | cudaHostAllocPortable));
+  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->h_words), 32 * 8, cudaHostAllocMapped | cudaHostAllocPortable));
   int st = c->counters.ensure(C_COUNT * 8);
   if (st) return st;
   *out = c.release();
@@ -237,6 +239,7 @@ extern "C" void s2m_ctx_destroy(s2m_ctx* c) {
     b->release();
   for (auto& b : c->pinned) cudaFreeHost(b.p);
   if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->h_words) cudaFreeHost(c->h_words);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_pool) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -430,6 +433,8 @@ struct s2m_result {
   struct Span { int kind; size_t e0, e1; };  // kind: 0 K1, 1 K2, 2 K3, 3 K4a, 4 K4b, 5 copy
   std::vector<Span> spans;
   bool finished = false;
+  bool quads_u32() const { return (params.flags & S2M_MESH_QUADS_U32) != 0; }
+  size_t quad_bytes() const { return quads_u32() ? 16 : 32; }  // bytes per quad, device and host
 };
 
 extern "C" void s2m_result_free(s2m_result* r) {
@@ -490,7 +495,7 @@ int ensure_pinned_outputs(s2m_ctx* c, s2m_result* r, uint64_t need_v, uint64_t n
   }
   if (want_quads && (need_q > r->cap_q || !r->h_quads)) {
     if (r->h_quads) c->release_pinned(r->h_quads);
-    r->h_quads = (uint64_t*)c->lease_pinned(need_q * 32);
+    r->h_quads = (uint64_t*)c->lease_pinned(need_q * r->quad_bytes());
     if (!r->h_quads) return fail(S2M_ERR_OOM, "cudaHostAlloc for quad output failed");
     r->cap_q = need_q;
   }
@@ -508,7 +513,10 @@ int copy_out(s2m_ctx* c, s2m_result* r, cudaStream_t st, uint64_t v0, uint64_t v
     CUDA_TRY(cudaMemcpyAsync(r->h_key + h, c->v_key.as<unsigned long long>() + v0, n * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(r->h_nib + h, c->v_nib.as<unsigned char>() + v0, n, cudaMemcpyDeviceToHost, st));
   }
-  if (q1 > q0) CUDA_TRY(cudaMemcpyAsync(r->h_quads + 4 * q0, c->quads.as<unsigned long long>() + 4 * q0, (q1 - q0) * 32, cudaMemcpyDeviceToHost, st));
+  if (q1 > q0) {
+    const size_t qb = r->quad_bytes();
+    CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(r->h_quads) + qb * q0, c->quads.as<char>() + qb * q0, (q1 - q0) * qb, cudaMemcpyDeviceToHost, st));
+  }
   return S2M_OK;
 }
 
@@ -518,7 +526,8 @@ int launch_k4b(s2m_ctx* c, s2m_result* r, cudaStream_t s, uint64_t v_begin, uint
   if (v_end <= v_begin) return S2M_OK;
   const unsigned tiles = s2m_k4b_tiles(v_end - v_begin);
   int st;
-  if ((st = c->quads.ensure_preserve((size_t)(quad_base + (v_end - v_begin) * 3) * 32 + 64, (size_t)quad_base * 32, s))) return st;
+  const size_t qb = r->quad_bytes();
+  if ((st = c->quads.ensure_preserve((size_t)(quad_base + (v_end - v_begin) * 3) * qb + 64, (size_t)quad_base * qb, s))) return st;
   if ((st = c->scratch.ensure(((size_t)tiles + 8) * 8 + 64))) return st;
   CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, ((size_t)tiles + 8) * 8 + 64, s));
   S2mK4bArgs a{};
@@ -527,7 +536,8 @@ int launch_k4b(s2m_ctx* c, s2m_result* r, cudaStream_t s, uint64_t v_begin, uint
   a.cand_mask = c->cand_mask.as<uint32_t>(); a.word_prefix = c->word_prefix.as<uint32_t>(); a.cand_vrank = c->cand_vrank.as<uint32_t>();
   a.words_x = r->words_x; a.res_y = r->grid.res[1]; a.z_first = r->z_first; a.label_add = r->label_add;
   a.index_offset = index_offset;
-  a.quads = c->quads.as<unsigned long long>(); a.status = c->scratch.as<unsigned long long>() + 1;
+  a.quads = c->quads.as<unsigned long long>(); a.quads32 = r->quads_u32() ? c->quads.as<unsigned>() : nullptr;
+  a.status = c->scratch.as<unsigned long long>() + 1;
   a.ticket = reinterpret_cast<unsigned*>(c->scratch.p); a.n_quads = d_cnt + C_NQUAD; a.n_invalid = d_cnt + C_NINVALID;
   if (r->params.flags & S2M_MESH_KEEP_INVALID) {
     if ((st = c->invalid.ensure(kInvalidCapacity * 48))) return st;
@@ -634,7 +644,14 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       if (st != S2M_ERR_OOM || zc <= 1) return st;
       budget = (unsigned long long)(zc + 1) * plane_bytes / 2;
     }
-    const uint32_t n_chunks = (r->nz + zc - 1) / zc;
+    uint32_t n_chunks = (r->nz + zc - 1) / zc;
+    if (!dense && !getenv("S2M_NO_CHUNK_OVERLAP")) {
+      // a slab that fits the budget in one piece is still cut into 2-4 chunks when it is large enough
+      // (>= 0.5 G voxels per chunk) for the two-stream overlap and the early output copies to pay
+      const double voxels = (double)g.res[0] * g.res[1] * r->nz;
+      const uint32_t want = (uint32_t)std::min(4.0, voxels / 5.0e8);
+      n_chunks = std::max(n_chunks, std::min(want, r->nz));
+    }
     const uint32_t even = (r->nz + n_chunks - 1) / n_chunks;  // equal chunks instead of a short last one
     for (uint32_t z0 = 0; z0 < r->nz; z0 += even) chunks.push_back({z0, std::min(even, r->nz - z0)});
   }
@@ -859,6 +876,8 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   cudaStream_t s = c->stream;
   int st;
   r->global_base = global_vertex_base;
+  if (r->quads_u32() && (global_vertex_base < 0 || (uint64_t)global_vertex_base + (r->n_vert_total - r->n_halo) > 0xffffffffull))
+    return fail(S2M_ERR_UNSUPPORTED, "S2M_MESH_QUADS_U32: vertex indices of this slab do not fit 32 bits");
   if (!r->quads_done) {
     // ---- K4b over all own vertices with the global base, then the quad copy
     if ((st = launch_k4b(c, r, s, 0, r->n_vert_total, 0, (long long)global_vertex_base - (long long)r->n_halo))) return st;
@@ -922,7 +941,8 @@ extern "C" int s2m_result_get(const s2m_result* r, s2m_result_info* o) {
   o->n_invalid_quads = r->n_invalid;
   o->n_candidates = r->n_cand;
   o->positions = r->h_pos; o->normals = r->h_nrm; o->cell_keys = r->h_key; o->sign_nibbles = r->h_nib;
-  o->quads = r->h_quads; o->candidates = r->h_cand;
+  o->quads = r->quads_u32() ? nullptr : r->h_quads; o->quads32 = r->quads_u32() ? reinterpret_cast<const uint32_t*>(r->h_quads) : nullptr;
+  o->candidates = r->h_cand;
   o->invalid_records = r->h_invalid; o->n_invalid_records = r->n_invalid_records;
   o->halo_positions = r->h_halo_pos; o->global_vertex_base = r->global_base;
   o->timings = r->t;
@@ -973,6 +993,17 @@ extern "C" int s2m_debug_slab_plane(s2m_ctx* c, s2m_module* m, const s2m_mesh_pa
   CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)(g.res[0] + 1) * 4, slab, (size_t)g.pitch_x * 4, (size_t)(g.res[0] + 1) * 4, g.rows,
                              cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return S2M_OK;
+}
+
+extern "C" int s2m_read_device_words(s2m_ctx* c, const void* device_words, uint32_t n, uint64_t* out, void* cuda_stream) {
+  if (!c || !device_words || !out || n == 0 || n > 32) return fail(S2M_ERR_INVALID_ARG, "s2m_read_device_words: bad argument (n must be 1..32)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->stream;
+  int e = s2m_launch_publish(static_cast<const unsigned long long*>(device_words), c->h_words, n, s);
+  if (e) return fail(S2M_ERR_CUDA, std::string("k_publish launch: ") + cudaGetErrorString((cudaError_t)e));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (uint32_t i = 0; i < n; ++i) out[i] = c->h_words[i];
   return S2M_OK;
 }
 

@@ -252,6 +252,7 @@ struct QuadParams {
   uint32_t label_add;     // label = true z + label_add
   long long index_offset; // global index = local vertex index + index_offset
   unsigned long long* quads;  // 4 per quad
+  uint32_t* quads32;          // S2M_MESH_QUADS_U32: 4 x u32 per quad instead (the reference's index type, lib.rs Quad)
   unsigned long long* status;
   unsigned* ticket;
   unsigned long long* n_quads;
@@ -337,6 +338,12 @@ k4_quads(QuadParams p) {
   if ((threadIdx.x & 31u) == 0) s_inv[threadIdx.x >> 5] = inv;
   __syncthreads();
   unsigned long long at = s_base + local;
+  if (p.quads32) {
+    for (unsigned k = 0; k < nvalid; ++k, ++at)
+      *reinterpret_cast<uint4*>(p.quads32 + 4ull * at) =
+          make_uint4((uint32_t)((long long)q[k][0] + p.index_offset), (uint32_t)((long long)q[k][1] + p.index_offset),
+                     (uint32_t)((long long)q[k][2] + p.index_offset), (uint32_t)((long long)q[k][3] + p.index_offset));
+  } else
   for (unsigned k = 0; k < nvalid; ++k, ++at) {
     ulonglong2* dst = reinterpret_cast<ulonglong2*>(p.quads + 4ull * at);
     dst[0] = make_ulonglong2((unsigned long long)((long long)q[k][0] + p.index_offset), (unsigned long long)((long long)q[k][1] + p.index_offset));
@@ -405,7 +412,7 @@ extern "C" int s2m_launch_k4b(const S2mK4bArgs* a, cudaStream_t stream) {
   p.vert_key = a->vert_key; p.vert_nibble = a->vert_nibble; p.v_begin = a->v_begin; p.v_end = a->v_end; p.quad_base = a->quad_base;
   p.cand_mask = a->cand_mask; p.word_prefix = a->word_prefix; p.cand_vrank = a->cand_vrank;
   p.words_x = a->words_x; p.res_y = a->res_y; p.z_first = a->z_first; p.label_add = a->label_add;
-  p.index_offset = a->index_offset; p.quads = a->quads; p.status = a->status; p.ticket = a->ticket;
+  p.index_offset = a->index_offset; p.quads = a->quads; p.quads32 = a->quads32; p.status = a->status; p.ticket = a->ticket;
   p.n_quads = a->n_quads; p.n_invalid = a->n_invalid;
   p.invalid_records = a->invalid_records; p.invalid_cursor = a->invalid_cursor; p.invalid_capacity = a->invalid_capacity;
   k4_quads<<<tiles, 256, 0, stream>>>(p);

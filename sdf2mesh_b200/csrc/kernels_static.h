@@ -45,6 +45,7 @@ typedef struct S2mK4bArgs {
   uint32_t words_x, res_y, z_first, label_add;
   long long index_offset;
   unsigned long long* quads;
+  unsigned* quads32;              /* non-NULL: write 4 x u32 per quad here instead of quads */
   unsigned long long* status;     /* >= s2m_k4b_tiles(v_end - v_begin) zeroed words */
   unsigned* ticket;               /* zeroed */
   unsigned long long* n_quads;    /* out: quad_base + quads of this launch */

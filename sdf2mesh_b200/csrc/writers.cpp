@@ -63,6 +63,8 @@ struct Part {
   s2m_result_info i;
   int64_t base;   // global index of this part's first own vertex
 };
+inline uint64_t quad_index(const s2m_result_info& m, uint64_t i) { return m.quads ? m.quads[i] : (uint64_t)m.quads32[i]; }
+
 struct Parts {
   std::vector<Part> parts;
   uint64_t n_vertices = 0, n_quads = 0;
@@ -86,7 +88,7 @@ int get_parts(const s2m_result* const* rs, int n, Parts* out, bool whole_mesh) {
     Part p;
     int st = s2m_result_get(rs[k], &p.i);
     if (st) return st;
-    if (p.i.n_quads && !p.i.quads) return fail(S2M_ERR_STATE, "s2m_mesh_finish has not been called");
+    if (p.i.n_quads && !p.i.quads && !p.i.quads32) return fail(S2M_ERR_STATE, "s2m_mesh_finish has not been called");
     p.base = p.i.global_vertex_base;
     if (k > 0 && p.base != out->parts.back().base + (int64_t)out->parts.back().i.n_vertices)
       return fail(S2M_ERR_STATE, "parts must be consecutive z-slabs with consecutive global vertex bases");
@@ -99,7 +101,7 @@ int get_parts(const s2m_result* const* rs, int n, Parts* out, bool whole_mesh) {
   for (size_t k = 0; k < out->parts.size(); ++k) {
     const Part& p = out->parts[k];
     for (uint64_t q = 0; q < 4 * p.i.n_quads; ++q)
-      if (!out->pos(p.i.quads[q], k)) return fail(S2M_ERR_STATE, "a quad refers to a vertex outside the given parts");
+      if (!out->pos(quad_index(p.i, q), k)) return fail(S2M_ERR_STATE, "a quad refers to a vertex outside the given parts");
   }
   return S2M_OK;
 }
@@ -127,7 +129,8 @@ int parallel_write(FILE* f, uint64_t n, uint64_t chunk, Fn fn) {
   return S2M_OK;
 }
 
-inline void tri_of_quad(const uint64_t* q, int t, uint64_t tri[3]) {  // lib.rs:199-204
+inline void tri_of_quad(const s2m_result_info& m, uint64_t quad, int t, uint64_t tri[3]) {  // lib.rs:199-204
+  const uint64_t q[4] = {quad_index(m, 4 * quad), quad_index(m, 4 * quad + 1), quad_index(m, 4 * quad + 2), quad_index(m, 4 * quad + 3)};
   if (t == 0) { tri[0] = q[2]; tri[1] = q[1]; tri[2] = q[0]; }
   else { tri[0] = q[0]; tri[1] = q[3]; tri[2] = q[2]; }
 }
@@ -150,7 +153,7 @@ int write_stl_ascii(const Parts& v, const char* path) {
       for (uint64_t q = b; q < e; ++q)
         for (int t = 0; t < 2; ++t) {
           uint64_t tri[3];
-          tri_of_quad(m.quads + 4 * q, t, tri);
+          tri_of_quad(m, q, t, tri);
           const float* p0 = v.pos(tri[0], k);
           const float* p1 = v.pos(tri[1], k);
           const float* p2 = v.pos(tri[2], k);
@@ -199,7 +202,7 @@ int write_ply_ascii(const Parts& v, const char* path) {
       for (uint64_t q = b; q < e; ++q)
         for (int t = 0; t < 2; ++t) {
           uint64_t tri[3];
-          tri_of_quad(m.quads + 4 * q, t, tri);
+          tri_of_quad(m, q, t, tri);
           int n = snprintf(buf, sizeof buf, "3 %u %u %u\n", (unsigned)tri[0], (unsigned)tri[1], (unsigned)tri[2]);  // Triangle<u32>
           out.append(buf, (size_t)n);
         }
@@ -228,7 +231,7 @@ int write_stl_binary(const Parts& v, const char* path) {
       for (uint64_t q = b; q < e; ++q)
         for (int t = 0; t < 2; ++t) {
           uint64_t tri[3];
-          tri_of_quad(m.quads + 4 * q, t, tri);
+          tri_of_quad(m, q, t, tri);
           const float* p[3] = {v.pos(tri[0], k), v.pos(tri[1], k), v.pos(tri[2], k)};
           float n[3];
           tri_normal(p[0], p[1], p[2], n);

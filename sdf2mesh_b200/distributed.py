@@ -52,11 +52,14 @@ def exclusive_bases(counts: Sequence[int]) -> List[int]:
 _GATHER_BUF = {}
 
 
-def allgather_counts(local_count: int, device=None) -> List[int]:
+def allgather_counts(local_count: int, device=None, ctx=None) -> List[int]:
     """one all-gather of a single int64 per rank over torch.distributed (nccl or gloo).
 
     One collective into one tensor and one device->host read (a per-rank `.item()` costs a device
-    synchronisation each: 8 of them took 2 ms of a 12 ms step on 8 GPUs)."""
+    synchronisation each: 8 of them took 2 ms of a 12 ms step on 8 GPUs).  With `ctx` (the engine
+    context of this rank) the result is read through `Context.read_device_words` -- a one-warp kernel
+    writing to mapped pinned memory on torch's current stream -- because a `.tolist()` is a D2H
+    memcpy that queues on the copy engine behind the slab's vertex copy (another 2 ms)."""
     import torch
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
@@ -69,6 +72,8 @@ def allgather_counts(local_count: int, device=None) -> List[int]:
     src, dst = _GATHER_BUF[key]
     src.fill_(int(local_count))
     dist.all_gather_into_tensor(dst, src)
+    if ctx is not None and dst.is_cuda and world <= 32:
+        return ctx.read_device_words(dst.data_ptr(), world, torch.cuda.current_stream(dst.device).cuda_stream)
     return [int(x) for x in dst.tolist()]
 
 
@@ -148,7 +153,7 @@ def mesh_slab(ctx, module, params, z_begin: int, z_end: int, gather=allgather_co
     from . import engine
     params.z_begin, params.z_end = int(z_begin), int(z_end)
     res = engine.mesh_begin(ctx, module, params)
-    counts = gather(res.info().n_vertices, device) if gather is allgather_counts else gather(res.info().n_vertices)
+    counts = gather(res.info().n_vertices, device, ctx) if gather is allgather_counts else gather(res.info().n_vertices)
     base = exclusive_bases(counts)[rank]
     res.finish(base)
     return res, base, counts

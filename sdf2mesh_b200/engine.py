@@ -34,6 +34,13 @@ class Context:
         check(lib().s2m_ctx_device_info(self._h, name, 256, ctypes.byref(sms), ctypes.byref(mem)))
         return name.value.decode(), sms.value, mem.value
 
+    def read_device_words(self, device_ptr: int, n: int, cuda_stream: int = 0):
+        """n (<= 32) u64 words from device memory, through a kernel + mapped pinned memory on
+        `cuda_stream` (a cudaStream_t handle; 0 = the context's stream) instead of a cudaMemcpy"""
+        out = (ctypes.c_uint64 * n)()
+        check(lib().s2m_read_device_words(self._h, ctypes.c_void_p(device_ptr), n, out, ctypes.c_void_p(cuda_stream)))
+        return [int(v) for v in out]
+
 
 class Module:
     """A compiled SDF (replaces create_shader_module + create_compute_pipeline)."""
@@ -147,7 +154,7 @@ class MeshResult:
         return MeshData(
             _view(i.positions, nv * 3, np.float32, (-1, 3)), _view(i.normals, nv * 3, np.float32, (-1, 3)),
             _view(i.cell_keys, nv, np.uint64), _view(i.sign_nibbles, nv, np.uint8),
-            _view(i.quads, nq * 4, np.uint64, (-1, 4)),
+            _view(i.quads32, nq * 4, np.uint32, (-1, 4)) if i.quads32 else _view(i.quads, nq * 4, np.uint64, (-1, 4)),
             _view(i.candidates, i.n_candidates if i.candidates else 0, np.uint64),
             _view(i.invalid_records, i.n_invalid_records * 6 if i.invalid_records else 0, np.uint64, (-1, 6)),
             i.n_invalid_quads, i.n_halo_vertices, i.n_candidates, t)

@@ -309,3 +309,42 @@ def test_watertight_mode_closes_the_2048_mesh_cracks(ctx):
     _, counts = np.unique(code, return_counts=True)
     assert (counts % 2 == 0).all() and (counts == 2).mean() > 0.99  # one vertex per cell: a few edges are shared by 4
     r.free()
+
+
+def test_u32_quad_indices(ctx, tmp_path):
+    """S2M_MESH_QUADS_U32: the reference's own index type (lib.rs Quad(u32, ..)); same values, same files,
+    and an index that would not fit is refused"""
+    name, res, bounds = "mandelbulb", 128, 5.0
+    m = module_for(ctx, name)
+    p, _ = s2m.params_from_cli(res, bounds, flags=s2m.MESH_QUADS_U32)
+    r = s2m.mesh_run(ctx, m, p)
+    o = oracle.mesh_run(name, res, bounds)
+    d = r.data()
+    assert d.quads.dtype == np.uint32
+    assert_same(d, o, "u32 quads")
+    ref = tmp_path / "ref.ply"
+    o.write_ply(ref)
+    r.write_mesh(tmp_path / "one.ply")
+    assert (tmp_path / "one.ply").read_bytes() == ref.read_bytes()
+    # z-slabs with u32 indices and global bases
+    parts, base = [], 0
+    for zb, ze in ((0, 50), (50, 90), (90, 127)):
+        p.z_begin, p.z_end = zb, ze
+        s = s2m.mesh_begin(ctx, m, p)
+        n_own = s.info().n_vertices
+        s.finish(base)
+        base += n_own
+        parts.append(s)
+    assert np.array_equal(np.concatenate([s.data().quads for s in parts]), o.quads)
+    s2m.write_mesh_parts(parts, tmp_path / "parts.ply")
+    assert (tmp_path / "parts.ply").read_bytes() == ref.read_bytes()
+    for s in parts:
+        s.free()
+    p.z_begin, p.z_end = 0, 50
+    s = s2m.mesh_begin(ctx, m, p)
+    with pytest.raises(s2m.S2mError) as e:
+        s.finish(2 ** 32 - 5)
+    assert "32 bits" in str(e.value)
+    s.free()
+    r.free()
+    o.free()
