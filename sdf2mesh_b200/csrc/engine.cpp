@@ -433,6 +433,10 @@ struct s2m_result {
   struct Span { int kind; size_t e0, e1; };  // kind: 0 K1, 1 K2, 2 K3, 3 K4a, 4 K4b, 5 copy
   std::vector<Span> spans;
   bool finished = false;
+  // two-call form: the last chunk's vertex copy is issued by finish(), after the caller's count exchange --
+  // a bulk copy in flight delays every small device->host read behind it (PCIe), including that exchange's result
+  bool deferred_copy = false;
+  uint64_t deferred_v0 = 0;
   bool quads_u32() const { return (params.flags & S2M_MESH_QUADS_U32) != 0; }
   size_t quad_bytes() const { return quads_u32() ? 16 : 32; }  // bytes per quad, device and host
 };
@@ -647,9 +651,9 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
     uint32_t n_chunks = (r->nz + zc - 1) / zc;
     if (!dense && !getenv("S2M_NO_CHUNK_OVERLAP")) {
       // a slab that fits the budget in one piece is still cut into 2-4 chunks when it is large enough
-      // (>= 0.5 G voxels per chunk) for the two-stream overlap and the early output copies to pay
+      // (>= 0.15 G voxels per chunk) for the two-stream overlap and the early output copies to pay
       const double voxels = (double)g.res[0] * g.res[1] * r->nz;
-      const uint32_t want = (uint32_t)std::min(4.0, voxels / 5.0e8);
+      const uint32_t want = (uint32_t)std::min(4.0, voxels / 1.5e8);
       n_chunks = std::max(n_chunks, std::min(want, r->nz));
     }
     const uint32_t even = (r->nz + n_chunks - 1) / n_chunks;  // equal chunks instead of a short last one
@@ -814,6 +818,9 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       const uint64_t own = vert_total - std::min<uint64_t>(vert_total, r->n_halo);
       if (own > r->cap_v || (fuse_quads && quad_total > r->cap_q)) {
         r->streamed = false;  // the hint was too small: everything is copied at the end instead
+      } else if (!fuse_quads && ci + 1 == chunks.size()) {
+        r->deferred_copy = true;  // see s2m_result::deferred_copy
+        r->deferred_v0 = vert_done;
       } else {
         const size_t e = take_event(c, r);
         CUDA_TRY(cudaEventRecord(c->ev_pool[e], s));
@@ -878,6 +885,12 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   r->global_base = global_vertex_base;
   if (r->quads_u32() && (global_vertex_base < 0 || (uint64_t)global_vertex_base + (r->n_vert_total - r->n_halo) > 0xffffffffull))
     return fail(S2M_ERR_UNSUPPORTED, "S2M_MESH_QUADS_U32: vertex indices of this slab do not fit 32 bits");
+  if (r->deferred_copy && r->streamed) {
+    SPAN_BEGIN(5, c->copy_stream);
+    if ((st = copy_out(c, r, c->copy_stream, r->deferred_v0, r->n_vert_total, 0, 0))) return st;
+    SPAN_END(c->copy_stream);
+    r->deferred_copy = false;
+  }
   if (!r->quads_done) {
     // ---- K4b over all own vertices with the global base, then the quad copy
     if ((st = launch_k4b(c, r, s, 0, r->n_vert_total, 0, (long long)global_vertex_base - (long long)r->n_halo))) return st;
