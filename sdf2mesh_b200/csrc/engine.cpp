@@ -405,8 +405,8 @@ int make_grid(const s2m_mesh_params* p, GridDev* g) {
   return S2M_OK;
 }
 
-int launch(CUfunction_t f, dim3 grid, dim3 block, cudaStream_t st, void** args, const char* name) {
-  CUresult_t r = driver().cuLaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, 0, st, args, nullptr);
+int launch(CUfunction_t f, dim3 grid, dim3 block, cudaStream_t st, void** args, const char* name, unsigned dyn_smem = 0) {
+  CUresult_t r = driver().cuLaunchKernel(f, grid.x, grid.y, grid.z, block.x, block.y, block.z, dyn_smem, st, args, nullptr);
   if (r) return fail(S2M_ERR_CUDA, std::string("cuLaunchKernel(") + name + "): " + cu_err(r));
   return S2M_OK;
 }
@@ -793,6 +793,8 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
                       c->cand_vrank.as<unsigned>() + cand_done, status + 2 + k3_tiles, tickets + 1, d_cnt + C_NVERT, d_cnt + C_NHALO};
       void* a4[] = {&gd, &ck, &nc, &vbase, &label_add, &halo_below, &want_normals, &sv, &vo};
       SPAN_BEGIN(3, s);
+      // (capping K4a's blocks per SM with unused dynamic shared memory, to keep K1 blocks of the next chunk
+      // resident beside them, was measured: K4a 4.3 -> 6.4 ms and the run got 2 ms slower)
       if ((st = launch(m->k4, dim3(k4_tiles), dim3(128), s, a4, "s2m_k4_vertices"))) return st;
       SPAN_END(s);
       r->t.launches += 1;
