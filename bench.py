@@ -271,6 +271,19 @@ def main():
         time.sleep(0.35 - wall)  # let at least a couple of 100 ms samples land
     clocks = sampler.stop(t_start, t_end)
 
+    # The timed steps run K1 of chunk c+1 beside K3/K4a/K4b of chunk c (two streams), so K1's event span
+    # contains those kernels' share of the machine.  Two extra UNTIMED steps with the overlap switched
+    # off give every kernel's duration when it has the GPU to itself: that is what the roofline and the
+    # ncu launch list (serialised by construction) are compared on.
+    serial = None
+    if world == 1:
+        os.environ["S2M_NO_CHUNK_OVERLAP"] = "1"
+        try:
+            step()
+            serial = step()[3]
+        finally:
+            del os.environ["S2M_NO_CHUNK_OVERLAP"]
+
     dev_ms = sum(s[3]["device_ms"] for s in stats)
     tot_ms = sum(s[3]["total_ms"] for s in stats)
     launches = sum(s[3]["launches"] for s in stats)
@@ -305,7 +318,7 @@ def main():
     # K1 algorithmic bytes: one f32 per grid corner it writes (4 B/voxel slab write)
     planes = (ze - max(zb - 1, 0)) + 1 if world > 1 else n_slices + 1
     k1_bytes = 4.0 * (res + 1) * (res + 1) * planes
-    k1_s = per["k1_slab_ms"] * 1e-3
+    k1_s = (serial["k1_slab_ms"] if serial else per["k1_slab_ms"]) * 1e-3
     # K2 reads K1's corner-class planes (8 B per 32 corners) and writes 1 bit per cell
     k2_bytes = (res + 1.0) * (((res + 1 + 31) // 32) * 8.0) * planes + (res * res * (planes - 1)) / 8.0
     full, early, frac_in = FLOPS_PER_EVAL.get(osdf, (100.0, 100.0, 1.0))
@@ -328,14 +341,21 @@ def main():
         "jit_ms": jit_ms,
         "roofline": {"kernel": "s2m_k1_slab", "bound": "hbm", "achieved": k1_bytes / k1_s / 1e9 if k1_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (k1_bytes / k1_s / 1e9 / hbm_peak) if k1_s > 0 else None, "traffic": K1_TRAFFIC[wl]["bytes_per_launch"] if traffic_known else None, "traffic_detail": K1_TRAFFIC[wl] if traffic_known else None, "peak_source": peak_src,
-                     "note": "K1 is FP32/issue bound for this SDF, not HBM bound (ncu: issue slots ~90 % busy, DRAM ~5 %); see fp32. "
-                             "achieved = 4 B per corner written (SURVEY 8d) / K1 time",
+                     "note": "K1 is FP32/issue bound for this SDF, not HBM bound (ncu: issue slots ~96 % busy, DRAM ~6 %); see fp32. "
+                             "achieved = 4 B per corner written (SURVEY 8d) / K1 time with the GPU to itself (kernels_serialized; "
+                             "in the timed steps K1 shares the machine with the previous chunk's K3/K4a/K4b, see kernels)",
                      "fp32": {"achieved_tflops_source_level": flops / k1_s / 1e12 if k1_s > 0 else None, "peak_tflops_nominal": fp32_peak,
                               "frac": flops / k1_s / 1e12 / fp32_peak if k1_s > 0 else None}},
         "kernels": {"k1_slab": {"ms": per["k1_slab_ms"], "GBps": k1_bytes / k1_s / 1e9 if k1_s > 0 else None},
                     "k2_classify": {"ms": per["k2_classify_ms"], "GBps": k2_bytes / (per["k2_classify_ms"] * 1e-3) / 1e9 if per["k2_classify_ms"] > 0 else None},
                     "k3_compact": {"ms": per["k3_compact_ms"]}, "k4_vertices": {"ms": per["k4_vertices_ms"]}, "k4_quads": {"ms": per["k4_quads_ms"]},
-                    "d2h": {"ms": per["d2h_ms"]}, "device_total_ms": dev_ms / args.steps, "event_total_ms": tot_ms / args.steps},
+                    "d2h": {"ms": per["d2h_ms"]}, "device_total_ms": dev_ms / args.steps, "event_total_ms": tot_ms / args.steps,
+                    "note": "event spans on each kernel's own stream; K1 (producer stream) overlaps K3/K4a/K4b (consumer stream), so the spans add up to more than device_total_ms"},
+        "kernels_serialized": None if not serial else {
+            "k1_slab_ms": serial["k1_slab_ms"], "k2_classify_ms": serial["k2_classify_ms"], "k3_compact_ms": serial["k3_compact_ms"],
+            "k4_vertices_ms": serial["k4_vertices_ms"], "k4_quads_ms": serial["k4_quads_ms"], "device_ms": serial["device_ms"],
+            "k1_share": serial["k1_slab_ms"] / serial["device_ms"],
+            "note": "one untimed step with S2M_NO_CHUNK_OVERLAP=1: each kernel alone on the GPU, comparable with the ncu launch list in profiles/"},
     }
     if not args.no_cpu_baseline and world == 1:
         v, cores, dt, desc = cpu_reference_sample(osdf, res, bounds, args.cpu_baseline_slices)

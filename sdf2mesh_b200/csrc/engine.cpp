@@ -304,6 +304,11 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   if (const char* e = getenv("S2M_K1_ROWS")) m->k1_rows = atoi(e) == 2 ? 2u : 1u;  // experiment knob
   const std::string rows_opt = "-DS2M_K1_ROWS=" + std::to_string(m->k1_rows);
   opts.push_back(rows_opt.c_str());
+  std::string minb_opt;
+  if (const char* e = getenv("S2M_K1_MINBLOCKS")) {  // experiment knob
+    minb_opt = std::string("-DS2M_K1_MINBLOCKS=") + std::to_string(std::max(1, std::min(8, atoi(e))));
+    opts.push_back(minb_opt.c_str());
+  }
   r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);

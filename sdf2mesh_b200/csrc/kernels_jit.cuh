@@ -63,7 +63,10 @@ __device__ __forceinline__ unsigned s2m_k1_class_byte(const float v[4], float ta
          (v[0] < -tau ? 16u : 0u) | (v[1] < -tau ? 32u : 0u) | (v[2] < -tau ? 64u : 0u) | (v[3] < -tau ? 128u : 0u);
 }
 
-extern "C" __global__ void __launch_bounds__(256)
+#ifndef S2M_K1_MINBLOCKS
+#define S2M_K1_MINBLOCKS 1   /* resident 256-thread blocks per SM the register allocator must allow (8 = at most 32 registers) */
+#endif
+extern "C" __global__ void __launch_bounds__(256, S2M_K1_MINBLOCKS)
 s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned n_planes,
             float tau, uint2* __restrict__ cls, unsigned cls_words) {
   const unsigned x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
