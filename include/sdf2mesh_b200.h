@@ -133,7 +133,8 @@ typedef struct s2m_mesh_params {
   uint32_t dims[3];
   uint32_t flags;
   uint32_t z_begin, z_end;     /* z-slab of true cell slices [z_begin, z_end); 0,0 = whole grid */
-  float tau_voxels;            /* candidate band half-width in voxels; 0 = default (0.5) */
+  float tau_voxels;            /* candidate band half-width in voxels; 0 = default: max(1/16, 443 x the 1-ulp coordinate
+                                  mismatch between the reference's corners and the slab's, in voxels) */
   uint64_t slab_budget_bytes;  /* max bytes of corner slab resident at once; 0 = default */
 } s2m_mesh_params;
 

@@ -621,7 +621,15 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
   r->words_x = (g.res[0] + 31u) / 32u;
   if (r->halo) fuse_quads = false;  // a halo means there are lower slabs: the global vertex base comes later
   const float min_size = std::min(g.size[0], std::min(g.size[1], g.size[2]));
-  const float tau = (p->tau_voxels > 0.0f ? p->tau_voxels : 0.5f) * min_size;
+  // Candidate band.  The reference's corner coordinate (min + size) and the slab's (bmin + size*(i+1))
+  // differ by at most 1 ulp of the coordinate; in voxels that is 2^-23 * max|coordinate| / size.  The
+  // default band tolerates field changes of up to 256x that move (a true SDF changes by 1x), and is
+  // never thinner than 1/16 voxel.
+  float ulp_voxels = 0.0f;
+  for (int a = 0; a < 3; ++a)
+    ulp_voxels = std::max(ulp_voxels, std::max(std::fabs(p->bb_min[a]), std::fabs(p->bb_max[a])) * 1.1920929e-7f / g.size[a]);
+  const float tau_default = std::max(0.0625f, 256.0f * 1.7320508f * ulp_voxels);
+  const float tau = (p->tau_voxels > 0.0f ? p->tau_voxels : tau_default) * min_size;
 
   Trace tr;
   c->busy = true;

@@ -92,7 +92,9 @@ def test_candidates_are_a_superset_and_match_numpy(ctx):
     d = r.data()
     slab = np.stack([s2m.debug_slab_plane(ctx, mod, p, z) for z in range(res + 1)])  # [z][y][x]
     size = (np.float32(bmax[0]) - np.float32(bmin[0])) / np.float32(res - 1)
-    tau = np.float32(0.5) * size
+    # default band (engine.cpp): max(1/16, 256 * sqrt(3) * ulp-of-coordinate-in-voxels) voxels
+    ulp_voxels = np.float32(max(abs(bmin[0]), abs(bmax[0]))) * np.float32(1.1920929e-7) / size
+    tau = np.float32(max(np.float32(0.0625), np.float32(256.0) * np.float32(1.7320508) * ulp_voxels)) * size
     P, N = slab > tau, slab < -tau
 
     def all8(m):
@@ -105,7 +107,14 @@ def test_candidates_are_a_superset_and_match_numpy(ctx):
     assert np.array_equal(d.candidates, want)
     vert = (d.keys - (np.uint64(1) << np.uint64(32)))
     assert np.isin(vert, d.candidates).all()
+    keys, quads = d.keys.copy(), d.quads.copy()
     r.free()
+    # an explicit band: wider band, more candidates, same mesh
+    p.tau_voxels = 0.5
+    r2 = s2m.mesh_run(ctx, mod, p)
+    d2 = r2.data()
+    assert d2.n_candidates > len(want) and np.array_equal(d2.keys, keys) and np.array_equal(d2.quads, quads)
+    r2.free()
 
 
 def test_cost_probe(ctx):
