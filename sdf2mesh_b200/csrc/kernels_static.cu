@@ -17,6 +17,7 @@
 //                   search, stable single-pass emission of 64-bit-index quads.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels_static.h"
 #include "s2m_scan.cuh"
@@ -170,9 +171,14 @@ k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t row
 
 // ------------------------------------------------------------------------------------------ K3
 constexpr int K3_THREADS = 256;
-constexpr int K3_WORDS_PER_THREAD = 16;  // 4 x uint4
-constexpr int K3_TILE_WORDS = K3_THREADS * K3_WORDS_PER_THREAD;
+constexpr int K3_WPT_DEFAULT = 16;
+// mask words per thread (4, 8 or 16 = 1, 2 or 4 uint4 loads); S2M_K3_WPT selects at run time
+static int k3_wpt() {
+  static const int v = [] { const char* e = getenv("S2M_K3_WPT"); const int w = e ? atoi(e) : 0; return (w == 4 || w == 8 || w == 16) ? w : K3_WPT_DEFAULT; }();
+  return v;
+}
 
+template <int K3_WORDS_PER_THREAD>
 __global__ void __launch_bounds__(K3_THREADS)
 k3_compact(const uint32_t* __restrict__ cand_mask, unsigned long long n_words, uint32_t words_x, uint32_t res_y,
            uint32_t z_offset, uint32_t* __restrict__ word_prefix, unsigned long long* __restrict__ cand_key,
@@ -183,6 +189,7 @@ k3_compact(const uint32_t* __restrict__ cand_mask, unsigned long long n_words, u
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const unsigned tile = s_tile;
+  constexpr int K3_TILE_WORDS = K3_THREADS * K3_WORDS_PER_THREAD;
   const unsigned long long w0 = (unsigned long long)tile * K3_TILE_WORDS + (unsigned long long)threadIdx.x * K3_WORDS_PER_THREAD;
   uint32_t m[K3_WORDS_PER_THREAD];
   // a chunk's region starts at a multiple of the per-slice word count, which need not be 16-byte aligned
@@ -394,14 +401,18 @@ extern "C" int s2m_launch_k2_bits(const S2mK2Args* a, cudaStream_t stream) {
 }
 
 extern "C" unsigned s2m_k3_tiles(unsigned long long n_words) {
-  return (unsigned)((n_words + K3_TILE_WORDS - 1) / K3_TILE_WORDS);
+  const unsigned long long tile_words = (unsigned long long)K3_THREADS * k3_wpt();
+  return (unsigned)((n_words + tile_words - 1) / tile_words);
 }
 
 extern "C" int s2m_launch_k3(const S2mK3Args* a, cudaStream_t stream) {
   const unsigned tiles = s2m_k3_tiles(a->n_words);
   if (!tiles) return 0;
-  k3_compact<<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->n_words, a->words_x, a->res_y, a->z_offset,
-                                               a->word_prefix, a->cand_key, a->base, a->status, a->ticket);
+  switch (k3_wpt()) {
+    case 4: k3_compact<4><<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->n_words, a->words_x, a->res_y, a->z_offset, a->word_prefix, a->cand_key, a->base, a->status, a->ticket); break;
+    case 8: k3_compact<8><<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->n_words, a->words_x, a->res_y, a->z_offset, a->word_prefix, a->cand_key, a->base, a->status, a->ticket); break;
+    default: k3_compact<16><<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->n_words, a->words_x, a->res_y, a->z_offset, a->word_prefix, a->cand_key, a->base, a->status, a->ticket); break;
+  }
   return (int)cudaGetLastError();
 }
 
