@@ -356,6 +356,27 @@ ExprP Builder::binary(Op op, ExprP a, ExprP b) {
     return e;
   }
   if (a->ty.is_bool() || b->ty.is_bool()) error("arithmetic on bool operands");
+  if (op == Op::Shl || op == Op::Shr) {
+    // e1 << e2: the result has e1's type; e2 is an unsigned (GLSL: any integer) scalar or a vector of e1's width
+    if (!a->ty.is_int() || !b->ty.is_int() || a->ty.is_matrix() || b->ty.is_matrix()) error("shift needs integer operands, found " + a->ty.str() + " and " + b->ty.str());
+    if (b->ty.is_vector() && b->ty.n != a->ty.n) error("shift count width differs from the shifted value");
+    ConstVal ca, cb;
+    if (a->ty.is_abstract() && b->ty.is_abstract() && const_eval(*a, &ca) && const_eval(*b, &cb)) {
+      ConstVal r = ca;
+      for (int c = 0; c < ca.ty.n; ++c) {
+        const int64_t sh = cb.i[cb.ty.n > 1 ? c : 0];
+        if (sh < 0 || sh > 62) error("shift count out of range");
+        r.i[c] = op == Op::Shl ? (ca.i[c] << sh) : (ca.i[c] >> sh);
+      }
+      return lit_from(r);
+    }
+    a = concretize(a);
+    if (b->ty.is_abstract()) b = coerce(b, b->ty.with_sk(Sk::U32), "shift count");
+    if (lang == Lang::Wgsl && b->ty.sk != Sk::U32) error("shift count must be u32, found " + b->ty.str());
+    ExprP e = mk(Expr::Binary, a->ty);
+    e->op = op; e->args = {a, b};
+    return e;
+  }
   if (a->ty.is_matrix() || b->ty.is_matrix()) {
     // linear algebra: mat*vec, vec*mat, mat*mat, mat*scalar, scalar*mat, mat/scalar, mat+-mat
     if (a->ty.is_abstract()) a = concretize(a);
@@ -406,7 +427,6 @@ ExprP Builder::binary(Op op, ExprP a, ExprP b) {
   } else error("operands of different types: " + a->ty.str() + " and " + b->ty.str());
   const bool bitop = op == Op::BitAnd || op == Op::BitOr || op == Op::BitXor || op == Op::Shl || op == Op::Shr;
   if (bitop && !(sk == Sk::I32 || sk == Sk::U32 || sk == Sk::AInt)) error("bit operation on non-integer operands");
-  if ((op == Op::Shl || op == Op::Shr) && n > 1) unsupported("vector shifts");
   ExprP e = mk(Expr::Binary, is_cmp(op) ? Type::vec(Sk::Bool, n) : Type::vec(sk, n));
   e->op = op; e->args = {a, b};
   return e;
@@ -450,6 +470,16 @@ ExprP Builder::index(ExprP base, ExprP idx) {
   ExprP e = mk(Expr::Index, rt);
   e->args = {base, idx};
   return e;
+}
+
+ExprP Builder::bitcast(Sk target, ExprP e) {
+  e = concretize(e);
+  if (!(e->ty.is_scalar() || e->ty.is_vector()) || e->ty.is_bool()) error("bitcast of " + e->ty.str());
+  if (target != Sk::F32 && target != Sk::I32 && target != Sk::U32) error("bitcast to a non-numeric type");
+  ExprP c = mk(Expr::Call, e->ty.with_sk(target));
+  c->callee = target == Sk::F32 ? "bits_f" : target == Sk::I32 ? "bits_i" : "bits_u";
+  c->args.push_back(e);
+  return c;
 }
 
 ExprP Builder::array_length(ExprP base) {
@@ -610,8 +640,9 @@ const BuiltinInfo kBuiltins[] = {
     {"atan", "atan2", 2, 'm', 2},    {"step", "step", 2, 'm', 3},     {"mod", "mod", 2, 'm', 2},       {"distance", "distance", 2, 's', 3},
     {"dot", "dot", 2, 's', 3},       {"cross", "cross", 2, 'x', 3},   {"reflect", "reflect", 2, 'r', 3},
     {"clamp", "clamp", 3, 'n', 3},   {"mix", "mix", 3, 'm', 3},       {"smoothstep", "smoothstep", 3, 'm', 3}, {"fma", "fma", 3, 'm', 3},
-    {"select", "select", 3, 'S', 1}, {"any", "any", 1, 'b', 3},       {"all", "all", 1, 'b', 3},
+    {"select", "select", 3, 'S', 3}, {"any", "any", 1, 'b', 3},       {"all", "all", 1, 'b', 3},
     {"transpose", "transpose", 1, 'T', 3}, {"determinant", "determinant", 1, 'D', 3},
+    {"refract", "refract", 3, 'R', 3}, {"faceForward", "faceforward", 3, 'F', 1}, {"faceforward", "faceforward", 3, 'F', 2},
 };
 }  // namespace
 
@@ -661,12 +692,13 @@ ExprP Builder::call_builtin(const std::string& name, std::vector<ExprP> args) {
     if (!a->ty.is_abstract()) all_abstract = false;
     if (!a->ty.is_int()) all_int = false;
   }
-  if (bi->kind == 'n' && all_int && !all_abstract) {  // integer abs / min / max / clamp
-    if (n != 1) unsupported("integer vector " + name + "()");
+  if ((bi->kind == 'n' || std::string(bi->canon) == "sign") && all_int && !all_abstract) {  // integer abs / min / max / clamp / sign
     Sk sk = Sk::I32;
     for (const ExprP& a : args) if (!a->ty.is_abstract()) sk = a->ty.sk;
-    for (ExprP& a : args) a = coerce(a, Type::scalar(sk), "integer builtin argument");
-    ExprP e = call(Type::scalar(sk));
+    for (const ExprP& a : args) if (!a->ty.is_abstract() && a->ty.sk != sk) error("integer arguments of different types to " + name + "()");
+    if (std::string(bi->canon) == "sign" && sk == Sk::U32) error("sign() of an unsigned value");
+    for (ExprP& a : args) a = coerce(a, a->ty.with_sk(sk), "integer builtin argument");
+    ExprP e = call(Type::vec(sk, n));
     e->callee = std::string("i_") + bi->canon;
     return e;
   }
@@ -695,6 +727,12 @@ ExprP Builder::call_builtin(const std::string& name, std::vector<ExprP> args) {
       return call(Type::vec(sk, n));
     case 'r':
       if (n == 1 || args[0]->ty.n != args[1]->ty.n) error("reflect() needs two vectors of the same size");
+      return call(Type::vec(sk, n));
+    case 'R':
+      if (n == 1 || args[0]->ty.n != n || args[1]->ty.n != n || !args[2]->ty.is_scalar()) error("refract() needs two vectors of the same size and a scalar");
+      return call(Type::vec(sk, n));
+    case 'F':
+      if (n == 1 || args[0]->ty.n != n || args[1]->ty.n != n || args[2]->ty.n != n) error(name + "() needs three vectors of the same size");
       return call(Type::vec(sk, n));
     default:
       return call(Type::vec(sk, n));

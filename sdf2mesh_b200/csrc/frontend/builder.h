@@ -32,6 +32,7 @@ class Builder {
   ExprP member(ExprP base, const std::string& name);   // struct field or vector swizzle
   ExprP index(ExprP base, ExprP idx);                  // a[i], v[i], m[i] (constant or dynamic index)
   ExprP array_length(ExprP base);                      // GLSL a.length()
+  ExprP bitcast(Sk target, ExprP e);                   // WGSL bitcast<T>(e), GLSL floatBitsToInt(e) ...: same width, other scalar kind
   Module* module = nullptr;                            // for interning array types
   ExprP construct(Type target, bool infer_sk, std::vector<ExprP> args);  // vecN(...) / scalar casts
   ExprP call_builtin(const std::string& name, std::vector<ExprP> args);  // returns null if not a builtin

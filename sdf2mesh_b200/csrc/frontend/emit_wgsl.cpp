@@ -106,6 +106,7 @@ class WgslWriter {
   }
   static std::string wgsl_builtin(const std::string& canon) {
     if (canon == "inversesqrt") return "inverseSqrt";
+    if (canon == "faceforward") return "faceForward";
     return canon;
   }
 
@@ -128,12 +129,16 @@ class WgslWriter {
             {Op::Add, "+"}, {Op::Sub, "-"}, {Op::Mul, "*"}, {Op::Div, "/"}, {Op::Rem, "%"}, {Op::And, "&&"}, {Op::Or, "||"},
             {Op::BitAnd, "&"}, {Op::BitOr, "|"}, {Op::BitXor, "^"}, {Op::Shl, "<<"}, {Op::Shr, ">>"}, {Op::Lt, "<"},
             {Op::Le, "<="}, {Op::Gt, ">"}, {Op::Ge, ">="}, {Op::Eq, "=="}, {Op::Ne, "!="}};
-        return "(" + expr(*e.args[0]) + " " + ops.at(e.op) + " " + expr(*e.args[1]) + ")";
+        std::string rhs = expr(*e.args[1]);
+        if ((e.op == Op::Shl || e.op == Op::Shr) && e.args[1]->ty.sk != Sk::U32)  // WGSL shift counts are u32
+          rhs = type_name(e.args[1]->ty.with_sk(Sk::U32)) + "(" + rhs + ")";
+        return "(" + expr(*e.args[0]) + " " + ops.at(e.op) + " " + rhs + ")";
       }
       case Expr::Ternary:  // both sides are pure expressions here
         return "select(" + expr(*e.args[2]) + ", " + expr(*e.args[1]) + ", " + expr(*e.args[0]) + ")";
       case Expr::Call: {
         std::string name = e.callee;
+        if (name.compare(0, 5, "bits_") == 0) return "bitcast<" + type_name(e.ty) + ">(" + expr(*e.args[0]) + ")";
         if (name.compare(0, 2, "i_") == 0) name = name.substr(2);
         int n = 1;
         for (const ExprP& a : e.args) n = std::max(n, a->ty.n);
@@ -143,7 +148,7 @@ class WgslWriter {
         }
         std::string s = wgsl_builtin(name) + "(";
         for (size_t i = 0; i < e.args.size(); ++i) {
-          const bool keep_scalar = (name == "mix" && i == 2) || name == "dot" || name == "length" || name == "distance" || name == "select" || name == "any" || name == "all";
+          const bool keep_scalar = (name == "mix" && i == 2) || (name == "refract" && i == 2) || name == "dot" || name == "length" || name == "distance" || name == "select" || name == "any" || name == "all";
           s += (i ? ", " : "") + (keep_scalar ? expr(*e.args[i]) : splat_to(*e.args[i], n));
         }
         return s + ")";

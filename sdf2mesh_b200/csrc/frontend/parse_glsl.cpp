@@ -633,6 +633,30 @@ class GlslParser : public ParserBase {
         return b.call_user(best, args);
       }
       if (name == "texture" || name == "texelFetch" || name == "textureLod") b.unsupported("texture sampling (" + name + ")");
+      // bit reinterpretation, vector relational functions, mix with a bool selector
+      if (args.size() == 1 && (name == "floatBitsToInt" || name == "floatBitsToUint" || name == "intBitsToFloat" || name == "uintBitsToFloat")) {
+        const bool from_float = name[0] == 'f';
+        if (from_float != args[0]->ty.is_float()) b.error(name + "() argument has the wrong type: " + args[0]->ty.str());
+        return b.bitcast(name == "floatBitsToInt" ? Sk::I32 : name == "floatBitsToUint" ? Sk::U32 : Sk::F32, args[0]);
+      }
+      if (args.size() == 2) {
+        static const std::map<std::string, Op> rel = {{"lessThan", Op::Lt}, {"lessThanEqual", Op::Le}, {"greaterThan", Op::Gt},
+                                                       {"greaterThanEqual", Op::Ge}, {"equal", Op::Eq}, {"notEqual", Op::Ne}};
+        auto it = rel.find(name);
+        if (it != rel.end()) {
+          if (!args[0]->ty.is_vector() || !args[1]->ty.is_vector()) b.error(name + "() needs vector operands");
+          return b.binary(it->second, args[0], args[1]);
+        }
+      }
+      if (args.size() == 1 && name == "not") {
+        if (!args[0]->ty.is_vector() || !args[0]->ty.is_bool()) b.error("not() needs a bool vector");
+        return b.unary(Op::Not, args[0]);
+      }
+      if (args.size() == 3 && name == "mix" && args[2]->ty.is_bool()) {  // mix(x, y, bool / bvec): component selection
+        ExprP e = b.call_builtin("select", {args[0], args[1], args[2]});
+        if (!e) b.error("mix() with a bool selector: bad operands");
+        return e;
+      }
       ExprP e = b.call_builtin(name, args);
       if (!e) b.error("unknown function '" + name + "'");
       return e;

@@ -669,6 +669,18 @@ class WgslParser : public ParserBase {
       std::vector<ExprP> args = parse_args();
       return b.construct(ty, infer, args);
     }
+    if (name == "bitcast" && is_punct("<", 1)) {  // bitcast<T>(e): T = f32 / i32 / u32 or a vector of them
+      advance();
+      expect("<");
+      Type t = parse_type();
+      expect_close_angle();
+      std::vector<ExprP> args = parse_args();
+      if (args.size() != 1) b.error("bitcast takes one argument");
+      if (!(t.is_scalar() || t.is_vector())) b.error("bitcast to " + t.str());
+      ExprP e = b.bitcast(t.sk, args[0]);
+      if (e->ty != t) b.error("bitcast between types of different size: " + args[0]->ty.str() + " -> " + t.str());
+      return e;
+    }
     if (is_punct("(", 1)) {
       advance();
       std::vector<ExprP> args = parse_args();
@@ -677,7 +689,6 @@ class WgslParser : public ParserBase {
         if (it->second->is_entry) b.error("entry point '" + name + "' cannot be called");
         return b.call_user(it->second, args);
       }
-      if (name == "bitcast") b.unsupported("bitcast");
       ExprP e = b.call_builtin(name, args);
       if (!e) b.error("unknown function '" + name + "'");
       return e;

@@ -21,6 +21,9 @@ struct vec4 { float x, y, z, w; };
 struct ivec2 { int x, y; };
 struct ivec3 { int x, y, z; };
 struct ivec4 { int x, y, z, w; };
+struct uvec2 { unsigned x, y; };
+struct uvec3 { unsigned x, y, z; };
+struct uvec4 { unsigned x, y, z, w; };
 struct bvec2 { bool x, y; };
 struct bvec3 { bool x, y, z; };
 struct bvec4 { bool x, y, z, w; };
@@ -31,6 +34,16 @@ S2M_HD vec4 mk4(float x, float y, float z, float w) { vec4 v; v.x = x; v.y = y; 
 S2M_HD ivec2 mki2(int x, int y) { ivec2 v; v.x = x; v.y = y; return v; }
 S2M_HD ivec3 mki3(int x, int y, int z) { ivec3 v; v.x = x; v.y = y; v.z = z; return v; }
 S2M_HD ivec4 mki4(int x, int y, int z, int w) { ivec4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+S2M_HD uvec2 mku2(unsigned x, unsigned y) { uvec2 v; v.x = x; v.y = y; return v; }
+S2M_HD uvec3 mku3(unsigned x, unsigned y, unsigned z) { uvec3 v; v.x = x; v.y = y; v.z = z; return v; }
+S2M_HD uvec4 mku4(unsigned x, unsigned y, unsigned z, unsigned w) { uvec4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
+S2M_HD uvec3 mku3(const uvec2& a, unsigned b) { return mku3(a.x, a.y, b); }
+S2M_HD uvec3 mku3(unsigned a, const uvec2& b) { return mku3(a, b.x, b.y); }
+S2M_HD uvec4 mku4(const uvec3& a, unsigned b) { return mku4(a.x, a.y, a.z, b); }
+S2M_HD uvec4 mku4(const uvec2& a, const uvec2& b) { return mku4(a.x, a.y, b.x, b.y); }
+S2M_HD uvec2 splatu2(unsigned a) { return mku2(a, a); }
+S2M_HD uvec3 splatu3(unsigned a) { return mku3(a, a, a); }
+S2M_HD uvec4 splatu4(unsigned a) { return mku4(a, a, a, a); }
 S2M_HD bvec2 mkb2(bool x, bool y) { bvec2 v; v.x = x; v.y = y; return v; }
 S2M_HD bvec3 mkb3(bool x, bool y, bool z) { bvec3 v; v.x = x; v.y = y; v.z = z; return v; }
 S2M_HD bvec4 mkb4(bool x, bool y, bool z, bool w) { bvec4 v; v.x = x; v.y = y; v.z = z; v.w = w; return v; }
@@ -77,6 +90,10 @@ S2M_HD void cset(ivec3& v, int i, int f) { if (i == 0) v.x = f; else if (i == 1)
 S2M_HD void cset(ivec4& v, int i, int f) { if (i == 0) v.x = f; else if (i == 1) v.y = f; else if (i == 2) v.z = f; else v.w = f; }
 
 
+S2M_HD unsigned cget(const uvec2& v, int i) { return i == 0 ? v.x : v.y; }
+S2M_HD unsigned cget(const uvec3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+S2M_HD unsigned cget(const uvec4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
 /* multi-component swizzle reads: swz3(v, 0, 2, 1) == v.xzy */
 S2M_HD vec2 swz2(const vec2& v, int a, int b) { return mk2(cget(v, a), cget(v, b)); }
 S2M_HD vec2 swz2(const vec3& v, int a, int b) { return mk2(cget(v, a), cget(v, b)); }
@@ -113,17 +130,103 @@ S2M_HD vec2 operator-(const vec2& a) { return mk2(-a.x, -a.y); }
 S2M_HD vec3 operator-(const vec3& a) { return mk3(-a.x, -a.y, -a.z); }
 S2M_HD vec4 operator-(const vec4& a) { return mk4(-a.x, -a.y, -a.z, -a.w); }
 
-#define S2M_IVEC_BINOP(OP)                                                                            \
-  S2M_HD ivec2 operator OP(const ivec2& a, const ivec2& b) { return mki2(a.x OP b.x, a.y OP b.y); }   \
-  S2M_HD ivec3 operator OP(const ivec3& a, const ivec3& b) { return mki3(a.x OP b.x, a.y OP b.y, a.z OP b.z); } \
-  S2M_HD ivec4 operator OP(const ivec4& a, const ivec4& b) { return mki4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); } \
-  S2M_HD ivec2 operator OP(const ivec2& a, int b) { return mki2(a.x OP b, a.y OP b); }                \
-  S2M_HD ivec3 operator OP(const ivec3& a, int b) { return mki3(a.x OP b, a.y OP b, a.z OP b); }      \
-  S2M_HD ivec4 operator OP(const ivec4& a, int b) { return mki4(a.x OP b, a.y OP b, a.z OP b, a.w OP b); }
-S2M_IVEC_BINOP(+)
-S2M_IVEC_BINOP(-)
-S2M_IVEC_BINOP(*)
-#undef S2M_IVEC_BINOP
+/* ---- integer scalars and vectors.  Pinned to WGSL's rules where C++ would be undefined:
+ * x / 0 = x, x % 0 = 0, INT_MIN / -1 = INT_MIN, INT_MIN % -1 = 0; shift counts are taken mod 32;
+ * signed overflow wraps (computed in unsigned). */
+S2M_HD int i_add(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+S2M_HD int i_sub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+S2M_HD int i_mul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
+S2M_HD int i_div(int a, int b) { return (b == 0 || (a == (-2147483647 - 1) && b == -1)) ? a : a / b; }
+S2M_HD int i_rem(int a, int b) { return (b == 0 || (a == (-2147483647 - 1) && b == -1)) ? 0 : a % b; }
+S2M_HD int i_shl(int a, unsigned b) { return (int)((unsigned)a << (b & 31u)); }
+S2M_HD int i_shr(int a, unsigned b) { return a >> (b & 31u); }
+S2M_HD int i_shl(int a, int b) { return i_shl(a, (unsigned)b); }
+S2M_HD int i_shr(int a, int b) { return i_shr(a, (unsigned)b); }
+S2M_HD int i_and(int a, int b) { return a & b; }
+S2M_HD int i_or(int a, int b) { return a | b; }
+S2M_HD int i_xor(int a, int b) { return a ^ b; }
+S2M_HD int i_neg(int a) { return (int)(0u - (unsigned)a); }
+S2M_HD int i_not(int a) { return ~a; }
+S2M_HD unsigned i_add(unsigned a, unsigned b) { return a + b; }
+S2M_HD unsigned i_sub(unsigned a, unsigned b) { return a - b; }
+S2M_HD unsigned i_mul(unsigned a, unsigned b) { return a * b; }
+S2M_HD unsigned i_div(unsigned a, unsigned b) { return b == 0u ? a : a / b; }
+S2M_HD unsigned i_rem(unsigned a, unsigned b) { return b == 0u ? 0u : a % b; }
+S2M_HD unsigned i_shl(unsigned a, unsigned b) { return a << (b & 31u); }
+S2M_HD unsigned i_shr(unsigned a, unsigned b) { return a >> (b & 31u); }
+S2M_HD unsigned i_shl(unsigned a, int b) { return i_shl(a, (unsigned)b); }
+S2M_HD unsigned i_shr(unsigned a, int b) { return i_shr(a, (unsigned)b); }
+S2M_HD unsigned i_and(unsigned a, unsigned b) { return a & b; }
+S2M_HD unsigned i_or(unsigned a, unsigned b) { return a | b; }
+S2M_HD unsigned i_xor(unsigned a, unsigned b) { return a ^ b; }
+S2M_HD unsigned i_neg(unsigned a) { return 0u - a; }
+S2M_HD unsigned i_not(unsigned a) { return ~a; }
+#define S2M_INT_VEC2(NAME, V2, V3, V4, T, M2, M3, M4)                                                  \
+  S2M_HD V2 NAME(const V2& a, const V2& b) { return M2(NAME(a.x, b.x), NAME(a.y, b.y)); }              \
+  S2M_HD V3 NAME(const V3& a, const V3& b) { return M3(NAME(a.x, b.x), NAME(a.y, b.y), NAME(a.z, b.z)); } \
+  S2M_HD V4 NAME(const V4& a, const V4& b) { return M4(NAME(a.x, b.x), NAME(a.y, b.y), NAME(a.z, b.z), NAME(a.w, b.w)); } \
+  S2M_HD V2 NAME(const V2& a, T b) { return M2(NAME(a.x, b), NAME(a.y, b)); }                          \
+  S2M_HD V3 NAME(const V3& a, T b) { return M3(NAME(a.x, b), NAME(a.y, b), NAME(a.z, b)); }            \
+  S2M_HD V4 NAME(const V4& a, T b) { return M4(NAME(a.x, b), NAME(a.y, b), NAME(a.z, b), NAME(a.w, b)); } \
+  S2M_HD V2 NAME(T a, const V2& b) { return M2(NAME(a, b.x), NAME(a, b.y)); }                          \
+  S2M_HD V3 NAME(T a, const V3& b) { return M3(NAME(a, b.x), NAME(a, b.y), NAME(a, b.z)); }            \
+  S2M_HD V4 NAME(T a, const V4& b) { return M4(NAME(a, b.x), NAME(a, b.y), NAME(a, b.z), NAME(a, b.w)); }
+#define S2M_INT_VEC1(NAME, V2, V3, V4, M2, M3, M4)                                                     \
+  S2M_HD V2 NAME(const V2& a) { return M2(NAME(a.x), NAME(a.y)); }                                     \
+  S2M_HD V3 NAME(const V3& a) { return M3(NAME(a.x), NAME(a.y), NAME(a.z)); }                          \
+  S2M_HD V4 NAME(const V4& a) { return M4(NAME(a.x), NAME(a.y), NAME(a.z), NAME(a.w)); }
+#define S2M_INT_FAMILY(V2, V3, V4, T, M2, M3, M4)                                                      \
+  S2M_INT_VEC2(i_add, V2, V3, V4, T, M2, M3, M4) S2M_INT_VEC2(i_sub, V2, V3, V4, T, M2, M3, M4)        \
+  S2M_INT_VEC2(i_mul, V2, V3, V4, T, M2, M3, M4) S2M_INT_VEC2(i_div, V2, V3, V4, T, M2, M3, M4)        \
+  S2M_INT_VEC2(i_rem, V2, V3, V4, T, M2, M3, M4) S2M_INT_VEC2(i_and, V2, V3, V4, T, M2, M3, M4)        \
+  S2M_INT_VEC2(i_or, V2, V3, V4, T, M2, M3, M4) S2M_INT_VEC2(i_xor, V2, V3, V4, T, M2, M3, M4)         \
+  S2M_INT_VEC1(i_neg, V2, V3, V4, M2, M3, M4) S2M_INT_VEC1(i_not, V2, V3, V4, M2, M3, M4)
+S2M_INT_FAMILY(ivec2, ivec3, ivec4, int, mki2, mki3, mki4)
+S2M_INT_FAMILY(uvec2, uvec3, uvec4, unsigned, mku2, mku3, mku4)
+/* shifts: the count is always unsigned (scalar or vector of the same width) */
+#define S2M_INT_SHIFT(NAME, V2, V3, V4, M2, M3, M4)                                                    \
+  S2M_HD V2 NAME(const V2& a, const uvec2& b) { return M2(NAME(a.x, b.x), NAME(a.y, b.y)); }           \
+  S2M_HD V3 NAME(const V3& a, const uvec3& b) { return M3(NAME(a.x, b.x), NAME(a.y, b.y), NAME(a.z, b.z)); } \
+  S2M_HD V4 NAME(const V4& a, const uvec4& b) { return M4(NAME(a.x, b.x), NAME(a.y, b.y), NAME(a.z, b.z), NAME(a.w, b.w)); } \
+  S2M_HD V2 NAME(const V2& a, const ivec2& b) { return M2(NAME(a.x, b.x), NAME(a.y, b.y)); }           \
+  S2M_HD V3 NAME(const V3& a, const ivec3& b) { return M3(NAME(a.x, b.x), NAME(a.y, b.y), NAME(a.z, b.z)); } \
+  S2M_HD V4 NAME(const V4& a, const ivec4& b) { return M4(NAME(a.x, b.x), NAME(a.y, b.y), NAME(a.z, b.z), NAME(a.w, b.w)); } \
+  S2M_HD V2 NAME(const V2& a, unsigned b) { return M2(NAME(a.x, b), NAME(a.y, b)); }                   \
+  S2M_HD V3 NAME(const V3& a, unsigned b) { return M3(NAME(a.x, b), NAME(a.y, b), NAME(a.z, b)); }     \
+  S2M_HD V4 NAME(const V4& a, unsigned b) { return M4(NAME(a.x, b), NAME(a.y, b), NAME(a.z, b), NAME(a.w, b)); } \
+  S2M_HD V2 NAME(const V2& a, int b) { return NAME(a, (unsigned)b); }                                  \
+  S2M_HD V3 NAME(const V3& a, int b) { return NAME(a, (unsigned)b); }                                  \
+  S2M_HD V4 NAME(const V4& a, int b) { return NAME(a, (unsigned)b); }
+S2M_INT_SHIFT(i_shl, ivec2, ivec3, ivec4, mki2, mki3, mki4) S2M_INT_SHIFT(i_shr, ivec2, ivec3, ivec4, mki2, mki3, mki4)
+S2M_INT_SHIFT(i_shl, uvec2, uvec3, uvec4, mku2, mku3, mku4) S2M_INT_SHIFT(i_shr, uvec2, uvec3, uvec4, mku2, mku3, mku4)
+#undef S2M_INT_SHIFT
+/* integer abs / sign / min / max / clamp */
+S2M_HD int i_min(int a, int b) { return a < b ? a : b; }
+S2M_HD int i_max(int a, int b) { return a > b ? a : b; }
+S2M_HD int i_abs(int a) { return a < 0 ? i_neg(a) : a; }
+S2M_HD int i_sign(int a) { return a > 0 ? 1 : (a < 0 ? -1 : 0); }
+S2M_HD int i_clamp(int x, int lo, int hi) { return i_min(i_max(x, lo), hi); }
+S2M_HD unsigned i_min(unsigned a, unsigned b) { return a < b ? a : b; }
+S2M_HD unsigned i_max(unsigned a, unsigned b) { return a > b ? a : b; }
+S2M_HD unsigned i_abs(unsigned a) { return a; }
+S2M_HD unsigned i_clamp(unsigned x, unsigned lo, unsigned hi) { return i_min(i_max(x, lo), hi); }
+S2M_INT_VEC2(i_min, ivec2, ivec3, ivec4, int, mki2, mki3, mki4) S2M_INT_VEC2(i_max, ivec2, ivec3, ivec4, int, mki2, mki3, mki4)
+S2M_INT_VEC2(i_min, uvec2, uvec3, uvec4, unsigned, mku2, mku3, mku4) S2M_INT_VEC2(i_max, uvec2, uvec3, uvec4, unsigned, mku2, mku3, mku4)
+S2M_INT_VEC1(i_abs, ivec2, ivec3, ivec4, mki2, mki3, mki4) S2M_INT_VEC1(i_sign, ivec2, ivec3, ivec4, mki2, mki3, mki4)
+S2M_INT_VEC1(i_abs, uvec2, uvec3, uvec4, mku2, mku3, mku4)
+#define S2M_INT_CLAMP(V2, V3, V4, T, M2, M3, M4)                                                       \
+  S2M_HD V2 i_clamp(const V2& x, const V2& lo, const V2& hi) { return i_min(i_max(x, lo), hi); }       \
+  S2M_HD V3 i_clamp(const V3& x, const V3& lo, const V3& hi) { return i_min(i_max(x, lo), hi); }       \
+  S2M_HD V4 i_clamp(const V4& x, const V4& lo, const V4& hi) { return i_min(i_max(x, lo), hi); }       \
+  S2M_HD V2 i_clamp(const V2& x, T lo, T hi) { return i_min(i_max(x, lo), hi); }                       \
+  S2M_HD V3 i_clamp(const V3& x, T lo, T hi) { return i_min(i_max(x, lo), hi); }                       \
+  S2M_HD V4 i_clamp(const V4& x, T lo, T hi) { return i_min(i_max(x, lo), hi); }
+S2M_INT_CLAMP(ivec2, ivec3, ivec4, int, mki2, mki3, mki4)
+S2M_INT_CLAMP(uvec2, uvec3, uvec4, unsigned, mku2, mku3, mku4)
+#undef S2M_INT_CLAMP
+#undef S2M_INT_FAMILY
+#undef S2M_INT_VEC1
+#undef S2M_INT_VEC2
 
 /* ---- conversions */
 S2M_HD vec2 to_f(const ivec2& v) { return mk2((float)v.x, (float)v.y); }
@@ -132,6 +235,66 @@ S2M_HD vec4 to_f(const ivec4& v) { return mk4((float)v.x, (float)v.y, (float)v.z
 S2M_HD ivec2 to_i(const vec2& v) { return mki2(s2m_f2int(v.x), s2m_f2int(v.y)); }
 S2M_HD ivec3 to_i(const vec3& v) { return mki3(s2m_f2int(v.x), s2m_f2int(v.y), s2m_f2int(v.z)); }
 S2M_HD ivec4 to_i(const vec4& v) { return mki4(s2m_f2int(v.x), s2m_f2int(v.y), s2m_f2int(v.z), s2m_f2int(v.w)); }
+S2M_HD vec2 to_f(const uvec2& v) { return mk2((float)v.x, (float)v.y); }
+S2M_HD vec3 to_f(const uvec3& v) { return mk3((float)v.x, (float)v.y, (float)v.z); }
+S2M_HD vec4 to_f(const uvec4& v) { return mk4((float)v.x, (float)v.y, (float)v.z, (float)v.w); }
+S2M_HD uvec2 to_u(const vec2& v) { return mku2(s2m_f2uint(v.x), s2m_f2uint(v.y)); }
+S2M_HD uvec3 to_u(const vec3& v) { return mku3(s2m_f2uint(v.x), s2m_f2uint(v.y), s2m_f2uint(v.z)); }
+S2M_HD uvec4 to_u(const vec4& v) { return mku4(s2m_f2uint(v.x), s2m_f2uint(v.y), s2m_f2uint(v.z), s2m_f2uint(v.w)); }
+S2M_HD uvec2 to_u(const ivec2& v) { return mku2((unsigned)v.x, (unsigned)v.y); }
+S2M_HD uvec3 to_u(const ivec3& v) { return mku3((unsigned)v.x, (unsigned)v.y, (unsigned)v.z); }
+S2M_HD uvec4 to_u(const ivec4& v) { return mku4((unsigned)v.x, (unsigned)v.y, (unsigned)v.z, (unsigned)v.w); }
+S2M_HD ivec2 to_i(const uvec2& v) { return mki2((int)v.x, (int)v.y); }
+S2M_HD ivec3 to_i(const uvec3& v) { return mki3((int)v.x, (int)v.y, (int)v.z); }
+S2M_HD ivec4 to_i(const uvec4& v) { return mki4((int)v.x, (int)v.y, (int)v.z, (int)v.w); }
+S2M_HD vec2 to_f(const bvec2& v) { return mk2(v.x ? 1.0f : 0.0f, v.y ? 1.0f : 0.0f); }
+S2M_HD vec3 to_f(const bvec3& v) { return mk3(v.x ? 1.0f : 0.0f, v.y ? 1.0f : 0.0f, v.z ? 1.0f : 0.0f); }
+S2M_HD vec4 to_f(const bvec4& v) { return mk4(v.x ? 1.0f : 0.0f, v.y ? 1.0f : 0.0f, v.z ? 1.0f : 0.0f, v.w ? 1.0f : 0.0f); }
+S2M_HD ivec2 to_i(const bvec2& v) { return mki2(v.x, v.y); }
+S2M_HD ivec3 to_i(const bvec3& v) { return mki3(v.x, v.y, v.z); }
+S2M_HD ivec4 to_i(const bvec4& v) { return mki4(v.x, v.y, v.z, v.w); }
+S2M_HD uvec2 to_u(const bvec2& v) { return mku2(v.x, v.y); }
+S2M_HD uvec3 to_u(const bvec3& v) { return mku3(v.x, v.y, v.z); }
+S2M_HD uvec4 to_u(const bvec4& v) { return mku4(v.x, v.y, v.z, v.w); }
+/* bit reinterpretation (WGSL bitcast<T>, GLSL floatBitsToInt / floatBitsToUint / intBitsToFloat / uintBitsToFloat) */
+S2M_HD int bits_i(float a) { return s2m_f2i(a); }
+S2M_HD int bits_i(unsigned a) { return (int)a; }
+S2M_HD int bits_i(int a) { return a; }
+S2M_HD unsigned bits_u(float a) { return (unsigned)s2m_f2i(a); }
+S2M_HD unsigned bits_u(int a) { return (unsigned)a; }
+S2M_HD unsigned bits_u(unsigned a) { return a; }
+S2M_HD float bits_f(int a) { return s2m_i2f(a); }
+S2M_HD float bits_f(unsigned a) { return s2m_i2f((int)a); }
+S2M_HD float bits_f(float a) { return a; }
+#define S2M_BITS_VEC(NAME, R2, R3, R4, M2, M3, M4, A2, A3, A4)                                         \
+  S2M_HD R2 NAME(const A2& a) { return M2(NAME(a.x), NAME(a.y)); }                                     \
+  S2M_HD R3 NAME(const A3& a) { return M3(NAME(a.x), NAME(a.y), NAME(a.z)); }                          \
+  S2M_HD R4 NAME(const A4& a) { return M4(NAME(a.x), NAME(a.y), NAME(a.z), NAME(a.w)); }
+S2M_BITS_VEC(bits_i, ivec2, ivec3, ivec4, mki2, mki3, mki4, vec2, vec3, vec4)
+S2M_BITS_VEC(bits_i, ivec2, ivec3, ivec4, mki2, mki3, mki4, uvec2, uvec3, uvec4)
+S2M_BITS_VEC(bits_u, uvec2, uvec3, uvec4, mku2, mku3, mku4, vec2, vec3, vec4)
+S2M_BITS_VEC(bits_u, uvec2, uvec3, uvec4, mku2, mku3, mku4, ivec2, ivec3, ivec4)
+S2M_BITS_VEC(bits_f, vec2, vec3, vec4, mk2, mk3, mk4, ivec2, ivec3, ivec4)
+S2M_BITS_VEC(bits_f, vec2, vec3, vec4, mk2, mk3, mk4, uvec2, uvec3, uvec4)
+#undef S2M_BITS_VEC
+
+#define S2M_SWZ_FAMILY(V2, V3, V4, M2, M3, M4)                                                          \
+  S2M_HD V2 swz2(const V2& v, int a, int b) { return M2(cget(v, a), cget(v, b)); }                      \
+  S2M_HD V2 swz2(const V3& v, int a, int b) { return M2(cget(v, a), cget(v, b)); }                      \
+  S2M_HD V2 swz2(const V4& v, int a, int b) { return M2(cget(v, a), cget(v, b)); }                      \
+  S2M_HD V3 swz3(const V2& v, int a, int b, int c) { return M3(cget(v, a), cget(v, b), cget(v, c)); }   \
+  S2M_HD V3 swz3(const V3& v, int a, int b, int c) { return M3(cget(v, a), cget(v, b), cget(v, c)); }   \
+  S2M_HD V3 swz3(const V4& v, int a, int b, int c) { return M3(cget(v, a), cget(v, b), cget(v, c)); }   \
+  S2M_HD V4 swz4(const V2& v, int a, int b, int c, int d) { return M4(cget(v, a), cget(v, b), cget(v, c), cget(v, d)); } \
+  S2M_HD V4 swz4(const V3& v, int a, int b, int c, int d) { return M4(cget(v, a), cget(v, b), cget(v, c), cget(v, d)); } \
+  S2M_HD V4 swz4(const V4& v, int a, int b, int c, int d) { return M4(cget(v, a), cget(v, b), cget(v, c), cget(v, d)); }
+S2M_SWZ_FAMILY(uvec2, uvec3, uvec4, mku2, mku3, mku4)
+S2M_SWZ_FAMILY(bvec2, bvec3, bvec4, mkb2, mkb3, mkb4)
+#undef S2M_SWZ_FAMILY
+S2M_HD ivec3 swz3(const ivec2& v, int a, int b, int c) { return mki3(cget(v, a), cget(v, b), cget(v, c)); }
+S2M_HD ivec4 swz4(const ivec2& v, int a, int b, int c, int d) { return mki4(cget(v, a), cget(v, b), cget(v, c), cget(v, d)); }
+S2M_HD ivec4 swz4(const ivec3& v, int a, int b, int c, int d) { return mki4(cget(v, a), cget(v, b), cget(v, c), cget(v, d)); }
+S2M_HD ivec4 swz4(const ivec4& v, int a, int b, int c, int d) { return mki4(cget(v, a), cget(v, b), cget(v, c), cget(v, d)); }
 
 /* ---- component-wise maps of the scalar builtins in s2m_math.h */
 #define S2M_MAP1(NAME, FN)                                                              \
@@ -171,11 +334,6 @@ S2M_HD vec4 f_saturate(const vec4& a) { return mk4(s2m__saturate(a.x), s2m__satu
 S2M_MAP2(f_min, s2m_min)   S2M_MAP2(f_max, s2m_max)   S2M_MAP2(f_pow, s2m_pow)   S2M_MAP2(f_atan2, s2m_atan2)
 S2M_MAP2(f_step, s2m_step) S2M_MAP2(f_mod, s2m_mod_floor) S2M_MAP2(f_rem, s2m_fmod_trunc)
 #undef S2M_MAP2
-
-S2M_HD int i_min(int a, int b) { return a < b ? a : b; }
-S2M_HD int i_max(int a, int b) { return a > b ? a : b; }
-S2M_HD int i_abs(int a) { return a < 0 ? -a : a; }
-S2M_HD int i_clamp(int x, int lo, int hi) { return i_min(i_max(x, lo), hi); }
 
 S2M_HD float f_clamp(float x, float lo, float hi) { return s2m_clamp(x, lo, hi); }
 S2M_HD vec2 f_clamp(const vec2& x, const vec2& lo, const vec2& hi) { return mk2(s2m_clamp(x.x, lo.x, hi.x), s2m_clamp(x.y, lo.y, hi.y)); }
@@ -227,6 +385,18 @@ S2M_HD vec3 f_cross(const vec3& a, const vec3& b) {
 }
 S2M_HD vec2 f_reflect(const vec2& i, const vec2& n) { return i - (2.0f * f_dot(n, i)) * n; }
 S2M_HD vec3 f_reflect(const vec3& i, const vec3& n) { return i - (2.0f * f_dot(n, i)) * n; }
+S2M_HD vec4 f_reflect(const vec4& i, const vec4& n) { return i - (2.0f * f_dot(n, i)) * n; }
+/* refract(I, N, eta): k = 1 - eta^2 (1 - dot(N,I)^2); k < 0 ? 0 : eta*I - (eta*dot(N,I) + sqrt(k))*N */
+#define S2M_REFRACT(V, ZERO)                                                                           \
+  S2M_HD V f_refract(const V& i, const V& n, float eta) {                                              \
+    const float d = f_dot(n, i);                                                                       \
+    const float k = 1.0f - eta * eta * (1.0f - d * d);                                                 \
+    if (k < 0.0f) return ZERO;                                                                         \
+    return eta * i - (eta * d + s2m_sqrt(k)) * n;                                                      \
+  }                                                                                                    \
+  S2M_HD V f_faceforward(const V& n, const V& i, const V& nref) { return f_dot(nref, i) < 0.0f ? n : -n; }
+S2M_REFRACT(vec2, splat2(0.0f)) S2M_REFRACT(vec3, splat3(0.0f)) S2M_REFRACT(vec4, splat4(0.0f))
+#undef S2M_REFRACT
 
 
 /* ---- square matrices, column-major (c0 = first column), as in WGSL / GLSL.
@@ -293,6 +463,20 @@ S2M_HD float f_determinant(const mat3& m) { return f_dot(m.c0, f_cross(m.c1, m.c
   S2M_HD bvec4 NAME(const vec4& a, const vec4& b) { return mkb4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); }
 S2M_CMP(v_lt, <) S2M_CMP(v_le, <=) S2M_CMP(v_gt, >) S2M_CMP(v_ge, >=) S2M_CMP(v_eq, ==) S2M_CMP(v_ne, !=)
 #undef S2M_CMP
+#define S2M_CMP_FAMILY(NAME, OP, V2, V3, V4)                                                             \
+  S2M_HD bvec2 NAME(const V2& a, const V2& b) { return mkb2(a.x OP b.x, a.y OP b.y); }                   \
+  S2M_HD bvec3 NAME(const V3& a, const V3& b) { return mkb3(a.x OP b.x, a.y OP b.y, a.z OP b.z); }       \
+  S2M_HD bvec4 NAME(const V4& a, const V4& b) { return mkb4(a.x OP b.x, a.y OP b.y, a.z OP b.z, a.w OP b.w); }
+S2M_CMP_FAMILY(v_lt, <, ivec2, ivec3, ivec4) S2M_CMP_FAMILY(v_le, <=, ivec2, ivec3, ivec4) S2M_CMP_FAMILY(v_gt, >, ivec2, ivec3, ivec4)
+S2M_CMP_FAMILY(v_ge, >=, ivec2, ivec3, ivec4) S2M_CMP_FAMILY(v_eq, ==, ivec2, ivec3, ivec4) S2M_CMP_FAMILY(v_ne, !=, ivec2, ivec3, ivec4)
+S2M_CMP_FAMILY(v_lt, <, uvec2, uvec3, uvec4) S2M_CMP_FAMILY(v_le, <=, uvec2, uvec3, uvec4) S2M_CMP_FAMILY(v_gt, >, uvec2, uvec3, uvec4)
+S2M_CMP_FAMILY(v_ge, >=, uvec2, uvec3, uvec4) S2M_CMP_FAMILY(v_eq, ==, uvec2, uvec3, uvec4) S2M_CMP_FAMILY(v_ne, !=, uvec2, uvec3, uvec4)
+S2M_CMP_FAMILY(v_eq, ==, bvec2, bvec3, bvec4) S2M_CMP_FAMILY(v_ne, !=, bvec2, bvec3, bvec4)
+S2M_CMP_FAMILY(v_and, &&, bvec2, bvec3, bvec4) S2M_CMP_FAMILY(v_or, ||, bvec2, bvec3, bvec4)
+#undef S2M_CMP_FAMILY
+S2M_HD bvec2 v_not(const bvec2& a) { return mkb2(!a.x, !a.y); }
+S2M_HD bvec3 v_not(const bvec3& a) { return mkb3(!a.x, !a.y, !a.z); }
+S2M_HD bvec4 v_not(const bvec4& a) { return mkb4(!a.x, !a.y, !a.z, !a.w); }
 S2M_HD bool b_all(bool a) { return a; }
 S2M_HD bool b_all(const bvec2& a) { return a.x && a.y; }
 S2M_HD bool b_all(const bvec3& a) { return a.x && a.y && a.z; }
@@ -304,12 +488,25 @@ S2M_HD bool b_any(const bvec4& a) { return a.x || a.y || a.z || a.w; }
 /* WGSL select(f, t, cond) */
 S2M_HD float f_select(float f, float t, bool c) { return c ? t : f; }
 S2M_HD int f_select(int f, int t, bool c) { return c ? t : f; }
+S2M_HD unsigned f_select(unsigned f, unsigned t, bool c) { return c ? t : f; }
+S2M_HD bool f_select(bool f, bool t, bool c) { return c ? t : f; }
 S2M_HD vec2 f_select(const vec2& f, const vec2& t, bool c) { return c ? t : f; }
 S2M_HD vec3 f_select(const vec3& f, const vec3& t, bool c) { return c ? t : f; }
 S2M_HD vec4 f_select(const vec4& f, const vec4& t, bool c) { return c ? t : f; }
 S2M_HD vec2 f_select(const vec2& f, const vec2& t, const bvec2& c) { return mk2(c.x ? t.x : f.x, c.y ? t.y : f.y); }
 S2M_HD vec3 f_select(const vec3& f, const vec3& t, const bvec3& c) { return mk3(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z); }
 S2M_HD vec4 f_select(const vec4& f, const vec4& t, const bvec4& c) { return mk4(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z, c.w ? t.w : f.w); }
+#define S2M_SELECT_FAMILY(V2, V3, V4, M2, M3, M4)                                                        \
+  S2M_HD V2 f_select(const V2& f, const V2& t, bool c) { return c ? t : f; }                             \
+  S2M_HD V3 f_select(const V3& f, const V3& t, bool c) { return c ? t : f; }                             \
+  S2M_HD V4 f_select(const V4& f, const V4& t, bool c) { return c ? t : f; }                             \
+  S2M_HD V2 f_select(const V2& f, const V2& t, const bvec2& c) { return M2(c.x ? t.x : f.x, c.y ? t.y : f.y); } \
+  S2M_HD V3 f_select(const V3& f, const V3& t, const bvec3& c) { return M3(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z); } \
+  S2M_HD V4 f_select(const V4& f, const V4& t, const bvec4& c) { return M4(c.x ? t.x : f.x, c.y ? t.y : f.y, c.z ? t.z : f.z, c.w ? t.w : f.w); }
+S2M_SELECT_FAMILY(ivec2, ivec3, ivec4, mki2, mki3, mki4)
+S2M_SELECT_FAMILY(uvec2, uvec3, uvec4, mku2, mku3, mku4)
+S2M_SELECT_FAMILY(bvec2, bvec3, bvec4, mkb2, mkb3, mkb4)
+#undef S2M_SELECT_FAMILY
 
 
 /* ---------------------------------------------------------------- arrays and dynamic indexing
@@ -325,6 +522,7 @@ template <class T, int N, class I> S2M_HD const T& s2m_at(const s2m_array<T, N>&
   template <class I> S2M_HD const T& s2m_at(const V& v, I i) { return (&v.x)[s2m_clamp_index(i, N)]; }
 S2M_VAT(vec2, float, 2) S2M_VAT(vec3, float, 3) S2M_VAT(vec4, float, 4)
 S2M_VAT(ivec2, int, 2) S2M_VAT(ivec3, int, 3) S2M_VAT(ivec4, int, 4)
+S2M_VAT(uvec2, unsigned, 2) S2M_VAT(uvec3, unsigned, 3) S2M_VAT(uvec4, unsigned, 4)
 S2M_VAT(bvec2, bool, 2) S2M_VAT(bvec3, bool, 3) S2M_VAT(bvec4, bool, 4)
 #undef S2M_VAT
 #define S2M_MAT_AT(M, V, N) \

@@ -498,6 +498,135 @@ def test_mutable_globals_switch_structs_arrays(built, tmp_path):
     assert "falls through" in str(e.value)
 
 
+def test_integer_vectors_and_bit_functions(built, tmp_path):
+    """f2: uvec / ivec arithmetic with wrap-around, shifts, bit operations, integer min/max/clamp/abs/sign,
+    WGSL-defined division by zero, floatBitsToUint / bitcast, GLSL relational functions, mix with a bool
+    selector, refract -- an integer-hash value-noise SDF in GLSL and a bit-twiddling one in WGSL, each
+    against a numpy transcription"""
+    glsl = textwrap.dedent("""\
+        #version 450 core
+        uvec3 pcg3d(uvec3 v) {
+          v = v * 1664525u + 1013904223u;
+          v.x += v.y * v.z; v.y += v.z * v.x; v.z += v.x * v.y;
+          v ^= v >> 16u;
+          v.x += v.y * v.z; v.y += v.z * v.x; v.z += v.x * v.y;
+          return v;
+        }
+        vec3 hash33(vec3 p) {
+          uvec3 q = pcg3d(uvec3(ivec3(floor(p)) + 1000));
+          return vec3(q) * (1.0 / float(0xffffffffu));
+        }
+        float vnoise(vec3 p) {
+          vec3 i = floor(p), f = fract(p);
+          vec3 u = f * f * (3.0 - 2.0 * f);
+          float acc = 0.0;
+          for (int k = 0; k < 8; ++k) {
+            ivec3 o = ivec3(k & 1, (k >> 1) & 1, (k >> 2) & 1);
+            vec3 w = mix(1.0 - u, u, equal(o, ivec3(1)));
+            acc += hash33(i + vec3(o)).x * w.x * w.y * w.z;
+          }
+          return acc;
+        }
+        float sdf(vec3 p) {
+          bvec3 neg = lessThan(p, vec3(0.0));
+          vec3 q = mix(p, -p, neg);
+          int m = int(floatBitsToUint(q.x) >> 23u) & 0xff;
+          float e = float(m - 127) * 0.001;
+          float bump = 0.05 * vnoise(p * 4.0) + (any(neg) ? 0.0 : 0.01) + (all(not(neg)) ? 0.002 : 0.0);
+          ivec3 c = clamp(ivec3(p * 2.0), ivec3(-2), ivec3(2));
+          return length(q) - 1.0 + bump + e + 0.001 * float(abs(c.x) + max(c.y, c.z) + sign(c.z)) + 0.0001 * float(7 / (c.x - c.x));
+        }
+        void main() {}
+        """)
+    f, u32 = np.float32, np.uint32
+
+    def pcg3d(v):
+        v = (v * u32(1664525) + u32(1013904223)).astype(u32)
+        v[0] += v[1] * v[2]; v[1] += v[2] * v[0]; v[2] += v[0] * v[1]
+        v ^= v >> u32(16)
+        v[0] += v[1] * v[2]; v[1] += v[2] * v[0]; v[2] += v[0] * v[1]
+        return v
+
+    def hash33x(p):
+        q = pcg3d((np.floor(p).astype(np.int32) + np.int32(1000)).astype(u32))
+        return f(f(q[0]) * f(f(1.0) / f(4294967295.0)))
+
+    def vnoise(p):
+        i, fr = np.floor(p).astype(np.float32), (p - np.floor(p)).astype(np.float32)
+        u = ((fr * fr).astype(np.float32) * (f(3.0) - (f(2.0) * fr).astype(np.float32)).astype(np.float32)).astype(np.float32)
+        acc = f(0.0)
+        for k in range(8):
+            o = np.array([k & 1, (k >> 1) & 1, (k >> 2) & 1])
+            w = np.where(o == 1, u, (f(1.0) - u).astype(np.float32)).astype(np.float32)
+            acc = f(acc + f(f(f(hash33x((i + o.astype(np.float32)).astype(np.float32)) * w[0]) * w[1]) * w[2]))
+        return acc
+
+    def expect(p):
+        neg = p < 0
+        q = np.where(neg, -p, p).astype(np.float32)
+        m = int((q[:1].view(u32)[0] >> u32(23)) & u32(0xff))
+        e = f(f(m - 127) * f(0.001))
+        bump = f(f(f(0.05) * vnoise((p * f(4.0)).astype(np.float32))) + (f(0.0) if neg.any() else f(0.01)))
+        bump = f(bump + (f(0.002) if (~neg).all() else f(0.0)))
+        c = np.clip(np.trunc((p * f(2.0)).astype(np.float32)).astype(np.int32), -2, 2)
+        r = f(f(np.sqrt(f(f(q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]))) - f(1.0))
+        r = f(f(r + bump) + e)
+        r = f(r + f(f(0.001) * f(abs(int(c[0])) + max(int(c[1]), int(c[2])) + int(np.sign(c[2])))))
+        return f(r + f(f(0.0001) * f(7)))       # 7 / 0 = 7 (WGSL rule)
+
+    with np.errstate(over="ignore"):
+        pts = points(4.0, 600)
+        want = np.array([expect(p) for p in pts], np.float32)
+    frag = tmp_path / "hash.frag"
+    frag.write_text(glsl)
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    assert "vec3<u32>" in sh.source and "bitcast<u32>(" in sh.source
+    cuda = sh.lower_to_cuda()
+    assert "uvec3 u_pcg3d(uvec3" in cuda
+    assert f32_equal(host_eval.eval_points(cuda, pts), want).all()
+    assert sh.create_shader_module(None).cubin_size > 0
+    wgsl = textwrap.dedent("""\
+        fn mantissa_bits(x: f32) -> u32 { return bitcast<u32>(x) & 0x7fffffu; }
+        fn sdf3d(p: vec3f) -> f32 {
+          let b = bitcast<vec3<u32>>(abs(p));
+          let e = vec3<i32>((b >> vec3<u32>(23u)) & vec3<u32>(255u)) - vec3<i32>(127);
+          let lo = mantissa_bits(p.x) >> 20u;
+          let s = select(vec3<i32>(1), vec3<i32>(-1), p < vec3f(0.0));
+          let t = (e * s) % vec3<i32>(3, 0, 2);
+          let one = bitcast<f32>(0x3f800000u);
+          return length(p) - one + 0.01 * f32(t.x + t.y + t.z) + 0.001 * f32(lo) + 0.0001 * f32(max(e.x, min(e.y, e.z)) << 2u)
+                 + refract(normalize(p + 0.1), vec3f(0.0, 1.0, 0.0), 0.9).x * 1e-3 + faceForward(p, vec3f(0.0, 0.0, 1.0), p).z * 1e-3;
+        }
+        """)
+
+    def expect2(p):
+        b = np.abs(p).astype(np.float32).view(u32)
+        e = ((b >> u32(23)) & u32(255)).astype(np.int32) - np.int32(127)
+        lo = int((p[:1].view(u32)[0] & u32(0x7fffff)) >> u32(20))
+        s = np.where(p < 0, -1, 1)
+        es = e * s
+        t = [int(np.fmod(es[0], 3)), 0, int(np.fmod(es[2], 2))]    # truncated remainder; x % 0 = 0
+        ln = f(np.sqrt(f(f(p[0] * p[0] + p[1] * p[1]) + p[2] * p[2])))
+        r = f(ln - f(1.0))
+        r = f(r + f(f(0.01) * f(t[0] + t[1] + t[2])))
+        r = f(r + f(f(0.001) * f(lo)))
+        r = f(r + f(f(0.0001) * f(int(max(e[0], min(e[1], e[2]))) << 2)))
+        i = (p + f(0.1)).astype(np.float32)
+        i = (i / f(np.sqrt(f(f(i[0] * i[0] + i[1] * i[1]) + i[2] * i[2])))).astype(np.float32)
+        eta = f(0.9)
+        d = f(f(f(0.0) * i[0] + f(1.0) * i[1]) + f(0.0) * i[2])
+        k = f(f(1.0) - f(f(eta * eta) * f(f(1.0) - f(d * d))))
+        rx = f(0.0) if k < 0 else f(f(eta * i[0]) - f(f(f(eta * d) + f(np.sqrt(k))) * f(0.0)))
+        r = f(r + f(rx * f(1e-3)))
+        ff = p[2] if f(f(f(p[0] * f(0.0) + p[1] * f(0.0)) + p[2] * f(1.0))) < 0 else -p[2]
+        return f(r + f(f(ff) * f(1e-3)))
+
+    pts2 = points(4.0, 600)
+    want2 = np.array([expect2(p) for p in pts2], np.float32)
+    cuda2 = s2m.Sdf3DShader.from_source(wgsl).lower_to_cuda()
+    assert f32_equal(host_eval.eval_points(cuda2, pts2), want2).all()
+
+
 def test_matrices(built, tmp_path):
     """mat2/mat3 (GLSL) and mat2x2f/mat3x3<f32> (WGSL): constructors, m*v, v*m, m*m, m[i], transpose"""
     glsl = textwrap.dedent("""\

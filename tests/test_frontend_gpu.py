@@ -56,9 +56,48 @@ WGSL_PROGRAMS = {
 }
 
 
-@pytest.mark.parametrize("name", sorted(WGSL_PROGRAMS))
-def test_device_bits_equal_host_bits(ctx, name):
-    sh = s2m.Sdf3DShader.from_source(textwrap.dedent(WGSL_PROGRAMS[name]))
+GLSL_PROGRAMS = {
+    "integer_hash_noise": """#version 450 core
+        uvec3 pcg3d(uvec3 v) {
+          v = v * 1664525u + 1013904223u;
+          v.x += v.y * v.z; v.y += v.z * v.x; v.z += v.x * v.y;
+          v ^= v >> 16u;
+          v.x += v.y * v.z; v.y += v.z * v.x; v.z += v.x * v.y;
+          return v;
+        }
+        vec3 hash33(vec3 p) { uvec3 q = pcg3d(uvec3(ivec3(floor(p)) + 1000)); return vec3(q) * (1.0 / float(0xffffffffu)); }
+        float vnoise(vec3 p) {
+          vec3 i = floor(p), f = fract(p);
+          vec3 u = f * f * (3.0 - 2.0 * f);
+          float acc = 0.0;
+          for (int k = 0; k < 8; ++k) {
+            ivec3 o = ivec3(k & 1, (k >> 1) & 1, (k >> 2) & 1);
+            vec3 w = mix(1.0 - u, u, equal(o, ivec3(1)));
+            acc += hash33(i + vec3(o)).x * w.x * w.y * w.z;
+          }
+          return acc;
+        }
+        float sdf(vec3 p) {
+          bvec3 neg = lessThan(p, vec3(0.0));
+          vec3 q = mix(p, -p, neg);
+          int m = int(floatBitsToUint(q.x) >> 23u) & 0xff;
+          ivec3 c = clamp(ivec3(p * 2.0), ivec3(-2), ivec3(2));
+          return length(q) - 1.0 + 0.05 * vnoise(p * 4.0) + float(m - 127) * 0.001 + 0.001 * float(abs(c.x) + max(c.y, c.z) + sign(c.z) + 7 / (c.x - c.x))
+                 + refract(normalize(p + 0.1), vec3(0.0, 1.0, 0.0), 0.9).x * 1e-3;
+        }
+        void main() {}
+        """,
+}
+
+
+@pytest.mark.parametrize("name", sorted(WGSL_PROGRAMS) + sorted(GLSL_PROGRAMS))
+def test_device_bits_equal_host_bits(ctx, name, tmp_path):
+    if name in GLSL_PROGRAMS:
+        frag = tmp_path / (name + ".frag")
+        frag.write_text(textwrap.dedent(GLSL_PROGRAMS[name]))
+        sh = s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    else:
+        sh = s2m.Sdf3DShader.from_source(textwrap.dedent(WGSL_PROGRAMS[name]))
     cuda = sh.lower_to_cuda()
     rng = np.random.default_rng(11)
     pts = rng.uniform(-3, 3, (200_000, 3)).astype(np.float32)
