@@ -642,6 +642,7 @@ const BuiltinInfo kBuiltins[] = {
     {"clamp", "clamp", 3, 'n', 3},   {"mix", "mix", 3, 'm', 3},       {"smoothstep", "smoothstep", 3, 'm', 3}, {"fma", "fma", 3, 'm', 3},
     {"select", "select", 3, 'S', 3}, {"any", "any", 1, 'b', 3},       {"all", "all", 1, 'b', 3},
     {"transpose", "transpose", 1, 'T', 3}, {"determinant", "determinant", 1, 'D', 3},
+    {"inverse", "inverse", 1, 'T', 3},  // GLSL; accepted in WGSL text too (naga writes GLSL's inverse() as a helper function)
     {"refract", "refract", 3, 'R', 3}, {"faceForward", "faceforward", 3, 'F', 1}, {"faceforward", "faceforward", 3, 'F', 2},
 };
 }  // namespace

@@ -500,11 +500,18 @@ class GlslParser : public ParserBase {
     for (;;) {
       if (peek().k != Token::Punct) break;
       std::string p = peek().text;
-      if (p == "^" && is_punct("^", 1)) b.unsupported("^^ operator");
+      const bool logical_xor = p == "^" && is_punct("^", 1);  // the lexer has no ^^ token
+      if (logical_xor) p = "^^";
       const int prec = prec_of(p);
       if (prec < 0 || prec < min_prec) break;
       advance();
+      if (logical_xor) advance();
       ExprP rhs = parse_binary(prec + 1);
+      if (logical_xor) {
+        if (!lhs->ty.is_bool() || !rhs->ty.is_bool() || !lhs->ty.is_scalar() || !rhs->ty.is_scalar()) b.error("^^ needs bool operands");
+        lhs = b.binary(Op::Ne, lhs, rhs);
+        continue;
+      }
       Op op = p == "||" ? Op::Or : p == "&&" ? Op::And : p == "|" ? Op::BitOr : p == "^" ? Op::BitXor : p == "&" ? Op::BitAnd
               : p == "==" ? Op::Eq : p == "!=" ? Op::Ne : p == "<" ? Op::Lt : p == ">" ? Op::Gt : p == "<=" ? Op::Le : p == ">=" ? Op::Ge
               : p == "<<" ? Op::Shl : p == ">>" ? Op::Shr : p == "+" ? Op::Add : p == "-" ? Op::Sub : p == "*" ? Op::Mul : p == "/" ? Op::Div : Op::Rem;

@@ -455,6 +455,45 @@ S2M_HD mat4 f_transpose(const mat4& m) {
 }
 S2M_HD float f_determinant(const mat2& m) { return m.c0.x * m.c1.y - m.c1.x * m.c0.y; }
 S2M_HD float f_determinant(const mat3& m) { return f_dot(m.c0, f_cross(m.c1, m.c2)); }
+/* 4x4: 2x2 minors of the first two and the last two columns (Laplace expansion along column pairs);
+ * the same minors give the inverse.  a_ij = row i of column j. */
+struct s2m__minors4 { float s0, s1, s2, s3, s4, s5, c0, c1, c2, c3, c4, c5; };
+S2M_HD s2m__minors4 s2m__mat4_minors(const mat4& m) {
+  s2m__minors4 k;
+  k.s0 = m.c0.x * m.c1.y - m.c0.y * m.c1.x; k.s1 = m.c0.x * m.c1.z - m.c0.z * m.c1.x; k.s2 = m.c0.x * m.c1.w - m.c0.w * m.c1.x;
+  k.s3 = m.c0.y * m.c1.z - m.c0.z * m.c1.y; k.s4 = m.c0.y * m.c1.w - m.c0.w * m.c1.y; k.s5 = m.c0.z * m.c1.w - m.c0.w * m.c1.z;
+  k.c5 = m.c2.z * m.c3.w - m.c2.w * m.c3.z; k.c4 = m.c2.y * m.c3.w - m.c2.w * m.c3.y; k.c3 = m.c2.y * m.c3.z - m.c2.z * m.c3.y;
+  k.c2 = m.c2.x * m.c3.w - m.c2.w * m.c3.x; k.c1 = m.c2.x * m.c3.z - m.c2.z * m.c3.x; k.c0 = m.c2.x * m.c3.y - m.c2.y * m.c3.x;
+  return k;
+}
+S2M_HD float f_determinant(const mat4& m) {
+  const s2m__minors4 k = s2m__mat4_minors(m);
+  return k.s0 * k.c5 - k.s1 * k.c4 + k.s2 * k.c3 + k.s3 * k.c2 - k.s4 * k.c1 + k.s5 * k.c0;
+}
+/* inverse = adjugate * (1 / determinant); a singular matrix gives inf / NaN entries (GLSL: undefined) */
+S2M_HD mat2 f_inverse(const mat2& m) {
+  const float r = 1.0f / f_determinant(m);
+  return mkm2(m.c1.y * r, -m.c0.y * r, -m.c1.x * r, m.c0.x * r);
+}
+S2M_HD mat3 f_inverse(const mat3& m) {
+  const vec3 r0 = f_cross(m.c1, m.c2), r1 = f_cross(m.c2, m.c0), r2 = f_cross(m.c0, m.c1);  /* rows of the adjugate */
+  const float r = 1.0f / f_dot(m.c0, r0);
+  return mkm3(r0.x * r, r1.x * r, r2.x * r, r0.y * r, r1.y * r, r2.y * r, r0.z * r, r1.z * r, r2.z * r);
+}
+S2M_HD mat4 f_inverse(const mat4& m) {
+  const s2m__minors4 k = s2m__mat4_minors(m);
+  const float r = 1.0f / (k.s0 * k.c5 - k.s1 * k.c4 + k.s2 * k.c3 + k.s3 * k.c2 - k.s4 * k.c1 + k.s5 * k.c0);
+  /* inv[i][j] (row i, column j); columns of the result are listed one after the other */
+  return mkm4(
+      ( m.c1.y * k.c5 - m.c1.z * k.c4 + m.c1.w * k.c3) * r, (-m.c0.y * k.c5 + m.c0.z * k.c4 - m.c0.w * k.c3) * r,
+      ( m.c3.y * k.s5 - m.c3.z * k.s4 + m.c3.w * k.s3) * r, (-m.c2.y * k.s5 + m.c2.z * k.s4 - m.c2.w * k.s3) * r,
+      (-m.c1.x * k.c5 + m.c1.z * k.c2 - m.c1.w * k.c1) * r, ( m.c0.x * k.c5 - m.c0.z * k.c2 + m.c0.w * k.c1) * r,
+      (-m.c3.x * k.s5 + m.c3.z * k.s2 - m.c3.w * k.s1) * r, ( m.c2.x * k.s5 - m.c2.z * k.s2 + m.c2.w * k.s1) * r,
+      ( m.c1.x * k.c4 - m.c1.y * k.c2 + m.c1.w * k.c0) * r, (-m.c0.x * k.c4 + m.c0.y * k.c2 - m.c0.w * k.c0) * r,
+      ( m.c3.x * k.s4 - m.c3.y * k.s2 + m.c3.w * k.s0) * r, (-m.c2.x * k.s4 + m.c2.y * k.s2 - m.c2.w * k.s0) * r,
+      (-m.c1.x * k.c3 + m.c1.y * k.c1 - m.c1.z * k.c0) * r, ( m.c0.x * k.c3 - m.c0.y * k.c1 + m.c0.z * k.c0) * r,
+      (-m.c3.x * k.s3 + m.c3.y * k.s1 - m.c3.z * k.s0) * r, ( m.c2.x * k.s3 - m.c2.y * k.s1 + m.c2.z * k.s0) * r);
+}
 
 /* ---- comparisons / selection */
 #define S2M_CMP(NAME, OP)                                                                                \

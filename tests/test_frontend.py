@@ -627,6 +627,36 @@ def test_integer_vectors_and_bit_functions(built, tmp_path):
     assert f32_equal(host_eval.eval_points(cuda2, pts2), want2).all()
 
 
+def test_matrix_inverse_and_logical_xor(built, tmp_path):
+    """GLSL inverse() for mat2/mat3/mat4 (adjugate / determinant, pinned operation order), determinant(mat4), ^^"""
+    glsl = textwrap.dedent("""\
+        #version 450 core
+        float sdf(vec3 p) {
+          mat2 m = mat2(2.0, 1.0, 0.0, 4.0);
+          mat3 r = mat3(1.0, 0.5, 0.0,  0.0, 2.0, 0.25,  0.1, 0.0, 1.5);
+          mat4 t = mat4(1.0, 0.0, 0.0, 0.0,  0.0, 2.0, 0.0, 0.0,  0.0, 0.5, 1.0, 0.0,  0.3, 0.2, 0.1, 1.0);
+          bool a = p.x > 0.0, b = p.y > 0.0;
+          vec4 h = inverse(t) * vec4(p, 1.0);
+          return (inverse(m) * p.xy).x + (inverse(r) * p).z + h.x + h.w + ((a ^^ b) ? 1.0 : 0.0) + determinant(t);
+        }
+        void main() {}
+        """)
+    frag = tmp_path / "inv.frag"
+    frag.write_text(glsl)
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    pts = points(4.0, 500)
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+    m = np.array([[2, 0], [1, 4]], np.float64)
+    r = np.array([[1, 0, 0.1], [0.5, 2, 0], [0, 0.25, 1.5]])
+    t = np.array([[1, 0, 0, 0.3], [0, 2, 0.5, 0.2], [0, 0, 1, 0.1], [0, 0, 0, 1]])
+    want = []
+    for p in pts.astype(np.float64):
+        h = np.linalg.inv(t) @ np.append(p, 1)
+        want.append((np.linalg.inv(m) @ p[:2])[0] + (np.linalg.inv(r) @ p)[2] + h[0] + h[3] + float((p[0] > 0) != (p[1] > 0)) + np.linalg.det(t))
+    assert np.abs(got - np.array(want)).max() < 1e-5
+    assert sh.create_shader_module(None).cubin_size > 0
+
+
 def test_matrices(built, tmp_path):
     """mat2/mat3 (GLSL) and mat2x2f/mat3x3<f32> (WGSL): constructors, m*v, v*m, m*m, m[i], transpose"""
     glsl = textwrap.dedent("""\
