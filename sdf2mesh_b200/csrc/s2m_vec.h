@@ -525,6 +525,8 @@ S2M_HD bool b_any(const bvec2& a) { return a.x || a.y; }
 S2M_HD bool b_any(const bvec3& a) { return a.x || a.y || a.z; }
 S2M_HD bool b_any(const bvec4& a) { return a.x || a.y || a.z || a.w; }
 /* WGSL select(f, t, cond) */
+/* any other type (structs, arrays, matrices) with a scalar condition: GLSL's ?: on aggregates arrives here */
+template <class T> S2M_HD T f_select(const T& f, const T& t, bool c) { return c ? t : f; }
 S2M_HD float f_select(float f, float t, bool c) { return c ? t : f; }
 S2M_HD int f_select(int f, int t, bool c) { return c ? t : f; }
 S2M_HD unsigned f_select(unsigned f, unsigned t, bool c) { return c ? t : f; }

@@ -10,7 +10,7 @@ import pytest
 
 import oracle
 import sdf2mesh_b200 as s2m
-from tests.conftest import EXAMPLES, load_example_shader
+from tests.conftest import EXAMPLES, ROOT, load_example_shader
 from tests.support import host_eval
 from tests.support.digest import f32_equal
 
@@ -654,6 +654,73 @@ def test_matrix_inverse_and_logical_xor(built, tmp_path):
         h = np.linalg.inv(t) @ np.append(p, 1)
         want.append((np.linalg.inv(m) @ p[:2])[0] + (np.linalg.inv(r) @ p)[2] + h[0] + h[3] + float((p[0] > 0) != (p[1] > 0)) + np.linalg.det(t))
     assert np.abs(got - np.array(want)).max() < 1e-5
+    assert sh.create_shader_module(None).cubin_size > 0
+
+
+def test_shadertoy_style_raymarcher(built):
+    """tests/data/shadertoy_raymarcher.glsl -- structs with ?:, mat2 rotation, smooth min, mod repetition,
+    value noise, swizzle stores, #define constants, mainImage + ShaderToy uniforms -- through
+    from_shadertoy_source; values against a float64 numpy transcription (tolerance, not bits)"""
+    code = open(os.path.join(ROOT, "tests", "data", "shadertoy_raymarcher.glsl")).read()
+    sh = s2m.Sdf3DShader.from_shadertoy_source(code, "map")
+    assert "fn mapHit(" in sh.source and "struct Hit {" in sh.source
+    pts = points(4.0, 1500)
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+
+    f = np.float32
+    F = lambda *v: np.array(v, np.float32)
+
+    def fract(x): return (x - np.floor(x)).astype(np.float32)
+    def mix(a, b, t): return f(f(a * f(f(1) - t)) + f(b * t))
+    def length(v):
+        acc = f(v[0] * v[0])
+        for c in v[1:]:
+            acc = f(acc + f(c * c))
+        return f(np.sqrt(acc))
+    def dot(a, b):
+        acc = f(a[0] * b[0])
+        for x, y in zip(a[1:], b[1:]):
+            acc = f(acc + f(x * y))
+        return acc
+    def hash_(p):
+        p = fract((p * f(0.3183099) + f(0.1)).astype(np.float32))
+        p = (p * f(17.0)).astype(np.float32)
+        return fract(f(f(f(p[0] * p[1]) * p[2]) * f(f(p[0] + p[1]) + p[2])))
+    def noise(x):
+        i, fr = np.floor(x).astype(np.float32), fract(x)
+        fr = ((fr * fr).astype(np.float32) * (f(3) - (f(2) * fr).astype(np.float32)).astype(np.float32)).astype(np.float32)
+        h = lambda a, b, c: hash_((i + F(a, b, c)).astype(np.float32))
+        return mix(mix(mix(h(0, 0, 0), h(1, 0, 0), fr[0]), mix(h(0, 1, 0), h(1, 1, 0), fr[0]), fr[1]),
+                   mix(mix(h(0, 0, 1), h(1, 0, 1), fr[0]), mix(h(0, 1, 1), h(1, 1, 1), fr[0]), fr[1]), fr[2])
+    def box(p, s):
+        p = (np.abs(p) - s).astype(np.float32)
+        return f(length(np.maximum(p, f(0))) + min(max(p[0], max(p[1], p[2])), f(0)))
+    def smin(a, b, k):
+        h = min(max(f(f(0.5) + f(f(f(0.5) * f(b - a)) / k)), f(0)), f(1))
+        return f(mix(b, a, h) - f(f(k * h) * f(f(1) - h)))
+    s_, c_ = f(0.479425550), f(0.877582550)       # sin / cos of fl(0 * 0.2 + 0.5) (iTime = 0), rounded to f32
+
+    def expect(p):
+        q = p.copy()
+        x, z = q[0], q[2]                         # q.xz *= mat2(c, -s, s, c): row vector times matrix
+        q[0], q[2] = f(f(x * c_) + f(z * -s_)), f(f(x * s_) + f(z * c_))
+        d = box(q, F(0.5, 0.5, 0.5))
+        rp = p.copy()
+        t0 = f(rp[0] + f(1))
+        rp[0] = f(f(t0 - f(f(2) * np.floor(f(t0 / f(2))))) - f(1))
+        t = (rp - F(0, 0.8, 0)).astype(np.float32)
+        tor = f(length(F(f(length(F(t[0], t[2])) - f(0.4)), t[1])) - f(0.1))
+        d = d if d < tor else tor
+        a_, b_ = F(-1, 0, 0), F(1, 0.5, 0.3)
+        ab, ap = (b_ - a_).astype(np.float32), (p - a_).astype(np.float32)
+        tt = min(max(f(dot(ab, ap) / dot(ab, ab)), f(0)), f(1))
+        cap = f(length((p - (a_ + (tt * ab).astype(np.float32)).astype(np.float32)).astype(np.float32)) - f(0.15))
+        d = d if d < cap else cap
+        d = smin(d, f(length((p - F(0, -0.6, 0)).astype(np.float32)) - f(0.4)), f(0.2))
+        return f(d + f(f(0.03) * noise((p * f(6.0)).astype(np.float32))))
+
+    want = np.array([expect(p) for p in pts], np.float32)
+    assert np.abs(got - want).max() < 2e-6   # the only non-pinned step above is rounding sin/cos(0.5) by hand
     assert sh.create_shader_module(None).cubin_size > 0
 
 
