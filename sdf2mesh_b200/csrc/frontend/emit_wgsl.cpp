@@ -270,7 +270,43 @@ class WgslWriter {
         out_ << ";\n";
         break;
       case Stmt::Assign: assign(s, d, false); out_ << "\n"; break;
-      case Stmt::CallStmt: out_ << expr(*s.a) << ";\n"; break;
+      case Stmt::CallStmt: {
+        // f(p.xz, a) with an out/inout parameter: WGSL cannot take the address of a swizzle, so the
+        // components travel through a temporary (what naga does for GLSL out-parameters)
+        const Expr& c = *s.a;
+        std::vector<std::pair<const Expr*, std::string>> temps;
+        if (c.k == Expr::UserCall) {
+          for (size_t i = 0; i < c.args.size(); ++i) {
+            const Expr* a = c.args[i].get();
+            if (c.fn->params[i]->by_ref && a->k == Expr::Swizzle && a->nswz > 1 && !a->args[0]->ty.is_matrix()) {
+              const std::string t = fresh("swz");
+              temps.emplace_back(a, t);
+              out_ << "var " << t << ": " << type_name(a->ty) << " = " << expr(*a) << ";\n";
+              indent(d);
+            }
+          }
+        }
+        if (temps.empty()) { out_ << expr(c) << ";\n"; break; }
+        out_ << c.fn->name << "(";
+        for (size_t i = 0; i < c.args.size(); ++i) {
+          out_ << (i ? ", " : "");
+          const std::string* t = nullptr;
+          for (const auto& tp : temps) if (tp.first == c.args[i].get()) t = &tp.second;
+          if (t) out_ << "&" << *t;
+          else if (c.fn->params[i]->by_ref) {
+            const Expr& a = *c.args[i];
+            if (a.k == Expr::VarRef && a.var->by_ref && a.var->storage == Var::Param && !rename_.count(a.var)) out_ << a.var->name;
+            else out_ << "&" << expr(a);
+          } else out_ << expr(*c.args[i]);
+        }
+        out_ << ");\n";
+        for (const auto& tp : temps)
+          for (int k = 0; k < tp.first->nswz; ++k) {
+            indent(d);
+            out_ << expr(*tp.first->args[0]) << "." << "xyzw"[tp.first->swz[k]] << " = " << tp.second << "." << "xyzw"[k] << ";\n";
+          }
+        break;
+      }
       case Stmt::Return:
         if (s.a) out_ << "return " << expr(*s.a) << ";\n"; else out_ << "return;\n";
         break;

@@ -724,6 +724,63 @@ def test_shadertoy_style_raymarcher(built):
     assert sh.create_shader_module(None).cubin_size > 0
 
 
+def test_shadertoy_idioms_swizzled_inout_argument(built):
+    """tests/data/shadertoy_idioms.glsl: pModPolar(q.xz, 6.) -- an inout parameter fed with a swizzle --
+    plus function-like macros, a global written per call, a constant array, float loop counters,
+    while(true)/break, folding with swizzle swaps; against a float64 numpy transcription"""
+    code = open(os.path.join(ROOT, "tests", "data", "shadertoy_idioms.glsl")).read()
+    sh = s2m.Sdf3DShader.from_shadertoy_source(code, "map")
+    assert "pModPolar(&swz_1, 6f);" in sh.source and "q.z = swz_1.y;" in sh.source   # standard WGSL, no &q.xz
+    pts = points(4.0, 1500)
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+
+    def rbox(p, b, r):
+        q = np.abs(p) - b
+        return np.linalg.norm(np.maximum(q, 0)) + min(max(q[0], max(q[1], q[2])), 0) - r
+    def hexprism(p, h):
+        k = np.array([-0.8660254, 0.5, 0.57735])
+        p = np.abs(p)
+        p[:2] = p[:2] - 2.0 * min(k[:2] @ p[:2], 0.0) * k[:2]
+        d0 = np.linalg.norm(p[:2] - np.array([np.clip(p[0], -k[2] * h[0], k[2] * h[0]), h[0]])) * np.sign(p[1] - h[0])
+        d = np.array([d0, p[2] - h[1]])
+        return min(max(d[0], d[1]), 0.0) + np.linalg.norm(np.maximum(d, 0.0))
+    def mod(x, y): return x - y * np.floor(x / y)
+    def fractal(p):
+        s_ = 1.0
+        for i in range(5):
+            p = np.abs(p) - np.array([0.6, 0.4, 0.3]) * s_
+            if p[0] < p[1]: p[[0, 1]] = p[[1, 0]]
+            if p[0] < p[2]: p[[0, 2]] = p[[2, 0]]
+            a = 0.3 + i * 0.1
+            y, z = p[1], p[2]                      # p.yz *= mat2(c, s, -s, c): row vector times matrix
+            p[1], p[2] = y * np.cos(a) + z * np.sin(a), y * -np.sin(a) + z * np.cos(a)
+            s_ *= 0.6
+        return rbox(p, np.full(3, 0.1 * s_ * 4.0), 0.01)
+    def expect(p):
+        d = 1e10
+        q = p.copy()
+        ang = 6.2831853 / 6.0
+        a = np.arctan2(q[2], q[0]) + ang / 2
+        r = np.hypot(q[0], q[2])
+        a = mod(a, ang) - ang / 2
+        q[0], q[2] = np.cos(a) * r, np.sin(a) * r
+        d = min(d, hexprism(q - np.array([1.2, 0, 0]), (0.2, 0.3)))
+        t = np.float32(0.0)
+        while t < 1.0:
+            d = min(d, np.linalg.norm(p - np.array([0, float(t) - 0.5, 0])) - 0.15 * (1 - float(t)))
+            t = np.float32(t + np.float32(0.34))
+        for k in range(3):
+            d = min(d, np.linalg.norm(p - np.eye(3)[k] * 0.9) - 0.1)
+        d = min(d, fractal(p * 1.3) / 1.3)
+        rr = mod(p + 0.75, 1.5) - 0.75
+        return max(d, -(np.linalg.norm(rr) - 0.2))     # gTime = 0
+
+    want = np.array([expect(p) for p in pts.astype(np.float64)])
+    err = np.abs(got - want)
+    assert np.quantile(err, 0.99) < 2e-5 and err.max() < 1e-3
+    assert sh.create_shader_module(None).cubin_size > 0
+
+
 def test_matrices(built, tmp_path):
     """mat2/mat3 (GLSL) and mat2x2f/mat3x3<f32> (WGSL): constructors, m*v, v*m, m*m, m[i], transpose"""
     glsl = textwrap.dedent("""\
