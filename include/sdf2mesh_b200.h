@@ -96,7 +96,9 @@ int s2m_ctx_device_info(const s2m_ctx* ctx, char* name, size_t name_len, int* sm
 /* ------------------------------------------------------------------ module = compiled SDF
  * replaces Sdf3DShader::create_shader_module (shader.rs:220) + create_compute_pipeline (main.rs:283-290):
  * front-end -> CUDA C++ -> NVRTC (sm_100a, --fmad=false) -> cubin -> cuModuleLoadData.
- * ctx may be NULL: compile to cubin only (no device needed; used by CPU-side tests). */
+ * ctx may be NULL: compile to cubin only (no device needed; used by CPU-side tests).
+ * With the environment variable S2M_CACHE_DIR set, cubins are kept there (one file per distinct
+ * translation unit + options + NVRTC version) and a repeated compile is a file read. */
 typedef struct s2m_module s2m_module;
 #define S2M_COMPILE_ALLOW_FMA 1u /* let ptxas contract a*b+c (faster, NOT bit-identical to the oracle) */
 int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32_t flags, s2m_module** out);

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -309,6 +310,40 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
     minb_opt = std::string("-DS2M_K1_MINBLOCKS=") + std::to_string(std::max(1, std::min(8, atoi(e))));
     opts.push_back(minb_opt.c_str());
   }
+  // Optional on-disk cubin cache (S2M_CACHE_DIR): keyed by everything that determines the cubin -- the
+  // generated translation unit, the embedded headers, the options and the NVRTC version.  A serving
+  // process that sees the same SDF again skips the ~0.5 s compile.
+  std::string cache_path;
+  if (const char* dir = getenv("S2M_CACHE_DIR")) {
+    if (*dir) {
+      int nv_major = 0, nv_minor = 0;
+      nvrtcVersion(&nv_major, &nv_minor);
+      std::string key = m->cuda_source;
+      for (const char* h : hdr_src) { key += '\0'; key += h; }
+      for (const char* o : opts) { key += '\0'; key += o; }
+      key += "\0nvrtc " + std::to_string(nv_major) + "." + std::to_string(nv_minor) + " " + s2m_version();
+      unsigned long long h1 = 1469598103934665603ull, h2 = 0x9e3779b97f4a7c15ull;  // two independent 64-bit FNV-1a style hashes
+      for (unsigned char ch : key) { h1 = (h1 ^ ch) * 1099511628211ull; h2 = (h2 + ch) * 0xff51afd7ed558ccdull; h2 ^= h2 >> 29; }
+      char name[64];
+      snprintf(name, sizeof name, "/%016llx%016llx.cubin", h1, h2);
+      cache_path = std::string(dir) + name;
+      if (FILE* f = fopen(cache_path.c_str(), "rb")) {
+        fseek(f, 0, SEEK_END);
+        const long n = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (n > 64) {
+          m->cubin.resize((size_t)n);
+          if (fread(m->cubin.data(), 1, (size_t)n, f) != (size_t)n || memcmp(m->cubin.data(), "\x7f" "ELF", 4) != 0) m->cubin.clear();
+        }
+        fclose(f);
+      }
+    }
+  }
+  const bool cache_hit = !m->cubin.empty();
+  if (cache_hit) {
+    nvrtcDestroyProgram(&prog);
+    m->log = "cubin loaded from " + cache_path;
+  } else {
   r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);
@@ -323,6 +358,15 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   m->cubin.resize(cs);
   nvrtcGetCUBIN(prog, m->cubin.data());
   nvrtcDestroyProgram(&prog);
+  if (!cache_path.empty()) {  // best effort: write to a temporary name, then rename (atomic on POSIX)
+    const std::string tmp = cache_path + ".tmp" + std::to_string((long long)getpid());
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      const bool ok = fwrite(m->cubin.data(), 1, m->cubin.size(), f) == m->cubin.size();
+      fclose(f);
+      if (!ok || rename(tmp.c_str(), cache_path.c_str()) != 0) remove(tmp.c_str());
+    }
+  }
+  }  // !cache_hit
   double t2 = now_ms();
   m->ms_nvrtc = t2 - t1;
   if (ctx) {

@@ -80,3 +80,23 @@ def test_params_from_cli(built):
     for res, want in [(128, 128), (100, 128), (129, 256), (3, 4), (2048, 2048), (2049, 4096)]:
         p, r = s2m.params_from_cli(res, 5.0)
         assert p.dims[0] == want and r == (res != want) and p.bb_max[2] == 2.5
+
+
+def test_cubin_cache(built, tmp_path, monkeypatch):
+    """S2M_CACHE_DIR: the second compile of the same SDF loads the cubin from disk; another SDF gets another file"""
+    import sdf2mesh_b200 as s2m
+    monkeypatch.setenv("S2M_CACHE_DIR", str(tmp_path))
+    src = "fn sdf3d(p: vec3f) -> f32 { return length(p) - 0.75; }"
+    a = s2m.Sdf3DShader.from_source(src).create_shader_module(None)
+    assert "loaded from" not in a.log and len(list(tmp_path.glob("*.cubin"))) == 1
+    b = s2m.Sdf3DShader.from_source(src).create_shader_module(None)
+    assert "cubin loaded from" in b.log and b.cubin_size == a.cubin_size
+    s2m.Sdf3DShader.from_source(src.replace("0.75", "0.5")).create_shader_module(None)
+    assert len(list(tmp_path.glob("*.cubin"))) == 2 and not list(tmp_path.glob("*.tmp*"))
+    # a damaged entry is ignored and rewritten
+    f = sorted(tmp_path.glob("*.cubin"))[0]
+    f.write_bytes(b"garbage" * 20)
+    monkeypatch.setenv("S2M_CACHE_DIR", str(tmp_path))
+    for s in (src, src.replace("0.75", "0.5")):
+        assert s2m.Sdf3DShader.from_source(s).create_shader_module(None).cubin_size > 1000
+    assert f.read_bytes()[:4] == b"\x7fELF"
