@@ -352,27 +352,56 @@ class GlslParser : public ParserBase {
       StmtP s = mk_stmt(Stmt::For);
       push_scope();
       expect("(");
+      std::vector<StmtP> inits;  // several declarators / comma-separated init expressions
       if (!is_punct(";")) {
         if (at_type() && (peek(1).k == Token::Ident || is_punct("[", 1))) {
           StmtP tmp = mk_stmt(Stmt::Block);
           parse_declaration_into(tmp);
-          if (tmp->body.size() != 1) b.unsupported("several declarators in a for-init");
-          s->init = tmp->body[0];
-        } else s->init = parse_expression_statement();
+          inits = tmp->body;
+        } else {
+          inits.push_back(parse_expression_statement());
+          while (accept(",")) inits.push_back(parse_expression_statement());
+        }
       }
       expect(";");
       if (!is_punct(";")) s->a = parse_condition();
       expect(";");
+      std::vector<StmtP> conts;
       if (!is_punct(")")) {
-        s->cont = parse_expression_statement();
-        if (is_punct(",")) b.unsupported("comma operator in a for header");
+        conts.push_back(parse_expression_statement());
+        while (accept(",")) conts.push_back(parse_expression_statement());
       }
       expect(")");
       ++loop_depth;
-      s->body.push_back(parse_body());
+      StmtP body = parse_body();
       --loop_depth;
       pop_scope();
-      blk->body.push_back(s);
+      if (inits.size() <= 1 && conts.size() <= 1) {
+        if (!inits.empty()) s->init = inits[0];
+        if (!conts.empty()) s->cont = conts[0];
+        s->body.push_back(body);
+        blk->body.push_back(s);
+        return;
+      }
+      // for (a, b; c; d, e) body  ==  { a; b; loop { if (!c) break; body; continuing { d; e; } } }
+      // (`continue` in the body still runs d and e: that is what a WGSL continuing block does)
+      StmtP outer = mk_stmt(Stmt::Block);
+      for (const StmtP& i : inits) outer->body.push_back(i);
+      StmtP loop = mk_stmt(Stmt::Loop);
+      StmtP lbody = mk_stmt(Stmt::Block);
+      if (s->a) {
+        StmtP guard = mk_stmt(Stmt::If);
+        guard->a = b.unary(Op::Not, s->a);
+        guard->then_s = mk_stmt(Stmt::Block);
+        guard->then_s->body.push_back(mk_stmt(Stmt::Break));
+        lbody->body.push_back(guard);
+      }
+      lbody->body.push_back(body);
+      loop->body.push_back(lbody);
+      loop->cont = mk_stmt(Stmt::Block);
+      for (const StmtP& c : conts) loop->cont->body.push_back(c);
+      outer->body.push_back(loop);
+      blk->body.push_back(outer);
       return;
     }
     if (accept_ident("while")) {
@@ -530,7 +559,7 @@ class GlslParser : public ParserBase {
     ExprP e = parse_postfix(parse_primary());
     if (is_punct("++") || is_punct("--")) {
       // allowed only when the whole statement is `x++;` -- handled by the caller; elsewhere reject
-      if (!(is_punct(";", 1) || is_punct(")", 1))) b.unsupported("++/-- inside an expression");
+      if (!(is_punct(";", 1) || is_punct(")", 1) || is_punct(",", 1))) b.unsupported("++/-- inside an expression");
     }
     return e;
   }

@@ -781,6 +781,36 @@ def test_shadertoy_idioms_swizzled_inout_argument(built):
     assert sh.create_shader_module(None).cubin_size > 0
 
 
+def test_glsl_comma_in_for_header(built, tmp_path):
+    """for (int i = 0, j = 5; i < j; i++, j--): several declarators and a comma-separated continuing part
+    become a WGSL loop with a continuing block, so `continue` still advances both counters"""
+    frag = tmp_path / "comma.frag"
+    frag.write_text(textwrap.dedent("""\
+        #version 450 core
+        float sdf(vec3 p) {
+          float r = 0.0;
+          for (int i = 0, j = 5; i < j; i++, j--) { if (i == 1) continue; r += p.x * float(i) + p.y * float(j); }
+          int k; float w;
+          for (k = 0, w = 1.0; k < 3; ++k, w *= 0.5) r += w * p.z;
+          return r;
+        }
+        void main() {}
+        """))
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    assert "continuing {" in sh.source
+    pts = points(4.0, 300)
+    want = []
+    for p in pts.astype(np.float64):
+        r, i, j = 0.0, 0, 5
+        while i < j:
+            if i != 1:
+                r += p[0] * i + p[1] * j
+            i, j = i + 1, j - 1
+        r += (1.0 + 0.5 + 0.25) * p[2]
+        want.append(r)
+    assert np.abs(host_eval.eval_points(sh.lower_to_cuda(), pts) - np.array(want)).max() < 1e-5
+
+
 def test_matrices(built, tmp_path):
     """mat2/mat3 (GLSL) and mat2x2f/mat3x3<f32> (WGSL): constructors, m*v, v*m, m*m, m[i], transpose"""
     glsl = textwrap.dedent("""\
