@@ -80,13 +80,44 @@ class GlslParser : public ParserBase {
       if (base.is_array() || base_unsized) b.unsupported("arrays of arrays");
       ty = parse_array_suffix(base, &unsized);
     }
-    if (allow_init && accept("=")) *init = parse_assignment_expr();
+    if (allow_init && accept("=")) {
+      if (is_punct("{")) {  // GLSL 4.20 initializer list: float a[3] = {1., 2., 3.};  S s = {1., vec3(0.)};
+        *init = parse_initializer_list(unsized ? Type::void_() : ty, base);
+      } else {
+        *init = parse_assignment_expr();
+      }
+    }
     if (unsized) {
       if (!*init || !(*init)->ty.is_array() || !((*init)->ty.adef->elem == base)) b.error("unsized array needs an array initializer of the same element type");
       ty = (*init)->ty;
     }
     return ty;
   }
+  // `{ a, b, ... }` for an array (elements), a struct (members in order) or a vector / matrix
+  // (constructor arguments).  `ty` void: an unsized array of `elem`.
+  ExprP parse_initializer_list(Type ty, Type elem) {
+    expect("{");
+    std::vector<ExprP> items;
+    const bool as_array = ty.is_void() || ty.is_array();
+    const Type el = ty.is_array() ? ty.adef->elem : elem;
+    while (!is_punct("}")) {
+      Type item_ty = as_array ? el : ty.is_struct() ? (items.size() < ty.sdef->field_types.size() ? ty.sdef->field_types[items.size()] : Type::void_()) : Type::void_();
+      if (is_punct("{")) {
+        if (item_ty.is_void() || !(item_ty.is_aggregate() || item_ty.is_vector() || item_ty.is_matrix())) b.error("unexpected nested initializer list");
+        items.push_back(parse_initializer_list(item_ty, item_ty.is_array() ? item_ty.adef->elem : item_ty));
+      } else {
+        items.push_back(parse_assignment_expr());
+      }
+      if (!accept(",")) break;
+    }
+    expect("}");
+    if (ty.is_void()) {
+      if (items.empty()) b.error("cannot infer the length of an empty initializer list");
+      ty = mod->array_of(el, (int)items.size());
+    }
+    return b.construct(ty, false, items);
+  }
+
   void parse_struct() {  // struct Name { float a; vec3 b, c; float d[3]; };
     advance();
     StructDef* d = declare_struct(expect_ident("struct name"));

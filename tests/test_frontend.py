@@ -811,6 +811,27 @@ def test_glsl_comma_in_for_header(built, tmp_path):
     assert np.abs(host_eval.eval_points(sh.lower_to_cuda(), pts) - np.array(want)).max() < 1e-5
 
 
+def test_glsl_initializer_lists(built, tmp_path):
+    """GLSL 4.20 brace initializers for arrays (sized and unsized), structs (nested) and vectors"""
+    frag = tmp_path / "init.frag"
+    frag.write_text(textwrap.dedent("""\
+        #version 450 core
+        struct S { float r; vec3 c; float w[2]; };
+        const float K[] = {0.5, 0.25, 0.125};
+        float sdf(vec3 p) {
+          float a[3] = {1.0, 2.0, 3.0};
+          S s = {0.75, {0.1, 0.2, 0.3}, {2.0, 4.0}};
+          vec2 v = {p.x, p.y};
+          return length(p - s.c) - s.r + a[1] * K[2] + s.w[1] * 0.01 + v.y * 0.001;
+        }
+        void main() {}
+        """))
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    pts = points(4.0, 300)
+    want = [np.linalg.norm(p - np.array([0.1, 0.2, 0.3])) - 0.75 + 2 * 0.125 + 0.04 + p[1] * 0.001 for p in pts.astype(np.float64)]
+    assert np.abs(host_eval.eval_points(sh.lower_to_cuda(), pts) - np.array(want)).max() < 1e-5
+
+
 def test_matrices(built, tmp_path):
     """mat2/mat3 (GLSL) and mat2x2f/mat3x3<f32> (WGSL): constructors, m*v, v*m, m*m, m[i], transpose"""
     glsl = textwrap.dedent("""\
