@@ -348,3 +348,53 @@ def test_u32_quad_indices(ctx, tmp_path):
     s.free()
     r.free()
     o.free()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_configurations(ctx, seed):
+    """random grid shapes, boxes, flag combinations, slab budgets (1 .. many z-chunks, so both the single-
+    stream and the two-stream chunk pipeline) and z-slab splits, each against the oracle; every
+    configuration runs twice on the same context (the second run streams its output copies)"""
+    rng = np.random.default_rng(1000 + seed)
+    name = ["torus", "mandelbulb", "martin_cube", "p_key"][seed % 4]
+    scale = {"torus": 1.0, "mandelbulb": 1.6, "martin_cube": 1.2, "p_key": 9.0}[name]
+    dims = tuple(int(v) for v in rng.integers(9, 72, 3))
+    centre = rng.uniform(-0.15, 0.15, 3) * scale
+    half = rng.uniform(0.7, 1.3, 3) * scale
+    bmin, bmax = (centre - half).astype(np.float32), (centre + half).astype(np.float32)
+    all_slices = bool(rng.integers(0, 2))
+    consistent = bool(rng.integers(0, 2))
+    flags = (s2m.MESH_ALL_SLICES if all_slices else 0) | (s2m.MESH_CONSISTENT_CORNERS if consistent else 0)
+    flags |= s2m.MESH_QUADS_U32 if rng.integers(0, 2) else 0
+    flags |= s2m.MESH_CLASSIFY_FROM_SLAB if rng.integers(0, 4) == 0 else 0
+    oflags = (oracle.FLAG_ALL_SLICES if all_slices else 0) | (oracle.FLAG_CONSISTENT_CORNERS if consistent else 0)
+    plane_bytes = ((dims[0] + 1 + 31) // 32 * 32) * (dims[1] + 1) * 4
+    budget = int(plane_bytes * rng.choice([2, 3, 5, 9, 1000])) + 64
+    n_slices = dims[2] if all_slices else dims[2] - 1
+    cuts = sorted(set([0, n_slices] + [int(c) for c in rng.integers(1, max(2, n_slices), rng.integers(0, 3))]))
+    o = oracle.mesh_run(name, dims, flags=oflags, bmin=bmin, bmax=bmax)
+    m = module_for(ctx, name)
+    try:
+        for rep in range(2):
+            p = s2m.make_params(dims, bmin, bmax, flags=flags, slab_budget_bytes=budget)
+            r = s2m.mesh_run(ctx, m, p)
+            assert_same(r.data(), o, f"seed {seed} rep {rep}: {name} {dims} flags {flags} budget {budget}")
+            r.free()
+        parts, base = [], 0
+        for zb, ze in zip(cuts[:-1], cuts[1:]):
+            p = s2m.make_params(dims, bmin, bmax, flags=flags, slab_budget_bytes=budget, z_begin=zb, z_end=ze)
+            s = s2m.mesh_begin(ctx, m, p)
+            n_own = s.info().n_vertices
+            s.finish(base)
+            base += n_own
+            parts.append(s)
+        what = f"seed {seed}: {name} {dims} cuts {cuts} flags {flags}"
+        if parts:
+            assert np.array_equal(np.concatenate([s.data().keys for s in parts]), o.keys), what
+            assert np.array_equal(np.concatenate([s.data().quads for s in parts]).astype(np.uint64).reshape(-1, 4), o.quads), what
+            assert f32_equal(np.concatenate([s.data().positions for s in parts]), o.positions).all(), what
+            assert sum(s.data().n_invalid_quads for s in parts) == o.n_invalid_quads, what
+        for s in parts:
+            s.free()
+    finally:
+        o.free()
