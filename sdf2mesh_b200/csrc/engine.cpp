@@ -165,6 +165,7 @@ struct s2m_ctx {
   std::vector<cudaEvent_t> ev_pool;   // per-launch timing events, grown on demand
   uint64_t hint_nv = 0, hint_nq = 0;  // output sizes of the previous run (pinned capacity guess)
   bool busy = false;  // a begin() without finish()/free() is outstanding
+  uint32_t publish_launches = 0;  // k_publish launches since the last begin() (they count as kernel launches too)
 
   void* lease_pinned(size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -608,6 +609,7 @@ int read_counters(s2m_ctx* c, cudaStream_t s) {
   // not a cudaMemcpy: see k_publish in kernels_static.cu
   int e = s2m_launch_publish(c->counters.as<unsigned long long>(), c->h_counters, C_COUNT, s);
   if (e) return fail(S2M_ERR_CUDA, std::string("k_publish launch: ") + cudaGetErrorString((cudaError_t)e));
+  ++c->publish_launches;
   CUDA_TRY(cudaStreamSynchronize(s));
   return S2M_OK;
 }
@@ -677,6 +679,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
 
   Trace tr;
   c->busy = true;
+  c->publish_launches = 0;
   struct BusyGuard { s2m_ctx* c; bool keep = false; ~BusyGuard() { if (!keep) c->busy = false; } } guard{c};
   r->wall0 = now_ms();
   cudaStream_t s = c->stream;
@@ -990,6 +993,8 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
   tr.mark("finish: copies done");
   r->t.host_wall_ms = now_ms() - r->wall0;
+  r->t.launches += c->publish_launches;
+  c->publish_launches = 0;
   finalize_timings(c, r);
   r->finished = true;
   c->busy = false;
