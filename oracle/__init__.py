@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-SDF_IDS = {"torus": 0, "martin_cube": 1, "p_key": 2, "mandelbulb": 3, "naga_sphere": 4}
+SDF_IDS = {"torus": 0, "martin_cube": 1, "p_key": 2, "mandelbulb": 3, "naga_sphere": 4, "plugin": 99}
 FLAG_ALL_SLICES = 1
 FLAG_CONSISTENT_CORNERS = 64  # not the reference's arithmetic; mirrors S2M_MESH_CONSISTENT_CORNERS
 
@@ -44,6 +44,7 @@ def lib():
         L.oracle_write_stl.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.oracle_write_ply.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         L.oracle_eval.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.oracle_set_plugin.argtypes = [ctypes.c_void_p]
         L.oracle_axis_coords.argtypes = [ctypes.c_uint32, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
         L.oracle_rust_f32.restype = ctypes.c_char_p
         L.oracle_rust_f32.argtypes = [ctypes.c_float]
@@ -109,6 +110,13 @@ def mesh_run(sdf, res, bounds=2.0, eps=1e-4, flags=0, z_begin=0, z_end=0, thread
     quads = np.empty((nq.value, 4), np.uint64)
     L.oracle_mesh_copy(h, pos.ctypes.data, nrm.ctypes.data, keys.ctypes.data, nib.ctypes.data, quads.ctypes.data)
     return OracleMesh(pos, nrm, keys, nib, quads, ninv.value, sc.value, sq.value, h)
+
+
+def set_plugin(fn_ptr) -> None:
+    """SDF id "plugin" = this host function `float f(float x, float y, float z)` (a ctypes function or
+    an address): the front-end's emitted code compiled for the host, see tests/support/host_eval.py"""
+    addr = ctypes.cast(fn_ptr, ctypes.c_void_p) if fn_ptr is not None else ctypes.c_void_p(0)
+    lib().oracle_set_plugin(addr)
 
 
 def eval_points(sdf, pts) -> np.ndarray:

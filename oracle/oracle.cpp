@@ -226,6 +226,8 @@ int oracle_num_threads() {
   return n ? (int)n : 1;
 }
 
+void oracle_set_plugin(void* fn) { osdf::g_plugin = reinterpret_cast<osdf::PluginFn>(fn); }
+
 void oracle_eval(int sdf, const float* pts, float* out, uint64_t n) {
   for (uint64_t i = 0; i < n; ++i) out[i] = osdf::eval(sdf, V3{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]});
 }

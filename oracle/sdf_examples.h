@@ -218,7 +218,13 @@ static inline float sdf_naga_sphere(V3 p) {
   return sphere_0 + displacement;
 }
 
-enum SdfId { SDF_TORUS = 0, SDF_MARTIN_CUBE = 1, SDF_P_KEY = 2, SDF_MANDELBULB = 3, SDF_NAGA_SPHERE = 4, SDF_COUNT };
+enum SdfId { SDF_TORUS = 0, SDF_MARTIN_CUBE = 1, SDF_P_KEY = 2, SDF_MANDELBULB = 3, SDF_NAGA_SPHERE = 4, SDF_COUNT, SDF_PLUGIN = 99 };
+
+// SDF_PLUGIN: a function supplied by the test (oracle_set_plugin) -- the front-end's emitted C++ compiled
+// for the host by tests/support/host_eval.py -- so that the oracle's cell loop, scan and quad assembly
+// can be compared with the GPU path for shaders that have no hand transcription here.
+typedef float (*PluginFn)(float, float, float);
+static PluginFn g_plugin = nullptr;
 
 static inline float eval(int id, V3 p) {
   switch (id) {
@@ -227,6 +233,7 @@ static inline float eval(int id, V3 p) {
     case SDF_P_KEY: return pkey::sdf(p);
     case SDF_MANDELBULB: return sdf_mandelbulb(p);
     case SDF_NAGA_SPHERE: return sdf_naga_sphere(p);
+    case SDF_PLUGIN: return g_plugin ? g_plugin(p.x, p.y, p.z) : 0.0f;
   }
   return 0.0f;
 }

@@ -21,6 +21,7 @@ namespace s2m_user {
 using namespace s2m;
 %s
 }
+extern "C" float host_eval1(float x, float y, float z) { return s2m_user::sdf3d(s2m::mk3(x, y, z)); }
 extern "C" void host_eval(const float* pts, float* out, unsigned long long n) {
   for (unsigned long long i = 0; i < n; ++i)
     out[i] = s2m_user::sdf3d(s2m::mk3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
@@ -43,6 +44,12 @@ def compile_host(cuda_body: str):
     lib.host_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
     _CACHE[key] = lib
     return lib
+
+
+def scalar_function(cuda_body: str):
+    """the compiled `float sdf3d(x, y, z)` as a ctypes function (for oracle.set_plugin); the library
+    stays loaded for the life of the process"""
+    return compile_host(cuda_body).host_eval1
 
 
 def eval_points(cuda_body: str, pts) -> np.ndarray:

@@ -124,3 +124,37 @@ def test_naga_test_shader_meshes_to_its_golden_digest(ctx, tmp_path):
         d = r.data()
         assert mesh_digests(d.positions, d.normals, d.keys, d.nibbles, d.quads, d.n_invalid_quads) == golden[key]
         r.free()
+
+
+def _program(name, tmp_path):
+    if name.startswith("shadertoy_"):
+        return s2m.Sdf3DShader.from_shadertoy_source(open(os.path.join(ROOT, "tests", "data", name + ".glsl")).read(), "map")
+    if name in GLSL_PROGRAMS:
+        frag = tmp_path / (name + ".frag")
+        frag.write_text(textwrap.dedent(GLSL_PROGRAMS[name]))
+        return s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    return s2m.Sdf3DShader.from_source(textwrap.dedent(WGSL_PROGRAMS[name]))
+
+
+@pytest.mark.parametrize("name,res,bounds", [("aggregates", 48, 4.0), ("control_flow", 40, 3.0), ("integer_hash_noise", 48, 3.0),
+                                             ("shadertoy_raymarcher", 64, 3.0), ("shadertoy_idioms", 64, 3.5)])
+def test_generated_programs_mesh_like_the_oracle(ctx, tmp_path, name, res, bounds):
+    """whole-path parity for shaders without a hand transcription: the oracle runs its cell loop on the
+    front-end's emitted code compiled for the host (SDF id "plugin"), the GPU path on the same code
+    compiled by NVRTC; keys, nibbles, quads, positions and normals must agree bit for bit"""
+    import oracle
+    from tests.test_parity_gpu import assert_same
+    sh = _program(name, tmp_path)
+    oracle.set_plugin(host_eval.scalar_function(sh.lower_to_cuda()))
+    try:
+        for flags, oflags in ((0, 0), (s2m.MESH_ALL_SLICES | s2m.MESH_CONSISTENT_CORNERS, oracle.FLAG_ALL_SLICES | oracle.FLAG_CONSISTENT_CORNERS)):
+            o = oracle.mesh_run("plugin", res, bounds, flags=oflags)
+            bmin, bmax = oracle.cube_bounds(bounds)
+            p = s2m.make_params(res, bmin, bmax, flags=flags)   # not params_from_cli: that rounds res up to a power of two
+            r = s2m.mesh_run(ctx, sh.create_shader_module(ctx), p)
+            assert len(o.keys) > 300, "the test box should contain some surface"
+            assert_same(r.data(), o, f"{name} flags {flags}")
+            r.free()
+            o.free()
+    finally:
+        oracle.set_plugin(None)

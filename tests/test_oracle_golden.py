@@ -86,3 +86,21 @@ def test_stl_ply_text_shape(tmp_path):
     assert ply[:3] == ["ply", "format ascii 1.0", "comment written by rust-sdf"]
     assert ply[3] == f"element vertex {len(m.keys)}" and ply[10] == f"element face {2 * len(m.quads)}" and ply[12] == "end_header"
     m.free()
+
+
+def test_plugin_sdf_equals_hand_transcriptions(built):
+    """oracle SDF id "plugin" (the front-end's emitted code compiled for the host) against the hand
+    transcriptions in oracle/sdf_examples.h: the same meshes, bit for bit, for every example input"""
+    from tests.conftest import load_example_shader
+    from tests.support import host_eval
+    from tests.support.digest import f32_equal
+    for name, res, bounds in (("torus", 48, 2.0), ("martin_cube", 40, 2.0), ("p_key", 40, 20.0), ("mandelbulb", 40, 5.0)):
+        oracle.set_plugin(host_eval.scalar_function(load_example_shader(name).lower_to_cuda()))
+        a = oracle.mesh_run("plugin", res, bounds)
+        b = oracle.mesh_run(name, res, bounds)
+        assert len(a.keys) > 500
+        assert np.array_equal(a.keys, b.keys) and np.array_equal(a.quads, b.quads) and np.array_equal(a.nibbles, b.nibbles)
+        assert f32_equal(a.positions, b.positions).all() and f32_equal(a.normals, b.normals).all()
+        a.free()
+        b.free()
+    oracle.set_plugin(None)
