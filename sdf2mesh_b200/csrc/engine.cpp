@@ -421,15 +421,16 @@ struct SlabViewDev {  // must match S2mSlabView
 };
 // K1 block shape (bx, by), bx*by = 256; S2M_K1_BLOCK=8x32 overrides the default for experiments
 void k1_block_shape(unsigned* bx, unsigned* by) {
-  static unsigned sx = 0, sy = 0;
-  if (!sx) {
-    sx = 8; sy = 32;
+  struct Shape { unsigned x = 8, y = 32; };
+  static const Shape shape = [] {  // initialised once, thread-safe (contexts may be driven from several host threads)
+    Shape sh;
     if (const char* e = getenv("S2M_K1_BLOCK")) {
       unsigned a = 0, b = 0;
-      if (sscanf(e, "%ux%u", &a, &b) == 2 && a && b && a * b <= 256 && (a * b) % 32 == 0 && a % 8 == 0) { sx = a; sy = b; }
+      if (sscanf(e, "%ux%u", &a, &b) == 2 && a && b && a * b <= 256 && (a * b) % 32 == 0 && a % 8 == 0) { sh.x = a; sh.y = b; }
     }
-  }
-  *bx = sx; *by = sy;
+    return sh;
+  }();
+  *bx = shape.x; *by = shape.y;
 }
 struct VertexOutDev {  // must match S2mVertexOut
   float* pos; float* nrm; unsigned long long* key; unsigned char* nibble; unsigned* cand_vrank;
