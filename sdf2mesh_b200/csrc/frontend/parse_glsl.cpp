@@ -12,6 +12,28 @@ class GlslParser : public ParserBase {
   explicit GlslParser(Module* m) : ParserBase(Lang::Glsl, m) {}
   std::map<std::string, std::vector<Function*>> overloads_;
 
+  // Side effects inside expressions (`d += e = map(p)`, `a[i++]`, `while (i++ < n)`): the effect becomes a
+  // statement of its own, issued before the statement that contains the expression (GLSL leaves the
+  // order of operand evaluation undefined, so any order is a valid one); where GLSL does define an
+  // order -- the right side of && and ||, the branches of ?: -- side effects are rejected.
+  std::vector<StmtP>* side_ = nullptr;   // where pending effects go; null: not allowed here
+  int cond_depth_ = 0;                   // > 0 while parsing a conditionally evaluated operand
+  bool leave_postfix_ = false;           // the statement parser itself handles a trailing ++ / --
+  int post_tmp_ = 0;
+  struct SideScope {
+    GlslParser& p;
+    std::vector<StmtP> stmts;
+    std::vector<StmtP>* saved;
+    int saved_depth;
+    explicit SideScope(GlslParser& parser) : p(parser), saved(parser.side_), saved_depth(parser.cond_depth_) { p.side_ = &stmts; p.cond_depth_ = 0; }
+    ~SideScope() { p.side_ = saved; p.cond_depth_ = saved_depth; }
+    void flush_into(const StmtP& blk) { for (const StmtP& st : stmts) blk->body.push_back(st); stmts.clear(); }
+  };
+  void need_side_context(const char* what) {
+    if (!side_) b.unsupported(std::string(what) + " in this position");
+    if (cond_depth_ > 0) b.unsupported(std::string(what) + " inside a conditionally evaluated operand (&&, ||, ?:)");
+  }
+
   void parse(const std::string& src) {
     LexOptions lo;
     lo.glsl = true;
@@ -305,7 +327,9 @@ class GlslParser : public ParserBase {
     for (;;) {
       const std::string name = expect_ident("a variable name");
       ExprP init;
+      SideScope sc(*this);
       const Type ty = declarator_type(base, unsized, &init, true);
+      sc.flush_into(blk);
       if (init) init = b.coerce(init, ty, "initializer");
       Var* v = declare(name, ty, Var::Local);
       v->immutable = q.is_const;
@@ -324,7 +348,9 @@ class GlslParser : public ParserBase {
       ExprP lhs = parse_unary();
       return make_assign(lhs, b.binary(inc ? Op::Add : Op::Sub, lhs, one_for(lhs)));
     }
+    leave_postfix_ = true;
     ExprP lhs = parse_unary();
+    leave_postfix_ = false;
     if (is_punct("=")) {
       advance();
       return make_assign(lhs, parse_assignment_expr());
@@ -372,99 +398,127 @@ class GlslParser : public ParserBase {
       StmtP s = mk_stmt(Stmt::Return);
       if (!is_punct(";")) {
         if (cur_fn->ret.is_void()) b.error("return with a value in a void function");
+        SideScope sc(*this);
         s->a = b.coerce(parse_expr(), cur_fn->ret, "return");
+        sc.flush_into(blk);
       } else if (!cur_fn->ret.is_void()) b.error("return without a value");
       expect(";");
       blk->body.push_back(s);
       return;
     }
-    if (accept_ident("if")) { blk->body.push_back(parse_if()); return; }
+    if (accept_ident("if")) { blk->body.push_back(parse_if(blk)); return; }
     if (accept_ident("for")) {
       StmtP s = mk_stmt(Stmt::For);
       push_scope();
       expect("(");
-      std::vector<StmtP> inits;  // several declarators / comma-separated init expressions
+      std::vector<StmtP> inits;  // several declarators / comma-separated init expressions (+ their side effects)
       if (!is_punct(";")) {
         if (at_type() && (peek(1).k == Token::Ident || is_punct("[", 1))) {
           StmtP tmp = mk_stmt(Stmt::Block);
           parse_declaration_into(tmp);
           inits = tmp->body;
         } else {
-          inits.push_back(parse_expression_statement());
-          while (accept(",")) inits.push_back(parse_expression_statement());
+          for (;;) {
+            SideScope sc(*this);
+            StmtP st = parse_expression_statement();
+            for (const StmtP& e : sc.stmts) inits.push_back(e);
+            inits.push_back(st);
+            if (!accept(",")) break;
+          }
         }
       }
       expect(";");
-      if (!is_punct(";")) s->a = parse_condition();
+      std::vector<StmtP> cond_effects;
+      if (!is_punct(";")) {
+        SideScope sc(*this);
+        s->a = parse_condition();
+        cond_effects = sc.stmts;
+      }
       expect(";");
       std::vector<StmtP> conts;
       if (!is_punct(")")) {
-        conts.push_back(parse_expression_statement());
-        while (accept(",")) conts.push_back(parse_expression_statement());
+        for (;;) {
+          SideScope sc(*this);
+          StmtP st = parse_expression_statement();
+          for (const StmtP& e : sc.stmts) conts.push_back(e);
+          conts.push_back(st);
+          if (!accept(",")) break;
+        }
       }
       expect(")");
       ++loop_depth;
       StmtP body = parse_body();
       --loop_depth;
       pop_scope();
-      if (inits.size() <= 1 && conts.size() <= 1) {
+      if (inits.size() <= 1 && conts.size() <= 1 && cond_effects.empty()) {
         if (!inits.empty()) s->init = inits[0];
         if (!conts.empty()) s->cont = conts[0];
         s->body.push_back(body);
         blk->body.push_back(s);
         return;
       }
-      // for (a, b; c; d, e) body  ==  { a; b; loop { if (!c) break; body; continuing { d; e; } } }
+      // for (a, b; c; d, e) body  ==  { a; b; loop { [effects of c;] if (!c) break; body; continuing { d; e; } } }
       // (`continue` in the body still runs d and e: that is what a WGSL continuing block does)
       StmtP outer = mk_stmt(Stmt::Block);
       for (const StmtP& i : inits) outer->body.push_back(i);
-      StmtP loop = mk_stmt(Stmt::Loop);
-      StmtP lbody = mk_stmt(Stmt::Block);
-      if (s->a) {
-        StmtP guard = mk_stmt(Stmt::If);
-        guard->a = b.unary(Op::Not, s->a);
-        guard->then_s = mk_stmt(Stmt::Block);
-        guard->then_s->body.push_back(mk_stmt(Stmt::Break));
-        lbody->body.push_back(guard);
-      }
-      lbody->body.push_back(body);
-      loop->body.push_back(lbody);
-      loop->cont = mk_stmt(Stmt::Block);
-      for (const StmtP& c : conts) loop->cont->body.push_back(c);
-      outer->body.push_back(loop);
+      outer->body.push_back(make_loop(cond_effects, s->a, body, conts));
       blk->body.push_back(outer);
       return;
     }
     if (accept_ident("while")) {
       StmtP s = mk_stmt(Stmt::While);
       expect("(");
-      s->a = parse_condition();
+      std::vector<StmtP> cond_effects;
+      {
+        SideScope sc(*this);
+        s->a = parse_condition();
+        cond_effects = sc.stmts;
+      }
       expect(")");
       ++loop_depth;
-      s->body.push_back(parse_body());
+      StmtP body = parse_body();
       --loop_depth;
+      if (cond_effects.empty()) s->body.push_back(body);
+      else s = make_loop(cond_effects, s->a, body, {});   // while (i++ < n): the effect runs before every test
       blk->body.push_back(s);
       return;
     }
     if (accept_ident("do")) {
       StmtP s = mk_stmt(Stmt::DoWhile);
       ++loop_depth;
-      s->body.push_back(parse_body());
+      StmtP body = parse_body();
       --loop_depth;
       if (!accept_ident("while")) perr("expected 'while' after do body");
       expect("(");
-      s->a = parse_condition();
+      std::vector<StmtP> cond_effects;
+      {
+        SideScope sc(*this);
+        s->a = parse_condition();
+        cond_effects = sc.stmts;
+      }
       expect(")");
       expect(";");
+      if (cond_effects.empty()) {
+        s->body.push_back(body);
+      } else {  // loop { body; continuing { effects; break if !cond; } }
+        StmtP loop = mk_stmt(Stmt::Loop);
+        loop->body.push_back(body);
+        loop->cont = mk_stmt(Stmt::Block);
+        for (const StmtP& e : cond_effects) loop->cont->body.push_back(e);
+        loop->break_if = b.unary(Op::Not, s->a);
+        s = loop;
+      }
       blk->body.push_back(s);
       return;
     }
     if (accept_ident("break")) { if (!loop_depth && !switch_depth) b.error("break outside of a loop or switch"); expect(";"); blk->body.push_back(mk_stmt(Stmt::Break)); return; }
     if (accept_ident("continue")) { if (!loop_depth) b.error("continue outside of a loop"); expect(";"); blk->body.push_back(mk_stmt(Stmt::Continue)); return; }
     if (accept_ident("discard")) { expect(";"); blk->body.push_back(mk_stmt(Stmt::Discard)); return; }
-    if (accept_ident("switch")) { blk->body.push_back(parse_switch()); return; }
+    if (accept_ident("switch")) { blk->body.push_back(parse_switch(blk)); return; }
+    SideScope sc(*this);
     StmtP s = parse_expression_statement();
     expect(";");
+    sc.flush_into(blk);
     blk->body.push_back(s);
   }
 
@@ -476,10 +530,14 @@ class GlslParser : public ParserBase {
   // switch (e) { case 1: case 2: ...; break; default: ... }  -- labels group into cases; a case
   // that runs into the next label without break/return/continue/discard would fall through,
   // which the IR (like WGSL) does not model.
-  StmtP parse_switch() {
+  StmtP parse_switch(const StmtP& blk) {
     StmtP sw = mk_stmt(Stmt::Switch);
     expect("(");
-    sw->a = switch_selector(parse_expr());
+    {
+      SideScope sc(*this);
+      sw->a = switch_selector(parse_expr());
+      sc.flush_into(blk);
+    }
     expect(")");
     expect("{");
     ++switch_depth;
@@ -514,14 +572,46 @@ class GlslParser : public ParserBase {
     return sw;
   }
 
-  StmtP parse_if() {
+  // loop { effects; if (!cond) break; body; continuing { conts } }
+  StmtP make_loop(const std::vector<StmtP>& effects, const ExprP& cond, const StmtP& body, const std::vector<StmtP>& conts) {
+    StmtP loop = mk_stmt(Stmt::Loop);
+    StmtP lbody = mk_stmt(Stmt::Block);
+    for (const StmtP& e : effects) lbody->body.push_back(e);
+    if (cond) {
+      StmtP guard = mk_stmt(Stmt::If);
+      guard->a = b.unary(Op::Not, cond);
+      guard->then_s = mk_stmt(Stmt::Block);
+      guard->then_s->body.push_back(mk_stmt(Stmt::Break));
+      lbody->body.push_back(guard);
+    }
+    lbody->body.push_back(body);
+    loop->body.push_back(lbody);
+    if (!conts.empty()) {
+      loop->cont = mk_stmt(Stmt::Block);
+      for (const StmtP& c : conts) loop->cont->body.push_back(c);
+    }
+    return loop;
+  }
+
+  // `blk`: where side effects of the condition go (before the if); null for `else if` chains, whose
+  // conditions are evaluated conditionally
+  StmtP parse_if(const StmtP& blk) {
     StmtP s = mk_stmt(Stmt::If);
     expect("(");
-    s->a = parse_condition();
+    if (blk) {
+      SideScope sc(*this);
+      s->a = parse_condition();
+      sc.flush_into(blk);
+    } else {
+      std::vector<StmtP>* saved = side_;
+      side_ = nullptr;
+      s->a = parse_condition();
+      side_ = saved;
+    }
     expect(")");
     s->then_s = parse_body();
     if (accept_ident("else")) {
-      if (accept_ident("if")) s->else_s = parse_if();
+      if (accept_ident("if")) s->else_s = parse_if(nullptr);
       else s->else_s = parse_body();
     }
     return s;
@@ -529,16 +619,27 @@ class GlslParser : public ParserBase {
 
   // ---------------------------------------------------------------- expressions
   ExprP parse_expr() { return parse_assignment_expr(); }
-  ExprP parse_assignment_expr() {  // assignments inside expressions are not supported; this is the ?: level
+  ExprP parse_assignment_expr() {  // the ?: level; an assignment here is a side effect of the enclosing statement
     ExprP c = parse_binary(0);
     if (accept("?")) {
+      ++cond_depth_;
       ExprP t = parse_assignment_expr();
       expect(":");
       ExprP f = parse_assignment_expr();
+      --cond_depth_;
       return b.ternary(c, t, f);
     }
-    if (is_punct("=") || is_punct("+=") || is_punct("-=") || is_punct("*=") || is_punct("/="))
-      b.unsupported("assignment used as an expression");
+    if (peek().k == Token::Punct) {
+      const std::string p = peek().text;
+      const bool compound = p == "+=" || p == "-=" || p == "*=" || p == "/=" || p == "%=" || p == "&=" || p == "|=" || p == "^=" || p == "<<=" || p == ">>=";
+      if (p == "=" || compound) {
+        need_side_context("an assignment inside an expression");
+        advance();
+        ExprP rhs = parse_assignment_expr();   // right-associative: a = b = c
+        side_->push_back(make_assign(c, compound ? b.binary(compound_op(p), c, rhs) : rhs));
+        return c;                               // the value of the assignment is the assigned variable
+      }
+    }
     return c;
   }
   static int prec_of(const std::string& p) {
@@ -566,7 +667,10 @@ class GlslParser : public ParserBase {
       if (prec < 0 || prec < min_prec) break;
       advance();
       if (logical_xor) advance();
+      const bool short_circuit = p == "&&" || p == "||";
+      if (short_circuit) ++cond_depth_;
       ExprP rhs = parse_binary(prec + 1);
+      if (short_circuit) --cond_depth_;
       if (logical_xor) {
         if (!lhs->ty.is_bool() || !rhs->ty.is_bool() || !lhs->ty.is_scalar() || !rhs->ty.is_scalar()) b.error("^^ needs bool operands");
         lhs = b.binary(Op::Ne, lhs, rhs);
@@ -582,15 +686,32 @@ class GlslParser : public ParserBase {
   }
   ExprP parse_unary() {
     b.cur_line = peek().line;
+    const bool leave = leave_postfix_;   // set by parse_expression_statement for its own first operand only
+    leave_postfix_ = false;
     if (accept("-")) return b.unary(Op::Neg, parse_unary());
     if (accept("+")) return parse_unary();
     if (accept("!")) return b.unary(Op::Not, parse_unary());
     if (accept("~")) return b.unary(Op::BitNot, parse_unary());
-    if (is_punct("++") || is_punct("--")) b.unsupported("++/-- inside an expression");
+    if (is_punct("++") || is_punct("--")) {   // ++x inside an expression: x = x + 1 first, value x
+      need_side_context("++/-- inside an expression");
+      const bool inc = advance().text == "++";
+      ExprP lv = parse_unary();
+      side_->push_back(make_assign(lv, b.binary(inc ? Op::Add : Op::Sub, lv, one_for(lv))));
+      return lv;
+    }
     ExprP e = parse_postfix(parse_primary());
     if (is_punct("++") || is_punct("--")) {
-      // allowed only when the whole statement is `x++;` -- handled by the caller; elsewhere reject
-      if (!(is_punct(";", 1) || is_punct(")", 1) || is_punct(",", 1))) b.unsupported("++/-- inside an expression");
+      if (leave && (is_punct(";", 1) || is_punct(")", 1) || is_punct(",", 1))) return e;   // `x++;` is the statement itself
+      // x++ inside an expression: t = x; x = x + 1; value t
+      need_side_context("++/-- inside an expression");
+      const bool inc = advance().text == "++";
+      if (!Builder::is_lvalue(*e)) b.error("++/-- needs a variable");
+      Var* t = declare("_post" + std::to_string(++post_tmp_), e->ty, Var::Local);
+      StmtP decl = mk_stmt(Stmt::VarDecl);
+      decl->var = t; decl->a = e;
+      side_->push_back(decl);
+      side_->push_back(make_assign(e, b.binary(inc ? Op::Add : Op::Sub, e, one_for(e))));
+      return b.var_ref(t);
     }
     return e;
   }

@@ -832,6 +832,51 @@ def test_glsl_initializer_lists(built, tmp_path):
     assert np.abs(host_eval.eval_points(sh.lower_to_cuda(), pts) - np.array(want)).max() < 1e-5
 
 
+def test_glsl_side_effects_inside_expressions(built, tmp_path):
+    """`d += e = map(p)`, `w[i++]`, `while (i++ < n)`, `for (; k++ < 3;)`, `do ... while (++j < 3)`, `a = b = c`,
+    `if ((e = f(p)) > x)`: each effect becomes its own statement in front of the statement that contains it
+    (loop conditions: in front of every test); effects on the conditional side of && / || / ?: are refused"""
+    frag = tmp_path / "fx.frag"
+    frag.write_text(textwrap.dedent("""\
+        #version 450 core
+        float map(vec3 p) { return length(p) - 1.0; }
+        float sdf(vec3 p) {
+          float d = 0.0, e, acc = 0.0;
+          int i = 0, n = 0;
+          float w[4] = float[4](1.0, 2.0, 4.0, 8.0);
+          d += e = map(p);
+          acc += w[i++] + w[i++];
+          while (i++ < 4) acc += 0.5;
+          for (int k = 0; k++ < 3;) { if (k == 2) continue; n += k; }
+          int j = 0;
+          do { acc += 0.25; } while (++j < 3);
+          float a, b2;
+          a = b2 = p.x * 2.0;
+          if ((e = abs(p.y)) > 0.5) acc += e;
+          return d + acc + float(n) + a + b2 + float(i) * 0.01 + float(j) * 0.001;
+        }
+        void main() {}
+        """))
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    assert "var _post1: i32 = i;" in sh.source and "break if !((j < 3i));" in sh.source
+    pts = points(4.0, 300)
+    want = []
+    for p in pts.astype(np.float64):
+        acc = 1 + 2 + 2 * 0.5 + 3 * 0.25        # w[0] + w[1]; i = 2 -> two passes of the while; three of the do
+        e = abs(p[1])
+        if e > 0.5:
+            acc += e
+        want.append((np.linalg.norm(p) - 1.0) + acc + (1 + 3) + 4 * p[0] + 5 * 0.01 + 3 * 0.001)
+    assert np.abs(host_eval.eval_points(sh.lower_to_cuda(), pts) - np.array(want)).max() < 1e-5
+    for bad in ("float sdf(vec3 p) { float e = 0.0; if (p.x > 0.0 && (e = p.y) > 0.0) return e; return 1.0; }",
+                "float sdf(vec3 p) { int i = 0; return p.x > 0.0 ? float(i++) : 1.0; }",
+                "int g = 0; float h = float(g++); float sdf(vec3 p) { return h; }"):
+        frag.write_text("#version 450\n" + bad + "\nvoid main() {}\n")
+        with pytest.raises(s2m.S2mError) as e:
+            s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+        assert "UNSUPPORTED" in str(e.value)
+
+
 def test_matrices(built, tmp_path):
     """mat2/mat3 (GLSL) and mat2x2f/mat3x3<f32> (WGSL): constructors, m*v, v*m, m*m, m[i], transpose"""
     glsl = textwrap.dedent("""\
