@@ -836,6 +836,18 @@ class GlslParser : public ParserBase {
           return b.binary(it->second, args[0], args[1]);
         }
       }
+      if (args.size() == 2 && name == "modf") {  // modf(x, out whole): whole = trunc(x) (an effect of the statement), value x - trunc(x)
+        need_side_context("modf() with its out parameter");
+        if (!Builder::is_lvalue(*args[1])) b.error("second argument of modf() must be a variable");
+        ExprP whole = b.call_builtin("trunc", {args[0]});
+        side_->push_back(make_assign(args[1], whole));
+        return b.binary(Op::Sub, args[0], b.call_builtin("trunc", {args[0]}));
+      }
+      if (args.size() == 2 && name == "ldexp") {  // x * 2^e
+        ExprP e = args[1];
+        if (!e->ty.is_int()) b.error("second argument of ldexp() must be an integer");
+        return b.binary(Op::Mul, args[0], b.call_builtin("exp2", {b.construct(e->ty.with_sk(Sk::F32), false, {e})}));
+      }
       if (args.size() == 1 && name == "not") {
         if (!args[0]->ty.is_vector() || !args[0]->ty.is_bool()) b.error("not() needs a bool vector");
         return b.unary(Op::Not, args[0]);

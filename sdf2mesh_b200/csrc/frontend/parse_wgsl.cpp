@@ -669,6 +669,26 @@ class WgslParser : public ParserBase {
       std::vector<ExprP> args = parse_args();
       return b.construct(ty, infer, args);
     }
+    if (name == "modf" && is_punct("(", 1) && !functions.count(name)) {  // modf(e).fract / modf(e).whole
+      advance();
+      std::vector<ExprP> args = parse_args();
+      if (args.size() != 1) b.error("modf takes one argument");
+      expect(".");
+      const std::string m = expect_ident("fract or whole");
+      ExprP x = b.concretize(args[0]);
+      ExprP whole = b.call_builtin("trunc", {x});
+      if (m == "whole") return whole;
+      if (m == "fract") return b.binary(Op::Sub, x, whole);
+      b.error("modf() result has members fract and whole");
+    }
+    if (name == "ldexp" && is_punct("(", 1) && !functions.count(name)) {  // x * 2^e
+      advance();
+      std::vector<ExprP> args = parse_args();
+      if (args.size() != 2) b.error("ldexp takes two arguments");
+      ExprP e = b.concretize(args[1]);
+      if (!e->ty.is_int()) b.error("second argument of ldexp() must be an integer");
+      return b.binary(Op::Mul, args[0], b.call_builtin("exp2", {b.construct(e->ty.with_sk(Sk::F32), false, {e})}));
+    }
     if (name == "bitcast" && is_punct("<", 1)) {  // bitcast<T>(e): T = f32 / i32 / u32 or a vector of them
       advance();
       expect("<");

@@ -877,6 +877,23 @@ def test_glsl_side_effects_inside_expressions(built, tmp_path):
         assert "UNSUPPORTED" in str(e.value)
 
 
+def test_modf_and_ldexp(built, tmp_path):
+    """GLSL modf(x, out whole) / WGSL modf(x).fract|.whole (whole = trunc(x)), ldexp(x, e) = x * 2^e"""
+    frag = tmp_path / "modf.frag"
+    frag.write_text("#version 450\nfloat sdf(vec3 p) { float i; float f = modf(p.x * 3.0, i); vec3 w; vec3 g = modf(p * 2.0, w); "
+                    "return f + 10.0 * i + g.y + 100.0 * w.z + ldexp(p.y, 3) + ldexp(1.0, int(p.z)); }\nvoid main() {}\n")
+    pts = points(4.0, 300)
+    P = pts.astype(np.float64)
+    got = host_eval.eval_points(s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf").lower_to_cuda(), pts)
+    want = (P[:, 0] * 3 - np.trunc(P[:, 0] * 3)) + 10 * np.trunc(P[:, 0] * 3) + (P[:, 1] * 2 - np.trunc(P[:, 1] * 2)) + 100 * np.trunc(P[:, 2] * 2) \
+        + P[:, 1] * 8 + 2.0 ** np.trunc(P[:, 2])
+    assert np.abs(got - want).max() < 1e-4
+    wgsl = "fn sdf3d(p: vec3f) -> f32 { return modf(p.x * 3.0).fract + 10.0 * modf(p.x * 3.0).whole + modf(p * 2.0).fract.y + ldexp(p.y, 3); }"
+    got = host_eval.eval_points(s2m.Sdf3DShader.from_source(wgsl).lower_to_cuda(), pts)
+    want = (P[:, 0] * 3 - np.trunc(P[:, 0] * 3)) + 10 * np.trunc(P[:, 0] * 3) + (P[:, 1] * 2 - np.trunc(P[:, 1] * 2)) + P[:, 1] * 8
+    assert np.abs(got - want).max() < 1e-4
+
+
 def test_matrices(built, tmp_path):
     """mat2/mat3 (GLSL) and mat2x2f/mat3x3<f32> (WGSL): constructors, m*v, v*m, m*m, m[i], transpose"""
     glsl = textwrap.dedent("""\
