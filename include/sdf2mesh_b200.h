@@ -78,6 +78,10 @@ int s2m_shader_write_to_file(const s2m_shader* s, const char* path);
 const char* s2m_shader_log(const s2m_shader* s);
 /* lower to CUDA C++ without compiling (returns malloc'd text; S2M_ERR_PARSE/VALIDATION/MISSING_SDF) */
 int s2m_shader_lower_to_cuda(const s2m_shader* s, char** cuda_out);
+/* the same code over packed f32x2 pairs (two evaluations per call, sm_100a FFMA2; csrc/s2m_pvec.h): what K1
+ * compiles next to the scalar form.  An empty string if the shader uses something the packed types do not
+ * cover (matrices) -- K1 then evaluates one corner at a time. */
+int s2m_shader_lower_to_cuda_packed(const s2m_shader* s, char** cuda_out);
 void s2m_shader_free(s2m_shader* s);
 
 /* WGSL text munging used by the GLSL / ShaderToy path (shadertoy.rs:169-352); results malloc'd. */

@@ -92,6 +92,7 @@ SYMBOLS = {
     "s2m_shader_write_to_file": (ctypes.c_int, [_P, _S]),
     "s2m_shader_log": (_S, [_P]),
     "s2m_shader_lower_to_cuda": (ctypes.c_int, [_P, _PP]),
+    "s2m_shader_lower_to_cuda_packed": (ctypes.c_int, [_P, _PP]),
     "s2m_shader_free": (None, [_P]),
     "s2m_glsl_to_wgsl": (ctypes.c_int, [_S, _PP]),
     "s2m_wgsl_remove_function": (ctypes.c_int, [_S, _S, _PP]),

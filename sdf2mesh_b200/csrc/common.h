@@ -16,6 +16,7 @@ int fail(int status, const std::string& msg);
 extern const char* const kSrcMathH;
 extern const char* const kSrcVecH;
 extern const char* const kSrcSdfLibH;
+extern const char* const kSrcPvecH;
 extern const char* const kSrcScanCuh;
 extern const char* const kSrcKernelsJit;
 
@@ -35,5 +36,5 @@ struct s2m_shader {
 
 namespace s2m_frontend {
 // Lower an assembled shader to CUDA C++ (the body of namespace s2m_user).  Returns s2m_status.
-int lower_to_cuda(const s2m_shader& sh, std::string* cuda, std::string* err);
+int lower_to_cuda(const s2m_shader& sh, std::string* cuda, std::string* err, std::string* packed);
 }

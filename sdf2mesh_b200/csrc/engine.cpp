@@ -259,6 +259,8 @@ extern "C" int s2m_ctx_device_info(const s2m_ctx* c, char* name, size_t name_len
 }
 
 // ------------------------------------------------------------------ module
+constexpr bool kK1PackedDefault = true;  // see s2m_pvec.h; S2M_K1_PACKED=0/1 overrides
+constexpr int kK1PackedMinScore = 4;     // transcendental calls in the SDF (mandelmesh.frag: 7; the .sdf3d examples: 0)
 constexpr unsigned kK1RowsDefault = 2;  // measured: mandelbulb K1 -0.6 %, torus K1 -7 %; +10-20 % NVRTC time
 
 struct s2m_module {
@@ -268,6 +270,7 @@ struct s2m_module {
   CUfunction_t k1 = nullptr, k4 = nullptr, k_eval = nullptr, k_probe = nullptr;
   s2m_ctx* ctx = nullptr;
   unsigned k1_rows = 1;  // grid rows per K1 thread (S2M_K1_ROWS the kernels were compiled with)
+  bool k1_packed = false;  // K1 evaluates corner pairs in f32x2 arithmetic (s2m_pvec.h)
   double ms_frontend = 0, ms_nvrtc = 0, ms_load = 0;
 };
 
@@ -278,22 +281,41 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   std::unique_ptr<s2m_module> m(new s2m_module());
   m->ctx = ctx;
   double t0 = now_ms();
-  std::string user, err;
+  std::string user, user_packed, err;
   if (shader->kind == S2M_SRC_CUDA) {
     user = shader->source;
   } else {
-    int st = s2m_frontend::lower_to_cuda(*shader, &user, &err);
+    int st = s2m_frontend::lower_to_cuda(*shader, &user, &err, &user_packed);
     if (st != S2M_OK) return fail(st, err);
   }
   double t1 = now_ms();
   m->ms_frontend = t1 - t0;
+  // K1 evaluates two corners per call in packed f32x2 arithmetic (s2m_pvec.h) when the front-end
+  // could express the shader over pairs; S2M_K1_PACKED=0 keeps the one-corner-at-a-time kernel.
+  // Default: only when the SDF is dominated by transcendental functions (their polynomials are what
+  // f32x2 halves; IEEE sqrt / division sequences stay per lane), judged by the front-end's count.
+  if (const char* e = getenv("S2M_K1_PACKED")) {
+    if (atoi(e) == 0) user_packed.clear();
+  } else {
+    int score = 0;
+    const size_t at = user_packed.find("// s2m-packed-score: ");
+    if (at != std::string::npos) score = atoi(user_packed.c_str() + at + 21);
+    if (!kK1PackedDefault || score < kK1PackedMinScore) user_packed.clear();
+  }
+  nvrtcResult r = NVRTC_SUCCESS;
+  std::string packed_log;
+  for (int attempt = 0; attempt < 2; ++attempt) {  // second attempt: without the packed form, should NVRTC reject it
+  m->k1_packed = !user_packed.empty();
   m->cuda_source = std::string("#include \"s2m_sdf3d_lib.h\"\n#include \"s2m_scan.cuh\"\n") +
-                   "namespace s2m_user {\nusing namespace s2m;\n" + user + "\n}  // namespace s2m_user\n" +
-                   "#include \"kernels_jit.cuh\"\n";
+                   "namespace s2m_user {\nusing namespace s2m;\n" + user + "\n}  // namespace s2m_user\n";
+  if (m->k1_packed)
+    m->cuda_source += "#include \"s2m_pvec.h\"\n#define S2M_K1_PACKED 1\nnamespace s2m_user_p {\nusing namespace s2m;\n" + user_packed +
+                      "\n}  // namespace s2m_user_p\n";
+  m->cuda_source += "#include \"kernels_jit.cuh\"\n";
   nvrtcProgram prog = nullptr;
-  const char* hdr_src[] = {kSrcMathH, kSrcVecH, kSrcSdfLibH, kSrcScanCuh, kSrcKernelsJit};
-  const char* hdr_name[] = {"s2m_math.h", "s2m_vec.h", "s2m_sdf3d_lib.h", "s2m_scan.cuh", "kernels_jit.cuh"};
-  nvrtcResult r = nvrtcCreateProgram(&prog, m->cuda_source.c_str(), "sdf_module.cu", 5, hdr_src, hdr_name);
+  const char* hdr_src[] = {kSrcMathH, kSrcVecH, kSrcSdfLibH, kSrcPvecH, kSrcScanCuh, kSrcKernelsJit};
+  const char* hdr_name[] = {"s2m_math.h", "s2m_vec.h", "s2m_sdf3d_lib.h", "s2m_pvec.h", "s2m_scan.cuh", "kernels_jit.cuh"};
+  r = nvrtcCreateProgram(&prog, m->cuda_source.c_str(), "sdf_module.cu", 6, hdr_src, hdr_name);
   if (r != NVRTC_SUCCESS) return fail(S2M_ERR_NVRTC, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r));
   std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   opts.push_back((flags & S2M_COMPILE_ALLOW_FMA) ? "--fmad=true" : "--fmad=false");
@@ -315,6 +337,7 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   // generated translation unit, the embedded headers, the options and the NVRTC version.  A serving
   // process that sees the same SDF again skips the ~0.5 s compile.
   std::string cache_path;
+  m->cubin.clear();
   if (const char* dir = getenv("S2M_CACHE_DIR")) {
     if (*dir) {
       int nv_major = 0, nv_minor = 0;
@@ -352,6 +375,12 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   if (r != NVRTC_SUCCESS) {
     std::string msg = std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + m->log;
     nvrtcDestroyProgram(&prog);
+    if (m->k1_packed && attempt == 0) {  // keep the diagnostics, compile the scalar kernels only
+      packed_log = "packed (f32x2) form rejected, K1 falls back to one corner per evaluation:\n" + m->log + "\n";
+      user_packed.clear();
+      m->cubin.clear();
+      continue;
+    }
     return fail(S2M_ERR_NVRTC, msg);
   }
   size_t cs = 0;
@@ -368,6 +397,9 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
     }
   }
   }  // !cache_hit
+  break;
+  }  // attempt
+  if (!packed_log.empty()) m->log = packed_log + m->log;
   double t2 = now_ms();
   m->ms_nvrtc = t2 - t1;
   if (ctx) {

@@ -10,5 +10,6 @@ void parse_wgsl(const std::string& src, const std::vector<std::string>& builtin_
 void parse_glsl(const std::string& src, Module* out);
 int optimize_module(Module& m);  // returns the number of rewrites applied
 std::string emit_cuda(const Module& m);
+std::string emit_cuda_packed(const Module& m);  // "" when the module has no packed (f32x2) form
 std::string emit_wgsl(const Module& m);
 }  // namespace s2m_frontend

@@ -44,7 +44,10 @@ __device__ __noinline__ float s2m_sdf_call(float x, float y, float z) { return s
 #define S2M_K1_ROWS 2   /* grid rows a thread evaluates (1 or 2): 2 amortises the index / class / store overhead */
 #endif
 
-__device__ __forceinline__ void s2m_k1_eval4(bool on, const float cx[4], float cy, float cz, float v[4]) {
+/* `redo`: with S2M_K1_PACKED the corners (0,1) and (2,3) are evaluated as f32x2 pairs
+ * (s2m_user_p::sdf3d2, s2m_pvec.h); bit (redo_shift + k/2) is set when the lanes of pair k disagreed on a
+ * comparison or conversion, i.e. v[k+1] is not valid and the caller evaluates that corner alone. */
+__device__ __forceinline__ void s2m_k1_eval4(bool on, const float cx[4], float cy, float cz, float v[4], unsigned& redo, unsigned redo_shift) {
   v[0] = 0.0f; v[1] = 0.0f; v[2] = 0.0f; v[3] = 0.0f;
   /* One guard per thread, not per corner: a float4 whose first corner is inside the grid is
    * evaluated whole (at most 3 corners past the last one per row, in the padding nobody reads). */
@@ -54,7 +57,17 @@ __device__ __forceinline__ void s2m_k1_eval4(bool on, const float cx[4], float c
 #else
 #pragma unroll
 #endif
+#if defined(S2M_K1_PACKED)
+    for (int k = 0; k < 4; k += 2) {
+      bool dv;
+      const s2m::pf r = s2m_user_p::sdf3d2(s2m::pmk3(s2m::pf(cx[k], cx[k + 1]), s2m::pf(cy), s2m::pf(cz)), &dv);
+      v[k] = r.lo; v[k + 1] = r.hi;
+      if (dv) redo |= 1u << (redo_shift + (unsigned)(k >> 1));
+    }
+#else
     for (int k = 0; k < 4; ++k) v[k] = s2m_sdf(cx[k], cy, cz);
+    (void)redo; (void)redo_shift;
+#endif
   }
 }
 /* corner classes of 4 values: low nibble P (value > tau), high nibble N (value < -tau) */
@@ -85,12 +98,33 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
 #pragma unroll
   for (int k = 0; k < 4; ++k) cx[k] = g.bmin[0] + g.size[0] * (float)(x4 + (unsigned)k);
   const bool in_x = x4 <= g.res[0];
-  s2m_k1_eval4(active && in_x, cx, g.bmin[1] + g.size[1] * (float)y, cz, va);
-  if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(va[0], va[1], va[2], va[3]);
+  unsigned redo = 0;
+  const float cy_a = g.bmin[1] + g.size[1] * (float)y;
+  s2m_k1_eval4(active && in_x, cx, cy_a, cz, va, redo, 0u);
 #if S2M_K1_ROWS == 2
   const bool active_b = active && y + 1u < g.rows;
+  const float cy_b = g.bmin[1] + g.size[1] * (float)(y + 1u);
   float vb[4];
-  s2m_k1_eval4(active_b && in_x, cx, g.bmin[1] + g.size[1] * (float)(y + 1u), cz, vb);
+  s2m_k1_eval4(active_b && in_x, cx, cy_b, cz, vb, redo, 2u);
+#endif
+#if defined(S2M_K1_PACKED)
+  /* Rare (0.3 % of the mandelbulb's pairs at 2048^3): the two lanes of a pair took different paths.
+   * Lane lo is always right; the hi corner is evaluated again on its own, all such corners of the
+   * thread in one loop so that a warp pays max-over-lanes evaluations, not one per call site. */
+  while (redo) {
+    const unsigned b = (unsigned)__ffs((int)redo) - 1u;
+    redo &= redo - 1u;
+#if S2M_K1_ROWS == 2
+    const float r = s2m_sdf_call((b & 1u) ? cx[3] : cx[1], (b & 2u) ? cy_b : cy_a, cz);
+    if (b == 0u) va[1] = r; else if (b == 1u) va[3] = r; else if (b == 2u) vb[1] = r; else vb[3] = r;
+#else
+    const float r = s2m_sdf_call((b & 1u) ? cx[3] : cx[1], cy_a, cz);
+    if (b == 0u) va[1] = r; else va[3] = r;
+#endif
+  }
+#endif
+  if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(va[0], va[1], va[2], va[3]);
+#if S2M_K1_ROWS == 2
   if (active_b) *reinterpret_cast<float4*>(slab + (row + 1ull) * g.pitch_x + x4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
 #endif
   /* Corner classes for K2: P = value > +tau, N = value < -tau (NaN and the |v| <= tau band are

@@ -353,10 +353,21 @@ extern "C" int s2m_shader_lower_to_cuda(const s2m_shader* s, char** cuda_out) {
   std::string cuda, err;
   if (s->kind == S2M_SRC_CUDA) cuda = s->source;
   else {
-    int st = s2m_frontend::lower_to_cuda(*s, &cuda, &err);
+    int st = s2m_frontend::lower_to_cuda(*s, &cuda, &err, nullptr);
     if (st) return fail(st, err);
   }
   *cuda_out = dup_string(cuda);
+  return *cuda_out ? S2M_OK : fail(S2M_ERR_OOM, "malloc");
+}
+extern "C" int s2m_shader_lower_to_cuda_packed(const s2m_shader* s, char** cuda_out) {
+  if (!s || !cuda_out) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
+  *cuda_out = nullptr;
+  std::string cuda, packed, err;
+  if (s->kind != S2M_SRC_CUDA) {
+    int st = s2m_frontend::lower_to_cuda(*s, &cuda, &err, &packed);
+    if (st) return fail(st, err);
+  }
+  *cuda_out = dup_string(packed);
   return *cuda_out ? S2M_OK : fail(S2M_ERR_OOM, "malloc");
 }
 extern "C" void s2m_shader_free(s2m_shader* s) { delete s; }

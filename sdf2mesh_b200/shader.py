@@ -115,6 +115,12 @@ class Sdf3DShader:
         check(lib().s2m_shader_lower_to_cuda(self._h, ctypes.byref(out)))
         return _capi.take_string(out)
 
+    def lower_to_cuda_packed(self) -> str:
+        """the f32x2 form K1 evaluates two corners at a time with ("" if the shader has none)"""
+        out = ctypes.c_void_p()
+        check(lib().s2m_shader_lower_to_cuda_packed(self._h, ctypes.byref(out)))
+        return _capi.take_string(out)
+
     def create_shader_module(self, ctx=None, flags: int = 0):
         """shader.rs:220.  ctx=None compiles to a cubin without loading it (no GPU needed)."""
         from .engine import Module

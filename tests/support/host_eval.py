@@ -46,6 +46,54 @@ def compile_host(cuda_body: str):
     return lib
 
 
+WRAP_PACKED = r'''
+#include "s2m_pvec.h"
+namespace s2m_user_p {
+using namespace s2m;
+%s
+}
+// lane lo = point a[i], lane hi = point b[i]
+extern "C" void host_eval2(const float* a, const float* b, float* out_a, float* out_b, unsigned char* dv, unsigned long long n) {
+  for (unsigned long long i = 0; i < n; ++i) {
+    bool d = false;
+    const s2m::pf r = s2m_user_p::sdf3d2(s2m::pmk3(s2m::pf(a[3 * i], b[3 * i]), s2m::pf(a[3 * i + 1], b[3 * i + 1]), s2m::pf(a[3 * i + 2], b[3 * i + 2])), &d);
+    out_a[i] = r.lo; out_b[i] = r.hi; dv[i] = d ? 1 : 0;
+  }
+}
+'''
+
+
+def compile_host_packed(packed_body: str):
+    """the packed (f32x2) form of a shader, compiled for the host: pairs are two scalar operations there"""
+    key = "p" + hashlib.sha1(packed_body.encode()).hexdigest()
+    if key in _CACHE:
+        return _CACHE[key]
+    d = tempfile.mkdtemp(prefix="s2m_hostp_")
+    src = os.path.join(d, "sdfp.cpp")
+    so = os.path.join(d, "sdfp.so")
+    with open(src, "w") as f:
+        f.write(WRAP_PACKED % packed_body)
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-mfma", "-std=c++17", "-fPIC", "-shared",
+                           "-I", CSRC, src, "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.host_eval2.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_uint64]
+    _CACHE[key] = lib
+    return lib
+
+
+def eval_pairs(packed_body: str, pts_a, pts_b):
+    """-> (values lane lo, values lane hi, lanes-disagreed flags)"""
+    lib = compile_host_packed(packed_body)
+    a = np.ascontiguousarray(pts_a, np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(pts_b, np.float32).reshape(-1, 3)
+    assert a.shape == b.shape
+    oa = np.empty(a.shape[0], np.float32)
+    ob = np.empty(a.shape[0], np.float32)
+    dv = np.empty(a.shape[0], np.uint8)
+    lib.host_eval2(a.ctypes.data, b.ctypes.data, oa.ctypes.data, ob.ctypes.data, dv.ctypes.data, a.shape[0])
+    return oa, ob, dv.astype(bool)
+
+
 def scalar_function(cuda_body: str):
     """the compiled `float sdf3d(x, y, z)` as a ctypes function (for oracle.set_plugin); the library
     stays loaded for the life of the process"""
