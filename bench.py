@@ -332,6 +332,7 @@ def main():
         "config": {"workload": wl, "sdf": f, "resolution": res, "bounds": bounds, "mode": "faithful (slices 0..R-2)" if not (args.flags & 1) else "all slices",
                    "quad_index": "u64" if args.u64_quads else "u32 (the reference's Quad(u32, u32, u32, u32))",
                    "parallelism": f"z-slabs x{world}" + ("" if world == 1 else (" equal" if args.no_balance else (" cost-probe" if args.no_rebalance else " cost-probe + refined from warm-up step times"))), "z_boundaries": bounds_z,
+                   "k1": ("packed f32x2: two corners per evaluation (FFMA2/FMUL2)" + (", sqrt refinement packed" if os.environ.get("S2M_K1_PACKED") == "2" else "")) if module.packed else "one corner per evaluation",
                    "l2": "no L2 flush needed: the corner slab alone is %.1f GB per step, far larger than the 126 MB L2" % (k1_bytes / 1e9)},
         "mesh": {"candidates": ncand, "vertices": nv, "quads": nq, "invalid_quads": ninv, "triangles": 2 * nq, "Mtriangles_per_s": 2 * nq * args.steps / wall / 1e6},
         "e2e": {"value": e2e, "unit": "Gvoxel/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": d2h_bytes},

@@ -217,6 +217,13 @@ int s2m_read_device_words(s2m_ctx* ctx, const void* device_words, uint32_t n, ui
 
 /* diagnostics */
 int s2m_eval_points(s2m_ctx* ctx, s2m_module* m, const float* xyz, uint64_t n, float* out);
+/* 1 if K1 of this module evaluates corner pairs in packed f32x2 arithmetic (csrc/s2m_pvec.h) */
+int s2m_module_is_packed(const s2m_module* m);
+/* the packed form, raw: lane lo evaluates xyz_a[i], lane hi xyz_b[i]; disagreed[i] != 0: the lanes took
+ * different decisions and out_b[i] is not valid (K1 re-evaluates such corners on their own).
+ * S2M_ERR_UNSUPPORTED if the module has no packed form. */
+int s2m_eval_pairs(s2m_ctx* ctx, s2m_module* m, const float* xyz_a, const float* xyz_b, uint64_t n, float* out_a, float* out_b,
+                   uint8_t* disagreed);
 /* one corner plane of K1's slab: (dims[1]+1) x (dims[0]+1) floats, row-major */
 int s2m_debug_slab_plane(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, uint32_t plane, float* out);
 /* relative K1 cost of `planes` equal-thickness z bands (for balancing z-slabs across GPUs) */

@@ -117,6 +117,8 @@ SYMBOLS = {
     "s2m_result_write_stl_binary": (ctypes.c_int, [_P, _S]),
     "s2m_write_mesh_parts": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _S, ctypes.c_int]),
     "s2m_eval_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_uint64, _P]),
+    "s2m_module_is_packed": (ctypes.c_int, [_P]),
+    "s2m_eval_pairs": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P]),
     "s2m_debug_slab_plane": (ctypes.c_int, [_P, _P, ctypes.POINTER(MeshParams), ctypes.c_uint32, _P]),
     "s2m_cost_probe": (ctypes.c_int, [_P, _P, ctypes.POINTER(MeshParams), ctypes.c_uint32, _P]),
     "s2m_read_device_words": (ctypes.c_int, [_P, _P, ctypes.c_uint32, _P, _P]),

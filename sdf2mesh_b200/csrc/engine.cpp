@@ -260,6 +260,7 @@ extern "C" int s2m_ctx_device_info(const s2m_ctx* c, char* name, size_t name_len
 
 // ------------------------------------------------------------------ module
 constexpr bool kK1PackedDefault = true;  // see s2m_pvec.h; S2M_K1_PACKED=0/1 overrides
+constexpr bool kK1PackedSqrtDefault = false;
 constexpr int kK1PackedMinScore = 4;     // transcendental calls in the SDF (mandelmesh.frag: 7; the .sdf3d examples: 0)
 constexpr unsigned kK1RowsDefault = 2;  // measured: mandelbulb K1 -0.6 %, torus K1 -7 %; +10-20 % NVRTC time
 
@@ -267,7 +268,7 @@ struct s2m_module {
   std::string cuda_source, log;
   std::vector<char> cubin;
   CUmodule_t mod = nullptr;
-  CUfunction_t k1 = nullptr, k4 = nullptr, k_eval = nullptr, k_probe = nullptr;
+  CUfunction_t k1 = nullptr, k4 = nullptr, k_eval = nullptr, k_probe = nullptr, k_eval2 = nullptr;
   s2m_ctx* ctx = nullptr;
   unsigned k1_rows = 1;  // grid rows per K1 thread (S2M_K1_ROWS the kernels were compiled with)
   bool k1_packed = false;  // K1 evaluates corner pairs in f32x2 arithmetic (s2m_pvec.h)
@@ -294,8 +295,10 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   // could express the shader over pairs; S2M_K1_PACKED=0 keeps the one-corner-at-a-time kernel.
   // Default: only when the SDF is dominated by transcendental functions (their polynomials are what
   // f32x2 halves; IEEE sqrt / division sequences stay per lane), judged by the front-end's count.
+  bool packed_sqrt = kK1PackedSqrtDefault;  // S2M_K1_PACKED=1: sqrt per lane, =2: refinement step of sqrt in f32x2 as well
   if (const char* e = getenv("S2M_K1_PACKED")) {
     if (atoi(e) == 0) user_packed.clear();
+    packed_sqrt = atoi(e) >= 2;
   } else {
     int score = 0;
     const size_t at = user_packed.find("// s2m-packed-score: ");
@@ -309,7 +312,7 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   m->cuda_source = std::string("#include \"s2m_sdf3d_lib.h\"\n#include \"s2m_scan.cuh\"\n") +
                    "namespace s2m_user {\nusing namespace s2m;\n" + user + "\n}  // namespace s2m_user\n";
   if (m->k1_packed)
-    m->cuda_source += "#include \"s2m_pvec.h\"\n#define S2M_K1_PACKED 1\nnamespace s2m_user_p {\nusing namespace s2m;\n" + user_packed +
+    m->cuda_source += std::string(packed_sqrt ? "#define S2M_PACKED_SQRT 1\n" : "") + "#include \"s2m_pvec.h\"\n#define S2M_K1_PACKED 1\nnamespace s2m_user_p {\nusing namespace s2m;\n" + user_packed +
                       "\n}  // namespace s2m_user_p\n";
   m->cuda_source += "#include \"kernels_jit.cuh\"\n";
   nvrtcProgram prog = nullptr;
@@ -411,6 +414,10 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
     for (auto& f : fns) {
       cr = driver().cuModuleGetFunction(f.f, m->mod, f.n);
       if (cr) return fail(S2M_ERR_CUDA, std::string("cuModuleGetFunction(") + f.n + "): " + cu_err(cr));
+    }
+    if (m->k1_packed) {
+      cr = driver().cuModuleGetFunction(&m->k_eval2, m->mod, "s2m_k_eval2");
+      if (cr) return fail(S2M_ERR_CUDA, "cuModuleGetFunction(s2m_k_eval2): " + cu_err(cr));
     }
     m->ms_load = now_ms() - t2;
   }
@@ -1079,6 +1086,37 @@ extern "C" int s2m_eval_points(s2m_ctx* c, s2m_module* m, const float* xyz, uint
   in.release(); o.release();
   if (st) return st;
   if (e != cudaSuccess) return fail(S2M_ERR_CUDA, std::string("s2m_eval_points: ") + cudaGetErrorString(e));
+  return S2M_OK;
+}
+
+extern "C" int s2m_module_is_packed(const s2m_module* m) { return m && m->k1_packed ? 1 : 0; }
+
+extern "C" int s2m_eval_pairs(s2m_ctx* c, s2m_module* m, const float* xyz_a, const float* xyz_b, uint64_t n, float* out_a, float* out_b,
+                              uint8_t* disagreed) {
+  if (!c || !m || !xyz_a || !xyz_b || !out_a || !out_b || !disagreed) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
+  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (!m->k_eval2) return fail(S2M_ERR_UNSUPPORTED, "module has no packed (f32x2) form");
+  if (n == 0) return S2M_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  DevBuf in, o;  // in: a | b;  o: out_a | out_b | dv
+  int st;
+  if ((st = in.ensure(n * 24))) return st;
+  if ((st = o.ensure(n * 9))) { in.release(); return st; }
+  cudaStream_t s = c->stream;
+  cudaError_t e = cudaMemcpyAsync(in.p, xyz_a, n * 12, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(in.as<char>() + n * 12, xyz_b, n * 12, cudaMemcpyHostToDevice, s);
+  const float* pa = in.as<float>(); const float* pb = pa + n * 3;
+  float* oa = o.as<float>(); float* ob = oa + n; unsigned char* dv = reinterpret_cast<unsigned char*>(ob + n);
+  unsigned long long nn = n;
+  void* args[] = {&pa, &pb, &oa, &ob, &dv, &nn};
+  if (e == cudaSuccess) st = launch(m->k_eval2, dim3((unsigned)((n + 127) / 128)), dim3(128), s, args, "s2m_k_eval2");
+  if (e == cudaSuccess && !st) e = cudaMemcpyAsync(out_a, oa, n * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && !st) e = cudaMemcpyAsync(out_b, ob, n * 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && !st) e = cudaMemcpyAsync(disagreed, dv, n, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess && !st) e = cudaStreamSynchronize(s);
+  in.release(); o.release();
+  if (st) return st;
+  if (e != cudaSuccess) return fail(S2M_ERR_CUDA, std::string("s2m_eval_pairs: ") + cudaGetErrorString(e));
   return S2M_OK;
 }
 

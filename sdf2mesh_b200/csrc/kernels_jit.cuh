@@ -364,6 +364,19 @@ extern "C" __global__ void s2m_k_eval(const float* __restrict__ pts, float* __re
   if (i < n) out[i] = s2m_sdf(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
 }
 
+#if defined(S2M_K1_PACKED)
+/* the packed form on caller-supplied pairs, raw: lane lo = a[i], lane hi = b[i]; dv[i] = the lanes
+ * disagreed (out_b[i] is then not valid).  Parity tests compare this with s2m_k_eval. */
+extern "C" __global__ void s2m_k_eval2(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out_a,
+                                       float* __restrict__ out_b, unsigned char* __restrict__ dv, unsigned long long n) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool d;
+  const s2m::pf r = s2m_user_p::sdf3d2(s2m::pmk3(s2m::pf(a[3 * i], b[3 * i]), s2m::pf(a[3 * i + 1], b[3 * i + 1]), s2m::pf(a[3 * i + 2], b[3 * i + 2])), &d);
+  out_a[i] = r.lo; out_b[i] = r.hi; dv[i] = d ? 1 : 0;
+}
+#endif
+
 /* Coarse cost probe: block b evaluates a (probe x probe) lattice of plane z_b of a `planes`-plane
  * coarse grid; every warp adds the SM cycles it spent (issue time including divergence), so the
  * per-plane sums are proportional to K1's work per z-slice. */

@@ -77,6 +77,21 @@ class Module:
     def compile_ms(self):
         return tuple(lib().s2m_module_compile_ms(self._h, i) for i in range(3))
 
+    @property
+    def packed(self) -> bool:
+        """K1 of this module evaluates corner pairs in packed f32x2 arithmetic (csrc/s2m_pvec.h)"""
+        return bool(lib().s2m_module_is_packed(self._h))
+
+    def eval_pairs(self, pts_a, pts_b):
+        """the packed form, raw: -> (values of pts_a, values of pts_b, lanes-disagreed flags)"""
+        a = np.ascontiguousarray(pts_a, np.float32).reshape(-1, 3)
+        b = np.ascontiguousarray(pts_b, np.float32).reshape(-1, 3)
+        assert a.shape == b.shape
+        oa, ob = np.empty(a.shape[0], np.float32), np.empty(a.shape[0], np.float32)
+        dv = np.empty(a.shape[0], np.uint8)
+        check(lib().s2m_eval_pairs(self.ctx._h, self._h, a.ctypes.data, b.ctypes.data, a.shape[0], oa.ctypes.data, ob.ctypes.data, dv.ctypes.data))
+        return oa, ob, dv.astype(bool)
+
     def eval_points(self, pts) -> np.ndarray:
         pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
         out = np.empty(pts.shape[0], np.float32)

@@ -22,6 +22,25 @@ def built():
     return True
 
 
+@pytest.fixture(scope="session", autouse=True)
+def packed_crosscheck(built):
+    """Every shader a test lowers with Sdf3DShader.lower_to_cuda() is also lowered to its packed f32x2
+    form (csrc/s2m_pvec.h); tests.support.host_eval.eval_points then evaluates both and compares them
+    lane by lane.  So the whole front-end suite doubles as the packed emitter's suite."""
+    import sdf2mesh_b200 as s2m
+    from tests.support import host_eval
+    orig = s2m.Sdf3DShader.lower_to_cuda
+
+    def lower_and_register(self):
+        text = orig(self)
+        host_eval.register_packed(text, self.lower_to_cuda_packed())
+        return text
+
+    s2m.Sdf3DShader.lower_to_cuda = lower_and_register
+    yield
+    s2m.Sdf3DShader.lower_to_cuda = orig
+
+
 @pytest.fixture(scope="session")
 def ctx(built):
     import sdf2mesh_b200 as s2m

@@ -100,9 +100,51 @@ def scalar_function(cuda_body: str):
     return compile_host(cuda_body).host_eval1
 
 
+# scalar body -> packed body of the same shader (tests/conftest.py registers every shader a test lowers);
+# eval_points() then also runs the packed form on the same points and checks it lane by lane
+_PACKED = {}
+PACKED_STATS = {"shaders": set(), "pairs": 0, "disagreed": 0, "unpackable": set()}
+
+
+def register_packed(cuda_body: str, packed_body: str) -> None:
+    if packed_body:
+        _PACKED[cuda_body] = packed_body
+    else:
+        PACKED_STATS["unpackable"].add(hashlib.sha1(cuda_body.encode()).hexdigest())
+
+
+def _same(a, b):
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
+def check_packed(cuda_body: str, packed_body: str, pts, scalar_out) -> None:
+    """The packed (f32x2) form against the scalar form: lane lo must ALWAYS carry the scalar value of
+    its point; lane hi must carry it whenever the lanes-disagreed flag stayed clear.  Pairs: each point
+    with (i) its +x neighbour one 2048^3-voxel away, (ii) an unrelated point."""
+    lib = compile_host(cuda_body)
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)[:20000]
+    scalar_out = scalar_out[:pts.shape[0]]
+    near = pts.copy()
+    near[:, 0] += np.float32(5.0 / 2047.0)
+    far = np.roll(pts, 1, axis=0)
+    for other in (near, far):
+        other = np.ascontiguousarray(other)
+        want = np.empty(other.shape[0], np.float32)
+        lib.host_eval(other.ctypes.data, want.ctypes.data, other.shape[0])
+        lo, hi, dv = eval_pairs(packed_body, pts, other)
+        assert _same(lo, scalar_out).all(), "packed form: lane lo differs from the scalar evaluation"
+        assert _same(hi, want)[~dv].all(), "packed form: lane hi differs from the scalar evaluation although the lanes agreed"
+        PACKED_STATS["pairs"] += int(pts.shape[0])
+        PACKED_STATS["disagreed"] += int(dv.sum())
+    PACKED_STATS["shaders"].add(hashlib.sha1(cuda_body.encode()).hexdigest())
+
+
 def eval_points(cuda_body: str, pts) -> np.ndarray:
     lib = compile_host(cuda_body)
     pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
     out = np.empty(pts.shape[0], np.float32)
     lib.host_eval(pts.ctypes.data, out.ctypes.data, pts.shape[0])
+    packed = _PACKED.get(cuda_body)
+    if packed and pts.shape[0] > 0:
+        check_packed(cuda_body, packed, pts, out)
     return out

@@ -1048,3 +1048,15 @@ def test_glsl_preprocessor_conditionals(built, tmp_path):
     with pytest.raises(s2m.S2mError) as e:
         s2m.Sdf3DShader.from_glsl_fragment_shader(f, "sdf")
     assert e.value.kind == "PARSE" and "unterminated #if" in str(e.value)
+
+
+def test_packed_form_was_cross_checked(built):
+    """tests/conftest.py lowers every shader of this file to its packed f32x2 form as well, and
+    host_eval.eval_points compares the two lane by lane (lane lo always; lane hi unless the lanes
+    disagreed).  This test only makes sure that this happened for the bulk of the suite."""
+    st = host_eval.PACKED_STATS
+    print(f"packed cross-check: {len(st['shaders'])} shaders, {st['pairs']} pairs, {st['disagreed']} with disagreeing lanes, "
+          f"{len(st['unpackable'])} shaders without a packed form (matrices)")
+    assert len(st["shaders"]) >= 20
+    assert st["pairs"] > 100_000
+    assert len(st["unpackable"]) <= 10
