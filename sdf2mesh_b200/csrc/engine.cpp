@@ -260,7 +260,8 @@ extern "C" int s2m_ctx_device_info(const s2m_ctx* c, char* name, size_t name_len
 
 // ------------------------------------------------------------------ module
 constexpr bool kK1PackedDefault = true;  // see s2m_pvec.h; S2M_K1_PACKED=0/1 overrides
-constexpr bool kK1PackedSqrtDefault = false;
+constexpr bool kK1PackedSqrtDefault = true;
+constexpr int kK1PackedMaxTinySize = 64;  // expression nodes of one evaluation (torus.sdf3d: 21, p_key.sdf3d: 206)
 constexpr int kK1PackedMinScore = 4;     // transcendental calls in the SDF (mandelmesh.frag: 7; the .sdf3d examples: 0)
 constexpr unsigned kK1RowsDefault = 2;  // measured: mandelbulb K1 -0.6 %, torus K1 -7 %; +10-20 % NVRTC time
 
@@ -293,17 +294,23 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   m->ms_frontend = t1 - t0;
   // K1 evaluates two corners per call in packed f32x2 arithmetic (s2m_pvec.h) when the front-end
   // could express the shader over pairs; S2M_K1_PACKED=0 keeps the one-corner-at-a-time kernel.
-  // Default: only when the SDF is dominated by transcendental functions (their polynomials are what
-  // f32x2 halves; IEEE sqrt / division sequences stay per lane), judged by the front-end's count.
+  // Default (measured on B200, tools/k1_ab.py): packed when the SDF is dominated by transcendental
+  // functions (mandelbulb K1 41.4 -> 40.3 ms: the polynomials halve, but the kernel then waits on
+  // latency with 48-62 registers) or when it is tiny (torus K1 13.5 -> 12.3 ms); not for mid-sized
+  // primitive compositions, whose packed kernels need 75-160 registers (martin_cube 24 -> 41 ms).
+  // The front-end reports both measures in the first comment line of the packed text.
   bool packed_sqrt = kK1PackedSqrtDefault;  // S2M_K1_PACKED=1: sqrt per lane, =2: refinement step of sqrt in f32x2 as well
+  int score = 0, size = 0;
+  {
+    const size_t at = user_packed.find("// s2m-packed-score: ");
+    if (at != std::string::npos) sscanf(user_packed.c_str() + at + 21, "%d %d", &score, &size);
+  }
+  const bool heavy = score >= kK1PackedMinScore;
   if (const char* e = getenv("S2M_K1_PACKED")) {
     if (atoi(e) == 0) user_packed.clear();
-    packed_sqrt = atoi(e) >= 2;
-  } else {
-    int score = 0;
-    const size_t at = user_packed.find("// s2m-packed-score: ");
-    if (at != std::string::npos) score = atoi(user_packed.c_str() + at + 21);
-    if (!kK1PackedDefault || score < kK1PackedMinScore) user_packed.clear();
+    else packed_sqrt = atoi(e) >= 2;
+  } else if (!kK1PackedDefault || !(heavy || size <= kK1PackedMaxTinySize)) {
+    user_packed.clear();
   }
   nvrtcResult r = NVRTC_SUCCESS;
   std::string packed_log;
@@ -327,13 +334,19 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
     unroll_opt = std::string("-DS2M_K1_UNROLL=") + (atoi(e) == 1 ? "1" : "4");
     opts.push_back(unroll_opt.c_str());
   }
-  m->k1_rows = kK1RowsDefault;
+  // a packed evaluation carries twice the state: for a heavy SDF one row per thread and a 48-register
+  // cap (5 resident blocks) measured best (mandelbulb: 62 registers / 4 blocks otherwise)
+  const bool packed_heavy = !user_packed.empty() && heavy;
+  m->k1_rows = packed_heavy ? 1u : kK1RowsDefault;
   if (const char* e = getenv("S2M_K1_ROWS")) m->k1_rows = atoi(e) == 2 ? 2u : 1u;  // experiment knob
   const std::string rows_opt = "-DS2M_K1_ROWS=" + std::to_string(m->k1_rows);
   opts.push_back(rows_opt.c_str());
   std::string minb_opt;
   if (const char* e = getenv("S2M_K1_MINBLOCKS")) {  // experiment knob
     minb_opt = std::string("-DS2M_K1_MINBLOCKS=") + std::to_string(std::max(1, std::min(8, atoi(e))));
+    opts.push_back(minb_opt.c_str());
+  } else if (packed_heavy) {
+    minb_opt = "-DS2M_K1_MINBLOCKS=5";
     opts.push_back(minb_opt.c_str());
   }
   // Optional on-disk cubin cache (S2M_CACHE_DIR): keyed by everything that determines the cubin -- the

@@ -23,7 +23,7 @@ from tests.test_parity_gpu import assert_same
 pytestmark = pytest.mark.gpu
 
 # "1": sqrt per lane, "2": sqrt's refinement step in f32x2 as well (S2M_TEST_PACKED_VARIANT selects)
-VARIANT = os.environ.get("S2M_TEST_PACKED_VARIANT", "1")
+VARIANT = os.environ.get("S2M_TEST_PACKED_VARIANT", "2")
 
 PROGRAMS = ["torus", "martin_cube", "p_key", "mandelbulb", "wgsl:control_flow", "wgsl:math_mix", "glsl:integer_hash_noise"]
 
@@ -102,5 +102,6 @@ def test_packed_slab_equals_scalar_slab(ctx, name, bounds, monkeypatch):
 def test_default_policy(ctx):
     """packed by default only where it pays: SDFs dominated by transcendental functions"""
     assert load_example_shader("mandelbulb").create_shader_module(ctx).packed
-    assert not load_example_shader("torus").create_shader_module(ctx).packed
+    assert load_example_shader("torus").create_shader_module(ctx).packed          # tiny: gains as well
+    assert not load_example_shader("p_key").create_shader_module(ctx).packed
     assert not load_example_shader("martin_cube").create_shader_module(ctx).packed

@@ -6,7 +6,8 @@ Prints one JSON line per (workload, variant): K1 time with the GPU to itself (S2
 the step's device time and host wall time with the normal chunk pipeline, and the mesh counts
 (which must not depend on the variant).
 
-usage: python tools/k1_ab.py [workload:variants ...]   e.g.  mandelmesh2048:0,1,2 torus2048:0,2
+usage: python tools/k1_ab.py [workload:variants[:ENV=VAL,ENV=VAL] ...]
+       e.g.  mandelmesh2048:0,1,2 torus2048:0,2 mandelmesh2048:1:S2M_K1_MINBLOCKS=5,S2M_K1_ROWS=1
 """
 import json
 import os
@@ -46,11 +47,18 @@ def main():
     specs = sys.argv[1:] or ["mandelmesh2048:0,1,2", "torus2048:0,1,2", "martin_cube1024:0,2", "p_key1024:0,2"]
     ctx = s2m.Context(0)
     for spec in specs:
-        wl, variants = spec.split(":")
+        wl, variants, *extra = spec.split(":")
+        knobs = dict(kv.split("=") for kv in extra[0].split(",")) if extra else {}
+        for k in ("S2M_K1_MINBLOCKS", "S2M_K1_ROWS", "S2M_K1_UNROLL", "S2M_K1_BLOCK"):
+            os.environ.pop(k, None)
+        os.environ.update(knobs)
         f, res, bounds = W[wl]
         params, _ = s2m.params_from_cli(res, bounds, flags=s2m.MESH_QUADS_U32)
         for v in variants.split(","):
-            os.environ["S2M_K1_PACKED"] = v
+            if v == "d":  # the engine's default policy
+                os.environ.pop("S2M_K1_PACKED", None)
+            else:
+                os.environ["S2M_K1_PACKED"] = v
             t0 = time.perf_counter()
             mod = shader(f).create_shader_module(ctx)
             jit = (time.perf_counter() - t0) * 1e3
@@ -59,7 +67,7 @@ def main():
             alone = run(ctx, mod, params, 2)
             del os.environ["S2M_NO_CHUNK_OVERLAP"]
             piped = run(ctx, mod, params, 4)
-            print(json.dumps({"workload": wl, "S2M_K1_PACKED": int(v), "packed": mod.packed, "jit_ms": round(jit, 1),
+            print(json.dumps({"workload": wl, "S2M_K1_PACKED": v, "knobs": knobs, "packed": mod.packed, "jit_ms": round(jit, 1),
                               "k1_alone_ms": round(alone["k1_slab_ms"], 3), "k4a_alone_ms": round(alone["k4_vertices_ms"], 3),
                               "device_alone_ms": round(alone["device_ms"], 3),
                               "device_ms": round(piped["device_ms"], 3), "wall_ms": round(piped["wall_ms"], 3),
