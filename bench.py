@@ -146,8 +146,8 @@ def run_reference_arm(args, wl):
 # default 4 GiB slab budget) from the ncu --set full capture summarised in profiles/r01c_k1_2048_full.md.
 # Algorithmic bytes of that launch: 229 * 2049^2 * 4 B = 3.846 GB of corner values (+ 0.244 GB of
 # corner-class planes that save K2 from re-reading the slab) -> no wasted DRAM traffic.
-K1_TRAFFIC = {"mandelmesh2048": {"bytes_per_launch": 4.0910e9, "algorithmic_bytes_per_launch": 3.8457e9, "launches_per_step": 9,
-                                 "source": "profiles/r01c_k1_2048_full.md"}}
+K1_TRAFFIC = {"mandelmesh2048": {"bytes_per_launch": 4.1174e9, "algorithmic_bytes_per_launch": 3.8457e9, "launches_per_step": 9,
+                                 "source": "profiles/r01g_ncu_k1_packed_vs_scalar.md"}}
 
 
 def main():
@@ -332,7 +332,7 @@ def main():
         "config": {"workload": wl, "sdf": f, "resolution": res, "bounds": bounds, "mode": "faithful (slices 0..R-2)" if not (args.flags & 1) else "all slices",
                    "quad_index": "u64" if args.u64_quads else "u32 (the reference's Quad(u32, u32, u32, u32))",
                    "parallelism": f"z-slabs x{world}" + ("" if world == 1 else (" equal" if args.no_balance else (" cost-probe" if args.no_rebalance else " cost-probe + refined from warm-up step times"))), "z_boundaries": bounds_z,
-                   "k1": ("packed f32x2: two corners per evaluation (FFMA2/FMUL2)" + (", sqrt refinement packed" if os.environ.get("S2M_K1_PACKED") == "2" else "")) if module.packed else "one corner per evaluation",
+                   "k1": "packed f32x2: two corners per evaluation (FFMA2/FMUL2)" if module.packed else "one corner per evaluation",
                    "l2": "no L2 flush needed: the corner slab alone is %.1f GB per step, far larger than the 126 MB L2" % (k1_bytes / 1e9)},
         "mesh": {"candidates": ncand, "vertices": nv, "quads": nq, "invalid_quads": ninv, "triangles": 2 * nq, "Mtriangles_per_s": 2 * nq * args.steps / wall / 1e6},
         "e2e": {"value": e2e, "unit": "Gvoxel/s", "h2d_bytes_per_step": 64, "d2h_bytes_per_step": d2h_bytes},
@@ -342,7 +342,7 @@ def main():
         "jit_ms": jit_ms,
         "roofline": {"kernel": "s2m_k1_slab", "bound": "hbm", "achieved": k1_bytes / k1_s / 1e9 if k1_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                      "frac": (k1_bytes / k1_s / 1e9 / hbm_peak) if k1_s > 0 else None, "traffic": K1_TRAFFIC[wl]["bytes_per_launch"] if traffic_known else None, "traffic_detail": K1_TRAFFIC[wl] if traffic_known else None, "peak_source": peak_src,
-                     "note": "K1 is FP32/issue bound for this SDF, not HBM bound (ncu: issue slots ~96 % busy, DRAM ~6 %); see fp32. "
+                     "note": "K1 is FP32/issue bound for this SDF, not HBM bound (ncu: issue slots 83 % busy, FMA pipe 56 %, ALU pipe 51 %, DRAM 8 %); see fp32. "
                              "achieved = 4 B per corner written (SURVEY 8d) / K1 time with the GPU to itself (kernels_serialized; "
                              "in the timed steps K1 shares the machine with the previous chunk's K3/K4a/K4b, see kernels)",
                      "fp32": {"achieved_tflops_source_level": flops / k1_s / 1e12 if k1_s > 0 else None, "peak_tflops_nominal": fp32_peak,
