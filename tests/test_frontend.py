@@ -1050,6 +1050,75 @@ def test_glsl_preprocessor_conditionals(built, tmp_path):
     assert e.value.kind == "PARSE" and "unterminated #if" in str(e.value)
 
 
+def test_packed_lane_uniformity_analysis(built, tmp_path):
+    """The packed emitter keeps values that cannot differ between the two lanes as plain floats.  The
+    cases that decide a variable's kind: assignment of a varying value, by-reference parameters (one object
+    behind two names), module-scope state, aggregates (always pairs), float -> int conversions and bit casts
+    (lanes must agree).  The analysis is monovariant: a function has ONE signature, so a parameter is a
+    pair as soon as one call site passes a varying value (helpers used only with constants stay scalar)."""
+    src = textwrap.dedent("""\
+        struct Acc { sum: f32, n: i32, }
+        var<private> seen: f32;
+        fn scale(v: f32, k: f32) -> f32 { return v * k + 0.125; }            // v: varying at its call site, k: uniform
+        fn scale_u(v: f32, k: f32) -> f32 { return v * k + 0.125; }          // only ever called with uniform values
+        fn bump(a: ptr<function, f32>, by: f32) { *a = *a + by; seen = seen + by; }
+        fn bump_u(a: ptr<function, f32>, by: f32) { *a = *a + by; seen = seen + by; }
+        fn sdf3d(p: vec3f) -> f32 {
+            var gain = 2.0;                       // uniform all the way
+            gain = scale_u(gain, 1.5);
+            var u = 0.5;                          // starts uniform, becomes varying through the pointer
+            bump(&u, p.x);
+            var w = 0.25;                         // stays uniform: its function only sees uniform values
+            bump_u(&w, gain);
+            var acc: Acc;
+            acc.sum = scale(p.y, gain);
+            acc.n = i32(floor(p.z * 3.0));        // varying float -> int
+            var t = vec3f(gain, w, 1.0);          // uniform vector ...
+            t.y = t.y + p.z;                      // ... until a component becomes varying
+            let bits = bitcast<u32>(p.x) >> 31u;  // sign bit: lanes must agree
+            var r = length(p + t) - u + acc.sum * 0.01 + f32(acc.n) * 0.001 + seen * 0.5 + f32(bits);
+            if (w > 3.0) { r = r + 1.0; }         // comparison of uniform values
+            return r;
+        }""")
+    sh = s2m.Sdf3DShader.from_source(src)
+    packed = sh.lower_to_cuda_packed()
+    assert "float u_gain" in packed and "float u_w" in packed          # never varying
+    assert "pf u_u" in packed and "pvec3 u_t" in packed                # became varying
+    assert "pf u_scale(S2mState& G, pf u_v, float u_k)" in packed
+    assert "float u_scale_u(S2mState& G, float u_v, float u_k)" in packed
+    assert "void u_bump(S2mState& G, pf& u_a, pf u_by)" in packed and "void u_bump_u(S2mState& G, float& u_a, float u_by)" in packed
+    assert "pf u_seen;" in packed                                        # module-scope state written with a varying value
+    assert "p_f2int(G," in packed and "p_bits_u(G," in packed
+    assert "((u_w_" in packed and ") > (3.0f))" in packed               # plain comparison, no lane check
+    pts = points(4.0, 20_000)
+
+    def ref(p):
+        f = np.float32
+        gain = f(f(f(2.0) * f(1.5)) + f(0.125))
+        u = f(f(0.5) + p[0]); seen = p[0]
+        w = f(f(0.25) + gain); seen = f(seen + gain)
+        acc_sum = f(f(p[1] * gain) + f(0.125))
+        n = int(np.floor(f(p[2] * f(3.0))))
+        t = np.array([gain, f(w + p[2]), f(1.0)], f)
+        q = (p + t).astype(f)
+        ln = f(np.sqrt(f(f(f(q[0] * q[0]) + f(q[1] * q[1])) + f(q[2] * q[2]))))
+        bits = 1.0 if np.signbit(p[0]) else 0.0
+        r = f(f(f(f(f(ln - u) + f(acc_sum * f(0.01))) + f(f(n) * f(0.001))) + f(seen * f(0.5))) + f(bits))
+        return f(r + f(1.0)) if w > 3.0 else r
+
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)   # (also runs the packed form on the same points)
+    want = np.array([ref(p) for p in pts], np.float32)
+    assert f32_equal(got, want).all()
+    a, b = pts, np.roll(pts, 1, axis=0)
+    lo, hi, dv = host_eval.eval_pairs(packed, a, b)
+    assert f32_equal(lo, want).all()
+    assert (f32_equal(hi, np.roll(want, 1)) | dv).all()
+    # the lanes disagree exactly when floor(3z) differs or the bit patterns of x differ (the bit cast itself
+    # is where a float turns into an integer; that only its sign bit is used afterwards is not seen)
+    expect_dv = (np.floor(a[:, 2] * np.float32(3)) != np.floor(b[:, 2] * np.float32(3))) | (a[:, 0].view(np.uint32) != b[:, 0].view(np.uint32))
+    assert np.array_equal(dv, expect_dv)
+
+
 def test_packed_form_was_cross_checked(built):
     """tests/conftest.py lowers every shader of this file to its packed f32x2 form as well, and
     host_eval.eval_points compares the two lane by lane (lane lo always; lane hi unless the lanes
