@@ -321,6 +321,7 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   if (m->k1_packed)
     m->cuda_source += std::string(packed_sqrt ? "#define S2M_PACKED_SQRT 1\n" : "") + "#include \"s2m_pvec.h\"\n#define S2M_K1_PACKED 1\nnamespace s2m_user_p {\nusing namespace s2m;\n" + user_packed +
                       "\n}  // namespace s2m_user_p\n";
+  if (m->k1_packed && getenv("S2M_TEST_BREAK_PACKED")) m->cuda_source += "#error packed form rejected on request (S2M_TEST_BREAK_PACKED)\n";  // tests the retry below
   m->cuda_source += "#include \"kernels_jit.cuh\"\n";
   nvrtcProgram prog = nullptr;
   const char* hdr_src[] = {kSrcMathH, kSrcVecH, kSrcSdfLibH, kSrcPvecH, kSrcScanCuh, kSrcKernelsJit};

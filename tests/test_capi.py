@@ -100,3 +100,25 @@ def test_cubin_cache(built, tmp_path, monkeypatch):
     for s in (src, src.replace("0.75", "0.5")):
         assert s2m.Sdf3DShader.from_source(s).create_shader_module(None).cubin_size > 1000
     assert f.read_bytes()[:4] == b"\x7fELF"
+
+
+def test_packed_k1_policy_and_fallback(built, monkeypatch):
+    """K1 in packed f32x2 arithmetic (csrc/s2m_pvec.h) is a per-module decision: default policy, the
+    S2M_K1_PACKED override, shaders without a packed form, and -- if NVRTC rejects the packed translation
+    unit -- a second compile without it instead of an error."""
+    from tests.conftest import load_example_shader
+    monkeypatch.delenv("S2M_K1_PACKED", raising=False)
+    assert load_example_shader("mandelbulb").create_shader_module(None).packed      # 7 transcendental calls
+    assert load_example_shader("torus").create_shader_module(None).packed           # tiny
+    assert not load_example_shader("p_key").create_shader_module(None).packed
+    monkeypatch.setenv("S2M_K1_PACKED", "0")
+    assert not load_example_shader("mandelbulb").create_shader_module(None).packed
+    monkeypatch.setenv("S2M_K1_PACKED", "1")
+    m = load_example_shader("p_key").create_shader_module(None)
+    assert m.packed and "namespace s2m_user_p" in m.cuda_source and "S2M_PACKED_SQRT" not in m.cuda_source
+    mat = s2m.Sdf3DShader.from_source("fn sdf3d(p: vec3f) -> f32 { let m = mat2x2f(0.0, 1.0, -1.0, 0.0); return length(m * p.xy) - 1.0; }")
+    assert mat.lower_to_cuda_packed() == "" and not mat.create_shader_module(None).packed   # matrices: no packed form
+    monkeypatch.setenv("S2M_TEST_BREAK_PACKED", "1")
+    m = load_example_shader("torus").create_shader_module(None)
+    assert not m.packed and m.cubin_size > 0
+    assert "packed (f32x2) form rejected" in m.log and "S2M_TEST_BREAK_PACKED" in m.log
