@@ -122,3 +122,25 @@ def test_packed_k1_policy_and_fallback(built, monkeypatch):
     m = load_example_shader("torus").create_shader_module(None)
     assert not m.packed and m.cubin_size > 0
     assert "packed (f32x2) form rejected" in m.log and "S2M_TEST_BREAK_PACKED" in m.log
+
+
+def test_rust_binding_declares_the_same_abi():
+    """bindings/rust/ cannot be compiled here (no rustc); at least its extern block must name exactly the
+    header's functions, and its constants must carry the header's values"""
+    ffi = open(os.path.join(ROOT, "bindings", "rust", "sdf2mesh-b200", "src", "ffi.rs")).read()
+    assert sorted(set(re.findall(r"pub fn (s2m_[a-z0-9_]+)\(", ffi))) == header_functions()
+    hdr = open(os.path.join(ROOT, "include", "sdf2mesh_b200.h")).read()
+    consts = dict(re.findall(r"pub const (S2M_[A-Z0-9_]+): (?:c_int|u32) = (\d+);", ffi))
+    assert len(consts) >= 25
+    for name, value in consts.items():
+        m = re.search(r"\b%s\s*=\s*(\d+)" % name, hdr) or re.search(r"#define\s+%s\s+(\d+)u" % name, hdr)
+        assert m, f"{name} is not in the header"
+        assert m.group(1) == value, f"{name}: Rust says {value}, header says {m.group(1)}"
+    # struct fields in header order
+    for struct in ("s2m_mesh_params", "s2m_timings", "s2m_result_info"):
+        body_c = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, re.S).group(1)
+        body_c = re.sub(r"/\*.*?\*/", "", body_c, flags=re.S)
+        fields_c = [f for decl in body_c.split(";") for f in re.findall(r"\*?\s*([a-z_0-9]+)(?:\[\d+\])?\s*(?:,|$)", decl.strip().split(" ", 1)[-1] if decl.strip() else "")]
+        body_r = re.search(r"pub struct %s \{(.*?)\n\}" % struct, ffi, re.S).group(1)
+        fields_r = re.findall(r"pub ([a-z_0-9]+):", body_r)
+        assert fields_r == [f for f in fields_c if f], f"{struct}: {fields_r} vs {fields_c}"
