@@ -276,80 +276,74 @@ struct s2m_module {
   double ms_frontend = 0, ms_nvrtc = 0, ms_load = 0;
 };
 
-extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32_t flags, s2m_module** out) {
-  using namespace s2m_internal;
-  if (!shader || !out) return fail(S2M_ERR_INVALID_ARG, "s2m_module_compile: NULL argument");
-  *out = nullptr;
-  std::unique_ptr<s2m_module> m(new s2m_module());
-  m->ctx = ctx;
-  double t0 = now_ms();
-  std::string user, user_packed, err;
-  if (shader->kind == S2M_SRC_CUDA) {
-    user = shader->source;
-  } else {
-    int st = s2m_frontend::lower_to_cuda(*shader, &user, &err, &user_packed);
-    if (st != S2M_OK) return fail(st, err);
-  }
-  double t1 = now_ms();
-  m->ms_frontend = t1 - t0;
-  // K1 evaluates two corners per call in packed f32x2 arithmetic (s2m_pvec.h) when the front-end
-  // could express the shader over pairs; S2M_K1_PACKED=0 keeps the one-corner-at-a-time kernel.
-  // Default (measured on B200, tools/k1_ab.py): packed when the SDF is dominated by transcendental
-  // functions (mandelbulb K1 41.4 -> 40.3 ms: the polynomials halve, but the kernel then waits on
-  // latency with 48-62 registers) or when it is tiny (torus K1 13.5 -> 12.3 ms); not for mid-sized
-  // primitive compositions, whose packed kernels need 75-160 registers (martin_cube 24 -> 41 ms).
-  // The front-end reports both measures in the first comment line of the packed text.
-  bool packed_sqrt = kK1PackedSqrtDefault;  // S2M_K1_PACKED=1: sqrt per lane, =2: refinement step of sqrt in f32x2 as well
+namespace {
+
+// How K1 evaluates the SDF.  `packed_text` is the front-end's packed (f32x2)
+// translation, empty for "one corner per evaluation".
+struct K1Plan {
+  std::string packed_text;
+  bool packed_sqrt = kK1PackedSqrtDefault;  // the refinement step of sqrt in f32x2 as well (S2M_K1_PACKED=2)
+  bool heavy = false;                       // >= kK1PackedMinScore transcendental calls
+  bool packed() const { return !packed_text.empty(); }
+};
+
+// Default (measured on B200, tools/k1_ab.py): packed when the SDF is dominated by transcendental
+// functions (mandelbulb K1 41.4 -> 40.3 ms: the polynomials halve, but the kernel then waits on
+// latency with 48-62 registers) or when it is tiny (torus K1 13.5 -> 12.3 ms); not for mid-sized
+// primitive compositions, whose packed kernels need 75-160 registers (martin_cube 24 -> 41 ms).
+// The front-end reports both measures in the first comment line of the packed text.
+// S2M_K1_PACKED=0 / 1 / 2 overrides: scalar / pairs / pairs + packed sqrt.
+K1Plan plan_k1(std::string packed_text) {
+  K1Plan plan;
   int score = 0, size = 0;
-  {
-    const size_t at = user_packed.find("// s2m-packed-score: ");
-    if (at != std::string::npos) sscanf(user_packed.c_str() + at + 21, "%d %d", &score, &size);
-  }
-  const bool heavy = score >= kK1PackedMinScore;
+  const size_t at = packed_text.find("// s2m-packed-score: ");
+  if (at != std::string::npos) sscanf(packed_text.c_str() + at + 21, "%d %d", &score, &size);
+  plan.heavy = score >= kK1PackedMinScore;
+  bool use = kK1PackedDefault && (plan.heavy || size <= kK1PackedMaxTinySize);
   if (const char* e = getenv("S2M_K1_PACKED")) {
-    if (atoi(e) == 0) user_packed.clear();
-    else packed_sqrt = atoi(e) >= 2;
-  } else if (!kK1PackedDefault || !(heavy || size <= kK1PackedMaxTinySize)) {
-    user_packed.clear();
+    use = atoi(e) != 0;
+    if (use) plan.packed_sqrt = atoi(e) >= 2;
   }
-  nvrtcResult r = NVRTC_SUCCESS;
-  std::string packed_log;
-  for (int attempt = 0; attempt < 2; ++attempt) {  // second attempt: without the packed form, should NVRTC reject it
-  m->k1_packed = !user_packed.empty();
+  if (use) plan.packed_text = std::move(packed_text);
+  return plan;
+}
+
+// Translation unit + options -> cubin in m->cubin (from S2M_CACHE_DIR when it is there).  Returns S2M_OK or
+// S2M_ERR_NVRTC with the compiler's message in *error (m->log holds the NVRTC log either way).
+int build_cubin(s2m_module* m, const std::string& user, const K1Plan& plan, uint32_t flags, std::string* error) {
+  using namespace s2m_internal;
+  m->k1_packed = plan.packed();
   m->cuda_source = std::string("#include \"s2m_sdf3d_lib.h\"\n#include \"s2m_scan.cuh\"\n") +
                    "namespace s2m_user {\nusing namespace s2m;\n" + user + "\n}  // namespace s2m_user\n";
-  if (m->k1_packed)
-    m->cuda_source += std::string(packed_sqrt ? "#define S2M_PACKED_SQRT 1\n" : "") + "#include \"s2m_pvec.h\"\n#define S2M_K1_PACKED 1\nnamespace s2m_user_p {\nusing namespace s2m;\n" + user_packed +
+  if (plan.packed()) {
+    m->cuda_source += std::string(plan.packed_sqrt ? "#define S2M_PACKED_SQRT 1\n" : "") +
+                      "#include \"s2m_pvec.h\"\n#define S2M_K1_PACKED 1\nnamespace s2m_user_p {\nusing namespace s2m;\n" + plan.packed_text +
                       "\n}  // namespace s2m_user_p\n";
-  if (m->k1_packed && getenv("S2M_TEST_BREAK_PACKED")) m->cuda_source += "#error packed form rejected on request (S2M_TEST_BREAK_PACKED)\n";  // tests the retry below
-  m->cuda_source += "#include \"kernels_jit.cuh\"\n";
-  nvrtcProgram prog = nullptr;
-  const char* hdr_src[] = {kSrcMathH, kSrcVecH, kSrcSdfLibH, kSrcPvecH, kSrcScanCuh, kSrcKernelsJit};
-  const char* hdr_name[] = {"s2m_math.h", "s2m_vec.h", "s2m_sdf3d_lib.h", "s2m_pvec.h", "s2m_scan.cuh", "kernels_jit.cuh"};
-  r = nvrtcCreateProgram(&prog, m->cuda_source.c_str(), "sdf_module.cu", 6, hdr_src, hdr_name);
-  if (r != NVRTC_SUCCESS) return fail(S2M_ERR_NVRTC, std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r));
-  std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
-  opts.push_back((flags & S2M_COMPILE_ALLOW_FMA) ? "--fmad=true" : "--fmad=false");
-  std::string unroll_opt;
-  if (const char* e = getenv("S2M_K1_UNROLL")) {  // experiment knob, see kernels_jit.cuh
-    unroll_opt = std::string("-DS2M_K1_UNROLL=") + (atoi(e) == 1 ? "1" : "4");
-    opts.push_back(unroll_opt.c_str());
+    if (getenv("S2M_TEST_BREAK_PACKED"))  // lets tests/test_capi.py exercise the fallback in s2m_module_compile
+      m->cuda_source += "#error packed form rejected on request (S2M_TEST_BREAK_PACKED)\n";
   }
+  m->cuda_source += "#include \"kernels_jit.cuh\"\n";
+
+  std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
+                                   (flags & S2M_COMPILE_ALLOW_FMA) ? "--fmad=true" : "--fmad=false"};
+  if (const char* e = getenv("S2M_K1_UNROLL"))  // experiment knob, see kernels_jit.cuh
+    opts.push_back(std::string("-DS2M_K1_UNROLL=") + (atoi(e) == 1 ? "1" : "4"));
   // a packed evaluation carries twice the state: for a heavy SDF one row per thread and a 48-register
   // cap (5 resident blocks) measured best (mandelbulb: 62 registers / 4 blocks otherwise)
-  const bool packed_heavy = !user_packed.empty() && heavy;
+  const bool packed_heavy = plan.packed() && plan.heavy;
   m->k1_rows = packed_heavy ? 1u : kK1RowsDefault;
   if (const char* e = getenv("S2M_K1_ROWS")) m->k1_rows = atoi(e) == 2 ? 2u : 1u;  // experiment knob
-  const std::string rows_opt = "-DS2M_K1_ROWS=" + std::to_string(m->k1_rows);
-  opts.push_back(rows_opt.c_str());
-  std::string minb_opt;
-  if (const char* e = getenv("S2M_K1_MINBLOCKS")) {  // experiment knob
-    minb_opt = std::string("-DS2M_K1_MINBLOCKS=") + std::to_string(std::max(1, std::min(8, atoi(e))));
-    opts.push_back(minb_opt.c_str());
-  } else if (packed_heavy) {
-    minb_opt = "-DS2M_K1_MINBLOCKS=5";
-    opts.push_back(minb_opt.c_str());
-  }
+  opts.push_back("-DS2M_K1_ROWS=" + std::to_string(m->k1_rows));
+  if (const char* e = getenv("S2M_K1_MINBLOCKS"))  // experiment knob
+    opts.push_back("-DS2M_K1_MINBLOCKS=" + std::to_string(std::max(1, std::min(8, atoi(e)))));
+  else if (packed_heavy)
+    opts.push_back("-DS2M_K1_MINBLOCKS=5");
+  std::vector<const char*> opt_ptrs;
+  for (const std::string& o : opts) opt_ptrs.push_back(o.c_str());
+
+  const char* hdr_src[] = {kSrcMathH, kSrcVecH, kSrcSdfLibH, kSrcPvecH, kSrcScanCuh, kSrcKernelsJit};
+  const char* hdr_name[] = {"s2m_math.h", "s2m_vec.h", "s2m_sdf3d_lib.h", "s2m_pvec.h", "s2m_scan.cuh", "kernels_jit.cuh"};
+
   // Optional on-disk cubin cache (S2M_CACHE_DIR): keyed by everything that determines the cubin -- the
   // generated translation unit, the embedded headers, the options and the NVRTC version.  A serving
   // process that sees the same SDF again skips the ~0.5 s compile.
@@ -361,7 +355,7 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
       nvrtcVersion(&nv_major, &nv_minor);
       std::string key = m->cuda_source;
       for (const char* h : hdr_src) { key += '\0'; key += h; }
-      for (const char* o : opts) { key += '\0'; key += o; }
+      for (const std::string& o : opts) { key += '\0'; key += o; }
       key += "\0nvrtc " + std::to_string(nv_major) + "." + std::to_string(nv_minor) + " " + s2m_version();
       unsigned long long h1 = 1469598103934665603ull, h2 = 0x9e3779b97f4a7c15ull;  // two independent 64-bit FNV-1a style hashes
       for (unsigned char ch : key) { h1 = (h1 ^ ch) * 1099511628211ull; h2 = (h2 + ch) * 0xff51afd7ed558ccdull; h2 ^= h2 >> 29; }
@@ -380,25 +374,26 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
       }
     }
   }
-  const bool cache_hit = !m->cubin.empty();
-  if (cache_hit) {
-    nvrtcDestroyProgram(&prog);
+  if (!m->cubin.empty()) {
     m->log = "cubin loaded from " + cache_path;
-  } else {
-  r = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    return S2M_OK;
+  }
+
+  nvrtcProgram prog = nullptr;
+  nvrtcResult r = nvrtcCreateProgram(&prog, m->cuda_source.c_str(), "sdf_module.cu", 6, hdr_src, hdr_name);
+  if (r != NVRTC_SUCCESS) {
+    *error = std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r);
+    return S2M_ERR_NVRTC;
+  }
+  r = nvrtcCompileProgram(prog, (int)opt_ptrs.size(), opt_ptrs.data());
   size_t ls = 0;
   nvrtcGetProgramLogSize(prog, &ls);
+  m->log.clear();
   if (ls > 1) { m->log.resize(ls); nvrtcGetProgramLog(prog, &m->log[0]); }
   if (r != NVRTC_SUCCESS) {
-    std::string msg = std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + m->log;
+    *error = std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + m->log;
     nvrtcDestroyProgram(&prog);
-    if (m->k1_packed && attempt == 0) {  // keep the diagnostics, compile the scalar kernels only
-      packed_log = "packed (f32x2) form rejected, K1 falls back to one corner per evaluation:\n" + m->log + "\n";
-      user_packed.clear();
-      m->cubin.clear();
-      continue;
-    }
-    return fail(S2M_ERR_NVRTC, msg);
+    return S2M_ERR_NVRTC;
   }
   size_t cs = 0;
   nvrtcGetCUBINSize(prog, &cs);
@@ -413,9 +408,36 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
       if (!ok || rename(tmp.c_str(), cache_path.c_str()) != 0) remove(tmp.c_str());
     }
   }
-  }  // !cache_hit
-  break;
-  }  // attempt
+  return S2M_OK;
+}
+
+}  // namespace
+
+extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32_t flags, s2m_module** out) {
+  using namespace s2m_internal;
+  if (!shader || !out) return fail(S2M_ERR_INVALID_ARG, "s2m_module_compile: NULL argument");
+  *out = nullptr;
+  std::unique_ptr<s2m_module> m(new s2m_module());
+  m->ctx = ctx;
+  double t0 = now_ms();
+  std::string user, user_packed, err;
+  if (shader->kind == S2M_SRC_CUDA) {
+    user = shader->source;
+  } else {
+    int st = s2m_frontend::lower_to_cuda(*shader, &user, &err, &user_packed);
+    if (st != S2M_OK) return fail(st, err);
+  }
+  double t1 = now_ms();
+  m->ms_frontend = t1 - t0;
+  K1Plan plan = plan_k1(std::move(user_packed));
+  std::string packed_log;
+  int st = build_cubin(m.get(), user, plan, flags, &err);
+  if (st != S2M_OK && plan.packed()) {  // NVRTC rejected the packed form: keep its diagnostics, compile the scalar kernels only
+    packed_log = "packed (f32x2) form rejected, K1 falls back to one corner per evaluation:\n" + m->log + "\n";
+    plan.packed_text.clear();
+    st = build_cubin(m.get(), user, plan, flags, &err);
+  }
+  if (st != S2M_OK) return fail(st, err);
   if (!packed_log.empty()) m->log = packed_log + m->log;
   double t2 = now_ms();
   m->ms_nvrtc = t2 - t1;
