@@ -108,7 +108,11 @@ typedef struct s2m_module s2m_module;
 int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32_t flags, s2m_module** out);
 const char* s2m_module_log(const s2m_module* m);         /* NVRTC log */
 const char* s2m_module_cuda_source(const s2m_module* m); /* what NVRTC compiled */
-int s2m_module_cubin(const s2m_module* m, const void** data, size_t* size);
+int s2m_module_cubin(const s2m_module* m, const void** data, size_t* size); /* part 0 */
+/* The module is compiled as up to three NVRTC programs on concurrent host threads: part 0 holds K1
+ * (s2m_k1_slab), part 1 K4a (s2m_k4_vertices), part 2 the diagnostic kernels.  S2M_ERR_INVALID_ARG past
+ * the last part (S2M_JIT_SPLIT=0 in the environment: one part with everything). */
+int s2m_module_cubin_part(const s2m_module* m, int part, const void** data, size_t* size);
 double s2m_module_compile_ms(const s2m_module* m, int which); /* 0 front-end, 1 NVRTC, 2 load */
 void s2m_module_free(s2m_module* m);
 

@@ -105,6 +105,7 @@ SYMBOLS = {
     "s2m_module_log": (_S, [_P]),
     "s2m_module_cuda_source": (_S, [_P]),
     "s2m_module_cubin": (ctypes.c_int, [_P, _PP, ctypes.POINTER(ctypes.c_size_t)]),
+    "s2m_module_cubin_part": (ctypes.c_int, [_P, ctypes.c_int, _PP, ctypes.POINTER(ctypes.c_size_t)]),
     "s2m_module_compile_ms": (ctypes.c_double, [_P, ctypes.c_int]),
     "s2m_module_free": (None, [_P]),
     "s2m_params_from_cli": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_float, ctypes.POINTER(MeshParams), ctypes.POINTER(ctypes.c_int)]),

@@ -27,6 +27,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.h"
@@ -267,8 +268,10 @@ constexpr unsigned kK1RowsDefault = 2;  // measured: mandelbulb K1 -0.6 %, torus
 
 struct s2m_module {
   std::string cuda_source, log;
-  std::vector<char> cubin;
-  CUmodule_t mod = nullptr;
+  static constexpr int kMaxParts = 3;   // kernels_jit.cuh S2M_JIT_PART: K1 | K4a | diagnostic kernels
+  int n_parts = 0;                      // 3, or 1 when everything was compiled as one program (S2M_JIT_SPLIT=0)
+  std::vector<char> cubin[kMaxParts];
+  CUmodule_t mod[kMaxParts] = {nullptr, nullptr, nullptr};
   CUfunction_t k1 = nullptr, k4 = nullptr, k_eval = nullptr, k_probe = nullptr, k_eval2 = nullptr;
   s2m_ctx* ctx = nullptr;
   unsigned k1_rows = 1;  // grid rows per K1 thread (S2M_K1_ROWS the kernels were compiled with)
@@ -277,6 +280,13 @@ struct s2m_module {
 };
 
 namespace {
+
+void unload_parts(s2m_module* m) {
+  if (!m->ctx) return;
+  for (CUmodule_t& mod : m->mod)
+    if (mod) { cudaSetDevice(m->ctx->device); driver().cuModuleUnload(mod); mod = nullptr; }
+  m->k1 = m->k4 = m->k_eval = m->k_probe = m->k_eval2 = nullptr;
+}
 
 // How K1 evaluates the SDF.  `packed_text` is the front-end's packed (f32x2)
 // translation, empty for "one corner per evaluation".
@@ -308,10 +318,91 @@ K1Plan plan_k1(std::string packed_text) {
   return plan;
 }
 
-// Translation unit + options -> cubin in m->cubin (from S2M_CACHE_DIR when it is there).  Returns S2M_OK or
-// S2M_ERR_NVRTC with the compiler's message in *error (m->log holds the NVRTC log either way).
-int build_cubin(s2m_module* m, const std::string& user, const K1Plan& plan, uint32_t flags, std::string* error) {
+// One NVRTC program: translation unit + options -> cubin (from S2M_CACHE_DIR when it is there).  Touches
+// nothing but its arguments, so several parts compile concurrently.  Returns S2M_OK or S2M_ERR_NVRTC with
+// the compiler's message in *error (*log holds the NVRTC log either way).
+int compile_part(const std::string& source, const std::vector<std::string>& opts, std::vector<char>* cubin,
+                 std::string* log, std::string* error) {
   using namespace s2m_internal;
+  std::vector<const char*> opt_ptrs;
+  for (const std::string& o : opts) opt_ptrs.push_back(o.c_str());
+  const char* hdr_src[] = {kSrcMathH, kSrcVecH, kSrcSdfLibH, kSrcPvecH, kSrcScanCuh, kSrcKernelsJit};
+  const char* hdr_name[] = {"s2m_math.h", "s2m_vec.h", "s2m_sdf3d_lib.h", "s2m_pvec.h", "s2m_scan.cuh", "kernels_jit.cuh"};
+
+  // Optional on-disk cubin cache (S2M_CACHE_DIR): keyed by everything that determines the cubin -- the
+  // generated translation unit, the embedded headers, the options (which name the part) and the NVRTC
+  // version.  A serving process that sees the same SDF again skips the compile.
+  std::string cache_path;
+  cubin->clear();
+  log->clear();
+  if (const char* dir = getenv("S2M_CACHE_DIR")) {
+    if (*dir) {
+      int nv_major = 0, nv_minor = 0;
+      nvrtcVersion(&nv_major, &nv_minor);
+      std::string key = source;
+      for (const char* h : hdr_src) { key += '\0'; key += h; }
+      for (const std::string& o : opts) { key += '\0'; key += o; }
+      key += "\0nvrtc " + std::to_string(nv_major) + "." + std::to_string(nv_minor) + " " + s2m_version();
+      unsigned long long h1 = 1469598103934665603ull, h2 = 0x9e3779b97f4a7c15ull;  // two independent 64-bit FNV-1a style hashes
+      for (unsigned char ch : key) { h1 = (h1 ^ ch) * 1099511628211ull; h2 = (h2 + ch) * 0xff51afd7ed558ccdull; h2 ^= h2 >> 29; }
+      char name[64];
+      snprintf(name, sizeof name, "/%016llx%016llx.cubin", h1, h2);
+      cache_path = std::string(dir) + name;
+      if (FILE* f = fopen(cache_path.c_str(), "rb")) {
+        fseek(f, 0, SEEK_END);
+        const long n = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (n > 64) {
+          cubin->resize((size_t)n);
+          if (fread(cubin->data(), 1, (size_t)n, f) != (size_t)n || memcmp(cubin->data(), "\x7f" "ELF", 4) != 0) cubin->clear();
+        }
+        fclose(f);
+      }
+    }
+  }
+  if (!cubin->empty()) {
+    *log = "cubin loaded from " + cache_path;
+    return S2M_OK;
+  }
+
+  nvrtcProgram prog = nullptr;
+  nvrtcResult r = nvrtcCreateProgram(&prog, source.c_str(), "sdf_module.cu", 6, hdr_src, hdr_name);
+  if (r != NVRTC_SUCCESS) {
+    *error = std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r);
+    return S2M_ERR_NVRTC;
+  }
+  r = nvrtcCompileProgram(prog, (int)opt_ptrs.size(), opt_ptrs.data());
+  size_t ls = 0;
+  nvrtcGetProgramLogSize(prog, &ls);
+  if (ls > 1) { log->resize(ls); nvrtcGetProgramLog(prog, &(*log)[0]); log->resize(strlen(log->c_str())); }
+  if (r != NVRTC_SUCCESS) {
+    *error = std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + *log;
+    nvrtcDestroyProgram(&prog);
+    return S2M_ERR_NVRTC;
+  }
+  size_t cs = 0;
+  nvrtcGetCUBINSize(prog, &cs);
+  cubin->resize(cs);
+  nvrtcGetCUBIN(prog, cubin->data());
+  nvrtcDestroyProgram(&prog);
+  if (!cache_path.empty()) {  // best effort: write to a temporary name, then rename (atomic on POSIX)
+    const std::string tmp = cache_path + ".tmp" + std::to_string((long long)getpid()) + "." + std::to_string((unsigned long long)(uintptr_t)cubin);
+    if (FILE* f = fopen(tmp.c_str(), "wb")) {
+      const bool ok = fwrite(cubin->data(), 1, cubin->size(), f) == cubin->size();
+      fclose(f);
+      if (!ok || rename(tmp.c_str(), cache_path.c_str()) != 0) remove(tmp.c_str());
+    }
+  }
+  return S2M_OK;
+}
+
+// Generated text + plan -> the module's cubins.  The translation unit is compiled as three programs
+// that differ in -DS2M_JIT_PART (kernels_jit.cuh: K1 / K4a / diagnostic kernels), concurrently on three
+// host threads: each carries only the copies of the user's SDF its kernels inline, and NVRTC compiles
+// separate programs in parallel (8-vCPU build container, median of 5: martin_cube.sdf3d 1170 -> 670 ms,
+// mandelmesh.frag 1050 -> 810 ms, p_key 560 -> 520 ms, torus unchanged at 550 ms; K4a's part is the longest).
+// S2M_JIT_SPLIT=0 compiles one program with everything, as one would offline with nvcc.
+int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uint32_t flags, std::string* error) {
   m->k1_packed = plan.packed();
   m->cuda_source = std::string("#include \"s2m_sdf3d_lib.h\"\n#include \"s2m_scan.cuh\"\n") +
                    "namespace s2m_user {\nusing namespace s2m;\n" + user + "\n}  // namespace s2m_user\n";
@@ -338,76 +429,30 @@ int build_cubin(s2m_module* m, const std::string& user, const K1Plan& plan, uint
     opts.push_back("-DS2M_K1_MINBLOCKS=" + std::to_string(std::max(1, std::min(8, atoi(e)))));
   else if (packed_heavy)
     opts.push_back("-DS2M_K1_MINBLOCKS=5");
-  std::vector<const char*> opt_ptrs;
-  for (const std::string& o : opts) opt_ptrs.push_back(o.c_str());
 
-  const char* hdr_src[] = {kSrcMathH, kSrcVecH, kSrcSdfLibH, kSrcPvecH, kSrcScanCuh, kSrcKernelsJit};
-  const char* hdr_name[] = {"s2m_math.h", "s2m_vec.h", "s2m_sdf3d_lib.h", "s2m_pvec.h", "s2m_scan.cuh", "kernels_jit.cuh"};
-
-  // Optional on-disk cubin cache (S2M_CACHE_DIR): keyed by everything that determines the cubin -- the
-  // generated translation unit, the embedded headers, the options and the NVRTC version.  A serving
-  // process that sees the same SDF again skips the ~0.5 s compile.
-  std::string cache_path;
-  m->cubin.clear();
-  if (const char* dir = getenv("S2M_CACHE_DIR")) {
-    if (*dir) {
-      int nv_major = 0, nv_minor = 0;
-      nvrtcVersion(&nv_major, &nv_minor);
-      std::string key = m->cuda_source;
-      for (const char* h : hdr_src) { key += '\0'; key += h; }
-      for (const std::string& o : opts) { key += '\0'; key += o; }
-      key += "\0nvrtc " + std::to_string(nv_major) + "." + std::to_string(nv_minor) + " " + s2m_version();
-      unsigned long long h1 = 1469598103934665603ull, h2 = 0x9e3779b97f4a7c15ull;  // two independent 64-bit FNV-1a style hashes
-      for (unsigned char ch : key) { h1 = (h1 ^ ch) * 1099511628211ull; h2 = (h2 + ch) * 0xff51afd7ed558ccdull; h2 ^= h2 >> 29; }
-      char name[64];
-      snprintf(name, sizeof name, "/%016llx%016llx.cubin", h1, h2);
-      cache_path = std::string(dir) + name;
-      if (FILE* f = fopen(cache_path.c_str(), "rb")) {
-        fseek(f, 0, SEEK_END);
-        const long n = ftell(f);
-        fseek(f, 0, SEEK_SET);
-        if (n > 64) {
-          m->cubin.resize((size_t)n);
-          if (fread(m->cubin.data(), 1, (size_t)n, f) != (size_t)n || memcmp(m->cubin.data(), "\x7f" "ELF", 4) != 0) m->cubin.clear();
-        }
-        fclose(f);
-      }
-    }
-  }
-  if (!m->cubin.empty()) {
-    m->log = "cubin loaded from " + cache_path;
-    return S2M_OK;
-  }
-
-  nvrtcProgram prog = nullptr;
-  nvrtcResult r = nvrtcCreateProgram(&prog, m->cuda_source.c_str(), "sdf_module.cu", 6, hdr_src, hdr_name);
-  if (r != NVRTC_SUCCESS) {
-    *error = std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r);
-    return S2M_ERR_NVRTC;
-  }
-  r = nvrtcCompileProgram(prog, (int)opt_ptrs.size(), opt_ptrs.data());
-  size_t ls = 0;
-  nvrtcGetProgramLogSize(prog, &ls);
+  const char* split = getenv("S2M_JIT_SPLIT");
+  const int n_parts = (split && atoi(split) == 0) ? 1 : s2m_module::kMaxParts;
+  m->n_parts = n_parts;
+  int status[s2m_module::kMaxParts] = {0, 0, 0};
+  std::string logs[s2m_module::kMaxParts], errors[s2m_module::kMaxParts];
+  auto work = [&](int k) {
+    std::vector<std::string> o = opts;
+    if (n_parts > 1) o.push_back("-DS2M_JIT_PART=" + std::to_string(k + 1));
+    status[k] = compile_part(m->cuda_source, o, &m->cubin[k], &logs[k], &errors[k]);
+  };
+  std::vector<std::thread> threads;
+  for (int k = 1; k < n_parts; ++k) threads.emplace_back(work, k);
+  work(0);
+  for (std::thread& t : threads) t.join();
   m->log.clear();
-  if (ls > 1) { m->log.resize(ls); nvrtcGetProgramLog(prog, &m->log[0]); }
-  if (r != NVRTC_SUCCESS) {
-    *error = std::string("NVRTC: ") + nvrtcGetErrorString(r) + "\n" + m->log;
-    nvrtcDestroyProgram(&prog);
-    return S2M_ERR_NVRTC;
-  }
-  size_t cs = 0;
-  nvrtcGetCUBINSize(prog, &cs);
-  m->cubin.resize(cs);
-  nvrtcGetCUBIN(prog, m->cubin.data());
-  nvrtcDestroyProgram(&prog);
-  if (!cache_path.empty()) {  // best effort: write to a temporary name, then rename (atomic on POSIX)
-    const std::string tmp = cache_path + ".tmp" + std::to_string((long long)getpid());
-    if (FILE* f = fopen(tmp.c_str(), "wb")) {
-      const bool ok = fwrite(m->cubin.data(), 1, m->cubin.size(), f) == m->cubin.size();
-      fclose(f);
-      if (!ok || rename(tmp.c_str(), cache_path.c_str()) != 0) remove(tmp.c_str());
+  for (int k = 0; k < n_parts; ++k)
+    if (!logs[k].empty() && m->log.find(logs[k]) == std::string::npos) m->log += (m->log.empty() ? "" : "\n") + logs[k];
+  for (int k = 0; k < n_parts; ++k)
+    if (status[k] != S2M_OK) {
+      for (auto& c : m->cubin) c.clear();
+      *error = errors[k];
+      return status[k];
     }
-  }
   return S2M_OK;
 }
 
@@ -431,11 +476,11 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   m->ms_frontend = t1 - t0;
   K1Plan plan = plan_k1(std::move(user_packed));
   std::string packed_log;
-  int st = build_cubin(m.get(), user, plan, flags, &err);
+  int st = build_cubins(m.get(), user, plan, flags, &err);
   if (st != S2M_OK && plan.packed()) {  // NVRTC rejected the packed form: keep its diagnostics, compile the scalar kernels only
     packed_log = "packed (f32x2) form rejected, K1 falls back to one corner per evaluation:\n" + m->log + "\n";
     plan.packed_text.clear();
-    st = build_cubin(m.get(), user, plan, flags, &err);
+    st = build_cubins(m.get(), user, plan, flags, &err);
   }
   if (st != S2M_OK) return fail(st, err);
   if (!packed_log.empty()) m->log = packed_log + m->log;
@@ -443,17 +488,19 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   m->ms_nvrtc = t2 - t1;
   if (ctx) {
     CUDA_TRY(cudaSetDevice(ctx->device));
-    CUresult_t cr = driver().cuModuleLoadData(&m->mod, m->cubin.data());
-    if (cr) return fail(S2M_ERR_CUDA, "cuModuleLoadData: " + cu_err(cr));
-    struct { CUfunction_t* f; const char* n; } fns[] = {
-        {&m->k1, "s2m_k1_slab"}, {&m->k4, "s2m_k4_vertices"}, {&m->k_eval, "s2m_k_eval"}, {&m->k_probe, "s2m_k_cost_probe"}};
-    for (auto& f : fns) {
-      cr = driver().cuModuleGetFunction(f.f, m->mod, f.n);
-      if (cr) return fail(S2M_ERR_CUDA, std::string("cuModuleGetFunction(") + f.n + "): " + cu_err(cr));
+    CUresult_t cr;
+    for (int k = 0; k < m->n_parts; ++k) {
+      cr = driver().cuModuleLoadData(&m->mod[k], m->cubin[k].data());
+      if (cr) { unload_parts(m.get()); return fail(S2M_ERR_CUDA, "cuModuleLoadData: " + cu_err(cr)); }
     }
-    if (m->k1_packed) {
-      cr = driver().cuModuleGetFunction(&m->k_eval2, m->mod, "s2m_k_eval2");
-      if (cr) return fail(S2M_ERR_CUDA, "cuModuleGetFunction(s2m_k_eval2): " + cu_err(cr));
+    const bool split = m->n_parts > 1;
+    struct { CUfunction_t* f; const char* n; int part; bool wanted; } fns[] = {
+        {&m->k1, "s2m_k1_slab", 0, true}, {&m->k4, "s2m_k4_vertices", 1, true}, {&m->k_eval, "s2m_k_eval", 2, true},
+        {&m->k_probe, "s2m_k_cost_probe", 2, true}, {&m->k_eval2, "s2m_k_eval2", 2, m->k1_packed}};
+    for (auto& f : fns) {
+      if (!f.wanted) continue;
+      cr = driver().cuModuleGetFunction(f.f, m->mod[split ? f.part : 0], f.n);
+      if (cr) { unload_parts(m.get()); return fail(S2M_ERR_CUDA, std::string("cuModuleGetFunction(") + f.n + "): " + cu_err(cr)); }
     }
     m->ms_load = now_ms() - t2;
   }
@@ -463,9 +510,11 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
 
 extern "C" const char* s2m_module_log(const s2m_module* m) { return m ? m->log.c_str() : ""; }
 extern "C" const char* s2m_module_cuda_source(const s2m_module* m) { return m ? m->cuda_source.c_str() : ""; }
-extern "C" int s2m_module_cubin(const s2m_module* m, const void** data, size_t* size) {
+extern "C" int s2m_module_cubin(const s2m_module* m, const void** data, size_t* size) { return s2m_module_cubin_part(m, 0, data, size); }
+extern "C" int s2m_module_cubin_part(const s2m_module* m, int part, const void** data, size_t* size) {
   if (!m || !data || !size) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
-  *data = m->cubin.data(); *size = m->cubin.size();
+  if (part < 0 || part >= m->n_parts) return fail(S2M_ERR_INVALID_ARG, "s2m_module_cubin_part: the module has " + std::to_string(m->n_parts) + " part(s)");
+  *data = m->cubin[part].data(); *size = m->cubin[part].size();
   return S2M_OK;
 }
 extern "C" double s2m_module_compile_ms(const s2m_module* m, int which) {
@@ -474,7 +523,7 @@ extern "C" double s2m_module_compile_ms(const s2m_module* m, int which) {
 }
 extern "C" void s2m_module_free(s2m_module* m) {
   if (!m) return;
-  if (m->mod && m->ctx) { cudaSetDevice(m->ctx->device); driver().cuModuleUnload(m->mod); }
+  unload_parts(m);
   delete m;
 }
 
@@ -720,7 +769,7 @@ void finalize_timings(s2m_ctx* c, s2m_result* r) {
 int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fuse_quads, s2m_result** out) {
   if (!c || !m || !p || !out) return fail(S2M_ERR_INVALID_ARG, "s2m_mesh_begin: NULL argument");
   *out = nullptr;
-  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (!m->k1 || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
   if (c->busy) return fail(S2M_ERR_STATE, "a previous s2m_mesh_begin on this ctx has not been finished or freed");
   CUDA_TRY(cudaSetDevice(c->device));
   std::unique_ptr<s2m_result> rp(new s2m_result());
@@ -1105,7 +1154,7 @@ extern "C" int s2m_result_get(const s2m_result* r, s2m_result_info* o) {
 // ------------------------------------------------------------------ diagnostics
 extern "C" int s2m_eval_points(s2m_ctx* c, s2m_module* m, const float* xyz, uint64_t n, float* out) {
   if (!c || !m || !xyz || !out) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
-  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (!m->k1 || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
   if (n == 0) return S2M_OK;
   CUDA_TRY(cudaSetDevice(c->device));
   DevBuf in, o;
@@ -1130,7 +1179,7 @@ extern "C" int s2m_module_is_packed(const s2m_module* m) { return m && m->k1_pac
 extern "C" int s2m_eval_pairs(s2m_ctx* c, s2m_module* m, const float* xyz_a, const float* xyz_b, uint64_t n, float* out_a, float* out_b,
                               uint8_t* disagreed) {
   if (!c || !m || !xyz_a || !xyz_b || !out_a || !out_b || !disagreed) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
-  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (!m->k1 || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
   if (!m->k_eval2) return fail(S2M_ERR_UNSUPPORTED, "module has no packed (f32x2) form");
   if (n == 0) return S2M_OK;
   CUDA_TRY(cudaSetDevice(c->device));
@@ -1158,7 +1207,7 @@ extern "C" int s2m_eval_pairs(s2m_ctx* c, s2m_module* m, const float* xyz_a, con
 
 extern "C" int s2m_debug_slab_plane(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, uint32_t plane, float* out) {
   if (!c || !m || !p || !out) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
-  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (!m->k1 || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
   if (c->busy) return fail(S2M_ERR_STATE, "ctx is busy");
   GridDev g;
   int st = make_grid(p, &g);
@@ -1193,7 +1242,7 @@ extern "C" int s2m_read_device_words(s2m_ctx* c, const void* device_words, uint3
 
 extern "C" int s2m_cost_probe(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, uint32_t planes, double* cost_out) {
   if (!c || !m || !p || !cost_out || planes == 0) return fail(S2M_ERR_INVALID_ARG, "bad argument");
-  if (!m->mod || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (!m->k1 || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
   GridDev g;
   int st = make_grid(p, &g);
   if (st) return st;

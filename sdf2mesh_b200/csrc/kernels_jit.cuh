@@ -15,6 +15,22 @@
  *     s2m_k_cost_probe per-z-plane evaluation cost estimate used to balance multi-GPU z-slabs.
  */
 
+/* The module is compiled as three independent NVRTC programs, concurrently on three host threads
+ * (engine.cpp build_module): S2M_JIT_PART = 1: K1, 2: K4a, 3: the diagnostic kernels; undefined: all
+ * of them in one translation unit (tools/, offline nvcc).  Each part carries the copies of the
+ * user's SDF that it needs and nothing else, which is what the compile time is made of. */
+#if !defined(S2M_JIT_PART)
+#define S2M_JIT_K1 1
+#define S2M_JIT_K4 1
+#define S2M_JIT_MISC 1
+#elif S2M_JIT_PART == 1
+#define S2M_JIT_K1 1
+#elif S2M_JIT_PART == 2
+#define S2M_JIT_K4 1
+#elif S2M_JIT_PART == 3
+#define S2M_JIT_MISC 1
+#endif
+
 #ifndef S2M_K1_UNROLL
 #define S2M_K1_UNROLL 4
 #endif
@@ -35,6 +51,7 @@ __device__ __forceinline__ float s2m_sdf(float x, float y, float z) {
 __device__ __noinline__ float s2m_sdf_call(float x, float y, float z) { return s2m_sdf(x, y, z); }
 
 /* ------------------------------------------------------------------------------------------ K1 */
+#if defined(S2M_JIT_K1)
 /* A thread evaluates 4 consecutive x corners and stores one float4.  The block shape is chosen by
  * the host: blockDim = (bx, by) with bx*by = 256.  A warp is 32 consecutive threads, x fastest, so
  * its footprint is (4*min(bx,32)) x (32/min(bx,32)) corners: (32,8) = 128x1 rows (512 B contiguous
@@ -153,7 +170,10 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   }
 }
 
+#endif  /* S2M_JIT_K1 */
+
 /* ------------------------------------------------------------------------------------------ K4a */
+#if defined(S2M_JIT_K4)
 __device__ __forceinline__ float s2m_cell_adapt(float v0, float v1) { return (0.0f - v0) / (v1 - v0); }
 
 struct S2mVertexOut {
@@ -358,7 +378,10 @@ s2m_k4_vertices(S2mGrid g, const unsigned long long* __restrict__ cand_key, unsi
   if (threadIdx.x == 0 && (unsigned long long)(tile + 1) * blockDim.x >= n_cand) *out.n_vertices = s_base + total;
 }
 
+#endif  /* S2M_JIT_K4 */
+
 /* ------------------------------------------------------------------------------------------ misc */
+#if defined(S2M_JIT_MISC)
 extern "C" __global__ void s2m_k_eval(const float* __restrict__ pts, float* __restrict__ out, unsigned long long n) {
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = s2m_sdf(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
@@ -401,3 +424,4 @@ s2m_k_cost_probe(S2mGrid g, unsigned probe, unsigned planes, unsigned long long*
   if (lane == 0) atomicAdd(cycles + pz, (unsigned long long)(t1 - t0));
   if (acc == 123.456f) sink[0] = acc;
 }
+#endif  /* S2M_JIT_MISC */

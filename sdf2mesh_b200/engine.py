@@ -74,6 +74,15 @@ class Module:
         check(lib().s2m_module_cubin(self._h, ctypes.byref(data), ctypes.byref(size)))
         return size.value
 
+    def cubins(self):
+        """the module's cubins: K1 | K4a | diagnostic kernels (one with everything under S2M_JIT_SPLIT=0)"""
+        out = []
+        while True:
+            data, size = ctypes.c_void_p(), ctypes.c_size_t()
+            if lib().s2m_module_cubin_part(self._h, len(out), ctypes.byref(data), ctypes.byref(size)) != 0:
+                return out
+            out.append(ctypes.string_at(data, size.value))
+
     def compile_ms(self):
         return tuple(lib().s2m_module_compile_ms(self._h, i) for i in range(3))
 

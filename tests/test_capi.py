@@ -64,11 +64,27 @@ def test_examples_jit_to_sm100a_cubin(built, name, tmp_path):
     assert m.cubin_size > 10000
     data, size = ctypes.c_void_p(), ctypes.c_size_t()
     _capi.check(_capi.lib().s2m_module_cubin(m._h, ctypes.byref(data), ctypes.byref(size)))
-    cubin = tmp_path / "m.cubin"
-    cubin.write_bytes(ctypes.string_at(data, size.value))
+    parts = m.cubins()
+    assert len(parts) == 3 and parts[0] == ctypes.string_at(data, size.value)   # three NVRTC programs; part 0 = K1
+    for i, (part, kernels) in enumerate(zip(parts, (["s2m_k1_slab"], ["s2m_k4_vertices"], ["s2m_k_eval", "s2m_k_cost_probe"]))):
+        cubin = tmp_path / f"m{i}.cubin"
+        cubin.write_bytes(part)
+        out = subprocess.run(["cuobjdump", "-elf", str(cubin)], capture_output=True, text=True).stdout
+        assert "sm_100" in out or "SM100" in out.upper() or "EF_CUDA_SM100" in out
+        for k in ("s2m_k1_slab", "s2m_k4_vertices", "s2m_k_eval", "s2m_k_cost_probe"):
+            assert (k + "\n" in out or k + " " in out or ".text." + k in out) == (k in kernels), (i, k)
+
+
+def test_jit_split_off_is_one_program(built, monkeypatch, tmp_path):
+    """S2M_JIT_SPLIT=0: one NVRTC program holding every kernel (what an offline nvcc build of the unit gives)"""
+    monkeypatch.setenv("S2M_JIT_SPLIT", "0")
+    m = load_example_shader("torus").create_shader_module(None)
+    parts = m.cubins()
+    assert len(parts) == 1 and m.cubin_size == len(parts[0])
+    cubin = tmp_path / "one.cubin"
+    cubin.write_bytes(parts[0])
     out = subprocess.run(["cuobjdump", "-elf", str(cubin)], capture_output=True, text=True).stdout
-    assert "sm_100" in out or "SM100" in out.upper() or "EF_CUDA_SM100" in out
-    for k in ("s2m_k1_slab", "s2m_k4_vertices", "s2m_k_eval"):
+    for k in ("s2m_k1_slab", "s2m_k4_vertices", "s2m_k_eval", "s2m_k_cost_probe", "s2m_k_eval2"):
         assert k in out
 
 
@@ -88,11 +104,11 @@ def test_cubin_cache(built, tmp_path, monkeypatch):
     monkeypatch.setenv("S2M_CACHE_DIR", str(tmp_path))
     src = "fn sdf3d(p: vec3f) -> f32 { return length(p) - 0.75; }"
     a = s2m.Sdf3DShader.from_source(src).create_shader_module(None)
-    assert "loaded from" not in a.log and len(list(tmp_path.glob("*.cubin"))) == 1
+    assert "loaded from" not in a.log and len(list(tmp_path.glob("*.cubin"))) == 3   # one file per NVRTC program
     b = s2m.Sdf3DShader.from_source(src).create_shader_module(None)
-    assert "cubin loaded from" in b.log and b.cubin_size == a.cubin_size
+    assert b.log.count("cubin loaded from") == 3 and b.cubins() == a.cubins()
     s2m.Sdf3DShader.from_source(src.replace("0.75", "0.5")).create_shader_module(None)
-    assert len(list(tmp_path.glob("*.cubin"))) == 2 and not list(tmp_path.glob("*.tmp*"))
+    assert len(list(tmp_path.glob("*.cubin"))) == 6 and not list(tmp_path.glob("*.tmp*"))
     # a damaged entry is ignored and rewritten
     f = sorted(tmp_path.glob("*.cubin"))[0]
     f.write_bytes(b"garbage" * 20)
