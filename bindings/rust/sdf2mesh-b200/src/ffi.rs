@@ -137,6 +137,7 @@ extern "C" {
     pub fn s2m_result_write_mesh(r: *const s2m_result, path: *const c_char) -> c_int; // mesh.rs:182
     pub fn s2m_result_write_stl_binary(r: *const s2m_result, path: *const c_char) -> c_int;
     pub fn s2m_result_free(r: *mut s2m_result);
+    pub fn s2m_write_mesh_arrays(parts: *const s2m_result_info, n_parts: c_int, path: *const c_char, binary_stl: c_int) -> c_int;
     pub fn s2m_write_mesh_parts(parts: *const *const s2m_result, n_parts: c_int, path: *const c_char, binary_stl: c_int) -> c_int;
     pub fn s2m_read_device_words(ctx: *mut s2m_ctx, device_words: *const c_void, n: u32, out: *mut u64, cuda_stream: *mut c_void) -> c_int;
 

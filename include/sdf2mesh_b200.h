@@ -211,6 +211,11 @@ int s2m_result_write_stl_binary(const s2m_result* r, const char* path);
  * given in z order with consecutive global vertex bases: one STL / PLY file for the whole mesh.
  * binary_stl != 0 writes binary STL for a .stl path. */
 int s2m_write_mesh_parts(const s2m_result* const* parts, int n_parts, const char* path, int binary_stl);
+/* The same writers over caller-owned host arrays -- TriangleMesh::write_to_file (mesh.rs:182) for a mesh
+ * that is not held in an s2m_result (another process's z-slabs, a mesh read back from disk).  Of each
+ * s2m_result_info only n_vertices, positions, normals (PLY), n_quads, quads or quads32,
+ * global_vertex_base, n_halo_vertices and halo_positions are read.  Needs no device. */
+int s2m_write_mesh_arrays(const s2m_result_info* parts, int n_parts, const char* path, int binary_stl);
 
 /* Reads n (<= 32) 64-bit words that live in device memory -- the output of the count all-gather --
  * into host memory with a one-warp kernel writing through mapped pinned memory, on the caller's CUDA

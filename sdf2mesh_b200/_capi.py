@@ -117,6 +117,7 @@ SYMBOLS = {
     "s2m_result_write_mesh": (ctypes.c_int, [_P, _S]),
     "s2m_result_write_stl_binary": (ctypes.c_int, [_P, _S]),
     "s2m_write_mesh_parts": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _S, ctypes.c_int]),
+    "s2m_write_mesh_arrays": (ctypes.c_int, [_P, ctypes.c_int, _S, ctypes.c_int]),
     "s2m_eval_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_uint64, _P]),
     "s2m_module_is_packed": (ctypes.c_int, [_P]),
     "s2m_eval_pairs": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P]),

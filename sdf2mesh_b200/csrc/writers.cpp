@@ -81,14 +81,14 @@ struct Parts {
   }
 };
 
-int get_parts(const s2m_result* const* rs, int n, Parts* out, bool whole_mesh) {
-  if (!rs || n <= 0) return fail(S2M_ERR_INVALID_ARG, "no results to write");
+int get_parts(const s2m_result_info* infos, int n, Parts* out, bool whole_mesh) {
+  if (!infos || n <= 0) return fail(S2M_ERR_INVALID_ARG, "no results to write");
   for (int k = 0; k < n; ++k) {
-    if (!rs[k]) return fail(S2M_ERR_INVALID_ARG, "result is NULL");
     Part p;
-    int st = s2m_result_get(rs[k], &p.i);
-    if (st) return st;
+    p.i = infos[k];
     if (p.i.n_quads && !p.i.quads && !p.i.quads32) return fail(S2M_ERR_STATE, "s2m_mesh_finish has not been called");
+    if (p.i.n_vertices && !p.i.positions) return fail(S2M_ERR_INVALID_ARG, "positions is NULL");
+    if (whole_mesh && p.i.n_vertices && !p.i.normals) return fail(S2M_ERR_INVALID_ARG, "normals is NULL (PLY writes them)");
     p.base = p.i.global_vertex_base;
     if (k > 0 && p.base != out->parts.back().base + (int64_t)out->parts.back().i.n_vertices)
       return fail(S2M_ERR_STATE, "parts must be consecutive z-slabs with consecutive global vertex bases");
@@ -104,6 +104,16 @@ int get_parts(const s2m_result* const* rs, int n, Parts* out, bool whole_mesh) {
       if (!out->pos(quad_index(p.i, q), k)) return fail(S2M_ERR_STATE, "a quad refers to a vertex outside the given parts");
   }
   return S2M_OK;
+}
+int get_parts(const s2m_result* const* rs, int n, Parts* out, bool whole_mesh) {
+  if (!rs || n <= 0) return fail(S2M_ERR_INVALID_ARG, "no results to write");
+  std::vector<s2m_result_info> infos((size_t)n);
+  for (int k = 0; k < n; ++k) {
+    if (!rs[k]) return fail(S2M_ERR_INVALID_ARG, "result is NULL");
+    int st = s2m_result_get(rs[k], &infos[(size_t)k]);
+    if (st) return st;
+  }
+  return get_parts(infos.data(), n, out, whole_mesh);
 }
 
 // run fn(begin, end, out) over [0, n) in ordered chunks, formatting chunks on several threads and
@@ -256,7 +266,8 @@ std::string upper_extension(const char* path) {  // Path::extension().to_ascii_u
   return ext;
 }
 
-int write_parts(const s2m_result* const* rs, int n, const char* path, int binary_stl) {
+template <class Src>
+int write_parts(const Src* rs, int n, const char* path, int binary_stl) {
   if (!path) return fail(S2M_ERR_INVALID_ARG, "path is NULL");
   const std::string ext = upper_extension(path);
   if (ext != "STL" && ext != "PLY") {
@@ -283,5 +294,9 @@ extern "C" int s2m_result_write_stl_binary(const s2m_result* r, const char* path
 }
 
 extern "C" int s2m_write_mesh_parts(const s2m_result* const* parts, int n_parts, const char* path, int binary_stl) {
+  return write_parts(parts, n_parts, path, binary_stl);
+}
+
+extern "C" int s2m_write_mesh_arrays(const s2m_result_info* parts, int n_parts, const char* path, int binary_stl) {
   return write_parts(parts, n_parts, path, binary_stl);
 }

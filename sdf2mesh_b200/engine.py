@@ -208,6 +208,44 @@ def write_mesh_parts(parts, path, binary_stl: bool = False):
     check(lib().s2m_write_mesh_parts(arr, len(parts), str(path).encode(), 1 if binary_stl else 0))
 
 
+def write_mesh_arrays(parts, path, binary_stl: bool = False):
+    """TriangleMesh::write_to_file (mesh.rs:182) over caller-owned arrays; needs no device.
+
+    parts: [(positions (n,3) f32, normals (n,3) f32 or None, quads (m,4) u64 or u32)] for the whole mesh,
+    or one (positions, normals, quads, global_vertex_base, halo_positions) tuple per z-slab in z order."""
+    infos = (ResultInfo * len(parts))()
+    keep = []
+    for k, part in enumerate(parts):
+        pos, nrm, quads = part[0], part[1], part[2]
+        base = int(part[3]) if len(part) > 3 else 0
+        halo = part[4] if len(part) > 4 else None
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        quads = np.ascontiguousarray(quads)
+        if quads.dtype != np.uint32:
+            quads = quads.astype(np.uint64, copy=False)
+        quads = quads.reshape(-1, 4)
+        keep += [pos, quads]
+        i = infos[k]
+        i.n_vertices, i.n_quads, i.global_vertex_base = pos.shape[0], quads.shape[0], base
+        i.positions = pos.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        if nrm is not None:
+            nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 3)
+            assert nrm.shape == pos.shape
+            keep.append(nrm)
+            i.normals = nrm.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        if quads.dtype == np.uint32:
+            i.quads32 = quads.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+        else:
+            i.quads = quads.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+        if halo is not None:
+            halo = np.ascontiguousarray(halo, np.float32).reshape(-1, 3)
+            keep.append(halo)
+            i.n_halo_vertices = halo.shape[0]
+            i.halo_positions = halo.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    check(lib().s2m_write_mesh_arrays(infos, len(parts), str(path).encode(), 1 if binary_stl else 0))
+    del keep
+
+
 def mesh_begin(ctx: Context, module: Module, params: MeshParams) -> MeshResult:
     h = ctypes.c_void_p()
     check(lib().s2m_mesh_begin(ctx._h, module._h, ctypes.byref(params), ctypes.byref(h)))
