@@ -11,7 +11,11 @@
 #include <charconv>
 #include <cmath>
 #include <cstdio>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -22,16 +26,20 @@ using s2m_internal::fail;
 
 namespace {
 
-// appends Rust `{}` formatting of f to out
-void rust_f32(float f, std::string& out) {
-  if (f != f) { out += "NaN"; return; }
-  if (std::isinf(f)) { out += f > 0 ? "inf" : "-inf"; return; }
-  if (f == 0.0f) { out += std::signbit(f) ? "-0" : "0"; return; }
+// Rust `{}` formatting of f at o (at most kMaxF32Chars bytes); returns the end
+constexpr size_t kMaxF32Chars = 64;  // "-0." + 44 zeros + 9 digits
+inline char* put(char* o, const char* text, size_t n) { memcpy(o, text, n); return o + n; }
+template <size_t N>
+inline char* put(char* o, const char (&text)[N]) { return put(o, text, N - 1); }
+char* rust_f32(float f, char* o) {
+  if (f != f) return put(o, "NaN");
+  if (std::isinf(f)) return f > 0 ? put(o, "inf") : put(o, "-inf");
+  if (f == 0.0f) return std::signbit(f) ? put(o, "-0") : put(o, "0");
   char buf[48];
   auto r = std::to_chars(buf, buf + sizeof buf, f, std::chars_format::scientific);  // shortest round-trip
   // buf = [-]d[.ddd]e[+-]XX
   const char* p = buf;
-  if (*p == '-') { out += '-'; ++p; }
+  if (*p == '-') { *o++ = '-'; ++p; }
   char digits[16];
   int nd = 0;
   while (p < r.ptr && *p != 'e') { if (*p != '.') digits[nd++] = *p; ++p; }
@@ -45,18 +53,26 @@ void rust_f32(float f, std::string& out) {
   }
   while (nd > 1 && digits[nd - 1] == '0') --nd;
   if (ex < 0) {
-    out += "0.";
-    out.append((size_t)(-ex - 1), '0');
-    out.append(digits, (size_t)nd);
-  } else if (ex + 1 >= nd) {
-    out.append(digits, (size_t)nd);
-    out.append((size_t)(ex + 1 - nd), '0');
-  } else {
-    out.append(digits, (size_t)(ex + 1));
-    out += '.';
-    out.append(digits + ex + 1, (size_t)(nd - ex - 1));
+    *o++ = '0'; *o++ = '.';
+    memset(o, '0', (size_t)(-ex - 1)); o += -ex - 1;
+    return put(o, digits, (size_t)nd);
   }
+  if (ex + 1 >= nd) {
+    o = put(o, digits, (size_t)nd);
+    memset(o, '0', (size_t)(ex + 1 - nd));
+    return o + (ex + 1 - nd);
+  }
+  o = put(o, digits, (size_t)(ex + 1));
+  *o++ = '.';
+  return put(o, digits + ex + 1, (size_t)(nd - ex - 1));
 }
+inline char* rust_f32x3(const float* v, char* o, char last) {
+  o = rust_f32(v[0], o); *o++ = ' ';
+  o = rust_f32(v[1], o); *o++ = ' ';
+  o = rust_f32(v[2], o); *o++ = last;
+  return o;
+}
+inline char* put_u32(char* o, uint32_t v) { return std::to_chars(o, o + 10, v).ptr; }
 
 // One or more z-slab results, in z order, addressed by global vertex index.
 struct Part {
@@ -116,27 +132,71 @@ int get_parts(const s2m_result* const* rs, int n, Parts* out, bool whole_mesh) {
   return get_parts(infos.data(), n, out, whole_mesh);
 }
 
-// run fn(begin, end, out) over [0, n) in ordered chunks, formatting chunks on several threads and
-// writing them in order
+// Runs `char* fn(begin, end, char* out)` over [0, n) in chunks of `chunk` items (at most `max_item_bytes`
+// of output each) and writes the chunks to f in order.  Worker threads take chunk numbers from a
+// counter and format into a ring of reusable buffers; the calling thread writes buffer after buffer as
+// they become ready, so formatting and fwrite overlap and no memory is touched for the first time after
+// the ring has been filled once.
 template <class Fn>
-int parallel_write(FILE* f, uint64_t n, uint64_t chunk, Fn fn) {
-  const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+int parallel_write(FILE* f, uint64_t n, uint64_t chunk, size_t max_item_bytes, Fn fn) {
+  if (n == 0) return S2M_OK;
+  if (const char* e = getenv("S2M_WRITER_CHUNK")) chunk = (uint64_t)std::max(1, atoi(e));  // tests: many chunks from a small mesh
   const uint64_t n_chunks = (n + chunk - 1) / chunk;
-  for (uint64_t base = 0; base < n_chunks; base += hw) {
-    const unsigned cnt = (unsigned)std::min<uint64_t>(hw, n_chunks - base);
-    std::vector<std::string> bufs(cnt);
-    std::vector<std::thread> th;
-    for (unsigned t = 0; t < cnt; ++t)
-      th.emplace_back([&, t] {
-        const uint64_t b = (base + t) * chunk, e = std::min(n, b + chunk);
-        bufs[t].reserve((size_t)(e - b) * 96);
-        fn(b, e, bufs[t]);
-      });
-    for (auto& x : th) x.join();
-    for (unsigned t = 0; t < cnt; ++t)
-      if (fwrite(bufs[t].data(), 1, bufs[t].size(), f) != bufs[t].size()) return fail(S2M_ERR_IO, "short write");
+  unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+  if (const char* e = getenv("S2M_WRITER_THREADS")) hw = (unsigned)std::max(1, std::min(256, atoi(e)));
+  const unsigned workers = (unsigned)std::min<uint64_t>(hw, n_chunks);
+  const unsigned n_slots = 2 * workers;
+  struct Slot {
+    std::unique_ptr<char[]> buf;
+    size_t len = 0;
+    uint64_t holds = ~0ull;   // chunk number whose text is in buf
+  };
+  std::vector<Slot> slots(n_slots);
+  for (Slot& sl : slots) sl.buf.reset(new char[(size_t)chunk * max_item_bytes]);  // untouched pages cost nothing
+  std::mutex mu;
+  std::condition_variable cv_ready, cv_free;
+  uint64_t next_chunk = 0, written = 0;   // guarded by mu; chunk c may use its slot once c < written + n_slots
+  bool stop = false;
+  auto work = [&] {
+    for (;;) {
+      uint64_t c;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        if (stop || next_chunk >= n_chunks) return;
+        c = next_chunk++;
+        cv_free.wait(lk, [&] { return stop || c < written + n_slots; });
+        if (stop) return;
+      }
+      Slot& sl = slots[c % n_slots];
+      const uint64_t b = c * chunk, e = std::min(n, b + chunk);
+      sl.len = (size_t)(fn(b, e, sl.buf.get()) - sl.buf.get());
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        sl.holds = c;
+      }
+      cv_ready.notify_one();
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < workers; ++t) th.emplace_back(work);
+  int st = S2M_OK;
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    Slot& sl = slots[c % n_slots];
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_ready.wait(lk, [&] { return sl.holds == c; });
+    }
+    const bool ok = fwrite(sl.buf.get(), 1, sl.len, f) == sl.len;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      written = c + 1;
+      if (!ok) stop = true;
+    }
+    cv_free.notify_all();
+    if (!ok) { st = fail(S2M_ERR_IO, std::string("short write: ") + strerror(errno)); break; }
   }
-  return S2M_OK;
+  for (auto& x : th) x.join();
+  return st;
 }
 
 inline void tri_of_quad(const s2m_result_info& m, uint64_t quad, int t, uint64_t tri[3]) {  // lib.rs:199-204
@@ -159,7 +219,8 @@ int write_stl_ascii(const Parts& v, const char* path) {
   int st = S2M_OK;
   for (size_t k = 0; k < v.parts.size() && st == S2M_OK; ++k) {
     const s2m_result_info& m = v.parts[k].i;
-    st = parallel_write(f, m.n_quads, 1u << 15, [&](uint64_t b, uint64_t e, std::string& out) {
+    // per quad: 2 facets of 4 float triples and 70 bytes of keywords
+    st = parallel_write(f, m.n_quads, 1u << 13, 2 * (12 * (kMaxF32Chars + 1) + 70), [&](uint64_t b, uint64_t e, char* o) {
       for (uint64_t q = b; q < e; ++q)
         for (int t = 0; t < 2; ++t) {
           uint64_t tri[3];
@@ -169,16 +230,16 @@ int write_stl_ascii(const Parts& v, const char* path) {
           const float* p2 = v.pos(tri[2], k);
           float n[3];
           tri_normal(p0, p1, p2, n);
-          out += "facet normal ";
-          rust_f32(n[0], out); out += ' '; rust_f32(n[1], out); out += ' '; rust_f32(n[2], out);
-          out += "\n\touter loop\n";
+          o = put(o, "facet normal ");
+          o = rust_f32x3(n, o, '\n');
+          o = put(o, "\touter loop\n");
           for (const float* p : {p0, p1, p2}) {
-            out += "\t\tvertex ";
-            rust_f32(p[0], out); out += ' '; rust_f32(p[1], out); out += ' '; rust_f32(p[2], out);
-            out += '\n';
+            o = put(o, "\t\tvertex ");
+            o = rust_f32x3(p, o, '\n');
           }
-          out += "\tendloop\nendfacet\n";
+          o = put(o, "\tendloop\nendfacet\n");
         }
+      return o;
     });
   }
   fputs("endsolid\n", f);
@@ -196,26 +257,26 @@ int write_ply_ascii(const Parts& v, const char* path) {
   int st = S2M_OK;
   for (size_t k = 0; k < v.parts.size() && st == S2M_OK; ++k) {
     const s2m_result_info& m = v.parts[k].i;
-    st = parallel_write(f, m.n_vertices, 1u << 16, [&](uint64_t b, uint64_t e, std::string& out) {
+    st = parallel_write(f, m.n_vertices, 1u << 14, 6 * (kMaxF32Chars + 1), [&](uint64_t b, uint64_t e, char* o) {
       for (uint64_t i = b; i < e; ++i) {
-        const float* p = m.positions + 3 * i;
-        const float* n = m.normals + 3 * i;
-        rust_f32(p[0], out); out += ' '; rust_f32(p[1], out); out += ' '; rust_f32(p[2], out); out += ' ';
-        rust_f32(n[0], out); out += ' '; rust_f32(n[1], out); out += ' '; rust_f32(n[2], out); out += '\n';
+        o = rust_f32x3(m.positions + 3 * i, o, ' ');
+        o = rust_f32x3(m.normals + 3 * i, o, '\n');
       }
+      return o;
     });
   }
   for (size_t k = 0; k < v.parts.size() && st == S2M_OK; ++k) {
     const s2m_result_info& m = v.parts[k].i;
-    st = parallel_write(f, m.n_quads, 1u << 16, [&](uint64_t b, uint64_t e, std::string& out) {
-      char buf[128];
+    st = parallel_write(f, m.n_quads, 1u << 15, 2 * (3 * 11 + 2), [&](uint64_t b, uint64_t e, char* o) {
       for (uint64_t q = b; q < e; ++q)
         for (int t = 0; t < 2; ++t) {
           uint64_t tri[3];
           tri_of_quad(m, q, t, tri);
-          int n = snprintf(buf, sizeof buf, "3 %u %u %u\n", (unsigned)tri[0], (unsigned)tri[1], (unsigned)tri[2]);  // Triangle<u32>
-          out.append(buf, (size_t)n);
+          *o++ = '3';
+          for (int c = 0; c < 3; ++c) { *o++ = ' '; o = put_u32(o, (uint32_t)tri[c]); }  // Triangle<u32>
+          *o++ = '\n';
         }
+      return o;
     });
   }
   if (fclose(f) != 0 && st == S2M_OK) st = fail(S2M_ERR_IO, std::string("close failed for ") + path);
@@ -235,9 +296,7 @@ int write_stl_binary(const Parts& v, const char* path) {
   int st = S2M_OK;
   for (size_t k = 0; k < v.parts.size() && st == S2M_OK; ++k) {
     const s2m_result_info& m = v.parts[k].i;
-    st = parallel_write(f, m.n_quads, 1u << 16, [&](uint64_t b, uint64_t e, std::string& out) {
-      out.resize((size_t)(e - b) * 100);
-      char* o = &out[0];
+    st = parallel_write(f, m.n_quads, 1u << 16, 100, [&](uint64_t b, uint64_t e, char* o) {
       for (uint64_t q = b; q < e; ++q)
         for (int t = 0; t < 2; ++t) {
           uint64_t tri[3];
@@ -251,6 +310,7 @@ int write_stl_binary(const Parts& v, const char* path) {
           for (int c = 0; c < 3; ++c) { memcpy(o, p[c], 12); o += 12; }
           o[0] = o[1] = 0; o += 2;
         }
+      return o;
     });
   }
   if (fclose(f) != 0 && st == S2M_OK) st = fail(S2M_ERR_IO, std::string("close failed for ") + path);

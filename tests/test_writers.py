@@ -114,9 +114,7 @@ def test_z_slab_parts_write_the_whole_mesh(built, tmp_path):
     cut = int(np.median(z))
     lower = z < cut
     n0 = int(lower.sum())
-    owner_z = z[o.quads[:, 2].astype(np.int64)]   # a quad belongs to the cell that emits it: its q2 or q1 ...
-    emit = np.maximum.reduce([z[o.quads[:, k].astype(np.int64)] for k in range(4)])  # ... which has the largest z of the four
-    del owner_z
+    emit = np.maximum.reduce([z[o.quads[:, k].astype(np.int64)] for k in range(4)])  # a quad belongs to the slab of the cell that emits it: the largest z of its four
     q_low, q_up = o.quads[emit < cut], o.quads[emit >= cut]
     assert len(q_low) and len(q_up) and len(q_low) + len(q_up) == len(o.quads)
     first_halo = int(q_up.min())
@@ -138,6 +136,38 @@ def test_z_slab_parts_write_the_whole_mesh(built, tmp_path):
     with pytest.raises(s2m.S2mError) as e:   # PLY names vertices by index: whole mesh only
         s2m.write_mesh_arrays([(o.positions[n0:], o.normals[n0:], q_up, n0, halo)], tmp_path / "up.ply")
     assert "whole mesh" in str(e.value)
+    o.free()
+
+
+@pytest.mark.parametrize("threads,chunk", [(1, 5), (3, 7), (8, 1), (2, 1000)])
+def test_chunk_pipeline_keeps_the_order(built, tmp_path, monkeypatch, threads, chunk):
+    """the writers format chunks on worker threads into a ring of buffers and write them in order: any
+    thread count and chunk size gives the file of the (serial) oracle writer"""
+    o = oracle.mesh_run("torus", 24, 2.0)
+    monkeypatch.setenv("S2M_WRITER_THREADS", str(threads))
+    monkeypatch.setenv("S2M_WRITER_CHUNK", str(chunk))
+    for ext in ("stl", "ply"):
+        s2m.write_mesh_arrays([(o.positions, o.normals, o.quads)], tmp_path / f"a.{ext}")
+        (o.write_ply if ext == "ply" else o.write_stl)(tmp_path / f"ref.{ext}")
+        assert (tmp_path / f"a.{ext}").read_bytes() == (tmp_path / f"ref.{ext}").read_bytes()
+    s2m.write_mesh_arrays([(o.positions, None, o.quads)], tmp_path / "b.stl", binary_stl=True)
+    monkeypatch.delenv("S2M_WRITER_THREADS")
+    monkeypatch.delenv("S2M_WRITER_CHUNK")
+    s2m.write_mesh_arrays([(o.positions, None, o.quads)], tmp_path / "b0.stl", binary_stl=True)
+    assert (tmp_path / "b.stl").read_bytes() == (tmp_path / "b0.stl").read_bytes()
+    o.free()
+
+
+def test_writer_reports_a_full_disk(built, tmp_path):
+    import os
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    link = tmp_path / "full.stl"
+    os.symlink("/dev/full", link)
+    o = oracle.mesh_run("torus", 16, 2.0)
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.write_mesh_arrays([(o.positions, o.normals, o.quads)], link)
+    assert e.value.kind == "IO"
     o.free()
 
 
