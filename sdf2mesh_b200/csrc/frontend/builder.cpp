@@ -429,6 +429,13 @@ ExprP Builder::binary(Op op, ExprP a, ExprP b) {
   if (bitop && !(sk == Sk::I32 || sk == Sk::U32 || sk == Sk::AInt)) error("bit operation on non-integer operands");
   ExprP e = mk(Expr::Binary, is_cmp(op) ? Type::vec(Sk::Bool, n) : Type::vec(sk, n));
   e->op = op; e->args = {a, b};
+  if (aa && ba && is_cmp(op)) {
+    // a comparison of two abstract values has a concrete (bool) result, so nothing downstream would
+    // concretize its operands: it is a constant expression, evaluated in abstract precision here
+    ConstVal cv;
+    if (const_eval(*e, &cv)) return lit_from(cv);
+    e->args = {concretize(a), concretize(b)};
+  }
   return e;
 }
 

@@ -394,4 +394,67 @@ class WgslWriter {
 
 std::string emit_wgsl(const Module& m) { return WgslWriter(m).run(); }
 
+// A GLSL program may name things `f32`, `fn`, `target`, ...: legal there, not in WGSL.  naga's namer
+// (which writes the text the reference dumps with --debug-wgsl and compiles,
+// /root/reference/src/shadertoy.rs:169-194) appends `_` to such names; so does this pass, over every
+// name the writer prints: functions, variables, parameters, struct types and their fields.
+void make_names_wgsl_safe(Module& m) {
+  static const std::set<std::string> reserved = {
+      // keywords
+      "alias", "break", "case", "const", "const_assert", "continue", "continuing", "default", "diagnostic", "discard", "else",
+      "enable", "false", "fn", "for", "if", "let", "loop", "override", "requires", "return", "struct", "switch", "true", "var", "while",
+      // predeclared types and type generators
+      "bool", "f16", "f32", "i32", "u32", "vec2", "vec3", "vec4", "vec2f", "vec3f", "vec4f", "vec2i", "vec3i", "vec4i", "vec2u", "vec3u",
+      "vec4u", "vec2h", "vec3h", "vec4h", "mat2x2", "mat2x3", "mat2x4", "mat3x2", "mat3x3", "mat3x4", "mat4x2", "mat4x3", "mat4x4",
+      "mat2x2f", "mat2x3f", "mat2x4f", "mat3x2f", "mat3x3f", "mat3x4f", "mat4x2f", "mat4x3f", "mat4x4f", "mat2x2h", "mat3x3h", "mat4x4h",
+      "array", "atomic", "ptr", "sampler", "sampler_comparison", "texture_1d", "texture_2d", "texture_2d_array", "texture_3d",
+      "texture_cube", "texture_cube_array", "texture_multisampled_2d", "texture_storage_1d", "texture_storage_2d",
+      "texture_storage_2d_array", "texture_storage_3d", "texture_depth_2d", "texture_depth_2d_array", "texture_depth_cube",
+      "texture_depth_cube_array", "texture_depth_multisampled_2d", "bitcast",
+      // reserved words (WGSL specification, section "Reserved Words")
+      "NULL", "Self", "abstract", "active", "alignas", "alignof", "as", "asm", "asm_fragment", "async", "attribute", "auto", "await",
+      "become", "binding_array", "cast", "catch", "class", "co_await", "co_return", "co_yield", "coherent", "column_major", "common",
+      "compile", "compile_fragment", "concept", "const_cast", "consteval", "constexpr", "constinit", "crate", "debugger", "decltype",
+      "delete", "demote", "demote_to_helper", "do", "dynamic_cast", "enum", "explicit", "export", "extends", "extern", "external",
+      "fallthrough", "filter", "final", "finally", "friend", "from", "fxgroup", "get", "goto", "groupshared", "highp", "impl",
+      "implements", "import", "inline", "instanceof", "interface", "layout", "lowp", "macro", "macro_rules", "match", "mediump", "meta",
+      "mod", "module", "move", "mut", "mutable", "namespace", "new", "nil", "noexcept", "noinline", "nointerpolation", "noperspective",
+      "null", "nullptr", "of", "operator", "package", "packoffset", "partition", "pass", "patch", "pixelfragment", "precise",
+      "precision", "premerge", "priv", "protected", "pub", "public", "readonly", "ref", "regardless", "register", "reinterpret_cast",
+      "require", "resource", "restrict", "self", "set", "shared", "sizeof", "smooth", "snorm", "static", "static_assert", "static_cast",
+      "std", "subroutine", "super", "target", "template", "this", "thread_local", "throw", "trait", "try", "type", "typedef", "typeid",
+      "typename", "typeof", "union", "unless", "unorm", "unsafe", "unsized", "use", "using", "varying", "virtual", "volatile", "wgsl",
+      "where", "with", "writeonly", "yield"};
+  std::set<std::string> taken;
+  for (const auto& v : m.vars) taken.insert(v->name);
+  for (const auto& f : m.functions) taken.insert(f->name);
+  for (const auto& sd : m.structs) taken.insert(sd->name);
+  std::map<std::string, std::string> renamed;  // one new name per old name, so that equal names stay equal
+  auto safe = [&](std::string& name) {
+    if (!reserved.count(name)) return;
+    auto it = renamed.find(name);
+    if (it == renamed.end()) {
+      std::string n = name + "_";
+      while (taken.count(n)) n += "_";
+      taken.insert(n);
+      it = renamed.emplace(name, n).first;
+    }
+    name = it->second;
+  };
+  for (auto& v : m.vars) safe(v->name);
+  for (auto& f : m.functions)
+    if (!f->is_entry && !f->builtin_lib) safe(f->name);
+  for (auto& sd : m.structs) {
+    safe(sd->name);
+    std::set<std::string> fields(sd->field_names.begin(), sd->field_names.end());
+    for (std::string& fld : sd->field_names)
+      if (reserved.count(fld)) {
+        std::string n = fld + "_";
+        while (fields.count(n)) n += "_";
+        fields.insert(n);
+        fld = n;
+      }
+  }
+}
+
 }  // namespace s2m_frontend

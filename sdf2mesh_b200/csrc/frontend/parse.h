@@ -12,4 +12,5 @@ int optimize_module(Module& m);  // returns the number of rewrites applied
 std::string emit_cuda(const Module& m);
 std::string emit_cuda_packed(const Module& m);  // "" when the module has no packed (f32x2) form
 std::string emit_wgsl(const Module& m);
+void make_names_wgsl_safe(Module& m);  // GLSL identifiers that WGSL reserves get a `_` suffix, as naga's namer does
 }  // namespace s2m_frontend

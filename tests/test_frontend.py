@@ -1129,3 +1129,41 @@ def test_packed_form_was_cross_checked(built):
     assert len(st["shaders"]) >= 20
     assert st["pairs"] > 100_000
     assert len(st["unpackable"]) <= 10
+
+
+def test_comparison_of_two_abstract_constants(built):
+    """`(-2.5) == (-1.0)` has a concrete (bool) type but abstract operands: it folds in abstract precision
+    (found by tests/test_frontend_fuzz.py: the literals used to reach the emitter unconverted)"""
+    sh = s2m.Sdf3DShader.from_source("fn sdf3d(p: vec3f) -> f32 { return select(p.y, p.z, ((-2.5) == (-1.0))) + select(1.0, p.x, 1 < 2) "
+                                     "+ select(0.0, 8.0, 0.1 + 0.2 == 0.3); }")
+    pts = points(2.0, 500)
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+    # 0.1 + 0.2 == 0.3 is false in abstract-float (f64) arithmetic, true in f32
+    assert f32_equal(got, (pts[:, 1] + pts[:, 0]).astype(np.float32)).all()
+
+
+def test_glsl_names_that_wgsl_reserves(built, tmp_path):
+    """GLSL identifiers that are WGSL keywords, reserved words or predeclared types get a `_` suffix in the
+    WGSL text (naga's namer does the same), so the dumped WGSL is valid and parses back"""
+    glsl = textwrap.dedent("""\
+        #version 450 core
+        struct type { float fn; float ok; };
+        float f16(vec3 target) { return target.x * 2.0; }
+        float sdf(vec3 p) {
+            float filter = p.y, let = 0.5, f32 = p.z, f32_ = 1.0;
+            type self = type(filter, let);
+            return f16(p) + self.fn * self.ok + f32 * f32_;
+        }
+        void main() {}
+        """)
+    wgsl = s2m.convert_glsl_to_wgsl(glsl)
+    for name in ("struct type_ ", "fn_: f32", "fn f16_(target_: vec3<f32>)", "var filter_:", "var let_:", "var f32__:", "var self_: type_", "self_.fn_ * self_.ok"):
+        assert name in wgsl, (name, wgsl)
+    f = tmp_path / "r.frag"
+    f.write_text(glsl)
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(f, "sdf")
+    pts = points(2.0, 500)
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+    x, y, z = (pts[:, i] for i in range(3))
+    want = ((x * np.float32(2) + (y * np.float32(0.5)).astype(np.float32)).astype(np.float32) + (z * np.float32(1)).astype(np.float32)).astype(np.float32)
+    assert f32_equal(got, want).all()

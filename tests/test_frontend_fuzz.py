@@ -1,0 +1,358 @@
+"""Differential test of the front-end on generated programs (no GPU).
+
+A seeded generator builds typed expression trees (f32, vec2, vec3) over the exactly-defined part of the
+shading languages -- arithmetic, comparisons / select, min max clamp mix step smoothstep, floor ceil
+trunc round fract sign abs sqrt, dot length distance normalize cross reflect, constructors and
+swizzles -- prints every tree as WGSL and as GLSL, and evaluates it in numpy with one IEEE f32
+operation per source operation (the semantics DESIGN.md section 3 pins; csrc/s2m_math.h, s2m_vec.h).
+The front-end's CUDA C++ for the WGSL text and for the GLSL text (through the GLSL -> naga-IR-shaped
+path the reference takes, /root/reference/src/shadertoy.rs:169-194), compiled for the host, must
+reproduce the numpy values bit for bit.  host_eval.eval_points also runs the packed (f32x2) form of
+each program against the scalar one.
+"""
+import numpy as np
+import pytest
+
+import sdf2mesh_b200 as s2m
+from sdf2mesh_b200 import _capi
+from tests.support import host_eval
+
+F = np.float32
+CONSTS = [0.0, 0.5, 1.0, 1.5, 2.0, 0.25, 3.0, 0.125, -0.75, -1.0, 0.375, 4.0, -2.5]
+DIM = {"f": 1, "v2": 2, "v3": 3}
+
+
+# ------------------------------------------------------------------ pinned semantics in numpy (arrays of f32)
+def _bits(a):
+    return np.ascontiguousarray(a, F).view(np.uint32)
+
+
+def s_min(a, b):
+    eq = np.where(a == b, (_bits(a) | _bits(b)).view(F), np.where(a < b, a, b))   # equal: -0 wins
+    return np.where(np.isnan(a), b, np.where(np.isnan(b), a, eq)).astype(F)
+
+
+def s_max(a, b):
+    eq = np.where(a == b, (_bits(a) & _bits(b)).view(F), np.where(a > b, a, b))   # equal: +0 wins
+    return np.where(np.isnan(a), b, np.where(np.isnan(b), a, eq)).astype(F)
+
+
+def s_clamp(x, lo, hi):
+    return s_min(s_max(x, lo), hi)
+
+
+def s_mix(a, b, t):
+    return (a * (F(1) - t) + b * t).astype(F)
+
+
+def s_sign(x):
+    return np.where(x > 0, F(1), np.where(x < 0, F(-1), np.where(x == 0, F(0), x))).astype(F)
+
+
+def s_smoothstep(lo, hi, x):
+    t = s_clamp(((x - lo) / (hi - lo)).astype(F), F(0), F(1))
+    return (t * t * (F(3) - F(2) * t)).astype(F)
+
+
+def s_dot(a, b):
+    acc = (a[..., 0] * b[..., 0]).astype(F)
+    for k in range(1, a.shape[-1]):
+        acc = (acc + (a[..., k] * b[..., k]).astype(F)).astype(F)
+    return acc
+
+
+def s_length(a):
+    return np.sqrt(s_dot(a, a)).astype(F)
+
+
+def s_cross(a, b):
+    return np.stack([a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1], a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+                     a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]], axis=-1).astype(F)
+
+
+def bc(x, like):
+    """scalar (N,) against vector (N,k)"""
+    return x[..., None] if like.ndim == 2 and x.ndim == 1 else x
+
+
+# ------------------------------------------------------------------ expression trees
+class Node:
+    def __init__(self, op, ty, kids=(), arg=None):
+        self.op, self.ty, self.kids, self.arg = op, ty, tuple(kids), arg
+
+
+def gen(rng, ty, depth):
+    """a random tree of type ty ('f' | 'v2' | 'v3' | 'b')"""
+    r = rng.random()
+    if ty == "b":
+        a, b = gen(rng, "f", depth - 1), gen(rng, "f", depth - 1)
+        return Node(rng.choice(["<", "<=", ">", ">=", "==", "!="]), "b", (a, b))
+    if depth <= 0 or r < 0.12:
+        if ty == "f":
+            return Node("comp", "f", (), int(rng.integers(3))) if rng.random() < 0.65 else Node("const", "f", (), float(rng.choice(CONSTS)))
+        if rng.random() < 0.7:
+            idx = tuple(int(i) for i in rng.integers(0, 3, DIM[ty]))
+            return Node("qswz", ty, (), idx)
+        return Node("ctor", ty, tuple(Node("const", "f", (), float(rng.choice(CONSTS))) for _ in range(DIM[ty])))
+    d = depth - 1
+    if ty == "f":
+        choices = ["+", "-", "*", "/", "neg", "abs", "min", "max", "clamp", "mix", "floor", "ceil", "trunc", "round", "fract", "sign",
+                   "step", "sqrtabs", "length", "dot", "distance", "pick", "select", "smoothstep", "fmod"]
+        op = rng.choice(choices)
+        if op in ("+", "-", "*", "/", "min", "max", "step", "fmod"):
+            return Node(op, "f", (gen(rng, "f", d), gen(rng, "f", d)))
+        if op in ("neg", "abs", "floor", "ceil", "trunc", "round", "fract", "sign", "sqrtabs"):
+            return Node(op, "f", (gen(rng, "f", d),))
+        if op in ("clamp", "mix", "smoothstep"):
+            return Node(op, "f", (gen(rng, "f", d), gen(rng, "f", d), gen(rng, "f", d)))
+        if op == "length":
+            return Node(op, "f", (gen(rng, rng.choice(["v2", "v3"]), d),))
+        if op in ("dot", "distance"):
+            vt = rng.choice(["v2", "v3"])
+            return Node(op, "f", (gen(rng, vt, d), gen(rng, vt, d)))
+        if op == "pick":
+            vt = rng.choice(["v2", "v3"])
+            return Node(op, "f", (gen(rng, vt, d),), int(rng.integers(DIM[vt])))
+        return Node("select", "f", (gen(rng, "f", d), gen(rng, "f", d), gen(rng, "b", d)))
+    choices = ["+", "-", "*", "/", "vs*", "sv*", "vs/", "vs+", "neg", "abs", "min", "max", "clamp", "mixs", "mixv", "floor", "fract", "sign",
+               "step", "normalize", "reflect", "ctor", "swz", "select"]
+    if ty == "v3":
+        choices += ["cross", "ctor21", "ctor12", "widen"]
+    else:
+        choices += ["narrow"]
+    op = rng.choice(choices)
+    if op in ("+", "-", "*", "/", "min", "max", "step", "reflect", "cross"):
+        return Node(op, ty, (gen(rng, ty, d), gen(rng, ty, d)))
+    if op in ("vs*", "vs/", "vs+"):
+        return Node(op, ty, (gen(rng, ty, d), gen(rng, "f", d)))
+    if op == "sv*":
+        return Node(op, ty, (gen(rng, "f", d), gen(rng, ty, d)))
+    if op in ("neg", "abs", "floor", "fract", "sign", "normalize"):
+        return Node(op, ty, (gen(rng, ty, d),))
+    if op in ("clamp", "mixv"):
+        return Node(op, ty, (gen(rng, ty, d), gen(rng, ty, d), gen(rng, ty, d)))
+    if op == "mixs":
+        return Node(op, ty, (gen(rng, ty, d), gen(rng, ty, d), gen(rng, "f", d)))
+    if op == "ctor":
+        return Node(op, ty, tuple(gen(rng, "f", d) for _ in range(DIM[ty])))
+    if op == "swz":
+        return Node(op, ty, (gen(rng, ty, d),), tuple(int(i) for i in rng.integers(0, DIM[ty], DIM[ty])))
+    if op == "select":
+        return Node(op, ty, (gen(rng, ty, d), gen(rng, ty, d), gen(rng, "b", d)))
+    if op == "ctor21":
+        return Node(op, "v3", (gen(rng, "v2", d), gen(rng, "f", d)))
+    if op == "ctor12":
+        return Node(op, "v3", (gen(rng, "f", d), gen(rng, "v2", d)))
+    if op == "widen":   # v2.xyx-style swizzle to a wider vector
+        return Node(op, "v3", (gen(rng, "v2", d),), tuple(int(i) for i in rng.integers(0, 2, 3)))
+    return Node("narrow", "v2", (gen(rng, "v3", d),), tuple(int(i) for i in rng.integers(0, 3, 2)))
+
+
+XYZ = "xyz"
+
+
+def lit(v):
+    s = repr(float(v))
+    return s if ("." in s or "e" in s) else s + ".0"
+
+
+def show(n, glsl):
+    """source text of a tree; fully parenthesised except where the test wants precedence to matter"""
+    k = [show(c, glsl) for c in n.kids]
+    V = {"v2": "vec2" if glsl else "vec2f", "v3": "vec3" if glsl else "vec3f"}
+    op = n.op
+    if op == "comp":
+        return f"q.{XYZ[n.arg]}"
+    if op == "const":
+        return lit(n.arg) if n.arg >= 0 else f"({lit(n.arg)})"
+    if op == "qswz":
+        return "q." + "".join(XYZ[i] for i in n.arg)
+    if op in ("ctor", "ctor21", "ctor12"):
+        return f"{V[n.ty]}({', '.join(k)})"
+    if op in ("+", "-", "*", "/"):
+        return f"({k[0]} {op} {k[1]})"
+    if op in ("vs*", "sv*"):
+        return f"({k[0]} * {k[1]})"
+    if op == "vs/":
+        return f"({k[0]} / {k[1]})"
+    if op == "vs+":
+        return f"({k[0]} + {k[1]})"
+    if op in ("<", "<=", ">", ">=", "==", "!="):
+        return f"({k[0]} {op} {k[1]})"
+    if op == "neg":
+        return f"(-{k[0]})"
+    if op == "sqrtabs":
+        return f"sqrt(abs({k[0]}))"
+    if op == "fmod":
+        return f"({k[0]} - {k[1]} * trunc({k[0]} / {k[1]}))" if glsl else f"({k[0]} % {k[1]})"
+    if op in ("mixs", "mixv"):
+        if op == "mixs" and not glsl:
+            return f"mix({k[0]}, {k[1]}, {V[n.ty]}({k[2]}))"   # exercise both: WGSL splat, GLSL mix(v, v, float)
+        return f"mix({k[0]}, {k[1]}, {k[2]})"
+    if op == "pick":
+        return f"{k[0]}.{XYZ[n.arg]}"
+    if op in ("swz", "widen", "narrow"):
+        return f"{k[0]}." + "".join(XYZ[i] for i in n.arg)
+    if op == "select":
+        return f"({k[2]} ? {k[1]} : {k[0]})" if glsl else f"select({k[0]}, {k[1]}, {k[2]})"
+    if op == "round":
+        return f"roundEven({k[0]})" if glsl else f"round({k[0]})"
+    return f"{op}({', '.join(k)})"
+
+
+def evaluate(n, q):
+    """numpy value of a tree at the points q (N,3): (N,) for f / b, (N,k) for vectors"""
+    k = [evaluate(c, q) for c in n.kids]
+    op = n.op
+    N = q.shape[0]
+    with np.errstate(all="ignore"):
+        if op == "comp":
+            return q[:, n.arg]
+        if op == "const":
+            return np.full(N, n.arg, F)
+        if op == "qswz":
+            return q[:, list(n.arg)]
+        if op == "ctor":
+            return np.stack(k, axis=-1).astype(F)
+        if op == "ctor21":
+            return np.concatenate([k[0], k[1][:, None]], axis=-1).astype(F)
+        if op == "ctor12":
+            return np.concatenate([k[0][:, None], k[1]], axis=-1).astype(F)
+        if op in ("+", "vs+"):
+            return (k[0] + bc(k[1], k[0])).astype(F)
+        if op == "-":
+            return (k[0] - k[1]).astype(F)
+        if op in ("*", "vs*"):
+            return (k[0] * bc(k[1], k[0])).astype(F)
+        if op == "sv*":
+            return (bc(k[0], k[1]) * k[1]).astype(F)
+        if op in ("/", "vs/"):
+            return (k[0] / bc(k[1], k[0])).astype(F)
+        if op in ("<", "<=", ">", ">=", "==", "!="):
+            return {"<": np.less, "<=": np.less_equal, ">": np.greater, ">=": np.greater_equal, "==": np.equal, "!=": np.not_equal}[op](k[0], k[1])
+        if op == "neg":
+            return (-k[0]).astype(F)
+        if op == "abs":
+            return np.abs(k[0]).astype(F)
+        if op == "min":
+            return s_min(k[0], k[1])
+        if op == "max":
+            return s_max(k[0], k[1])
+        if op == "clamp":
+            return s_clamp(k[0], k[1], k[2])
+        if op in ("mix", "mixv"):
+            return s_mix(k[0], k[1], k[2])
+        if op == "mixs":
+            return s_mix(k[0], k[1], bc(k[2], k[0]))
+        if op == "floor":
+            return np.floor(k[0]).astype(F)
+        if op == "ceil":
+            return np.ceil(k[0]).astype(F)
+        if op == "trunc":
+            return np.trunc(k[0]).astype(F)
+        if op == "round":
+            return np.rint(k[0]).astype(F)
+        if op == "fract":
+            return (k[0] - np.floor(k[0])).astype(F)
+        if op == "sign":
+            return s_sign(k[0])
+        if op == "step":
+            return np.where(k[0] <= k[1], F(1), F(0)).astype(F)
+        if op == "sqrtabs":
+            return np.sqrt(np.abs(k[0])).astype(F)
+        if op == "smoothstep":
+            return s_smoothstep(k[0], k[1], k[2])
+        if op == "fmod":
+            return (k[0] - (k[1] * np.trunc((k[0] / k[1]).astype(F))).astype(F)).astype(F)
+        if op == "length":
+            return s_length(k[0])
+        if op == "dot":
+            return s_dot(k[0], k[1])
+        if op == "distance":
+            return s_length((k[0] - k[1]).astype(F))
+        if op == "normalize":
+            return (k[0] / s_length(k[0])[:, None]).astype(F)
+        if op == "cross":
+            return s_cross(k[0], k[1])
+        if op == "reflect":   # i - (2*dot(n,i))*n
+            return (k[0] - ((F(2) * s_dot(k[1], k[0])).astype(F)[:, None] * k[1]).astype(F)).astype(F)
+        if op == "pick":
+            return k[0][:, n.arg]
+        if op in ("swz", "widen", "narrow"):
+            return k[0][:, list(n.arg)]
+        if op == "select":
+            c = k[2] if k[0].ndim == 1 else k[2][:, None]
+            return np.where(c, k[1], k[0]).astype(F)
+    raise AssertionError(op)
+
+
+def program(trees, glsl):
+    fns = []
+    for i, t in enumerate(trees):
+        body = show(t, glsl)
+        fns.append(f"float g{i}(vec3 q) {{ return {body}; }}" if glsl else f"fn g{i}(q: vec3f) -> f32 {{ return {body}; }}")
+    if glsl:
+        sel = "\n".join(f"    if (k == {i}) return g{i}(q);" for i in range(len(trees)))
+        main = ("float sdf(vec3 p) {\n    int k = int(floor(p.z));\n    vec3 q = vec3(p.x, p.y, p.z - float(k));\n" + sel +
+                "\n    return 0.0;\n}\nvoid main() {}\n")
+        return "#version 450 core\n" + "\n".join(fns) + "\n" + main
+    sel = "\n".join(f"        case {i}: {{ return g{i}(q); }}" for i in range(len(trees)))
+    main = ("fn sdf3d(p: vec3f) -> f32 {\n    let k = i32(floor(p.z));\n    let q = vec3f(p.x, p.y, p.z - f32(k));\n    switch k {\n" + sel +
+            "\n        default: { return 0.0; }\n    }\n}\n")
+    return "\n".join(fns) + "\n" + main
+
+
+N_FUNCS = 48
+PTS_PER_FUNC = 160
+
+
+def sample_points(rng, n_funcs):
+    """PTS_PER_FUNC points per function: selector k in the integer part of z; q spans magnitudes and signs, with
+    exact ties (multiples of 0.5) mixed in so that min/max/step/round/select see equal operands"""
+    n = n_funcs * PTS_PER_FUNC
+    q = rng.uniform(-2.0, 2.0, (n, 3)).astype(F)
+    tie = rng.random((n, 3)) < 0.25
+    q[tie] = (np.round(q[tie] * 2) / 2).astype(F)
+    q[:, 2] = np.abs(q[:, 2]) % F(1.0)          # fractional part carried by z
+    k = np.repeat(np.arange(n_funcs), PTS_PER_FUNC)
+    p = q.copy()
+    p[:, 2] = (q[:, 2] + k.astype(F)).astype(F)
+    q[:, 2] = (p[:, 2] - k.astype(F)).astype(F)   # what the program recomputes (exact for these magnitudes)
+    return p, q, k
+
+
+def same(a, b):
+    return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_generated_programs_wgsl_and_glsl_equal_numpy(built, seed):
+    rng = np.random.default_rng(seed)
+    trees = [gen(rng, "f", int(rng.integers(2, 6))) for _ in range(N_FUNCS)]
+    p, q, k = sample_points(rng, N_FUNCS)
+    want = np.zeros(p.shape[0], F)
+    for i, t in enumerate(trees):
+        m = k == i
+        want[m] = evaluate(t, q[m])
+    assert np.isfinite(want).mean() > 0.5   # the programs are not all-NaN
+    for glsl in (False, True):
+        text = program(trees, glsl)
+        sh = s2m.Sdf3DShader.from_source(text, _capi.SRC_GLSL_FRAGMENT if glsl else _capi.SRC_SDF3D, "sdf")
+        body = sh.lower_to_cuda()
+        host_eval.register_packed(body, sh.lower_to_cuda_packed())
+        got = host_eval.eval_points(body, p)
+        ok = same(got, want)
+        if not ok.all():
+            bad = int(np.flatnonzero(~ok)[0])
+            i = int(k[bad])
+            raise AssertionError(f"{'GLSL' if glsl else 'WGSL'} seed {seed} g{i}: {show(trees[i], glsl)}\n at q = {q[bad].tolist()}: "
+                                 f"got {got[bad]!r}, numpy {want[bad]!r} ({int((~ok).sum())} mismatches in all)")
+
+
+def test_generated_program_compiles_for_sm100a(built):
+    """one generated program through NVRTC (no device needed): the emitter's output is valid device code too"""
+    rng = np.random.default_rng(5)
+    trees = [gen(rng, "f", 4) for _ in range(12)]
+    for glsl in (False, True):
+        sh = s2m.Sdf3DShader.from_source(program(trees, glsl), _capi.SRC_GLSL_FRAGMENT if glsl else _capi.SRC_SDF3D, "sdf")
+        assert sh.create_shader_module(None).cubin_size > 0
