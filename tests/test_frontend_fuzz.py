@@ -81,8 +81,32 @@ class Node:
         self.op, self.ty, self.kids, self.arg = op, ty, tuple(kids), arg
 
 
-def gen(rng, ty, depth):
-    """a random tree of type ty ('f' | 'v2' | 'v3' | 'b')"""
+def gen(rng, ty, depth, env=None):
+    """a random tree of type ty ('f' | 'v2' | 'v3' | 'b'); env = {"f": [names], "v3": [names], "trig": bool}
+    adds local variables as leaves and (trig) sin / cos of shared arguments"""
+    if env is not None:
+        return _gen_env(rng, ty, depth, env)
+    return _gen(rng, ty, depth)
+
+
+def _gen_env(rng, ty, depth, env):
+    """gen() with env: the recursion of _gen below, with some leaves replaced by variables afterwards"""
+    t = _gen(rng, ty, depth)
+
+    def patch(n):
+        kids = tuple(patch(c) for c in n.kids)
+        if n.op == "comp" and env.get("f") and rng.random() < 0.6:
+            return Node("var", "f", (), str(rng.choice(env["f"])))
+        if n.op == "qswz" and n.ty == "v3" and env.get("v3") and rng.random() < 0.6:
+            return Node("var", "v3", (), str(rng.choice(env["v3"])))
+        if n.op == "sqrtabs" and env.get("trig"):   # sin(e) * cos(e): the optimizer pairs them
+            return Node("sincos", "f", kids)
+        return Node(n.op, n.ty, kids, n.arg)
+    return patch(t)
+
+
+def _gen(rng, ty, depth):
+    gen = _gen
     r = rng.random()
     if ty == "b":
         a, b = gen(rng, "f", depth - 1), gen(rng, "f", depth - 1)
@@ -163,6 +187,10 @@ def show(n, glsl):
     op = n.op
     if op == "comp":
         return f"q.{XYZ[n.arg]}"
+    if op == "var":
+        return n.arg
+    if op == "sincos":
+        return f"(sin({k[0]}) * cos({k[0]}))"
     if op == "const":
         return lit(n.arg) if n.arg >= 0 else f"({lit(n.arg)})"
     if op == "qswz":
@@ -356,3 +384,80 @@ def test_generated_program_compiles_for_sm100a(built):
     for glsl in (False, True):
         sh = s2m.Sdf3DShader.from_source(program(trees, glsl), _capi.SRC_GLSL_FRAGMENT if glsl else _capi.SRC_SDF3D, "sdf")
         assert sh.create_shader_module(None).cubin_size > 0
+
+
+# ------------------------------------------------------------------ statements: the IR optimizer against itself
+def gen_loop_function(rng, i):
+    """GLSL: locals, a counted loop whose body is `prefix; if (c) continue|break; rest` with assignments,
+    compound assignments, if/else and sin/cos pairs -- the shapes frontend/optimize.cpp rewrites
+    (continue -> break, sin/cos pairing) next to shapes it must leave alone (prefix reads what it
+    writes, condition or prefix uses the counter, the counter lives on after the loop)"""
+    env = {"f": ["a", "b", "acc"], "v3": ["z", "q"], "trig": True}
+    pure = {"f": ["b"], "v3": ["z", "q"], "trig": True}   # what an idempotent prefix writing `a` may read
+
+    def e(ty, depth, en=env):
+        return show(gen(rng, ty, depth, en), True)
+
+    def assign(en=env):
+        r = rng.random()
+        if r < 0.3:
+            return f"a = {e('f', 2, en)};"
+        if r < 0.45:
+            return f"b {rng.choice(['=', '+=', '*=', '-='])} {e('f', 2, en)};"
+        if r < 0.6:
+            return f"acc += {e('f', 2, en)};"
+        if r < 0.8:
+            return f"z = {e('v3', 2, en)};"
+        if r < 0.9:
+            return f"z.{rng.choice(['x', 'y', 'z'])} = {e('f', 2, en)};"
+        return f"if ({e('b', 2, en)}) {{ a = {e('f', 1, en)}; }} else {{ z = {e('v3', 1, en)}; acc += 0.5; }}"
+
+    n_iter = int(rng.integers(2, 7))
+    shape = rng.random()
+    uses_counter = shape > 0.8
+    outer_counter = 0.7 < shape <= 0.8
+    if shape < 0.55:   # the rewritable shape: a = f(b, z, q); if (c(a, b, z)) continue; rest changes b, z, acc
+        prefix = [f"a = {e('f', 3, pure)};"] + ([f"float t = {e('f', 2, pure)};", "a = a * 0.5 + t;"] if rng.random() < 0.4 else [])
+        cond = show(gen(rng, "b", 2, {"f": ["a", "b"], "v3": ["z"], "trig": False}), True)
+    else:
+        prefix = [assign() for _ in range(int(rng.integers(1, 4)))]
+        cond = e("b", 2)
+    if uses_counter:
+        prefix.append("a += float(i) * 0.25;")
+    jump = "continue" if rng.random() < 0.8 else "break"
+    rest = [assign() for _ in range(int(rng.integers(1, 4)))]
+    if rng.random() < 0.3:
+        rest.insert(int(rng.integers(0, len(rest) + 1)), f"if ({e('b', 1)}) continue;")
+    body = "\n        ".join(prefix + [f"if ({cond}) {jump};"] + rest)
+    head = f"int i = 0;\n    for (; i < {n_iter}; i++)" if outer_counter else f"for (int i = 0; i < {n_iter}; i++)"
+    tail = " + float(i)" if outer_counter else ""
+    return (f"float g{i}(vec3 q) {{\n    float a = {e('f', 2, {'f': [], 'v3': ['q'], 'trig': False})};\n    float b = q.y * 0.5;\n    float acc = 0.0;\n    vec3 z = q;\n"
+            f"    {head} {{\n        {body}\n    }}\n    return a + b + acc + dot(z, vec3(1.0, 0.5, 0.25)){tail};\n}}")
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_generated_loops_optimized_equals_unoptimized(built, monkeypatch, seed):
+    rng = np.random.default_rng(seed)
+    n = 40
+    fns = [gen_loop_function(rng, i) for i in range(n)]
+    sel = "\n".join(f"    if (k == {i}) return g{i}(q);" for i in range(n))
+    text = ("#version 450 core\n" + "\n".join(fns) + "\nfloat sdf(vec3 p) {\n    int k = int(floor(p.z));\n    vec3 q = vec3(p.x, p.y, p.z - float(k));\n" +
+            sel + "\n    return 0.0;\n}\nvoid main() {}\n")
+    p, _, _ = sample_points(rng, n)
+    monkeypatch.delenv("S2M_NO_IR_OPT", raising=False)
+    sh = s2m.Sdf3DShader.from_source(text, _capi.SRC_GLSL_FRAGMENT, "sdf")
+    opt = sh.lower_to_cuda()
+    host_eval.register_packed(opt, sh.lower_to_cuda_packed())
+    monkeypatch.setenv("S2M_NO_IR_OPT", "1")
+    plain = s2m.Sdf3DShader.from_source(text, _capi.SRC_GLSL_FRAGMENT, "sdf").lower_to_cuda()
+    monkeypatch.delenv("S2M_NO_IR_OPT", raising=False)
+    # the optimizer did something on this program, and not everywhere
+    n_loops = plain.count("for (") + plain.count("while (")
+    assert 0 < opt.count("break;") - plain.count("break;") < n_loops
+    assert opt.count("f_sincos_pair(") > 0 and "f_sincos_pair(" not in plain
+    a, b = host_eval.eval_points(opt, p), host_eval.eval_points(plain, p)
+    ok = same(a, b)
+    assert np.isfinite(b).mean() > 0.3
+    if not ok.all():
+        bad = int(np.flatnonzero(~ok)[0])
+        raise AssertionError(f"seed {seed}: optimized {a[bad]!r} != unoptimized {b[bad]!r} at p = {p[bad].tolist()} in\n{fns[bad // PTS_PER_FUNC]}")
