@@ -157,3 +157,48 @@ def mesh_slab(ctx, module, params, z_begin: int, z_end: int, gather=allgather_co
     base = exclusive_bases(counts)[rank]
     res.finish(base)
     return res, base, counts
+
+
+def write_mesh_gathered(positions, normals, quads, global_vertex_base: int, path, binary_stl: bool = False,
+                        group=None, dst: int = 0) -> None:
+    """One STL / PLY file from a one-process-per-GPU run: every rank hands in its z-slab as it sits in
+    pinned host memory after finish(base) -- own vertices, quads with global indices -- and rank `dst`
+    writes the file the single-GPU run would have written (engine.write_mesh_arrays; slabs are
+    consecutive in rank order, so no halo copies are needed).
+
+    The arrays travel host to host, so `group` must be a gloo group when the default backend is nccl
+    (`torch.distributed.new_group(backend="gloo")`); sizes first, then three point-to-point messages
+    per rank.  The reference has one device and one writer (mesh.rs:182); this is its multi-process form."""
+    import torch
+    import torch.distributed as dist
+    from . import engine
+    pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals if normals is not None else np.zeros_like(pos), np.float32).reshape(-1, 3)
+    q = np.ascontiguousarray(quads, np.uint64).reshape(-1, 4)
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        engine.write_mesh_arrays([(pos, nrm, q, int(global_vertex_base))], path, binary_stl)
+        return
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = torch.tensor([pos.shape[0], q.shape[0], int(global_vertex_base)], dtype=torch.int64)
+    sizes = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(sizes, mine, group=group)
+    dst_global = dist.get_global_rank(group, dst) if group is not None else dst
+    if rank != dst:
+        for a in (pos, nrm, q.view(np.int64)):
+            if a.size:
+                dist.send(torch.from_numpy(a.reshape(-1)), dst_global, group=group)
+    else:
+        parts = []
+        for r in range(world):
+            nv, nq, base = (int(x) for x in sizes[r].tolist())
+            if r == rank:
+                parts.append((pos, nrm, q, base))
+                continue
+            src = dist.get_global_rank(group, r) if group is not None else r
+            bufs = [torch.empty(nv * 3, dtype=torch.float32), torch.empty(nv * 3, dtype=torch.float32), torch.empty(nq * 4, dtype=torch.int64)]
+            for b in bufs:
+                if b.numel():
+                    dist.recv(b, src, group=group)
+            parts.append((bufs[0].numpy().reshape(-1, 3), bufs[1].numpy().reshape(-1, 3), bufs[2].numpy().view(np.uint64).reshape(-1, 4), base))
+        engine.write_mesh_arrays(parts, path, binary_stl)
+    dist.barrier(group=group)

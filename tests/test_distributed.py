@@ -64,6 +64,57 @@ def test_count_exchange_gloo_world2():
     assert out[1] == (1, [1007, 2007], 1007, [0, 300, 511])
 
 
+def _writer_worker(rank, world, port, path, q):
+    """each rank owns a z-slab of one oracle mesh, split the way the engine's slabs are (own vertices,
+    quads of the cells it emits, global indices); rank 0 writes"""
+    import torch.distributed as dist
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = oracle.mesh_run("torus", 32, 2.0)
+    z = (o.keys >> np.uint64(32)).astype(np.int64)
+    cuts = [0] + [int(np.quantile(z, (g + 1) / world)) for g in range(world - 1)] + [1 << 20]
+    emit = np.maximum.reduce([z[o.quads[:, k].astype(np.int64)] for k in range(4)])
+    own_v = (z >= cuts[rank]) & (z < cuts[rank + 1])
+    own_q = (emit >= cuts[rank]) & (emit < cuts[rank + 1])
+    base = int((z < cuts[rank]).sum())
+    for ext, binary in (("stl", False), ("ply", False), ("bin.stl", True)):
+        D.write_mesh_gathered(o.positions[own_v], o.normals[own_v], o.quads[own_q], base, f"{path}.{ext}", binary_stl=binary)
+    q.put((rank, int(own_v.sum()), int(own_q.sum())))
+    o.free()
+    dist.destroy_process_group()
+
+
+def test_gathered_writer_gloo_world2(tmp_path):
+    """one-process-per-GPU output path on CPU: two ranks' z-slabs -> the file of the whole mesh"""
+    import oracle
+    import sdf2mesh_b200 as s2m
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_writer_worker, args=(r, 2, port, str(tmp_path / "g"), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o = oracle.mesh_run("torus", 32, 2.0)
+    assert out[0][1] > 0 and out[1][1] > 0 and out[0][1] + out[1][1] == len(o.keys) and out[0][2] + out[1][2] == len(o.quads)
+    o.write_stl(tmp_path / "ref.stl")
+    o.write_ply(tmp_path / "ref.ply")
+    assert (tmp_path / "g.stl").read_bytes() == (tmp_path / "ref.stl").read_bytes()
+    assert (tmp_path / "g.ply").read_bytes() == (tmp_path / "ref.ply").read_bytes()
+    s2m.write_mesh_arrays([(o.positions, None, o.quads)], tmp_path / "ref.bin.stl", binary_stl=True)
+    assert (tmp_path / "g.bin.stl").read_bytes() == (tmp_path / "ref.bin.stl").read_bytes()
+    o.free()
+
+
 def test_rebalance_from_measured_times():
     b = [0, 406, 678, 864, 1023, 1183, 1368, 1640, 2047]
     t = [6.75, 8.3, 10.7, 10.3, 10.45, 10.1, 7.9, 6.8]
