@@ -122,6 +122,7 @@ extern "C" {
     pub fn s2m_module_compile(ctx: *mut s2m_ctx, shader: *const s2m_shader, flags: u32, out: *mut *mut s2m_module) -> c_int;
     pub fn s2m_module_log(m: *const s2m_module) -> *const c_char;
     pub fn s2m_module_cuda_source(m: *const s2m_module) -> *const c_char;
+    pub fn s2m_module_instantiate(compiled: *const s2m_module, ctx: *mut s2m_ctx, out: *mut *mut s2m_module) -> c_int;
     pub fn s2m_module_cubin(m: *const s2m_module, data: *mut *const c_void, size: *mut usize) -> c_int;
     pub fn s2m_module_cubin_part(m: *const s2m_module, part: c_int, data: *mut *const c_void, size: *mut usize) -> c_int;
     pub fn s2m_module_compile_ms(m: *const s2m_module, which: c_int) -> c_double;

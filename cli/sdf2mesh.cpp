@@ -161,10 +161,25 @@ int run_multi_gpu(const Args& a, s2m_mesh_params params) {
     else cv.wait(lk, [&] { return generation != gen; });
   };
   std::atomic<bool> failed{false};
+  // one NVRTC compile for all GPUs, on this thread, while the workers bring their contexts up
+  s2m_module* compiled = nullptr;
+  std::string compile_error;
+  bool compile_finished = false;  // guarded by mu
+  auto wait_compiled = [&] {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return compile_finished; });
+  };
+  auto compile_done = [&] {
+    { std::lock_guard<std::mutex> lk(mu); compile_finished = true; }
+    cv.notify_all();
+  };
   auto worker = [&](int g) {
     auto fail_here = [&](const char* what) { errors[g] = std::string(what) + ": " + s2m_last_error(); failed = true; };
     if (s2m_ctx_create(a.device + g, &ctx[g])) fail_here("no usable CUDA device");
-    else if (s2m_module_compile(ctx[g], shader, 0, &mod[g])) fail_here("shader module creation failed");
+    wait_compiled();
+    if (!ctx[g]) {}  // failed above
+    else if (!compiled) { errors[g] = "shader module creation failed: " + compile_error; failed = true; }
+    else if (s2m_module_instantiate(compiled, ctx[g], &mod[g])) fail_here("shader module creation failed");
     if (g == 0 && !failed) {
       const uint32_t bands = 128;
       std::vector<double> cost(bands, 1.0);
@@ -205,7 +220,10 @@ int run_multi_gpu(const Args& a, s2m_mesh_params params) {
   const auto t0 = std::chrono::steady_clock::now();
   std::vector<std::thread> threads;
   for (int g = 0; g < n; ++g) threads.emplace_back(worker, g);
+  if (s2m_module_compile(nullptr, shader, 0, &compiled)) { compiled = nullptr; compile_error = s2m_last_error(); }
+  compile_done();
   for (auto& t : threads) t.join();
+  if (compiled) s2m_module_free(compiled);
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   if (failed) {
     for (int g = 0; g < n; ++g) if (!errors[g].empty()) error("GPU " + std::to_string(a.device + g) + ": " + errors[g]);
@@ -295,15 +313,30 @@ int main(int argc, char** argv) {
 
   if (a.gpus > 1) return run_multi_gpu(a, params);
 
+  // The CUDA context comes up on its own thread while this one reads, lowers and NVRTC-compiles the
+  // shader (neither needs the device); the cubins are loaded once both are there.
+  const auto t_start = std::chrono::steady_clock::now();
   s2m_ctx* ctx = nullptr;
-  if (s2m_ctx_create(a.device, &ctx)) die("no usable CUDA device");  // request_adapter/request_device .unwrap()
+  int ctx_status = 0;
+  std::string ctx_error;
+  std::thread ctx_thread([&] {
+    ctx_status = s2m_ctx_create(a.device, &ctx);  // request_adapter/request_device .unwrap()
+    if (ctx_status) ctx_error = s2m_last_error();  // the error slot is per thread
+  });
 
   s2m_shader* shader = load_shader(a, false);
-  if (!a.debug_wgsl.empty() && s2m_shader_write_to_file(shader, a.debug_wgsl.c_str())) die("cannot write --debug-wgsl file");
+  if (!a.debug_wgsl.empty() && s2m_shader_write_to_file(shader, a.debug_wgsl.c_str())) { ctx_thread.join(); die("cannot write --debug-wgsl file"); }
   if (!a.debug_png.empty()) warn("--debug-png is ignored: this engine has no per-slice textures to dump");
 
+  s2m_module* compiled = nullptr;
+  const int compile_status = s2m_module_compile(nullptr, shader, 0, &compiled);
+  ctx_thread.join();
+  if (ctx_status) { error("no usable CUDA device: " + ctx_error); exit(101); }
+  if (compile_status) die("shader module creation failed");
   s2m_module* module = nullptr;
-  if (s2m_module_compile(ctx, shader, 0, &module)) die("shader module creation failed");
+  if (s2m_module_instantiate(compiled, ctx, &module)) die("shader module creation failed");
+  s2m_module_free(compiled);
+  const double setup_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
   if (!a.debug_cuda.empty()) {
     FILE* f = fopen(a.debug_cuda.c_str(), "wb");
     if (f) { fputs(s2m_module_cuda_source(module), f); fclose(f); }
@@ -336,10 +369,14 @@ int main(int argc, char** argv) {
   int st;
   const std::string& m = a.mesh;
   const bool is_stl = m.size() >= 4 && strcasecmp(m.c_str() + m.size() - 4, ".stl") == 0;
+  const auto t_write = std::chrono::steady_clock::now();
   if (a.binary_stl && is_stl) st = s2m_result_write_stl_binary(result, m.c_str());
   else st = s2m_result_write_mesh(result, m.c_str());
   if (st) error(std::string("Could not write mesh to ") + s2m_last_error() + "!");  // main.rs:359-361 (and it carries on)
   info("Mesh written to " + a.mesh);
+  if (a.stats)
+    fprintf(stderr, "stats: context + shader + NVRTC + module load %.1f ms wall (context creation overlaps the compile) | file written in %.1f ms\n",
+            setup_ms, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_write).count());
 
   s2m_result_free(result);
   s2m_module_free(module);

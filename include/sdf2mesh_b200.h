@@ -106,6 +106,10 @@ int s2m_ctx_device_info(const s2m_ctx* ctx, char* name, size_t name_len, int* sm
 typedef struct s2m_module s2m_module;
 #define S2M_COMPILE_ALLOW_FMA 1u /* let ptxas contract a*b+c (faster, NOT bit-identical to the oracle) */
 int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32_t flags, s2m_module** out);
+/* Loads the cubins of an already compiled module (compiled with ctx NULL, or for another device) into
+ * ctx as a new module: compile once while the contexts are still being created, then instantiate per
+ * GPU.  `compiled` stays valid and is freed separately. */
+int s2m_module_instantiate(const s2m_module* compiled, s2m_ctx* ctx, s2m_module** out);
 const char* s2m_module_log(const s2m_module* m);         /* NVRTC log */
 const char* s2m_module_cuda_source(const s2m_module* m); /* what NVRTC compiled */
 int s2m_module_cubin(const s2m_module* m, const void** data, size_t* size); /* part 0 */

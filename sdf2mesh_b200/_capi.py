@@ -104,6 +104,7 @@ SYMBOLS = {
     "s2m_module_compile": (ctypes.c_int, [_P, _P, ctypes.c_uint32, _PP]),
     "s2m_module_log": (_S, [_P]),
     "s2m_module_cuda_source": (_S, [_P]),
+    "s2m_module_instantiate": (ctypes.c_int, [_P, _P, _PP]),
     "s2m_module_cubin": (ctypes.c_int, [_P, _PP, ctypes.POINTER(ctypes.c_size_t)]),
     "s2m_module_cubin_part": (ctypes.c_int, [_P, ctypes.c_int, _PP, ctypes.POINTER(ctypes.c_size_t)]),
     "s2m_module_compile_ms": (ctypes.c_double, [_P, ctypes.c_int]),

@@ -288,6 +288,29 @@ void unload_parts(s2m_module* m) {
   m->k1 = m->k4 = m->k_eval = m->k_probe = m->k_eval2 = nullptr;
 }
 
+// cubins -> CUmodules and kernel handles on m->ctx's device
+int load_parts(s2m_module* m) {
+  using namespace s2m_internal;
+  const double t0 = now_ms();
+  CUDA_TRY(cudaSetDevice(m->ctx->device));
+  CUresult_t cr;
+  for (int k = 0; k < m->n_parts; ++k) {
+    cr = driver().cuModuleLoadData(&m->mod[k], m->cubin[k].data());
+    if (cr) { unload_parts(m); return fail(S2M_ERR_CUDA, "cuModuleLoadData: " + cu_err(cr)); }
+  }
+  const bool split = m->n_parts > 1;
+  struct { CUfunction_t* f; const char* n; int part; bool wanted; } fns[] = {
+      {&m->k1, "s2m_k1_slab", 0, true}, {&m->k4, "s2m_k4_vertices", 1, true}, {&m->k_eval, "s2m_k_eval", 2, true},
+      {&m->k_probe, "s2m_k_cost_probe", 2, true}, {&m->k_eval2, "s2m_k_eval2", 2, m->k1_packed}};
+  for (auto& f : fns) {
+    if (!f.wanted) continue;
+    cr = driver().cuModuleGetFunction(f.f, m->mod[split ? f.part : 0], f.n);
+    if (cr) { unload_parts(m); return fail(S2M_ERR_CUDA, std::string("cuModuleGetFunction(") + f.n + "): " + cu_err(cr)); }
+  }
+  m->ms_load = now_ms() - t0;
+  return S2M_OK;
+}
+
 // How K1 evaluates the SDF.  `packed_text` is the front-end's packed (f32x2)
 // translation, empty for "one corner per evaluation".
 struct K1Plan {
@@ -487,23 +510,30 @@ extern "C" int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32
   double t2 = now_ms();
   m->ms_nvrtc = t2 - t1;
   if (ctx) {
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    CUresult_t cr;
-    for (int k = 0; k < m->n_parts; ++k) {
-      cr = driver().cuModuleLoadData(&m->mod[k], m->cubin[k].data());
-      if (cr) { unload_parts(m.get()); return fail(S2M_ERR_CUDA, "cuModuleLoadData: " + cu_err(cr)); }
-    }
-    const bool split = m->n_parts > 1;
-    struct { CUfunction_t* f; const char* n; int part; bool wanted; } fns[] = {
-        {&m->k1, "s2m_k1_slab", 0, true}, {&m->k4, "s2m_k4_vertices", 1, true}, {&m->k_eval, "s2m_k_eval", 2, true},
-        {&m->k_probe, "s2m_k_cost_probe", 2, true}, {&m->k_eval2, "s2m_k_eval2", 2, m->k1_packed}};
-    for (auto& f : fns) {
-      if (!f.wanted) continue;
-      cr = driver().cuModuleGetFunction(f.f, m->mod[split ? f.part : 0], f.n);
-      if (cr) { unload_parts(m.get()); return fail(S2M_ERR_CUDA, std::string("cuModuleGetFunction(") + f.n + "): " + cu_err(cr)); }
-    }
-    m->ms_load = now_ms() - t2;
+    st = load_parts(m.get());
+    if (st != S2M_OK) return st;
   }
+  *out = m.release();
+  return S2M_OK;
+}
+
+extern "C" int s2m_module_instantiate(const s2m_module* compiled, s2m_ctx* ctx, s2m_module** out) {
+  using namespace s2m_internal;
+  if (!compiled || !ctx || !out) return fail(S2M_ERR_INVALID_ARG, "s2m_module_instantiate: NULL argument");
+  *out = nullptr;
+  if (compiled->n_parts < 1) return fail(S2M_ERR_STATE, "s2m_module_instantiate: the module holds no cubin");
+  std::unique_ptr<s2m_module> m(new s2m_module());
+  m->cuda_source = compiled->cuda_source;
+  m->log = compiled->log;
+  m->n_parts = compiled->n_parts;
+  for (int k = 0; k < compiled->n_parts; ++k) m->cubin[k] = compiled->cubin[k];
+  m->k1_rows = compiled->k1_rows;
+  m->k1_packed = compiled->k1_packed;
+  m->ms_frontend = compiled->ms_frontend;
+  m->ms_nvrtc = compiled->ms_nvrtc;
+  m->ctx = ctx;
+  int st = load_parts(m.get());
+  if (st != S2M_OK) return st;
   *out = m.release();
   return S2M_OK;
 }

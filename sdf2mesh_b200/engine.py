@@ -49,7 +49,15 @@ class Module:
         self._h = ctypes.c_void_p()
         self.ctx = ctx
         self._shader = shader
-        check(lib().s2m_module_compile(ctx._h if ctx is not None else None, shader._h, flags, ctypes.byref(self._h)))
+        if shader is not None:
+            check(lib().s2m_module_compile(ctx._h if ctx is not None else None, shader._h, flags, ctypes.byref(self._h)))
+
+    def instantiate(self, ctx: Context) -> "Module":
+        """this module's cubins loaded into ctx as a new Module (compile once with ctx=None, load per GPU)"""
+        m = Module(None, ctx)
+        m._shader = self._shader
+        check(lib().s2m_module_instantiate(self._h, ctx._h, ctypes.byref(m._h)))
+        return m
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -214,3 +214,24 @@ def test_cli_multi_gpu_threads(ctx, tmp_path):
     p = subprocess.run(args + ["-0", str(many), "--gpus", str(n), "--stats"], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert one.read_bytes() == many.read_bytes()
+
+
+def test_module_compiled_without_a_device_then_instantiated(ctx):
+    """s2m_module_instantiate: NVRTC output produced with ctx = NULL (what the CLI compiles while its
+    context comes up, and what --gpus N compiles once for all GPUs) loaded into a context: the same
+    mesh as the oracle, the same kernels as a module compiled for the context directly"""
+    compiled = load_example_shader("torus").create_shader_module(None)
+    with pytest.raises(s2m.S2mError):
+        s2m.mesh_run(ctx, compiled, s2m.params_from_cli(32, 2.0)[0])   # not loaded anywhere
+    m = compiled.instantiate(ctx)
+    assert m.cubins() == compiled.cubins() and m.packed == compiled.packed and m.compile_ms()[2] > 0
+    del compiled   # the instance owns copies of the cubins
+    p, _ = s2m.params_from_cli(32, 2.0)
+    r = s2m.mesh_run(ctx, m, p)
+    o = oracle.mesh_run("torus", 32, 2.0)
+    d = r.data()
+    assert np.array_equal(d.keys, o.keys) and np.array_equal(d.quads, o.quads) and f32_equal(d.positions, o.positions).all()
+    pts = np.random.default_rng(1).uniform(-1, 1, (1000, 3)).astype(np.float32)
+    assert f32_equal(m.eval_points(pts), oracle.eval_points("torus", pts)).all()
+    r.free()
+    o.free()
