@@ -107,6 +107,13 @@ impl Sdf3DShader {
         check(unsafe { ffi::s2m_shader_write_to_file(self.0, p.as_ptr()) }).map_err(|e| std::io::Error::new(std::io::ErrorKind::Other, format!("{e:?}")))
     }
 
+    /// Front-end + NVRTC without a device: the cubins for sm_100a, to be loaded with `Context::instantiate`.
+    pub fn compile(&self) -> Result<Module, Error> {
+        let mut h = ptr::null_mut();
+        check(unsafe { ffi::s2m_module_compile(ptr::null_mut(), self.0, 0, &mut h) })?;
+        Ok(Module(h))
+    }
+
     pub fn source(&self) -> String {
         unsafe { CStr::from_ptr(ffi::s2m_shader_source(self.0)).to_string_lossy().into_owned() }
     }
@@ -138,6 +145,14 @@ impl Context {
     pub fn create_shader_module(&self, shader: &Sdf3DShader) -> Result<Module, Error> {
         let mut h = ptr::null_mut();
         check(unsafe { ffi::s2m_module_compile(self.0, shader.0, 0, &mut h) })?;
+        Ok(Module(h))
+    }
+
+    /// Loads a module compiled without a device (`Sdf3DShader::compile`) or for another GPU into this
+    /// context: compile once while the contexts come up, instantiate per GPU.
+    pub fn instantiate(&self, compiled: &Module) -> Result<Module, Error> {
+        let mut h = ptr::null_mut();
+        check(unsafe { ffi::s2m_module_instantiate(compiled.0, self.0, &mut h) })?;
         Ok(Module(h))
     }
 
