@@ -47,6 +47,12 @@ class WgslWriter {
       function(*f);
       out_ << "\n";
     }
+    for (const auto& d : m_.dropped) {
+      std::string why = d.second;
+      for (char& c : why) if (c == '\n' || c == '\r') c = ' ';
+      out_ << "// left out: fn " << d.first << " -- " << why << "\n";
+    }
+    if (!m_.dropped.empty()) out_ << "\n";
     // naga's shape for an empty GLSL `void main() {}`
     out_ << "fn main_1() {\n    return;\n}\n\n@fragment \nfn main() {\n    main_1();\n    return;\n}\n";
     return out_.str();

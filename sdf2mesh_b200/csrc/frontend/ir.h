@@ -138,6 +138,9 @@ struct Module {
   std::map<const Var*, ExprP> global_init;       // initializer expressions of globals
   std::vector<std::unique_ptr<StructDef>> structs;   // in declaration order
   std::vector<std::unique_ptr<ArrayDef>> arrays;     // interned
+  // GLSL functions left out because their bodies need something this engine has no counterpart for
+  // (texture sampling, screen-space derivatives, ...): name and reason.  Only calling one is an error.
+  std::vector<std::pair<std::string, std::string>> dropped;
   Var* new_var() { vars.emplace_back(new Var()); vars.back()->id = (int)vars.size(); return vars.back().get(); }
   Type array_of(const Type& elem, int len) {
     for (const auto& a : arrays) if (a->elem == elem && a->len == len) return Type::array_(a.get());

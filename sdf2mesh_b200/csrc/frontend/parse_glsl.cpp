@@ -285,16 +285,34 @@ class GlslParser : public ParserBase {
       fn->body = mk_stmt(Stmt::Block);
       return;
     }
+    // A ShaderToy image pass is mostly shading code around the distance function.  The reference hands
+    // all of it to naga (shadertoy.rs:154-167) and only ever calls the SDF; here a function whose body
+    // needs something with no counterpart in this engine (textures, derivatives, ...) is left out, and
+    // the error is raised only if something that is kept calls it.
+    const size_t body_tok = pos;
+    const size_t scope_depth = scopes.size();
     cur_fn = fn;
-    push_scope();
-    for (Var* p : params) {
-      if (scopes.back().count(p->name)) b.error("duplicate parameter '" + p->name + "'");
-      scopes.back()[p->name] = p;
+    try {
+      push_scope();
+      for (Var* p : params) {
+        if (scopes.back().count(p->name)) b.error("duplicate parameter '" + p->name + "'");
+        scopes.back()[p->name] = p;
+      }
+      fn->body = parse_compound(false);
+      pop_scope();
+    } catch (const FrontendError& e) {
+      if (e.status != 11) throw;
+      while (scopes.size() > scope_depth) pop_scope();
+      side_ = nullptr; cond_depth_ = 0; leave_postfix_ = false;
+      pos = body_tok;
+      skip_braces();
+      fn->body = nullptr;
+      dropped_[fn] = e.what();
+      mod->dropped.emplace_back(fn->name, e.what());
     }
-    fn->body = parse_compound(false);
-    pop_scope();
     cur_fn = nullptr;
   }
+  std::map<const Function*, std::string> dropped_;
 
   // ---------------------------------------------------------------- statements
   StmtP parse_compound(bool new_scope) {
@@ -818,9 +836,12 @@ class GlslParser : public ParserBase {
           else b.error("no overload of '" + name + "' matches the argument types");
         }
         if (best->is_entry) b.error("main() cannot be called");
+        if (dropped_.count(best)) throw FrontendError(11, "calls '" + best->name + "', which was left out: " + dropped_[best]);
         return b.call_user(best, args);
       }
-      if (name == "texture" || name == "texelFetch" || name == "textureLod") b.unsupported("texture sampling (" + name + ")");
+      if (name == "texture" || name == "texelFetch" || name == "textureLod" || name == "textureGrad" || name == "textureSize" || name == "texture2D")
+        b.unsupported("texture sampling (" + name + ")");
+      if (name == "dFdx" || name == "dFdy" || name == "fwidth") b.unsupported("screen-space derivatives (" + name + ") outside a fragment stage");
       // bit reinterpretation, vector relational functions, mix with a bool selector
       if (args.size() == 1 && (name == "floatBitsToInt" || name == "floatBitsToUint" || name == "intBitsToFloat" || name == "uintBitsToFloat")) {
         const bool from_float = name[0] == 'f';
@@ -863,6 +884,7 @@ class GlslParser : public ParserBase {
     }
     if (Var* v = lookup(name)) { advance(); return b.var_ref(v); }
     if (name.compare(0, 3, "gl_") == 0) b.unsupported("built-in variable " + name);
+    if (name.compare(0, 8, "iChannel") == 0) b.unsupported("ShaderToy channel input " + name);
     b.error("unknown identifier '" + name + "'");
   }
 };

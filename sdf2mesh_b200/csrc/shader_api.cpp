@@ -230,6 +230,15 @@ std::string remove_line(const std::string& wgsl, const std::string& what) {
   return s;
 }
 
+// the front-end's note about a function it left out ("// left out: fn NAME -- reason"), for the error text
+std::string why_left_out(const std::string& wgsl, const std::string& fn) {
+  const std::string tag = "// left out: fn " + fn + " -- ";
+  const size_t at = wgsl.find(tag);
+  if (at == std::string::npos) return "";
+  const size_t end = wgsl.find('\n', at);
+  return wgsl.substr(at + tag.size(), end == std::string::npos ? std::string::npos : end - at - tag.size());
+}
+
 int build_from_glsl(const std::string& glsl, const std::string& sdf, s2m_shader** out) {
   std::string wgsl, err;
   int st = s2m_frontend::glsl_to_wgsl(glsl, &wgsl, &err);  // shadertoy.rs:199 WgslShaderCode::from_glsl
@@ -241,6 +250,8 @@ int build_from_glsl(const std::string& glsl, const std::string& sdf, s2m_shader*
   if (has_function(wgsl, sdf)) {                                                       // :89-98
     if (!has_function(wgsl, "sdf3d")) wgsl += "fn sdf3d(p: vec3<f32>) -> f32 { return " + sdf + "(p); }\n";
   } else {
+    const std::string why = why_left_out(wgsl, sdf);
+    if (!why.empty()) return fail(S2M_ERR_UNSUPPORTED, "SDF function `" + sdf + "`: " + why);
     return fail(S2M_ERR_MISSING_SDF, "Missing SDF function `" + sdf + "` in shader");
   }
   s2m_shader* sh = new s2m_shader();
@@ -278,6 +289,8 @@ int build_from_shadertoy(const std::string& code, const std::string& sdf, s2m_sh
   if (has_function(wgsl, sdf)) {
     if (!has_function(wgsl, "sdf3d")) wgsl += "fn sdf3d(p: vec3<f32>) -> f32 { return " + sdf + "(p); }\n";
   } else {
+    const std::string why = why_left_out(wgsl, sdf);
+    if (!why.empty()) return fail(S2M_ERR_UNSUPPORTED, "SDF function `" + sdf + "`: " + why);
     return fail(S2M_ERR_MISSING_SDF, "Missing SDF function `" + sdf + "` in shader");
   }
   wgsl += kModNormal; wgsl += "\n";  // shader.rs:139

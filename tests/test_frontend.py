@@ -1167,3 +1167,37 @@ def test_glsl_names_that_wgsl_reserves(built, tmp_path):
     x, y, z = (pts[:, i] for i in range(3))
     want = ((x * np.float32(2) + (y * np.float32(0.5)).astype(np.float32)).astype(np.float32) + (z * np.float32(1)).astype(np.float32)).astype(np.float32)
     assert f32_equal(got, want).all()
+
+
+def test_shading_code_with_textures_and_derivatives_is_left_out(built):
+    """a ShaderToy image pass is shading code around the distance function: functions that need textures,
+    channel inputs or screen-space derivatives (and their callers) are left out of the module with a note;
+    it is an error only when the SDF itself is among them"""
+    code = textwrap.dedent("""\
+        float map(vec3 p) { return length(p) - 0.75; }
+        vec3 shade(vec3 p, vec2 uv) { vec3 t = texture(iChannel0, uv).xyz; return t * fwidth(p.x); }
+        float aa(float d) { return d / fwidth(d); }
+        vec3 render(vec3 ro, vec3 rd, vec2 uv) { float t = 0.0; for (int i = 0; i < 64; i++) { t += map(ro + rd * t); } return shade(ro + rd * t, uv); }
+        float after(vec3 p) { return map(p) * 2.0; }
+        void mainImage(out vec4 fragColor, in vec2 fragCoord) { vec2 uv = fragCoord / iResolution.xy; fragColor = vec4(render(vec3(0, 0, -3), vec3(uv, 1), uv), 1.0); }
+        """)
+    sh = s2m.Sdf3DShader.from_shadertoy_source(code, "map")
+    src = sh.source
+    assert "fn map(" in src and "fn after(" in src and "fn shade(" not in src and "fn render(" not in src and "fn aa(" not in src
+    assert "// left out: fn shade -- " in src and "iChannel0" in src and "// left out: fn render -- calls 'shade'" in src and "// left out: fn aa -- " in src
+    pts = points(2.0, 300)
+    want = (np.sqrt(((pts[:, 0] * pts[:, 0]).astype(np.float32) + (pts[:, 1] * pts[:, 1]).astype(np.float32)).astype(np.float32)
+                    + (pts[:, 2] * pts[:, 2]).astype(np.float32)).astype(np.float32) - np.float32(0.75)).astype(np.float32)
+    assert f32_equal(host_eval.eval_points(sh.lower_to_cuda(), pts), want).all()
+    assert sh.create_shader_module(None).cubin_size > 0
+    for name, why in (("aa", "fwidth"), ("render", "calls 'shade'"), ("shade", "iChannel0")):
+        with pytest.raises(s2m.S2mError) as e:
+            s2m.Sdf3DShader.from_shadertoy_source(code, name)
+        assert e.value.kind == "UNSUPPORTED" and why in str(e.value), str(e.value)
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_shadertoy_source(code, "nope")
+    assert e.value.kind == "MISSING_SDF"
+    # a syntax error is still an error, wherever it is
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_shadertoy_source(code + "\nfloat broken(vec3 p) { return p.x +; }\n", "map")
+    assert e.value.kind == "PARSE"
