@@ -869,6 +869,14 @@ class GlslParser : public ParserBase {
         if (!e->ty.is_int()) b.error("second argument of ldexp() must be an integer");
         return b.binary(Op::Mul, args[0], b.call_builtin("exp2", {b.construct(e->ty.with_sk(Sk::F32), false, {e})}));
       }
+      if (args.size() == 1 && (name == "isnan" || name == "isinf")) {  // component-wise; WGSL has neither, so they are spelled out
+        ExprP x = args[0];
+        if (!x->ty.is_float() || x->ty.is_matrix()) b.error(name + "() needs a float scalar or vector");
+        if (name == "isnan") return b.binary(Op::Ne, x, x);
+        ExprP big = b.lit_float(3.4028234663852886e38, Sk::F32);   // the largest finite f32
+        if (x->ty.is_vector()) big = b.construct(x->ty, false, {big});
+        return b.binary(Op::Gt, b.call_builtin("abs", {x}), big);
+      }
       if (args.size() == 1 && name == "not") {
         if (!args[0]->ty.is_vector() || !args[0]->ty.is_bool()) b.error("not() needs a bool vector");
         return b.unary(Op::Not, args[0]);

@@ -1201,3 +1201,12 @@ def test_shading_code_with_textures_and_derivatives_is_left_out(built):
     with pytest.raises(s2m.S2mError) as e:
         s2m.Sdf3DShader.from_shadertoy_source(code + "\nfloat broken(vec3 p) { return p.x +; }\n", "map")
     assert e.value.kind == "PARSE"
+
+
+def test_glsl_isnan_isinf(built):
+    src = ("#version 450 core\nfloat sdf(vec3 p) { float big = p.x * 3.0e38; float n = (big - big) * p.y; vec2 v = vec2(big * 4.0, p.z);\n"
+           "  return float(isnan(n)) + 2.0 * float(isinf(big * 4.0)) + 4.0 * float(isinf(p.y)) + 8.0 * float(any(isinf(v))) + 16.0 * float(any(isnan(vec3(n, 1.0, 2.0)))); }\nvoid main() {}\n")
+    sh = s2m.Sdf3DShader.from_source(src, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    pts = np.array([[1, 1, 1], [2, 0.5, 0], [0.1, 1, 1], [-3, 2, 1], [0, 0, 0]], np.float32)
+    assert host_eval.eval_points(sh.lower_to_cuda(), pts).tolist() == [10.0, 27.0, 0.0, 27.0, 0.0]
+    assert sh.create_shader_module(None).cubin_size > 0
