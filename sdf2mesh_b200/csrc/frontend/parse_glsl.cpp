@@ -542,8 +542,16 @@ class GlslParser : public ParserBase {
 
   static bool ends_flow(const Stmt& blk) {  // last statement leaves the case for good
     if (blk.body.empty()) return false;
-    const Stmt::K k = blk.body.back()->k;
+    const Stmt& last = *blk.body.back();
+    const Stmt::K k = last.k;
+    if (k == Stmt::Block) return ends_flow(last);   // case 1: { ...; return x; }
+    if (k == Stmt::If) return last.then_s && last.else_s && ends_flow_stmt(*last.then_s) && ends_flow_stmt(*last.else_s);
     return k == Stmt::Break || k == Stmt::Return || k == Stmt::Continue || k == Stmt::Discard;
+  }
+  static bool ends_flow_stmt(const Stmt& s) {
+    if (s.k == Stmt::Block) return ends_flow(s);
+    if (s.k == Stmt::If) return s.then_s && s.else_s && ends_flow_stmt(*s.then_s) && ends_flow_stmt(*s.else_s);
+    return s.k == Stmt::Break || s.k == Stmt::Return || s.k == Stmt::Continue || s.k == Stmt::Discard;
   }
   // switch (e) { case 1: case 2: ...; break; default: ... }  -- labels group into cases; a case
   // that runs into the next label without break/return/continue/discard would fall through,

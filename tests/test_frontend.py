@@ -1210,3 +1210,83 @@ def test_glsl_isnan_isinf(built):
     pts = np.array([[1, 1, 1], [2, 0.5, 0], [0.1, 1, 1], [-3, 2, 1], [0, 0, 0]], np.float32)
     assert host_eval.eval_points(sh.lower_to_cuda(), pts).tolist() == [10.0, 27.0, 0.0, 27.0, 0.0]
     assert sh.create_shader_module(None).cubin_size > 0
+
+
+def test_glsl_idioms_from_shadertoy_code(built):
+    """braced switch cases that end in return / break, do-while over a local array, a float loop counter,
+    matrix column and element stores, a dynamically indexed vector store, integer xor / and, while with continue"""
+    src = textwrap.dedent("""\
+        #version 450 core
+        #define N 4
+        float shape(vec3 p, int kind) {
+            switch (kind) {
+                case 0: return p.x - 1.0;
+                case 1: { vec3 d = abs(p) - vec3(0.75); return max(max(d.x, d.y), d.z); }
+                case 2:
+                case 3: { if (p.y > 0.0) { return p.y * 0.5; } else { break; } }
+                default: break;
+            }
+            return 8.0;
+        }
+        float sdf(vec3 p) {
+            float arr[N];
+            for (int i = 0; i < N; i++) arr[i] = shape(p, i);
+            float d = 100.0;
+            int k = 0;
+            do { d = min(d, arr[k]); k++; } while (k < N);
+            for (float f = 0.; f < 1.; f += .25) d = min(d, abs(p.z - f) + 0.5);
+            mat3 m = mat3(1.0);
+            m[1] = vec3(0., 2., 0.);
+            m[2][0] = 0.5;
+            vec3 w = m * p;
+            w[k % 3] += 0.25;
+            ivec2 ij = ivec2(floor(p.xy * 4.0));
+            d += float((ij.x ^ ij.y) & 1) * 0.125;
+            int n = 0;
+            while (n < 3) { if (d > float(n) * 0.25) { n += 2; continue; } n++; }
+            return d + w.x + w.y * 0.5 + w.z * 0.25 + float(n);
+        }
+        void main() {}
+        """)
+    sh = s2m.Sdf3DShader.from_source(src, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    F = np.float32
+
+    def shape(p, kind):
+        if kind == 0:
+            return F(p[0] - F(1))
+        if kind == 1:
+            d = np.abs(p) - F(0.75)
+            return max(max(d[0], d[1]), d[2])
+        if kind in (2, 3) and p[1] > 0:
+            return F(p[1] * F(0.5))
+        return F(8)
+
+    def ref(p):
+        arr = [shape(p, i) for i in range(4)]
+        d = F(100)
+        for k in range(4):
+            d = min(d, arr[k])
+        f = F(0)
+        while f < 1:
+            d = min(d, F(F(abs(F(p[2] - f))) + F(0.5)))
+            f = F(f + F(0.25))
+        # m = columns (1,0,0), (0,2,0), (0.5,0,1);  w = m * p = c0*p.x + c1*p.y + c2*p.z, summed left to right
+        w = [F(F(F(F(1) * p[0]) + F(F(0) * p[1])) + F(F(0.5) * p[2])),
+             F(F(F(F(0) * p[0]) + F(F(2) * p[1])) + F(F(0) * p[2])),
+             F(F(F(F(0) * p[0]) + F(F(0) * p[1])) + F(F(1) * p[2]))]
+        w[4 % 3] = F(w[4 % 3] + F(0.25))
+        ij = np.floor(p[:2] * F(4)).astype(np.int32)
+        d = F(d + F(F((int(ij[0]) ^ int(ij[1])) & 1) * F(0.125)))
+        n = 0
+        while n < 3:
+            if d > F(F(n) * F(0.25)):
+                n += 2
+                continue
+            n += 1
+        return F(F(F(F(d + w[0]) + F(w[1] * F(0.5))) + F(w[2] * F(0.25))) + F(n))
+
+    pts = points(3.0, 1500)
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+    want = np.array([ref(p) for p in pts], np.float32)
+    assert f32_equal(got, want).all()
+    assert sh.create_shader_module(None).cubin_size > 0
