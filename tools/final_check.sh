@@ -5,6 +5,7 @@ python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tai
 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -c 300 gpurun_out/bench_final.json
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_final_reference.json 2>> gpurun_out/bench_final.err; tail -c 200 gpurun_out/bench_final_reference.json
 python bench.py --workload mandelmesh4096 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_final_4096.json 2>> gpurun_out/bench_final.err; tail -c 300 gpurun_out/bench_final_4096.json
+python tools/host_side_timings.py jit writer cli > gpurun_out/host_side_timings.jsonl 2>&1; cat gpurun_out/host_side_timings.jsonl
 for tool in memcheck racecheck; do
   timeout 600 compute-sanitizer --tool $tool --error-exitcode 9 python tools/sanitize_run.py > gpurun_out/sanitize_final_$tool.log 2>&1
   echo "$tool rc=$?"; tail -2 gpurun_out/sanitize_final_$tool.log
