@@ -461,3 +461,174 @@ def test_generated_loops_optimized_equals_unoptimized(built, monkeypatch, seed):
     if not ok.all():
         bad = int(np.flatnonzero(~ok)[0])
         raise AssertionError(f"seed {seed}: optimized {a[bad]!r} != unoptimized {b[bad]!r} at p = {p[bad].tolist()} in\n{fns[bad // PTS_PER_FUNC]}")
+
+
+# ------------------------------------------------------------------ integers: i32 / u32 trees
+# Semantics pinned in csrc/s2m_vec.h (WGSL's): two's-complement wrap-around, x / 0 = x, x % 0 = 0,
+# INT_MIN / -1 = INT_MIN, INT_MIN % -1 = 0, truncating division, shift counts taken mod 32, arithmetic >> on
+# i32, float -> int conversions truncate and saturate (NaN -> 0), int -> float rounds to nearest even.
+I64 = np.int64
+
+
+def wrap_i(x):
+    return ((x.astype(I64) + (1 << 31)) % (1 << 32)) - (1 << 31)
+
+
+def wrap_u(x):
+    return x.astype(I64) % (1 << 32)
+
+
+def gen_int(rng, ty, depth):
+    """ty: 'i' (i32) | 'u' (u32)"""
+    if depth <= 0 or rng.random() < 0.15:
+        r = rng.random()
+        if r < 0.45:   # from the point: trunc(q.c * scale), saturating for the big scales
+            return Node("fromf", ty, (), (int(rng.integers(3)), float(rng.choice([8.0, 1000.0, 65536.0, 3.0e9, -3.0e9 if ty == "i" else 5.0e9]))))
+        if r < 0.6:
+            return Node("bits", ty, (), int(rng.integers(3)))   # bitcast of q.c
+        c = int(rng.choice([0, 1, 2, 3, 7, 16, 255, 65535, 1664525, 1013904223, 2147483647] + ([-1, -2147483648, -7] if ty == "i" else [4294967295, 2654435769])))
+        return Node("iconst", ty, (), c)
+    d = depth - 1
+    ops = ["+", "-", "*", "/", "%", "&", "|", "^", "<<", ">>", "not", "min", "max", "clamp", "cast", "sel"] + (["neg", "abs", "sign"] if ty == "i" else [])
+    op = rng.choice(ops)
+    if op in ("+", "-", "*", "/", "%", "&", "|", "^", "min", "max"):
+        return Node(op, ty, (gen_int(rng, ty, d), gen_int(rng, ty, d)))
+    if op in ("<<", ">>"):
+        cnt = Node("iconst", "u", (), int(rng.integers(0, 32))) if rng.random() < 0.6 else Node("&", "u", (gen_int(rng, "u", d), Node("iconst", "u", (), 31)))
+        return Node(op, ty, (gen_int(rng, ty, d), cnt))
+    if op in ("not", "neg", "abs", "sign"):
+        return Node(op, ty, (gen_int(rng, ty, d),))
+    if op == "clamp":
+        return Node(op, ty, (gen_int(rng, ty, d), gen_int(rng, ty, d), gen_int(rng, ty, d)))
+    if op == "cast":   # i32(u) / u32(i): same bits
+        return Node("cast", ty, (gen_int(rng, "u" if ty == "i" else "i", d),))
+    return Node("sel", ty, (gen_int(rng, ty, d), gen_int(rng, ty, d), Node(rng.choice(["<", ">=", "=="]), "b", (gen_int(rng, ty, d), gen_int(rng, ty, d)))))
+
+
+def show_int(n, glsl):
+    k = [show_int(c, glsl) for c in n.kids]
+    T = {"i": "int" if glsl else "i32", "u": "uint" if glsl else "u32"}
+    op = n.op
+    if op == "fromf":
+        return f"{T[n.ty]}(q.{XYZ[n.arg[0]]} * {lit(n.arg[1]) if n.arg[1] >= 0 else '(' + lit(n.arg[1]) + ')'})"
+    if op == "bits":
+        return (f"floatBitsTo{'Int' if n.ty == 'i' else 'Uint'}(q.{XYZ[n.arg]})" if glsl else f"bitcast<{T[n.ty]}>(q.{XYZ[n.arg]})")
+    if op == "iconst":
+        if n.ty == "u":
+            return f"{n.arg}u"
+        if n.arg == -2147483648:
+            return "(-2147483647 - 1)"
+        s = str(n.arg) if glsl else f"{n.arg}i"
+        return f"({s})" if n.arg < 0 else s
+    if op in ("+", "-", "*", "/", "%", "&", "|", "^", "<<", ">>", "<", ">=", "=="):
+        return f"({k[0]} {op} {k[1]})"
+    if op == "not":
+        return f"(~{k[0]})"
+    if op == "neg":
+        return f"(-{k[0]})"
+    if op == "cast":
+        return f"{T[n.ty]}({k[0]})"
+    if op == "sel":
+        return f"({k[2]} ? {k[1]} : {k[0]})" if glsl else f"select({k[0]}, {k[1]}, {k[2]})"
+    return f"{op}({', '.join(k)})"
+
+
+def eval_int(n, q):
+    """int64 arrays holding the i32 / u32 value"""
+    k = [eval_int(c, q) for c in n.kids]
+    w = wrap_i if n.ty == "i" else wrap_u
+    op = n.op
+    N = q.shape[0]
+    if op == "fromf":
+        with np.errstate(all="ignore"):
+            f = (q[:, n.arg[0]] * F(n.arg[1])).astype(F).astype(np.float64)
+        lo, hi = (-(1 << 31), (1 << 31) - 1) if n.ty == "i" else (0, (1 << 32) - 1)
+        t = np.where(np.isnan(f), 0.0, np.clip(np.trunc(f), lo, hi))
+        return t.astype(I64)
+    if op == "bits":
+        b = np.ascontiguousarray(q[:, n.arg]).view(np.uint32).astype(I64)
+        return wrap_i(b) if n.ty == "i" else b
+    if op == "iconst":
+        return np.full(N, n.arg, I64)
+    if op == "+":
+        return w(k[0] + k[1])
+    if op == "-":
+        return w(k[0] - k[1])
+    if op == "*":
+        a, b = k[0].astype(object), k[1].astype(object)   # exact products, then wrap
+        return w(np.array([int(x) * int(y) % (1 << 64) for x, y in zip(a, b)], dtype=np.uint64).astype(I64))
+    if op in ("/", "%"):
+        a, b = k[0], k[1]
+        bad = (b == 0) | ((a == -(1 << 31)) & (b == -1) & (n.ty == "i"))
+        bs = np.where(bad, 1, b)
+        quo = np.sign(a) * np.sign(bs) * (np.abs(a) // np.abs(bs))
+        if op == "/":
+            return np.where(bad, a, quo)
+        return np.where(bad, 0, a - quo * bs)
+    if op == "&":
+        return w(wrap_u(k[0]) & wrap_u(k[1]))
+    if op == "|":
+        return w(wrap_u(k[0]) | wrap_u(k[1]))
+    if op == "^":
+        return w(wrap_u(k[0]) ^ wrap_u(k[1]))
+    if op == "<<":
+        return w(wrap_u(k[0]) << (k[1] % 32))
+    if op == ">>":
+        return k[0] >> (k[1] % 32)   # arithmetic on the signed value, logical on the unsigned one
+    if op == "not":
+        return w(~k[0])
+    if op == "neg":
+        return w(-k[0])
+    if op == "abs":
+        return w(np.abs(k[0]))
+    if op == "sign":
+        return np.sign(k[0])
+    if op == "min":
+        return np.minimum(k[0], k[1])
+    if op == "max":
+        return np.maximum(k[0], k[1])
+    if op == "clamp":
+        return np.minimum(np.maximum(k[0], k[1]), k[2])
+    if op == "cast":
+        return w(k[0])
+    if op == "sel":
+        return np.where(k[2], k[1], k[0])
+    if op == "<":
+        return k[0] < k[1]
+    if op == ">=":
+        return k[0] >= k[1]
+    if op == "==":
+        return k[0] == k[1]
+    raise AssertionError(op)
+
+
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_generated_integer_programs_equal_numpy(built, seed):
+    rng = np.random.default_rng(seed)
+    trees = [gen_int(rng, str(rng.choice(["i", "u"])), int(rng.integers(2, 6))) for _ in range(N_FUNCS)]
+    low_bits = rng.random(N_FUNCS) < 0.5   # f32(e) keeps the top 24 bits; f32(e & 1023) the bottom ones
+    p, q, k = sample_points(rng, N_FUNCS)
+    want = np.zeros(p.shape[0], F)
+    for i, t in enumerate(trees):
+        m = k == i
+        v = eval_int(t, q[m])
+        want[m] = ((wrap_u(v) & 1023) if low_bits[i] else v).astype(F)
+    for glsl in (False, True):
+        fns = []
+        for i, t in enumerate(trees):
+            e = show_int(t, glsl)
+            e = f"({e} & 1023{'u' if t.ty == 'u' else ''})" if low_bits[i] else e
+            fns.append(f"float g{i}(vec3 q) {{ return float({e}); }}" if glsl else f"fn g{i}(q: vec3f) -> f32 {{ return f32({e}); }}")
+        text = program(trees, glsl)
+        text = text[text.index("float sdf(vec3 p)" if glsl else "fn sdf3d("):]
+        text = ("#version 450 core\n" if glsl else "") + "\n".join(fns) + "\n" + text
+        sh = s2m.Sdf3DShader.from_source(text, _capi.SRC_GLSL_FRAGMENT if glsl else _capi.SRC_SDF3D, "sdf")
+        body = sh.lower_to_cuda()
+        host_eval.register_packed(body, sh.lower_to_cuda_packed())
+        got = host_eval.eval_points(body, p)
+        ok = same(got, want)
+        if not ok.all():
+            bad = int(np.flatnonzero(~ok)[0])
+            i = int(k[bad])
+            raise AssertionError(f"{'GLSL' if glsl else 'WGSL'} seed {seed} g{i} ({trees[i].ty}32{', low bits' if low_bits[i] else ''}): {show_int(trees[i], glsl)}\n"
+                                 f" at q = {q[bad].tolist()}: got {got[bad]!r}, numpy {want[bad]!r} ({int((~ok).sum())} mismatches in all)")
