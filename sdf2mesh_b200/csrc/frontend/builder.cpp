@@ -560,7 +560,24 @@ ExprP Builder::construct(Type target, bool infer_sk, std::vector<ExprP> args) {
   if (target.is_matrix()) {
     const int n = target.n;
     for (ExprP& a : args) {
-      if (a->ty.is_matrix()) { if (args.size() != 1 || a->ty.n != n) unsupported("matrix constructor from a matrix of another size"); return a; }
+      if (a->ty.is_matrix()) {
+        if (args.size() != 1) error("a matrix constructor takes one matrix or scalars and vectors");
+        if (a->ty.n == n) return a;
+        // matN(matM): the upper-left block of the argument, the rest of the identity (GLSL 5.4.2)
+        const int m = a->ty.n;
+        static const char* const kFirst[] = {"", "x", "xy", "xyz", "xyzw"};
+        std::vector<ExprP> cols;
+        for (int c = 0; c < n; ++c) {
+          std::vector<ExprP> parts;
+          if (c < m) {
+            ExprP col = index(a, lit_int(c, Sk::I32));
+            parts.push_back(m >= n ? swizzle(col, kFirst[n]) : col);
+          }
+          for (int r = (c < m ? std::min(m, n) : 0); r < n; ++r) parts.push_back(lit_float(r == c ? 1.0 : 0.0, Sk::F32));
+          cols.push_back(construct(Type::vec(Sk::F32, n), false, parts));
+        }
+        return construct(target, false, cols);
+      }
       if (a->ty.is_abstract() || (lang == Lang::Glsl && a->ty.is_int())) a = convert_sk(a, Sk::F32);
       if (a->ty.sk != Sk::F32) error("matrix constructor needs f32 components, found " + a->ty.str());
     }

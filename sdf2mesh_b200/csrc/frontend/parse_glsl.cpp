@@ -1,5 +1,7 @@
 // parse_glsl.cpp -- GLSL (fragment shader) front-end: the subset ShaderToy-style SDF code uses.
 // Replaces naga's glsl::Frontend behind convert_glsl_to_wgsl (/root/reference/src/shadertoy.rs:169-194).
+#include <cstring>
+
 #include "parse.h"
 #include "parser_base.h"
 
@@ -191,6 +193,20 @@ class GlslParser : public ParserBase {
     Qualifiers q = parse_qualifiers();
     if (is_ident("buffer") || is_ident("shared")) b.unsupported("storage qualifier " + peek().text);
     if (accept(";")) return;  // e.g. `layout(...) in;`
+    if (peek().k == Token::Ident && is_opaque_type(peek().text)) {
+      // `uniform sampler2D tex;` -- there is nothing to sample from here: the declaration is accepted, and a
+      // function that uses the name is left out like any other that needs a texture
+      const std::string tname = advance().text;
+      for (;;) {
+        const std::string vname = expect_ident("a name");
+        while (is_punct("[")) { while (!is_punct("]") && peek().k != Token::End) advance(); expect("]"); }
+        opaque_globals_[vname] = tname;
+        if (!accept(",")) break;
+      }
+      expect(";");
+      return;
+    }
+    if (q.uniform && peek().k == Token::Ident && is_punct("{", 1) && !structs.count(peek().text)) { parse_uniform_block(q); return; }
     bool unsized = false;
     Type base = parse_type(&unsized);
     const std::string name = expect_ident("a name");
@@ -207,6 +223,44 @@ class GlslParser : public ParserBase {
       declare_global(q, ty, n, init);
       if (!accept(",")) break;
       n = expect_ident("a name");
+    }
+    expect(";");
+  }
+
+  std::map<std::string, std::string> opaque_globals_;   // name -> type of sampler / image uniforms
+  static bool is_opaque_type(const std::string& s) {
+    auto starts = [&](const char* p) { return s.compare(0, strlen(p), p) == 0; };
+    return starts("sampler") || starts("isampler") || starts("usampler") || starts("image") || starts("iimage") || starts("uimage") ||
+           starts("texture") || starts("itexture") || starts("utexture") || s == "atomic_uint" || starts("subpassInput");
+  }
+  // layout(...) uniform Block { float t; vec3 c; } [instance];  -- like every uniform here the members read as
+  // zero.  Without an instance name the members are globals; with one they are the fields of one global struct.
+  void parse_uniform_block(const Qualifiers& q) {
+    const std::string block = advance().text;
+    expect("{");
+    std::vector<std::pair<std::string, Type>> members;
+    while (!is_punct("}")) {
+      parse_qualifiers();
+      bool unsized = false;
+      Type base = parse_type(&unsized);
+      if (unsized) b.error("unsized array member");
+      for (;;) {
+        const std::string fname = expect_ident("a member name");
+        members.emplace_back(fname, is_punct("[") ? parse_array_suffix(base, nullptr) : base);
+        if (!accept(",")) break;
+      }
+      expect(";");
+    }
+    expect("}");
+    if (members.empty()) b.error("uniform block " + block + " has no members");
+    if (peek().k == Token::Ident) {
+      const std::string inst = advance().text;
+      if (is_punct("[")) b.unsupported("arrays of uniform blocks");
+      StructDef* d = declare_struct(block);
+      for (const auto& m : members) add_field(d, m.first, m.second);
+      declare_global(q, Type::struct_(d), inst, nullptr);
+    } else {
+      for (const auto& m : members) declare_global(q, m.second, m.first, nullptr);
     }
     expect(";");
   }
@@ -534,10 +588,14 @@ class GlslParser : public ParserBase {
     if (accept_ident("discard")) { expect(";"); blk->body.push_back(mk_stmt(Stmt::Discard)); return; }
     if (accept_ident("switch")) { blk->body.push_back(parse_switch(blk)); return; }
     SideScope sc(*this);
-    StmtP s = parse_expression_statement();
+    for (;;) {  // `a = 1., b = 2.;` -- the comma operator at statement level is a sequence of statements
+      StmtP s = parse_expression_statement();
+      sc.flush_into(blk);
+      blk->body.push_back(s);
+      if (!accept(",")) break;
+      b.cur_line = peek().line;
+    }
     expect(";");
-    sc.flush_into(blk);
-    blk->body.push_back(s);
   }
 
   static bool ends_flow(const Stmt& blk) {  // last statement leaves the case for good
@@ -706,7 +764,20 @@ class GlslParser : public ParserBase {
               : p == "==" ? Op::Eq : p == "!=" ? Op::Ne : p == "<" ? Op::Lt : p == ">" ? Op::Gt : p == "<=" ? Op::Le : p == ">=" ? Op::Ge
               : p == "<<" ? Op::Shl : p == ">>" ? Op::Shr : p == "+" ? Op::Add : p == "-" ? Op::Sub : p == "*" ? Op::Mul : p == "/" ? Op::Div : Op::Rem;
       if (op == Op::Rem && (lhs->ty.is_float() || rhs->ty.is_float())) b.error("% needs integer operands in GLSL (use mod())");
+      if ((op == Op::Eq || op == Op::Ne) && (lhs->ty.is_matrix() || rhs->ty.is_matrix())) {
+        // GLSL: == and != compare whole operands and yield ONE bool (equal() / notEqual() are the component-wise forms)
+        if (lhs->ty != rhs->ty) b.error("== / != on matrices of different sizes");
+        ExprP acc;
+        for (int c = 0; c < lhs->ty.n; ++c) {
+          ExprP col = b.binary(op, b.index(lhs, b.lit_int(c, Sk::I32)), b.index(rhs, b.lit_int(c, Sk::I32)));
+          col = b.call_builtin(op == Op::Eq ? "all" : "any", {col});
+          acc = acc ? b.binary(op == Op::Eq ? Op::And : Op::Or, acc, col) : col;
+        }
+        lhs = acc;
+        continue;
+      }
       lhs = b.binary(op, lhs, rhs);
+      if ((op == Op::Eq || op == Op::Ne) && lhs->ty.is_vector()) lhs = b.call_builtin(op == Op::Eq ? "all" : "any", {lhs});
     }
     return lhs;
   }
@@ -901,6 +972,7 @@ class GlslParser : public ParserBase {
     if (Var* v = lookup(name)) { advance(); return b.var_ref(v); }
     if (name.compare(0, 3, "gl_") == 0) b.unsupported("built-in variable " + name);
     if (name.compare(0, 8, "iChannel") == 0) b.unsupported("ShaderToy channel input " + name);
+    if (opaque_globals_.count(name)) b.unsupported(opaque_globals_[name] + " uniform '" + name + "' (no textures or images here)");
     b.error("unknown identifier '" + name + "'");
   }
 };

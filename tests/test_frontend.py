@@ -1290,3 +1290,40 @@ def test_glsl_idioms_from_shadertoy_code(built):
     want = np.array([ref(p) for p in pts], np.float32)
     assert f32_equal(got, want).all()
     assert sh.create_shader_module(None).cubin_size > 0
+
+
+def test_glsl_whole_operand_equality_comma_statements_matrix_resize_uniform_blocks(built):
+    """GLSL semantics WGSL does not share: == / != on vectors and matrices give ONE bool; the comma operator at
+    statement level; matN(matM) keeps the upper-left block and fills with the identity; sampler uniforms are
+    accepted (their users are left out); uniform blocks with and without an instance name read as zero"""
+    src = textwrap.dedent("""\
+        #version 450 core
+        layout(binding = 1) uniform sampler2D tex0, tex1[2];
+        layout(std140, binding = 2) uniform Params { float t; vec3 c; float w[2]; };
+        layout(std140) uniform Scene { vec4 sphere; int n; } scene;
+        vec3 albedo(vec2 uv) { return texture(tex0, uv).rgb; }
+        float sdf(vec3 p) {
+            float a, b; int i = 0;
+            a = 1., b = 2.;
+            a += p.x, b *= p.y, i++;
+            mat2 m = mat2(1.), n = mat2(1., 0., 0., p.z);
+            float r = (p.xy == vec2(0.5, 0.25)) ? 100. : 0.;
+            r += (p.xy != p.yx) ? 10. : 0.;
+            r += (m == n) ? 1000. : 0.;
+            r += (m != n) ? 5. : 0.;
+            mat4 big = mat4(vec4(1., 2., 3., 4.), vec4(5., 6., 7., 8.), vec4(9., 10., 11., 12.), vec4(13., 14., 15., 16.));
+            mat3 n3 = mat3(big);
+            mat4 back = mat4(mat2(n3));
+            r += (n3 * vec3(0., 1., 0.)).z * 1e4 + (back * vec4(0., 0., 1., 1.)).z * 1e5 + (back * vec4(1., 0., 0., 0.)).y * 1e6;
+            return r + a + b + float(i) + t + c.x + w[1] + scene.sphere.w + float(scene.n);
+        }
+        void main() {}
+        """)
+    sh = s2m.Sdf3DShader.from_source(src, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    assert "// left out: fn albedo -- " in sh.source and "sampler2D uniform 'tex0'" in sh.source
+    assert "var<private> scene: Scene;" in sh.source and "var<private> c: vec3<f32>;" in sh.source
+    pts = np.array([[0.5, 0.25, 1.0], [0.5, 0.5, 2.0], [1, 2, 1], [0.5, 0.25, 3]], np.float32)
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+    # (n3 * e_y).z = 7, (back * (0,0,1,1)).z = 1, (back * e_x).y = 2
+    assert got.tolist() == [2170000.0 + v for v in (1113.0, 8.5, 1017.0, 118.0)]
+    assert sh.create_shader_module(None).cubin_size > 0
