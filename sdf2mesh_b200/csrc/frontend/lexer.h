@@ -32,7 +32,19 @@ struct Macro {
 
 class Lexer {
  public:
-  Lexer(const std::string& src, const LexOptions& opt) : s_(src), opt_(opt) {}
+  Lexer(const std::string& src, const LexOptions& opt) : s_(normalized(src)), opt_(opt) {}
+  // Editors on other platforms leave a UTF-8 byte-order mark and \r\n (or bare \r) line ends; neither means
+  // anything to WGSL or GLSL, and `\` + `\r\n` must still continue a preprocessor line.
+  static std::string normalized(const std::string& src) {
+    std::string out;
+    out.reserve(src.size());
+    size_t i = src.compare(0, 3, "\xef\xbb\xbf") == 0 ? 3 : 0;
+    for (; i < src.size(); ++i) {
+      if (src[i] == '\r') { out += '\n'; if (i + 1 < src.size() && src[i + 1] == '\n') ++i; }
+      else out += src[i];
+    }
+    return out;
+  }
   std::vector<Token> run() {
     std::vector<Token> raw;
     for (;;) {
@@ -45,7 +57,7 @@ class Lexer {
   }
 
  private:
-  const std::string& s_;
+  const std::string s_;   // normalized copy: no byte-order mark, \n line ends
   LexOptions opt_;
   size_t i_ = 0;
   int line_ = 1, col_ = 1;

@@ -111,6 +111,7 @@ bool read_file(const std::string& path, std::string* out) {
   std::ostringstream ss;
   ss << f.rdbuf();
   *out = ss.str();
+  if (out->compare(0, 3, "\xef\xbb\xbf") == 0) out->erase(0, 3);  // a UTF-8 byte-order mark would hide a `use ...;` on line 1
   return true;
 }
 

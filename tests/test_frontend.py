@@ -1327,3 +1327,17 @@ def test_glsl_whole_operand_equality_comma_statements_matrix_resize_uniform_bloc
     # (n3 * e_y).z = 7, (back * (0,0,1,1)).z = 1, (back * e_x).y = 2
     assert got.tolist() == [2170000.0 + v for v in (1113.0, 8.5, 1017.0, 118.0)]
     assert sh.create_shader_module(None).cubin_size > 0
+
+
+def test_byte_order_mark_and_crlf_line_ends(built, tmp_path):
+    """files saved on other platforms: UTF-8 BOM, \\r\\n line ends (also after a preprocessor line continuation), tabs, non-ASCII comments"""
+    f = tmp_path / "w.sdf3d"
+    f.write_bytes(b"\xef\xbb\xbfuse sdf3d::*;\r\n// caf\xc3\xa9 \xe2\x80\x94 comment\r\nfn sdf3d(p: vec3f) -> f32 {\r\n\treturn sdf3d_torus(p, vec2f(0.75, 0.25));\r\n}\r\n")
+    a = s2m.Sdf3DShader.from_path(f)
+    g = tmp_path / "g.frag"
+    g.write_bytes(b"\xef\xbb\xbf#version 450 core\r\n#define R 0.25 // caf\xc3\xa9\r\n#define LONG(a) \\\r\n   ((a) + 0.5)\r\nfloat sdf(vec3 p) {\r\n"
+                  b"\tvec2 q = vec2(length(p.xz) - (LONG(0.0) + 0.25), p.y);\r\n\treturn length(q) - R;\r\n}\r\nvoid main() {}\r\n")
+    b = s2m.Sdf3DShader.from_glsl_fragment_shader(g, "sdf")
+    pts = points(2.0, 2000)
+    va, vb = host_eval.eval_points(a.lower_to_cuda(), pts), host_eval.eval_points(b.lower_to_cuda(), pts)
+    assert f32_equal(va, vb).all() and np.isfinite(va).all()
