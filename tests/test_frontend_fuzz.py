@@ -632,3 +632,59 @@ def test_generated_integer_programs_equal_numpy(built, seed):
             i = int(k[bad])
             raise AssertionError(f"{'GLSL' if glsl else 'WGSL'} seed {seed} g{i} ({trees[i].ty}32{', low bits' if low_bits[i] else ''}): {show_int(trees[i], glsl)}\n"
                                  f" at q = {q[bad].tolist()}: got {got[bad]!r}, numpy {want[bad]!r} ({int((~ok).sum())} mismatches in all)")
+
+
+# ------------------------------------------------------------------ damaged inputs: errors, never crashes
+MUTATION_TOKENS = ["(", ")", "{", "}", "[", "]", ";", ",", ".", "+", "-", "*", "/", "%", "=", "==", "<", ">", "<<", ">>", "&", "|", "^", "!", "~", "?", ":", "#", "\\", "\n",
+                   "if", "else", "for", "while", "return", "float", "vec3", "fn", "let", "var", "0", "1.0", "1e40", "0x", "1u", "struct", "switch", "case", "default", "break",
+                   "continue", "#define", "#if", "#endif", "#else", "/*", "*/", "//", "mat3", "array", "->", "@", "&&", "||", "++", "--", "+=", "vec3f", "f32", "i32", "ptr",
+                   "loop", "continuing", "\x00", "\xff", "é"]
+
+
+def test_damaged_sources_give_errors_not_crashes(built):
+    """every example and fixture with random deletions, insertions, duplications and truncations: the library
+    answers with an S2mError or a translation (which NVRTC then accepts, packed form included) -- the C++
+    front-end runs inside the caller's process, so anything else would take the caller down"""
+    import os
+    import random
+    from tests.conftest import ROOT
+    rnd = random.Random(2024)
+    corpus = [(open(os.path.join(ROOT, "examples", f)).read(), _capi.SRC_SDF3D) for f in ("torus.sdf3d", "martin_cube.sdf3d", "p_key.sdf3d")]
+    corpus.append((open(os.path.join(ROOT, "examples", "mandelmesh.frag")).read(), _capi.SRC_GLSL_FRAGMENT))
+    corpus.append((open(os.path.join(ROOT, "tests", "data", "wgsl_features.sdf3d")).read(), _capi.SRC_SDF3D))
+    for f in sorted(os.listdir(os.path.join(ROOT, "tests", "data"))):
+        if f.endswith(".glsl"):
+            corpus.append(("#version 450 core\nuniform float iTime; uniform vec3 iResolution; uniform int iFrame; uniform vec4 iMouse;\n" +
+                           open(os.path.join(ROOT, "tests", "data", f)).read() + "\nvoid main() {}\n", _capi.SRC_GLSL_FRAGMENT))
+    for text, kind in corpus:   # the undamaged corpus translates
+        s2m.Sdf3DShader.from_source(text, kind, "sdf" if "float sdf(" in text else "map").lower_to_cuda()
+    accepted = rejected = compiled = 0
+    for it in range(500):
+        src, kind = rnd.choice(corpus)
+        s = src
+        for _ in range(rnd.randint(1, 4)):
+            m, i = rnd.random(), rnd.randrange(len(s) + 1)
+            if m < 0.3:
+                s = s[:i] + s[min(len(s), i + rnd.randint(1, 12)):]
+            elif m < 0.6:
+                s = s[:i] + rnd.choice(MUTATION_TOKENS) + s[i:]
+            elif m < 0.75:
+                j = min(len(s), i + rnd.randint(1, 30))
+                s = s[:i] + s[i:j] * 2 + s[j:]
+            elif m < 0.9:
+                s = s[:i] + " " + rnd.choice(MUTATION_TOKENS) + " " + s[i:]
+            else:
+                s = s[:i]
+        try:
+            sh = s2m.Sdf3DShader.from_source(s, kind, "sdf")
+            sh.lower_to_cuda()
+            sh.lower_to_cuda_packed()
+        except s2m.S2mError as e:
+            assert e.kind in ("PARSE", "VALIDATION", "UNSUPPORTED", "MISSING_SDF", "SHADER"), str(e)
+            rejected += 1
+            continue
+        accepted += 1
+        if compiled < 12:   # what the front-end lets through must be valid CUDA C++ (NVRTC, no device needed)
+            assert sh.create_shader_module(None).cubin_size > 0
+            compiled += 1
+    assert accepted > 10 and rejected > 300
