@@ -101,6 +101,7 @@ extern "C" {
     pub fn s2m_shader_from_glsl_fragment_shader(path: *const c_char, sdf: *const c_char, out: *mut *mut s2m_shader) -> c_int;
     pub fn s2m_shader_from_source(text: *const c_char, len: usize, kind: c_int, sdf: *const c_char, include_dir: *const c_char, out: *mut *mut s2m_shader) -> c_int;
     pub fn s2m_shader_from_shadertoy_source(code: *const c_char, len: usize, sdf: *const c_char, out: *mut *mut s2m_shader) -> c_int;
+    pub fn s2m_shader_from_shadertoy_response(body: *const c_char, len: usize, sdf: *const c_char, out: *mut *mut s2m_shader) -> c_int;
     pub fn s2m_shader_add_to_source(s: *mut s2m_shader, text: *const c_char) -> c_int;
     pub fn s2m_shader_source(s: *const s2m_shader) -> *const c_char;
     pub fn s2m_shader_write_to_file(s: *const s2m_shader, path: *const c_char) -> c_int;

@@ -100,7 +100,8 @@ s2m_shader* load_shader(const Args& a, bool quiet) {
   s2m_shader* shader = nullptr;
   if (!a.shadertoy_id.empty()) {
     if (!quiet) info("Reading SDF from ShaderToy (shader ID " + a.shadertoy_id + ")");
-    error("the ShaderToy REST fetch is not part of this build (no network access); save the shader's code to a file and use --shadertoy-file");
+    error("the ShaderToy REST fetch is not part of this build (no network access); save the API response "
+          "(https://www.shadertoy.com/api/v1/shaders/" + a.shadertoy_id + "?key=<your key>) or the shader's code to a file and use --shadertoy-file");
     exit(101);
   } else if (!a.shadertoy_file.empty()) {
     if (!quiet) info("Reading SDF from ShaderToy code in " + a.shadertoy_file + "...");
@@ -111,7 +112,13 @@ s2m_shader* load_shader(const Args& a, bool quiet) {
     size_t n;
     while ((n = fread(buf, 1, sizeof buf, f)) > 0) code.append(buf, n);
     fclose(f);
-    if (s2m_shader_from_shadertoy_source(code.data(), code.size(), a.shadertoy_sdf.c_str(), &shader)) die("cannot convert ShaderToy shader");
+    // either the image-pass GLSL itself or a saved API response (curl 'https://www.shadertoy.com/api/v1/shaders/ID?key=...' > file)
+    size_t first = 0;
+    while (first < code.size() && (code[first] == ' ' || code[first] == '\n' || code[first] == '\r' || code[first] == '\t')) ++first;
+    const bool is_json = first < code.size() && code[first] == '{';
+    if (is_json ? s2m_shader_from_shadertoy_response(code.data(), code.size(), a.shadertoy_sdf.c_str(), &shader)
+                : s2m_shader_from_shadertoy_source(code.data(), code.size(), a.shadertoy_sdf.c_str(), &shader))
+      die("cannot convert ShaderToy shader");
   } else if (!a.sdf.empty()) {
     if (!quiet) info("Reading SDF from " + a.sdf + "...");
     if (s2m_shader_from_path(a.sdf.c_str(), &shader)) die("cannot read SDF");

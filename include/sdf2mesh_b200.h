@@ -68,6 +68,11 @@ int s2m_shader_from_source(const char* text, size_t len, int kind, const char* s
  * wrapped with the ShaderToy uniform block and an empty main() (shadertoy.rs:141-167), converted,
  * and main_1 / main / mainImage are removed.  Same errors as the GLSL constructor. */
 int s2m_shader_from_shadertoy_source(const char* code, size_t len, const char* sdf_name, s2m_shader** out);
+/* The same from the body of the API response the host fetched (shadertoy.rs:126-131:
+ * GET https://www.shadertoy.com/api/v1/shaders/{id}?key=...): {"Shader": {"info": ..., "renderpass": [{"code": ...}]}}
+ * -- the code of all passes is concatenated like fetch_code_from_last_pass (:126-132 of impl Shader) -- or
+ * {"Error": "..."} -> S2M_ERR_SHADER with the API's message (ShaderProcessingError::ShaderError). */
+int s2m_shader_from_shadertoy_response(const char* body, size_t len, const char* sdf_name, s2m_shader** out);
 /* Sdf3DShader::add_to_source (shader.rs:155) */
 int s2m_shader_add_to_source(s2m_shader* s, const char* text);
 /* the `source` field: assembled WGSL (for GLSL input: WGSL regenerated from the IR) */

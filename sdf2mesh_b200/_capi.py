@@ -13,7 +13,9 @@ S2M_OK = 0
 STATUS_NAMES = {
     0: "OK", 1: "INVALID_ARG", 2: "IO", 3: "PARSE", 4: "VALIDATION", 5: "MISSING_SDF", 6: "SHADER",
     7: "NVRTC", 8: "CUDA", 9: "NO_DEVICE", 10: "OOM", 11: "UNSUPPORTED", 12: "STATE",
+    100: "REQUEST",   # host side only (ShaderProcessingError::RequestError, shadertoy.rs:71): the C library makes no requests
 }
+ERR_SHADER, ERR_REQUEST = 6, 100
 SRC_SDF3D, SRC_GLSL_FRAGMENT, SRC_WGSL, SRC_CUDA = 0, 1, 2, 3
 COMPILE_ALLOW_FMA = 1
 MESH_ALL_SLICES, MESH_NO_NORMALS, MESH_EXACT_DENSE, MESH_KEEP_CANDIDATES, MESH_CLASSIFY_FROM_SLAB = 1, 2, 4, 8, 16
@@ -87,6 +89,7 @@ SYMBOLS = {
     "s2m_shader_from_glsl_fragment_shader": (ctypes.c_int, [_S, _S, _PP]),
     "s2m_shader_from_source": (ctypes.c_int, [_S, ctypes.c_size_t, ctypes.c_int, _S, _S, _PP]),
     "s2m_shader_from_shadertoy_source": (ctypes.c_int, [_S, ctypes.c_size_t, _S, _PP]),
+    "s2m_shader_from_shadertoy_response": (ctypes.c_int, [_S, ctypes.c_size_t, _S, _PP]),
     "s2m_shader_add_to_source": (ctypes.c_int, [_P, _S]),
     "s2m_shader_source": (_S, [_P]),
     "s2m_shader_write_to_file": (ctypes.c_int, [_P, _S]),

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -306,6 +307,131 @@ int build_from_shadertoy(const std::string& code, const std::string& sdf, s2m_sh
 }
 
 }  // namespace
+
+namespace {
+// --- just enough JSON for a ShaderToy API response (shadertoy.rs:5-68, :119-123) -----------------------
+struct Json {
+  const std::string& s;
+  size_t i = 0;
+  bool ok = true;
+  explicit Json(const std::string& text) : s(text) {}
+  void ws() { while (i < s.size() && (s[i] == ' ' || s[i] == '\n' || s[i] == '\r' || s[i] == '\t')) ++i; }
+  bool eat(char c) { ws(); if (i < s.size() && s[i] == c) { ++i; return true; } return false; }
+  static void utf8(unsigned cp, std::string* out) {
+    if (cp < 0x80) *out += (char)cp;
+    else if (cp < 0x800) { *out += (char)(0xC0 | (cp >> 6)); *out += (char)(0x80 | (cp & 0x3F)); }
+    else if (cp < 0x10000) { *out += (char)(0xE0 | (cp >> 12)); *out += (char)(0x80 | ((cp >> 6) & 0x3F)); *out += (char)(0x80 | (cp & 0x3F)); }
+    else { *out += (char)(0xF0 | (cp >> 18)); *out += (char)(0x80 | ((cp >> 12) & 0x3F)); *out += (char)(0x80 | ((cp >> 6) & 0x3F)); *out += (char)(0x80 | (cp & 0x3F)); }
+  }
+  bool hex4(unsigned* v) {
+    if (i + 4 > s.size()) return false;
+    *v = 0;
+    for (int k = 0; k < 4; ++k) {
+      const char c = s[i++];
+      *v = *v * 16 + (c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : 99);
+      if ((*v & 0xFF) >= 99 && !(c >= '0' && c <= '9') && !(c >= 'a' && c <= 'f') && !(c >= 'A' && c <= 'F')) return false;
+    }
+    return true;
+  }
+  bool string(std::string* out) {
+    if (!eat('"')) return ok = false;
+    while (i < s.size() && s[i] != '"') {
+      char c = s[i++];
+      if (c != '\\') { if (out) *out += c; continue; }
+      if (i >= s.size()) return ok = false;
+      c = s[i++];
+      std::string piece;
+      switch (c) {
+        case 'n': piece = "\n"; break; case 't': piece = "\t"; break; case 'r': piece = "\r"; break;
+        case 'b': piece = "\b"; break; case 'f': piece = "\f"; break;
+        case 'u': {
+          unsigned cp = 0;
+          if (!hex4(&cp)) return ok = false;
+          if (cp >= 0xD800 && cp < 0xDC00 && i + 1 < s.size() && s[i] == '\\' && s[i + 1] == 'u') {  // surrogate pair
+            i += 2;
+            unsigned lo = 0;
+            if (!hex4(&lo)) return ok = false;
+            cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+          }
+          utf8(cp, &piece);
+          break;
+        }
+        default: piece = std::string(1, c);  // \" \\ \/
+      }
+      if (out) *out += piece;
+    }
+    if (i >= s.size()) return ok = false;
+    ++i;
+    return true;
+  }
+  // skips any value; for an object calls member(key) before each value -- it returns true if it consumed the value
+  typedef std::function<bool(const std::string&)> Member;
+  static bool skip_member(const std::string&) { return false; }
+  bool value(const Member& member) {
+    ws();
+    if (i >= s.size()) return ok = false;
+    if (s[i] == '"') return string(nullptr);
+    if (s[i] == '{') {
+      ++i;
+      if (eat('}')) return true;
+      do {
+        std::string key;
+        if (!string(&key) || !eat(':')) return ok = false;
+        if (!member(key) && !value(Member(skip_member))) return false;
+      } while (ok && eat(','));
+      return ok && eat('}') ? true : (ok = false);
+    }
+    if (s[i] == '[') {
+      ++i;
+      if (eat(']')) return true;
+      do { if (!value(member)) return false; } while (eat(','));
+      return eat(']') ? true : (ok = false);
+    }
+    const size_t start = i;
+    while (i < s.size() && s[i] != ',' && s[i] != '}' && s[i] != ']' && s[i] != ' ' && s[i] != '\n' && s[i] != '\r' && s[i] != '\t') ++i;
+    return i > start ? true : (ok = false);
+  }
+};
+}  // namespace
+
+// Sdf3DShader::from_shadertoy_api (shader.rs:110-144) after the HTTP GET the host makes (shadertoy.rs:126-131:
+// https://www.shadertoy.com/api/v1/shaders/{id}?key=...): `body` is the response, {"Shader": {..., "renderpass":
+// [{"code": ...}, ...]}} or {"Error": "..."}.  The code of all passes is concatenated, as fetch_code_from_last_pass does.
+extern "C" int s2m_shader_from_shadertoy_response(const char* body, size_t len, const char* sdf_name, s2m_shader** out) {
+  if (!body || !out) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
+  *out = nullptr;
+  const std::string text(body, len);
+  Json j(text);
+  std::string code, api_error, name, username;
+  bool saw_shader = false, saw_error = false;
+  // top level: {"Shader": {...}} | {"Error": "..."}
+  std::function<bool(const std::string&)> in_pass = [&](const std::string& key) {
+    if (key == "code") { std::string c; if (j.string(&c)) code += c; return true; }
+    return false;
+  };
+  std::function<bool(const std::string&)> in_info = [&](const std::string& key) {
+    if (key == "name") { j.string(&name); return true; }
+    if (key == "username") { j.string(&username); return true; }
+    return false;
+  };
+  std::function<bool(const std::string&)> in_shader = [&](const std::string& key) {
+    if (key == "renderpass") { j.value(in_pass); return true; }
+    if (key == "info") { j.value(in_info); return true; }
+    return false;
+  };
+  std::function<bool(const std::string&)> top = [&](const std::string& key) {
+    if (key == "Shader") { saw_shader = true; j.value(in_shader); return true; }
+    if (key == "Error") { saw_error = true; j.ws(); if (j.i < text.size() && text[j.i] == '"') j.string(&api_error); else j.value(Json::Member(Json::skip_member)); return true; }
+    return false;
+  };
+  j.ws();
+  if (j.i >= text.size() || text[j.i] != '{' || !j.value(top) || !j.ok) return fail(S2M_ERR_SHADER, "ShaderToy response is not valid JSON");
+  if (saw_error) return fail(S2M_ERR_SHADER, api_error.empty() ? "ShaderToy API error" : api_error);  // ShaderProcessingError::ShaderError
+  if (!saw_shader) return fail(S2M_ERR_SHADER, "not a ShaderToy API response (no `Shader` member)");
+  int st = build_from_shadertoy(code, sdf_name && *sdf_name ? sdf_name : "sdf", out);
+  if (st == S2M_OK) (*out)->log = "INFO Shader: " + name + "\nINFO Shader author: " + username + "\n" + (*out)->log;  // shader.rs:115-116
+  return st;
+}
 
 extern "C" int s2m_shader_from_shadertoy_source(const char* code, size_t len, const char* sdf_name, s2m_shader** out) {
   if (!code || !out) return fail(S2M_ERR_INVALID_ARG, "NULL argument");

@@ -95,6 +95,44 @@ class Sdf3DShader:
         check(lib().s2m_shader_from_shadertoy_source(raw, len(raw), sdf.encode(), ctypes.byref(h)))
         return cls(h)
 
+    SHADERTOY_API_KEY = "rdnjhn"   # shadertoy.rs:1
+
+    @classmethod
+    def from_shadertoy_json(cls, response, sdf: str = "sdf") -> "Sdf3DShader":
+        """A ShaderToy API response (text or parsed) -> shader, as shader.rs:110-144 does after the fetch:
+        `{"Shader": {"info": ..., "renderpass": [{"code": ...}, ...]}}` or `{"Error": "..."}` (shadertoy.rs:119-123).
+        Like the reference's fetch_code_from_last_pass (shadertoy.rs:126-132) the code of ALL passes is concatenated."""
+        import json
+        if isinstance(response, (bytes, bytearray)):
+            raw = bytes(response)
+        else:
+            raw = (response if isinstance(response, str) else json.dumps(response)).encode()
+        h = ctypes.c_void_p()
+        check(lib().s2m_shader_from_shadertoy_response(raw, len(raw), sdf.encode(), ctypes.byref(h)))
+        sh = cls(h)
+        lines = dict(l[5:].split(": ", 1) for l in sh.log.splitlines() if l.startswith("INFO Shader") and ": " in l)
+        sh.info = {"name": lines.get("Shader", ""), "username": lines.get("Shader author", "")}   # what the reference logs (shader.rs:115-116)
+        return sh
+
+    @classmethod
+    def from_shadertoy_api(cls, shader_id: str, sdf: str = "sdf", fetch=None) -> "Sdf3DShader":
+        """shader.rs:110 from_shadertoy_api: GET https://www.shadertoy.com/api/v1/shaders/{id}?key=... (shadertoy.rs:126-131),
+        then from_shadertoy_json.  `fetch(url) -> bytes` replaces the HTTP client (tests, proxies); a failed request is
+        S2mError(REQUEST), the reference's ShaderProcessingError::RequestError."""
+        url = f"https://www.shadertoy.com/api/v1/shaders/{shader_id}?key={cls.SHADERTOY_API_KEY}"
+        try:
+            if fetch is None:
+                import urllib.request
+                with urllib.request.urlopen(url, timeout=30) as r:
+                    body = r.read()
+            else:
+                body = fetch(url)
+        except _capi.S2mError:
+            raise
+        except Exception as e:
+            raise _capi.S2mError(_capi.ERR_REQUEST, f"request for {url} failed: {e}") from e
+        return cls.from_shadertoy_json(body, sdf)
+
     # --- reference API ------------------------------------------------------------------
     def add_to_source(self, source: str) -> None:
         check(lib().s2m_shader_add_to_source(self._h, source.encode()))

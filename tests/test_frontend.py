@@ -1341,3 +1341,53 @@ def test_byte_order_mark_and_crlf_line_ends(built, tmp_path):
     pts = points(2.0, 2000)
     va, vb = host_eval.eval_points(a.lower_to_cuda(), pts), host_eval.eval_points(b.lower_to_cuda(), pts)
     assert f32_equal(va, vb).all() and np.isfinite(va).all()
+
+
+def test_from_shadertoy_api_and_json(built):
+    """Sdf3DShader::from_shadertoy_api (shader.rs:110-144) with the HTTP client replaced: URL and key as the
+    reference builds them (shadertoy.rs:126-131), the code of all render passes concatenated (:126-132 of impl
+    Shader), `Error` responses -> ShaderError, a failed request -> RequestError, a missing SDF -> MissingSdf"""
+    import json
+    common = "float sphere(vec3 p, float r) { return length(p) - r; }\n"
+    image = "float sdf(vec3 p) { return sphere(p, 0.75); }\nvoid mainImage(out vec4 c, in vec2 u) { c = vec4(sdf(vec3(u, iTime))); }\n"
+    response = {"Shader": {"ver": "0.1", "info": {"id": "DldfR7", "name": "ball", "username": "someone"},
+                           "renderpass": [{"inputs": [], "outputs": [], "code": common, "name": "Common", "type": "common"},
+                                          {"inputs": [], "outputs": [], "code": image, "name": "Image", "type": "image"}]}}
+    seen = []
+
+    def fetch(url):
+        seen.append(url)
+        return json.dumps(response).encode()
+
+    sh = s2m.Sdf3DShader.from_shadertoy_api("DldfR7", "sdf", fetch=fetch)
+    assert seen == ["https://www.shadertoy.com/api/v1/shaders/DldfR7?key=rdnjhn"]
+    assert sh.info == {"name": "ball", "username": "someone"}
+    assert "fn sphere(" in sh.source and "fn sdf3d(p: vec3<f32>) -> f32 { return sdf(p); }" in sh.source and "mainImage" not in sh.source
+    pts = points(2.0, 500)
+    want = (np.sqrt(((pts[:, 0] * pts[:, 0]).astype(np.float32) + (pts[:, 1] * pts[:, 1]).astype(np.float32)).astype(np.float32)
+                    + (pts[:, 2] * pts[:, 2]).astype(np.float32)).astype(np.float32) - np.float32(0.75)).astype(np.float32)
+    assert f32_equal(host_eval.eval_points(sh.lower_to_cuda(), pts), want).all()
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_shadertoy_api("DldfR7", "distance", fetch=fetch)
+    assert e.value.kind == "MISSING_SDF"
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_shadertoy_api("nope", fetch=lambda url: b'{"Error": "Shader not found"}')
+    assert e.value.kind == "SHADER" and "Shader not found" in str(e.value)
+
+    def offline(url):
+        raise OSError("network unreachable")
+
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_shadertoy_api("DldfR7", fetch=offline)
+    assert e.value.kind == "REQUEST" and "network unreachable" in str(e.value)
+    for bad in ("[1, 2]", "{", '{"Shader": {"renderpass": [{"code": "abc}]}}', '{"Other": 1}', ""):
+        with pytest.raises(s2m.S2mError) as e:
+            s2m.Sdf3DShader.from_shadertoy_json(bad)
+        assert e.value.kind == "SHADER"
+    # JSON escapes in the code string: \n \t \" \\ \/ \u00e9 and a surrogate pair, nested objects with their own "code" keys are not passes
+    body = ('{"Shader": {"info": {"name": "esc \\u00e9", "username": "u", "tags": ["a", "b"]}, "ver": "0.1", "renderpass": ['
+            '{"inputs": [{"id": 1, "sampler": {"filter": "linear", "code": "not code"}}], "outputs": [], '
+            '"code": "// caf\\u00e9 \\ud83d\\ude00 \\"quoted\\" a\\/b\\nfloat sdf(vec3 p) {\\n\\treturn length(p) - 0.75; // back\\\\slash\\n}\\nvoid mainImage(out vec4 c, in vec2 u) { c = vec4(0.0); }\\n", "name": "Image", "type": "image"}]}}')
+    sh = s2m.Sdf3DShader.from_shadertoy_json(body)
+    assert sh.info == {"name": "esc \u00e9", "username": "u"}
+    assert f32_equal(host_eval.eval_points(sh.lower_to_cuda(), pts), want).all()
