@@ -95,6 +95,18 @@ impl Sdf3DShader {
         }
     }
 
+    /// shader.rs:110 `from_shadertoy_api` after the HTTP GET (`shadertoy::Shader::from_api`, shadertoy.rs:126-131):
+    /// `body` is the API response; an `{"Error": ...}` response becomes `ShaderError`, as in the reference.
+    pub fn from_shadertoy_response(body: &str, sdf: &str) -> Result<Self, ShaderProcessingError> {
+        let mut h = ptr::null_mut();
+        let f = CString::new(sdf).unwrap();
+        match check(unsafe { ffi::s2m_shader_from_shadertoy_response(body.as_ptr() as *const _, body.len(), f.as_ptr(), &mut h) }) {
+            Ok(()) => Ok(Self(h)),
+            Err(Error::Shader(e)) => Err(e),
+            Err(e) => Err(ShaderProcessingError::ShaderError(format!("{e:?}"))),
+        }
+    }
+
     /// shader.rs:155
     pub fn add_to_source(&mut self, source: &str) {
         let c = CString::new(source).expect("source contains a NUL byte");
