@@ -27,6 +27,10 @@ int main(int argc, char** argv) {
     const int kind = name.find(".glsl") != std::string::npos ? S2M_SRC_GLSL_FRAGMENT : S2M_SRC_SDF3D;
     s2m_shader* sh = nullptr;
     ++n;
+    if (name.find(".json") != std::string::npos) {  // a ShaderToy API response
+      if (s2m_shader_from_shadertoy_response(text.data(), text.size(), "sdf", &sh) == 0) { ++ok; s2m_shader_free(sh); }
+      continue;
+    }
     if (s2m_shader_from_source(text.data(), text.size(), kind, "sdf", nullptr, &sh) == 0) {
       char* c = nullptr;
       if (s2m_shader_lower_to_cuda(sh, &c) == 0) { ++ok; free(c); c = nullptr; if (s2m_shader_lower_to_cuda_packed(sh, &c) == 0) free(c); }
