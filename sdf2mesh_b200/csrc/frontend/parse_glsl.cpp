@@ -586,6 +586,7 @@ class GlslParser : public ParserBase {
     if (accept_ident("break")) { if (!loop_depth && !switch_depth) b.error("break outside of a loop or switch"); expect(";"); blk->body.push_back(mk_stmt(Stmt::Break)); return; }
     if (accept_ident("continue")) { if (!loop_depth) b.error("continue outside of a loop"); expect(";"); blk->body.push_back(mk_stmt(Stmt::Continue)); return; }
     if (accept_ident("discard")) { expect(";"); blk->body.push_back(mk_stmt(Stmt::Discard)); return; }
+    if (is_ident("precision") && peek(1).k == Token::Ident) { while (!is_punct(";") && peek().k != Token::End) advance(); expect(";"); return; }  // precision highp float;
     if (accept_ident("switch")) { blk->body.push_back(parse_switch(blk)); return; }
     SideScope sc(*this);
     for (;;) {  // `a = 1., b = 2.;` -- the comma operator at statement level is a sequence of statements
