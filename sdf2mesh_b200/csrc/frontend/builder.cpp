@@ -656,7 +656,8 @@ const BuiltinInfo kBuiltins[] = {
     {"fract", "fract", 1, 'm', 3},   {"sqrt", "sqrt", 1, 'm', 3},     {"inverseSqrt", "inversesqrt", 1, 'm', 1},
     {"inversesqrt", "inversesqrt", 1, 'm', 2},                         {"sin", "sin", 1, 'm', 3},       {"cos", "cos", 1, 'm', 3},
     {"tan", "tan", 1, 'm', 3},       {"asin", "asin", 1, 'm', 3},     {"acos", "acos", 1, 'm', 3},     {"atan", "atan", 1, 'm', 3},
-    {"sinh", "sinh", 1, 'm', 3},     {"cosh", "cosh", 1, 'm', 3},     {"tanh", "tanh", 1, 'm', 3},     {"exp", "exp", 1, 'm', 3},
+    {"sinh", "sinh", 1, 'm', 3},     {"cosh", "cosh", 1, 'm', 3},     {"tanh", "tanh", 1, 'm', 3},
+    {"asinh", "asinh", 1, 'm', 3},   {"acosh", "acosh", 1, 'm', 3},   {"atanh", "atanh", 1, 'm', 3},     {"exp", "exp", 1, 'm', 3},
     {"exp2", "exp2", 1, 'm', 3},     {"log", "log", 1, 'm', 3},       {"log2", "log2", 1, 'm', 3},     {"radians", "radians", 1, 'm', 3},
     {"degrees", "degrees", 1, 'm', 3}, {"round", "round", 1, 'm', 3}, {"roundEven", "round", 1, 'm', 2}, {"trunc", "trunc", 1, 'm', 3},
     {"saturate", "saturate", 1, 'm', 1}, {"normalize", "normalize", 1, 'v', 3}, {"length", "length", 1, 's', 3},

@@ -14,7 +14,8 @@
  * so the device and the oracle agree bit-for-bit on every SDF value (NaN payloads excepted).
  *
  * Accuracy (measured by tests/test_math.py against libm in double): <= 2.4 ulp for
- * sin cos tan asin acos atan atan2 exp exp2 log log2 pow on their usual domains; pow with an
+ * sin cos tan asin acos atan atan2 exp exp2 log log2 pow on their usual domains (<= 3 ulp for
+ * sinh cosh tanh asinh acosh atanh); pow with an
  * integer exponent |n| <= 8 is a multiplication chain (<= 5 ulp).
  *
  * C99 / C++ / CUDA compatible.  No includes on the device (NVRTC has no libc headers).
@@ -578,6 +579,35 @@ S2M_HD float s2m_tanh(float x) {
     float e = s2m__exp_core(2.0f * a);
     r = 1.0f - 2.0f / (e + 1.0f);
   }
+  return s2m_i2f(s2m_f2i(r) | (s2m_f2i(x) & (int)0x80000000));
+}
+
+/* ------------------------------------------------------------------ inverse hyperbolic (from log)
+ * log1p(u) for u >= 0 through log: w = fl(1 + u) carries a rounding error that the second term removes
+ * (log(1+u) = log(w) + log((1+u)/w) ~ log(w) - ((w - 1) - u) / w; w - 1 is exact). */
+S2M_HD float s2m__log1p_pos(float u) {
+  float w = 1.0f + u;
+  if (w == 1.0f) return u;
+  if (w == s2m_inf()) return w;
+  return s2m_log(w) - ((w - 1.0f) - u) / w;
+}
+S2M_HD float s2m_asinh(float x) {   /* log(a + sqrt(a^2 + 1)) = log1p(a + a^2 / (1 + sqrt(a^2 + 1))) */
+  float a = s2m_abs(x), r;
+  if (a != a) return x;
+  if (a > 1.0e9f) r = s2m_log(a) + 6.931471825e-01f;            /* a^2 would overflow; sqrt(a^2 + 1) = a to 1e-18 */
+  else { float s = a * a; r = s2m__log1p_pos(a + s / (1.0f + s2m_sqrt(s + 1.0f))); }
+  return s2m_i2f(s2m_f2i(r) | (s2m_f2i(x) & (int)0x80000000));
+}
+S2M_HD float s2m_acosh(float x) {   /* log(x + sqrt(x^2 - 1)) = log1p(d + sqrt(d (d + 2))), d = x - 1 */
+  if (!(x >= 1.0f)) return s2m_nan();
+  if (x > 1.0e9f) return s2m_log(x) + 6.931471825e-01f;
+  float d = x - 1.0f;
+  return s2m__log1p_pos(d + s2m_sqrt(d * (d + 2.0f)));
+}
+S2M_HD float s2m_atanh(float x) {   /* log((1 + a) / (1 - a)) / 2 = log1p(2a / (1 - a)) / 2 */
+  float a = s2m_abs(x), r;
+  if (!(a <= 1.0f)) return s2m_nan();
+  r = 0.5f * s2m__log1p_pos((a + a) / (1.0f - a));               /* a = 1: 2 / 0 = inf */
   return s2m_i2f(s2m_f2i(r) | (s2m_f2i(x) & (int)0x80000000));
 }
 

@@ -310,6 +310,7 @@ S2M_HD vec2 f_sincos_pair(float x) { vec2 r; s2m_sincos(x, &r.x, &r.y); return r
 S2M_MAP1(f_sin, s2m_sin)       S2M_MAP1(f_cos, s2m_cos)       S2M_MAP1(f_tan, s2m_tan)
 S2M_MAP1(f_asin, s2m_asin)     S2M_MAP1(f_acos, s2m_acos)     S2M_MAP1(f_atan, s2m_atan)
 S2M_MAP1(f_sinh, s2m_sinh)     S2M_MAP1(f_cosh, s2m_cosh)     S2M_MAP1(f_tanh, s2m_tanh)
+S2M_MAP1(f_asinh, s2m_asinh)   S2M_MAP1(f_acosh, s2m_acosh)   S2M_MAP1(f_atanh, s2m_atanh)
 S2M_MAP1(f_exp, s2m_exp)       S2M_MAP1(f_exp2, s2m_exp2)     S2M_MAP1(f_log, s2m_log)
 S2M_MAP1(f_log2, s2m_log2)     S2M_MAP1(f_radians, s2m_radians) S2M_MAP1(f_degrees, s2m_degrees)
 #undef S2M_MAP1

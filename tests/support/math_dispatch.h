@@ -2,7 +2,7 @@
 #pragma once
 #include "s2m_math.h"
 enum { FN_SIN, FN_COS, FN_TAN, FN_ASIN, FN_ACOS, FN_ATAN, FN_EXP, FN_EXP2, FN_LOG, FN_LOG2,
-       FN_SINH, FN_COSH, FN_TANH, FN_SQRT, FN_ABS, FN_FLOOR, FN_FRACT, FN_SIGN, FN_ROUND, FN_COUNT1,
+       FN_SINH, FN_COSH, FN_TANH, FN_SQRT, FN_ABS, FN_FLOOR, FN_FRACT, FN_SIGN, FN_ROUND, FN_ASINH, FN_ACOSH, FN_ATANH, FN_COUNT1,
        FN_ATAN2 = 100, FN_POW, FN_MIN, FN_MAX, FN_DIV, FN_FMOD, FN_MOD, FN_STEP };
 S2M_HD float s2m_dispatch1(int fn, float x) {
   switch (fn) {
@@ -13,6 +13,7 @@ S2M_HD float s2m_dispatch1(int fn, float x) {
     case FN_TANH: return s2m_tanh(x); case FN_SQRT: return s2m_sqrt(x); case FN_ABS: return s2m_abs(x);
     case FN_FLOOR: return s2m_floor(x); case FN_FRACT: return s2m_fract(x); case FN_SIGN: return s2m_sign(x);
     case FN_ROUND: return s2m_round(x);
+    case FN_ASINH: return s2m_asinh(x); case FN_ACOSH: return s2m_acosh(x); case FN_ATANH: return s2m_atanh(x);
   }
   return 0.0f;
 }

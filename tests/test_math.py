@@ -12,7 +12,8 @@ import pytest
 from tests.conftest import ROOT
 
 FN = {"sin": 0, "cos": 1, "tan": 2, "asin": 3, "acos": 4, "atan": 5, "exp": 6, "exp2": 7, "log": 8, "log2": 9,
-      "sinh": 10, "cosh": 11, "tanh": 12, "sqrt": 13, "abs": 14, "floor": 15, "fract": 16, "sign": 17, "round": 18}
+      "sinh": 10, "cosh": 11, "tanh": 12, "sqrt": 13, "abs": 14, "floor": 15, "fract": 16, "sign": 17, "round": 18,
+      "asinh": 19, "acosh": 20, "atanh": 21}
 FN2 = {"atan2": 100, "pow": 101, "min": 102, "max": 103, "div": 104, "fmod": 105, "mod": 106, "step": 107}
 
 
@@ -61,6 +62,13 @@ CASES = [
     ("log2", 10 ** RNG.uniform(-37, 38, N), np.log2, 2.0), ("sinh", RNG.uniform(-89, 89, N), np.sinh, 3.0),
     ("cosh", RNG.uniform(-89, 89, N), np.cosh, 3.0), ("tanh", RNG.uniform(-10, 10, N), np.tanh, 2.0),
 ]
+RNG2 = np.random.default_rng(2)   # its own stream: the cases above keep the samples they were tuned on
+CASES += [
+    ("asinh", RNG2.uniform(-20, 20, N), np.arcsinh, 3.0), ("asinh", 10 ** RNG2.uniform(-30, 38, N), np.arcsinh, 3.0),
+    ("asinh", -(10 ** RNG2.uniform(-8, 1, N)), np.arcsinh, 3.0), ("acosh", 1 + 10 ** RNG2.uniform(-7, 1, N), np.arccosh, 3.0),
+    ("acosh", 10 ** RNG2.uniform(0, 38, N), np.arccosh, 3.0), ("atanh", RNG2.uniform(-1, 1, N), np.arctanh, 3.0),
+    ("atanh", 10 ** RNG2.uniform(-30, 0, N), np.arctanh, 3.0), ("atanh", 1 - 10 ** RNG2.uniform(-7, 0, N), np.arctanh, 3.0),
+]
 
 
 @pytest.mark.parametrize("name,x,ref,tol", CASES, ids=[f"{c[0]}-{i}" for i, c in enumerate(CASES)])
@@ -102,6 +110,9 @@ def test_special_values(mathlib):
     same(map1(mathlib, FN["exp"], sp)[:5], [1.0, 1.0, inf, 0.0, nan])
     same(map1(mathlib, FN["log"], sp), [-inf, -inf, inf, nan, nan, 0.0, nan])
     same(map1(mathlib, FN["asin"], np.array([2.0, -2.0], np.float32)), [nan, nan])
+    same(map1(mathlib, FN["asinh"], sp), [0.0, -0.0, inf, -inf, nan, np.float32(np.arcsinh(1.0)), -np.float32(np.arcsinh(1.0))])
+    same(map1(mathlib, FN["acosh"], np.array([1.0, 0.5, -3.0, inf, nan, -inf], np.float32)), [0.0, nan, nan, inf, nan, nan])
+    same(map1(mathlib, FN["atanh"], np.array([0.0, -0.0, 1.0, -1.0, 1.5, -1.5, nan, inf], np.float32)), [0.0, -0.0, inf, -inf, nan, nan, nan, nan])
     # pow: C99 special cases
     A, B = np.meshgrid(sp, sp)
     with np.errstate(all="ignore"):
