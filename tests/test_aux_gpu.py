@@ -40,7 +40,7 @@ def test_device_math_is_bit_identical_to_host_math(ctx, host_math):
                         -103.9, -104.1, 105615.0, 105616.0, 1e9, 1e30, 0.70710678, 1.41421356], np.float32)
     xs = np.concatenate([special, rng.uniform(-30, 30, n), 10 ** rng.uniform(-45, 38, n), -(10 ** rng.uniform(-45, 38, n)),
                          rng.uniform(-1, 1, n), rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32).view(np.float32)]).astype(np.float32)
-    for fn in range(19):
+    for fn in range(19):   # 19-21 (asinh, acosh, atanh; added after the round's last GPU run) join once they have run on a device
         pts = np.stack([xs, np.zeros_like(xs), np.full_like(xs, fn)], 1)
         dev = mod.eval_points(pts)
         host = np.empty_like(xs)
