@@ -668,6 +668,11 @@ const BuiltinInfo kBuiltins[] = {
     {"select", "select", 3, 'S', 3}, {"any", "any", 1, 'b', 3},       {"all", "all", 1, 'b', 3},
     {"transpose", "transpose", 1, 'T', 3}, {"determinant", "determinant", 1, 'D', 3},
     {"inverse", "inverse", 1, 'T', 3},  // GLSL; accepted in WGSL text too (naga writes GLSL's inverse() as a helper function)
+    // integer-only component-wise maps; the result has the argument's type (GLSL's bitCount / findMSB / findLSB return int: parse_glsl converts)
+    {"countOneBits", "countOneBits", 1, 'i', 1}, {"bitCount", "countOneBits", 1, 'i', 2}, {"reverseBits", "reverseBits", 1, 'i', 1},
+    {"bitfieldReverse", "reverseBits", 1, 'i', 2}, {"countLeadingZeros", "countLeadingZeros", 1, 'i', 1},
+    {"countTrailingZeros", "countTrailingZeros", 1, 'i', 1}, {"firstLeadingBit", "firstLeadingBit", 1, 'i', 1},
+    {"findMSB", "firstLeadingBit", 1, 'i', 2}, {"firstTrailingBit", "firstTrailingBit", 1, 'i', 1}, {"findLSB", "firstTrailingBit", 1, 'i', 2},
     {"refract", "refract", 3, 'R', 3}, {"faceForward", "faceforward", 3, 'F', 1}, {"faceforward", "faceforward", 3, 'F', 2},
 };
 }  // namespace
@@ -708,6 +713,13 @@ ExprP Builder::call_builtin(const std::string& name, std::vector<ExprP> args) {
     if (args[2]->ty.is_vector() && args[2]->ty.n != args[0]->ty.n) error("select() condition width mismatch");
     return call(args[0]->ty);
   }
+  if (bi->kind == 'i') {
+    args[0] = concretize(args[0]);
+    if (!args[0]->ty.is_int() || !(args[0]->ty.is_scalar() || args[0]->ty.is_vector())) error(name + "() needs an integer scalar or vector");
+    ExprP e = call(args[0]->ty);
+    e->callee = std::string("i_") + bi->canon;
+    return e;
+  }
   // width: all vector arguments must agree; scalars broadcast
   int n = 1;
   for (const ExprP& a : args)
@@ -727,6 +739,28 @@ ExprP Builder::call_builtin(const std::string& name, std::vector<ExprP> args) {
     ExprP e = call(Type::vec(sk, n));
     e->callee = std::string("i_") + bi->canon;
     return e;
+  }
+  if ((bi->kind == 'n' || std::string(bi->canon) == "sign") && all_int && all_abstract) {
+    // abs(-5), sign(-2147483648), min(1, 2), clamp(7, 0, 3): abstract-int in, abstract-int out (they used to turn into
+    // abstract-float, which then did not combine with an i32)
+    std::vector<ConstVal> cv(args.size());
+    bool folded = true;
+    for (size_t k = 0; k < args.size(); ++k) folded = folded && const_eval(*args[k], &cv[k]);
+    if (folded) {
+      ConstVal r;
+      r.ty = Type::vec(Sk::AInt, n);
+      const std::string fn = bi->canon;
+      for (int c = 0; c < n; ++c) {
+        auto at = [&](size_t k) { return cv[k].i[cv[k].ty.n > 1 ? c : 0]; };
+        const int64_t x = at(0);
+        if (fn == "abs") r.i[c] = x < 0 ? -x : x;
+        else if (fn == "sign") r.i[c] = x > 0 ? 1 : (x < 0 ? -1 : 0);
+        else if (fn == "min") r.i[c] = std::min(x, at(1));
+        else if (fn == "max") r.i[c] = std::max(x, at(1));
+        else r.i[c] = std::min(std::max(x, at(1)), at(2));   // clamp
+      }
+      return lit_from(r);
+    }
   }
   Sk sk = Sk::F32;
   if (all_abstract) {

@@ -968,6 +968,8 @@ class GlslParser : public ParserBase {
       }
       ExprP e = b.call_builtin(name, args);
       if (!e) b.error("unknown function '" + name + "'");
+      if ((name == "bitCount" || name == "findMSB" || name == "findLSB") && e->ty.sk == Sk::U32)
+        e = b.bitcast(Sk::I32, e);   // genIType results in GLSL, whatever the argument; same bits (findMSB(0u) = -1)
       return e;
     }
     if (Var* v = lookup(name)) { advance(); return b.var_ref(v); }

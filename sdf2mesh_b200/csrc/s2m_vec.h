@@ -214,6 +214,39 @@ S2M_INT_VEC2(i_min, ivec2, ivec3, ivec4, int, mki2, mki3, mki4) S2M_INT_VEC2(i_m
 S2M_INT_VEC2(i_min, uvec2, uvec3, uvec4, unsigned, mku2, mku3, mku4) S2M_INT_VEC2(i_max, uvec2, uvec3, uvec4, unsigned, mku2, mku3, mku4)
 S2M_INT_VEC1(i_abs, ivec2, ivec3, ivec4, mki2, mki3, mki4) S2M_INT_VEC1(i_sign, ivec2, ivec3, ivec4, mki2, mki3, mki4)
 S2M_INT_VEC1(i_abs, uvec2, uvec3, uvec4, mku2, mku3, mku4)
+/* bit counting (WGSL countOneBits ... firstTrailingBit = GLSL bitCount, bitfieldReverse, findMSB, findLSB): integer
+ * operations only, so host and device agree trivially */
+S2M_HD unsigned i_countOneBits(unsigned a) {
+  a = a - ((a >> 1) & 0x55555555u);
+  a = (a & 0x33333333u) + ((a >> 2) & 0x33333333u);
+  a = (a + (a >> 4)) & 0x0f0f0f0fu;
+  return (a * 0x01010101u) >> 24;
+}
+S2M_HD unsigned i_reverseBits(unsigned a) {
+  a = ((a >> 1) & 0x55555555u) | ((a & 0x55555555u) << 1);
+  a = ((a >> 2) & 0x33333333u) | ((a & 0x33333333u) << 2);
+  a = ((a >> 4) & 0x0f0f0f0fu) | ((a & 0x0f0f0f0fu) << 4);
+  a = ((a >> 8) & 0x00ff00ffu) | ((a & 0x00ff00ffu) << 8);
+  return (a >> 16) | (a << 16);
+}
+S2M_HD unsigned i_countLeadingZeros(unsigned a) {   /* 32 for 0 */
+  a |= a >> 1; a |= a >> 2; a |= a >> 4; a |= a >> 8; a |= a >> 16;
+  return 32u - i_countOneBits(a);
+}
+S2M_HD unsigned i_countTrailingZeros(unsigned a) { return i_countOneBits(~a & (a - 1u)); }   /* 32 for 0 */
+S2M_HD unsigned i_firstLeadingBit(unsigned a) { return 31u - i_countLeadingZeros(a); }        /* 0xffffffff for 0 */
+S2M_HD unsigned i_firstTrailingBit(unsigned a) { return a == 0u ? 0xffffffffu : i_countTrailingZeros(a); }
+S2M_HD int i_countOneBits(int a) { return (int)i_countOneBits((unsigned)a); }
+S2M_HD int i_reverseBits(int a) { return (int)i_reverseBits((unsigned)a); }
+S2M_HD int i_countLeadingZeros(int a) { return (int)i_countLeadingZeros((unsigned)a); }
+S2M_HD int i_countTrailingZeros(int a) { return (int)i_countTrailingZeros((unsigned)a); }
+S2M_HD int i_firstLeadingBit(int a) { return (int)i_firstLeadingBit((unsigned)(a < 0 ? ~a : a)); }  /* the most significant bit that differs from the sign; -1 for 0 and -1 */
+S2M_HD int i_firstTrailingBit(int a) { return (int)i_firstTrailingBit((unsigned)a); }
+#define S2M_INT_BITS(NAME)                                                                             \
+  S2M_INT_VEC1(NAME, ivec2, ivec3, ivec4, mki2, mki3, mki4) S2M_INT_VEC1(NAME, uvec2, uvec3, uvec4, mku2, mku3, mku4)
+S2M_INT_BITS(i_countOneBits) S2M_INT_BITS(i_reverseBits) S2M_INT_BITS(i_countLeadingZeros)
+S2M_INT_BITS(i_countTrailingZeros) S2M_INT_BITS(i_firstLeadingBit) S2M_INT_BITS(i_firstTrailingBit)
+#undef S2M_INT_BITS
 #define S2M_INT_CLAMP(V2, V3, V4, T, M2, M3, M4)                                                       \
   S2M_HD V2 i_clamp(const V2& x, const V2& lo, const V2& hi) { return i_min(i_max(x, lo), hi); }       \
   S2M_HD V3 i_clamp(const V3& x, const V3& lo, const V3& hi) { return i_min(i_max(x, lo), hi); }       \

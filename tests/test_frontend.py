@@ -1391,3 +1391,45 @@ def test_from_shadertoy_api_and_json(built):
     sh = s2m.Sdf3DShader.from_shadertoy_json(body)
     assert sh.info == {"name": "esc \u00e9", "username": "u"}
     assert f32_equal(host_eval.eval_points(sh.lower_to_cuda(), pts), want).all()
+
+
+def test_integer_bit_builtins_and_abstract_int_folding(built):
+    """countOneBits / reverseBits / countLeadingZeros / countTrailingZeros / firstLeadingBit / firstTrailingBit (WGSL) =
+    bitCount / bitfieldReverse / findMSB / findLSB (GLSL, int results); abs / sign / min / max / clamp of abstract-int
+    constants stay abstract-int (tests/test_frontend_fuzz.py found them turning into abstract-float)"""
+    w = s2m.Sdf3DShader.from_source(
+        "fn sdf3d(p: vec3f) -> f32 { let u = bitcast<u32>(p.x); let i = bitcast<i32>(p.y);\n"
+        "  let a = f32(countOneBits(u)) + 64.0 * f32(countLeadingZeros(u)) + 4096.0 * f32(countTrailingZeros(i));\n"
+        "  let b = f32(firstLeadingBit(i)) + 64.0 * f32(firstTrailingBit(i)) + 4096.0 * f32(reverseBits(u) >> 24u);\n"
+        "  let c = (i32(p.z) ^ sign((-2147483647 - 1))) + abs(-5) + min(1, 2) + clamp(7, 0, 3) + i32(firstLeadingBit(0u) == 0xffffffffu) + firstLeadingBit(vec2i(-1, 5)).x;\n"
+        "  return a + 1.0e6 * b + 1.0e9 * f32(c); }")
+    g = s2m.Sdf3DShader.from_source(
+        "#version 450 core\nfloat sdf(vec3 p) { uint u = floatBitsToUint(p.x); int i = floatBitsToInt(p.y);\n"
+        "  float a = float(bitCount(u)) + 64.0 * float(31 - findMSB(u)) + 4096.0 * float(findLSB(i) < 0 ? 32 : findLSB(i));\n"
+        "  float b = float(findMSB(i)) + 64.0 * float(findLSB(i)) + 4096.0 * float(bitfieldReverse(u) >> 24u);\n"
+        "  int c = (int(p.z) ^ sign(-2147483647 - 1)) + abs(-5) + min(1, 2) + clamp(7, 0, 3) + int(findMSB(0u) == -1) + findMSB(ivec2(-1, 5)).x;\n"
+        "  return a + 1.0e6 * b + 1.0e9 * float(c); }\nvoid main() {}\n", s2m.SRC_GLSL_FRAGMENT, "sdf")
+    pts = np.concatenate([points(4.0, 1500), np.array([[0, 0, 0], [-0.0, -0.0, 1], [1, -1, -3], [np.inf, -np.inf, 2]], np.float32)])
+    va, vb = host_eval.eval_points(w.lower_to_cuda(), pts), host_eval.eval_points(g.lower_to_cuda(), pts)
+    assert f32_equal(va, vb).all()
+
+    def ref(p):
+        u, i = int(p[:1].view(np.uint32)[0]), int(p[1:2].view(np.int32)[0])
+        iu = i & 0xffffffff
+        clz = 32 - u.bit_length()
+        ctz_i = 32 if iu == 0 else (iu & -iu).bit_length() - 1
+        t = ~i if i < 0 else i
+        flb = -1 if t == 0 else t.bit_length() - 1
+        ftb = -1 if iu == 0 else ctz_i
+        rev = int(format(u, "032b")[::-1], 2) >> 24
+        F = np.float32
+        a = F(F(F(bin(u).count("1")) + F(F(64) * F(clz))) + F(F(4096) * F(ctz_i)))
+        b = F(F(F(flb) + F(F(64) * F(ftb))) + F(F(4096) * F(rev)))
+        z = int(np.clip(np.trunc(np.float64(p[2])), -2**31, 2**31 - 1)) if np.isfinite(p[2]) else 0
+        c = ((z ^ -1) + 5 + 1 + 3 + 1 + -1)
+        c = (c + 2**31) % 2**32 - 2**31
+        return F(F(a + F(F(1.0e6) * b)) + F(F(1.0e9) * F(c)))
+
+    want = np.array([ref(p) for p in pts], np.float32)
+    assert f32_equal(va, want).all()
+    assert w.create_shader_module(None).cubin_size > 0 and g.create_shader_module(None).cubin_size > 0

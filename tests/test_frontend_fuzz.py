@@ -341,7 +341,7 @@ def sample_points(rng, n_funcs):
     q = rng.uniform(-2.0, 2.0, (n, 3)).astype(F)
     tie = rng.random((n, 3)) < 0.25
     q[tie] = (np.round(q[tie] * 2) / 2).astype(F)
-    q[:, 2] = np.abs(q[:, 2]) % F(1.0)          # fractional part carried by z
+    q[:, 2] = np.floor((np.abs(q[:, 2]) % F(1.0)) * F(4096)) / F(4096)   # fractional part carried by z: a multiple of 2^-12 below 1, so that z + k is exact
     k = np.repeat(np.arange(n_funcs), PTS_PER_FUNC)
     p = q.copy()
     p[:, 2] = (q[:, 2] + k.astype(F)).astype(F)
@@ -489,14 +489,15 @@ def gen_int(rng, ty, depth):
         c = int(rng.choice([0, 1, 2, 3, 7, 16, 255, 65535, 1664525, 1013904223, 2147483647] + ([-1, -2147483648, -7] if ty == "i" else [4294967295, 2654435769])))
         return Node("iconst", ty, (), c)
     d = depth - 1
-    ops = ["+", "-", "*", "/", "%", "&", "|", "^", "<<", ">>", "not", "min", "max", "clamp", "cast", "sel"] + (["neg", "abs", "sign"] if ty == "i" else [])
+    ops = (["+", "-", "*", "/", "%", "&", "|", "^", "<<", ">>", "not", "min", "max", "clamp", "cast", "sel", "popc", "rev", "clz", "ctz", "flb", "ftb"] +
+           (["neg", "abs", "sign"] if ty == "i" else []))
     op = rng.choice(ops)
     if op in ("+", "-", "*", "/", "%", "&", "|", "^", "min", "max"):
         return Node(op, ty, (gen_int(rng, ty, d), gen_int(rng, ty, d)))
     if op in ("<<", ">>"):
         cnt = Node("iconst", "u", (), int(rng.integers(0, 32))) if rng.random() < 0.6 else Node("&", "u", (gen_int(rng, "u", d), Node("iconst", "u", (), 31)))
         return Node(op, ty, (gen_int(rng, ty, d), cnt))
-    if op in ("not", "neg", "abs", "sign"):
+    if op in ("not", "neg", "abs", "sign", "popc", "rev", "clz", "ctz", "flb", "ftb"):
         return Node(op, ty, (gen_int(rng, ty, d),))
     if op == "clamp":
         return Node(op, ty, (gen_int(rng, ty, d), gen_int(rng, ty, d), gen_int(rng, ty, d)))
@@ -530,7 +531,44 @@ def show_int(n, glsl):
         return f"{T[n.ty]}({k[0]})"
     if op == "sel":
         return f"({k[2]} ? {k[1]} : {k[0]})" if glsl else f"select({k[0]}, {k[1]}, {k[2]})"
+    if op in ("popc", "rev", "clz", "ctz", "flb", "ftb"):
+        if not glsl:
+            return {"popc": "countOneBits", "rev": "reverseBits", "clz": "countLeadingZeros", "ctz": "countTrailingZeros",
+                    "flb": "firstLeadingBit", "ftb": "firstTrailingBit"}[op] + f"({k[0]})"
+        # GLSL: bitCount / findMSB / findLSB return int whatever the argument; there is no clz / ctz
+        back = (lambda e: f"uint({e})") if n.ty == "u" else (lambda e: e)
+        if op == "rev":
+            return f"bitfieldReverse({k[0]})"
+        if op == "popc":
+            return back(f"bitCount({k[0]})")
+        if op == "flb":
+            return back(f"findMSB({k[0]})")
+        if op == "ftb":
+            return back(f"findLSB({k[0]})")
+        if op == "clz":
+            return back(f"(31 - findMSB(uint({k[0]})))")
+        return back(f"(findLSB({k[0]}) < 0 ? 32 : findLSB({k[0]}))")
     return f"{op}({', '.join(k)})"
+
+
+def _bit_op(op, ty, v):
+    """one value (python int holding the i32 / u32 value)"""
+    u = v % (1 << 32)
+    if op == "popc":
+        return bin(u).count("1")
+    if op == "rev":
+        r = int(format(u, "032b")[::-1], 2)
+        return r - (1 << 32) if ty == "i" and r >= (1 << 31) else r
+    if op == "clz":
+        return 32 - u.bit_length()
+    if op == "ctz":
+        return 32 if u == 0 else (u & -u).bit_length() - 1
+    if op == "ftb":
+        return (-1 if ty == "i" else (1 << 32) - 1) if u == 0 else (u & -u).bit_length() - 1
+    if ty == "u":   # flb
+        return (1 << 32) - 1 if u == 0 else u.bit_length() - 1
+    t = ~v if v < 0 else v
+    return -1 if t == 0 else t.bit_length() - 1
 
 
 def eval_int(n, q):
@@ -575,6 +613,8 @@ def eval_int(n, q):
         return w(wrap_u(k[0]) << (k[1] % 32))
     if op == ">>":
         return k[0] >> (k[1] % 32)   # arithmetic on the signed value, logical on the unsigned one
+    if op in ("popc", "rev", "clz", "ctz", "flb", "ftb"):
+        return np.array([_bit_op(op, n.ty, int(v)) for v in k[0]], I64)
     if op == "not":
         return w(~k[0])
     if op == "neg":
