@@ -160,3 +160,17 @@ def test_rust_binding_declares_the_same_abi():
         body_r = re.search(r"pub struct %s \{(.*?)\n\}" % struct, ffi, re.S).group(1)
         fields_r = re.findall(r"pub ([a-z_0-9]+):", body_r)
         assert fields_r == [f for f in fields_c if f], f"{struct}: {fields_r} vs {fields_c}"
+
+
+def test_missing_library_fails_loudly(built, tmp_path):
+    """no CPU fallback: without the built shared library the package refuses to do anything (a copy of the package
+    without its .so, in a fresh interpreter)"""
+    import shutil
+    import sys
+    pkg = tmp_path / "sdf2mesh_b200"
+    shutil.copytree(os.path.join(ROOT, "sdf2mesh_b200"), pkg, ignore=shutil.ignore_patterns("*.so", "csrc", "__pycache__", "sdf2mesh"))
+    code = ("import sdf2mesh_b200 as s2m\n"
+            "try:\n    s2m.Sdf3DShader.from_source('fn sdf3d(p: vec3f) -> f32 { return 0.0; }')\n"
+            "except ImportError as e:\n    print('IMPORTERROR', e)\n")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=tmp_path, env={**os.environ, "PYTHONPATH": str(tmp_path)})
+    assert "IMPORTERROR" in p.stdout and "no CPU fallback" in p.stdout, p.stdout + p.stderr
