@@ -627,24 +627,57 @@ class GlslParser : public ParserBase {
     expect("{");
     ++switch_depth;
     push_scope();
-    StmtP cur;
-    while (!is_punct("}")) {
-      if (peek().k == Token::End) perr("unterminated switch");
-      if (is_ident("case") || is_ident("default")) {
-        const bool starts_new = !cur || !cur->body[0]->body.empty();
-        if (starts_new) {
-          if (cur && !ends_flow(*cur->body[0])) b.unsupported("switch case that falls through into the next one");
-          cur = mk_stmt(Stmt::Case);
-          cur->body.push_back(mk_stmt(Stmt::Block));
-          sw->body.push_back(cur);
+    // Groups of labels and the statements that follow them.  The IR (like WGSL) has no fall-through: a group that
+    // runs into the next label without break / return / continue / discard gets the statements of the following
+    // group(s) parsed into it again, up to the first one that leaves -- which is what falling through executes.
+    struct Group { size_t labels = 0, stmts = 0, end = 0; };
+    std::vector<Group> groups;
+    {
+      int depth = 0;
+      size_t i = pos;
+      bool in_labels = false;
+      for (;; ++i) {
+        const Token& t = toks[i];
+        if (t.k == Token::End) perr("unterminated switch");
+        if (t.k == Token::Punct && (t.text == "{" || t.text == "(" || t.text == "[")) ++depth;
+        if (t.k == Token::Punct && (t.text == "}" || t.text == ")" || t.text == "]")) { if (depth == 0) break; --depth; }
+        if (depth == 0 && t.k == Token::Ident && (t.text == "case" || t.text == "default")) {
+          if (!in_labels) { if (!groups.empty()) groups.back().end = i; groups.push_back(Group()); groups.back().labels = i; in_labels = true; }
+          int ternaries = 0;   // skip to the label's own ':'
+          for (++i;; ++i) {
+            const Token& u = toks[i];
+            if (u.k == Token::End) perr("unterminated case label");
+            if (u.k == Token::Punct && u.text == "?") ++ternaries;
+            if (u.k == Token::Punct && u.text == ":") { if (ternaries == 0) break; --ternaries; }
+          }
+          groups.back().stmts = i + 1;
+          continue;
         }
-        if (accept_ident("default")) cur->is_default = true;
-        else { advance(); cur->case_values.push_back(case_value(parse_binary(0), sw->a->ty)); }
-        expect(":");
-        continue;
+        if (groups.empty()) perr("statement before the first case label");
+        in_labels = false;
       }
-      if (!cur) perr("statement before the first case label");
-      parse_statement_into(cur->body[0]);
+      if (!groups.empty()) groups.back().end = i;
+      for (Group& g : groups) if (g.end < g.stmts) g.end = g.stmts;
+      // parse group by group; `i` is the closing brace
+      for (size_t g = 0; g < groups.size(); ++g) {
+        StmtP cur = mk_stmt(Stmt::Case);
+        cur->body.push_back(mk_stmt(Stmt::Block));
+        sw->body.push_back(cur);
+        pos = groups[g].labels;
+        while (pos < groups[g].stmts) {
+          if (accept_ident("default")) cur->is_default = true;
+          else { if (!accept_ident("case")) perr("expected a case label"); cur->case_values.push_back(case_value(parse_binary(0), sw->a->ty)); }
+          expect(":");
+        }
+        while (pos < groups[g].end) parse_statement_into(cur->body[0]);
+        for (size_t h = g + 1; h < groups.size() && !ends_flow(*cur->body[0]); ++h) {
+          push_scope();   // the statements are parsed a second time: their declarations are new variables
+          pos = groups[h].stmts;
+          while (pos < groups[h].end) parse_statement_into(cur->body[0]);
+          pop_scope();
+        }
+      }
+      pos = i;
     }
     expect("}");
     pop_scope();

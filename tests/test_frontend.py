@@ -491,11 +491,10 @@ def test_mutable_globals_switch_structs_arrays(built, tmp_path):
         assert f32_equal(host_eval.eval_points(cuda, pts), want).all(), lang
         assert sh.create_shader_module(None).cubin_size > 0   # NVRTC accepts it for sm_100a
     assert "struct Scene {" in shaders["glsl"].source and "var<private> evals: i32;" in shaders["glsl"].source
-    # GLSL fall-through between non-empty cases is not modelled
-    frag.write_text("#version 450\nfloat sdf(vec3 p) { float w = 0.0; switch (int(p.x)) { case 0: w = 1.0; case 1: w = 2.0; break; } return w; }\nvoid main() {}\n")
-    with pytest.raises(s2m.S2mError) as e:
-        s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
-    assert "falls through" in str(e.value)
+    # GLSL fall-through between non-empty cases: the following statements are parsed into the falling case (test_glsl_switch_fall_through)
+    frag.write_text("#version 450\nfloat sdf(vec3 p) { float w = 0.0; switch (int(p.x)) { case 0: w = 1.0; case 1: w += 2.0; break; } return w; }\nvoid main() {}\n")
+    fall = s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    assert host_eval.eval_points(fall.lower_to_cuda(), np.array([[0.5, 0, 0], [1.5, 0, 0], [2.5, 0, 0]], np.float32)).tolist() == [3.0, 2.0, 0.0]
 
 
 def test_integer_vectors_and_bit_functions(built, tmp_path):
@@ -1433,3 +1432,55 @@ def test_integer_bit_builtins_and_abstract_int_folding(built):
     want = np.array([ref(p) for p in pts], np.float32)
     assert f32_equal(va, want).all()
     assert w.create_shader_module(None).cubin_size > 0 and g.create_shader_module(None).cubin_size > 0
+
+
+def test_glsl_switch_fall_through(built):
+    """a case that runs into the next label executes the following cases' statements up to the first break / return:
+    the front-end parses those statements into the falling case again (the IR, like WGSL, has no fall-through)"""
+    src = textwrap.dedent("""\
+        #version 450 core
+        float sdf(vec3 p) {
+            int k = int(floor(p.x));
+            float r = 0.;
+            switch (k) {
+                case 0: r = 1.; break;
+                case 1: r = 2.;            // falls into default
+                default: r += 3.;          // falls into case 5
+                case 5: { float t = 10.; r += t; }
+                case 6: case 7: r += 100.; if (p.y > 0.) break; r += 1000.;
+                case 8: r += 1e4; break;
+                case 9: r = (p.y > 0. ? 7. : 8.);
+            }
+            return r;
+        }
+        void main() {}
+        """)
+    sh = s2m.Sdf3DShader.from_source(src, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    xs = np.arange(-1, 11)
+    pts = np.stack([xs + 0.5, np.where(xs % 2 == 0, 1.0, -1.0), np.zeros(len(xs))], 1).astype(np.float32)
+
+    def ref(k, y):
+        r = 0.0
+        for step in range({0: 0, 1: 1, 5: 3, 6: 4, 7: 4, 8: 5, 9: 6}.get(k, 2), 7):
+            if step == 0:
+                return 1.0
+            if step == 1:
+                r = 2.0
+            if step == 2:
+                r += 3.0
+            if step == 3:
+                r += 10.0
+            if step == 4:
+                r += 100.0
+                if y > 0:
+                    return r
+                r += 1000.0
+            if step == 5:
+                return r + 1e4
+            if step == 6:
+                r = 7.0 if y > 0 else 8.0
+        return r
+
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+    assert got.tolist() == [ref(int(np.floor(p[0])), p[1]) for p in pts]
+    assert sh.create_shader_module(None).cubin_size > 0
