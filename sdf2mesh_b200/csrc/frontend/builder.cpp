@@ -673,6 +673,8 @@ const BuiltinInfo kBuiltins[] = {
     {"bitfieldReverse", "reverseBits", 1, 'i', 2}, {"countLeadingZeros", "countLeadingZeros", 1, 'i', 1},
     {"countTrailingZeros", "countTrailingZeros", 1, 'i', 1}, {"firstLeadingBit", "firstLeadingBit", 1, 'i', 1},
     {"findMSB", "firstLeadingBit", 1, 'i', 2}, {"firstTrailingBit", "firstTrailingBit", 1, 'i', 1}, {"findLSB", "firstTrailingBit", 1, 'i', 2},
+    {"extractBits", "extractBits", 3, 'E', 1}, {"bitfieldExtract", "extractBits", 3, 'E', 2},
+    {"insertBits", "insertBits", 4, 'E', 1}, {"bitfieldInsert", "insertBits", 4, 'E', 2},
     {"refract", "refract", 3, 'R', 3}, {"faceForward", "faceforward", 3, 'F', 1}, {"faceforward", "faceforward", 3, 'F', 2},
 };
 }  // namespace
@@ -712,6 +714,20 @@ ExprP Builder::call_builtin(const std::string& name, std::vector<ExprP> args) {
     args[0] = concretize(args[0]); args[1] = concretize(args[1]);
     if (args[2]->ty.is_vector() && args[2]->ty.n != args[0]->ty.n) error("select() condition width mismatch");
     return call(args[0]->ty);
+  }
+  if (bi->kind == 'E') {  // extractBits(e, offset, count) / insertBits(e, newbits, offset, count): offset and count are scalars, u32 in the IR
+    const size_t nv = args.size() - 2;
+    for (size_t k = 0; k < nv; ++k) args[k] = concretize(args[k]);
+    if (!args[0]->ty.is_int() || !(args[0]->ty.is_scalar() || args[0]->ty.is_vector())) error(name + "() needs an integer scalar or vector");
+    if (nv == 2) { if (args[1]->ty.is_abstract()) args[1] = coerce(args[1], args[0]->ty, "insertBits()"); if (args[1]->ty != args[0]->ty) error(name + "(): value and inserted bits differ in type"); }
+    for (size_t k = nv; k < args.size(); ++k) {
+      if (!args[k]->ty.is_int() || !args[k]->ty.is_scalar()) error(name + "(): offset and count must be integer scalars");
+      if (args[k]->ty.is_abstract()) args[k] = coerce(args[k], Type::scalar(Sk::U32), "bit-field argument");
+      else if (args[k]->ty.sk != Sk::U32) { if (lang == Lang::Wgsl) error(name + "(): offset and count must be u32"); args[k] = convert_sk(args[k], Sk::U32); }
+    }
+    ExprP e = call(args[0]->ty);
+    e->callee = std::string("i_") + bi->canon;
+    return e;
   }
   if (bi->kind == 'i') {
     args[0] = concretize(args[0]);

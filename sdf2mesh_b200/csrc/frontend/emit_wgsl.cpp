@@ -154,7 +154,8 @@ class WgslWriter {
         }
         std::string s = wgsl_builtin(name) + "(";
         for (size_t i = 0; i < e.args.size(); ++i) {
-          const bool keep_scalar = (name == "mix" && i == 2) || (name == "refract" && i == 2) || name == "dot" || name == "length" || name == "distance" || name == "select" || name == "any" || name == "all";
+          const bool keep_scalar = (name == "mix" && i == 2) || (name == "refract" && i == 2) || name == "dot" || name == "length" || name == "distance" || name == "select" || name == "any" || name == "all" ||
+                                   (name == "extractBits" && i >= 1) || (name == "insertBits" && i >= 2);   // offset, count: u32 scalars
           s += (i ? ", " : "") + (keep_scalar ? expr(*e.args[i]) : splat_to(*e.args[i], n));
         }
         return s + ")";

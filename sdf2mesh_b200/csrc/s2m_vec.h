@@ -242,6 +242,34 @@ S2M_HD int i_countLeadingZeros(int a) { return (int)i_countLeadingZeros((unsigne
 S2M_HD int i_countTrailingZeros(int a) { return (int)i_countTrailingZeros((unsigned)a); }
 S2M_HD int i_firstLeadingBit(int a) { return (int)i_firstLeadingBit((unsigned)(a < 0 ? ~a : a)); }  /* the most significant bit that differs from the sign; -1 for 0 and -1 */
 S2M_HD int i_firstTrailingBit(int a) { return (int)i_firstTrailingBit((unsigned)a); }
+/* extractBits / insertBits (GLSL bitfieldExtract / bitfieldInsert) with WGSL's clamping: o = min(offset, 32), c = min(count, 32 - o) */
+S2M_HD unsigned i_extractBits(unsigned e, unsigned offset, unsigned count) {
+  const unsigned o = offset < 32u ? offset : 32u, c = count < 32u - o ? count : 32u - o;
+  if (c == 0u) return 0u;
+  return (e >> o) & (c == 32u ? 0xffffffffu : ((1u << c) - 1u));   /* o < 32 here: c > 0 */
+}
+S2M_HD int i_extractBits(int e, unsigned offset, unsigned count) {
+  const unsigned o = offset < 32u ? offset : 32u, c = count < 32u - o ? count : 32u - o;
+  if (c == 0u) return 0;
+  return (int)((unsigned)e << (32u - c - o)) >> (32u - c);        /* sign-extended */
+}
+S2M_HD unsigned i_insertBits(unsigned e, unsigned newbits, unsigned offset, unsigned count) {
+  const unsigned o = offset < 32u ? offset : 32u, c = count < 32u - o ? count : 32u - o;
+  if (c == 0u) return e;
+  const unsigned mask = (c == 32u ? 0xffffffffu : ((1u << c) - 1u)) << o;
+  return (e & ~mask) | ((newbits << o) & mask);
+}
+S2M_HD int i_insertBits(int e, int newbits, unsigned offset, unsigned count) { return (int)i_insertBits((unsigned)e, (unsigned)newbits, offset, count); }
+#define S2M_INT_FIELD(V2, V3, V4, M2, M3, M4)                                                          \
+  S2M_HD V2 i_extractBits(const V2& e, unsigned o, unsigned c) { return M2(i_extractBits(e.x, o, c), i_extractBits(e.y, o, c)); } \
+  S2M_HD V3 i_extractBits(const V3& e, unsigned o, unsigned c) { return M3(i_extractBits(e.x, o, c), i_extractBits(e.y, o, c), i_extractBits(e.z, o, c)); } \
+  S2M_HD V4 i_extractBits(const V4& e, unsigned o, unsigned c) { return M4(i_extractBits(e.x, o, c), i_extractBits(e.y, o, c), i_extractBits(e.z, o, c), i_extractBits(e.w, o, c)); } \
+  S2M_HD V2 i_insertBits(const V2& e, const V2& n, unsigned o, unsigned c) { return M2(i_insertBits(e.x, n.x, o, c), i_insertBits(e.y, n.y, o, c)); } \
+  S2M_HD V3 i_insertBits(const V3& e, const V3& n, unsigned o, unsigned c) { return M3(i_insertBits(e.x, n.x, o, c), i_insertBits(e.y, n.y, o, c), i_insertBits(e.z, n.z, o, c)); } \
+  S2M_HD V4 i_insertBits(const V4& e, const V4& n, unsigned o, unsigned c) { return M4(i_insertBits(e.x, n.x, o, c), i_insertBits(e.y, n.y, o, c), i_insertBits(e.z, n.z, o, c), i_insertBits(e.w, n.w, o, c)); }
+S2M_INT_FIELD(ivec2, ivec3, ivec4, mki2, mki3, mki4)
+S2M_INT_FIELD(uvec2, uvec3, uvec4, mku2, mku3, mku4)
+#undef S2M_INT_FIELD
 #define S2M_INT_BITS(NAME)                                                                             \
   S2M_INT_VEC1(NAME, ivec2, ivec3, ivec4, mki2, mki3, mki4) S2M_INT_VEC1(NAME, uvec2, uvec3, uvec4, mku2, mku3, mku4)
 S2M_INT_BITS(i_countOneBits) S2M_INT_BITS(i_reverseBits) S2M_INT_BITS(i_countLeadingZeros)

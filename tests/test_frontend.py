@@ -1484,3 +1484,53 @@ def test_glsl_switch_fall_through(built):
     got = host_eval.eval_points(sh.lower_to_cuda(), pts)
     assert got.tolist() == [ref(int(np.floor(p[0])), p[1]) for p in pts]
     assert sh.create_shader_module(None).cubin_size > 0
+
+
+def test_extract_and_insert_bits(built):
+    """extractBits / insertBits (GLSL bitfieldExtract / bitfieldInsert) with WGSL's clamping of offset and count, signed
+    extraction sign-extends; offset and count stay scalars in the WGSL text when the value is a vector"""
+    w = ("fn sdf3d(p: vec3f) -> f32 { let u = bitcast<u32>(p.x); let i = bitcast<i32>(p.x); let o = u32(abs(p.y) * 40.0); let c = u32(abs(p.z) * 40.0);\n"
+         " return f32(extractBits(u, o, c) & 0xffffu) + 65536.0 * f32(extractBits(i, o, c) & 0xff) + f32(insertBits(u, 0x5a5a5a5au, o, c) >> 20u) * 0.0001"
+         " + f32(extractBits(vec2u(u, 7u), 1u, 2u).y) * 1e8 + f32(insertBits(i, -1, o, c) & 0xfff) * 1e-8; }")
+    g = ("#version 450 core\nfloat sdf(vec3 p) { uint u = floatBitsToUint(p.x); int i = floatBitsToInt(p.x); int o = int(abs(p.y) * 40.0); int c = int(abs(p.z) * 40.0);\n"
+         " return float(bitfieldExtract(u, o, c) & 0xffffu) + 65536.0 * float(bitfieldExtract(i, o, c) & 0xff) + float(bitfieldInsert(u, 0x5a5a5a5au, o, c) >> 20u) * 0.0001"
+         " + float(bitfieldExtract(uvec2(u, 7u), 1, 2).y) * 1e8 + float(bitfieldInsert(i, -1, o, c) & 0xfff) * 1e-8; }\nvoid main() {}\n")
+    pts = np.random.default_rng(3).uniform(-1, 1, (3000, 3)).astype(np.float32)
+    a, b = s2m.Sdf3DShader.from_source(w), s2m.Sdf3DShader.from_source(g, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    assert "extractBits(vec2<u32>(u, 7u), u32(1i), u32(2i))" in b.source
+    va, vb = host_eval.eval_points(a.lower_to_cuda(), pts), host_eval.eval_points(b.lower_to_cuda(), pts)
+    assert f32_equal(va, vb).all()
+
+    def clamp_oc(o, c):
+        o = min(o, 32)
+        return o, min(c, 32 - o)
+
+    def ext_u(e, o, c):
+        o, c = clamp_oc(o, c)
+        return 0 if c == 0 else (e >> o) & ((1 << c) - 1)
+
+    def ext_i(e, o, c):
+        o, c = clamp_oc(o, c)
+        if c == 0:
+            return 0
+        v = ((e & 0xffffffff) >> o) & ((1 << c) - 1)
+        return v - (1 << c) if v >> (c - 1) else v
+
+    def ins(e, n, o, c):
+        o, c = clamp_oc(o, c)
+        if c == 0:
+            return e
+        mask = ((1 << c) - 1) << o
+        return (e & ~mask & 0xffffffff) | ((n << o) & mask)
+
+    F = np.float32
+
+    def ref(p):
+        u, i = int(p[:1].view(np.uint32)[0]), int(p[:1].view(np.int32)[0])
+        o, c = int(np.trunc(F(abs(p[1]) * F(40)))), int(np.trunc(F(abs(p[2]) * F(40))))
+        t = [F(ext_u(u, o, c) & 0xffff), F(F(65536) * F(ext_i(i, o, c) & 0xff)), F(F(ins(u, 0x5a5a5a5a, o, c) >> 20) * F(0.0001)),
+             F(F(ext_u(7, 1, 2)) * F(1e8)), F(F(ins(i & 0xffffffff, 0xffffffff, o, c) & 0xfff) * F(1e-8))]
+        return F(F(F(F(t[0] + t[1]) + t[2]) + t[3]) + t[4])
+
+    assert f32_equal(va, np.array([ref(p) for p in pts], np.float32)).all()
+    assert a.create_shader_module(None).cubin_size > 0
