@@ -27,6 +27,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -464,7 +465,10 @@ int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uin
     status[k] = compile_part(m->cuda_source, o, &m->cubin[k], &logs[k], &errors[k]);
   };
   std::vector<std::thread> threads;
-  for (int k = 1; k < n_parts; ++k) threads.emplace_back(work, k);
+  for (int k = 1; k < n_parts; ++k) {
+    try { threads.emplace_back(work, k); }
+    catch (const std::system_error&) { work(k); }   // the process may not create threads: compile this part here
+  }
   work(0);
   for (std::thread& t : threads) t.join();
   m->log.clear();

@@ -17,6 +17,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -143,8 +144,18 @@ int parallel_write(FILE* f, uint64_t n, uint64_t chunk, size_t max_item_bytes, F
   if (const char* e = getenv("S2M_WRITER_CHUNK")) chunk = (uint64_t)std::max(1, atoi(e));  // tests: many chunks from a small mesh
   const uint64_t n_chunks = (n + chunk - 1) / chunk;
   unsigned hw = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
-  if (const char* e = getenv("S2M_WRITER_THREADS")) hw = (unsigned)std::max(1, std::min(256, atoi(e)));
+  if (const char* e = getenv("S2M_WRITER_THREADS")) hw = (unsigned)std::max(0, std::min(256, atoi(e)));
   const unsigned workers = (unsigned)std::min<uint64_t>(hw, n_chunks);
+  auto serial_from = [&](uint64_t first) {  // no worker threads (S2M_WRITER_THREADS=0, or the process may not create any): format and write in turn
+    std::unique_ptr<char[]> buf(new char[(size_t)chunk * max_item_bytes]);
+    for (uint64_t c = first; c < n_chunks; ++c) {
+      const uint64_t b = c * chunk, e = std::min(n, b + chunk);
+      const size_t len = (size_t)(fn(b, e, buf.get()) - buf.get());
+      if (fwrite(buf.get(), 1, len, f) != len) return fail(S2M_ERR_IO, std::string("short write: ") + strerror(errno));
+    }
+    return (int)S2M_OK;
+  };
+  if (workers == 0) return serial_from(0);
   const unsigned n_slots = 2 * workers;
   struct Slot {
     std::unique_ptr<char[]> buf;
@@ -178,7 +189,11 @@ int parallel_write(FILE* f, uint64_t n, uint64_t chunk, size_t max_item_bytes, F
     }
   };
   std::vector<std::thread> th;
-  for (unsigned t = 0; t < workers; ++t) th.emplace_back(work);
+  try {
+    for (unsigned t = 0; t < workers; ++t) th.emplace_back(work);
+  } catch (const std::system_error&) {   // thread limit of the process: carry on with the threads there are
+    if (th.empty()) return serial_from(0);
+  }
   int st = S2M_OK;
   for (uint64_t c = 0; c < n_chunks; ++c) {
     Slot& sl = slots[c % n_slots];

@@ -139,7 +139,7 @@ def test_z_slab_parts_write_the_whole_mesh(built, tmp_path):
     o.free()
 
 
-@pytest.mark.parametrize("threads,chunk", [(1, 5), (3, 7), (8, 1), (2, 1000)])
+@pytest.mark.parametrize("threads,chunk", [(0, 9), (1, 5), (3, 7), (8, 1), (2, 1000)])
 def test_chunk_pipeline_keeps_the_order(built, tmp_path, monkeypatch, threads, chunk):
     """the writers format chunks on worker threads into a ring of buffers and write them in order: any
     thread count and chunk size gives the file of the (serial) oracle writer"""
