@@ -3,7 +3,7 @@
 A seeded generator builds typed expression trees (f32, vec2, vec3) over the exactly-defined part of the
 shading languages -- arithmetic, comparisons / select, min max clamp mix step smoothstep, floor ceil
 trunc round fract sign abs sqrt, dot length distance normalize cross reflect, constructors and
-swizzles -- prints every tree as WGSL and as GLSL, and evaluates it in numpy with one IEEE f32
+swizzles, 2x2 / 3x3 matrices (columns, products with matrices, vectors and scalars, sums, transpose, determinant) -- prints every tree as WGSL and as GLSL, and evaluates it in numpy with one IEEE f32
 operation per source operation (the semantics DESIGN.md section 3 pins; csrc/s2m_math.h, s2m_vec.h).
 The front-end's CUDA C++ for the WGSL text and for the GLSL text (through the GLSL -> naga-IR-shaped
 path the reference takes, /root/reference/src/shadertoy.rs:169-194), compiled for the host, must
@@ -121,7 +121,7 @@ def _gen(rng, ty, depth):
     d = depth - 1
     if ty == "f":
         choices = ["+", "-", "*", "/", "neg", "abs", "min", "max", "clamp", "mix", "floor", "ceil", "trunc", "round", "fract", "sign",
-                   "step", "sqrtabs", "length", "dot", "distance", "pick", "select", "smoothstep", "fmod"]
+                   "step", "sqrtabs", "length", "dot", "distance", "pick", "select", "smoothstep", "fmod", "det", "elem"]
         op = rng.choice(choices)
         if op in ("+", "-", "*", "/", "min", "max", "step", "fmod"):
             return Node(op, "f", (gen(rng, "f", d), gen(rng, "f", d)))
@@ -137,6 +137,11 @@ def _gen(rng, ty, depth):
         if op == "pick":
             vt = rng.choice(["v2", "v3"])
             return Node(op, "f", (gen(rng, vt, d),), int(rng.integers(DIM[vt])))
+        if op == "det":
+            return Node("det", "f", (gen_mat(rng, int(rng.choice([2, 3])), d),))
+        if op == "elem":
+            n = int(rng.choice([2, 3]))
+            return Node("elem", "f", (gen_mat(rng, n, d),), (int(rng.integers(n)), int(rng.integers(n))))
         return Node("select", "f", (gen(rng, "f", d), gen(rng, "f", d), gen(rng, "b", d)))
     choices = ["+", "-", "*", "/", "vs*", "sv*", "vs/", "vs+", "neg", "abs", "min", "max", "clamp", "mixs", "mixv", "floor", "fract", "sign",
                "step", "normalize", "reflect", "ctor", "swz", "select"]
@@ -144,7 +149,14 @@ def _gen(rng, ty, depth):
         choices += ["cross", "ctor21", "ctor12", "widen"]
     else:
         choices += ["narrow"]
+    choices += ["mv", "vm", "col"]
     op = rng.choice(choices)
+    if op == "mv":   # matrix * vector
+        return Node("mv", ty, (gen_mat(rng, DIM[ty], d), gen(rng, ty, d)))
+    if op == "vm":   # vector * matrix
+        return Node("vm", ty, (gen(rng, ty, d), gen_mat(rng, DIM[ty], d)))
+    if op == "col":
+        return Node("col", ty, (gen_mat(rng, DIM[ty], d),), int(rng.integers(DIM[ty])))
     if op in ("+", "-", "*", "/", "min", "max", "step", "reflect", "cross"):
         return Node(op, ty, (gen(rng, ty, d), gen(rng, ty, d)))
     if op in ("vs*", "vs/", "vs+"):
@@ -172,6 +184,24 @@ def _gen(rng, ty, depth):
     return Node("narrow", "v2", (gen(rng, "v3", d),), tuple(int(i) for i in rng.integers(0, 3, 2)))
 
 
+def gen_mat(rng, n, depth):
+    """a square matrix of size n (type 'm2' | 'm3'): columns, products, sums, scalar multiples, transposes"""
+    ty, vt = f"m{n}", f"v{n}"
+    d = depth - 1
+    if depth <= 0 or rng.random() < 0.35:
+        return Node("mcols", ty, tuple(_gen(rng, vt, max(d, 0)) for _ in range(n)))
+    op = rng.choice(["mm", "m+", "m-", "ms", "sm", "transpose", "mcols"])
+    if op in ("mm", "m+", "m-"):
+        return Node(op, ty, (gen_mat(rng, n, d), gen_mat(rng, n, d)))
+    if op == "ms":
+        return Node(op, ty, (gen_mat(rng, n, d), _gen(rng, "f", d)))
+    if op == "sm":
+        return Node(op, ty, (_gen(rng, "f", d), gen_mat(rng, n, d)))
+    if op == "transpose":
+        return Node(op, ty, (gen_mat(rng, n, d),))
+    return Node("mcols", ty, tuple(_gen(rng, vt, d) for _ in range(n)))
+
+
 XYZ = "xyz"
 
 
@@ -185,6 +215,19 @@ def show(n, glsl):
     k = [show(c, glsl) for c in n.kids]
     V = {"v2": "vec2" if glsl else "vec2f", "v3": "vec3" if glsl else "vec3f"}
     op = n.op
+    if op == "mcols":
+        nn = len(n.kids)
+        return (f"mat{nn}(" if glsl else f"mat{nn}x{nn}f(") + ", ".join(k) + ")"
+    if op in ("mm", "ms", "sm", "mv", "vm"):
+        return f"({k[0]} * {k[1]})"
+    if op in ("m+", "m-"):
+        return f"({k[0]} {op[1]} {k[1]})"
+    if op == "det":
+        return f"determinant({k[0]})"
+    if op == "elem":
+        return f"{k[0]}[{n.arg[0]}].{XYZ[n.arg[1]]}"
+    if op == "col":
+        return f"{k[0]}[{n.arg}]"
     if op == "comp":
         return f"q.{XYZ[n.arg]}"
     if op == "var":
@@ -234,6 +277,39 @@ def evaluate(n, q):
     op = n.op
     N = q.shape[0]
     with np.errstate(all="ignore"):
+        # matrices: (N, column, row)
+        if op == "mcols":
+            return np.stack(k, axis=1).astype(F)
+        if op == "mv" or op == "mm":
+            def mat_vec(m, v):   # per row: c0.r * v.x + c1.r * v.y + ..., left to right
+                acc = (m[:, 0, :] * v[:, 0:1]).astype(F)
+                for c in range(1, m.shape[1]):
+                    acc = (acc + (m[:, c, :] * v[:, c:c + 1]).astype(F)).astype(F)
+                return acc
+            if op == "mv":
+                return mat_vec(k[0], k[1])
+            return np.stack([mat_vec(k[0], k[1][:, j, :]) for j in range(k[1].shape[1])], axis=1).astype(F)
+        if op == "vm":
+            return np.stack([s_dot(k[0], k[1][:, c, :]) for c in range(k[1].shape[1])], axis=-1).astype(F)
+        if op == "m+":
+            return (k[0] + k[1]).astype(F)
+        if op == "m-":
+            return (k[0] - k[1]).astype(F)
+        if op == "ms":
+            return (k[0] * k[1][:, None, None]).astype(F)
+        if op == "sm":
+            return (k[0][:, None, None] * k[1]).astype(F)
+        if op == "transpose":
+            return np.swapaxes(k[0], 1, 2).copy()
+        if op == "det":
+            m = k[0]
+            if m.shape[1] == 2:
+                return ((m[:, 0, 0] * m[:, 1, 1]).astype(F) - (m[:, 1, 0] * m[:, 0, 1]).astype(F)).astype(F)
+            return s_dot(m[:, 0, :], s_cross(m[:, 1, :], m[:, 2, :]))
+        if op == "elem":
+            return k[0][:, n.arg[0], n.arg[1]]
+        if op == "col":
+            return k[0][:, n.arg, :]
         if op == "comp":
             return q[:, n.arg]
         if op == "const":
