@@ -594,7 +594,7 @@ def show_int(n, glsl):
         if n.ty == "u":
             return f"{n.arg}u"
         if n.arg == -2147483648:
-            return "(-2147483647 - 1)"
+            return "(-2147483647 - 1)" if glsl else "i32(-2147483647 - 1)"   # WGSL: concrete, or -(...) of it would be the abstract-int +2147483648
         s = str(n.arg) if glsl else f"{n.arg}i"
         return f"({s})" if n.arg < 0 else s
     if op in ("+", "-", "*", "/", "%", "&", "|", "^", "<<", ">>", "<", ">=", "=="):
