@@ -889,7 +889,11 @@ class GlslParser : public ParserBase {
     if (t.k == Token::Int) {
       advance();
       if (t.suffix == 'f') return b.lit_float((double)t.ival, Sk::F32);
-      return b.lit_int(t.ival, t.suffix == 'u' ? Sk::U32 : Sk::I32);
+      // GLSL 4.1.3: a literal whose bit pattern does not fit in 32 bits is an error; the pattern is used unmodified, so
+      // an unsuffixed literal with the sign bit set is a negative int (0xFFFFFFFF == -1)
+      if (t.ival < 0 || t.ival > 0xFFFFFFFFll) perr("integer literal '" + t.text + "' does not fit in 32 bits");
+      if (t.suffix == 'u') return b.lit_int(t.ival, Sk::U32);
+      return b.lit_int(t.ival > 0x7FFFFFFFll ? t.ival - 0x100000000ll : t.ival, Sk::I32);
     }
     if (accept("(")) {
       ExprP e = parse_expr();

@@ -1534,3 +1534,26 @@ def test_extract_and_insert_bits(built):
 
     assert f32_equal(va, np.array([ref(p) for p in pts], np.float32)).all()
     assert a.create_shader_module(None).cubin_size > 0
+
+
+def test_glsl_integer_literal_bit_patterns_and_constant_folding(built):
+    """GLSL 4.1.3: an unsuffixed literal with the sign bit set is a negative int (0xFFFFFFFF == -1), more than 32 bits is
+    an error; integer constant expressions fold with 32-bit wrap-around like the run-time operations"""
+    cases = [("0xFFFFFFFF", -1.0), ("0x80000000", -2147483648.0), ("4294967295", -1.0), ("0xFFFFFFFFu", 4294967296.0), ("2147483647 + 1", -2147483648.0),
+             ("1 << 31", -2147483648.0), ("int(uint(-1) >> 1)", 2147483647.0), ("int(3000000000u)", -1294967296.0), ("7 / -2", -3.0), ("-7 % 3", -1.0),
+             ("int(-1.5)", -1.0), ("int(1e20)", 2147483647.0), ("int(uint(-5.0))", 0.0), ("65536 * 65536", 0.0), ("abs(-2147483647 - 1)", -2147483648.0),
+             ("int(float((1 << 24) + 1))", 16777216.0), ("5 & 3 | 8 ^ 2", 11.0), ("-3 >> 1", -2.0), ("int(uint(-3) >> 1u)", 2147483646.0), ("100 / 10 / 5", 2.0),
+             ("1 < 2 == true ? 1 : 0", 1.0)]
+    body = "\n".join(f"  if (k == {i}) return float({e});" for i, (e, _) in enumerate(cases))
+    dyn = "\n".join(f"  if (k == {100 + i}) return float({e.replace('1 <<', '(1 + z) <<').replace('7 /', '(7 + z) /').replace('-7 %', '(z - 7) %').replace('65536 *', '(65536 + z) *')});"
+                    for i, (e, _) in enumerate(cases))
+    src = "#version 450 core\nfloat sdf(vec3 p) {\n  int k = int(p.x); int z = int(p.y);\n" + body + "\n" + dyn + "\n  return 0.5;\n}\nvoid main() {}\n"
+    sh = s2m.Sdf3DShader.from_source(src, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    ks = np.array([i for i in range(len(cases))] + [100 + i for i in range(len(cases))], np.float32)
+    pts = np.stack([ks, np.zeros_like(ks), np.zeros_like(ks)], 1)
+    got = host_eval.eval_points(sh.lower_to_cuda(), pts)
+    want = np.array([w for _, w in cases] * 2, np.float32)
+    assert f32_equal(got, want).all(), [(cases[i % len(cases)][0], got[i], want[i]) for i in np.flatnonzero(~f32_equal(got, want))]
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_source("#version 450 core\nfloat sdf(vec3 p) { return float(0x1FFFFFFFF); }\nvoid main() {}\n", s2m.SRC_GLSL_FRAGMENT, "sdf")
+    assert e.value.kind == "PARSE" and "32 bits" in str(e.value)
