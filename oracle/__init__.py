@@ -29,6 +29,14 @@ def build(force: bool = False) -> str:
     return so
 
 
+def build_indep(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libindep.so")
+    src = os.path.join(_HERE, "indep.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libindep.so"])
+    return so
+
+
 def lib():
     global _LIB
     if _LIB is None:
@@ -136,3 +144,67 @@ def axis_coords(res, bmin, bmax):
 
 def rust_f32(x) -> str:
     return lib().oracle_rust_f32(ctypes.c_float(x)).decode()
+
+
+# ---------------------------------------------------------------- independent evaluation (indep.cpp)
+_INDEP = None
+
+
+def indep_lib():
+    global _INDEP
+    if _INDEP is None:
+        L = ctypes.CDLL(build_indep())
+        L.indep_run.restype = ctypes.c_void_p
+        L.indep_run.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                ctypes.c_uint32, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        L.indep_count.restype = ctypes.c_uint64
+        L.indep_count.argtypes = [ctypes.c_void_p]
+        L.indep_copy.argtypes = [ctypes.c_void_p] * 7
+        L.indep_free.argtypes = [ctypes.c_void_p]
+        L.indep_eval.restype = ctypes.c_double
+        L.indep_eval.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+        _INDEP = L
+    return _INDEP
+
+
+@dataclass
+class IndepCells:
+    """Cells of a z-range that the reference's rule, evaluated WITHOUT the engine's math (f64 + libm or
+    f32 + libm), makes active, plus every cell with a corner closer to the surface than `list_below`."""
+    keys: np.ndarray      # (n,) u64, label keys, ascending
+    active: np.ndarray    # (n,) bool
+    nibbles: np.ndarray   # (n,) u8
+    positions: np.ndarray  # (n,3) f64 (zeros where not active)
+    min_abs: np.ndarray   # (n,) f64: min |corner value| of the cell, SDF units
+    corners: np.ndarray   # (n,8) f64
+    voxel: float          # min voxel edge length, SDF units
+    seconds: float
+
+
+def indep_run(sdf, res, bounds=2.0, z_begin=0, z_end=None, label_add=1, list_below_voxels=1e-3, precision=64, threads=0,
+              bmin=None, bmax=None) -> IndepCells:
+    import time
+    L = indep_lib()
+    sid = SDF_IDS[sdf] if isinstance(sdf, str) else int(sdf)
+    res3 = np.array([res] * 3 if np.isscalar(res) else res, dtype=np.uint32)
+    if bmin is None:
+        bmin, bmax = cube_bounds(bounds)
+    bmin = np.ascontiguousarray(bmin, np.float32)
+    bmax = np.ascontiguousarray(bmax, np.float32)
+    if z_end is None:
+        z_end = int(res3[2]) - 1
+    voxel = float(np.min((bmax - bmin) / (res3.astype(np.float32) - np.float32(1))))
+    t0 = time.perf_counter()
+    h = L.indep_run(sid, res3.ctypes.data, bmin.ctypes.data, bmax.ctypes.data, int(z_begin), int(z_end), int(label_add),
+                    float(list_below_voxels) * voxel, int(precision), int(threads))
+    n = L.indep_count(h)
+    keys = np.empty(n, np.uint64); act = np.empty(n, np.uint8); nib = np.empty(n, np.uint8)
+    pos = np.empty((n, 3), np.float64); mabs = np.empty(n, np.float64); corners = np.empty((n, 8), np.float64)
+    L.indep_copy(h, keys.ctypes.data, act.ctypes.data, nib.ctypes.data, pos.ctypes.data, mabs.ctypes.data, corners.ctypes.data)
+    L.indep_free(h)
+    return IndepCells(keys, act.astype(bool), nib, pos, mabs, corners, voxel, time.perf_counter() - t0)
+
+
+def indep_eval(sdf, x, y, z, precision=64) -> float:
+    sid = SDF_IDS[sdf] if isinstance(sdf, str) else int(sdf)
+    return indep_lib().indep_eval(sid, float(x), float(y), float(z), int(precision))

@@ -366,7 +366,8 @@ int compile_part(const std::string& source, const std::vector<std::string>& opts
       std::string key = source;
       for (const char* h : hdr_src) { key += '\0'; key += h; }
       for (const std::string& o : opts) { key += '\0'; key += o; }
-      key += "\0nvrtc " + std::to_string(nv_major) + "." + std::to_string(nv_minor) + " " + s2m_version();
+      key.push_back('\0');  // (a "\0..." literal would end at its first byte)
+      key += "nvrtc " + std::to_string(nv_major) + "." + std::to_string(nv_minor) + " " + s2m_version();
       unsigned long long h1 = 1469598103934665603ull, h2 = 0x9e3779b97f4a7c15ull;  // two independent 64-bit FNV-1a style hashes
       for (unsigned char ch : key) { h1 = (h1 ^ ch) * 1099511628211ull; h2 = (h2 + ch) * 0xff51afd7ed558ccdull; h2 ^= h2 >> 29; }
       char name[64];

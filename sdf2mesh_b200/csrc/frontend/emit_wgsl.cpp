@@ -140,7 +140,7 @@ class WgslWriter {
           rhs = type_name(e.args[1]->ty.with_sk(Sk::U32)) + "(" + rhs + ")";
         return "(" + expr(*e.args[0]) + " " + ops.at(e.op) + " " + rhs + ")";
       }
-      case Expr::Ternary:  // both sides are pure expressions here
+      case Expr::Ternary:  // arms with calls or effects were lowered to if / else by the GLSL parser; what is left is pure
         return "select(" + expr(*e.args[2]) + ", " + expr(*e.args[1]) + ", " + expr(*e.args[0]) + ")";
       case Expr::Call: {
         std::string name = e.callee;

@@ -30,6 +30,7 @@ int glsl_to_wgsl(const std::string& glsl, std::string* wgsl, std::string* err) {
   try {
     Module m;
     parse_glsl(glsl, &m);
+    check_eager_conditionals(m);
     make_names_wgsl_safe(m);
     *wgsl = emit_wgsl(m);
     return S2M_OK;

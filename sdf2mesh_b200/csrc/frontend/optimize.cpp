@@ -363,6 +363,40 @@ std::set<const Function*> state_writers(const Module& m) {
   return w;
 }
 
+namespace {
+void eager_conditionals_in(const Expr& e, int line) {
+  if (e.k == Expr::Ternary) {
+    for (int arm = 1; arm <= 2; ++arm) {
+      std::set<const Var*> reads;
+      bool impure = false;
+      reads_of(*e.args[(size_t)arm], reads, &impure);
+      if (impure)
+        throw FrontendError(11 /*S2M_ERR_UNSUPPORTED*/, "unsupported near line " + std::to_string(line) +
+                                ": an arm of ?: calls a function with a side effect (it assigns a module-scope variable or has an out / inout "
+                                "parameter) in a position where no statement can be issued for it (an `else if` condition, the right side of "
+                                "&& or ||, a nested ?:); GLSL evaluates only the chosen arm -- assign the result to a variable first");
+    }
+  }
+  for (const ExprP& a : e.args) if (a) eager_conditionals_in(*a, line);
+}
+void eager_conditionals_in(const Stmt& s, int line) {
+  if (s.line > 0) line = s.line;
+  for (const ExprP* e : {&s.a, &s.b, &s.break_if}) if (*e) eager_conditionals_in(**e, line);
+  for (const StmtP& c : s.body) eager_conditionals_in(*c, line);
+  for (const StmtP* c : {&s.init, &s.cont, &s.then_s, &s.else_s}) if (*c) eager_conditionals_in(**c, line);
+}
+}  // namespace
+
+// GLSL's `c ? t : f` that stayed an expression (parse_glsl.cpp parse_conditional_arms) becomes WGSL select(),
+// which evaluates both arms: harmless for pure arms, wrong for an arm whose call has a side effect.
+void check_eager_conditionals(const Module& m) {
+  const std::set<const Function*> writers = state_writers(m);
+  g_state_writers = &writers;
+  struct Reset { ~Reset() { g_state_writers = nullptr; } } reset;
+  for (const auto& f : m.functions)
+    if (f->body) eager_conditionals_in(*f->body, f->line);
+}
+
 int optimize_module(Module& m) {
   int count = 0;
   const std::set<const Function*> writers = state_writers(m);

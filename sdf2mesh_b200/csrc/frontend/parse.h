@@ -9,6 +9,7 @@ namespace s2m_frontend {
 void parse_wgsl(const std::string& src, const std::vector<std::string>& builtin_fns, Module* out);
 void parse_glsl(const std::string& src, Module* out);
 int optimize_module(Module& m);  // returns the number of rewrites applied
+void check_eager_conditionals(const Module& m);  // GLSL ?: left as select() must not hide a side effect (throws S2M_ERR_UNSUPPORTED)
 std::string emit_cuda(const Module& m);
 std::string emit_cuda_packed(const Module& m);  // "" when the module has no packed (f32x2) form
 std::string emit_wgsl(const Module& m);

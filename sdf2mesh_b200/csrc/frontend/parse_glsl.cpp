@@ -736,10 +736,22 @@ class GlslParser : public ParserBase {
   }
 
   // ---------------------------------------------------------------- expressions
-  ExprP parse_expr() { return parse_assignment_expr(); }
-  ExprP parse_assignment_expr() {  // the ?: level; an assignment here is a side effect of the enclosing statement
-    ExprP c = parse_binary(0);
-    if (accept("?")) {
+  static bool has_user_call(const Expr& e) {
+    if (e.k == Expr::UserCall) return true;
+    for (const ExprP& a : e.args) if (a && has_user_call(*a)) return true;
+    return false;
+  }
+  // c ? t : f -- GLSL evaluates exactly one of the arms.  An arm that calls a user function (it may
+  // assign module-scope variables or write through an out parameter, and it may be expensive) or that
+  // contains an assignment / ++ / -- is therefore lowered the way naga lowers it: a temporary, declared
+  // in front of the statement, assigned in an if / else whose branches hold that arm's effects.  Arms
+  // made of operators and builtins only stay an expression (WGSL select(): both sides evaluated, which
+  // is unobservable for pure arms).  Where no statement can be issued (conditions of `else if`, the
+  // right side of && and ||, an enclosing ?: that stayed an expression) calls stay eager as well;
+  // check_eager_conditionals() rejects the module afterwards if such a call has a side effect.
+  ExprP parse_conditional_arms(ExprP c) {
+    const bool can_lower = side_ != nullptr && cond_depth_ == 0;
+    if (!can_lower) {
       ++cond_depth_;
       ExprP t = parse_assignment_expr();
       expect(":");
@@ -747,6 +759,41 @@ class GlslParser : public ParserBase {
       --cond_depth_;
       return b.ternary(c, t, f);
     }
+    std::vector<StmtP> t_side, f_side;
+    ExprP t, f;
+    {
+      SideScope sc(*this);
+      t = parse_assignment_expr();
+      t_side.swap(sc.stmts);
+    }
+    expect(":");
+    {
+      SideScope sc(*this);
+      f = parse_assignment_expr();
+      f_side.swap(sc.stmts);
+    }
+    ExprP sel = b.ternary(c, t, f);   // type checks and coerces the arms to their common type
+    if (sel->k != Expr::Ternary) return sel;   // folded (constant condition)
+    if (t_side.empty() && f_side.empty() && !has_user_call(*sel->args[1]) && !has_user_call(*sel->args[2])) return sel;
+    Var* tmp = declare("_cond" + std::to_string(++post_tmp_), sel->ty, Var::Local);
+    StmtP decl = mk_stmt(Stmt::VarDecl);
+    decl->var = tmp;
+    side_->push_back(decl);
+    StmtP br = mk_stmt(Stmt::If);
+    br->a = sel->args[0];
+    br->then_s = mk_stmt(Stmt::Block);
+    for (const StmtP& st : t_side) br->then_s->body.push_back(st);
+    br->then_s->body.push_back(make_assign(b.var_ref(tmp), sel->args[1]));
+    br->else_s = mk_stmt(Stmt::Block);
+    for (const StmtP& st : f_side) br->else_s->body.push_back(st);
+    br->else_s->body.push_back(make_assign(b.var_ref(tmp), sel->args[2]));
+    side_->push_back(br);
+    return b.var_ref(tmp);
+  }
+  ExprP parse_expr() { return parse_assignment_expr(); }
+  ExprP parse_assignment_expr() {  // the ?: level; an assignment here is a side effect of the enclosing statement
+    ExprP c = parse_binary(0);
+    if (accept("?")) return parse_conditional_arms(c);
     if (peek().k == Token::Punct) {
       const std::string p = peek().text;
       const bool compound = p == "+=" || p == "-=" || p == "*=" || p == "/=" || p == "%=" || p == "&=" || p == "|=" || p == "^=" || p == "<<=" || p == ">>=";

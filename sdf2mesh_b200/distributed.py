@@ -17,7 +17,7 @@ def n_scanned_slices(res_z: int, all_slices: bool) -> int:
 
 
 def partition_slices(n_slices: int, world: int, cost: Optional[Sequence[float]] = None) -> List[int]:
-    """Boundaries b[0..world] with b[0] = 0, b[world] = n_slices, non-decreasing.
+    """Boundaries b[0..world] with b[0] = 0, b[world] = n_slices, strictly increasing.
 
     cost: relative cost of equal-thickness z bands (any length >= 1, e.g. from s2m_cost_probe);
     None = equal thickness.  Slab g gets ~1/world of the total cost (for the mandelbulb
@@ -25,6 +25,9 @@ def partition_slices(n_slices: int, world: int, cost: Optional[Sequence[float]] 
     """
     if world < 1:
         raise ValueError("world must be >= 1")
+    if n_slices < world:
+        # an empty slab cannot be expressed: z_begin == z_end == 0 means "the whole grid" to s2m_mesh_begin
+        raise ValueError(f"{n_slices} z-slices cannot be split over {world} ranks (every rank needs at least one)")
     if cost is None or len(cost) == 0 or not np.isfinite(np.sum(cost)) or np.sum(cost) <= 0:
         return [int(round(n_slices * g / world)) for g in range(world + 1)]
     c = np.asarray(cost, np.float64)
@@ -36,8 +39,8 @@ def partition_slices(n_slices: int, world: int, cost: Optional[Sequence[float]] 
     b = np.interp(targets, cum, edges)
     out = [int(round(x)) for x in b]
     out[0], out[-1] = 0, n_slices
-    for i in range(1, len(out)):
-        out[i] = min(max(out[i], out[i - 1]), n_slices)
+    for i in range(1, world + 1):   # strictly increasing: every slab has at least one slice, however skewed the profile
+        out[i] = min(max(out[i], out[i - 1] + 1), n_slices - (world - i))
     return out
 
 

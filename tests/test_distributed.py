@@ -29,6 +29,19 @@ def test_partition_cost_weighted():
     assert D.partition_slices(10, 4, [0, 0, 0]) == D.partition_slices(10, 4)  # degenerate cost -> equal
 
 
+def test_partition_never_yields_an_empty_slab():
+    """z_begin == z_end == 0 means "whole grid" to s2m_mesh_begin, so an empty first slab must not come out of
+    the partitioner however skewed the cost profile is"""
+    cost = np.zeros(128)
+    cost[-1] = 1.0  # everything in the last band
+    b = D.partition_slices(64, 8, cost)
+    assert b[0] == 0 and b[-1] == 64 and all(y > x for x, y in zip(b, b[1:])), b
+    b = D.partition_slices(8, 8, cost)
+    assert b == list(range(9))
+    with pytest.raises(ValueError):
+        D.partition_slices(7, 8)
+
+
 def test_exclusive_bases_and_slice_count():
     assert D.exclusive_bases([5, 0, 7]) == [0, 5, 5]
     assert D.n_scanned_slices(2048, False) == 2047 and D.n_scanned_slices(2048, True) == 2048

@@ -868,12 +868,16 @@ def test_glsl_side_effects_inside_expressions(built, tmp_path):
         want.append((np.linalg.norm(p) - 1.0) + acc + (1 + 3) + 4 * p[0] + 5 * 0.01 + 3 * 0.001)
     assert np.abs(host_eval.eval_points(sh.lower_to_cuda(), pts) - np.array(want)).max() < 1e-5
     for bad in ("float sdf(vec3 p) { float e = 0.0; if (p.x > 0.0 && (e = p.y) > 0.0) return e; return 1.0; }",
-                "float sdf(vec3 p) { int i = 0; return p.x > 0.0 ? float(i++) : 1.0; }",
+                "float sdf(vec3 p) { int i = 0; if (p.y > 9.0) return 0.0; else if ((p.x > 0.0 ? float(i++) : 1.0) > 0.5) return 2.0; return float(i); }",
                 "int g = 0; float h = float(g++); float sdf(vec3 p) { return h; }"):
         frag.write_text("#version 450\n" + bad + "\nvoid main() {}\n")
         with pytest.raises(s2m.S2mError) as e:
             s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
         assert "UNSUPPORTED" in str(e.value)
+    # an effect inside an arm of ?: where a statement can be issued: the arm becomes a branch of an if / else
+    frag.write_text("#version 450\nfloat sdf(vec3 p) { int i = 3; float r = p.x > 0.0 ? float(i++) : 1.0; return r + 10.0 * float(i); }\nvoid main() {}\n")
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(frag, "sdf")
+    assert host_eval.eval_points(sh.lower_to_cuda(), np.array([[1, 0, 0], [-1, 0, 0]], np.float32)).tolist() == [43.0, 31.0]
 
 
 def test_modf_and_ldexp(built, tmp_path):
@@ -1557,3 +1561,51 @@ def test_glsl_integer_literal_bit_patterns_and_constant_folding(built):
     with pytest.raises(s2m.S2mError) as e:
         s2m.Sdf3DShader.from_source("#version 450 core\nfloat sdf(vec3 p) { return float(0x1FFFFFFFF); }\nvoid main() {}\n", s2m.SRC_GLSL_FRAGMENT, "sdf")
     assert e.value.kind == "PARSE" and "32 bits" in str(e.value)
+
+
+def test_glsl_conditional_evaluates_only_the_chosen_arm(built):
+    """`c ? t : f`: an arm that calls a user function is lowered to a temporary + if / else (as naga does), not to
+    select() -- the untaken arm's call must not run.  The ADVICE example: select() gave 15 for x <= 0."""
+    src = ("float g = 0.; float inc() { g += 1.; return g; }\n"
+           "float sdf(vec3 p) { g = 0.; float r = p.x > 0. ? inc() : 5.; return r + 10. * g; }\nvoid main() {}\n")
+    sh = s2m.Sdf3DShader.from_source(src, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    assert "select(" not in sh.source.split("// sdf3d::normal")[0] and "_cond1 = inc();" in sh.source
+    got = host_eval.eval_points(sh.lower_to_cuda(), np.array([[1, 0, 0], [-1, 0, 0]], np.float32))
+    assert got.tolist() == [11.0, 5.0]
+    # nested conditionals, an assignment inside an arm, an out parameter inside an arm
+    src = ("void bump(inout float v) { v += 2.; }\nfloat sq(float x) { return x * x; }\n"
+           "float sdf(vec3 p) {\n  float a = 1., b = 0.;\n"
+           "  float r = p.z > 0. ? (p.x > 0. ? sq(p.z) : 1.) : 7.;\n"
+           "  float s = p.y > 0. ? (b = 3.) : a;\n"
+           "  float t = p.x > 1. ? sq(a) : a; if (p.x > 2.) bump(a);\n"
+           "  return r + 10. * s + 100. * b + 1000. * t + 10000. * a; }\nvoid main() {}\n")
+    sh = s2m.Sdf3DShader.from_source(src, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    pts = np.array([[1, 1, 2], [-1, -1, 2], [3, 0, -1]], np.float32)
+    want = [4 + 30 + 300 + 1000 + 10000, 1 + 10 + 0 + 1000 + 10000, 7 + 10 + 0 + 1000 + 30000]
+    assert host_eval.eval_points(sh.lower_to_cuda(), pts).tolist() == [float(w) for w in want]
+    # pure arms stay an expression
+    sh = s2m.Sdf3DShader.from_source("float sdf(vec3 p) { return p.x > 0. ? length(p) : -p.y; }\nvoid main() {}\n", s2m.SRC_GLSL_FRAGMENT, "sdf")
+    assert "select(" in sh.source
+
+
+def test_glsl_conditional_with_a_side_effect_where_no_statement_fits_is_refused(built):
+    """in an `else if` condition (or right of && / ||) the conditional stays select(); a pure call there is fine,
+    a call that assigns module-scope state would run although its arm is not taken -> S2M_ERR_UNSUPPORTED"""
+    pure = ("float sq(float x) { return x * x; }\n"
+            "float sdf(vec3 p) { float r = 0.; if (p.y > 5.) r = 1.; else if ((p.x > 0. ? sq(p.x) : 5.) > 2.) r = 2.; return r; }\nvoid main() {}\n")
+    sh = s2m.Sdf3DShader.from_source(pure, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    assert host_eval.eval_points(sh.lower_to_cuda(), np.array([[1, 0, 0], [-1, 0, 0], [3, 0, 0]], np.float32)).tolist() == [0.0, 2.0, 2.0]
+    impure = ("float g = 0.; float inc() { g += 1.; return g; }\n"
+              "float sdf(vec3 p) { g = 0.; float r = 0.; if (p.y > 5.) r = 1.; else if ((p.x > 0. ? inc() : 5.) > 2.) r = 2.; return r + g; }\nvoid main() {}\n")
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_source(impure, s2m.SRC_GLSL_FRAGMENT, "sdf")
+    assert e.value.kind == "UNSUPPORTED" and "?:" in str(e.value)
+
+
+def test_module_scope_initialiser_that_reads_assigned_state_is_a_validation_error(built):
+    """used to surface as a raw compiler error ('G was not declared in this scope')"""
+    src = ("var<private> A: f32 = 1.0;\nvar<private> B: f32 = A * 3.0;\nfn bump() { A = A + 1.0; }\n"
+           "fn sdf3d(p: vec3f) -> f32 { bump(); let c = vec3(B, A, 1.0); return length(p) - c.x; }\n")
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.Sdf3DShader.from_source(src).lower_to_cuda()
+    assert e.value.kind == "VALIDATION" and "'B'" in str(e.value) and "'A'" in str(e.value)
