@@ -104,3 +104,31 @@ def test_plugin_sdf_equals_hand_transcriptions(built):
         a.free()
         b.free()
     oracle.set_plugin(None)
+
+
+def test_slab_extract_of_a_whole_run_equals_the_slab_run():
+    """the z-slab digest form used for grids too large for a full oracle run (tests/support/slabs.py, BASELINE config 5):
+    extracting [z, z+2) from a whole-grid mesh gives the same digest as oracle.mesh_run(z_begin=z, z_end=z+2)"""
+    from tests.support.slabs import extract_slab, slab_digest, stratified_pairs
+    for name, res, bounds in (("mandelbulb", 96, 5.0), ("torus", 64, 2.0)):
+        whole = oracle.mesh_run(name, res, bounds)
+        qmax = whole.quads.max(axis=1)
+        assert np.all(qmax[1:] >= qmax[:-1]), "a quad's largest index is its emitting vertex (mesh.rs:286-320)"
+        n_checked = 0
+        for z in stratified_pairs(res - 1, 12):
+            part = oracle.mesh_run(name, res, bounds, z_begin=z, z_end=z + 2)
+            want = slab_digest(part.keys, part.nibbles, part.positions, part.normals, part.quads)
+            i0, i1 = extract_slab(whole.keys, 1, z, z + 2)
+            j0, j1 = int(np.searchsorted(qmax, i0)), int(np.searchsorted(qmax, i1))
+            got = slab_digest(whole.keys[i0:i1], whole.nibbles[i0:i1], whole.positions[i0:i1], whole.normals[i0:i1], whole.quads[j0:j1], index_base=i0)
+            assert got == want, (name, z)
+            n_checked += got["n_vertices"]
+            part.free()
+        assert n_checked > 0
+        whole.free()
+
+
+def test_slab_golden_file_is_well_formed():
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "slab_digests.json")))
+    assert "mandelbulb_r4096_b5_f0" in d and len(d["mandelbulb_r4096_b5_f0"]["slabs"]) >= 32
+    assert sum(v["n_vertices"] for v in d["mandelbulb_r4096_b5_f0"]["slabs"].values()) > 500_000
