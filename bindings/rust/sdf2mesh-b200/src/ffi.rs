@@ -7,6 +7,7 @@ use std::os::raw::{c_char, c_double, c_float, c_int, c_void};
 #[repr(C)] pub struct s2m_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct s2m_module { _p: [u8; 0] }
 #[repr(C)] pub struct s2m_result { _p: [u8; 0] }
+#[repr(C)] pub struct s2m_multi { _p: [u8; 0] }
 
 pub const S2M_OK: c_int = 0;
 pub const S2M_ERR_INVALID_ARG: c_int = 1;
@@ -36,6 +37,11 @@ pub const S2M_MESH_CLASSIFY_FROM_SLAB: u32 = 16;
 pub const S2M_MESH_KEEP_INVALID: u32 = 32;
 pub const S2M_MESH_CONSISTENT_CORNERS: u32 = 64; // with ALL_SLICES: the watertight mode (not the reference's arithmetic)
 pub const S2M_MESH_QUADS_U32: u32 = 128; // indices as u32 in quads32 -- what Quad(u32, u32, u32, u32) wants anyway
+pub const S2M_MESH_NO_SLAB: u32 = 256; // slab-free form (the default for cheap SDFs)
+pub const S2M_MESH_RELATIVE_QUADS: u32 = 512; // global index = quad value + quad_index_add (wrapping)
+pub const S2M_MULTI_NO_NCCL: u32 = 1;
+pub const S2M_MULTI_EQUAL_SLABS: u32 = 2;
+pub const S2M_MULTI_NO_REBALANCE: u32 = 4;
 
 /// == AppState (main.rs:28-33) minus dims.w
 #[repr(C)]
@@ -88,7 +94,18 @@ pub struct s2m_result_info {
     pub halo_positions: *const c_float,
     pub global_vertex_base: i64,
     pub quads32: *const u32,          // with S2M_MESH_QUADS_U32 (then `quads` is null)
+    pub quad_index_add: i64,          // S2M_MESH_RELATIVE_QUADS: global index = quad value + this, wrapping in the index width
     pub timings: s2m_timings,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct s2m_multi_timings {
+    pub n: c_int,
+    pub wall_ms: c_double,
+    pub begin_ms: [c_double; 64],
+    pub exchange_ms: [c_double; 64],
+    pub finish_ms: [c_double; 64],
 }
 
 extern "C" {
@@ -128,6 +145,7 @@ extern "C" {
     pub fn s2m_module_cubin_part(m: *const s2m_module, part: c_int, data: *mut *const c_void, size: *mut usize) -> c_int;
     pub fn s2m_module_compile_ms(m: *const s2m_module, which: c_int) -> c_double;
     pub fn s2m_module_is_packed(m: *const s2m_module) -> c_int;
+    pub fn s2m_module_prefers_no_slab(m: *const s2m_module) -> c_int;
     pub fn s2m_module_free(m: *mut s2m_module);
 
     // meshing (replaces main.rs:298-356 and mesh.rs:229-331)
@@ -143,7 +161,20 @@ extern "C" {
     pub fn s2m_write_mesh_parts(parts: *const *const s2m_result, n_parts: c_int, path: *const c_char, binary_stl: c_int) -> c_int;
     pub fn s2m_read_device_words(ctx: *mut s2m_ctx, device_words: *const c_void, n: u32, out: *mut u64, cuda_stream: *mut c_void) -> c_int;
 
+    // several GPUs in one process: z-slabs, one ncclAllGather of the vertex counts (replaces main.rs:177-364 for N devices)
+    pub fn s2m_multi_create(device_ordinals: *const c_int, n: c_int, flags: u32, out: *mut *mut s2m_multi) -> c_int;
+    pub fn s2m_multi_destroy(mc: *mut s2m_multi);
+    pub fn s2m_multi_size(mc: *const s2m_multi) -> c_int;
+    pub fn s2m_multi_ctx(mc: *mut s2m_multi, k: c_int) -> *mut s2m_ctx;
+    pub fn s2m_multi_uses_nccl(mc: *const s2m_multi, nccl_version: *mut c_int) -> c_int;
+    pub fn s2m_multi_mesh_run(mc: *mut s2m_multi, compiled: *const s2m_module, p: *const s2m_mesh_params, parts_out: *mut *mut s2m_result) -> c_int;
+    pub fn s2m_multi_get_partition(mc: *const s2m_multi, bounds_out: *mut u32) -> c_int;
+    pub fn s2m_multi_last_timings(mc: *const s2m_multi, out: *mut s2m_multi_timings) -> c_int;
+    pub fn s2m_partition_slices(n_slices: u32, world: c_int, cost: *const c_double, n_cost: c_int, bounds_out: *mut u32) -> c_int;
+    pub fn s2m_rebalance_slices(bounds: *const u32, world: c_int, seconds: *const c_double, cost: *const c_double, n_cost: c_int, bounds_out: *mut u32) -> c_int;
+
     // diagnostics
+    pub fn s2m_measure_fp32_peak(ctx: *mut s2m_ctx, out_tflops: *mut c_double) -> c_int;
     pub fn s2m_eval_points(ctx: *mut s2m_ctx, m: *mut s2m_module, xyz: *const c_float, n: u64, out: *mut c_float) -> c_int;
     pub fn s2m_eval_pairs(ctx: *mut s2m_ctx, m: *mut s2m_module, xyz_a: *const c_float, xyz_b: *const c_float, n: u64,
                           out_a: *mut c_float, out_b: *mut c_float, disagreed: *mut u8) -> c_int;

@@ -61,6 +61,7 @@ void usage(FILE* f) {
       "  -b, --bounds <BOUNDS>                Size of bounding box. Default: 2\n"
       "      --device <N>                     CUDA device ordinal [default: 0]\n"
       "      --gpus <N>                       Split the grid into N z-slabs, one GPU (and host thread) each [default: 1]\n"
+      "      --no-nccl                        With --gpus: exchange the slab vertex counts through host memory, not ncclAllGather\n"
       "      --all-slices                     Mesh every z-slice (the reference never reads back the last one)\n"
       "      --watertight                     --all-slices plus consistent cell corners: no quads lost to rounding\n"
       "      --exact-dense                    Evaluate all 8 corners of every cell, like the reference (slow)\n"
@@ -78,6 +79,7 @@ struct Args {
   unsigned resolution = 0;
   float bounds = 0.0f;
   int device = 0, gpus = 1;
+  bool no_nccl = false;
   bool watertight = false, all_slices = false, exact_dense = false, no_normals = false, binary_stl = false, stats = false;
 };
 
@@ -144,114 +146,59 @@ s2m_shader* load_shader(const Args& a, bool quiet) {
   return shader;
 }
 
-// --gpus N: one host thread + one context per GPU, contiguous z-slabs balanced with the cost probe,
-// vertex counts exchanged in-process (the multi-process form of the same protocol, over NCCL, is
-// sdf2mesh_b200/distributed.py), one output file written from all parts.
+// --gpus N: the library's one-call form (s2m_multi, csrc/multi.cpp): one context and host thread per GPU, contiguous
+// z-slabs balanced with the cost probe, vertex counts exchanged by one ncclAllGather, one output file written from all
+// parts.  (The multi-process form of the same protocol is sdf2mesh_b200/distributed.py.)  --no-nccl exchanges the counts
+// through host memory.
 int run_multi_gpu(const Args& a, s2m_mesh_params params) {
   const int n = a.gpus;
   s2m_shader* shader = load_shader(a, false);
   if (!a.debug_wgsl.empty() && s2m_shader_write_to_file(shader, a.debug_wgsl.c_str())) die("cannot write --debug-wgsl file");
-  const uint32_t n_slices = (params.flags & S2M_MESH_ALL_SLICES) ? params.dims[2] : params.dims[2] - 1;
-  std::vector<s2m_ctx*> ctx(n, nullptr);
-  std::vector<s2m_module*> mod(n, nullptr);
-  std::vector<s2m_result*> res(n, nullptr);
-  std::vector<uint64_t> counts(n, 0);
-  std::vector<uint32_t> bounds(n + 1, 0);
-  std::vector<std::string> errors(n);
-  std::mutex mu;
-  std::condition_variable cv;
-  int arrived = 0, generation = 0;
-  auto barrier = [&] {
-    std::unique_lock<std::mutex> lk(mu);
-    const int gen = generation;
-    if (++arrived == n) { arrived = 0; ++generation; cv.notify_all(); }
-    else cv.wait(lk, [&] { return generation != gen; });
-  };
-  std::atomic<bool> failed{false};
-  // one NVRTC compile for all GPUs, on this thread, while the workers bring their contexts up
-  s2m_module* compiled = nullptr;
-  std::string compile_error;
-  bool compile_finished = false;  // guarded by mu
-  auto wait_compiled = [&] {
-    std::unique_lock<std::mutex> lk(mu);
-    cv.wait(lk, [&] { return compile_finished; });
-  };
-  auto compile_done = [&] {
-    { std::lock_guard<std::mutex> lk(mu); compile_finished = true; }
-    cv.notify_all();
-  };
-  auto worker = [&](int g) {
-    auto fail_here = [&](const char* what) { errors[g] = std::string(what) + ": " + s2m_last_error(); failed = true; };
-    if (s2m_ctx_create(a.device + g, &ctx[g])) fail_here("no usable CUDA device");
-    wait_compiled();
-    if (!ctx[g]) {}  // failed above
-    else if (!compiled) { errors[g] = "shader module creation failed: " + compile_error; failed = true; }
-    else if (s2m_module_instantiate(compiled, ctx[g], &mod[g])) fail_here("shader module creation failed");
-    if (g == 0 && !failed) {
-      const uint32_t bands = 128;
-      std::vector<double> cost(bands, 1.0);
-      if (s2m_cost_probe(ctx[0], mod[0], &params, bands, cost.data())) std::fill(cost.begin(), cost.end(), 1.0);
-      double total = 0, mx = 0;
-      for (double c : cost) mx = std::max(mx, c);
-      for (double& c : cost) { c = std::max(c, mx * 1e-3); total += c; }
-      double acc = 0;
-      int next = 1;
-      for (uint32_t b = 0; b < bands && next < n; ++b) {
-        const double before = acc;
-        acc += cost[b];
-        while (next < n && acc >= total * next / n) {
-          const double frac = cost[b] > 0 ? (total * next / n - before) / cost[b] : 0.0;
-          bounds[next] = (uint32_t)((b + frac) * n_slices / bands + 0.5);
-          ++next;
-        }
-      }
-      bounds[n] = n_slices;
-      for (int k = 1; k <= n; ++k) bounds[k] = std::min(std::max(bounds[k], bounds[k - 1] + 1), n_slices - (uint32_t)(n - k));
-    }
-    barrier();
-    if (failed) return;
-    s2m_mesh_params p = params;
-    p.z_begin = bounds[g]; p.z_end = bounds[g + 1];
-    if (s2m_mesh_begin(ctx[g], mod[g], &p, &res[g])) fail_here("meshing failed");
-    else {
-      s2m_result_info ri;
-      s2m_result_get(res[g], &ri);
-      counts[g] = ri.n_vertices;
-    }
-    barrier();  // the "all-gather": every slab's vertex count is now visible to every thread
-    if (failed) return;
-    int64_t base = 0;
-    for (int k = 0; k < g; ++k) base += (int64_t)counts[k];
-    if (s2m_mesh_finish(res[g], base)) fail_here("quad emission failed");
-  };
   const auto t0 = std::chrono::steady_clock::now();
-  std::vector<std::thread> threads;
-  for (int g = 0; g < n; ++g) threads.emplace_back(worker, g);
-  if (s2m_module_compile(nullptr, shader, 0, &compiled)) { compiled = nullptr; compile_error = s2m_last_error(); }
-  compile_done();
-  for (auto& t : threads) t.join();
-  if (compiled) s2m_module_free(compiled);
+  // the N contexts (and the NCCL communicators) come up on another thread while this one lowers and NVRTC-compiles the SDF
+  s2m_multi* mc = nullptr;
+  int mc_status = 0;
+  std::string mc_error;
+  std::vector<int> ordinals;
+  for (int g = 0; g < n; ++g) ordinals.push_back(a.device + g);
+  std::thread mc_thread([&] {
+    mc_status = s2m_multi_create(ordinals.data(), n, a.no_nccl ? S2M_MULTI_NO_NCCL : 0u, &mc);
+    if (mc_status) mc_error = s2m_last_error();   // the error slot is per thread
+  });
+  s2m_module* compiled = nullptr;
+  const int compile_status = s2m_module_compile(nullptr, shader, 0, &compiled);
+  const std::string compile_error = compile_status ? s2m_last_error() : "";
+  mc_thread.join();
+  if (mc_status) { error("no usable CUDA devices: " + mc_error); return 101; }
+  if (compile_status) { error("shader module creation failed: " + compile_error); s2m_multi_destroy(mc); return 101; }
+  int nccl_version = 0;
+  const bool with_nccl = s2m_multi_uses_nccl(mc, &nccl_version) != 0;
+  info("CUDA contexts set up on " + std::to_string(n) + " GPUs" + (with_nccl ? " (NCCL " + std::to_string(nccl_version) + ")." : "."));
+  std::vector<s2m_result*> res((size_t)n, nullptr);
+  if (s2m_multi_mesh_run(mc, compiled, &params, res.data())) { error(std::string("meshing failed: ") + s2m_last_error()); s2m_multi_destroy(mc); return 101; }
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (failed) {
-    for (int g = 0; g < n; ++g) if (!errors[g].empty()) error("GPU " + std::to_string(a.device + g) + ": " + errors[g]);
-    return 101;
-  }
-  info("CUDA contexts set up on " + std::to_string(n) + " GPUs.");
+  std::vector<uint32_t> bounds((size_t)n + 1, 0);
+  s2m_multi_get_partition(mc, bounds.data());
+  s2m_multi_timings mt;
+  s2m_multi_last_timings(mc, &mt);
   uint64_t nv = 0, nq = 0, ninv = 0;
   for (int g = 0; g < n; ++g) {
     s2m_result_info ri;
-    s2m_result_get(res[g], &ri);
+    s2m_result_get(res[(size_t)g], &ri);
     nv += ri.n_vertices; nq += ri.n_quads; ninv += ri.n_invalid_quads;
     if (a.stats)
-      fprintf(stderr, "stats: GPU %d slices [%u, %u): %llu vertices, %llu quads, device %.3f ms\n", a.device + g, bounds[g], bounds[g + 1],
-              (unsigned long long)ri.n_vertices, (unsigned long long)ri.n_quads, ri.timings.device_ms);
+      fprintf(stderr, "stats: GPU %d slices [%u, %u): %llu vertices, %llu quads, device %.3f ms | begin %.3f, count exchange %.3f, finish %.3f ms\n", a.device + g,
+              bounds[(size_t)g], bounds[(size_t)g + 1], (unsigned long long)ri.n_vertices, (unsigned long long)ri.n_quads, ri.timings.device_ms,
+              mt.begin_ms[g], mt.exchange_ms[g], mt.finish_ms[g]);
   }
   info("Mesh has " + std::to_string(nv) + " vertices.");
   if (ninv) warn(std::to_string(ninv) + " invalid quads. Mesh will not be water-tight!");
-  if (a.stats) fprintf(stderr, "stats: %llu quads; JIT + meshing on %d GPUs took %.1f ms wall\n", (unsigned long long)nq, n, ms);
+  if (a.stats) fprintf(stderr, "stats: %llu quads; meshing on %d GPUs %.3f ms; contexts + JIT + meshing %.1f ms wall\n", (unsigned long long)nq, n, mt.wall_ms, ms);
   if (s2m_write_mesh_parts(res.data(), n, a.mesh.c_str(), a.binary_stl ? 1 : 0)) error(std::string("Could not write mesh to ") + s2m_last_error() + "!");
   info("Mesh written to " + a.mesh);
-  for (int g = 0; g < n; ++g) { s2m_result_free(res[g]); s2m_module_free(mod[g]); s2m_ctx_destroy(ctx[g]); }
+  for (int g = 0; g < n; ++g) s2m_result_free(res[(size_t)g]);
+  s2m_module_free(compiled);
+  s2m_multi_destroy(mc);
   s2m_shader_free(shader);
   return 0;
 }
@@ -297,6 +244,7 @@ int main(int argc, char** argv) {
     if (s == "--no-normals") { a.no_normals = true; continue; }
     if (s == "--binary-stl") { a.binary_stl = true; continue; }
     if (s == "--stats") { a.stats = true; continue; }
+    if (s == "--no-nccl") { a.no_nccl = true; continue; }
     fprintf(stderr, "error: unexpected argument '%s' found\n\n", s.c_str());
     usage(stderr);
     return 2;

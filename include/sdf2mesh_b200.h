@@ -106,8 +106,9 @@ int s2m_ctx_device_info(const s2m_ctx* ctx, char* name, size_t name_len, int* sm
  * replaces Sdf3DShader::create_shader_module (shader.rs:220) + create_compute_pipeline (main.rs:283-290):
  * front-end -> CUDA C++ -> NVRTC (sm_100a, --fmad=false) -> cubin -> cuModuleLoadData.
  * ctx may be NULL: compile to cubin only (no device needed; used by CPU-side tests).
- * With the environment variable S2M_CACHE_DIR set, cubins are kept there (one file per distinct
- * translation unit + options + NVRTC version) and a repeated compile is a file read. */
+ * Cubins are kept on disk -- in $S2M_CACHE_DIR if set (set but empty: no cache), else $XDG_CACHE_HOME/sdf2mesh_b200, else
+ * ~/.cache/sdf2mesh_b200 -- one file per distinct translation unit + options + NVRTC version; a repeated compile, also by
+ * another process, is a file read. */
 typedef struct s2m_module s2m_module;
 #define S2M_COMPILE_ALLOW_FMA 1u /* let ptxas contract a*b+c (faster, NOT bit-identical to the oracle) */
 int s2m_module_compile(s2m_ctx* ctx, const s2m_shader* shader, uint32_t flags, s2m_module** out);
@@ -143,6 +144,13 @@ void s2m_module_free(s2m_module* m);
                                        s2m_result_info.quads32 instead of u64 in .quads: half the bytes to copy and keep.
                                        s2m_mesh_finish fails with S2M_ERR_UNSUPPORTED if an index would not fit. */
 #define S2M_MESH_CLASSIFY_FROM_SLAB 16u /* K2 re-reads the f32 slab through shared memory instead of K1's class bit planes */
+#define S2M_MESH_NO_SLAB 256u        /* slab-free form: K1 writes only the 2-bit corner classes (0.25 B per corner instead of 4.25), K4a
+                                       evaluates all 8 corners of every candidate cell.  The default for SDFs that are cheap to evaluate
+                                       (s2m_module_prefers_no_slab); same results either way. */
+#define S2M_MESH_RELATIVE_QUADS 512u /* quads keep the slab-relative indices the device wrote: global index = value + quad_index_add
+                                       (s2m_result_info; wrapping in the index width -- a vertex of the halo slice is "negative").
+                                       s2m_mesh_finish then only waits for the copies instead of adding the base on the host; the
+                                       writers (s2m_write_mesh_parts, s2m_result_write_*) accept both forms. */
 
 typedef struct s2m_mesh_params {
   uint32_t struct_size; /* sizeof(s2m_mesh_params) */
@@ -195,15 +203,22 @@ typedef struct s2m_result_info {
                                     global_vertex_base - n_halo_vertices + j), so a slab can be written on its own */
   int64_t global_vertex_base;    /* what s2m_mesh_finish was given (0 for s2m_mesh_run) */
   const uint32_t* quads32;       /* S2M_MESH_QUADS_U32: 4 * n_quads u32 indices, and .quads is NULL */
+  int64_t quad_index_add;        /* global vertex index = quad value + quad_index_add, wrapping in the index width: 0 unless
+                                    S2M_MESH_RELATIVE_QUADS (then = global_vertex_base) */
   s2m_timings timings;
 } s2m_result_info;
 
-/* replaces main.rs:298-356 (slice loop) + VertexList (mesh.rs:229-265): K1 slab, K2 classify,
- * K3 compact, K4a vertices; vertices land in pinned host memory. */
+/* replaces main.rs:298-356 (slice loop) + VertexList (mesh.rs:229-265) + VertexList::fetch_triangle_indices
+ * (mesh.rs:267-324): K1 slab, K2 classify, K3 compact, K4a vertices, K4b quads, z-chunk by z-chunk, each chunk's
+ * vertices and quads copied into pinned host memory while the next chunk computes.  Returns when the last copy has
+ * been QUEUED; the vertex count (s2m_result_get) is final, the arrays are not yet.  Quads are written with
+ * slab-relative indices (local vertex index, the recomputed halo slice counting as negative), so nothing waits for
+ * the global vertex base. */
 int s2m_mesh_begin(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, s2m_result** out);
-/* replaces VertexList::fetch_triangle_indices (mesh.rs:267-324): K4b quads with
- * index = local + global_vertex_base (the exclusive prefix of n_vertices over lower z-slabs,
- * obtained by the caller from an allgather across ranks; 0 on one GPU). */
+/* Waits for the copies and fixes the slab's place in the whole mesh: global_vertex_base = the exclusive prefix of
+ * n_vertices over lower z-slabs (from an all-gather across ranks; 0 on one GPU).  By default the quads in host
+ * memory become global indices (+ base, a pass over the quads on a few host threads); with S2M_MESH_RELATIVE_QUADS
+ * they stay relative and the base is reported as s2m_result_info.quad_index_add. */
 int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base);
 /* begin + finish(0) */
 int s2m_mesh_run(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, s2m_result** out);
@@ -233,10 +248,52 @@ int s2m_write_mesh_arrays(const s2m_result_info* parts, int n_parts, const char*
  * (measured: ~2 ms per step on 8 GPUs). */
 int s2m_read_device_words(s2m_ctx* ctx, const void* device_words, uint32_t n, uint64_t* out, void* cuda_stream);
 
+/* ------------------------------------------------------------------ several GPUs in one process: z-slabs
+ * The reference drives one device from one thread (main.rs:180-196, :298-356).  s2m_multi holds one s2m_ctx per device
+ * ordinal, one host thread per device (kept alive between runs) and one NCCL communicator per device (ncclCommInitAll;
+ * libnccl.so.2 is loaded with dlopen).  s2m_multi_mesh_run cuts the grid into contiguous z-slabs balanced by cost
+ * (s2m_cost_probe on the first device, refined once from the measured times of the second run on the same SDF and
+ * grid), meshes every slab with s2m_mesh_begin on its GPU -- each recomputing the slice below its slab as halo --
+ * exchanges the per-slab vertex counts with ONE ncclAllGather (8 bytes per rank) and calls s2m_mesh_finish with the
+ * exclusive prefix.  parts_out receives n results in z order (S2M_MESH_RELATIVE_QUADS form: global index = quad value +
+ * quad_index_add); free each with s2m_result_free, write them with s2m_write_mesh_parts.  One host thread drives one
+ * s2m_multi at a time. */
+typedef struct s2m_multi s2m_multi;
+#define S2M_MULTI_NO_NCCL 1u       /* exchange the counts through host memory (a barrier between the host threads) */
+#define S2M_MULTI_EQUAL_SLABS 2u   /* equal-thickness slabs: no cost probe, no refinement */
+#define S2M_MULTI_NO_REBALANCE 4u  /* keep the cost-probe partition: no refinement from measured times */
+typedef struct s2m_multi_timings {
+  int n;                     /* devices */
+  double wall_ms;            /* the whole call after partitioning, host clock */
+  double begin_ms[64];       /* per device, host clock: s2m_mesh_begin (K1 .. K4b, copies queued) */
+  double exchange_ms[64];    /* the count all-gather, including the wait for the slowest device's begin */
+  double finish_ms[64];      /* s2m_mesh_finish: the wait for this device's last copies */
+} s2m_multi_timings;
+int s2m_multi_create(const int* device_ordinals, int n, uint32_t flags, s2m_multi** out);
+void s2m_multi_destroy(s2m_multi* mc);
+int s2m_multi_size(const s2m_multi* mc);
+s2m_ctx* s2m_multi_ctx(s2m_multi* mc, int k);                  /* the k-th device's context (owned by mc) */
+int s2m_multi_uses_nccl(const s2m_multi* mc, int* nccl_version); /* 1 if the counts travel through ncclAllGather */
+/* `compiled`: a module from s2m_module_compile (with any ctx, or NULL); its cubins are loaded once per device. */
+int s2m_multi_mesh_run(s2m_multi* mc, const s2m_module* compiled, const s2m_mesh_params* p, s2m_result** parts_out);
+int s2m_multi_get_partition(const s2m_multi* mc, uint32_t* bounds_out /* n + 1 */);
+int s2m_multi_last_timings(const s2m_multi* mc, s2m_multi_timings* out);
+/* Slab boundaries (host arithmetic, needs no device): b[0..world] over n_slices z-slices, strictly increasing, slab g
+ * getting ~1/world of `cost` (relative cost of n_cost equal-thickness z bands; NULL = equal thickness). */
+int s2m_partition_slices(uint32_t n_slices, int world, const double* cost, int n_cost, uint32_t* bounds_out);
+/* the same boundaries refined from the seconds every slab actually took (cost: the band profile, or NULL) */
+int s2m_rebalance_slices(const uint32_t* bounds, int world, const double* seconds, const double* cost, int n_cost, uint32_t* bounds_out);
+
 /* diagnostics */
 int s2m_eval_points(s2m_ctx* ctx, s2m_module* m, const float* xyz, uint64_t n, float* out);
 /* 1 if K1 of this module evaluates corner pairs in packed f32x2 arithmetic (csrc/s2m_pvec.h) */
 int s2m_module_is_packed(const s2m_module* m);
+/* 1 if this module's SDF is cheap enough that meshing defaults to the slab-free form (S2M_MESH_NO_SLAB) */
+int s2m_module_prefers_no_slab(const s2m_module* m);
+/* FP32 FMA throughput of the device in TFLOP/s, measured with dependent-chain kernels (no memory traffic, ~2 ms each, best of 3):
+ * out[0] FFMA reg,reg,reg; out[1] FFMA reg,imm,imm; out[2] FFMA2 (packed f32x2) pair,bcast,imm.  The denominator of K1's
+ * FP32 roofline (bench.py); 148 SMs x 128 lanes x 2 x clock is the nominal figure beside it. */
+int s2m_measure_fp32_peak(s2m_ctx* ctx, double out_tflops[3]);
 /* the packed form, raw: lane lo evaluates xyz_a[i], lane hi xyz_b[i]; disagreed[i] != 0: the lanes took
  * different decisions and out_b[i] is not valid (K1 re-evaluates such corners on their own).
  * S2M_ERR_UNSUPPORTED if the module has no packed form. */

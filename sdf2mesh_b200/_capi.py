@@ -22,6 +22,8 @@ MESH_ALL_SLICES, MESH_NO_NORMALS, MESH_EXACT_DENSE, MESH_KEEP_CANDIDATES, MESH_C
 MESH_KEEP_INVALID = 32
 MESH_CONSISTENT_CORNERS = 64
 MESH_QUADS_U32 = 128
+MESH_NO_SLAB = 256
+MESH_RELATIVE_QUADS = 512
 
 
 class S2mError(RuntimeError):
@@ -71,10 +73,17 @@ class ResultInfo(ctypes.Structure):
         ("quads", ctypes.POINTER(ctypes.c_uint64)), ("candidates", ctypes.POINTER(ctypes.c_uint64)),
         ("invalid_records", ctypes.POINTER(ctypes.c_uint64)), ("n_invalid_records", ctypes.c_uint64),
         ("halo_positions", ctypes.POINTER(ctypes.c_float)), ("global_vertex_base", ctypes.c_int64),
-        ("quads32", ctypes.POINTER(ctypes.c_uint32)),
+        ("quads32", ctypes.POINTER(ctypes.c_uint32)), ("quad_index_add", ctypes.c_int64),
         ("timings", Timings),
     ]
 
+
+class MultiTimings(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int), ("wall_ms", ctypes.c_double), ("begin_ms", ctypes.c_double * 64),
+                ("exchange_ms", ctypes.c_double * 64), ("finish_ms", ctypes.c_double * 64)]
+
+
+MULTI_NO_NCCL, MULTI_EQUAL_SLABS, MULTI_NO_REBALANCE = 1, 2, 4
 
 # every symbol include/sdf2mesh_b200.h declares: name -> (restype, argtypes)
 _P = ctypes.c_void_p
@@ -124,10 +133,22 @@ SYMBOLS = {
     "s2m_write_mesh_arrays": (ctypes.c_int, [_P, ctypes.c_int, _S, ctypes.c_int]),
     "s2m_eval_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_uint64, _P]),
     "s2m_module_is_packed": (ctypes.c_int, [_P]),
+    "s2m_module_prefers_no_slab": (ctypes.c_int, [_P]),
+    "s2m_measure_fp32_peak": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
     "s2m_eval_pairs": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P]),
     "s2m_debug_slab_plane": (ctypes.c_int, [_P, _P, ctypes.POINTER(MeshParams), ctypes.c_uint32, _P]),
     "s2m_cost_probe": (ctypes.c_int, [_P, _P, ctypes.POINTER(MeshParams), ctypes.c_uint32, _P]),
     "s2m_read_device_words": (ctypes.c_int, [_P, _P, ctypes.c_uint32, _P, _P]),
+    "s2m_multi_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_uint32, _PP]),
+    "s2m_multi_destroy": (None, [_P]),
+    "s2m_multi_size": (ctypes.c_int, [_P]),
+    "s2m_multi_ctx": (_P, [_P, ctypes.c_int]),
+    "s2m_multi_uses_nccl": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int)]),
+    "s2m_multi_mesh_run": (ctypes.c_int, [_P, _P, ctypes.POINTER(MeshParams), ctypes.POINTER(ctypes.c_void_p)]),
+    "s2m_multi_get_partition": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint32)]),
+    "s2m_multi_last_timings": (ctypes.c_int, [_P, ctypes.POINTER(MultiTimings)]),
+    "s2m_partition_slices": (ctypes.c_int, [ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(ctypes.c_uint32)]),
+    "s2m_rebalance_slices": (ctypes.c_int, [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.POINTER(ctypes.c_uint32)]),
 }
 
 _lib = None

@@ -20,6 +20,9 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <cerrno>
 #include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
@@ -136,6 +139,42 @@ struct DevBuf {
 
 struct PinnedBlock { void* p; size_t cap; bool used; };
 
+// A growable pinned host array for one of a result's big outputs (positions, normals, keys, nibbles, quads).
+// The virtual address range is reserved once (mmap, MAP_NORESERVE: costs nothing until touched) for the largest
+// size the array can reach, and page-locked piece by piece (cudaHostRegister) as the run learns how much it
+// needs: the array stays contiguous, never moves, and a FIRST run on a context can start copying chunk 0's
+// vertices while later chunks are still being computed, without knowing the final size (cudaHostAlloc of the
+// whole output up front is what a cold run used to wait for: ~0.3 ms per MB).  Regions go back to the
+// context's pool with their pages still locked, so steady-state runs register nothing.
+struct PinnedRegion {
+  char* base = nullptr;
+  size_t reserved = 0, registered = 0;
+  bool used = false;
+  std::vector<std::pair<size_t, size_t>> segs;  // registered (offset, length) pieces, for cudaHostUnregister
+  int ensure(size_t bytes, size_t ahead) {
+    if (bytes <= registered) return S2M_OK;
+    if (bytes > reserved) return fail(S2M_ERR_OOM, "output exceeds the reserved host address range (" + std::to_string(reserved) + " B)");
+    constexpr size_t kGrain = 2u << 20;
+    size_t upto = std::min(reserved, (bytes + ahead + kGrain - 1) / kGrain * kGrain);
+    cudaError_t e = cudaHostRegister(base + registered, upto - registered, cudaHostRegisterPortable);
+    if (e != cudaSuccess && upto > bytes) {   // retry without the read-ahead
+      cudaGetLastError();
+      upto = std::min(reserved, (bytes + kGrain - 1) / kGrain * kGrain);
+      e = cudaHostRegister(base + registered, upto - registered, cudaHostRegisterPortable);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(S2M_ERR_OOM, std::string("cudaHostRegister(") + std::to_string(upto - registered) + " B): " + cudaGetErrorString(e)); }
+    segs.emplace_back(registered, upto - registered);
+    registered = upto;
+    return S2M_OK;
+  }
+  void destroy() {
+    for (auto& sg : segs) cudaHostUnregister(base + sg.first);
+    segs.clear();
+    if (base) munmap(base, reserved);
+    base = nullptr; reserved = registered = 0;
+  }
+};
+
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -160,14 +199,51 @@ struct s2m_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr, prod_stream = nullptr;
   DevBuf slab, cls, slab2, cls2, cand_mask, word_prefix, cand_key, cand_vrank, status, counters;
   DevBuf v_pos, v_nrm, v_key, v_nib, quads, scratch, invalid;
-  std::vector<PinnedBlock> pinned;
-  unsigned long long* h_counters = nullptr;  // pinned, 16 words
+  std::vector<PinnedBlock> pinned;            // small outputs (candidate list, invalid records, halo positions)
+  std::vector<std::unique_ptr<PinnedRegion>> regions;  // big outputs
+  unsigned long long* h_counters = nullptr;  // pinned + mapped, 16 words: [buf] = candidate count of the chunk in slab buffer buf (written by K2)
   unsigned long long* h_words = nullptr;     // pinned + mapped, 32 words (s2m_read_device_words)
+  unsigned long long* h_slots = nullptr;     // pinned + mapped, 8 words per z-chunk: written by K4b's last block
+  size_t h_slots_cap = 0;                    // chunks
+  size_t va_limit = ~(size_t)0;              // largest host address range mmap has been seen to refuse, halved (lease_region)
+  DevBuf chunk_tot;                          // u64 [n_chunks + 1][2]: {vertices, quads} emitted up to the end of each z-chunk
   cudaEvent_t ev[16]{};
   std::vector<cudaEvent_t> ev_pool;   // per-launch timing events, grown on demand
-  uint64_t hint_nv = 0, hint_nq = 0;  // output sizes of the previous run (pinned capacity guess)
   bool busy = false;  // a begin() without finish()/free() is outstanding
-  uint32_t publish_launches = 0;  // k_publish launches since the last begin() (they count as kernel launches too)
+
+  // a region whose address range can hold `reserve` bytes; prefers the one with the most pages already locked
+  PinnedRegion* lease_region(size_t reserve) {
+    PinnedRegion* best = nullptr;
+    for (auto& g : regions)
+      if (!g->used && g->reserved >= std::min(reserve, va_limit) && (!best || g->registered > best->registered)) best = g.get();
+    if (best) { best->used = true; return best; }
+    std::unique_ptr<PinnedRegion> g(new PinnedRegion());
+    size_t want = std::max<size_t>(reserve, 64u << 20);
+    want = (want + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+    void* m = MAP_FAILED;
+    for (;; want /= 2) {   // an address-space limit (ulimit -v, strict overcommit): settle for less; an output that outgrows it is an OOM error
+      want = std::min(want, va_limit);
+      m = mmap(nullptr, want, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+      if (m != MAP_FAILED) break;
+      if (want <= (64u << 20)) return nullptr;
+      va_limit = want / 2;
+    }
+    g->base = static_cast<char*>(m); g->reserved = want; g->used = true;
+    regions.push_back(std::move(g));
+    return regions.back().get();
+  }
+  int ensure_slots(size_t chunks) {
+    if (chunks <= h_slots_cap) return S2M_OK;
+    if (h_slots) cudaFreeHost(h_slots);
+    h_slots = nullptr; h_slots_cap = 0;
+    const size_t want = std::max<size_t>(chunks + chunks / 2, 64);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h_slots), want * 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(S2M_ERR_OOM, "cudaHostAlloc for the chunk result slots failed");
+    }
+    h_slots_cap = want;
+    return S2M_OK;
+  }
 
   void* lease_pinned(size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -193,8 +269,9 @@ struct s2m_ctx {
   }
 };
 
-enum Counter { C_NCAND = 0, C_NVERT = 1, C_NHALO = 2, C_NQUAD = 3, C_NINVALID = 4, C_TICKET0 = 5, C_TICKET1 = 6, C_TICKET2 = 7, C_INVALID_CURSOR = 8,
-               C_CHUNK_CAND0 = 9, C_CHUNK_CAND1 = 10 /* candidates of the chunk K2 classified into slab buffer 0 / 1 */, C_COUNT = 16 };
+// device counters (u64 words).  C_CHUNK_CANDb / C_K2_DONEb: candidates of the chunk K2 classified into slab buffer b and
+// K2's block-completion counter for it (adjacent: one 16-byte memset resets both).
+enum Counter { C_NHALO = 2, C_NINVALID = 4, C_INVALID_CURSOR = 8, C_CHUNK_CAND0 = 9, C_K2_DONE0 = 10, C_CHUNK_CAND1 = 11, C_K2_DONE1 = 12, C_COUNT = 16 };
 enum CtxEvent { EV_BEGIN = 0, EV_KERNELS_DONE = 1, EV_ALL_DONE = 2, EV_PRODUCED0 = 4, EV_PRODUCED1 = 5, EV_CONSUMED0 = 6, EV_CONSUMED1 = 7 };
 constexpr unsigned long long kInvalidCapacity = 1ull << 20;
 
@@ -242,8 +319,11 @@ extern "C" void s2m_ctx_destroy(s2m_ctx* c) {
                     &c->v_pos, &c->v_nrm, &c->v_key, &c->v_nib, &c->quads, &c->scratch, &c->invalid})
     b->release();
   for (auto& b : c->pinned) cudaFreeHost(b.p);
+  for (auto& g : c->regions) g->destroy();
+  c->chunk_tot.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->h_words) cudaFreeHost(c->h_words);
+  if (c->h_slots) cudaFreeHost(c->h_slots);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : c->ev_pool) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -265,6 +345,10 @@ constexpr bool kK1PackedDefault = true;  // see s2m_pvec.h; S2M_K1_PACKED=0/1 ov
 constexpr bool kK1PackedSqrtDefault = true;
 constexpr int kK1PackedMaxTinySize = 64;  // expression nodes of one evaluation (torus.sdf3d: 21, p_key.sdf3d: 206)
 constexpr int kK1PackedMinScore = 4;     // transcendental calls in the SDF (mandelmesh.frag: 7; the .sdf3d examples: 0)
+// Slab-free default (S2M_MESH_NO_SLAB): an SDF of at most this many expression nodes and no transcendental-heavy body.
+// Writing 4 B per corner costs K1 more than K4a saves by reading 5.5 of a candidate's 8 corners back (torus 2048^3:
+// K1 is 43 % of HBM write bandwidth with the slab and issue-bound without it).  torus.sdf3d: 21 nodes, p_key.sdf3d: 206.
+constexpr int kSlabFreeMaxSize = 256;
 constexpr unsigned kK1RowsDefault = 2;  // measured: mandelbulb K1 -0.6 %, torus K1 -7 %; +10-20 % NVRTC time
 
 struct s2m_module {
@@ -277,6 +361,7 @@ struct s2m_module {
   s2m_ctx* ctx = nullptr;
   unsigned k1_rows = 1;  // grid rows per K1 thread (S2M_K1_ROWS the kernels were compiled with)
   bool k1_packed = false;  // K1 evaluates corner pairs in f32x2 arithmetic (s2m_pvec.h)
+  bool slab_free_default = false;  // cheap SDF: K1 writes no f32 slab, K4a evaluates all 8 corners (S2M_MESH_NO_SLAB is the default for this module)
   double ms_frontend = 0, ms_nvrtc = 0, ms_load = 0;
 };
 
@@ -315,6 +400,7 @@ int load_parts(s2m_module* m) {
 // How K1 evaluates the SDF.  `packed_text` is the front-end's packed (f32x2)
 // translation, empty for "one corner per evaluation".
 struct K1Plan {
+  bool slab_free = false;                   // cheap SDF: meshing defaults to the slab-free form (kSlabFreeMaxSize)
   std::string packed_text;
   bool packed_sqrt = kK1PackedSqrtDefault;  // the refinement step of sqrt in f32x2 as well (S2M_K1_PACKED=2)
   bool heavy = false;                       // >= kK1PackedMinScore transcendental calls
@@ -333,6 +419,7 @@ K1Plan plan_k1(std::string packed_text) {
   const size_t at = packed_text.find("// s2m-packed-score: ");
   if (at != std::string::npos) sscanf(packed_text.c_str() + at + 21, "%d %d", &score, &size);
   plan.heavy = score >= kK1PackedMinScore;
+  plan.slab_free = at != std::string::npos && !plan.heavy && size > 0 && size <= kSlabFreeMaxSize;
   bool use = kK1PackedDefault && (plan.heavy || size <= kK1PackedMaxTinySize);
   if (const char* e = getenv("S2M_K1_PACKED")) {
     use = atoi(e) != 0;
@@ -340,6 +427,24 @@ K1Plan plan_k1(std::string packed_text) {
   }
   if (use) plan.packed_text = std::move(packed_text);
   return plan;
+}
+
+// Where compiled cubins are kept between processes: $S2M_CACHE_DIR if set (set but empty: no cache), else
+// $XDG_CACHE_HOME/sdf2mesh_b200, else $HOME/.cache/sdf2mesh_b200 (created on first use; no home directory: no cache).
+// A one-shot CLI run of an SDF it has seen before then skips NVRTC (0.5-0.8 s) for a file read of ~1 ms.
+std::string cubin_cache_dir() {
+  if (const char* e = getenv("S2M_CACHE_DIR")) return e;
+  std::string base;
+  if (const char* x = getenv("XDG_CACHE_HOME")) base = x;
+  if (base.empty()) {
+    const char* h = getenv("HOME");
+    if (!h || !*h) return "";
+    base = std::string(h) + "/.cache";
+    mkdir(base.c_str(), 0700);
+  }
+  const std::string dir = base + "/sdf2mesh_b200";
+  if (mkdir(dir.c_str(), 0700) != 0 && errno != EEXIST) return "";
+  return dir;
 }
 
 // One NVRTC program: translation unit + options -> cubin (from S2M_CACHE_DIR when it is there).  Touches
@@ -359,7 +464,8 @@ int compile_part(const std::string& source, const std::vector<std::string>& opts
   std::string cache_path;
   cubin->clear();
   log->clear();
-  if (const char* dir = getenv("S2M_CACHE_DIR")) {
+  const std::string cache_dir = cubin_cache_dir();
+  if (const char* dir = cache_dir.empty() ? nullptr : cache_dir.c_str()) {
     if (*dir) {
       int nv_major = 0, nv_minor = 0;
       nvrtcVersion(&nv_major, &nv_minor);
@@ -429,6 +535,7 @@ int compile_part(const std::string& source, const std::vector<std::string>& opts
 // S2M_JIT_SPLIT=0 compiles one program with everything, as one would offline with nvcc.
 int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uint32_t flags, std::string* error) {
   m->k1_packed = plan.packed();
+  m->slab_free_default = plan.slab_free;
   m->cuda_source = std::string("#include \"s2m_sdf3d_lib.h\"\n#include \"s2m_scan.cuh\"\n") +
                    "namespace s2m_user {\nusing namespace s2m;\n" + user + "\n}  // namespace s2m_user\n";
   if (plan.packed()) {
@@ -534,6 +641,7 @@ extern "C" int s2m_module_instantiate(const s2m_module* compiled, s2m_ctx* ctx, 
   for (int k = 0; k < compiled->n_parts; ++k) m->cubin[k] = compiled->cubin[k];
   m->k1_rows = compiled->k1_rows;
   m->k1_packed = compiled->k1_packed;
+  m->slab_free_default = compiled->slab_free_default;
   m->ms_frontend = compiled->ms_frontend;
   m->ms_nvrtc = compiled->ms_nvrtc;
   m->ctx = ctx;
@@ -630,33 +738,35 @@ struct s2m_result {
   GridDev grid{};
   uint32_t z_first = 0, nz = 0, label_add = 0, halo = 0, words_x = 0;
   uint64_t n_cand = 0, n_vert_total = 0, n_halo = 0, n_quads = 0, n_invalid = 0;
-  float* h_pos = nullptr; float* h_nrm = nullptr; uint64_t* h_key = nullptr; uint8_t* h_nib = nullptr;
-  uint64_t* h_quads = nullptr; uint64_t* h_cand = nullptr; uint64_t* h_invalid = nullptr; float* h_halo_pos = nullptr;
+  // big outputs: growable pinned regions (PinnedRegion); small ones: blocks of the pinned pool
+  PinnedRegion *g_pos = nullptr, *g_nrm = nullptr, *g_key = nullptr, *g_nib = nullptr, *g_quads = nullptr;
+  uint64_t* h_cand = nullptr; uint64_t* h_invalid = nullptr; float* h_halo_pos = nullptr;
   int64_t global_base = 0;
   uint64_t n_invalid_records = 0;
-  uint64_t cap_v = 0, cap_q = 0;   // capacity (elements) of the pinned vertex / quad blocks
-  bool streamed = false;           // vertex (and quad) chunks were copied while later chunks computed
-  bool quads_done = false;         // K4b ran inside begin (single-slab s2m_mesh_run)
+  uint64_t copied_v = 0, copied_q = 0;   // vertices (halo included) / quads whose device->host copy has been issued
   s2m_timings t{};
   double wall0 = 0;
   size_t ev_used = 0;              // events taken from the ctx pool by this run
   struct Span { int kind; size_t e0, e1; };  // kind: 0 K1, 1 K2, 2 K3, 3 K4a, 4 K4b, 5 copy
   std::vector<Span> spans;
   bool finished = false;
-  // two-call form: the last chunk's vertex copy is issued by finish(), after the caller's count exchange --
-  // a bulk copy in flight delays every small device->host read behind it (PCIe), including that exchange's result
-  bool deferred_copy = false;
-  uint64_t deferred_v0 = 0;
   bool quads_u32() const { return (params.flags & S2M_MESH_QUADS_U32) != 0; }
+  bool relative() const { return (params.flags & S2M_MESH_RELATIVE_QUADS) != 0; }
   size_t quad_bytes() const { return quads_u32() ? 16 : 32; }  // bytes per quad, device and host
+  template <class T> T* host(PinnedRegion* g) const { return g ? reinterpret_cast<T*>(g->base) : nullptr; }
 };
 
 extern "C" void s2m_result_free(s2m_result* r) {
   if (!r) return;
-  if (r->ctx) {
-    for (void* p : {(void*)r->h_pos, (void*)r->h_nrm, (void*)r->h_key, (void*)r->h_nib, (void*)r->h_quads, (void*)r->h_cand, (void*)r->h_invalid, (void*)r->h_halo_pos})
-      if (p) r->ctx->release_pinned(p);
-    if (!r->finished) r->ctx->busy = false;
+  if (s2m_ctx* c = r->ctx) {
+    if (!r->finished) {   // copies into the regions may still be in flight: wait before the memory is handed to the next run
+      cudaSetDevice(c->device);
+      cudaStreamSynchronize(c->copy_stream);
+      cudaStreamSynchronize(c->stream);
+      c->busy = false;
+    }
+    for (PinnedRegion* g : {r->g_pos, r->g_nrm, r->g_key, r->g_nib, r->g_quads}) if (g) g->used = false;
+    for (void* p : {(void*)r->h_cand, (void*)r->h_invalid, (void*)r->h_halo_pos}) if (p) c->release_pinned(p);
   }
   delete r;
 }
@@ -697,80 +807,32 @@ size_t take_event(s2m_ctx* c, s2m_result* r) {
 #define SPAN_END(stream_) \
   do { const size_t e1__ = take_event(c, r); CUDA_TRY(cudaEventRecord(c->ev_pool[e1__], stream_)); r->spans.push_back({span_kind__, span_e0__, e1__}); } while (0)
 
-int ensure_pinned_outputs(s2m_ctx* c, s2m_result* r, uint64_t need_v, uint64_t need_q, bool want_quads) {
-  if (need_v > r->cap_v || !r->h_pos) {
-    for (void* p : {(void*)r->h_pos, (void*)r->h_nrm, (void*)r->h_key, (void*)r->h_nib}) if (p) c->release_pinned(p);
-    r->h_pos = (float*)c->lease_pinned(need_v * 12);
-    r->h_nrm = (float*)c->lease_pinned(need_v * 12);
-    r->h_key = (uint64_t*)c->lease_pinned(need_v * 8);
-    r->h_nib = (uint8_t*)c->lease_pinned(need_v);
-    if (!r->h_pos || !r->h_nrm || !r->h_key || !r->h_nib) return fail(S2M_ERR_OOM, "cudaHostAlloc for vertex output failed");
-    r->cap_v = need_v;
-  }
-  if (want_quads && (need_q > r->cap_q || !r->h_quads)) {
-    if (r->h_quads) c->release_pinned(r->h_quads);
-    r->h_quads = (uint64_t*)c->lease_pinned(need_q * r->quad_bytes());
-    if (!r->h_quads) return fail(S2M_ERR_OOM, "cudaHostAlloc for quad output failed");
-    r->cap_q = need_q;
-  }
-  return S2M_OK;
-}
-
-// device -> pinned host copies of vertices [v0, v1) (indices include the halo) and quads [q0, q1)
-int copy_out(s2m_ctx* c, s2m_result* r, cudaStream_t st, uint64_t v0, uint64_t v1, uint64_t q0, uint64_t q1) {
-  v0 = std::max<uint64_t>(v0, r->n_halo);
+// Device -> pinned host copies of what the chunks up to now have added: vertices [copied_v, vert_total) (local
+// indices, the halo slice's first and never copied) and quads [copied_q, quad_total).  The pinned regions grow
+// (cudaHostRegister) by what this copy needs plus as much again, so a first run registers a chunk ahead.
+int copy_out(s2m_ctx* c, s2m_result* r, cudaStream_t st, uint64_t vert_total, uint64_t quad_total) {
+  const uint64_t v0 = std::max<uint64_t>(r->copied_v, r->n_halo), v1 = vert_total;
+  int e;
   if (v1 > v0) {
-    const uint64_t n = v1 - v0, h = v0 - r->n_halo;
-    CUDA_TRY(cudaMemcpyAsync(r->h_pos + 3 * h, c->v_pos.as<float>() + 3 * v0, n * 12, cudaMemcpyDeviceToHost, st));
-    if (!(r->params.flags & S2M_MESH_NO_NORMALS))
-      CUDA_TRY(cudaMemcpyAsync(r->h_nrm + 3 * h, c->v_nrm.as<float>() + 3 * v0, n * 12, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(r->h_key + h, c->v_key.as<unsigned long long>() + v0, n * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(r->h_nib + h, c->v_nib.as<unsigned char>() + v0, n, cudaMemcpyDeviceToHost, st));
+    const uint64_t n = v1 - v0, h = v0 - r->n_halo, own = v1 - r->n_halo;
+    const bool normals = !(r->params.flags & S2M_MESH_NO_NORMALS);
+    if ((e = r->g_pos->ensure(own * 12, n * 12))) return e;
+    if (normals && (e = r->g_nrm->ensure(own * 12, n * 12))) return e;
+    if ((e = r->g_key->ensure(own * 8, n * 8))) return e;
+    if ((e = r->g_nib->ensure(own, n))) return e;
+    CUDA_TRY(cudaMemcpyAsync(r->host<float>(r->g_pos) + 3 * h, c->v_pos.as<float>() + 3 * v0, n * 12, cudaMemcpyDeviceToHost, st));
+    if (normals) CUDA_TRY(cudaMemcpyAsync(r->host<float>(r->g_nrm) + 3 * h, c->v_nrm.as<float>() + 3 * v0, n * 12, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(r->host<uint64_t>(r->g_key) + h, c->v_key.as<unsigned long long>() + v0, n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(r->host<uint8_t>(r->g_nib) + h, c->v_nib.as<unsigned char>() + v0, n, cudaMemcpyDeviceToHost, st));
   }
-  if (q1 > q0) {
+  r->copied_v = std::max(r->copied_v, v1);
+  if (quad_total > r->copied_q) {
     const size_t qb = r->quad_bytes();
-    CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(r->h_quads) + qb * q0, c->quads.as<char>() + qb * q0, (q1 - q0) * qb, cudaMemcpyDeviceToHost, st));
+    const uint64_t q0 = r->copied_q, n = quad_total - q0;
+    if ((e = r->g_quads->ensure(quad_total * qb, n * qb))) return e;
+    CUDA_TRY(cudaMemcpyAsync(r->host<char>(r->g_quads) + qb * q0, c->quads.as<char>() + qb * q0, n * qb, cudaMemcpyDeviceToHost, st));
+    r->copied_q = quad_total;
   }
-  return S2M_OK;
-}
-
-int launch_k4b(s2m_ctx* c, s2m_result* r, cudaStream_t s, uint64_t v_begin, uint64_t v_end, uint64_t quad_base, long long index_offset) {
-  unsigned long long* d_cnt = c->counters.as<unsigned long long>();
-  v_begin = std::max<uint64_t>(v_begin, r->n_halo);
-  if (v_end <= v_begin) return S2M_OK;
-  const unsigned tiles = s2m_k4b_tiles(v_end - v_begin);
-  int st;
-  const size_t qb = r->quad_bytes();
-  if ((st = c->quads.ensure_preserve((size_t)(quad_base + (v_end - v_begin) * 3) * qb + 64, (size_t)quad_base * qb, s))) return st;
-  if ((st = c->scratch.ensure(((size_t)tiles + 8) * 8 + 64))) return st;
-  CUDA_TRY(cudaMemsetAsync(c->scratch.p, 0, ((size_t)tiles + 8) * 8 + 64, s));
-  S2mK4bArgs a{};
-  a.vert_key = c->v_key.as<unsigned long long>(); a.vert_nibble = c->v_nib.as<unsigned char>();
-  a.v_begin = v_begin; a.v_end = v_end; a.quad_base = quad_base;
-  a.cand_mask = c->cand_mask.as<uint32_t>(); a.word_prefix = c->word_prefix.as<uint32_t>(); a.cand_vrank = c->cand_vrank.as<uint32_t>();
-  a.words_x = r->words_x; a.res_y = r->grid.res[1]; a.z_first = r->z_first; a.label_add = r->label_add;
-  a.index_offset = index_offset;
-  a.quads = c->quads.as<unsigned long long>(); a.quads32 = r->quads_u32() ? c->quads.as<unsigned>() : nullptr;
-  a.status = c->scratch.as<unsigned long long>() + 1;
-  a.ticket = reinterpret_cast<unsigned*>(c->scratch.p); a.n_quads = d_cnt + C_NQUAD; a.n_invalid = d_cnt + C_NINVALID;
-  if (r->params.flags & S2M_MESH_KEEP_INVALID) {
-    if ((st = c->invalid.ensure(kInvalidCapacity * 48))) return st;
-    a.invalid_records = c->invalid.as<unsigned long long>(); a.invalid_cursor = d_cnt + C_INVALID_CURSOR; a.invalid_capacity = kInvalidCapacity;
-  }
-  SPAN_BEGIN(4, s);
-  int e = s2m_launch_k4b(&a, s);
-  if (e) return fail(S2M_ERR_CUDA, std::string("k4_quads launch: ") + cudaGetErrorString((cudaError_t)e));
-  SPAN_END(s);
-  r->t.launches += 1;
-  return S2M_OK;
-}
-
-int read_counters(s2m_ctx* c, cudaStream_t s) {
-  // not a cudaMemcpy: see k_publish in kernels_static.cu
-  int e = s2m_launch_publish(c->counters.as<unsigned long long>(), c->h_counters, C_COUNT, s);
-  if (e) return fail(S2M_ERR_CUDA, std::string("k_publish launch: ") + cudaGetErrorString((cudaError_t)e));
-  ++c->publish_launches;
-  CUDA_TRY(cudaStreamSynchronize(s));
   return S2M_OK;
 }
 
@@ -797,19 +859,24 @@ void finalize_timings(s2m_ctx* c, s2m_result* r) {
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]); r->t.total_ms = ms;
 }
 
-// The pipeline.  For every z-chunk: K1 slab -> K2 classify -> [count] -> K3 compact -> K4a vertices
-// -> [count] -> (K4b quads -> [count]) -> async copy of the chunk's vertices (and quads) into pinned
-// host memory on the copy stream, overlapping the next chunk's kernels.  [count] = the host reads
-// 8 bytes to size the next launch.
-int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fuse_quads, s2m_result** out) {
+// The pipeline.  For every z-chunk, on the PRODUCER stream: K1 (SDF once per corner -> f32 slab + 2-bit corner classes)
+// and K2 (classes -> candidate bit per cell; its last block writes the chunk's candidate count into mapped host memory);
+// on the CONSUMER stream: K3 (compaction + rank table), K4a (the reference's per-cell arithmetic on the candidates ->
+// vertices), K4b (quads, slab-relative indices; its last block writes the running totals into mapped host memory);
+// on the COPY stream: the chunk's vertices and quads into pinned host memory.  The host waits for exactly two events
+// per chunk -- "K2 done" (to size K4a's grid and the buffers) and "K4b done" (to size the copies) -- and both waits
+// happen while the producer stream already runs K1 of the next chunk.  Ranges that depend on counts the host has not
+// seen yet (vertices before / after this chunk, quads so far, halo vertices) are read by the kernels from device
+// memory (c->chunk_tot, the counters).
+int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_result** out) {
   if (!c || !m || !p || !out) return fail(S2M_ERR_INVALID_ARG, "s2m_mesh_begin: NULL argument");
   *out = nullptr;
   if (!m->k1 || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
   if (c->busy) return fail(S2M_ERR_STATE, "a previous s2m_mesh_begin on this ctx has not been finished or freed");
   CUDA_TRY(cudaSetDevice(c->device));
-  std::unique_ptr<s2m_result> rp(new s2m_result());
+  std::unique_ptr<s2m_result, void (*)(s2m_result*)> rp(new s2m_result(), [](s2m_result* x) { s2m_result_free(x); });
   s2m_result* r = rp.get();
-  r->ctx = c; r->mod = m; r->params = *p;
+  r->mod = m; r->params = *p;
   int st = make_grid(p, &r->grid);
   if (st) return st;
   const GridDev& g = r->grid;
@@ -825,7 +892,6 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
   r->z_first = zb - r->halo;
   r->nz = ze - r->z_first;
   r->words_x = (g.res[0] + 31u) / 32u;
-  if (r->halo) fuse_quads = false;  // a halo means there are lower slabs: the global vertex base comes later
   const float min_size = std::min(g.size[0], std::min(g.size[1], g.size[2]));
   // Candidate band.  The reference's corner coordinate (min + size) and the slab's (bmin + size*(i+1))
   // differ by at most 1 ulp of the coordinate; in voxels that is 2^-23 * max|coordinate| / size.  The
@@ -836,11 +902,17 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
     ulp_voxels = std::max(ulp_voxels, std::max(std::fabs(p->bb_min[a]), std::fabs(p->bb_max[a])) * 1.1920929e-7f / g.size[a]);
   const float tau_default = std::max(0.0625f, 256.0f * 1.7320508f * ulp_voxels);
   const float tau = (p->tau_voxels > 0.0f ? p->tau_voxels : tau_default) * min_size;
+  // Slab-free form: K1 writes only the corner classes, K4a evaluates all 8 corners of a candidate.  Chosen for SDFs
+  // that are cheap to evaluate (the f32 slab costs more to write than K4a saves by reading it back); S2M_MESH_NO_SLAB
+  // forces it, S2M_SLAB=0/1 in the environment overrides both (experiments).  K2 from the slab needs the slab.
+  bool no_slab = !dense && ((p->flags & S2M_MESH_NO_SLAB) || m->slab_free_default);
+  if (const char* e = getenv("S2M_SLAB")) no_slab = !dense && atoi(e) == 0;
+  const bool from_slab = (p->flags & S2M_MESH_CLASSIFY_FROM_SLAB) != 0;
+  if (from_slab) no_slab = false;
 
   Trace tr;
+  r->ctx = c;
   c->busy = true;
-  c->publish_launches = 0;
-  struct BusyGuard { s2m_ctx* c; bool keep = false; ~BusyGuard() { if (!keep) c->busy = false; } } guard{c};
   r->wall0 = now_ms();
   cudaStream_t s = c->stream;
   unsigned long long* d_cnt = c->counters.as<unsigned long long>();
@@ -858,40 +930,54 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
   const unsigned long long plane_bytes = g.plane_stride * 4ull;
   if (r->nz > 0) {
     unsigned long long budget = p->slab_budget_bytes ? p->slab_budget_bytes : (4ull << 30);
-    uint32_t zc = 0;
-    for (;;) {
-      const unsigned long long max_planes = std::max<unsigned long long>(2, budget / plane_bytes);
-      zc = (uint32_t)std::min<unsigned long long>(r->nz, max_planes - 1);
-      if (dense) break;
-      st = c->slab.ensure((unsigned long long)(zc + 1) * plane_bytes);
-      if (st == S2M_OK) break;
-      if (st != S2M_ERR_OOM || zc <= 1) return st;
-      budget = (unsigned long long)(zc + 1) * plane_bytes / 2;
+    uint32_t zc = r->nz;
+    if (!no_slab || p->slab_budget_bytes) {
+      for (;;) {
+        const unsigned long long max_planes = std::max<unsigned long long>(2, budget / plane_bytes);
+        zc = (uint32_t)std::min<unsigned long long>(r->nz, max_planes - 1);
+        if (dense || no_slab) break;
+        st = c->slab.ensure((unsigned long long)(zc + 1) * plane_bytes);
+        if (st == S2M_OK) break;
+        if (st != S2M_ERR_OOM || zc <= 1) return st;
+        budget = (unsigned long long)(zc + 1) * plane_bytes / 2;
+      }
     }
     uint32_t n_chunks = (r->nz + zc - 1) / zc;
     if (!dense && !getenv("S2M_NO_CHUNK_OVERLAP")) {
-      // a slab that fits the budget in one piece is still cut into 2-4 chunks when it is large enough
-      // (>= 0.15 G voxels per chunk) for the two-stream overlap and the early output copies to pay
+      // a slab that fits the budget in one piece is still cut into chunks when it is large enough
+      // (>= 0.15 G voxels per chunk) for the two-stream overlap and the early output copies to pay:
+      // up to 4 with a slab, up to 8 without one (nothing is resident per chunk but the class planes)
       const double voxels = (double)g.res[0] * g.res[1] * r->nz;
-      const uint32_t want = (uint32_t)std::min(4.0, voxels / 1.5e8);
+      const uint32_t want = (uint32_t)std::min(no_slab ? 8.0 : 4.0, voxels / 1.5e8);
       n_chunks = std::max(n_chunks, std::min(want, r->nz));
     }
     const uint32_t even = (r->nz + n_chunks - 1) / n_chunks;  // equal chunks instead of a short last one
     for (uint32_t z0 = 0; z0 < r->nz; z0 += even) chunks.push_back({z0, std::min(even, r->nz - z0)});
   }
-  r->t.chunks = (uint32_t)chunks.size();
+  const size_t n_chunks = chunks.size();
+  r->t.chunks = (uint32_t)n_chunks;
   // Two slab (and class-plane) buffers when there is more than one chunk: K1/K2 of chunk c+1 then run
   // on the producer stream while the consumer stream works through K3/K4a/K4b of chunk c.
-  bool pipelined = !dense && chunks.size() > 1 && !getenv("S2M_NO_CHUNK_OVERLAP");
-  if (pipelined) {
+  bool pipelined = !dense && n_chunks > 1 && !getenv("S2M_NO_CHUNK_OVERLAP");
+  if (pipelined && !no_slab) {
     const size_t max_planes = (size_t)chunks[0].nzc + 1;
     if (c->slab2.ensure(max_planes * plane_bytes) != S2M_OK) { cudaGetLastError(); pipelined = false; }  // not enough memory: one buffer, no overlap
   }
-  // pinned output sized from the previous run on this ctx (if any): lets chunk copies start early
-  const bool can_stream = c->hint_nv > 0;
-  if (can_stream) {
-    if ((st = ensure_pinned_outputs(c, r, c->hint_nv + c->hint_nv / 32 + 4096, c->hint_nq + c->hint_nq / 32 + 4096, fuse_quads))) return st;
-    r->streamed = true;
+  if ((st = c->ensure_slots(n_chunks + 1))) return st;
+  if ((st = c->chunk_tot.ensure((n_chunks + 2) * 16))) return st;
+  CUDA_TRY(cudaMemsetAsync(c->chunk_tot.p, 0, (n_chunks + 2) * 16, s));
+  unsigned long long* d_tot = c->chunk_tot.as<unsigned long long>();
+  // Host output regions: address ranges for the largest output this slab can have (one vertex per cell, three
+  // quads per vertex; capped -- vertex ranks are 32-bit), pages are locked as the chunks report their sizes.
+  {
+    const unsigned long long cells = (unsigned long long)g.res[0] * g.res[1] * std::max<uint32_t>(r->nz, 1u);
+    const unsigned long long vmax = std::min<unsigned long long>(cells, 0xffffffffull);
+    const unsigned long long qmax = std::min<unsigned long long>(3ull * vmax, 1ull << 33);
+    r->g_pos = c->lease_region(vmax * 12); r->g_nrm = c->lease_region(vmax * 12);
+    r->g_key = c->lease_region(vmax * 8); r->g_nib = c->lease_region(vmax);
+    r->g_quads = c->lease_region(qmax * r->quad_bytes());
+    if (!r->g_pos || !r->g_nrm || !r->g_key || !r->g_nib || !r->g_quads)
+      return fail(S2M_ERR_OOM, "mmap of the host output address ranges failed");
   }
   tr.mark("setup");
 
@@ -899,7 +985,6 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
   std::vector<uint32_t> dense_row;
   cudaStream_t ps = pipelined ? c->prod_stream : s;   // producer stream (K1, K2)
   if (pipelined) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_BEGIN], 0));  // after the counter reset
-  const bool from_slab = p->flags & S2M_MESH_CLASSIFY_FROM_SLAB;
   const unsigned cls_words = g.pitch_x / 32u;
   // K1 + K2 of chunk ci into slab buffer ci % 2 (buffer 0 when not pipelined)
   auto produce = [&](size_t ci) -> int {
@@ -909,7 +994,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
     DevBuf& cls_buf = buf ? c->cls2 : c->cls;
     int st2;
     GridDev gd = g;
-    float* slab = slab_buf.as<float>();
+    float* slab = no_slab ? nullptr : slab_buf.as<float>();
     unsigned first_plane = r->z_first + ch.z0, n_planes = ch.nzc + 1;
     unsigned cw = cls_words;
     void* cls = nullptr;
@@ -918,7 +1003,8 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       cls = cls_buf.p;
     }
     if (pipelined && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_CONSUMED0 + buf], 0));  // K4a of chunk ci-2 has read this buffer
-    CUDA_TRY(cudaMemsetAsync(d_cnt + C_CHUNK_CAND0 + buf, 0, 8, ps));
+    unsigned long long* cnt = d_cnt + (buf ? C_CHUNK_CAND1 : C_CHUNK_CAND0);
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, ps));   // the count and K2's block-completion counter
     float tau_arg = tau;
     void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw};
     unsigned bx, by;
@@ -932,35 +1018,35 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
     S2mK2Args a2{};
     a2.slab = slab; a2.pitch_x = g.pitch_x; a2.plane_stride = g.plane_stride;
     a2.res_x = g.res[0]; a2.res_y = g.res[1]; a2.nz_chunk = ch.nzc; a2.tau = tau;
-    a2.cand_mask = c->cand_mask.as<uint32_t>() + words_per_slice * ch.z0; a2.words_x = r->words_x; a2.total = d_cnt + C_CHUNK_CAND0 + buf;
+    a2.cand_mask = c->cand_mask.as<uint32_t>() + words_per_slice * ch.z0; a2.words_x = r->words_x; a2.total = cnt;
     a2.cls = cls; a2.cls_words = cls_words;
+    a2.done = reinterpret_cast<unsigned*>(cnt + 1); a2.host_total = c->h_counters + buf;
     {
       SPAN_BEGIN(1, ps);
       int e2 = from_slab ? s2m_launch_k2(&a2, ps) : s2m_launch_k2_bits(&a2, ps);
       if (e2) return fail(S2M_ERR_CUDA, std::string("k2_classify launch: ") + cudaGetErrorString((cudaError_t)e2));
       SPAN_END(ps);
     }
-    if (pipelined) CUDA_TRY(cudaEventRecord(c->ev[EV_PRODUCED0 + buf], ps));
+    CUDA_TRY(cudaEventRecord(c->ev[EV_PRODUCED0 + buf], ps));
     r->t.launches += 2;
     return S2M_OK;
   };
-  if (!dense && !chunks.empty() && (st = produce(0))) return st;
-  for (size_t ci = 0; ci < chunks.size(); ++ci) {
+  if (!dense && n_chunks && (st = produce(0))) return st;
+  for (size_t ci = 0; ci < n_chunks; ++ci) {
     const Chunk ch = chunks[ci];
     const int buf = pipelined ? (int)(ci & 1) : 0;
     const unsigned long long chunk_words = words_per_slice * ch.nzc;
     uint32_t* mask_chunk = c->cand_mask.as<uint32_t>() + words_per_slice * ch.z0;
     unsigned slab_first_plane = 0, slab_n_planes = 0;
-    uint64_t cand_total = cand_done;
+    uint64_t n_cand = 0;
     if (!dense) {
-      // the next chunk's K1/K2 are queued before this chunk's counts are waited for
-      if (pipelined && ci + 1 < chunks.size() && (st = produce(ci + 1))) return st;
+      // the next chunk's K1/K2 are queued before this chunk's count is waited for
+      if (pipelined && ci + 1 < n_chunks && (st = produce(ci + 1))) return st;
       if (pipelined) CUDA_TRY(cudaStreamWaitEvent(s, c->ev[EV_PRODUCED0 + buf], 0));
-      slab_first_plane = r->z_first + ch.z0; slab_n_planes = ch.nzc + 1;
-      // ---- [count] candidates of this chunk
-      if ((st = read_counters(c, s))) return st;
-      cand_total = cand_done + c->h_counters[C_CHUNK_CAND0 + buf];
-      if (!pipelined && ci + 1 < chunks.size()) { /* single buffer: the next K1 is issued after this chunk's K4a (below) */ }
+      if (!no_slab) { slab_first_plane = r->z_first + ch.z0; slab_n_planes = ch.nzc + 1; }
+      // ---- [count] candidates of this chunk: K2's last block wrote it into mapped host memory
+      CUDA_TRY(cudaEventSynchronize(c->ev[EV_PRODUCED0 + buf]));
+      n_cand = c->h_counters[buf];
     } else {
       // reference-cost mode: every cell of the chunk is a candidate
       if (dense_row.empty()) {
@@ -971,13 +1057,16 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       for (unsigned long long i = 0; i < chunk_words; i += r->words_x) memcpy(&host[i], dense_row.data(), r->words_x * 4);
       CUDA_TRY(cudaMemcpyAsync(mask_chunk, host.data(), chunk_words * 4, cudaMemcpyHostToDevice, s));
       CUDA_TRY(cudaStreamSynchronize(s));
-      cand_total = cand_done + (unsigned long long)g.res[0] * g.res[1] * ch.nzc;
+      n_cand = (unsigned long long)g.res[0] * g.res[1] * ch.nzc;
     }
-    const uint64_t n_cand = cand_total - cand_done;
+    const uint64_t cand_total = cand_done + n_cand;
     if (cand_total >= 0xffffffffull) return fail(S2M_ERR_UNSUPPORTED, "more than 2^32-1 candidate cells in one slab; split it with z_begin/z_end");
     const unsigned k3_tiles = s2m_k3_tiles(chunk_words);
-    const unsigned k4_tiles = (unsigned)((n_cand + 127) / 128);
-    const size_t status_words = (size_t)k3_tiles + k4_tiles + 16;
+    const unsigned k4_tiles = (unsigned)std::max<uint64_t>(1, (n_cand + 127) / 128);   // >= 1: an empty chunk still carries the totals forward
+    const unsigned k4b_tiles = s2m_k4b_tiles(n_cand);
+    const size_t status_words = (size_t)k3_tiles + k4_tiles + k4b_tiles + 16;
+    const size_t qb = r->quad_bytes();
+    // vertices <= candidates, quads <= 3 per vertex: exact upper bounds from counts the host already has
     if ((st = c->status.ensure(status_words * 8))) return st;
     if ((st = c->cand_key.ensure_preserve((cand_total + 1) * 8, cand_done * 8, s))) return st;
     if ((st = c->cand_vrank.ensure_preserve((cand_total + 1) * 4, cand_done * 4, s))) return st;
@@ -985,9 +1074,12 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
     if ((st = c->v_nrm.ensure_preserve((vert_done + n_cand + 1) * 12, vert_done * 12, s))) return st;
     if ((st = c->v_key.ensure_preserve((vert_done + n_cand + 1) * 8, vert_done * 8, s))) return st;
     if ((st = c->v_nib.ensure_preserve(vert_done + n_cand + 16, vert_done, s))) return st;
+    if ((st = c->quads.ensure_preserve((size_t)(quad_done + 3 * n_cand) * qb + 64, (size_t)quad_done * qb, s))) return st;
     CUDA_TRY(cudaMemsetAsync(c->status.p, 0, status_words * 8, s));
     unsigned long long* status = c->status.as<unsigned long long>();
-    unsigned* tickets = reinterpret_cast<unsigned*>(status);  // words 0..1: tickets; 2..: tile status
+    unsigned* tickets = reinterpret_cast<unsigned*>(status);  // words 0..1: K3 ticket, K4a ticket, K4b ticket, K4b completion counter; 2..: tile status
+    unsigned long long* tot_prev = d_tot + 2 * ci;
+    unsigned long long* tot_cur = d_tot + 2 * (ci + 1);
     // ---- K3
     {
       S2mK3Args a3{};
@@ -999,101 +1091,113 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, bool fu
       int e3 = s2m_launch_k3(&a3, s);
       if (e3) return fail(S2M_ERR_CUDA, std::string("k3_compact launch: ") + cudaGetErrorString((cudaError_t)e3));
       SPAN_END(s);
-      r->t.launches += 1;
     }
     // ---- K4a
-    if (k4_tiles) {
+    {
       GridDev gd = g;
       const unsigned long long* ck = c->cand_key.as<unsigned long long>() + cand_done;
-      unsigned long long nc = n_cand, vbase = vert_done;
+      unsigned long long nc = n_cand;
+      const unsigned long long* vbase = tot_prev;   // vertices emitted by earlier chunks, read on the device
       unsigned label_add = r->label_add, halo_below = r->halo ? (r->z_first + 1u) : 0u;
       unsigned want_normals = ((p->flags & S2M_MESH_NO_NORMALS) ? 0u : 1u) | ((p->flags & S2M_MESH_CONSISTENT_CORNERS) ? 2u : 0u);  // K4a's mode bits
-      SlabViewDev sv{(buf ? c->slab2 : c->slab).as<float>(), slab_first_plane, slab_n_planes};
+      SlabViewDev sv{no_slab || dense ? nullptr : (buf ? c->slab2 : c->slab).as<float>(), slab_first_plane, slab_n_planes};
       VertexOutDev vo{c->v_pos.as<float>(), c->v_nrm.as<float>(), c->v_key.as<unsigned long long>(), c->v_nib.as<unsigned char>(),
-                      c->cand_vrank.as<unsigned>() + cand_done, status + 2 + k3_tiles, tickets + 1, d_cnt + C_NVERT, d_cnt + C_NHALO};
+                      c->cand_vrank.as<unsigned>() + cand_done, status + 2 + k3_tiles, tickets + 1, tot_cur, d_cnt + C_NHALO};
       void* a4[] = {&gd, &ck, &nc, &vbase, &label_add, &halo_below, &want_normals, &sv, &vo};
       SPAN_BEGIN(3, s);
       // (capping K4a's blocks per SM with unused dynamic shared memory, to keep K1 blocks of the next chunk
       // resident beside them, was measured: K4a 4.3 -> 6.4 ms and the run got 2 ms slower)
       if ((st = launch(m->k4, dim3(k4_tiles), dim3(128), s, a4, "s2m_k4_vertices"))) return st;
       SPAN_END(s);
-      r->t.launches += 1;
     }
     if (pipelined) CUDA_TRY(cudaEventRecord(c->ev[EV_CONSUMED0 + buf], s));  // slab buffer `buf` may be overwritten
-    else if (!dense && ci + 1 < chunks.size() && (st = produce(ci + 1))) return st;
-    // ---- [count] vertices so far
-    uint64_t vert_total = vert_done;
-    if (k4_tiles) {
-      if ((st = read_counters(c, s))) return st;
-      vert_total = c->h_counters[C_NVERT];
-      r->n_halo = c->h_counters[C_NHALO];
-    }
-    // ---- K4b (single-slab runs only: the global vertex base is 0)
-    uint64_t quad_total = quad_done;
-    if (fuse_quads && vert_total > vert_done) {
-      if ((st = launch_k4b(c, r, s, vert_done, vert_total, quad_done, 0))) return st;
-      if ((st = read_counters(c, s))) return st;
-      quad_total = c->h_counters[C_NQUAD];
-    }
-    // ---- copy this chunk's output while the next chunk computes
-    if (r->streamed) {
-      const uint64_t own = vert_total - std::min<uint64_t>(vert_total, r->n_halo);
-      if (own > r->cap_v || (fuse_quads && quad_total > r->cap_q)) {
-        r->streamed = false;  // the hint was too small: everything is copied at the end instead
-      } else if (!fuse_quads && ci + 1 == chunks.size()) {
-        r->deferred_copy = true;  // see s2m_result::deferred_copy
-        r->deferred_v0 = vert_done;
-      } else {
-        const size_t e = take_event(c, r);
-        CUDA_TRY(cudaEventRecord(c->ev_pool[e], s));
-        CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_pool[e], 0));
-        SPAN_BEGIN(5, c->copy_stream);
-        if ((st = copy_out(c, r, c->copy_stream, vert_done, vert_total, quad_done, fuse_quads ? quad_total : quad_done))) return st;
-        SPAN_END(c->copy_stream);
+    // ---- K4b: this chunk's quads, slab-relative indices (local - n_halo); its last block publishes the totals
+    {
+      S2mK4bArgs a{};
+      a.vert_key = c->v_key.as<unsigned long long>(); a.vert_nibble = c->v_nib.as<unsigned char>();
+      a.max_vertices = n_cand; a.tot_prev = tot_prev; a.tot_cur = tot_cur; a.n_halo = d_cnt + C_NHALO;
+      a.cand_mask = c->cand_mask.as<uint32_t>(); a.word_prefix = c->word_prefix.as<uint32_t>(); a.cand_vrank = c->cand_vrank.as<uint32_t>();
+      a.words_x = r->words_x; a.res_y = g.res[1]; a.z_first = r->z_first; a.label_add = r->label_add;
+      a.index_add = 0;
+      a.quads = c->quads.as<unsigned long long>(); a.quads32 = r->quads_u32() ? c->quads.as<unsigned>() : nullptr;
+      a.status = status + 2 + k3_tiles + k4_tiles; a.ticket = tickets + 2; a.n_invalid = d_cnt + C_NINVALID;
+      a.done = tickets + 3; a.host_slot = c->h_slots + 8 * ci;
+      if (p->flags & S2M_MESH_KEEP_INVALID) {
+        if ((st = c->invalid.ensure(kInvalidCapacity * 48))) return st;
+        a.invalid_records = c->invalid.as<unsigned long long>(); a.invalid_cursor = d_cnt + C_INVALID_CURSOR; a.invalid_capacity = kInvalidCapacity;
       }
+      SPAN_BEGIN(4, s);
+      int e = s2m_launch_k4b(&a, s);
+      if (e) return fail(S2M_ERR_CUDA, std::string("k4_quads launch: ") + cudaGetErrorString((cudaError_t)e));
+      SPAN_END(s);
+    }
+    r->t.launches += 3;
+    const size_t ev_done = take_event(c, r);
+    CUDA_TRY(cudaEventRecord(c->ev_pool[ev_done], s));
+    if (ci + 1 == n_chunks) CUDA_TRY(cudaEventRecord(c->ev[1], s));  // device_ms: every kernel has finished
+    if (!pipelined && !dense && ci + 1 < n_chunks && (st = produce(ci + 1))) return st;
+    // ---- [count] what this chunk added; then its copies, while the next chunk computes
+    CUDA_TRY(cudaEventSynchronize(c->ev_pool[ev_done]));
+    const unsigned long long* slot = c->h_slots + 8 * ci;
+    const uint64_t vert_total = slot[0], quad_total = slot[1];
+    r->n_halo = slot[2]; r->n_invalid = slot[3]; r->n_invalid_records = std::min<uint64_t>(slot[4], kInvalidCapacity);
+    CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_pool[ev_done], 0));
+    if (vert_total > std::max<uint64_t>(r->copied_v, r->n_halo) || quad_total > r->copied_q) {
+      SPAN_BEGIN(5, c->copy_stream);
+      if ((st = copy_out(c, r, c->copy_stream, vert_total, quad_total))) return st;
+      SPAN_END(c->copy_stream);
     }
     cand_done = cand_total; vert_done = vert_total; quad_done = quad_total;
     tr.mark("chunk done");
   }
+  if (n_chunks == 0) CUDA_TRY(cudaEventRecord(c->ev[1], s));
   r->n_cand = cand_done;
   r->n_vert_total = vert_done;
+  r->n_quads = quad_done;
   const uint64_t n_own = r->n_vert_total - r->n_halo;
-  if (fuse_quads) {
-    r->quads_done = true;
-    r->n_quads = quad_done;
-    if ((st = read_counters(c, s))) return st;
-    r->n_invalid = c->h_counters[C_NINVALID];
-  }
-  CUDA_TRY(cudaEventRecord(c->ev[1], s));  // device_ms: every kernel of begin() has finished
-  // ---- whatever has not been streamed is copied now
-  if (!r->streamed) {
-    if ((st = ensure_pinned_outputs(c, r, n_own, fuse_quads ? r->n_quads : 0, fuse_quads))) return st;
-    SPAN_BEGIN(5, s);
-    if ((st = copy_out(c, r, s, 0, r->n_vert_total, 0, fuse_quads ? r->n_quads : 0))) return st;
-    SPAN_END(s);
-  }
-  if (p->flags & S2M_MESH_NO_NORMALS) memset(r->h_nrm, 0, n_own * 12);
+  if (p->flags & S2M_MESH_NO_NORMALS) memset(r->g_nrm->base, 0, n_own * 12);   // the result hands out zeros (plain pages: nothing is copied into them)
   if (p->flags & S2M_MESH_KEEP_CANDIDATES) {
     r->h_cand = (uint64_t*)c->lease_pinned(r->n_cand * 8);
     if (!r->h_cand) return fail(S2M_ERR_OOM, "cudaHostAlloc for candidate list failed");
-    if (r->n_cand) CUDA_TRY(cudaMemcpyAsync(r->h_cand, c->cand_key.p, r->n_cand * 8, cudaMemcpyDeviceToHost, s));
+    if (r->n_cand) CUDA_TRY(cudaMemcpyAsync(r->h_cand, c->cand_key.p, r->n_cand * 8, cudaMemcpyDeviceToHost, c->copy_stream));
   }
   if (r->n_halo) {  // the halo slice's positions, so that this slab's triangles can be written without the slab below
     r->h_halo_pos = (float*)c->lease_pinned(r->n_halo * 12);
     if (!r->h_halo_pos) return fail(S2M_ERR_OOM, "cudaHostAlloc for halo positions failed");
-    CUDA_TRY(cudaMemcpyAsync(r->h_halo_pos, c->v_pos.p, r->n_halo * 12, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(r->h_halo_pos, c->v_pos.p, r->n_halo * 12, cudaMemcpyDeviceToHost, c->copy_stream));
   }
-  c->hint_nv = n_own;
+  if ((p->flags & S2M_MESH_KEEP_INVALID) && r->n_invalid_records) {
+    r->h_invalid = (uint64_t*)c->lease_pinned(r->n_invalid_records * 48 + 48);
+    if (!r->h_invalid) return fail(S2M_ERR_OOM, "cudaHostAlloc for the invalid-quad list failed");
+    CUDA_TRY(cudaMemcpyAsync(r->h_invalid, c->invalid.p, r->n_invalid_records * 48, cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[2], c->copy_stream));   // total_ms: everything resident in pinned host memory
   tr.mark("begin done");
-  guard.keep = true;
   *out = rp.release();
   return S2M_OK;
+}
+
+// index += base over n indices, on a few host threads (the non-relative contract of s2m_mesh_finish)
+template <class T>
+void add_base(T* q, uint64_t n, T base) {
+  const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+  const unsigned nt = n < (1u << 18) ? 1u : hw;
+  auto work = [=](unsigned k) {
+    const uint64_t a = n * k / nt, b = n * (k + 1) / nt;
+    for (uint64_t i = a; i < b; ++i) q[i] = (T)(q[i] + base);
+  };
+  std::vector<std::thread> th;
+  for (unsigned k = 1; k < nt; ++k) {
+    try { th.emplace_back(work, k); } catch (const std::system_error&) { work(k); }
+  }
+  work(0);
+  for (auto& t : th) t.join();
 }
 
 }  // namespace
 
 extern "C" int s2m_mesh_begin(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_result** out) {
-  return mesh_begin_impl(c, m, p, false, out);
+  return mesh_begin_impl(c, m, p, out);
 }
 
 extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
@@ -1102,59 +1206,30 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   s2m_ctx* c = r->ctx;
   Trace tr;
   CUDA_TRY(cudaSetDevice(c->device));
-  cudaStream_t s = c->stream;
-  int st;
   r->global_base = global_vertex_base;
   if (r->quads_u32() && (global_vertex_base < 0 || (uint64_t)global_vertex_base + (r->n_vert_total - r->n_halo) > 0xffffffffull))
     return fail(S2M_ERR_UNSUPPORTED, "S2M_MESH_QUADS_U32: vertex indices of this slab do not fit 32 bits");
-  if (r->deferred_copy && r->streamed) {
-    SPAN_BEGIN(5, c->copy_stream);
-    if ((st = copy_out(c, r, c->copy_stream, r->deferred_v0, r->n_vert_total, 0, 0))) return st;
-    SPAN_END(c->copy_stream);
-    r->deferred_copy = false;
-  }
-  if (!r->quads_done) {
-    // ---- K4b over all own vertices with the global base, then the quad copy
-    if ((st = launch_k4b(c, r, s, 0, r->n_vert_total, 0, (long long)global_vertex_base - (long long)r->n_halo))) return st;
-    CUDA_TRY(cudaEventRecord(c->ev[1], s));
-    if ((st = read_counters(c, s))) return st;
-    r->n_quads = c->h_counters[C_NQUAD];
-    r->n_invalid = c->h_counters[C_NINVALID];
-    if ((st = ensure_pinned_outputs(c, r, r->cap_v, r->n_quads, true))) return st;
-    SPAN_BEGIN(5, s);
-    if ((st = copy_out(c, r, s, 0, 0, 0, r->n_quads))) return st;
-    SPAN_END(s);
-    r->quads_done = true;
-  } else if (global_vertex_base != 0) {
-    return fail(S2M_ERR_STATE, "quads were already emitted with base 0 (s2m_mesh_run); use s2m_mesh_begin for multi-slab runs");
-  }
-  c->hint_nq = r->n_quads;
-  if (r->params.flags & S2M_MESH_KEEP_INVALID) {
-    if ((st = read_counters(c, s))) return st;
-    r->n_invalid_records = std::min<uint64_t>(c->h_counters[C_INVALID_CURSOR], kInvalidCapacity);
-    r->h_invalid = (uint64_t*)c->lease_pinned(r->n_invalid_records * 48 + 48);
-    if (!r->h_invalid) return fail(S2M_ERR_OOM, "cudaHostAlloc for the invalid-quad list failed");
-    if (r->n_invalid_records) {
-      CUDA_TRY(cudaMemcpyAsync(r->h_invalid, c->invalid.p, r->n_invalid_records * 48, cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(cudaStreamSynchronize(s));
-      // the device appends in completion order; the reference reports them in (vertex, edge) order
-      struct Rec { uint64_t v[6]; };
-      Rec* recs = reinterpret_cast<Rec*>(r->h_invalid);
-      std::sort(recs, recs + r->n_invalid_records, [](const Rec& x, const Rec& y) { return x.v[0] != y.v[0] ? x.v[0] < y.v[0] : x.v[1] < y.v[1]; });
-    }
-  }
-  {  // everything (both streams) done -> total span
-    const size_t e = take_event(c, r);
-    CUDA_TRY(cudaEventRecord(c->ev_pool[e], c->copy_stream));
-    CUDA_TRY(cudaStreamWaitEvent(s, c->ev_pool[e], 0));
-  }
-  CUDA_TRY(cudaEventRecord(c->ev[2], s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  // everything was computed and queued for copying by begin(); what is left is to wait for the copies
   CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
   tr.mark("finish: copies done");
+  if (r->h_invalid && r->n_invalid_records) {
+    // the device appends in completion order; the reference reports them in (vertex, edge) order
+    struct Rec { uint64_t v[6]; };
+    Rec* recs = reinterpret_cast<Rec*>(r->h_invalid);
+    std::sort(recs, recs + r->n_invalid_records, [](const Rec& x, const Rec& y) { return x.v[0] != y.v[0] ? x.v[0] < y.v[0] : x.v[1] < y.v[1]; });
+  }
+  if (!r->relative() && global_vertex_base != 0) {
+    // the default contract: quads (and invalid records) carry GLOBAL indices.  The device wrote slab-relative ones
+    // (local - n_halo) so that nothing had to wait for the base; S2M_MESH_RELATIVE_QUADS keeps them that way.
+    if (r->quads_u32()) add_base<uint32_t>(r->host<uint32_t>(r->g_quads), 4 * r->n_quads, (uint32_t)global_vertex_base);
+    else add_base<uint64_t>(r->host<uint64_t>(r->g_quads), 4 * r->n_quads, (uint64_t)global_vertex_base);
+    for (uint64_t i = 0; i < r->n_invalid_records && r->h_invalid; ++i)
+      for (int t = 2; t < 6; ++t)
+        if (r->h_invalid[6 * i + t] != ~0ull) r->h_invalid[6 * i + t] += (uint64_t)global_vertex_base;
+    tr.mark("finish: base added");
+  }
   r->t.host_wall_ms = now_ms() - r->wall0;
-  r->t.launches += c->publish_launches;
-  c->publish_launches = 0;
   finalize_timings(c, r);
   r->finished = true;
   c->busy = false;
@@ -1162,7 +1237,7 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
 }
 
 extern "C" int s2m_mesh_run(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_result** out) {
-  int st = mesh_begin_impl(c, m, p, true, out);
+  int st = mesh_begin_impl(c, m, p, out);
   if (st) return st;
   st = s2m_mesh_finish(*out, 0);
   if (st) { s2m_result_free(*out); *out = nullptr; }
@@ -1177,8 +1252,10 @@ extern "C" int s2m_result_get(const s2m_result* r, s2m_result_info* o) {
   o->n_quads = r->n_quads;
   o->n_invalid_quads = r->n_invalid;
   o->n_candidates = r->n_cand;
-  o->positions = r->h_pos; o->normals = r->h_nrm; o->cell_keys = r->h_key; o->sign_nibbles = r->h_nib;
-  o->quads = r->quads_u32() ? nullptr : r->h_quads; o->quads32 = r->quads_u32() ? reinterpret_cast<const uint32_t*>(r->h_quads) : nullptr;
+  o->positions = r->host<float>(r->g_pos); o->normals = r->host<float>(r->g_nrm);
+  o->cell_keys = r->host<uint64_t>(r->g_key); o->sign_nibbles = r->host<uint8_t>(r->g_nib);
+  o->quads = r->quads_u32() ? nullptr : r->host<uint64_t>(r->g_quads); o->quads32 = r->quads_u32() ? r->host<uint32_t>(r->g_quads) : nullptr;
+  o->quad_index_add = r->relative() ? r->global_base : 0;
   o->candidates = r->h_cand;
   o->invalid_records = r->h_invalid; o->n_invalid_records = r->n_invalid_records;
   o->halo_positions = r->h_halo_pos; o->global_vertex_base = r->global_base;
@@ -1210,6 +1287,34 @@ extern "C" int s2m_eval_points(s2m_ctx* c, s2m_module* m, const float* xyz, uint
 }
 
 extern "C" int s2m_module_is_packed(const s2m_module* m) { return m && m->k1_packed ? 1 : 0; }
+extern "C" int s2m_module_prefers_no_slab(const s2m_module* m) { return m && m->slab_free_default ? 1 : 0; }
+
+extern "C" int s2m_measure_fp32_peak(s2m_ctx* c, double out_tflops[3]) {
+  if (!c || !out_tflops) return fail(S2M_ERR_INVALID_ARG, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  DevBuf sink;
+  int st = sink.ensure(64);
+  if (st) return st;
+  cudaStream_t s = c->stream;
+  const int blocks = c->prop.multiProcessorCount * 8, iters = 1 << 15;   // 8 x 256 threads per SM, 2^18 FMAs per thread: ~2 ms
+  const double flops = 2.0 * 8.0 * iters * 256.0 * blocks;
+  for (int mode = 0; mode < 3; ++mode) {
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {   // rep 0 warms up
+      CUDA_TRY(cudaEventRecord(c->ev[8], s));
+      int e = s2m_launch_fp32_probe(mode, blocks, iters, sink.as<float>(), s);
+      if (e) { sink.release(); return fail(S2M_ERR_CUDA, std::string("fp32 probe launch: ") + cudaGetErrorString((cudaError_t)e)); }
+      CUDA_TRY(cudaEventRecord(c->ev[9], s));
+      CUDA_TRY(cudaEventSynchronize(c->ev[9]));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev[8], c->ev[9]);
+      if (rep && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    out_tflops[mode] = best;
+  }
+  sink.release();
+  return S2M_OK;
+}
 
 extern "C" int s2m_eval_pairs(s2m_ctx* c, s2m_module* m, const float* xyz_a, const float* xyz_b, uint64_t n, float* out_a, float* out_b,
                               uint8_t* disagreed) {

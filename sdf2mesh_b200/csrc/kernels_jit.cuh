@@ -140,10 +140,14 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
 #endif
   }
 #endif
-  if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(va[0], va[1], va[2], va[3]);
+  /* slab == nullptr: the slab-free form for cheap SDFs (S2M_MESH_NO_SLAB) -- only the corner classes below are
+   * written (0.25 B per corner instead of 4.25) and K4a evaluates all 8 corners of every candidate cell itself. */
+  if (slab != nullptr) {
+    if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(va[0], va[1], va[2], va[3]);
 #if S2M_K1_ROWS == 2
-  if (active_b) *reinterpret_cast<float4*>(slab + (row + 1ull) * g.pitch_x + x4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    if (active_b) *reinterpret_cast<float4*>(slab + (row + 1ull) * g.pitch_x + x4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
 #endif
+  }
   /* Corner classes for K2: P = value > +tau, N = value < -tau (NaN and the |v| <= tau band are
    * neither).  One byte per thread and row: low nibble = P of its 4 corners, high nibble = N.
    * 8 lanes (32 corners of a row) make one 64-bit word, cls[plane][row][x/32] = (lanes 0-3,
@@ -184,7 +188,7 @@ struct S2mVertexOut {
   unsigned* cand_vrank;       /* per candidate: vertex index or 0xffffffff */
   unsigned long long* status; /* look-back tile status, zeroed by the host */
   unsigned* ticket;           /* tile ticket counter, zeroed by the host */
-  unsigned long long* n_vertices;  /* out: total */
+  unsigned long long* n_vertices;  /* out: vertices emitted up to the end of this launch (vert_base + this launch's) */
   unsigned long long* n_halo;      /* out: vertices whose true z < halo_below */
 };
 
@@ -229,11 +233,14 @@ __device__ __forceinline__ unsigned s2m_item_owner(const unsigned* inc, unsigned
  * evaluations plus the 4 normal taps of cells that get a vertex are spread over all 32 lanes.
  *
  * cand_key = x | y<<16 | z_true<<32 (this launch's slice of the list; cand_vrank likewise).
- * vert_base = vertices emitted by earlier chunks.  label_add = 1 in faithful mode.
+ * *vert_base_ptr = vertices emitted by earlier chunks.  label_add = 1 in faithful mode.
  * mode: bit 0 = compute normals, bit 1 = consistent corners. */
 extern "C" __global__ void __launch_bounds__(S2M_K4_THREADS)
 s2m_k4_vertices(S2mGrid g, const unsigned long long* __restrict__ cand_key, unsigned long long n_cand,
-                unsigned long long vert_base, unsigned label_add, unsigned halo_below, unsigned mode, S2mSlabView sv, S2mVertexOut out) {
+                const unsigned long long* __restrict__ vert_base_ptr, unsigned label_add, unsigned halo_below, unsigned mode, S2mSlabView sv, S2mVertexOut out) {
+  /* vertices emitted by earlier z-chunks: read from device memory (the previous launch's out.n_vertices), so that
+   * the host does not have to learn it between two chunks */
+  const unsigned long long vert_base = *vert_base_ptr;
   const unsigned want_normals = mode & 1u;
   const bool consistent = (mode & 2u) != 0u;  /* S2M_MESH_CONSISTENT_CORNERS: a cell's max corner IS the next cell's min corner */
   __shared__ unsigned s_scan[33];

@@ -20,6 +20,8 @@ typedef struct S2mK2Args {
   unsigned long long* total;      /* candidate counter (accumulates) */
   const void* cls;                /* s2m_launch_k2_bits: corner-class planes written by K1 (uint2 per 32 corners) */
   uint32_t cls_words;             /* class words per row */
+  unsigned* done;                 /* optional: zeroed block-completion counter; the last block to finish ... */
+  unsigned long long* host_total; /* ... writes *total here (mapped pinned host memory) */
 } S2mK2Args;
 
 typedef struct S2mK3Args {
@@ -37,25 +39,33 @@ typedef struct S2mK3Args {
 typedef struct S2mK4bArgs {
   const unsigned long long* vert_key;
   const unsigned char* vert_nibble;
-  unsigned long long v_begin, v_end; /* vertices to emit quads for (local indices, halo excluded by the caller) */
-  unsigned long long quad_base;      /* quads emitted by earlier launches */
+  unsigned long long max_vertices;   /* upper bound of the vertices of this launch (sizes the grid; the exact range is read on the device) */
+  const unsigned long long* tot_prev; /* device: {vertices, quads} emitted up to the end of the previous z-chunk */
+  unsigned long long* tot_cur;        /* device: {vertices (written by K4a), quads (written here)} up to the end of this z-chunk */
+  const unsigned long long* n_halo;   /* device: vertices of the recomputed slice below the slab (first in the list, no quads of their own) */
   const uint32_t* cand_mask;
   const uint32_t* word_prefix;
   const uint32_t* cand_vrank;
   uint32_t words_x, res_y, z_first, label_add;
-  long long index_offset;
+  long long index_add;            /* emitted index = local vertex index - n_halo + index_add */
   unsigned long long* quads;
   unsigned* quads32;              /* non-NULL: write 4 x u32 per quad here instead of quads */
-  unsigned long long* status;     /* >= s2m_k4b_tiles(v_end - v_begin) zeroed words */
+  unsigned long long* status;     /* >= s2m_k4b_tiles(max_vertices) zeroed words */
   unsigned* ticket;               /* zeroed */
-  unsigned long long* n_quads;    /* out: quad_base + quads of this launch */
   unsigned long long* n_invalid;  /* accumulates */
   unsigned long long* invalid_records; /* optional: 6 u64 per invalid quad (key, edge, q0..q3), unordered */
   unsigned long long* invalid_cursor;  /* optional: record counter (accumulates) */
   unsigned long long invalid_capacity;
+  unsigned* done;                 /* optional: zeroed block-completion counter; the last block to finish ... */
+  unsigned long long* host_slot;  /* ... writes {vertices, quads, n_halo, n_invalid, invalid cursor} here (mapped pinned host memory) */
 } S2mK4bArgs;
 
 int s2m_launch_publish(const unsigned long long* src, unsigned long long* dst_host, unsigned n, cudaStream_t stream); /* n <= 32 */
+/* dst_host = src_a[0..na) ++ src_b[0..nb), na + nb <= 32 */
+int s2m_launch_publish2(const unsigned long long* src_a, unsigned na, const unsigned long long* src_b, unsigned nb, unsigned long long* dst_host,
+                        cudaStream_t stream);
+/* FP32 throughput probe: 8 FMAs per thread and iteration, 256 threads per block; mode 0 FFMA r,r,r / 1 FFMA r,imm,imm / 2 FFMA2 */
+int s2m_launch_fp32_probe(int mode, int blocks, int iters, float* sink, cudaStream_t stream);
 int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream);      /* classify from the f32 slab */
 int s2m_launch_k2_bits(const S2mK2Args* a, cudaStream_t stream); /* classify from K1's class bit planes */
 unsigned s2m_k3_tiles(unsigned long long n_words);

@@ -80,7 +80,10 @@ struct Part {
   s2m_result_info i;
   int64_t base;   // global index of this part's first own vertex
 };
-inline uint64_t quad_index(const s2m_result_info& m, uint64_t i) { return m.quads ? m.quads[i] : (uint64_t)m.quads32[i]; }
+// global vertex index of quad entry i: value + quad_index_add, wrapping in the index width (S2M_MESH_RELATIVE_QUADS)
+inline uint64_t quad_index(const s2m_result_info& m, uint64_t i) {
+  return m.quads ? m.quads[i] + (uint64_t)m.quad_index_add : (uint64_t)(uint32_t)(m.quads32[i] + (uint32_t)m.quad_index_add);
+}
 
 struct Parts {
   std::vector<Part> parts;

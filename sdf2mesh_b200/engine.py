@@ -34,6 +34,12 @@ class Context:
         check(lib().s2m_ctx_device_info(self._h, name, 256, ctypes.byref(sms), ctypes.byref(mem)))
         return name.value.decode(), sms.value, mem.value
 
+    def measure_fp32_peak(self):
+        """FP32 FMA throughput in TFLOP/s: (FFMA reg,reg,reg; FFMA reg,imm,imm; FFMA2 pair,bcast,imm)"""
+        out = (ctypes.c_double * 3)()
+        check(lib().s2m_measure_fp32_peak(self._h, out))
+        return tuple(float(v) for v in out)
+
     def read_device_words(self, device_ptr: int, n: int, cuda_stream: int = 0):
         """n (<= 32) u64 words from device memory, through a kernel + mapped pinned memory on
         `cuda_stream` (a cudaStream_t handle; 0 = the context's stream) instead of a cudaMemcpy"""
@@ -99,6 +105,11 @@ class Module:
         """K1 of this module evaluates corner pairs in packed f32x2 arithmetic (csrc/s2m_pvec.h)"""
         return bool(lib().s2m_module_is_packed(self._h))
 
+    @property
+    def prefers_no_slab(self) -> bool:
+        """meshing with this module defaults to the slab-free form (MESH_NO_SLAB): its SDF is cheap to evaluate"""
+        return bool(lib().s2m_module_prefers_no_slab(self._h))
+
     def eval_pairs(self, pts_a, pts_b):
         """the packed form, raw: -> (values of pts_a, values of pts_b, lanes-disagreed flags)"""
         a = np.ascontiguousarray(pts_a, np.float32).reshape(-1, 3)
@@ -163,6 +174,14 @@ class MeshData:
     n_halo_vertices: int
     n_candidates: int
     timings: dict
+    quad_index_add: int = 0      # MESH_RELATIVE_QUADS: global index = quad value + quad_index_add (wrapping in the index width)
+
+    def global_quads(self) -> np.ndarray:
+        """quads as global 64-bit vertex indices, whichever form the result holds (a copy)"""
+        q = self.quads
+        if q.dtype == np.uint32:
+            return (q + np.uint32(self.quad_index_add & 0xFFFFFFFF)).astype(np.uint64)
+        return q + np.uint64(self.quad_index_add & 0xFFFFFFFFFFFFFFFF)
 
 
 class MeshResult:
@@ -189,7 +208,7 @@ class MeshResult:
             _view(i.quads32, nq * 4, np.uint32, (-1, 4)) if i.quads32 else _view(i.quads, nq * 4, np.uint64, (-1, 4)),
             _view(i.candidates, i.n_candidates if i.candidates else 0, np.uint64),
             _view(i.invalid_records, i.n_invalid_records * 6 if i.invalid_records else 0, np.uint64, (-1, 6)),
-            i.n_invalid_quads, i.n_halo_vertices, i.n_candidates, t)
+            i.n_invalid_quads, i.n_halo_vertices, i.n_candidates, t, int(i.quad_index_add))
 
     def write_mesh(self, path):
         """TriangleMesh::write_to_file (mesh.rs:182): .stl / .ply by extension."""

@@ -4,6 +4,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the suite always goes through NVRTC: no cubins from (or into) the user's ~/.cache/sdf2mesh_b200 (tests of the cache set their own directory)
+os.environ.setdefault("S2M_CACHE_DIR", "")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

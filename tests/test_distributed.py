@@ -152,3 +152,38 @@ def test_rebalance_from_measured_times():
     assert with_profile[1] > b0[1] and uniform[1] > b0[1]
     assert with_profile[4] - with_profile[3] < b0[4] - b0[3]
     assert all(x < y for x, y in zip(with_profile, with_profile[1:]))
+
+
+def test_c_abi_partition_matches_the_python_one(built):
+    """s2m_partition_slices / s2m_rebalance_slices (csrc/multi.cpp, used by s2m_multi_mesh_run and the CLI's --gpus N)
+    follow distributed.partition_slices / rebalance: same boundaries up to a tie in the rounding, always strictly
+    increasing, always covering [0, n]"""
+    from sdf2mesh_b200 import multi as M
+    rng = np.random.default_rng(0)
+    for t in range(200):
+        n, w = int(rng.integers(8, 3000)), int(rng.integers(1, 9))
+        cost = None if t % 5 == 0 else rng.uniform(0, 1, int(rng.integers(1, 200))) ** 3
+        a, b = D.partition_slices(n, w, cost), M.partition_slices(n, w, cost)
+        assert b[0] == 0 and b[-1] == n and all(y > x for x, y in zip(b, b[1:])), b
+        assert max(abs(x - y) for x, y in zip(a, b)) <= 1, (n, w, a, b)
+        if w >= 2:
+            sec = rng.uniform(0.5, 2, w)
+            a2, b2 = D.rebalance(a, sec, cost), M.rebalance_slices(a, sec, cost)
+            assert b2[0] == 0 and b2[-1] == n and all(y > x for x, y in zip(b2, b2[1:])), b2
+            assert max(abs(x - y) for x, y in zip(a2, b2)) <= 1, (n, w, a, a2, b2)
+    with pytest.raises(Exception):
+        M.partition_slices(3, 8)
+    # a slab that took twice as long gets thinner
+    b = M.rebalance_slices([0, 100, 200], [2.0, 1.0])
+    assert b[1] < 100
+
+
+def test_multi_context_needs_a_device(built):
+    """no CPU fallback behind s2m_multi_create either"""
+    import sdf2mesh_b200 as s2m
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(s2m.S2mError) as e:
+        s2m.MultiContext([0, 1])
+    assert e.value.kind == "NO_DEVICE"
