@@ -259,7 +259,8 @@ int s2m_read_device_words(s2m_ctx* ctx, const void* device_words, uint32_t n, ui
  * quad_index_add); free each with s2m_result_free, write them with s2m_write_mesh_parts.  One host thread drives one
  * s2m_multi at a time. */
 typedef struct s2m_multi s2m_multi;
-#define S2M_MULTI_NO_NCCL 1u       /* exchange the counts through host memory (a barrier between the host threads) */
+#define S2M_MULTI_NO_NCCL 1u       /* exchange the counts through host memory (a barrier between the host threads); only then may a
+                                      device ordinal appear more than once (several slabs sharing one GPU: one-GPU test boxes) */
 #define S2M_MULTI_EQUAL_SLABS 2u   /* equal-thickness slabs: no cost probe, no refinement */
 #define S2M_MULTI_NO_REBALANCE 4u  /* keep the cost-probe partition: no refinement from measured times */
 typedef struct s2m_multi_timings {

@@ -150,6 +150,7 @@ struct PinnedRegion {
   char* base = nullptr;
   size_t reserved = 0, registered = 0;
   bool used = false;
+  int role = 0;   // which output array it serves (s2m_ctx::lease_region)
   std::vector<std::pair<size_t, size_t>> segs;  // registered (offset, length) pieces, for cudaHostUnregister
   int ensure(size_t bytes, size_t ahead) {
     if (bytes <= registered) return S2M_OK;
@@ -165,6 +166,17 @@ struct PinnedRegion {
     if (e != cudaSuccess) { cudaGetLastError(); return fail(S2M_ERR_OOM, std::string("cudaHostRegister(") + std::to_string(upto - registered) + " B): " + cudaGetErrorString(e)); }
     segs.emplace_back(registered, upto - registered);
     registered = upto;
+    return S2M_OK;
+  }
+  // device -> this array at byte offset `off`.  One cudaMemcpyAsync may not straddle two cudaHostRegister ranges
+  // ("invalid argument"): the copy is cut at the boundaries of the registered pieces.
+  int copy_from_device(size_t off, const void* src, size_t bytes, cudaStream_t st) {
+    if (off + bytes > registered) return fail(S2M_ERR_STATE, "copy past the page-locked part of an output array");
+    for (const auto& sg : segs) {
+      const size_t a = std::max(off, sg.first), b = std::min(off + bytes, sg.first + sg.second);
+      if (a >= b) continue;
+      CUDA_TRY(cudaMemcpyAsync(base + a, static_cast<const char*>(src) + (a - off), b - a, cudaMemcpyDeviceToHost, st));
+    }
     return S2M_OK;
   }
   void destroy() {
@@ -211,11 +223,14 @@ struct s2m_ctx {
   std::vector<cudaEvent_t> ev_pool;   // per-launch timing events, grown on demand
   bool busy = false;  // a begin() without finish()/free() is outstanding
 
-  // a region whose address range can hold `reserve` bytes; prefers the one with the most pages already locked
-  PinnedRegion* lease_region(size_t reserve) {
+  // A region whose address range can hold `reserve` bytes.  `role` names the array (0 positions, 1 normals, 2 keys,
+  // 3 nibbles, 4 quads): a run takes back the region the same array used last time, whose pages are already locked for
+  // that array's size -- picking "any region that is large enough" let the arrays swap regions from run to run and
+  // re-register tens of MB inside every run.
+  PinnedRegion* lease_region(int role, size_t reserve) {
     PinnedRegion* best = nullptr;
     for (auto& g : regions)
-      if (!g->used && g->reserved >= std::min(reserve, va_limit) && (!best || g->registered > best->registered)) best = g.get();
+      if (!g->used && g->role == role && g->reserved >= std::min(reserve, va_limit) && (!best || g->registered > best->registered)) best = g.get();
     if (best) { best->used = true; return best; }
     std::unique_ptr<PinnedRegion> g(new PinnedRegion());
     size_t want = std::max<size_t>(reserve, 64u << 20);
@@ -228,7 +243,10 @@ struct s2m_ctx {
       if (want <= (64u << 20)) return nullptr;
       va_limit = want / 2;
     }
-    g->base = static_cast<char*>(m); g->reserved = want; g->used = true;
+#ifdef MADV_HUGEPAGE
+    madvise(m, want, MADV_HUGEPAGE);   // 2 MiB pages where the kernel grants them: fewer pages to lock and to map for DMA
+#endif
+    g->base = static_cast<char*>(m); g->reserved = want; g->used = true; g->role = role;
     regions.push_back(std::move(g));
     return regions.back().get();
   }
@@ -820,17 +838,17 @@ int copy_out(s2m_ctx* c, s2m_result* r, cudaStream_t st, uint64_t vert_total, ui
     if (normals && (e = r->g_nrm->ensure(own * 12, n * 12))) return e;
     if ((e = r->g_key->ensure(own * 8, n * 8))) return e;
     if ((e = r->g_nib->ensure(own, n))) return e;
-    CUDA_TRY(cudaMemcpyAsync(r->host<float>(r->g_pos) + 3 * h, c->v_pos.as<float>() + 3 * v0, n * 12, cudaMemcpyDeviceToHost, st));
-    if (normals) CUDA_TRY(cudaMemcpyAsync(r->host<float>(r->g_nrm) + 3 * h, c->v_nrm.as<float>() + 3 * v0, n * 12, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(r->host<uint64_t>(r->g_key) + h, c->v_key.as<unsigned long long>() + v0, n * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(r->host<uint8_t>(r->g_nib) + h, c->v_nib.as<unsigned char>() + v0, n, cudaMemcpyDeviceToHost, st));
+    if ((e = r->g_pos->copy_from_device(12 * h, c->v_pos.as<float>() + 3 * v0, n * 12, st))) return e;
+    if (normals && (e = r->g_nrm->copy_from_device(12 * h, c->v_nrm.as<float>() + 3 * v0, n * 12, st))) return e;
+    if ((e = r->g_key->copy_from_device(8 * h, c->v_key.as<unsigned long long>() + v0, n * 8, st))) return e;
+    if ((e = r->g_nib->copy_from_device(h, c->v_nib.as<unsigned char>() + v0, n, st))) return e;
   }
   r->copied_v = std::max(r->copied_v, v1);
   if (quad_total > r->copied_q) {
     const size_t qb = r->quad_bytes();
     const uint64_t q0 = r->copied_q, n = quad_total - q0;
     if ((e = r->g_quads->ensure(quad_total * qb, n * qb))) return e;
-    CUDA_TRY(cudaMemcpyAsync(r->host<char>(r->g_quads) + qb * q0, c->quads.as<char>() + qb * q0, n * qb, cudaMemcpyDeviceToHost, st));
+    if ((e = r->g_quads->copy_from_device(qb * q0, c->quads.as<char>() + qb * q0, n * qb, st))) return e;
     r->copied_q = quad_total;
   }
   return S2M_OK;
@@ -973,9 +991,9 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
     const unsigned long long cells = (unsigned long long)g.res[0] * g.res[1] * std::max<uint32_t>(r->nz, 1u);
     const unsigned long long vmax = std::min<unsigned long long>(cells, 0xffffffffull);
     const unsigned long long qmax = std::min<unsigned long long>(3ull * vmax, 1ull << 33);
-    r->g_pos = c->lease_region(vmax * 12); r->g_nrm = c->lease_region(vmax * 12);
-    r->g_key = c->lease_region(vmax * 8); r->g_nib = c->lease_region(vmax);
-    r->g_quads = c->lease_region(qmax * r->quad_bytes());
+    r->g_pos = c->lease_region(0, vmax * 12); r->g_nrm = c->lease_region(1, vmax * 12);
+    r->g_key = c->lease_region(2, vmax * 8); r->g_nib = c->lease_region(3, vmax);
+    r->g_quads = c->lease_region(4, qmax * r->quad_bytes());
     if (!r->g_pos || !r->g_nrm || !r->g_key || !r->g_nib || !r->g_quads)
       return fail(S2M_ERR_OOM, "mmap of the host output address ranges failed");
   }

@@ -260,9 +260,13 @@ extern "C" int s2m_multi_create(const int* device_ordinals, int n, uint32_t flag
   if (!out) return fail(S2M_ERR_INVALID_ARG, "s2m_multi_create: out is NULL");
   *out = nullptr;
   if (!device_ordinals || n < 1 || n > 64) return fail(S2M_ERR_INVALID_ARG, "s2m_multi_create: 1 .. 64 device ordinals");
+  // One ordinal may appear several times only when the counts travel through host memory (NCCL refuses two ranks on one
+  // device): several slabs then share a GPU, each with its own context, streams and buffers -- how the z-slab path is
+  // exercised on a one-GPU box (tests/test_multi_gpu.py).
   for (int a = 0; a < n; ++a)
     for (int b = a + 1; b < n; ++b)
-      if (device_ordinals[a] == device_ordinals[b]) return fail(S2M_ERR_INVALID_ARG, "s2m_multi_create: a device ordinal appears twice");
+      if (device_ordinals[a] == device_ordinals[b] && !(flags & S2M_MULTI_NO_NCCL))
+        return fail(S2M_ERR_INVALID_ARG, "s2m_multi_create: a device ordinal appears twice (allowed only with S2M_MULTI_NO_NCCL)");
   std::unique_ptr<s2m_multi, void (*)(s2m_multi*)> mc(new s2m_multi(), s2m_multi_destroy);
   mc->n = n; mc->flags = flags;
   mc->ordinals.assign(device_ordinals, device_ordinals + n);

@@ -30,23 +30,35 @@ from tests.support import tolerance as tol
 EXACT = {"torus", "martin_cube", "p_key"}   # + - * / sqrt only: IEEE-exact on every platform
 
 
-def assert_report(name, rep: tol.Report, vs: str, n_libm_over=None):
+def f32_position_floor_voxels(res, bounds):
+    """What f32 itself allows against an f64 ground truth: 8 ulp of the largest coordinate, in voxels.  The reference
+    computes in f32 (WGSL f32), so below this an f64 comparison measures the number format, not the implementation:
+    p_key at --bounds 20, R = 1024 has 6e-5 voxel per ulp; the bit-for-bit comparison against f32 + libm is the real claim there."""
+    voxel = bounds / (res - 1)
+    return 8.0 * 2.0 ** -23 * (bounds / 2) / voxel
+
+
+def assert_report(name, rep: tol.Report, vs: str, n_libm_over=None, res=None, bounds=None):
     s = rep.summary()
     if name in EXACT:
         assert rep.n_mesh == rep.n_indep_active and not rep.residual_keys and rep.identity_threshold_voxels == 0.0, s
         assert rep.nibble_mismatches == 0 and rep.quad_mismatches == 0, s
-        assert rep.n_position_over == 0 and rep.max_position_error_voxels < tol.NORTH_STAR_POSITION_VOXELS, s
+        floor = f32_position_floor_voxels(res, bounds) if res else 0.0
+        assert rep.max_position_error_voxels < max(tol.NORTH_STAR_POSITION_VOXELS, floor), s
+        assert rep.n_position_over == 0 or floor > tol.NORTH_STAR_POSITION_VOXELS, s
         if vs == "f32":
-            assert rep.max_position_error_voxels == 0.0 and rep.n_excluded_cells == 0, s   # bit for bit
+            assert rep.max_position_error_voxels == 0.0 and rep.n_excluded_cells == 0 and rep.n_position_over == 0, s   # bit for bit
     else:
         n = max(rep.n_mesh, 1)
         assert len(rep.residual_keys) <= max(2, 5e-4 * n), s             # active set: identical but for ~1e-4 of the cells ...
         assert rep.identity_threshold_voxels < 5e-3, s                    # ... each with a corner this close to the surface
         assert rep.nibble_mismatches <= max(3, 5e-4 * n), s
         assert rep.quad_mismatches <= 4 * (rep.nibble_mismatches + len(rep.residual_keys)), s
-        assert rep.n_position_over <= 0.03 * n, s                         # >= 97 % of the vertices within 1e-4 voxel
+        # positions: five iterations of z -> z^8 + c amplify every rounding; what counts is that the pinned functions are
+        # no worse against the f64 ground truth than glibc's f32 functions are (measured on the same slab)
+        assert rep.n_position_over <= 0.10 * n, s
         assert rep.p999_position_error_voxels < 5e-3, s
-        if n_libm_over is not None:   # no worse than glibc's f32 functions are against the same ground truth
+        if n_libm_over is not None:
             assert rep.n_position_over <= 1.5 * n_libm_over + 50, (s, n_libm_over)
 
 
@@ -118,7 +130,18 @@ def test_gpu_mesh_against_independent_evaluation(ctx, name, res, bounds, pairs):
     from tests.test_parity_gpu import module_for
     mod = module_for(ctx, name)
     p, _ = s2m.params_from_cli(res, bounds)
-    slabs = [(0, res - 1)] if pairs is None else [(z, z + 2) for z in stratified_pairs(res - 1, pairs)]
+    if pairs is None:
+        slabs = [(0, res - 1)]
+    else:
+        # half of the slab pairs evenly over the grid, half evenly over the slices that hold vertices at all (p_key with
+        # the default bounds is one flat cut through the key: 1024 x 1024 vertices in a single slice)
+        full = s2m.mesh_run(ctx, mod, p)
+        occupied = np.unique((full.data().keys >> np.uint64(32)).astype(np.int64) - 1)   # faithful mode: label = z + 1
+        full.free()
+        zs = set(stratified_pairs(res - 1, pairs // 2))
+        if len(occupied):
+            zs |= {min(res - 3, max(1, int(occupied[int((i + 0.5) * len(occupied) / (pairs // 2))]))) for i in range(pairs // 2)}
+        slabs = [(z, z + 2) for z in sorted(zs)]
     total = {"f64": tol.Report(), "f32": tol.Report(), "libm_vs_f64_over": 0}
     thr = {"f64": 0.0, "f32": 0.0}
     worst = {"f64": 0.0, "f32": 0.0}
@@ -129,7 +152,7 @@ def test_gpu_mesh_against_independent_evaluation(ctx, name, res, bounds, pairs):
         r.finish(n_halo)      # own vertex j <-> index n_halo + j; quads naming the halo slice drop out of the comparison
         d = r.data()
         i64 = oracle.indep_run(name, res, bounds, z_begin=z0, z_end=z1, precision=64)
-        three_way = name not in EXACT and k % 4 == 0
+        three_way = name not in EXACT
         i32 = oracle.indep_run(name, res, bounds, z_begin=z0, z_end=z1, precision=32) if (name in EXACT and k % 4 == 0) or three_way else None
         for vs, ind in (("f64", i64), ("f32", i32)):
             if ind is None:
@@ -140,7 +163,7 @@ def test_gpu_mesh_against_independent_evaluation(ctx, name, res, bounds, pairs):
                 n_libm_over = tol.compare(i32.keys[a], i32.positions[a], i32.nibbles[a], i64).n_position_over
                 total["libm_vs_f64_over"] += n_libm_over
             rep = tol.compare(d.keys, d.positions, d.nibbles, ind, d.quads, quad_index_base=n_halo)
-            assert_report(name, rep, vs, n_libm_over)
+            assert_report(name, rep, vs, n_libm_over, res, bounds)
             t = total[vs]
             for f in ("n_mesh", "n_indep_active", "n_excluded_cells", "n_excluded_corner_values", "nibble_mismatches", "n_position_over",
                       "quads_compared", "quad_mismatches", "seconds_indep"):
