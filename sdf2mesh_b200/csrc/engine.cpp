@@ -209,7 +209,7 @@ struct s2m_ctx {
   int device = 0;
   cudaDeviceProp prop{};
   cudaStream_t stream = nullptr, copy_stream = nullptr, prod_stream = nullptr;
-  DevBuf slab, cls, slab2, cls2, cand_mask, word_prefix, cand_key, cand_vrank, status, counters;
+  DevBuf slab, cls, slab2, cls2, cand_mask, seg_count, word_prefix, cand_key, cand_vrank, status, counters;
   DevBuf v_pos, v_nrm, v_key, v_nib, quads, scratch, invalid;
   std::vector<PinnedBlock> pinned;            // small outputs (candidate list, invalid records, halo positions)
   std::vector<std::unique_ptr<PinnedRegion>> regions;  // big outputs
@@ -290,7 +290,7 @@ struct s2m_ctx {
 // device counters (u64 words).  C_CHUNK_CANDb / C_K2_DONEb: candidates of the chunk K2 classified into slab buffer b and
 // K2's block-completion counter for it (adjacent: one 16-byte memset resets both).
 enum Counter { C_NHALO = 2, C_NINVALID = 4, C_INVALID_CURSOR = 8, C_CHUNK_CAND0 = 9, C_K2_DONE0 = 10, C_CHUNK_CAND1 = 11, C_K2_DONE1 = 12, C_COUNT = 16 };
-enum CtxEvent { EV_BEGIN = 0, EV_KERNELS_DONE = 1, EV_ALL_DONE = 2, EV_PRODUCED0 = 4, EV_PRODUCED1 = 5, EV_CONSUMED0 = 6, EV_CONSUMED1 = 7 };
+enum CtxEvent { EV_BEGIN = 0, EV_KERNELS_DONE = 1, EV_ALL_DONE = 2, EV_PRODUCED0 = 4, EV_PRODUCED1 = 5, EV_CONSUMED0 = 6, EV_CONSUMED1 = 7, EV_K1DONE0 = 10, EV_K1DONE1 = 11 };
 constexpr unsigned long long kInvalidCapacity = 1ull << 20;
 
 extern "C" int s2m_ctx_create(int device_ordinal, s2m_ctx** out) {
@@ -333,7 +333,7 @@ extern "C" void s2m_ctx_destroy(s2m_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (DevBuf* b : {&c->slab, &c->cls, &c->slab2, &c->cls2, &c->cand_mask, &c->word_prefix, &c->cand_key, &c->cand_vrank, &c->status, &c->counters,
+  for (DevBuf* b : {&c->slab, &c->cls, &c->slab2, &c->cls2, &c->cand_mask, &c->seg_count, &c->word_prefix, &c->cand_key, &c->cand_vrank, &c->status, &c->counters,
                     &c->v_pos, &c->v_nrm, &c->v_key, &c->v_nib, &c->quads, &c->scratch, &c->invalid})
     b->release();
   for (auto& b : c->pinned) cudaFreeHost(b.p);
@@ -877,9 +877,9 @@ void finalize_timings(s2m_ctx* c, s2m_result* r) {
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[2]); r->t.total_ms = ms;
 }
 
-// The pipeline.  For every z-chunk, on the PRODUCER stream: K1 (SDF once per corner -> f32 slab + 2-bit corner classes)
-// and K2 (classes -> candidate bit per cell; its last block writes the chunk's candidate count into mapped host memory);
-// on the CONSUMER stream: K3 (compaction + rank table), K4a (the reference's per-cell arithmetic on the candidates ->
+// The pipeline.  For every z-chunk, on the PRODUCER stream: K1 (SDF once per corner -> f32 slab + 2-bit corner classes);
+// on the CONSUMER stream: K2 (classes -> candidate bit per cell; its last block writes the chunk's candidate count into
+// mapped host memory), K3 (compaction + rank table), K4a (the reference's per-cell arithmetic on the candidates ->
 // vertices), K4b (quads, slab-relative indices; its last block writes the running totals into mapped host memory);
 // on the COPY stream: the chunk's vertices and quads into pinned host memory.  The host waits for exactly two events
 // per chunk -- "K2 done" (to size K4a's grid and the buffers) and "K4b done" (to size the copies) -- and both waits
@@ -942,7 +942,9 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
   if (r->nz > 0) {
     if ((st = c->cand_mask.ensure((n_words + 16) * 4))) return st;
     if ((st = c->word_prefix.ensure((n_words + 16) * 4))) return st;
+    if ((st = c->seg_count.ensure(((unsigned long long)g.res[1] * r->nz * s2m_segs_x(r->words_x) + 16) * 4))) return st;
   }
+  const unsigned long long segs_per_slice = (unsigned long long)g.res[1] * s2m_segs_x(r->words_x);
   // ---- chunk plan: bounded slab, and enough chunks that the copies hide behind later chunks
   std::vector<Chunk> chunks;
   const unsigned long long plane_bytes = g.plane_stride * 4ull;
@@ -1004,7 +1006,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
   cudaStream_t ps = pipelined ? c->prod_stream : s;   // producer stream (K1, K2)
   if (pipelined) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_BEGIN], 0));  // after the counter reset
   const unsigned cls_words = g.pitch_x / 32u;
-  // K1 + K2 of chunk ci into slab buffer ci % 2 (buffer 0 when not pipelined)
+  // K1 of chunk ci into slab / class-plane buffer ci % 2 (buffer 0 when not pipelined), on the producer stream
   auto produce = [&](size_t ci) -> int {
     const Chunk ch = chunks[ci];
     const int buf = pipelined ? (int)(ci & 1) : 0;
@@ -1020,9 +1022,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
       if ((st2 = cls_buf.ensure((size_t)n_planes * g.rows * cls_words * 8 + 64))) return st2;
       cls = cls_buf.p;
     }
-    if (pipelined && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_CONSUMED0 + buf], 0));  // K4a of chunk ci-2 has read this buffer
-    unsigned long long* cnt = d_cnt + (buf ? C_CHUNK_CAND1 : C_CHUNK_CAND0);
-    CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, ps));   // the count and K2's block-completion counter
+    if (pipelined && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_CONSUMED0 + buf], 0));  // K2 and K4a of chunk ci-2 have read this buffer
     float tau_arg = tau;
     void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw};
     unsigned bx, by;
@@ -1033,20 +1033,37 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
       if ((st2 = launch(m->k1, grid1, dim3(bx, by, 1), ps, a1, "s2m_k1_slab"))) return st2;
       SPAN_END(ps);
     }
+    CUDA_TRY(cudaEventRecord(c->ev[EV_K1DONE0 + buf], ps));
+    r->t.launches += 1;
+    return S2M_OK;
+  };
+  // K2 of chunk ci on the CONSUMER stream: it is bound by memory, K1 by instruction issue, so K2 of chunk c runs beside
+  // K1 of chunk c+1 instead of between two K1 launches (1.1 ms of a 2048^3 run).  Its last block writes the chunk's
+  // candidate count into mapped host memory; EV_PRODUCED is what the host waits for.
+  auto classify = [&](size_t ci) -> int {
+    const Chunk ch = chunks[ci];
+    const int buf = pipelined ? (int)(ci & 1) : 0;
+    float* slab = no_slab ? nullptr : (buf ? c->slab2 : c->slab).as<float>();
+    void* cls = from_slab ? nullptr : (buf ? c->cls2 : c->cls).p;
+    if (pipelined) CUDA_TRY(cudaStreamWaitEvent(s, c->ev[EV_K1DONE0 + buf], 0));
+    unsigned long long* cnt = d_cnt + (buf ? C_CHUNK_CAND1 : C_CHUNK_CAND0);
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, s));   // the count and K2's block-completion counter
     S2mK2Args a2{};
     a2.slab = slab; a2.pitch_x = g.pitch_x; a2.plane_stride = g.plane_stride;
     a2.res_x = g.res[0]; a2.res_y = g.res[1]; a2.nz_chunk = ch.nzc; a2.tau = tau;
     a2.cand_mask = c->cand_mask.as<uint32_t>() + words_per_slice * ch.z0; a2.words_x = r->words_x; a2.total = cnt;
     a2.cls = cls; a2.cls_words = cls_words;
     a2.done = reinterpret_cast<unsigned*>(cnt + 1); a2.host_total = c->h_counters + buf;
+    a2.seg_count = c->seg_count.as<uint32_t>() + segs_per_slice * ch.z0;
     {
-      SPAN_BEGIN(1, ps);
-      int e2 = from_slab ? s2m_launch_k2(&a2, ps) : s2m_launch_k2_bits(&a2, ps);
+      SPAN_BEGIN(1, s);
+      int e2 = from_slab ? s2m_launch_k2(&a2, s) : s2m_launch_k2_bits(&a2, s);
+      if (!e2 && from_slab) e2 = s2m_launch_seg_count(a2.cand_mask, (unsigned long long)g.res[1] * ch.nzc, r->words_x, a2.seg_count, s);
       if (e2) return fail(S2M_ERR_CUDA, std::string("k2_classify launch: ") + cudaGetErrorString((cudaError_t)e2));
-      SPAN_END(ps);
+      SPAN_END(s);
     }
-    CUDA_TRY(cudaEventRecord(c->ev[EV_PRODUCED0 + buf], ps));
-    r->t.launches += 2;
+    CUDA_TRY(cudaEventRecord(c->ev[EV_PRODUCED0 + buf], s));
+    r->t.launches += 1;
     return S2M_OK;
   };
   if (!dense && n_chunks && (st = produce(0))) return st;
@@ -1058,9 +1075,9 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
     unsigned slab_first_plane = 0, slab_n_planes = 0;
     uint64_t n_cand = 0;
     if (!dense) {
-      // the next chunk's K1/K2 are queued before this chunk's count is waited for
+      // the next chunk's K1 is queued before this chunk's count is waited for
       if (pipelined && ci + 1 < n_chunks && (st = produce(ci + 1))) return st;
-      if (pipelined) CUDA_TRY(cudaStreamWaitEvent(s, c->ev[EV_PRODUCED0 + buf], 0));
+      if ((st = classify(ci))) return st;
       if (!no_slab) { slab_first_plane = r->z_first + ch.z0; slab_n_planes = ch.nzc + 1; }
       // ---- [count] candidates of this chunk: K2's last block wrote it into mapped host memory
       CUDA_TRY(cudaEventSynchronize(c->ev[EV_PRODUCED0 + buf]));
@@ -1074,12 +1091,14 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
       std::vector<uint32_t> host(chunk_words);
       for (unsigned long long i = 0; i < chunk_words; i += r->words_x) memcpy(&host[i], dense_row.data(), r->words_x * 4);
       CUDA_TRY(cudaMemcpyAsync(mask_chunk, host.data(), chunk_words * 4, cudaMemcpyHostToDevice, s));
+      if (int e = s2m_launch_seg_count(mask_chunk, (unsigned long long)g.res[1] * ch.nzc, r->words_x, c->seg_count.as<uint32_t>() + segs_per_slice * ch.z0, s))
+        return fail(S2M_ERR_CUDA, std::string("k_seg_count launch: ") + cudaGetErrorString((cudaError_t)e));
       CUDA_TRY(cudaStreamSynchronize(s));
       n_cand = (unsigned long long)g.res[0] * g.res[1] * ch.nzc;
     }
     const uint64_t cand_total = cand_done + n_cand;
     if (cand_total >= 0xffffffffull) return fail(S2M_ERR_UNSUPPORTED, "more than 2^32-1 candidate cells in one slab; split it with z_begin/z_end");
-    const unsigned k3_tiles = s2m_k3_tiles(chunk_words);
+    const unsigned k3_tiles = s2m_k3_tiles(chunk_words, r->words_x);
     const unsigned k4_tiles = (unsigned)std::max<uint64_t>(1, (n_cand + 127) / 128);   // >= 1: an empty chunk still carries the totals forward
     const unsigned k4b_tiles = s2m_k4b_tiles(n_cand);
     const size_t status_words = (size_t)k3_tiles + k4_tiles + k4b_tiles + 16;
@@ -1101,7 +1120,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
     // ---- K3
     {
       S2mK3Args a3{};
-      a3.cand_mask = mask_chunk; a3.n_words = chunk_words; a3.words_x = r->words_x; a3.res_y = g.res[1];
+      a3.cand_mask = mask_chunk; a3.seg_count = c->seg_count.as<uint32_t>() + segs_per_slice * ch.z0; a3.n_words = chunk_words; a3.words_x = r->words_x; a3.res_y = g.res[1];
       a3.z_offset = r->z_first + ch.z0; a3.word_prefix = c->word_prefix.as<uint32_t>() + words_per_slice * ch.z0;
       a3.cand_key = c->cand_key.as<unsigned long long>(); a3.base = cand_done;
       a3.status = status + 2; a3.ticket = tickets;

@@ -141,7 +141,7 @@ __device__ __forceinline__ unsigned long long ld_u64(const uint2* p) {
 __global__ void __launch_bounds__(256)
 k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t rows, uint32_t res_x, uint32_t res_y,
                  uint32_t nz_chunk, uint32_t* __restrict__ cand_mask, uint32_t words_x, unsigned long long* __restrict__ total,
-                 unsigned* __restrict__ done, unsigned long long* __restrict__ host_total) {
+                 unsigned* __restrict__ done, unsigned long long* __restrict__ host_total, uint32_t* __restrict__ seg_count) {
   __shared__ unsigned s_red[8];
   const uint32_t xw = blockIdx.x * 32u + (threadIdx.x & 31u);
   const uint32_t y = blockIdx.y * 8u + (threadIdx.x >> 5);
@@ -153,6 +153,7 @@ k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t row
     const uint32_t plane = zt0 + k;
     if (plane > nz_chunk) break;
     unsigned long long cur = 0;
+    unsigned pc = 0;
     if (live) {
       const uint2* r0 = cls + ((unsigned long long)plane * rows + y) * cls_words + xw;
       const uint2* r1 = r0 + cls_words;
@@ -172,8 +173,15 @@ k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t row
         const uint32_t xb = xw * 32u;
         if (xb + 32u > res_x) cand &= (1u << (res_x - xb)) - 1u;
         cand_mask[((unsigned long long)z * res_y + y) * words_x + xw] = cand;
-        count += (unsigned)__popc(cand);
+        pc = (unsigned)__popc(cand);
+        count += pc;
       }
+    }
+    // a warp is one segment (32 consecutive words of one cell row): its candidate count, for K3's scan
+    if (seg_count != nullptr && k >= 1) {
+      const unsigned sc = __reduce_add_sync(0xffffffffu, pc);
+      if ((threadIdx.x & 31u) == 0 && y < res_y)
+        seg_count[((unsigned long long)(plane - 1u) * res_y + y) * gridDim.x + blockIdx.x] = sc;
     }
     prev = cur;
   }
@@ -188,81 +196,122 @@ k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t row
 }
 
 // ------------------------------------------------------------------------------------------ K3
+// Compaction of the candidate bits into the ordered candidate list + the rank table, in ONE pass over per-segment
+// counts instead of the mask.  A segment is 32 consecutive mask words of one cell row (1024 cells, one 128-byte line);
+// K2 writes every segment's candidate count while it writes the mask (k_seg_count does it for the other mask sources).
+// Segments in index order are mask words in index order, so: block scan of the counts + decoupled look-back across
+// tiles gives every segment its first rank; then the tile's NON-EMPTY segments -- at 2048^3 the surface passes through
+// a fraction of them -- are expanded by the block's warps, one segment per warp at a time: lane l owns word l, a warp
+// scan of the popcounts gives the word's rank (word_prefix) and each lane appends its cells' keys.  The mask is read
+// only where it has bits (the first version scanned all of it: 1.3 ms at 2048^3, 4 barriers per 16 KB of mask).
 constexpr int K3_THREADS = 256;
-constexpr int K3_WPT_DEFAULT = 16;
-// mask words per thread (4, 8 or 16 = 1, 2 or 4 uint4 loads); S2M_K3_WPT selects at run time
-static int k3_wpt() {
-  static const int v = [] { const char* e = getenv("S2M_K3_WPT"); const int w = e ? atoi(e) : 0; return (w == 4 || w == 8 || w == 16) ? w : K3_WPT_DEFAULT; }();
-  return v;
+constexpr int K3_SPT = 2;                         // segments per thread
+constexpr int K3_TILE_SEGS = K3_THREADS * K3_SPT; // 512 segments = 16384 mask words per tile
+
+__global__ void __launch_bounds__(32 * 8)
+k_seg_count(const uint32_t* __restrict__ cand_mask, unsigned long long n_rows, uint32_t words_x, uint32_t segs_x, uint32_t* __restrict__ seg_count) {
+  const unsigned long long seg = (unsigned long long)blockIdx.x * 8u + (threadIdx.x >> 5);
+  if (seg >= n_rows * segs_x) return;
+  const unsigned long long row = seg / segs_x;
+  const uint32_t xw = (uint32_t)(seg - row * segs_x) * 32u + (threadIdx.x & 31u);
+  const unsigned pc = xw < words_x ? (unsigned)__popc(cand_mask[row * words_x + xw]) : 0u;
+  const unsigned sc = __reduce_add_sync(0xffffffffu, pc);
+  if ((threadIdx.x & 31u) == 0) seg_count[seg] = sc;
 }
 
-template <int K3_WORDS_PER_THREAD>
 __global__ void __launch_bounds__(K3_THREADS)
-k3_compact(const uint32_t* __restrict__ cand_mask, unsigned long long n_words, uint32_t words_x, uint32_t res_y,
-           uint32_t z_offset, uint32_t* __restrict__ word_prefix, unsigned long long* __restrict__ cand_key,
+k3_compact(const uint32_t* __restrict__ cand_mask, const uint32_t* __restrict__ seg_count, unsigned long long n_segs, uint32_t words_x,
+           uint32_t segs_x, uint32_t res_y, uint32_t z_offset, uint32_t* __restrict__ word_prefix, unsigned long long* __restrict__ cand_key,
            unsigned long long base, unsigned long long* status, unsigned* ticket) {
   __shared__ unsigned s_scan[33];
-  __shared__ unsigned s_tile;
+  __shared__ unsigned s_tile, s_n;
   __shared__ unsigned long long s_base;
-  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __shared__ unsigned s_seg[K3_TILE_SEGS];   // non-empty segments of the tile (index within the tile) ...
+  __shared__ unsigned s_rank[K3_TILE_SEGS];  // ... and the rank of their first candidate within the tile
+  if (threadIdx.x == 0) { s_tile = atomicAdd(ticket, 1u); s_n = 0u; }
   __syncthreads();
   const unsigned tile = s_tile;
-  constexpr int K3_TILE_WORDS = K3_THREADS * K3_WORDS_PER_THREAD;
-  const unsigned long long w0 = (unsigned long long)tile * K3_TILE_WORDS + (unsigned long long)threadIdx.x * K3_WORDS_PER_THREAD;
-  uint32_t m[K3_WORDS_PER_THREAD];
-  // a chunk's region starts at a multiple of the per-slice word count, which need not be 16-byte aligned
-  const bool vec_ok = ((reinterpret_cast<unsigned long long>(cand_mask) | reinterpret_cast<unsigned long long>(word_prefix)) & 15ull) == 0ull;
-  if (vec_ok && w0 + K3_WORDS_PER_THREAD <= n_words) {
-    const uint4* p = reinterpret_cast<const uint4*>(cand_mask + w0);
+  const unsigned long long s0 = (unsigned long long)tile * K3_TILE_SEGS + (unsigned long long)threadIdx.x * K3_SPT;
+  unsigned c[K3_SPT];
+  if (s0 + K3_SPT <= n_segs) {   // seg_count regions start at multiples of the per-slice segment count: 8-byte aligned when that is even
+    if ((reinterpret_cast<unsigned long long>(seg_count) & 7ull) == 0ull) {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(seg_count + s0));
+      c[0] = t.x; c[1] = t.y;
+    } else {
 #pragma unroll
-    for (int q = 0; q < K3_WORDS_PER_THREAD / 4; ++q) {
-      const uint4 t = __ldg(p + q);
-      m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w;
+      for (int q = 0; q < K3_SPT; ++q) c[q] = __ldg(seg_count + s0 + q);
     }
   } else {
 #pragma unroll
-    for (int q = 0; q < K3_WORDS_PER_THREAD; ++q) m[q] = (w0 + q < n_words) ? cand_mask[w0 + q] : 0u;
+    for (int q = 0; q < K3_SPT; ++q) c[q] = (s0 + q < n_segs) ? __ldg(seg_count + s0 + q) : 0u;
   }
+  static_assert(K3_SPT == 2, "the vector load above reads 2 counts");
   unsigned mine = 0;
 #pragma unroll
-  for (int q = 0; q < K3_WORDS_PER_THREAD; ++q) mine += (unsigned)__popc(m[q]);
+  for (int q = 0; q < K3_SPT; ++q) mine += c[q];
   unsigned total = 0;
-  const unsigned local = s2m_block_exclusive_scan(mine, s_scan, &total);
+  unsigned local = s2m_block_exclusive_scan(mine, s_scan, &total);
   if (threadIdx.x < 32) {
     unsigned long long b = s2m_lookback_warp(status, tile, (unsigned long long)total, base);
     if (threadIdx.x == 0) s_base = b;
   }
-  __syncthreads();
-  unsigned long long run = s_base + local;
-  uint32_t pre[K3_WORDS_PER_THREAD];
+  if (total == 0u) return;   // uniform over the block: nothing to expand in this tile
 #pragma unroll
-  for (int q = 0; q < K3_WORDS_PER_THREAD; ++q) {
-    const unsigned long long w = w0 + q;
-    pre[q] = (uint32_t)run;
-    uint32_t bits = m[q];
-    if (bits && w < n_words) {
-      const unsigned long long rowi = w / words_x;
-      const uint32_t xw = (uint32_t)(w - rowi * words_x);
-      const uint32_t z = (uint32_t)(rowi / res_y);
-      const uint32_t y = (uint32_t)(rowi - (unsigned long long)z * res_y);
-      const unsigned long long hi = ((unsigned long long)y << 16) | ((unsigned long long)(z + z_offset) << 32);
-      while (bits) {
-        const int b = __ffs((int)bits) - 1;
-        bits &= bits - 1u;
-        cand_key[run++] = hi | (unsigned long long)(xw * 32u + (uint32_t)b);
+  for (int q = 0; q < K3_SPT; ++q) {
+    if (c[q]) {
+      const unsigned at = atomicAdd(&s_n, 1u);
+      s_seg[at] = threadIdx.x * K3_SPT + (unsigned)q;
+      s_rank[at] = local;
+    }
+    local += c[q];
+  }
+  __syncthreads();
+  const unsigned n = s_n;
+  const unsigned long long tile_base = s_base;
+  const unsigned lane = threadIdx.x & 31u;
+  // K3_BATCH segments per warp and round: their mask lines are requested together (a warp that expands one segment at
+  // a time has one 128-byte load in flight and waits a full memory latency per segment)
+  constexpr unsigned K3_BATCH = 4;
+  for (unsigned i0 = threadIdx.x >> 5; i0 < n; i0 += (K3_THREADS / 32) * K3_BATCH) {
+    unsigned long long rowi[K3_BATCH], w[K3_BATCH];
+    uint32_t xw[K3_BATCH], bits[K3_BATCH];
+    unsigned rank0[K3_BATCH];
+#pragma unroll
+    for (unsigned j = 0; j < K3_BATCH; ++j) {
+      const unsigned i = i0 + j * (K3_THREADS / 32);
+      bits[j] = 0u; rowi[j] = 0ull; w[j] = 0ull; xw[j] = 0xffffffffu; rank0[j] = 0u;
+      if (i < n) {
+        const unsigned long long seg = (unsigned long long)tile * K3_TILE_SEGS + s_seg[i];
+        rowi[j] = seg / segs_x;
+        xw[j] = (uint32_t)(seg - rowi[j] * segs_x) * 32u + lane;
+        w[j] = rowi[j] * words_x + xw[j];
+        rank0[j] = s_rank[i];
+        if (xw[j] < words_x) bits[j] = __ldg(cand_mask + w[j]); else xw[j] = 0xffffffffu;
       }
     }
-  }
-  // The rank table is only ever read for words with a set bit (rank_of in K4b): a thread whose 16
-  // words are all zero -- 99 % of them at 0.1 % candidate density -- has nothing to publish.
-  if (mine == 0) return;
-  if (vec_ok && w0 + K3_WORDS_PER_THREAD <= n_words) {
-    uint4* o = reinterpret_cast<uint4*>(word_prefix + w0);
 #pragma unroll
-    for (int q = 0; q < K3_WORDS_PER_THREAD / 4; ++q) o[q] = make_uint4(pre[4 * q], pre[4 * q + 1], pre[4 * q + 2], pre[4 * q + 3]);
-  } else {
-#pragma unroll
-    for (int q = 0; q < K3_WORDS_PER_THREAD; ++q) if (w0 + q < n_words) word_prefix[w0 + q] = pre[q];
+    for (unsigned j = 0; j < K3_BATCH; ++j) {
+      if (i0 + j * (K3_THREADS / 32) >= n) break;   // uniform over the warp
+      uint32_t b = bits[j];
+      const unsigned pc = (unsigned)__popc(b);
+      unsigned inc = pc;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+      }
+      unsigned long long run = tile_base + rank0[j] + (inc - pc);
+      if (xw[j] != 0xffffffffu) word_prefix[w[j]] = (uint32_t)run;   // the whole line: rank_of (K4b) reads it only for words with a set bit
+      if (b) {
+        const uint32_t z = (uint32_t)(rowi[j] / res_y);
+        const uint32_t y = (uint32_t)(rowi[j] - (unsigned long long)z * res_y);
+        const unsigned long long hi = ((unsigned long long)y << 16) | ((unsigned long long)(z + z_offset) << 32);
+        while (b) {
+          const int bit = __ffs((int)b) - 1;
+          b &= b - 1u;
+          cand_key[run++] = hi | (unsigned long long)(xw[j] * 32u + (uint32_t)bit);
+        }
+      }
+    }
   }
 }
 
@@ -502,23 +551,31 @@ extern "C" int s2m_launch_k2_bits(const S2mK2Args* a, cudaStream_t stream) {
   dim3 grid((a->words_x + 31u) / 32u, (a->res_y + 7u) / 8u, (a->nz_chunk + K2_ZT - 1) / K2_ZT);
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return 0;
   k2_classify_bits<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint2*>(a->cls), a->cls_words, a->res_y + 1u, a->res_x, a->res_y, a->nz_chunk,
-                                              a->cand_mask, a->words_x, a->total, a->done, a->host_total);
+                                              a->cand_mask, a->words_x, a->total, a->done, a->host_total, a->seg_count);
   return (int)cudaGetLastError();
 }
 
-extern "C" unsigned s2m_k3_tiles(unsigned long long n_words) {
-  const unsigned long long tile_words = (unsigned long long)K3_THREADS * k3_wpt();
-  return (unsigned)((n_words + tile_words - 1) / tile_words);
+extern "C" uint32_t s2m_segs_x(uint32_t words_x) { return (words_x + 31u) / 32u; }
+
+extern "C" int s2m_launch_seg_count(const uint32_t* cand_mask, unsigned long long n_rows, uint32_t words_x, uint32_t* seg_count, cudaStream_t stream) {
+  const uint32_t segs_x = s2m_segs_x(words_x);
+  const unsigned long long n_segs = n_rows * segs_x;
+  if (!n_segs) return 0;
+  k_seg_count<<<(unsigned)((n_segs + 7) / 8), 256, 0, stream>>>(cand_mask, n_rows, words_x, segs_x, seg_count);
+  return (int)cudaGetLastError();
+}
+
+extern "C" unsigned s2m_k3_tiles(unsigned long long n_words, uint32_t words_x) {
+  const unsigned long long n_segs = words_x ? n_words / words_x * s2m_segs_x(words_x) : 0ull;
+  return (unsigned)((n_segs + K3_TILE_SEGS - 1) / K3_TILE_SEGS);
 }
 
 extern "C" int s2m_launch_k3(const S2mK3Args* a, cudaStream_t stream) {
-  const unsigned tiles = s2m_k3_tiles(a->n_words);
+  const unsigned tiles = s2m_k3_tiles(a->n_words, a->words_x);
   if (!tiles) return 0;
-  switch (k3_wpt()) {
-    case 4: k3_compact<4><<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->n_words, a->words_x, a->res_y, a->z_offset, a->word_prefix, a->cand_key, a->base, a->status, a->ticket); break;
-    case 8: k3_compact<8><<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->n_words, a->words_x, a->res_y, a->z_offset, a->word_prefix, a->cand_key, a->base, a->status, a->ticket); break;
-    default: k3_compact<16><<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->n_words, a->words_x, a->res_y, a->z_offset, a->word_prefix, a->cand_key, a->base, a->status, a->ticket); break;
-  }
+  const uint32_t segs_x = s2m_segs_x(a->words_x);
+  k3_compact<<<tiles, K3_THREADS, 0, stream>>>(a->cand_mask, a->seg_count, a->n_words / a->words_x * segs_x, a->words_x, segs_x, a->res_y, a->z_offset,
+                                               a->word_prefix, a->cand_key, a->base, a->status, a->ticket);
   return (int)cudaGetLastError();
 }
 

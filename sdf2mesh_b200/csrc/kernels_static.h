@@ -22,17 +22,20 @@ typedef struct S2mK2Args {
   uint32_t cls_words;             /* class words per row */
   unsigned* done;                 /* optional: zeroed block-completion counter; the last block to finish ... */
   unsigned long long* host_total; /* ... writes *total here (mapped pinned host memory) */
+  uint32_t* seg_count;            /* candidates per SEGMENT (32 consecutive mask words of one cell row, = 1024 cells): entry
+                                     (slice * res_y + y) * segs_x + x_word / 32 of the chunk; what K3 scans instead of the mask */
 } S2mK2Args;
 
 typedef struct S2mK3Args {
   const uint32_t* cand_mask;
+  const uint32_t* seg_count;      /* per-segment candidate counts of the same region (S2mK2Args.seg_count) */
   unsigned long long n_words;
   uint32_t words_x, res_y;
   uint32_t z_offset;              /* true z of slice 0 of the mask */
   uint32_t* word_prefix;          /* same region as cand_mask */
   unsigned long long* cand_key;   /* GLOBAL list: entry `base + local rank` is written */
   unsigned long long base;        /* candidates in earlier chunks */
-  unsigned long long* status;     /* >= s2m_k3_tiles(n_words) zeroed words */
+  unsigned long long* status;     /* >= s2m_k3_tiles(n_words, words_x) zeroed words */
   unsigned* ticket;               /* zeroed */
 } S2mK3Args;
 
@@ -68,7 +71,10 @@ int s2m_launch_publish2(const unsigned long long* src_a, unsigned na, const unsi
 int s2m_launch_fp32_probe(int mode, int blocks, int iters, float* sink, cudaStream_t stream);
 int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream);      /* classify from the f32 slab */
 int s2m_launch_k2_bits(const S2mK2Args* a, cudaStream_t stream); /* classify from K1's class bit planes */
-unsigned s2m_k3_tiles(unsigned long long n_words);
+uint32_t s2m_segs_x(uint32_t words_x);                                         /* segments per cell row */
+/* seg_count of a mask that K2-from-bits did not write (classify from the slab, exact-dense mode) */
+int s2m_launch_seg_count(const uint32_t* cand_mask, unsigned long long n_rows, uint32_t words_x, uint32_t* seg_count, cudaStream_t stream);
+unsigned s2m_k3_tiles(unsigned long long n_words, uint32_t words_x);
 int s2m_launch_k3(const S2mK3Args* a, cudaStream_t stream);
 unsigned s2m_k4b_tiles(unsigned long long n_own);
 int s2m_launch_k4b(const S2mK4bArgs* a, cudaStream_t stream);
