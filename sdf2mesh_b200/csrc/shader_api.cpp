@@ -120,11 +120,34 @@ void add_builtin(s2m_shader* sh, const char* const* names, size_t n) {
   for (size_t i = 0; i < n; ++i) sh->builtin_functions.push_back(names[i]);
 }
 
+// The reference pastes the bytes of its three library files (shader.rs:12-20 include_str!).  This project does not carry
+// those files: the module texts above are its own wording of the same functions, and calls to them are linked against
+// s2m_sdf3d_lib.h.  A user who has the reference's files and needs --debug-wgsl to be BYTE-identical to the reference's
+// dump points S2M_WGSL_MODULE_DIR at the directory that holds sdf3d_primitives.wgsl, sdf_op.wgsl
+// and sdf3d_normal.wgsl: their bytes are then pasted verbatim and compiled through the front-end like any user code (same
+// operation order, so the same bits: tests/test_frontend.py::test_reference_module_files_give_the_reference_dump).
+bool module_file_text(const char* file, std::string* out) {
+  const char* dir = getenv("S2M_WGSL_MODULE_DIR");
+  if (!dir || !*dir) return false;
+  std::ifstream f(std::string(dir) + "/" + file, std::ios::binary);   // verbatim: no BOM stripping, no newline changes
+  if (!f) return false;
+  std::ostringstream ss;
+  ss << f.rdbuf();
+  *out = ss.str();
+  return true;
+}
+std::string normal_module_text(s2m_shader* sh) {
+  std::string t;
+  if (module_file_text("sdf3d_normal.wgsl", &t)) return t;
+  if (sh) sh->builtin_functions.push_back("sdf3d_normal");
+  return kModNormal;
+}
+
 // shader.rs:50-62 module table
 bool emit_module(s2m_shader* sh, const std::string& name, std::string* w) {
-  auto prim = [&] { *w += kModPrimitives; add_builtin(sh, kPrimitiveFns, 5); };
-  auto op = [&] { *w += kModSdfOp; add_builtin(sh, kOpFns, 3); };
-  auto nrm = [&] { *w += kModNormal; sh->builtin_functions.push_back("sdf3d_normal"); };
+  auto prim = [&] { std::string t; if (module_file_text("sdf3d_primitives.wgsl", &t)) *w += t; else { *w += kModPrimitives; add_builtin(sh, kPrimitiveFns, 5); } };
+  auto op = [&] { std::string t; if (module_file_text("sdf_op.wgsl", &t)) *w += t; else { *w += kModSdfOp; add_builtin(sh, kOpFns, 3); } };
+  auto nrm = [&] { *w += normal_module_text(sh); };
   if (name == "sdf::*" || name == "sdf::op") { op(); return true; }
   if (name == "sdf3d::normal") { nrm(); return true; }
   if (name == "sdf3d::primitives") { prim(); return true; }
@@ -248,7 +271,9 @@ int build_from_glsl(const std::string& glsl, const std::string& sdf, s2m_shader*
   if ((st = remove_function(wgsl, "fn main_1(", &wgsl, &err))) return fail(st, err);  // shader.rs:84
   if ((st = remove_function(wgsl, "fn main(", &wgsl, &err))) return fail(st, err);    // :85
   wgsl = remove_line(wgsl, "@fragment");                                               // :86
-  wgsl += kModNormal; wgsl += "\n";                                                    // :87
+  bool normal_is_builtin = true;
+  { std::string t; if (module_file_text("sdf3d_normal.wgsl", &t)) { wgsl += t; normal_is_builtin = false; } else wgsl += kModNormal; }
+  wgsl += "\n";                                                                        // :87 add_line(include_str!("sdf3d_normal.wgsl"))
   if (has_function(wgsl, sdf)) {                                                       // :89-98
     if (!has_function(wgsl, "sdf3d")) wgsl += "fn sdf3d(p: vec3<f32>) -> f32 { return " + sdf + "(p); }\n";
   } else {
@@ -261,7 +286,7 @@ int build_from_glsl(const std::string& glsl, const std::string& sdf, s2m_shader*
   sh->source = wgsl;
   sh->sdf_name = sdf;
   sh->glsl = glsl;
-  sh->builtin_functions.push_back("sdf3d_normal");
+  if (normal_is_builtin) sh->builtin_functions.push_back("sdf3d_normal");
   *out = sh;
   return S2M_OK;
 }
@@ -295,13 +320,15 @@ int build_from_shadertoy(const std::string& code, const std::string& sdf, s2m_sh
     if (!why.empty()) return fail(S2M_ERR_UNSUPPORTED, "SDF function `" + sdf + "`: " + why);
     return fail(S2M_ERR_MISSING_SDF, "Missing SDF function `" + sdf + "` in shader");
   }
-  wgsl += kModNormal; wgsl += "\n";  // shader.rs:139
+  bool normal_is_builtin = true;
+  { std::string t; if (module_file_text("sdf3d_normal.wgsl", &t)) { wgsl += t; normal_is_builtin = false; } else wgsl += kModNormal; }
+  wgsl += "\n";  // shader.rs:139
   s2m_shader* sh = new s2m_shader();
   sh->kind = S2M_SRC_WGSL;
   sh->source = wgsl;
   sh->sdf_name = sdf;
   sh->glsl = glsl;
-  sh->builtin_functions.push_back("sdf3d_normal");
+  if (normal_is_builtin) sh->builtin_functions.push_back("sdf3d_normal");
   *out = sh;
   return S2M_OK;
 }

@@ -42,6 +42,59 @@ def test_our_examples_equal_reference_examples(built, name, f, bounds):
     assert f32_equal(a, b).all()
 
 
+def _reference_expansion(path, src_dir):
+    """Sdf3DShader::shader_source_input (shader.rs:159-203) restated: a `use X;` line becomes the bytes of the module
+    files (module table :50-62), everything else is copied line by line with a newline"""
+    mod = lambda f: open(os.path.join(src_dir, f), encoding="utf-8").read()
+    table = {"sdf::*": ["sdf_op.wgsl"], "sdf::op": ["sdf_op.wgsl"], "sdf3d::normal": ["sdf3d_normal.wgsl"],
+             "sdf3d::primitives": ["sdf3d_primitives.wgsl"], "sdf3d::*": ["sdf3d_primitives.wgsl", "sdf3d_normal.wgsl"]}
+    out = ""
+    for line in open(path, encoding="utf-8").read().splitlines():
+        t = line.strip()
+        if t.endswith(";") and t.startswith("use"):
+            name = t.replace("use", "", 1).replace('"', "").replace(";", "").strip()
+            out += "".join(mod(f) for f in table.get(name, []))
+            continue
+        assert not (t.endswith(";") and t.startswith("include"))   # the examples have none
+        out += line + "\n"
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="reference checkout not present")
+@pytest.mark.parametrize("f,bounds", [("torus.sdf3d", 2.0), ("martin_cube.sdf3d", 2.5), ("p_key.sdf3d", 20.0)])
+def test_reference_module_files_give_the_reference_dump(built, tmp_path, monkeypatch, f, bounds):
+    """with S2M_WGSL_MODULE_DIR pointing at the reference's three library files, --debug-wgsl
+    (Sdf3DShader::write_to_file, shader.rs:206-210) is byte for byte what the reference writes, the pasted library text is
+    what gets compiled, and it evaluates to the same bits as the built-in device library"""
+    path = os.path.join(REF_EXAMPLES, f)
+    builtin = s2m.Sdf3DShader.from_path(path)
+    monkeypatch.setenv("S2M_WGSL_MODULE_DIR", "/root/reference/src")
+    sh = s2m.Sdf3DShader.from_path(path)
+    dump = tmp_path / "dump.wgsl"
+    sh.write_to_file(dump)
+    assert dump.read_bytes() == _reference_expansion(path, "/root/reference/src").encode("utf-8")
+    assert dump.read_bytes() != builtin.source.encode("utf-8")          # (the default dump carries this project's own library text)
+    cuda = sh.lower_to_cuda()
+    assert "u_sdf3d_normal" in cuda                                       # compiled from the pasted text, not linked from s2m_sdf3d_lib.h
+    pts = points(bounds, 50_000)
+    assert f32_equal(host_eval.eval_points(cuda, pts), host_eval.eval_points(builtin.lower_to_cuda(), pts)).all()
+    monkeypatch.setenv("S2M_WGSL_MODULE_DIR", str(tmp_path / "nowhere"))  # files not found: the built-in text
+    assert s2m.Sdf3DShader.from_path(path).source == builtin.source
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="reference checkout not present")
+def test_reference_normal_module_in_the_glsl_route(built, monkeypatch):
+    """from_glsl_fragment_shader appends include_str!("sdf3d_normal.wgsl") with add_line (shader.rs:87)"""
+    path = os.path.join(REF_EXAMPLES, "mandelmesh.frag")
+    builtin = s2m.Sdf3DShader.from_glsl_fragment_shader(path, "sdf")
+    monkeypatch.setenv("S2M_WGSL_MODULE_DIR", "/root/reference/src")
+    sh = s2m.Sdf3DShader.from_glsl_fragment_shader(path, "sdf")
+    normal = open("/root/reference/src/sdf3d_normal.wgsl", encoding="utf-8").read()
+    assert (normal + "\n") in sh.source and sh.source.endswith("fn sdf3d(p: vec3<f32>) -> f32 { return sdf(p); }\n")
+    pts = points(5.0, 20_000)
+    assert f32_equal(host_eval.eval_points(sh.lower_to_cuda(), pts), host_eval.eval_points(builtin.lower_to_cuda(), pts)).all()
+
+
 # --- the reference's own three unit tests (/root/reference/src/shadertoy.rs:354-453), restated -----
 NAGA_WGSL = textwrap.dedent("""\
     fn mainImage(fragColor: ptr<function, vec4<f32>>, fragCoord: vec2<f32>) {
