@@ -316,10 +316,10 @@ int main(int argc, char** argv) {
   if (a.stats) {
     const s2m_timings& t = ri.timings;
     const double vox = (double)params.dims[0] * params.dims[1] * params.dims[2];
-    fprintf(stderr, "stats: %llu candidates, %llu vertices, %llu quads | front-end %.1f ms, NVRTC %.1f ms | K1 %.3f K2 %.3f K3 %.3f K4a %.3f K4b %.3f d2h %.3f total %.3f ms (%u launches, %u chunks) | %.2f Gvoxel/s\n",
+    fprintf(stderr, "stats: %llu candidates, %llu vertices, %llu quads | front-end %.1f ms, NVRTC %.1f ms | K1 %.3f K2 %.3f K3 %.3f K4a %.3f K4b %.3f d2h %.3f total %.3f ms (%u launches, %u chunks), mesh phase on the host clock %.3f ms | %.2f Gvoxel/s\n",
             (unsigned long long)ri.n_candidates, (unsigned long long)ri.n_vertices, (unsigned long long)ri.n_quads,
             s2m_module_compile_ms(module, 0), s2m_module_compile_ms(module, 1), t.k1_slab_ms, t.k2_classify_ms, t.k3_compact_ms,
-            t.k4_vertices_ms, t.k4_quads_ms, t.d2h_ms, t.total_ms, t.launches, t.chunks, vox / (t.total_ms * 1e-3) / 1e9);
+            t.k4_vertices_ms, t.k4_quads_ms, t.d2h_ms, t.total_ms, t.launches, t.chunks, t.host_wall_ms, vox / (t.total_ms * 1e-3) / 1e9);
   }
   int st;
   const std::string& m = a.mesh;

@@ -378,6 +378,7 @@ struct s2m_module {
   CUfunction_t k1 = nullptr, k4 = nullptr, k_eval = nullptr, k_probe = nullptr, k_eval2 = nullptr;
   s2m_ctx* ctx = nullptr;
   unsigned k1_rows = 1;  // grid rows per K1 thread (S2M_K1_ROWS the kernels were compiled with)
+  unsigned k1_zpt = 1;   // planes per K1 thread (S2M_K1_ZPT)
   bool k1_packed = false;  // K1 evaluates corner pairs in f32x2 arithmetic (s2m_pvec.h)
   bool slab_free_default = false;  // cheap SDF: K1 writes no f32 slab, K4a evaluates all 8 corners (S2M_MESH_NO_SLAB is the default for this module)
   double ms_frontend = 0, ms_nvrtc = 0, ms_load = 0;
@@ -422,6 +423,7 @@ struct K1Plan {
   std::string packed_text;
   bool packed_sqrt = kK1PackedSqrtDefault;  // the refinement step of sqrt in f32x2 as well (S2M_K1_PACKED=2)
   bool heavy = false;                       // >= kK1PackedMinScore transcendental calls
+  int size = 0;                             // expression nodes of one evaluation (0: unknown, e.g. S2M_SRC_CUDA input)
   bool packed() const { return !packed_text.empty(); }
 };
 
@@ -437,6 +439,7 @@ K1Plan plan_k1(std::string packed_text) {
   const size_t at = packed_text.find("// s2m-packed-score: ");
   if (at != std::string::npos) sscanf(packed_text.c_str() + at + 21, "%d %d", &score, &size);
   plan.heavy = score >= kK1PackedMinScore;
+  plan.size = size;
   plan.slab_free = at != std::string::npos && !plan.heavy && size > 0 && size <= kSlabFreeMaxSize;
   bool use = kK1PackedDefault && (plan.heavy || size <= kK1PackedMaxTinySize);
   if (const char* e = getenv("S2M_K1_PACKED")) {
@@ -567,18 +570,33 @@ int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uin
 
   std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
                                    (flags & S2M_COMPILE_ALLOW_FMA) ? "--fmad=true" : "--fmad=false"};
-  if (const char* e = getenv("S2M_K1_UNROLL"))  // experiment knob, see kernels_jit.cuh
-    opts.push_back(std::string("-DS2M_K1_UNROLL=") + (atoi(e) == 1 ? "1" : "4"));
-  // a packed evaluation carries twice the state: for a heavy SDF one row per thread and a 48-register
-  // cap (5 resident blocks) measured best (mandelbulb: 62 registers / 4 blocks otherwise)
+  // Launch shape by the size of the SDF (measured on B200, profiles/r02_k1_ab.jsonl; every variant gives the same bits):
+  //  * heavy packed (>= 4 transcendental calls; mandelbulb): one row and one plane per thread, 48-register cap (5 resident
+  //    blocks; 62 registers / 4 blocks otherwise)
+  //  * tiny (<= 64 expression nodes; torus): two rows per thread and 16 planes marched per thread -- index, coordinate
+  //    and class overhead is a third of its instructions (K1 11.4 -> 8.7 ms at 2048^3)
+  //  * in between (p_key 206 nodes, martin_cube 683): one row per thread with a 64-register cap (two rows need 111 / 240
+  //    registers); up to 400 nodes 8 planes marched per thread (p_key K1 10.6 -> 6.6 ms at 1024^3), above that ONE inlined
+  //    copy of the SDF per thread instead of four (martin_cube 512^3: 5.0 -> 2.6 ms)
   const bool packed_heavy = plan.packed() && plan.heavy;
-  m->k1_rows = packed_heavy ? 1u : kK1RowsDefault;
+  const bool tiny = plan.size > 0 && plan.size <= kK1PackedMaxTinySize;
+  const bool mid = !plan.heavy && !tiny;
+  m->k1_rows = (packed_heavy || mid) ? 1u : kK1RowsDefault;
   if (const char* e = getenv("S2M_K1_ROWS")) m->k1_rows = atoi(e) == 2 ? 2u : 1u;  // experiment knob
   opts.push_back("-DS2M_K1_ROWS=" + std::to_string(m->k1_rows));
+  m->k1_zpt = tiny ? 16u : ((mid && plan.size > 0 && plan.size <= 400) ? 8u : 1u);
+  if (const char* e = getenv("S2M_K1_ZPT")) m->k1_zpt = (unsigned)std::max(1, std::min(64, atoi(e)));  // experiment knob
+  opts.push_back("-DS2M_K1_ZPT=" + std::to_string(m->k1_zpt));
+  if (const char* e = getenv("S2M_K1_UNROLL"))  // experiment knob, see kernels_jit.cuh
+    opts.push_back(std::string("-DS2M_K1_UNROLL=") + (atoi(e) == 1 ? "1" : "4"));
+  else if (mid && plan.size > 400)
+    opts.push_back("-DS2M_K1_UNROLL=1");
   if (const char* e = getenv("S2M_K1_MINBLOCKS"))  // experiment knob
     opts.push_back("-DS2M_K1_MINBLOCKS=" + std::to_string(std::max(1, std::min(8, atoi(e)))));
   else if (packed_heavy)
     opts.push_back("-DS2M_K1_MINBLOCKS=5");
+  else if (mid)
+    opts.push_back("-DS2M_K1_MINBLOCKS=4");
 
   const char* split = getenv("S2M_JIT_SPLIT");
   const int n_parts = (split && atoi(split) == 0) ? 1 : s2m_module::kMaxParts;
@@ -658,6 +676,7 @@ extern "C" int s2m_module_instantiate(const s2m_module* compiled, s2m_ctx* ctx, 
   m->n_parts = compiled->n_parts;
   for (int k = 0; k < compiled->n_parts; ++k) m->cubin[k] = compiled->cubin[k];
   m->k1_rows = compiled->k1_rows;
+  m->k1_zpt = compiled->k1_zpt;
   m->k1_packed = compiled->k1_packed;
   m->slab_free_default = compiled->slab_free_default;
   m->ms_frontend = compiled->ms_frontend;
@@ -973,6 +992,22 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
     }
     const uint32_t even = (r->nz + n_chunks - 1) / n_chunks;  // equal chunks instead of a short last one
     for (uint32_t z0 = 0; z0 < r->nz; z0 += even) chunks.push_back({z0, std::min(even, r->nz - z0)});
+    // Taper: what follows the LAST K1 launch -- K2, K3, K4a, K4b and the copy of the last chunk -- overlaps nothing, and
+    // it is proportional to that chunk's thickness (2 ms of a 25 ms slab at N = 2, 0.5 of 6 ms at N = 8).  The last
+    // chunk is therefore cut into 1/2, 1/4, 1/8, 1/8 of its thickness; every extra chunk costs five launches that run
+    // beside the next K1.  S2M_CHUNK_TAPER=0 keeps equal chunks.
+    static const bool taper = [] { const char* e = getenv("S2M_CHUNK_TAPER"); return !e || atoi(e) != 0; }();
+    if (taper && !dense && chunks.size() > 1 && chunks.back().nzc >= 32 && !getenv("S2M_NO_CHUNK_OVERLAP")) {
+      const Chunk last = chunks.back();
+      chunks.pop_back();
+      uint32_t z0 = last.z0, left = last.nzc;
+      for (int k = 0; k < 3 && left >= 16; ++k) {
+        const uint32_t t = (left + 1) / 2;
+        chunks.push_back({z0, t});
+        z0 += t; left -= t;
+      }
+      if (left) chunks.push_back({z0, left});
+    }
   }
   const size_t n_chunks = chunks.size();
   r->t.chunks = (uint32_t)n_chunks;
@@ -1027,7 +1062,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
     void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw};
     unsigned bx, by;
     k1_block_shape(&bx, &by);
-    dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), n_planes);
+    dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), (n_planes + m->k1_zpt - 1u) / m->k1_zpt);
     {
       SPAN_BEGIN(0, ps);
       if ((st2 = launch(m->k1, grid1, dim3(bx, by, 1), ps, a1, "s2m_k1_slab"))) return st2;

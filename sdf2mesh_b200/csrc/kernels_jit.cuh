@@ -93,6 +93,9 @@ __device__ __forceinline__ unsigned s2m_k1_class_byte(const float v[4], float ta
          (v[0] < -tau ? 16u : 0u) | (v[1] < -tau ? 32u : 0u) | (v[2] < -tau ? 64u : 0u) | (v[3] < -tau ? 128u : 0u);
 }
 
+#ifndef S2M_K1_ZPT
+#define S2M_K1_ZPT 1   /* planes a thread marches through (grid.z = ceil(planes / S2M_K1_ZPT)) */
+#endif
 #ifndef S2M_K1_MINBLOCKS
 #define S2M_K1_MINBLOCKS 1   /* resident 256-thread blocks per SM the register allocator must allow (8 = at most 32 registers) */
 #endif
@@ -101,26 +104,41 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
             float tau, uint2* __restrict__ cls, unsigned cls_words) {
   const unsigned x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
   const unsigned y = (blockIdx.y * blockDim.y + threadIdx.y) * (unsigned)S2M_K1_ROWS;
-  const unsigned pz = blockIdx.z;
   /* no early return: all 32 lanes take part in the shuffles below.  Groups of 8 lanes cover 32
    * consecutive corners of one row (blockDim.x is a multiple of 8, pitch_x of 32), so a group is
    * active or inactive as a whole. */
-  const bool active = x4 < g.pitch_x && y < g.rows && pz < n_planes;
-  const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
+  const bool active = x4 < g.pitch_x && y < g.rows;
   const unsigned lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31u;
-  const unsigned long long row = (unsigned long long)pz * g.rows + y;
   /* S2M_K1_UNROLL=1 keeps ONE inlined copy of the SDF per row in the kernel (4x less code); 4 =
    * unrolled (lets independent evaluations overlap; faster for the mandelbulb, measured). */
-  float cx[4], va[4];
+  float cx[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) cx[k] = g.bmin[0] + g.size[0] * (float)(x4 + (unsigned)k);
   const bool in_x = x4 <= g.res[0];
-  unsigned redo = 0;
   const float cy_a = g.bmin[1] + g.size[1] * (float)y;
-  s2m_k1_eval4(active && in_x, cx, cy_a, cz, va, redo, 0u);
 #if S2M_K1_ROWS == 2
   const bool active_b = active && y + 1u < g.rows;
   const float cy_b = g.bmin[1] + g.size[1] * (float)(y + 1u);
+#endif
+  /* For a tiny SDF a thread marches through S2M_K1_ZPT consecutive planes: its x and y coordinates, its indices and its
+   * activity are computed once (they are a third of the instructions of a torus evaluation), only z changes.  Not
+   * unrolled: one inlined copy of the SDF per row either way.  The plane range is the same for the whole block.
+   * Measured on B200 (profiles/r02_k1_ab.jsonl): torus 2048^3 K1 11.4 -> 8.7 ms at 16 planes; the mandelbulb and the
+   * primitive compositions lose 1-2 % (fewer, longer blocks), so they keep one plane per thread. */
+#if S2M_K1_ZPT > 1
+  const unsigned pz_end = min(n_planes, (blockIdx.z + 1u) * (unsigned)S2M_K1_ZPT);
+#pragma unroll 1
+  for (unsigned pz = blockIdx.z * (unsigned)S2M_K1_ZPT; pz < pz_end; ++pz) {
+#else
+  {  /* one plane per thread: no loop (a loop of one iteration still costs the larger kernels registers) */
+  const unsigned pz = blockIdx.z;
+#endif
+  const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
+  const unsigned long long row = (unsigned long long)pz * g.rows + y;
+  float va[4];
+  unsigned redo = 0;
+  s2m_k1_eval4(active && in_x, cx, cy_a, cz, va, redo, 0u);
+#if S2M_K1_ROWS == 2
   float vb[4];
   s2m_k1_eval4(active_b && in_x, cx, cy_b, cz, vb, redo, 2u);
 #endif
@@ -172,6 +190,7 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
     if (active_b && (lane & 3u) == 2u) reinterpret_cast<unsigned*>(cls)[at + 2ull * cls_words] = wb;
 #endif
   }
+  }  /* planes */
 }
 
 #endif  /* S2M_JIT_K1 */

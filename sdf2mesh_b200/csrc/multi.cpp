@@ -428,7 +428,7 @@ extern "C" int s2m_multi_mesh_run(s2m_multi* mc, const s2m_module* compiled, con
   ++mc->runs_on_partition;
   if (n > 1 && mc->runs_on_partition == 2 && !(mc->flags & (S2M_MULTI_EQUAL_SLABS | S2M_MULTI_NO_REBALANCE))) {
     std::vector<double> sec((size_t)n);
-    for (int k = 0; k < n; ++k) sec[(size_t)k] = begin_ms[(size_t)k] * 1e-3;
+    for (int k = 0; k < n; ++k) sec[(size_t)k] = (begin_ms[(size_t)k] + finish_ms[(size_t)k]) * 1e-3;   // until the slab is complete in host memory
     std::vector<uint32_t> nb((size_t)n + 1);
     if (s2m_rebalance_slices(mc->bounds.data(), n, sec.data(), mc->cost.empty() ? nullptr : mc->cost.data(), (int)mc->cost.size(), nb.data()) == S2M_OK) mc->bounds = nb;
   }

@@ -19,7 +19,8 @@ sys.path.insert(0, ROOT)
 import sdf2mesh_b200 as s2m  # noqa: E402
 
 W = {"mandelmesh2048": ("mandelmesh.frag", 2048, 5.0), "mandelmesh1024": ("mandelmesh.frag", 1024, 5.0), "torus2048": ("torus.sdf3d", 2048, 2.0),
-     "martin_cube1024": ("martin_cube.sdf3d", 1024, 2.0), "p_key1024": ("p_key.sdf3d", 1024, 20.0)}
+     "martin_cube1024": ("martin_cube.sdf3d", 1024, 2.0), "martin_cube512": ("martin_cube.sdf3d", 512, 2.0), "p_key1024": ("p_key.sdf3d", 1024, 20.0),
+     "p_key1024_b2": ("p_key.sdf3d", 1024, 2.0)}
 
 
 def shader(f):
@@ -49,7 +50,7 @@ def main():
     for spec in specs:
         wl, variants, *extra = spec.split(":")
         knobs = dict(kv.split("=") for kv in extra[0].split(",")) if extra else {}
-        for k in ("S2M_K1_MINBLOCKS", "S2M_K1_ROWS", "S2M_K1_UNROLL", "S2M_K1_BLOCK"):
+        for k in ("S2M_K1_MINBLOCKS", "S2M_K1_ROWS", "S2M_K1_UNROLL", "S2M_K1_BLOCK", "S2M_K1_ZPT", "S2M_SLAB"):
             os.environ.pop(k, None)
         os.environ.update(knobs)
         f, res, bounds = W[wl]
