@@ -145,6 +145,7 @@ extern "C" {
     pub fn s2m_module_cubin_part(m: *const s2m_module, part: c_int, data: *mut *const c_void, size: *mut usize) -> c_int;
     pub fn s2m_module_compile_ms(m: *const s2m_module, which: c_int) -> c_double;
     pub fn s2m_module_is_packed(m: *const s2m_module) -> c_int;
+    pub fn s2m_module_uid(m: *const s2m_module) -> u64;
     pub fn s2m_module_prefers_no_slab(m: *const s2m_module) -> c_int;
     pub fn s2m_module_free(m: *mut s2m_module);
 

@@ -289,6 +289,9 @@ int s2m_rebalance_slices(const uint32_t* bounds, int world, const double* second
 int s2m_eval_points(s2m_ctx* ctx, s2m_module* m, const float* xyz, uint64_t n, float* out);
 /* 1 if K1 of this module evaluates corner pairs in packed f32x2 arithmetic (csrc/s2m_pvec.h) */
 int s2m_module_is_packed(const s2m_module* m);
+/* a number no other module of this process has (an instance made by s2m_module_instantiate keeps the number of the module
+ * it was made from): caches keyed by it survive a module being freed and another one landing at the same address */
+uint64_t s2m_module_uid(const s2m_module* m);
 /* 1 if this module's SDF is cheap enough that meshing defaults to the slab-free form (S2M_MESH_NO_SLAB) */
 int s2m_module_prefers_no_slab(const s2m_module* m);
 /* FP32 FMA throughput of the device in TFLOP/s, measured with dependent-chain kernels (no memory traffic, ~2 ms each, best of 3):

@@ -133,6 +133,7 @@ SYMBOLS = {
     "s2m_write_mesh_arrays": (ctypes.c_int, [_P, ctypes.c_int, _S, ctypes.c_int]),
     "s2m_eval_points": (ctypes.c_int, [_P, _P, _P, ctypes.c_uint64, _P]),
     "s2m_module_is_packed": (ctypes.c_int, [_P]),
+    "s2m_module_uid": (ctypes.c_uint64, [_P]),
     "s2m_module_prefers_no_slab": (ctypes.c_int, [_P]),
     "s2m_measure_fp32_peak": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
     "s2m_eval_pairs": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_uint64, _P, _P, _P]),

@@ -18,6 +18,7 @@
 #include <nvrtc.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <sys/mman.h>
@@ -382,6 +383,8 @@ struct s2m_module {
   bool k1_packed = false;  // K1 evaluates corner pairs in f32x2 arithmetic (s2m_pvec.h)
   bool slab_free_default = false;  // cheap SDF: K1 writes no f32 slab, K4a evaluates all 8 corners (S2M_MESH_NO_SLAB is the default for this module)
   double ms_frontend = 0, ms_nvrtc = 0, ms_load = 0;
+  uint64_t uid = next_uid();   // s2m_module_uid; s2m_module_instantiate copies the number of the compiled module
+  static uint64_t next_uid() { static std::atomic<uint64_t> n{0}; return ++n; }
 };
 
 namespace {
@@ -677,6 +680,7 @@ extern "C" int s2m_module_instantiate(const s2m_module* compiled, s2m_ctx* ctx, 
   for (int k = 0; k < compiled->n_parts; ++k) m->cubin[k] = compiled->cubin[k];
   m->k1_rows = compiled->k1_rows;
   m->k1_zpt = compiled->k1_zpt;
+  m->uid = compiled->uid;
   m->k1_packed = compiled->k1_packed;
   m->slab_free_default = compiled->slab_free_default;
   m->ms_frontend = compiled->ms_frontend;
@@ -1359,6 +1363,7 @@ extern "C" int s2m_eval_points(s2m_ctx* c, s2m_module* m, const float* xyz, uint
 }
 
 extern "C" int s2m_module_is_packed(const s2m_module* m) { return m && m->k1_packed ? 1 : 0; }
+extern "C" uint64_t s2m_module_uid(const s2m_module* m) { return m ? m->uid : 0; }
 extern "C" int s2m_module_prefers_no_slab(const s2m_module* m) { return m && m->slab_free_default ? 1 : 0; }
 
 extern "C" int s2m_measure_fp32_peak(s2m_ctx* c, double out_tflops[3]) {

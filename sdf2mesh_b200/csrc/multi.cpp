@@ -172,10 +172,12 @@ struct s2m_multi {
   std::vector<cudaStream_t> xs;                        // per device: the stream the exchange runs on
   bool use_nccl = false;
   int nccl_version = 0;
-  // modules instantiated per device, keyed by the compiled module they came from
-  std::map<const s2m_module*, std::vector<s2m_module*>> modules;
+  // modules instantiated per device, keyed by s2m_module_uid of the compiled module they came from (not by its address:
+  // the caller may free it and compile another one that lands at the same address); the oldest of more than 8 is dropped
+  std::map<uint64_t, std::vector<s2m_module*>> modules;
+  std::vector<uint64_t> module_order;
   // partition state for the last (module, grid) seen
-  const s2m_module* part_module = nullptr;
+  uint64_t part_module = 0;
   s2m_mesh_params part_params{};
   std::vector<uint32_t> bounds;
   std::vector<double> cost;
@@ -339,7 +341,8 @@ extern "C" int s2m_multi_mesh_run(s2m_multi* mc, const s2m_module* compiled, con
     return S2M_OK;
   };
   // ---- modules: the compiled cubins loaded once per device
-  auto it = mc->modules.find(compiled);
+  const uint64_t uid = s2m_module_uid(compiled);
+  auto it = mc->modules.find(uid);
   if (it == mc->modules.end()) {
     std::vector<s2m_module*> mods((size_t)n, nullptr);
     mc->run_on_all([&](int k) {
@@ -347,11 +350,18 @@ extern "C" int s2m_multi_mesh_run(s2m_multi* mc, const s2m_module* compiled, con
       if (status[(size_t)k]) errors[(size_t)k] = s2m_last_error();
     });
     if (int st = first_error("s2m_module_instantiate")) { for (s2m_module* m : mods) if (m) s2m_module_free(m); return st; }
-    it = mc->modules.emplace(compiled, std::move(mods)).first;
+    if (mc->module_order.size() >= 8) {
+      const uint64_t old = mc->module_order.front();
+      mc->module_order.erase(mc->module_order.begin());
+      for (s2m_module* m : mc->modules[old]) if (m) s2m_module_free(m);
+      mc->modules.erase(old);
+    }
+    mc->module_order.push_back(uid);
+    it = mc->modules.emplace(uid, std::move(mods)).first;
   }
   std::vector<s2m_module*>& mods = it->second;
   // ---- partition: cost probe on the first GPU when the (module, grid) changes
-  if (mc->part_module != compiled || !same_grid(mc->part_params, *p) || mc->bounds.size() != (size_t)n + 1) {
+  if (mc->part_module != uid || !same_grid(mc->part_params, *p) || mc->bounds.size() != (size_t)n + 1) {
     mc->bounds.assign((size_t)n + 1, 0);
     mc->cost.clear();
     if (n > 1 && !(mc->flags & S2M_MULTI_EQUAL_SLABS)) {
@@ -360,7 +370,7 @@ extern "C" int s2m_multi_mesh_run(s2m_multi* mc, const s2m_module* compiled, con
     }
     int st = s2m_partition_slices(n_slices, n, mc->cost.empty() ? nullptr : mc->cost.data(), (int)mc->cost.size(), mc->bounds.data());
     if (st) return st;
-    mc->part_module = compiled; mc->part_params = *p; mc->runs_on_partition = 0;
+    mc->part_module = uid; mc->part_params = *p; mc->runs_on_partition = 0;
   }
   // ---- the run: begin on every GPU, one all-gather of the vertex counts, finish with the slab's base
   std::vector<double> begin_ms((size_t)n, 0.0), exch_ms((size_t)n, 0.0), finish_ms((size_t)n, 0.0);

@@ -65,13 +65,21 @@ class Module:
         check(lib().s2m_module_instantiate(self._h, ctx._h, ctypes.byref(m._h)))
         return m
 
-    def __del__(self):
+    def close(self):
         if getattr(self, "_h", None):
-            try:
-                lib().s2m_module_free(self._h)
-            except Exception:
-                pass
+            lib().s2m_module_free(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def uid(self) -> int:
+        """s2m_module_uid: unique in this process; an instance keeps the number of the module it was made from"""
+        return int(lib().s2m_module_uid(self._h))
 
     @property
     def log(self) -> str:

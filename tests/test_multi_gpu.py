@@ -105,6 +105,29 @@ def test_multi_rejects_what_it_cannot_do(ctx):
     mc4.close()
 
 
+def test_multi_context_with_changing_modules(ctx):
+    """the per-device module cache is keyed by s2m_module_uid, not by the address of the compiled module: a module that is
+    freed and another one compiled in its place (often at the same address) must not run the old kernels"""
+    mc = s2m.MultiContext([0, 0], _capi.MULTI_NO_NCCL)
+    p, _ = s2m.params_from_cli(64, 4.0)
+    seen = set()
+    for name in ("torus", "p_key", "torus", "mandelbulb", "p_key", "martin_cube"):
+        compiled = load_example_shader(name).create_shader_module(None)
+        seen.add(compiled.uid)
+        parts = mc.mesh_run(compiled, p)
+        o = oracle.mesh_run(name, 64, 4.0)
+        pos, nrm, keys, nib, quads, ninv = assemble(parts)
+        assert np.array_equal(keys, o.keys) and np.array_equal(quads, o.quads), name
+        assert np.array_equal(pos.view(np.uint32), np.asarray(o.positions, np.float32).view(np.uint32)), name
+        for r in parts:
+            r.free()
+        o.free()
+        compiled.close()
+        del compiled
+    assert len(seen) == 6
+    mc.close()
+
+
 @pytest.mark.parametrize("key", ["mandelbulb_r512_b5_f0", "torus_r512_b2_f0"])
 def test_nccl_count_exchange_over_all_gpus(key):
     """>= 2 GPUs: counts through ncclAllGather on communicators from ncclCommInitAll; golden digest of the assembled mesh"""
