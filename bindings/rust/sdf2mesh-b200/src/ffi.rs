@@ -39,6 +39,7 @@ pub const S2M_MESH_CONSISTENT_CORNERS: u32 = 64; // with ALL_SLICES: the waterti
 pub const S2M_MESH_QUADS_U32: u32 = 128; // indices as u32 in quads32 -- what Quad(u32, u32, u32, u32) wants anyway
 pub const S2M_MESH_NO_SLAB: u32 = 256; // slab-free form (the default for cheap SDFs)
 pub const S2M_MESH_RELATIVE_QUADS: u32 = 512; // global index = quad value + quad_index_add (wrapping)
+pub const S2M_MESH_TIMINGS: u32 = 1024;
 pub const S2M_MULTI_NO_NCCL: u32 = 1;
 pub const S2M_MULTI_EQUAL_SLABS: u32 = 2;
 pub const S2M_MULTI_NO_REBALANCE: u32 = 4;

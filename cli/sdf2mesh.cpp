@@ -265,6 +265,7 @@ int main(int argc, char** argv) {
   if (a.exact_dense) params.flags |= S2M_MESH_EXACT_DENSE;
   if (a.no_normals) params.flags |= S2M_MESH_NO_NORMALS;
   params.flags |= S2M_MESH_KEEP_INVALID;  // so that the reference's per-quad warnings can be printed
+  if (a.stats) params.flags |= S2M_MESH_TIMINGS;
 
   if (a.gpus > 1) return run_multi_gpu(a, params);
 

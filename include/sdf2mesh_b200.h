@@ -147,6 +147,9 @@ void s2m_module_free(s2m_module* m);
 #define S2M_MESH_NO_SLAB 256u        /* slab-free form: K1 writes only the 2-bit corner classes (0.25 B per corner instead of 4.25), K4a
                                        evaluates all 8 corners of every candidate cell.  The default for SDFs that are cheap to evaluate
                                        (s2m_module_prefers_no_slab); same results either way. */
+#define S2M_MESH_TIMINGS 1024u        /* fill the per-kernel fields of s2m_timings (k1_slab_ms ... d2h_ms) from CUDA-event spans around every
+                                       launch.  Off by default: the records keep consecutive kernels from overlapping head and tail and
+                                       reading them back costs ~0.35 ms per run; device_ms / total_ms / host_wall_ms are always measured. */
 #define S2M_MESH_RELATIVE_QUADS 512u /* quads keep the slab-relative indices the device wrote: global index = value + quad_index_add
                                        (s2m_result_info; wrapping in the index width -- a vertex of the halo slice is "negative").
                                        s2m_mesh_finish then only waits for the copies instead of adding the base on the host; the
@@ -252,7 +255,7 @@ int s2m_read_device_words(s2m_ctx* ctx, const void* device_words, uint32_t n, ui
  * The reference drives one device from one thread (main.rs:180-196, :298-356).  s2m_multi holds one s2m_ctx per device
  * ordinal, one host thread per device (kept alive between runs) and one NCCL communicator per device (ncclCommInitAll;
  * libnccl.so.2 is loaded with dlopen).  s2m_multi_mesh_run cuts the grid into contiguous z-slabs balanced by cost
- * (s2m_cost_probe on the first device, refined once from the measured times of the second run on the same SDF and
+ * (s2m_cost_probe on the first device, refined from the measured times of the second and the fourth run on the same SDF and
  * grid), meshes every slab with s2m_mesh_begin on its GPU -- each recomputing the slice below its slab as halo --
  * exchanges the per-slab vertex counts with ONE ncclAllGather (8 bytes per rank) and calls s2m_mesh_finish with the
  * exclusive prefix.  parts_out receives n results in z order (S2M_MESH_RELATIVE_QUADS form: global index = quad value +

@@ -24,6 +24,7 @@ MESH_CONSISTENT_CORNERS = 64
 MESH_QUADS_U32 = 128
 MESH_NO_SLAB = 256
 MESH_RELATIVE_QUADS = 512
+MESH_TIMINGS = 1024
 
 
 class S2mError(RuntimeError):

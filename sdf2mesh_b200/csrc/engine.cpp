@@ -790,6 +790,7 @@ struct s2m_result {
   size_t ev_used = 0;              // events taken from the ctx pool by this run
   struct Span { int kind; size_t e0, e1; };  // kind: 0 K1, 1 K2, 2 K3, 3 K4a, 4 K4b, 5 copy
   std::vector<Span> spans;
+  bool want_spans = false;         // S2M_MESH_TIMINGS / S2M_TRACE
   bool finished = false;
   bool quads_u32() const { return (params.flags & S2M_MESH_QUADS_U32) != 0; }
   bool relative() const { return (params.flags & S2M_MESH_RELATIVE_QUADS) != 0; }
@@ -843,10 +844,13 @@ size_t take_event(s2m_ctx* c, s2m_result* r) {
   }
   return r->ev_used++;
 }
+// per-kernel CUDA-event spans: only with S2M_MESH_TIMINGS (or S2M_TRACE).  Two event records around every launch keep
+// consecutive kernels of a stream from overlapping head and tail, and reading ~70 event pairs back costs 0.35 ms per run.
 #define SPAN_BEGIN(kind_, stream_) \
-  const size_t span_e0__ = take_event(c, r); CUDA_TRY(cudaEventRecord(c->ev_pool[span_e0__], stream_)); const int span_kind__ = kind_
+  size_t span_e0__ = 0; const int span_kind__ = kind_; \
+  if (r->want_spans) { span_e0__ = take_event(c, r); CUDA_TRY(cudaEventRecord(c->ev_pool[span_e0__], stream_)); }
 #define SPAN_END(stream_) \
-  do { const size_t e1__ = take_event(c, r); CUDA_TRY(cudaEventRecord(c->ev_pool[e1__], stream_)); r->spans.push_back({span_kind__, span_e0__, e1__}); } while (0)
+  do { if (r->want_spans) { const size_t e1__ = take_event(c, r); CUDA_TRY(cudaEventRecord(c->ev_pool[e1__], stream_)); r->spans.push_back({span_kind__, span_e0__, e1__}); } } while (0)
 
 // Device -> pinned host copies of what the chunks up to now have added: vertices [copied_v, vert_total) (local
 // indices, the halo slice's first and never copied) and quads [copied_q, quad_total).  The pinned regions grow
@@ -918,6 +922,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
   std::unique_ptr<s2m_result, void (*)(s2m_result*)> rp(new s2m_result(), [](s2m_result* x) { s2m_result_free(x); });
   s2m_result* r = rp.get();
   r->mod = m; r->params = *p;
+  r->want_spans = (p->flags & S2M_MESH_TIMINGS) != 0 || getenv("S2M_TRACE") != nullptr;
   int st = make_grid(p, &r->grid);
   if (st) return st;
   const GridDev& g = r->grid;
@@ -1045,6 +1050,7 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
   cudaStream_t ps = pipelined ? c->prod_stream : s;   // producer stream (K1, K2)
   if (pipelined) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_BEGIN], 0));  // after the counter reset
   const unsigned cls_words = g.pitch_x / 32u;
+  static const bool carry_planes = [] { const char* e = getenv("S2M_CARRY_PLANES"); return !e || atoi(e) != 0; }();
   // K1 of chunk ci into slab / class-plane buffer ci % 2 (buffer 0 when not pipelined), on the producer stream
   auto produce = [&](size_t ci) -> int {
     const Chunk ch = chunks[ci];
@@ -1062,8 +1068,21 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
       cls = cls_buf.p;
     }
     if (pipelined && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_CONSUMED0 + buf], 0));  // K2 and K4a of chunk ci-2 have read this buffer
+    // Consecutive chunks share one corner plane (the top of chunk ci-1 is the bottom of chunk ci): K1's plane-0 blocks
+    // copy it from the previous chunk's buffers instead of evaluating it again (kernels_jit.cuh).  (Two
+    // cudaMemcpyAsync in front of the launch did the same but left a 30 us gap on the producer stream, as much as
+    // they saved.)  Same values either way; S2M_CARRY_PLANES=0 evaluates every plane.
+    const float* carry_slab = nullptr;
+    const void* carry_cls = nullptr;
+    if (ci >= 1 && carry_planes) {
+      const int pbuf = pipelined ? (int)((ci - 1) & 1) : 0;
+      const size_t src_plane = chunks[ci - 1].nzc;
+      if (slab) carry_slab = (pbuf ? c->slab2 : c->slab).as<float>() + src_plane * g.plane_stride;
+      if (cls) carry_cls = static_cast<const char*>((pbuf ? c->cls2 : c->cls).p) + src_plane * (size_t)g.rows * cls_words * 8;
+      if (!pipelined) { carry_slab = nullptr; carry_cls = nullptr; }   // one buffer: source and destination planes would be the same launch's
+    }
     float tau_arg = tau;
-    void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw};
+    void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw, &carry_slab, &carry_cls};
     unsigned bx, by;
     k1_block_shape(&bx, &by);
     dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), (n_planes + m->k1_zpt - 1u) / m->k1_zpt);
@@ -1307,6 +1326,7 @@ extern "C" int s2m_mesh_finish(s2m_result* r, int64_t global_vertex_base) {
   }
   r->t.host_wall_ms = now_ms() - r->wall0;
   finalize_timings(c, r);
+  tr.mark("finish: timings read");
   r->finished = true;
   c->busy = false;
   return S2M_OK;
@@ -1436,7 +1456,9 @@ extern "C" int s2m_debug_slab_plane(s2m_ctx* c, s2m_module* m, const s2m_mesh_pa
   unsigned first_plane = plane, n_planes = 1, cls_words = 0;
   float tau_arg = 0.0f;
   void* cls = nullptr;
-  void* a1[] = {&g, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words};
+  const float* carry_slab = nullptr;
+  const void* carry_cls = nullptr;
+  void* a1[] = {&g, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words, &carry_slab, &carry_cls};
   unsigned bx, by;
   k1_block_shape(&bx, &by);
   if ((st = launch(m->k1, dim3((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), 1), dim3(bx, by, 1), c->stream, a1, "s2m_k1_slab"))) return st;

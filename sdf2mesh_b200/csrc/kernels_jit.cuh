@@ -101,7 +101,8 @@ __device__ __forceinline__ unsigned s2m_k1_class_byte(const float v[4], float ta
 #endif
 extern "C" __global__ void __launch_bounds__(256, S2M_K1_MINBLOCKS)
 s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned n_planes,
-            float tau, uint2* __restrict__ cls, unsigned cls_words) {
+            float tau, uint2* __restrict__ cls, unsigned cls_words,
+            const float* __restrict__ carry_slab, const uint2* __restrict__ carry_cls) {
   const unsigned x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
   const unsigned y = (blockIdx.y * blockDim.y + threadIdx.y) * (unsigned)S2M_K1_ROWS;
   /* no early return: all 32 lanes take part in the shuffles below.  Groups of 8 lanes cover 32
@@ -133,8 +134,28 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   {  /* one plane per thread: no loop (a loop of one iteration still costs the larger kernels registers) */
   const unsigned pz = blockIdx.z;
 #endif
-  const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
   const unsigned long long row = (unsigned long long)pz * g.rows + y;
+  /* Consecutive z-chunks share one corner plane: the top plane of the previous chunk (carry_*: that plane in the
+   * previous chunk's buffers) is this launch's plane 0.  Its blocks copy it instead of evaluating it again -- same
+   * values, a plane's worth of SDF evaluations saved per chunk boundary (3 % of K1 for a 146-slice slab in 6 chunks). */
+  if (pz == 0u && (carry_slab != nullptr || carry_cls != nullptr)) {
+    if (slab != nullptr) {
+      if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (unsigned long long)y * g.pitch_x + x4));
+#if S2M_K1_ROWS == 2
+      if (active_b) *reinterpret_cast<float4*>(slab + (row + 1ull) * g.pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (y + 1ull) * g.pitch_x + x4));
+#endif
+    }
+    if (cls != nullptr) {   /* the lanes that store a class word in the epilogue below copy the same word */
+      const unsigned long long at = ((unsigned long long)y * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u);
+#if S2M_K1_ROWS == 1
+      if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at);
+#else
+      if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at);
+      if (active_b && (lane & 3u) == 2u) reinterpret_cast<unsigned*>(cls)[at + 2ull * cls_words] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at + 2ull * cls_words);
+#endif
+    }
+  } else {
+  const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
   float va[4];
   unsigned redo = 0;
   s2m_k1_eval4(active && in_x, cx, cy_a, cz, va, redo, 0u);
@@ -190,6 +211,7 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
     if (active_b && (lane & 3u) == 2u) reinterpret_cast<unsigned*>(cls)[at + 2ull * cls_words] = wb;
 #endif
   }
+  }  /* evaluated plane */
   }  /* planes */
 }
 

@@ -434,9 +434,10 @@ extern "C" int s2m_multi_mesh_run(s2m_multi* mc, const s2m_module* compiled, con
   t.n = n;
   t.wall_ms = t_run1 - t_run0;
   for (int k = 0; k < n && k < 64; ++k) { t.begin_ms[k] = begin_ms[(size_t)k]; t.exchange_ms[k] = exch_ms[(size_t)k]; t.finish_ms[k] = finish_ms[(size_t)k]; }
-  // ---- one refinement of the boundaries, from the second run on a partition (the first pays for allocations)
+  // ---- the boundaries are refined from the second and the fourth run on a partition (the first pays for allocations,
+  //      the run after a refinement for re-allocations)
   ++mc->runs_on_partition;
-  if (n > 1 && mc->runs_on_partition == 2 && !(mc->flags & (S2M_MULTI_EQUAL_SLABS | S2M_MULTI_NO_REBALANCE))) {
+  if (n > 1 && (mc->runs_on_partition == 2 || mc->runs_on_partition == 4) && !(mc->flags & (S2M_MULTI_EQUAL_SLABS | S2M_MULTI_NO_REBALANCE))) {
     std::vector<double> sec((size_t)n);
     for (int k = 0; k < n; ++k) sec[(size_t)k] = (begin_ms[(size_t)k] + finish_ms[(size_t)k]) * 1e-3;   // until the slab is complete in host memory
     std::vector<uint32_t> nb((size_t)n + 1);

@@ -54,7 +54,7 @@ def main():
             os.environ.pop(k, None)
         os.environ.update(knobs)
         f, res, bounds = W[wl]
-        params, _ = s2m.params_from_cli(res, bounds, flags=s2m.MESH_QUADS_U32)
+        params, _ = s2m.params_from_cli(res, bounds, flags=s2m.MESH_QUADS_U32 | s2m.MESH_TIMINGS)
         for v in variants.split(","):
             if v == "d":  # the engine's default policy
                 os.environ.pop("S2M_K1_PACKED", None)

@@ -22,7 +22,8 @@ def main():
     runs = 0
     for mod, bounds in ((torus, 2.0), (bulb, 5.0)):
         for dims in ((40, 40, 40), (70, 45, 33)):
-            for flags in (0, s2m.MESH_CLASSIFY_FROM_SLAB, s2m.MESH_EXACT_DENSE, s2m.MESH_ALL_SLICES | s2m.MESH_KEEP_CANDIDATES | s2m.MESH_KEEP_INVALID):
+            for flags in (0, s2m.MESH_CLASSIFY_FROM_SLAB, s2m.MESH_EXACT_DENSE, s2m.MESH_ALL_SLICES | s2m.MESH_KEEP_CANDIDATES | s2m.MESH_KEEP_INVALID,
+                          s2m.MESH_NO_SLAB | s2m.MESH_QUADS_U32, s2m.MESH_RELATIVE_QUADS):
                 if flags == s2m.MESH_EXACT_DENSE and dims[0] > 40:
                     continue
                 for budget in (0, (dims[0] + 32) * (dims[1] + 1) * 4 * 4):
@@ -46,6 +47,16 @@ def main():
             runs += 1
         mod.eval_points(np.zeros((1000, 3), np.float32))
         s2m.cost_probe(ctx, mod, p, 8)
+    # several slabs behind s2m_multi (sharing this device; counts through host memory)
+    from sdf2mesh_b200 import _capi
+    mc = s2m.MultiContext([0, 0, 0], _capi.MULTI_NO_NCCL)
+    compiled = s2m.Sdf3DShader.from_glsl_fragment_shader(os.path.join(ex, "mandelmesh.frag"), "sdf").create_shader_module(None)
+    p, _ = s2m.params_from_cli(64, 5.0)
+    for _ in range(3):
+        for r in mc.mesh_run(compiled, p):
+            r.free()
+        runs += 1
+    mc.close()
     print("sanitize_run: %d runs ok" % runs)
     ctx.close()
 
