@@ -99,6 +99,28 @@ __device__ __forceinline__ unsigned s2m_k1_class_byte(const float v[4], float ta
 #ifndef S2M_K1_MINBLOCKS
 #define S2M_K1_MINBLOCKS 1   /* resident 256-thread blocks per SM the register allocator must allow (8 = at most 32 registers) */
 #endif
+/* Consecutive z-chunks share one corner plane: the top plane of the previous chunk (carry_*: that plane in the
+ * previous chunk's buffers) is this launch's plane 0.  Its blocks copy it instead of evaluating it again -- same
+ * values, a plane's worth of SDF evaluations saved per chunk boundary (3 % of K1 for a 146-slice slab in 6 chunks).
+ * Kept out of the plane loop: inside it the copy cost the tiny kernels 11 registers (torus 58 -> 69). */
+__device__ __noinline__ void s2m_k1_carry_plane(const S2mGrid& g, float* __restrict__ slab, uint2* __restrict__ cls, unsigned cls_words,
+                                                const float* __restrict__ carry_slab, const uint2* __restrict__ carry_cls,
+                                                unsigned x4, unsigned y, unsigned lane, bool active, bool active_b) {
+  if (slab != nullptr && carry_slab != nullptr) {
+    if (active) *reinterpret_cast<float4*>(slab + (unsigned long long)y * g.pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (unsigned long long)y * g.pitch_x + x4));
+    if (active_b) *reinterpret_cast<float4*>(slab + (y + 1ull) * g.pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (y + 1ull) * g.pitch_x + x4));
+  }
+  if (cls != nullptr && carry_cls != nullptr) {   /* the lanes that store a class word in the epilogue copy the same word */
+    const unsigned long long at = ((unsigned long long)y * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u);
+#if S2M_K1_ROWS == 1
+    if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at);
+#else
+    if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at);
+    if (active_b && (lane & 3u) == 2u) reinterpret_cast<unsigned*>(cls)[at + 2ull * cls_words] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at + 2ull * cls_words);
+#endif
+  }
+}
+
 extern "C" __global__ void __launch_bounds__(256, S2M_K1_MINBLOCKS)
 s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned n_planes,
             float tau, uint2* __restrict__ cls, unsigned cls_words,
@@ -126,35 +148,21 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
    * unrolled: one inlined copy of the SDF per row either way.  The plane range is the same for the whole block.
    * Measured on B200 (profiles/r02_k1_ab.jsonl): torus 2048^3 K1 11.4 -> 8.7 ms at 16 planes; the mandelbulb and the
    * primitive compositions lose 1-2 % (fewer, longer blocks), so they keep one plane per thread. */
+  const bool carry = blockIdx.z == 0u && (carry_slab != nullptr || carry_cls != nullptr);   /* uniform over the block */
+#if S2M_K1_ROWS == 2
+  if (carry) s2m_k1_carry_plane(g, slab, cls, cls_words, carry_slab, carry_cls, x4, y, lane, active, active_b);
+#else
+  if (carry) s2m_k1_carry_plane(g, slab, cls, cls_words, carry_slab, carry_cls, x4, y, lane, active, false);
+#endif
 #if S2M_K1_ZPT > 1
   const unsigned pz_end = min(n_planes, (blockIdx.z + 1u) * (unsigned)S2M_K1_ZPT);
 #pragma unroll 1
-  for (unsigned pz = blockIdx.z * (unsigned)S2M_K1_ZPT; pz < pz_end; ++pz) {
+  for (unsigned pz = blockIdx.z * (unsigned)S2M_K1_ZPT + (carry ? 1u : 0u); pz < pz_end; ++pz) {
 #else
-  {  /* one plane per thread: no loop (a loop of one iteration still costs the larger kernels registers) */
+  if (!carry) {  /* one plane per thread: no loop (a loop of one iteration still costs the larger kernels registers) */
   const unsigned pz = blockIdx.z;
 #endif
   const unsigned long long row = (unsigned long long)pz * g.rows + y;
-  /* Consecutive z-chunks share one corner plane: the top plane of the previous chunk (carry_*: that plane in the
-   * previous chunk's buffers) is this launch's plane 0.  Its blocks copy it instead of evaluating it again -- same
-   * values, a plane's worth of SDF evaluations saved per chunk boundary (3 % of K1 for a 146-slice slab in 6 chunks). */
-  if (pz == 0u && (carry_slab != nullptr || carry_cls != nullptr)) {
-    if (slab != nullptr) {
-      if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (unsigned long long)y * g.pitch_x + x4));
-#if S2M_K1_ROWS == 2
-      if (active_b) *reinterpret_cast<float4*>(slab + (row + 1ull) * g.pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (y + 1ull) * g.pitch_x + x4));
-#endif
-    }
-    if (cls != nullptr) {   /* the lanes that store a class word in the epilogue below copy the same word */
-      const unsigned long long at = ((unsigned long long)y * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u);
-#if S2M_K1_ROWS == 1
-      if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at);
-#else
-      if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at);
-      if (active_b && (lane & 3u) == 2u) reinterpret_cast<unsigned*>(cls)[at + 2ull * cls_words] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at + 2ull * cls_words);
-#endif
-    }
-  } else {
   const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
   float va[4];
   unsigned redo = 0;
@@ -211,7 +219,6 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
     if (active_b && (lane & 3u) == 2u) reinterpret_cast<unsigned*>(cls)[at + 2ull * cls_words] = wb;
 #endif
   }
-  }  /* evaluated plane */
   }  /* planes */
 }
 

@@ -1,0 +1,17 @@
+# ncu evidence with the final kernels: K1 counters per workload, launch list, --set full captures
+set -x
+B="python bench.py --steps 1 --warmup 1 --no-verify --no-cpu-baseline --no-other-workloads"
+M=$(python -c "import sys; sys.path.insert(0,'tools'); import ncu_k1_counters as n; print(n.METRICS)")
+timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_packed_gpu.py tests/test_multi_gpu.py -q -m gpu -x --timeout 900 2>&1 | tail -3
+timeout 300 python bench.py --no-cpu-baseline --workload torus2048 --no-other-workloads > gpurun_out/bench_j_torus.json 2> gpurun_out/bench_j.err; tail -c 200 gpurun_out/bench_j_torus.json
+for wl in mandelmesh2048 torus2048 martin_cube512 p_key1024 p_key1024_b20 torus128; do
+  timeout 600 ncu --metrics $M --clock-control none -k regex:s2m_k1_slab --csv --log-file gpurun_out/k1cnt_$wl.csv $B --workload $wl > /dev/null 2> gpurun_out/k1cnt_$wl.err
+  wc -l gpurun_out/k1cnt_$wl.csv
+done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_mandelmesh2048.csv python bench.py --steps 2 --warmup 1 --no-verify --no-cpu-baseline --no-other-workloads > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:s2m_k1_slab -s 17 -c 1 -o gpurun_out/r02_k1_mandel $B > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:s2m_k1_slab -s 12 -c 1 -o gpurun_out/r02_k1_torus $B --workload torus2048 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:s2m_k1_slab -s 2 -c 1 -o gpurun_out/r02_k1_martin $B --workload martin_cube512 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:s2m_k1_slab -s 12 -c 1 -o gpurun_out/r02_k1_pkey $B --workload p_key1024 > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k2_classify|k3_compact|s2m_k4_vertices|k4_quads" -s 24 -c 4 -o gpurun_out/r02_k234 $B > /dev/null 2>&1
+ls -la gpurun_out/*.ncu-rep

@@ -3,11 +3,12 @@
 
     ncu --metrics <METRICS below> --clock-control none -k regex:s2m_k1_slab --csv --log-file gpurun_out/k1cnt_<wl>.csv \\
         python bench.py --workload <wl> --steps 1 --warmup 1 --no-verify --no-cpu-baseline --no-other-workloads
-    python tools/ncu_k1_counters.py <wl>=gpurun_out/k1cnt_<wl>.csv ... > profiles/k1_counters.json
 
-That bench command runs 4 meshing steps (1 warm-up, 1 timed, 2 serialised); a step's launches are found from their
-grid depth (planes = slices + 1 per z-chunk, the chunks of a step add up to <resolution> - 1 slices) and the launches of
-the SECOND step are summed.
+    python tools/ncu_k1_counters.py <wl>=gpurun_out/k1cnt_<wl>.csv:<K1 launches per step> ...
+
+That bench command runs 5 meshing steps (warm-up, timed, one with event spans, two serialised); the launches of the
+SECOND step are summed.  <K1 launches per step> = z-chunks of a pipelined step = gpu_launches / (5 * steps) of a
+bench line of the same workload.
 Counters are properties of the instruction stream and the grid, so bench.py divides them by the K1 time it measures live.
 """
 import csv
@@ -39,18 +40,10 @@ def main():
     out = {}
     for spec in sys.argv[1:]:
         wl, path = spec.split("=", 1)
+        path, _, per_s = path.partition(":")
         ls = parse(path)
-        import re
-        res = int(re.search(r"(\d+)", wl.replace("p_key", "pkey").replace("martin_cube", "martincube")).group(1))
-        steps, cur, slices = [], [], 0
-        for l in ls:   # grid "(gx, gy, planes)"
-            cur.append(l)
-            slices += int(l["grid"].strip("()").split(",")[2]) - 1
-            if slices >= res - 1:
-                steps.append(cur)
-                cur, slices = [], 0
-        step = steps[1]
-        per = len(step)
+        per = int(per_s)          # z-chunks (= K1 launches) of a pipelined step: gpu_launches / (5 * steps) of the bench line
+        step = ls[per:2 * per]    # the second step (the first pipelined step after the warm-up)
         tot = lambda m: sum(l.get(m, 0.0) for l in step)
         op = lambda o: tot(f"sm__sass_thread_inst_executed_op_{o}_pred_on.sum")
         flops = sum(op(o) * f for o, f in FLOPS.items())
