@@ -1,4 +1,5 @@
-# multi-GPU pass: N = number of visible GPUs
+# N GPUs (gpurun --gpus N -- bash tools/gpu_multi.sh): the s2m_multi / NCCL tests, then the 2048^3 bench one process per GPU (torchrun), from one
+# process through s2m_multi_mesh_run (NCCL count exchange) and with the host-memory exchange
 set -x
 N=$(nvidia-smi -L | wc -l)
 timeout 900 python -m pytest tests/test_multi_gpu.py tests/test_aux_gpu.py -q -m gpu -k "multi or nccl or cli" --timeout 600 2>&1 | tail -6

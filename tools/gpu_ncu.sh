@@ -1,4 +1,5 @@
-# ncu evidence with the final kernels: K1 counters per workload, launch list, --set full captures
+# One B200: ncu evidence -- per-step K1 counters for every workload (-> tools/ncu_k1_counters.py -> profiles/k1_counters.json),
+# the launch list of the bench command and --set full captures of K1 (per example SDF) and of K2 / K3 / K4a / K4b
 set -x
 B="python bench.py --steps 1 --warmup 1 --no-verify --no-cpu-baseline --no-other-workloads"
 M=$(python -c "import sys; sys.path.insert(0,'tools'); import ncu_k1_counters as n; print(n.METRICS)")
