@@ -87,10 +87,19 @@ __device__ __forceinline__ void s2m_k1_eval4(bool on, const float cx[4], float c
 #endif
   }
 }
-/* corner classes of 4 values: low nibble P (value > tau), high nibble N (value < -tau) */
+/* corner classes of 4 values: low nibble P (value > tau), high nibble N (value < -tau).
+ * Sign bits of differences instead of compares: v > tau <=> tau - v < 0 and v < -tau <=> v + tau < 0 -- a difference of two
+ * floats that is not zero keeps its sign when rounded, an exact zero is +0, and a NaN operand gives the canonical NaN
+ * 0x7fffffff (sign clear: neither class, as with the compares).  One FADD (FMA pipe) and one funnel shift per bit instead
+ * of FSETP + SEL + LOP3 on the half-rate ALU pipe, which is what the tiny SDFs' K1 runs out of (torus: 29 instructions
+ * per corner, a third of them this epilogue). */
 __device__ __forceinline__ unsigned s2m_k1_class_byte(const float v[4], float tau) {
-  return (v[0] > tau ? 1u : 0u) | (v[1] > tau ? 2u : 0u) | (v[2] > tau ? 4u : 0u) | (v[3] > tau ? 8u : 0u) |
-         (v[0] < -tau ? 16u : 0u) | (v[1] < -tau ? 32u : 0u) | (v[2] < -tau ? 64u : 0u) | (v[3] < -tau ? 128u : 0u);
+  unsigned acc = 0u;
+#pragma unroll
+  for (int k = 3; k >= 0; --k) acc = __funnelshift_l(__float_as_uint(v[k] + tau), acc, 1);   /* N3 .. N0 -> bits 7 .. 4 */
+#pragma unroll
+  for (int k = 3; k >= 0; --k) acc = __funnelshift_l(__float_as_uint(tau - v[k]), acc, 1);   /* P3 .. P0 -> bits 3 .. 0 */
+  return acc;
 }
 
 #ifndef S2M_K1_ZPT

@@ -18,6 +18,14 @@ from tests.test_frontend import NAGA_TEST_GLSL
 pytestmark = pytest.mark.gpu
 
 WGSL_PROGRAMS = {
+    # NaN in a region of space: a NaN corner is neither "outside" (v > tau) nor "inside" (v < -tau) for the classifier, and
+    # "inside" (!(v > 0)) for the reference's cell rule
+    "nan_region": """
+        fn sdf3d(p: vec3f) -> f32 {
+          let d = length(p) - 0.8;
+          let hole = sqrt(0.09 - (p.x - 0.5) * (p.x - 0.5) - p.y * p.y);
+          return select(d, d + hole * 0.0, p.z > 0.2);
+        }""",
     "control_flow": """
         fn fold(q: vec3f) -> vec3f { var v = abs(q); if (v.x < v.y) { v = v.yxz; } if (v.x < v.z) { v = v.zyx; } return v; }
         fn sdf3d(p: vec3f) -> f32 {
@@ -136,7 +144,7 @@ def _program(name, tmp_path):
     return s2m.Sdf3DShader.from_source(textwrap.dedent(WGSL_PROGRAMS[name]))
 
 
-@pytest.mark.parametrize("name,res,bounds", [("aggregates", 48, 4.0), ("control_flow", 40, 3.0), ("integer_hash_noise", 48, 3.0),
+@pytest.mark.parametrize("name,res,bounds", [("aggregates", 48, 4.0), ("control_flow", 40, 3.0), ("integer_hash_noise", 48, 3.0), ("nan_region", 48, 2.5),
                                              ("shadertoy_raymarcher", 64, 3.0), ("shadertoy_idioms", 64, 3.5)])
 def test_generated_programs_mesh_like_the_oracle(ctx, tmp_path, name, res, bounds):
     """whole-path parity for shaders without a hand transcription: the oracle runs its cell loop on the
