@@ -138,6 +138,16 @@ __device__ __forceinline__ unsigned long long ld_u64(const uint2* p) {
   return (unsigned long long)t.x | ((unsigned long long)t.y << 32);
 }
 
+// a cell is NOT a candidate iff its P bit or its N bit survived in all 8 corners; the nibble per byte that is left is
+// squeezed to 32 bits with one OR of the word shifted by a nibble and a byte permute (three shift / or / and rounds on
+// 64 bits before: K2 is issue-bound, profiles/r02_ncu_k234.md)
+__device__ __forceinline__ uint32_t cls_candidates(unsigned long long prev, unsigned long long cur) {
+  const unsigned long long all8 = prev & cur;                       // low nibbles: all 8 corners > tau; high: all < -tau
+  const unsigned long long x = ~(all8 | (all8 >> 4)) & 0x0f0f0f0f0f0f0f0full;   // nibble per byte: candidate cells
+  const unsigned long long y = x | (x >> 4);                        // bytes 0, 2, 4, 6 now hold cells 0-7, 8-15, 16-23, 24-31
+  return __byte_perm((uint32_t)y, (uint32_t)(y >> 32), 0x6420);
+}
+
 __global__ void __launch_bounds__(256)
 k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t rows, uint32_t res_x, uint32_t res_y,
                  uint32_t nz_chunk, uint32_t* __restrict__ cand_mask, uint32_t words_x, unsigned long long* __restrict__ total,
@@ -163,13 +173,7 @@ k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t row
       cur = cls_pair_x(a, b) & cls_pair_x(c, d);  // P nibbles: all 4 corners of this plane > tau; N nibbles: all < -tau
       if (k >= 1) {
         const uint32_t z = plane - 1u;
-        const unsigned long long all8 = prev & cur;
-        // a cell is NOT a candidate iff its P bit or its N bit survived; compress the P positions to 32 bits
-        unsigned long long x = ~(all8 | (all8 >> 4)) & 0x0f0f0f0f0f0f0f0full;
-        x = (x | (x >> 4)) & 0x00ff00ff00ff00ffull;
-        x = (x | (x >> 8)) & 0x0000ffff0000ffffull;
-        x = (x | (x >> 16)) & 0x00000000ffffffffull;
-        uint32_t cand = (uint32_t)x;
+        uint32_t cand = cls_candidates(prev, cur);
         const uint32_t xb = xw * 32u;
         if (xb + 32u > res_x) cand &= (1u << (res_x - xb)) - 1u;
         cand_mask[((unsigned long long)z * res_y + y) * words_x + xw] = cand;

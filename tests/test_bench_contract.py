@@ -49,3 +49,35 @@ def test_product_arm_needs_a_device(built):
     p = run_bench("--workload", "torus128", "--steps", "1", "--warmup", "1", "--no-cpu-baseline")
     assert p.returncode != 0
     assert not [l for l in p.stdout.splitlines() if l.startswith("{")]   # no number without the CUDA path
+
+
+def test_parity_digest_of_slab_parts_equals_the_whole_mesh_digest(built):
+    """bench.py's parity_check hashes the slabs of all ranks in z order, array by array; that must be the digest
+    tests/support/digest.py gives for the assembled mesh (and what tests/golden/digests.json holds)"""
+    import importlib.util
+    import numpy as np
+    import oracle
+    from tests.support.digest import mesh_digests
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    o = oracle.mesh_run("torus", 64, 2.0)
+    whole = mesh_digests(o.positions, o.normals, o.keys, o.nibbles, o.quads, o.n_invalid_quads)
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "digests.json")))
+    assert whole == golden[bench.golden_key("torus", 64, 2.0, 0)]
+    # three "ranks": vertices cut at arbitrary places, quads cut elsewhere (each rank's quads already carry global indices);
+    # one rank holds nothing at all
+    nv, nq = len(o.keys), len(o.quads)
+    cuts_v, cuts_q = [0, nv // 3, nv // 3, nv], [0, nq // 2, nq // 2, nq]
+    pos = np.array(o.positions, np.float32)
+    pos[5, 1] = np.float32("nan")     # NaN payloads are canonicalised the same way in both
+    whole = mesh_digests(pos, o.normals, o.keys, o.nibbles, o.quads, o.n_invalid_quads)
+    parts = []
+    for k in range(3):
+        v0, v1, q0, q1 = cuts_v[k], cuts_v[k + 1], cuts_q[k], cuts_q[k + 1]
+        parts.append(({"keys": o.keys[v0:v1], "nibbles": o.nibbles[v0:v1], "quads": o.quads[q0:q1], "positions": pos[v0:v1], "normals": o.normals[v0:v1]},
+                      o.n_invalid_quads if k == 0 else 0))
+    assert bench.digest_parts(parts) == whole
+    rec = bench.parity_record(bench.digest_parts(parts), "no_such_key")
+    assert rec["golden"] is None and rec["ok"] is None
+    o.free()
