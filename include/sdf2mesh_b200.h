@@ -216,7 +216,10 @@ typedef struct s2m_result_info {
  * vertices and quads copied into pinned host memory while the next chunk computes.  Returns when the last copy has
  * been QUEUED; the vertex count (s2m_result_get) is final, the arrays are not yet.  Quads are written with
  * slab-relative indices (local vertex index, the recomputed halo slice counting as negative), so nothing waits for
- * the global vertex base. */
+ * the global vertex base.
+ * Limits: dims in [2, 65535] per axis (cell coordinates are u16 in the reference's key, mesh.rs:214); fewer than 2^32 - 1
+ * candidate cells PER SLAB (ranks are u32: S2M_ERR_UNSUPPORTED beyond -- split the grid with z_begin / z_end; 4096^3 of
+ * the mandelbulb has 4 x 10^7); vertex and quad indices are 64-bit (u32 on request, checked in s2m_mesh_finish). */
 int s2m_mesh_begin(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, s2m_result** out);
 /* Waits for the copies and fixes the slab's place in the whole mesh: global_vertex_base = the exclusive prefix of
  * n_vertices over lower z-slabs (from an all-gather across ranks; 0 on one GPU).  By default the quads in host

@@ -805,6 +805,7 @@ extern "C" void s2m_result_free(s2m_result* r) {
       cudaSetDevice(c->device);
       cudaStreamSynchronize(c->copy_stream);
       cudaStreamSynchronize(c->stream);
+      cudaStreamSynchronize(c->prod_stream);   // a run that failed midway may have queued the next chunk's K1
       c->busy = false;
     }
     for (PinnedRegion* g : {r->g_pos, r->g_nrm, r->g_key, r->g_nib, r->g_quads}) if (g) g->used = false;
