@@ -3,8 +3,6 @@
 set -x
 B="python bench.py --steps 1 --warmup 1 --no-verify --no-cpu-baseline --no-other-workloads"
 M=$(python -c "import sys; sys.path.insert(0,'tools'); import ncu_k1_counters as n; print(n.METRICS)")
-timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_packed_gpu.py tests/test_multi_gpu.py -q -m gpu -x --timeout 900 2>&1 | tail -3
-timeout 300 python bench.py --no-cpu-baseline --workload torus2048 --no-other-workloads > gpurun_out/bench_j_torus.json 2> gpurun_out/bench_j.err; tail -c 200 gpurun_out/bench_j_torus.json
 for wl in mandelmesh2048 torus2048 martin_cube512 p_key1024 p_key1024_b20 torus128; do
   timeout 600 ncu --metrics $M --clock-control none -k regex:s2m_k1_slab --csv --log-file gpurun_out/k1cnt_$wl.csv $B --workload $wl > /dev/null 2> gpurun_out/k1cnt_$wl.err
   wc -l gpurun_out/k1cnt_$wl.csv
