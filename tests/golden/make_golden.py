@@ -34,6 +34,10 @@ HUGE = [("mandelbulb", 1024, 5.0, 0), ("mandelbulb", 2048, 5.0, 0), ("p_key", 10
         ("p_key", 1024, 2.0, 0)]   # BASELINE config 3 as literally stated: --resolution 1024, default --bounds 2 (main.rs:150)
 
 
+# BASELINE config 5 in full: 68.7 G cells, 8 SDF evaluations each (~35 minutes on 8 cores, 5 GB); `--giant`
+GIANT = [("mandelbulb", 4096, 5.0, 0)]
+
+
 def key(c):
     return f"{c[0]}_r{c[1]}_b{c[2]:g}_f{c[3]}"
 
@@ -43,7 +47,7 @@ def main():
     out = json.load(open(path)) if os.path.exists(path) else {}
     if "--out" in sys.argv:
         path = sys.argv[sys.argv.index("--out") + 1]
-    cases = CASES + (BIG if "--big" in sys.argv else []) + (HUGE if "--huge" in sys.argv else [])
+    cases = CASES + (BIG if "--big" in sys.argv else []) + (HUGE if "--huge" in sys.argv else []) + (GIANT if "--giant" in sys.argv else [])
     for c in cases:
         if key(c) in out and "--force" not in sys.argv:
             continue
