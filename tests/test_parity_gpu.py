@@ -432,3 +432,24 @@ def test_randomized_configurations(ctx, seed):
             s.free()
     finally:
         o.free()
+
+
+def test_kernel_timing_spans_are_opt_in(ctx):
+    """S2M_MESH_TIMINGS: the per-kernel fields of s2m_timings come from CUDA-event spans around every launch; off by default
+    (device_ms / total_ms / host_wall_ms / launches / chunks are always there).  Same mesh either way."""
+    mod = module_for(ctx, "mandelbulb")
+    p, _ = s2m.params_from_cli(256, 5.0)
+    r = s2m.mesh_run(ctx, mod, p)
+    d0 = r.data()
+    t = d0.timings
+    assert t["k1_slab_ms"] == 0 and t["k4_vertices_ms"] == 0 and t["d2h_ms"] == 0
+    assert t["device_ms"] > 0 and t["total_ms"] >= t["device_ms"] and t["host_wall_ms"] > 0 and t["launches"] == 5 * t["chunks"]
+    keys0, quads0 = d0.keys.copy(), d0.quads.copy()
+    r.free()
+    p.flags |= s2m.MESH_TIMINGS
+    r = s2m.mesh_run(ctx, mod, p)
+    d1 = r.data()
+    t = d1.timings
+    assert min(t[k] for k in ("k1_slab_ms", "k2_classify_ms", "k3_compact_ms", "k4_vertices_ms", "k4_quads_ms", "d2h_ms")) > 0
+    assert np.array_equal(d1.keys, keys0) and np.array_equal(d1.quads, quads0)
+    r.free()
