@@ -170,7 +170,13 @@ k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t row
       const bool has_next = xw + 1u < cls_words;
       const unsigned long long a = ld_u64(r0), c = ld_u64(r1);
       const unsigned long long b = has_next ? ld_u64(r0 + 1) : 0ull, d = has_next ? ld_u64(r1 + 1) : 0ull;
-      cur = cls_pair_x(a, b) & cls_pair_x(c, d);  // P nibbles: all 4 corners of this plane > tau; N nibbles: all < -tau
+      // P nibbles: all 4 corners of this plane > tau; N nibbles: all < -tau.  Away from the surface -- 99 % of the words --
+      // both corner rows are uniformly P (or uniformly N) and so is the first corner of the next word: the pairing of
+      // such a word is the word itself (K2 is issue-bound; the two pairings are a third of its instructions)
+      const unsigned long long ac = a & c, bd = b & d;
+      if (ac == 0x0f0f0f0f0f0f0f0full && (a | c) == ac && (bd & 0x01ull)) cur = ac;
+      else if (ac == 0xf0f0f0f0f0f0f0f0ull && (a | c) == ac && (bd & 0x10ull)) cur = ac;
+      else cur = cls_pair_x(a, b) & cls_pair_x(c, d);
       if (k >= 1) {
         const uint32_t z = plane - 1u;
         uint32_t cand = cls_candidates(prev, cur);
