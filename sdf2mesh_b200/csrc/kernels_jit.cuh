@@ -111,13 +111,15 @@ __device__ __forceinline__ unsigned s2m_k1_class_byte(const float v[4], float ta
 /* Consecutive z-chunks share one corner plane: the top plane of the previous chunk (carry_*: that plane in the
  * previous chunk's buffers) is this launch's plane 0.  Its blocks copy it instead of evaluating it again -- same
  * values, a plane's worth of SDF evaluations saved per chunk boundary (3 % of K1 for a 146-slice slab in 6 chunks).
- * Kept out of the plane loop: inside it the copy cost the tiny kernels 11 registers (torus 58 -> 69). */
-__device__ __noinline__ void s2m_k1_carry_plane(const S2mGrid& g, float* __restrict__ slab, uint2* __restrict__ cls, unsigned cls_words,
+ * Kept out of the plane loop: inside it the copy cost the tiny kernels 11 registers (torus 58 -> 69).  Takes the pitch
+ * by value: a reference to the grid struct made every thread spill the kernel's parameters to local memory at entry
+ * (7 STL per thread, 1.7 % of the mandelbulb K1's instructions; ncu source view). */
+__device__ __noinline__ void s2m_k1_carry_plane(unsigned pitch_x, float* __restrict__ slab, uint2* __restrict__ cls, unsigned cls_words,
                                                 const float* __restrict__ carry_slab, const uint2* __restrict__ carry_cls,
                                                 unsigned x4, unsigned y, unsigned lane, bool active, bool active_b) {
   if (slab != nullptr && carry_slab != nullptr) {
-    if (active) *reinterpret_cast<float4*>(slab + (unsigned long long)y * g.pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (unsigned long long)y * g.pitch_x + x4));
-    if (active_b) *reinterpret_cast<float4*>(slab + (y + 1ull) * g.pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (y + 1ull) * g.pitch_x + x4));
+    if (active) *reinterpret_cast<float4*>(slab + (unsigned long long)y * pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (unsigned long long)y * pitch_x + x4));
+    if (active_b) *reinterpret_cast<float4*>(slab + (y + 1ull) * pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (y + 1ull) * pitch_x + x4));
   }
   if (cls != nullptr && carry_cls != nullptr) {   /* the lanes that store a class word in the epilogue copy the same word */
     const unsigned long long at = ((unsigned long long)y * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u);
@@ -159,9 +161,9 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
    * primitive compositions lose 1-2 % (fewer, longer blocks), so they keep one plane per thread. */
   const bool carry = blockIdx.z == 0u && (carry_slab != nullptr || carry_cls != nullptr);   /* uniform over the block */
 #if S2M_K1_ROWS == 2
-  if (carry) s2m_k1_carry_plane(g, slab, cls, cls_words, carry_slab, carry_cls, x4, y, lane, active, active_b);
+  if (carry) s2m_k1_carry_plane(g.pitch_x, slab, cls, cls_words, carry_slab, carry_cls, x4, y, lane, active, active_b);
 #else
-  if (carry) s2m_k1_carry_plane(g, slab, cls, cls_words, carry_slab, carry_cls, x4, y, lane, active, false);
+  if (carry) s2m_k1_carry_plane(g.pitch_x, slab, cls, cls_words, carry_slab, carry_cls, x4, y, lane, active, false);
 #endif
 #if S2M_K1_ZPT > 1
   const unsigned pz_end = min(n_planes, (blockIdx.z + 1u) * (unsigned)S2M_K1_ZPT);
