@@ -210,7 +210,7 @@ struct s2m_ctx {
   int device = 0;
   cudaDeviceProp prop{};
   cudaStream_t stream = nullptr, copy_stream = nullptr, prod_stream = nullptr;
-  DevBuf slab, cls, slab2, cls2, cand_mask, seg_count, word_prefix, cand_key, cand_vrank, status, counters;
+  DevBuf slab, cls, slab2, cls2, coords, cand_mask, seg_count, word_prefix, cand_key, cand_vrank, status, counters;
   DevBuf v_pos, v_nrm, v_key, v_nib, quads, scratch, invalid;
   std::vector<PinnedBlock> pinned;            // small outputs (candidate list, invalid records, halo positions)
   std::vector<std::unique_ptr<PinnedRegion>> regions;  // big outputs
@@ -380,6 +380,7 @@ struct s2m_module {
   s2m_ctx* ctx = nullptr;
   unsigned k1_rows = 1;  // grid rows per K1 thread (S2M_K1_ROWS the kernels were compiled with)
   unsigned k1_zpt = 1;   // planes per K1 thread (S2M_K1_ZPT)
+  bool k1_coords = false;  // K1 reads its corner coordinates from the run's table (S2M_K1_COORDS)
   bool k1_packed = false;  // K1 evaluates corner pairs in f32x2 arithmetic (s2m_pvec.h)
   bool slab_free_default = false;  // cheap SDF: K1 writes no f32 slab, K4a evaluates all 8 corners (S2M_MESH_NO_SLAB is the default for this module)
   double ms_frontend = 0, ms_nvrtc = 0, ms_load = 0;
@@ -590,6 +591,12 @@ int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uin
   m->k1_zpt = tiny ? 16u : ((mid && plan.size > 0 && plan.size <= 400) ? 8u : 1u);
   if (const char* e = getenv("S2M_K1_ZPT")) m->k1_zpt = (unsigned)std::max(1, std::min(64, atoi(e)));  // experiment knob
   opts.push_back("-DS2M_K1_ZPT=" + std::to_string(m->k1_zpt));
+  // Corner coordinates from the run's table instead of i2f + mul + add per coordinate (kernels_jit.cuh): the mandelbulb's
+  // K1 40.0 -> 38.5 ms at 2048^3, the others within noise (profiles/r02_k1_ab.jsonl); a thread that marches through
+  // planes computes its x and y once anyway.
+  m->k1_coords = m->k1_zpt == 1;
+  if (const char* e = getenv("S2M_K1_COORDS")) m->k1_coords = atoi(e) != 0;  // experiment knob
+  if (m->k1_coords) opts.push_back("-DS2M_K1_COORDS=1");
   if (const char* e = getenv("S2M_K1_UNROLL"))  // experiment knob, see kernels_jit.cuh
     opts.push_back(std::string("-DS2M_K1_UNROLL=") + (atoi(e) == 1 ? "1" : "4"));
   else if (mid && plan.size > 400)
@@ -680,6 +687,7 @@ extern "C" int s2m_module_instantiate(const s2m_module* compiled, s2m_ctx* ctx, 
   for (int k = 0; k < compiled->n_parts; ++k) m->cubin[k] = compiled->cubin[k];
   m->k1_rows = compiled->k1_rows;
   m->k1_zpt = compiled->k1_zpt;
+  m->k1_coords = compiled->k1_coords;
   m->uid = compiled->uid;
   m->k1_packed = compiled->k1_packed;
   m->slab_free_default = compiled->slab_free_default;
@@ -727,6 +735,20 @@ struct SlabViewDev {  // must match S2mSlabView
   unsigned first_plane;
   unsigned n_planes;
 };
+// The run's corner coordinate table for K1 (k_coords): x | y | z, each long enough for every thread of the K1 grid
+// (threads past the grid's edge are inactive but still load).  Filled on `stream`, in front of the first K1.
+static int prepare_coords(s2m_ctx* c, const s2m_module* m, const GridDev& g, unsigned bx, unsigned by, cudaStream_t stream, const float* out[3]) {
+  out[0] = out[1] = out[2] = nullptr;
+  if (!m->k1_coords) return S2M_OK;
+  const unsigned gx = (g.pitch_x + 4u * bx - 1u) / (4u * bx), gy = (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows);
+  const unsigned nx = gx * 4u * bx + 4u, ny = (gy * by * m->k1_rows + 2u + 3u) & ~3u, nz = g.res[2] + 1u;
+  int st = c->coords.ensure((size_t)(nx + ny + nz) * 4 + 64);
+  if (st) return st;
+  float* tab = c->coords.as<float>();
+  if (s2m_launch_coords(tab, nx, ny, nz, g.bmin, g.size, stream) != 0) return fail(S2M_ERR_CUDA, "k_coords launch failed");
+  out[0] = tab; out[1] = tab + nx; out[2] = tab + nx + ny;
+  return S2M_OK;
+}
 // K1 block shape (bx, by), bx*by = 256; S2M_K1_BLOCK=8x32 overrides the default for experiments
 void k1_block_shape(unsigned* bx, unsigned* by) {
   struct Shape { unsigned x = 8, y = 32; };
@@ -1052,6 +1074,12 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
   if (pipelined) CUDA_TRY(cudaStreamWaitEvent(ps, c->ev[EV_BEGIN], 0));  // after the counter reset
   const unsigned cls_words = g.pitch_x / 32u;
   static const bool carry_planes = [] { const char* e = getenv("S2M_CARRY_PLANES"); return !e || atoi(e) != 0; }();
+  const float* coord[3] = {nullptr, nullptr, nullptr};
+  {
+    unsigned bx, by;
+    k1_block_shape(&bx, &by);
+    if ((st = prepare_coords(c, m, g, bx, by, ps, coord))) return st;
+  }
   // K1 of chunk ci into slab / class-plane buffer ci % 2 (buffer 0 when not pipelined), on the producer stream
   auto produce = [&](size_t ci) -> int {
     const Chunk ch = chunks[ci];
@@ -1083,7 +1111,9 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
       if (!pipelined) { carry_slab = nullptr; carry_cls = nullptr; }   // one buffer: source and destination planes would be the same launch's
     }
     float tau_arg = tau;
-    void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw, &carry_slab, &carry_cls};
+    const float* coord_z = coord[2] ? coord[2] + first_plane : nullptr;
+    unsigned opt = ((carry_slab || carry_cls) ? 1u : 0u) | (slab ? 2u : 0u) | (cls ? 4u : 0u);
+    void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw, &carry_slab, &carry_cls, &coord[0], &coord[1], &coord_z, &opt};
     unsigned bx, by;
     k1_block_shape(&bx, &by);
     dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), (n_planes + m->k1_zpt - 1u) / m->k1_zpt);
@@ -1459,9 +1489,13 @@ extern "C" int s2m_debug_slab_plane(s2m_ctx* c, s2m_module* m, const s2m_mesh_pa
   void* cls = nullptr;
   const float* carry_slab = nullptr;
   const void* carry_cls = nullptr;
-  void* a1[] = {&g, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words, &carry_slab, &carry_cls};
   unsigned bx, by;
   k1_block_shape(&bx, &by);
+  const float* coord[3];
+  if ((st = prepare_coords(c, m, g, bx, by, c->stream, coord))) return st;
+  const float* coord_z = coord[2] ? coord[2] + first_plane : nullptr;
+  unsigned opt = 2u;   // the slab only
+  void* a1[] = {&g, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words, &carry_slab, &carry_cls, &coord[0], &coord[1], &coord_z, &opt};
   if ((st = launch(m->k1, dim3((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), 1), dim3(bx, by, 1), c->stream, a1, "s2m_k1_slab"))) return st;
   CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)(g.res[0] + 1) * 4, slab, (size_t)g.pitch_x * 4, (size_t)(g.res[0] + 1) * 4, g.rows,
                              cudaMemcpyDeviceToHost, c->stream));

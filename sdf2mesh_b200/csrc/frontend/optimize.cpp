@@ -10,12 +10,22 @@
 // examples/mandelmesh.frag has this shape (`r = length(z); if (r > 2.0) continue;`): for the 73 % of
 // grid corners outside the bailout radius it saves 4 of the 5 length() evaluations.
 //
+// rotate_guarded_loop (after the two above): a loop that tests an exit right after a cheap prefix,
+//     for (init; cond; step) { P; if (c) break; R }
+// becomes
+//     { init; if (cond) { P; if (c) {} else { for (;;) { R; step; if (cond) {} else { break; } P; if (c) break; } } } }
+// -- the same statements in the same order for every path, but everything the compiler hoists out of the
+// loop for R's sake (constants, invariant sub-expressions: ~30 instructions for the mandelbulb) now sits
+// behind the first test, and a point that leaves at once (96 % of the mandelbulb's grid corners at bounds 5)
+// no longer pays for it.  P is duplicated, so it must be plain assignments; R must not `continue` this loop.
+//
 // pair_sin_cos: within a run of plain statements of one block, sin(e) and cos(e) of a structurally
 // identical pure scalar f32 expression e -- with none of e's variables written in between -- become
 //     vec2 _sc = sincos_pair(e);   ... _sc.x ... _sc.y ...
 // declared before the first of them.  s2m_sincos returns exactly s2m_sin(e) and s2m_cos(e) (one
 // argument reduction and one big-argument test instead of two); rotation code and the spherical
 // coordinates of examples/mandelmesh.frag have this shape.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -319,6 +329,84 @@ struct TrigPairing {
   }
 };
 
+// ---------------------------------------------------------------------------- rotate_guarded_loop
+bool is_bare_break(const Stmt& s) {
+  if (s.k != Stmt::If || s.else_s || !s.then_s) return false;
+  const Stmt* t = s.then_s.get();
+  while (t->k == Stmt::Block && t->body.size() == 1) t = t->body[0].get();
+  return t->k == Stmt::Break;
+}
+// a `continue` that belongs to the loop whose body this is (nested loops keep theirs)
+bool continues_this_loop(const Stmt& s) {
+  if (s.k == Stmt::Continue) return true;
+  if (s.k == Stmt::For || s.k == Stmt::While || s.k == Stmt::DoWhile || s.k == Stmt::Loop) return false;
+  for (const StmtP& c : s.body) if (continues_this_loop(*c)) return true;
+  if (s.then_s && continues_this_loop(*s.then_s)) return true;
+  if (s.else_s && continues_this_loop(*s.else_s)) return true;
+  return false;
+}
+StmtP new_stmt(Stmt::K k, int line) { StmtP s(new Stmt()); s->k = k; s->line = line; return s; }
+
+bool rotate_loop(Stmt& loop) {
+  if (loop.k != Stmt::For || loop.body.size() != 1 || loop.body[0]->k != Stmt::Block) return false;
+  if (loop.init && loop.init->k != Stmt::VarDecl) return false;
+  if (loop.cont && loop.cont->k != Stmt::Assign && loop.cont->k != Stmt::CallStmt) return false;
+  std::vector<StmtP>& b = loop.body[0]->body;
+  size_t k = 0;
+  while (k < b.size() && b[k]->k == Stmt::Assign) ++k;      // P: plain assignments only (it is emitted twice)
+  if (k == 0 || k >= b.size() || !is_bare_break(*b[k]) || k + 1 >= b.size()) return false;
+  for (size_t j = k + 1; j < b.size(); ++j) if (continues_this_loop(*b[j])) return false;
+  const int line = loop.line;
+  const std::vector<StmtP> prefix(b.begin(), b.begin() + (long)k);
+  const StmtP exit_test = b[k];
+  const std::vector<StmtP> rest(b.begin() + (long)k + 1, b.end());
+  // for (;;) { R; step; if (cond) {} else { break; } P; if (c) break; }
+  StmtP inner_body = new_stmt(Stmt::Block, line);
+  inner_body->body = rest;
+  if (loop.cont) inner_body->body.push_back(loop.cont);
+  if (loop.a) {
+    StmtP leave = new_stmt(Stmt::If, line);
+    leave->a = loop.a;
+    leave->then_s = new_stmt(Stmt::Block, line);
+    leave->else_s = new_stmt(Stmt::Block, line);
+    leave->else_s->body.push_back(new_stmt(Stmt::Break, line));
+    inner_body->body.push_back(leave);
+  }
+  inner_body->body.insert(inner_body->body.end(), prefix.begin(), prefix.end());
+  inner_body->body.push_back(exit_test);
+  StmtP inner = new_stmt(Stmt::For, line);
+  inner->body.push_back(inner_body);
+  // P; if (c) {} else { inner }
+  StmtP first_test = new_stmt(Stmt::If, exit_test->line);
+  first_test->a = exit_test->a;
+  first_test->then_s = new_stmt(Stmt::Block, line);
+  first_test->else_s = new_stmt(Stmt::Block, line);
+  first_test->else_s->body.push_back(inner);
+  StmtP entered = new_stmt(Stmt::Block, line);
+  entered->body = prefix;
+  entered->body.push_back(first_test);
+  std::vector<StmtP> out;
+  if (loop.init) out.push_back(loop.init);
+  if (loop.a) {
+    StmtP guard = new_stmt(Stmt::If, line);
+    guard->a = loop.a;
+    guard->then_s = entered;
+    out.push_back(guard);
+  } else {
+    out.push_back(entered);
+  }
+  loop.k = Stmt::Block;
+  loop.body = out;
+  loop.init.reset(); loop.cont.reset(); loop.a.reset();
+  return true;
+}
+void rotate_walk(Stmt& s, int* count) {
+  for (StmtP& c : s.body) rotate_walk(*c, count);
+  if (s.then_s) rotate_walk(*s.then_s, count);
+  if (s.else_s) rotate_walk(*s.else_s, count);
+  if (rotate_loop(s)) ++*count;
+}
+
 void walk(Stmt& s, int* count) {
   for (StmtP& c : s.body) walk(*c, count);
   if (s.then_s) walk(*s.then_s, count);
@@ -407,6 +495,7 @@ int optimize_module(Module& m) {
     if (!f->body) continue;
     walk(*f->body, &count);
     pairing.nested(*f->body);
+    if (!getenv("S2M_NO_LOOP_ROTATION")) rotate_walk(*f->body, &count);   // last: it emits a loop's prefix twice
   }
   return count + pairing.pairs;
 }

@@ -135,7 +135,10 @@ __device__ __noinline__ void s2m_k1_carry_plane(unsigned pitch_x, float* __restr
 extern "C" __global__ void __launch_bounds__(256, S2M_K1_MINBLOCKS)
 s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned n_planes,
             float tau, uint2* __restrict__ cls, unsigned cls_words,
-            const float* __restrict__ carry_slab, const uint2* __restrict__ carry_cls) {
+            const float* __restrict__ carry_slab, const uint2* __restrict__ carry_cls,
+            const float* __restrict__ coord_x, const float* __restrict__ coord_y, const float* __restrict__ coord_z, unsigned opt) {
+  /* opt: what the pointer arguments say, as bits (one 32-bit test each instead of 64-bit pointer compares per thread):
+   * 1 = carry_slab or carry_cls is set, 2 = slab is set, 4 = cls is set.  coord_z points at first_plane's entry. */
   const unsigned x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
   const unsigned y = (blockIdx.y * blockDim.y + threadIdx.y) * (unsigned)S2M_K1_ROWS;
   /* no early return: all 32 lanes take part in the shuffles below.  Groups of 8 lanes cover 32
@@ -146,20 +149,37 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   /* S2M_K1_UNROLL=1 keeps ONE inlined copy of the SDF per row in the kernel (4x less code); 4 =
    * unrolled (lets independent evaluations overlap; faster for the mandelbulb, measured). */
   float cx[4];
+#if defined(S2M_K1_COORDS)
+  /* coordinates from the run's table (k_coords: the same two roundings): one 16-byte load for the 4 x, one load each for
+   * y and z, instead of a conversion, a multiplication and an addition per coordinate -- and nothing cheap for the
+   * register allocator to compute again in front of every inlined SDF (ncu source view: 45 of the mandelbulb K1's
+   * ~690 instructions per warp were coordinates) */
+  {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(coord_x + x4));
+    cx[0] = t.x; cx[1] = t.y; cx[2] = t.z; cx[3] = t.w;
+  }
+  const float cy_a = __ldg(coord_y + y);
+#else
+  (void)coord_x; (void)coord_y; (void)coord_z;
 #pragma unroll
   for (int k = 0; k < 4; ++k) cx[k] = g.bmin[0] + g.size[0] * (float)(x4 + (unsigned)k);
-  const bool in_x = x4 <= g.res[0];
   const float cy_a = g.bmin[1] + g.size[1] * (float)y;
+#endif
+  const bool in_x = x4 <= g.res[0];
 #if S2M_K1_ROWS == 2
   const bool active_b = active && y + 1u < g.rows;
+#if defined(S2M_K1_COORDS)
+  const float cy_b = __ldg(coord_y + y + 1u);
+#else
   const float cy_b = g.bmin[1] + g.size[1] * (float)(y + 1u);
+#endif
 #endif
   /* For a tiny SDF a thread marches through S2M_K1_ZPT consecutive planes: its x and y coordinates, its indices and its
    * activity are computed once (they are a third of the instructions of a torus evaluation), only z changes.  Not
    * unrolled: one inlined copy of the SDF per row either way.  The plane range is the same for the whole block.
    * Measured on B200 (profiles/r02_k1_ab.jsonl): torus 2048^3 K1 11.4 -> 8.7 ms at 16 planes; the mandelbulb and the
    * primitive compositions lose 1-2 % (fewer, longer blocks), so they keep one plane per thread. */
-  const bool carry = blockIdx.z == 0u && (carry_slab != nullptr || carry_cls != nullptr);   /* uniform over the block */
+  const bool carry = blockIdx.z == 0u && (opt & 1u) != 0u;   /* uniform over the block */
 #if S2M_K1_ROWS == 2
   if (carry) s2m_k1_carry_plane(g.pitch_x, slab, cls, cls_words, carry_slab, carry_cls, x4, y, lane, active, active_b);
 #else
@@ -174,7 +194,11 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   const unsigned pz = blockIdx.z;
 #endif
   const unsigned long long row = (unsigned long long)pz * g.rows + y;
+#if defined(S2M_K1_COORDS)
+  const float cz = __ldg(coord_z + pz);
+#else
   const float cz = g.bmin[2] + g.size[2] * (float)(first_plane + pz);
+#endif
   float va[4];
   unsigned redo = 0;
   s2m_k1_eval4(active && in_x, cx, cy_a, cz, va, redo, 0u);
@@ -200,7 +224,7 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
 #endif
   /* slab == nullptr: the slab-free form for cheap SDFs (S2M_MESH_NO_SLAB) -- only the corner classes below are
    * written (0.25 B per corner instead of 4.25) and K4a evaluates all 8 corners of every candidate cell itself. */
-  if (slab != nullptr) {
+  if (opt & 2u) {
     if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(va[0], va[1], va[2], va[3]);
 #if S2M_K1_ROWS == 2
     if (active_b) *reinterpret_cast<float4*>(slab + (row + 1ull) * g.pitch_x + x4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
@@ -210,7 +234,7 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
    * neither).  One byte per thread and row: low nibble = P of its 4 corners, high nibble = N.
    * 8 lanes (32 corners of a row) make one 64-bit word, cls[plane][row][x/32] = (lanes 0-3,
    * lanes 4-7): 0.25 B per corner instead of K2 re-reading 4 B.  Two shuffles per thread. */
-  if (cls != nullptr) {
+  if (opt & 4u) {
 #if S2M_K1_ROWS == 1
     unsigned w = s2m_k1_class_byte(va, tau) << (8u * (lane & 3u));
     w |= __shfl_xor_sync(0xffffffffu, w, 1);

@@ -543,6 +543,19 @@ extern "C" int s2m_launch_fp32_probe(int mode, int blocks, int iters, float* sin
   }
   return (int)cudaGetLastError();
 }
+/* Corner coordinates of one run, bmin + size * f32(i) per axis (two roundings, as K1 computed them per thread):
+ * tab = x[0 .. nx) | y[0 .. ny) | z[0 .. nz).  K1 loads them instead of converting, multiplying and adding. */
+__global__ void k_coords(float* __restrict__ tab, unsigned nx, unsigned ny, unsigned nz, float bx, float by, float bz, float sx, float sy, float sz) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nx) tab[i] = __fadd_rn(bx, __fmul_rn(sx, (float)i));
+  else if (i < nx + ny) tab[i] = __fadd_rn(by, __fmul_rn(sy, (float)(i - nx)));
+  else if (i < nx + ny + nz) tab[i] = __fadd_rn(bz, __fmul_rn(sz, (float)(i - nx - ny)));
+}
+extern "C" int s2m_launch_coords(float* tab, unsigned nx, unsigned ny, unsigned nz, const float* bmin, const float* size, cudaStream_t stream) {
+  const unsigned n = nx + ny + nz;
+  k_coords<<<(n + 255u) / 256u, 256, 0, stream>>>(tab, nx, ny, nz, bmin[0], bmin[1], bmin[2], size[0], size[1], size[2]);
+  return (int)cudaGetLastError();
+}
 extern "C" int s2m_launch_publish(const unsigned long long* src, unsigned long long* dst_host, unsigned n, cudaStream_t stream) {
   k_publish<<<1, 32, 0, stream>>>(src, dst_host, n);
   return (int)cudaGetLastError();

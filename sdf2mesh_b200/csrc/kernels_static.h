@@ -69,6 +69,7 @@ int s2m_launch_publish2(const unsigned long long* src_a, unsigned na, const unsi
                         cudaStream_t stream);
 /* FP32 throughput probe: 8 FMAs per thread and iteration, 256 threads per block; mode 0 FFMA r,r,r / 1 FFMA r,imm,imm / 2 FFMA2 */
 int s2m_launch_fp32_probe(int mode, int blocks, int iters, float* sink, cudaStream_t stream);
+int s2m_launch_coords(float* tab, unsigned nx, unsigned ny, unsigned nz, const float* bmin, const float* size, cudaStream_t stream); /* x | y | z corner coordinates for K1 */
 int s2m_launch_k2(const S2mK2Args* a, cudaStream_t stream);      /* classify from the f32 slab */
 int s2m_launch_k2_bits(const S2mK2Args* a, cudaStream_t stream); /* classify from K1's class bit planes */
 uint32_t s2m_segs_x(uint32_t words_x);                                         /* segments per cell row */

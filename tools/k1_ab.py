@@ -50,8 +50,9 @@ def main():
     for spec in specs:
         wl, variants, *extra = spec.split(":")
         knobs = dict(kv.split("=") for kv in extra[0].split(",")) if extra else {}
-        for k in ("S2M_K1_MINBLOCKS", "S2M_K1_ROWS", "S2M_K1_UNROLL", "S2M_K1_BLOCK", "S2M_K1_ZPT", "S2M_SLAB"):
-            os.environ.pop(k, None)
+        for k in list(os.environ):   # every knob of the previous spec goes, whatever it was
+            if k.startswith("S2M_") and k not in ("S2M_CACHE_DIR",):
+                os.environ.pop(k, None)
         os.environ.update(knobs)
         f, res, bounds = W[wl]
         params, _ = s2m.params_from_cli(res, bounds, flags=s2m.MESH_QUADS_U32 | s2m.MESH_TIMINGS)
