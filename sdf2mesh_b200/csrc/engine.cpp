@@ -575,8 +575,9 @@ int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uin
   std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
                                    (flags & S2M_COMPILE_ALLOW_FMA) ? "--fmad=true" : "--fmad=false"};
   // Launch shape by the size of the SDF (measured on B200, profiles/r02_k1_ab.jsonl; every variant gives the same bits):
-  //  * heavy packed (>= 4 transcendental calls; mandelbulb): one row and one plane per thread, 48-register cap (5 resident
-  //    blocks; 62 registers / 4 blocks otherwise)
+  //  * heavy packed (>= 4 transcendental calls; mandelbulb): one row and one plane per thread, 64-register cap (4 resident
+  //    blocks).  (5 blocks / 48 registers won by 1 % before the round-2 instruction diet; after it 4 blocks do:
+  //    K1 36.75 vs 36.99 ms at 2048^3, 6 blocks 37.6.)
   //  * tiny (<= 64 expression nodes; torus): two rows per thread and 16 planes marched per thread -- index, coordinate
   //    and class overhead is a third of its instructions (K1 11.4 -> 8.7 ms at 2048^3)
   //  * in between (p_key 206 nodes, martin_cube 683): one row per thread with a 64-register cap (two rows need 111 / 240
@@ -603,9 +604,7 @@ int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uin
     opts.push_back("-DS2M_K1_UNROLL=1");
   if (const char* e = getenv("S2M_K1_MINBLOCKS"))  // experiment knob
     opts.push_back("-DS2M_K1_MINBLOCKS=" + std::to_string(std::max(1, std::min(8, atoi(e)))));
-  else if (packed_heavy)
-    opts.push_back("-DS2M_K1_MINBLOCKS=5");
-  else if (mid)
+  else if (packed_heavy || mid)
     opts.push_back("-DS2M_K1_MINBLOCKS=4");
 
   const char* split = getenv("S2M_JIT_SPLIT");
