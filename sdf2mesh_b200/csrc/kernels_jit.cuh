@@ -114,21 +114,19 @@ __device__ __forceinline__ unsigned s2m_k1_class_byte(const float v[4], float ta
  * Kept out of the plane loop: inside it the copy cost the tiny kernels 11 registers (torus 58 -> 69).  Takes the pitch
  * by value: a reference to the grid struct made every thread spill the kernel's parameters to local memory at entry
  * (7 STL per thread, 1.7 % of the mandelbulb K1's instructions; ncu source view). */
-__device__ __noinline__ void s2m_k1_carry_plane(unsigned pitch_x, float* __restrict__ slab, uint2* __restrict__ cls, unsigned cls_words,
+__device__ __noinline__ void s2m_k1_carry_plane(unsigned pitch_x, float* __restrict__ slab, uint2* __restrict__ cls,
                                                 const float* __restrict__ carry_slab, const uint2* __restrict__ carry_cls,
-                                                unsigned x4, unsigned y, unsigned lane, bool active, bool active_b) {
+                                                unsigned x4, unsigned y, bool active, bool active_b) {
   if (slab != nullptr && carry_slab != nullptr) {
     if (active) *reinterpret_cast<float4*>(slab + (unsigned long long)y * pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (unsigned long long)y * pitch_x + x4));
     if (active_b) *reinterpret_cast<float4*>(slab + (y + 1ull) * pitch_x + x4) = __ldg(reinterpret_cast<const float4*>(carry_slab + (y + 1ull) * pitch_x + x4));
   }
-  if (cls != nullptr && carry_cls != nullptr) {   /* the lanes that store a class word in the epilogue copy the same word */
-    const unsigned long long at = ((unsigned long long)y * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u);
-#if S2M_K1_ROWS == 1
-    if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at);
-#else
-    if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at);
-    if (active_b && (lane & 3u) == 2u) reinterpret_cast<unsigned*>(cls)[at + 2ull * cls_words] = __ldg(reinterpret_cast<const unsigned*>(carry_cls) + at + 2ull * cls_words);
-#endif
+  if (cls != nullptr && carry_cls != nullptr) {   /* every thread copies the class byte(s) it stores in the epilogue */
+    const unsigned long long at = (unsigned long long)y * (pitch_x >> 2) + (x4 >> 2);
+    unsigned char* dst = reinterpret_cast<unsigned char*>(cls);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(carry_cls);
+    if (active) dst[at] = __ldg(src + at);
+    if (active_b) dst[at + (pitch_x >> 2)] = __ldg(src + at + (pitch_x >> 2));
   }
 }
 
@@ -141,11 +139,9 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
    * 1 = carry_slab or carry_cls is set, 2 = slab is set, 4 = cls is set.  coord_z points at first_plane's entry. */
   const unsigned x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
   const unsigned y = (blockIdx.y * blockDim.y + threadIdx.y) * (unsigned)S2M_K1_ROWS;
-  /* no early return: all 32 lanes take part in the shuffles below.  Groups of 8 lanes cover 32
-   * consecutive corners of one row (blockDim.x is a multiple of 8, pitch_x of 32), so a group is
-   * active or inactive as a whole. */
-  const bool active = x4 < g.pitch_x && y < g.rows;
-  const unsigned lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31u;
+  /* threads past the padded row or the last row have nothing to do (no warp-wide operation below needs them) */
+  if (x4 >= g.pitch_x || y >= g.rows) return;
+  const bool active = true;
   /* S2M_K1_UNROLL=1 keeps ONE inlined copy of the SDF per row in the kernel (4x less code); 4 =
    * unrolled (lets independent evaluations overlap; faster for the mandelbulb, measured). */
   float cx[4];
@@ -181,9 +177,9 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
    * primitive compositions lose 1-2 % (fewer, longer blocks), so they keep one plane per thread. */
   const bool carry = blockIdx.z == 0u && (opt & 1u) != 0u;   /* uniform over the block */
 #if S2M_K1_ROWS == 2
-  if (carry) s2m_k1_carry_plane(g.pitch_x, slab, cls, cls_words, carry_slab, carry_cls, x4, y, lane, active, active_b);
+  if (carry) s2m_k1_carry_plane(g.pitch_x, slab, cls, carry_slab, carry_cls, x4, y, active, active_b);
 #else
-  if (carry) s2m_k1_carry_plane(g.pitch_x, slab, cls, cls_words, carry_slab, carry_cls, x4, y, lane, active, false);
+  if (carry) s2m_k1_carry_plane(g.pitch_x, slab, cls, carry_slab, carry_cls, x4, y, active, false);
 #endif
 #if S2M_K1_ZPT > 1
   const unsigned pz_end = min(n_planes, (blockIdx.z + 1u) * (unsigned)S2M_K1_ZPT);
@@ -231,27 +227,16 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
 #endif
   }
   /* Corner classes for K2: P = value > +tau, N = value < -tau (NaN and the |v| <= tau band are
-   * neither).  One byte per thread and row: low nibble = P of its 4 corners, high nibble = N.
-   * 8 lanes (32 corners of a row) make one 64-bit word, cls[plane][row][x/32] = (lanes 0-3,
-   * lanes 4-7): 0.25 B per corner instead of K2 re-reading 4 B.  Two shuffles per thread. */
+   * neither).  One byte per thread and row: low nibble = P of its 4 corners, high nibble = N; byte l of
+   * cls[plane][row][x/32] holds corners 4l .. 4l+3, i.e. the bytes of a row are the threads of a row in order:
+   * 0.25 B per corner instead of K2 re-reading 4 B.  Every thread stores its own byte -- a warp's 32 bytes are one
+   * 32-byte sector -- which is 15 instructions per warp less than assembling words with two shuffles and storing
+   * them from every fourth lane (5 % of the instructions of a mandelbulb warp outside the fractal). */
   if (opt & 4u) {
-#if S2M_K1_ROWS == 1
-    unsigned w = s2m_k1_class_byte(va, tau) << (8u * (lane & 3u));
-    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-    if (active && (lane & 3u) == 0u)
-      reinterpret_cast<unsigned*>(cls)[(row * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u)] = w;
-#else
-    /* both rows travel in one register: bytes (A even lane, A odd lane, B even lane, B odd lane)
-     * after the first exchange, then lane pairs (0,1) and (2,3) swap their 16-bit halves */
-    unsigned w = (s2m_k1_class_byte(va, tau) << (8u * (lane & 1u))) | (s2m_k1_class_byte(vb, tau) << (16u + 8u * (lane & 1u)));
-    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-    const unsigned o = __shfl_xor_sync(0xffffffffu, w, 2);
-    const unsigned lo = (lane & 2u) ? o : w, hi = (lane & 2u) ? w : o;   /* lanes 0-1 of the quad, lanes 2-3 */
-    const unsigned wa = (lo & 0xffffu) | (hi << 16), wb = (lo >> 16) | (hi & 0xffff0000u);
-    const unsigned long long at = (row * cls_words + (x4 >> 5)) * 2ull + ((lane >> 2) & 1u);
-    if (active && (lane & 3u) == 0u) reinterpret_cast<unsigned*>(cls)[at] = wa;
-    if (active_b && (lane & 3u) == 2u) reinterpret_cast<unsigned*>(cls)[at + 2ull * cls_words] = wb;
+    unsigned char* cb = reinterpret_cast<unsigned char*>(cls) + row * (g.pitch_x >> 2) + (x4 >> 2);
+    if (active) *cb = (unsigned char)s2m_k1_class_byte(va, tau);
+#if S2M_K1_ROWS == 2
+    if (active_b) cb[g.pitch_x >> 2] = (unsigned char)s2m_k1_class_byte(vb, tau);
 #endif
   }
   }  /* planes */
