@@ -606,6 +606,8 @@ int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uin
     opts.push_back("-DS2M_K1_MINBLOCKS=" + std::to_string(std::max(1, std::min(8, atoi(e)))));
   else if (packed_heavy || mid)
     opts.push_back("-DS2M_K1_MINBLOCKS=4");
+  if (const char* e = getenv("S2M_K1_GUARD")) { if (atoi(e) != 0) opts.push_back("-DS2M_K1_GUARD=1"); }  // experiment knob
+  else if (packed_heavy) opts.push_back("-DS2M_K1_GUARD=1");   // see s2m_k1_eval4
 
   const char* split = getenv("S2M_JIT_SPLIT");
   const int n_parts = (split && atoi(split) == 0) ? 1 : s2m_module::kMaxParts;

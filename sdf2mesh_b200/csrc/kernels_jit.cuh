@@ -65,10 +65,19 @@ __device__ __noinline__ float s2m_sdf_call(float x, float y, float z) { return s
  * (s2m_user_p::sdf3d2, s2m_pvec.h); bit (redo_shift + k/2) is set when the lanes of pair k disagreed on a
  * comparison or conversion, i.e. v[k+1] is not valid and the caller evaluates that corner alone. */
 __device__ __forceinline__ void s2m_k1_eval4(bool on, const float cx[4], float cy, float cz, float v[4], unsigned& redo, unsigned redo_shift) {
+  /* Without S2M_K1_GUARD every thread that is still here evaluates its 4 corners, also those in the row padding past
+   * the last corner (x4 > res; their coordinates continue the grid) and, with two rows per thread, a row past the last
+   * one -- they sit in warps that run for their in-grid lanes anyway, nobody reads what they produce (K2 masks the cells
+   * beyond the grid), and the guard with its zero fill is 6 instructions per warp (torus 2048^3 K1 7.5 -> 6.95 ms).
+   * The heavy packed kernel keeps the guard: without it the compiler pairs registers differently and K1 of the
+   * mandelbulb is 1 ms slower at 2048^3 (profiles/r02_k1_ab.jsonl). */
+#if defined(S2M_K1_GUARD)
   v[0] = 0.0f; v[1] = 0.0f; v[2] = 0.0f; v[3] = 0.0f;
-  /* One guard per thread, not per corner: a float4 whose first corner is inside the grid is
-   * evaluated whole (at most 3 corners past the last one per row, in the padding nobody reads). */
-  if (on) {
+  if (on)
+#else
+  (void)on;
+#endif
+  {
 #if S2M_K1_UNROLL == 1
 #pragma unroll 1
 #else
@@ -161,7 +170,6 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   for (int k = 0; k < 4; ++k) cx[k] = g.bmin[0] + g.size[0] * (float)(x4 + (unsigned)k);
   const float cy_a = g.bmin[1] + g.size[1] * (float)y;
 #endif
-  const bool in_x = x4 <= g.res[0];
 #if S2M_K1_ROWS == 2
   const bool active_b = active && y + 1u < g.rows;
 #if defined(S2M_K1_COORDS)
@@ -189,7 +197,9 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   if (!carry) {  /* one plane per thread: no loop (a loop of one iteration still costs the larger kernels registers) */
   const unsigned pz = blockIdx.z;
 #endif
-  const unsigned long long row = (unsigned long long)pz * g.rows + y;
+  /* the thread's first corner as a float index into the chunk's slab; a launch has fewer than 2^32 rows.  The class
+   * byte of 4 corners sits at a quarter of it (pitch_x and x4 are multiples of 4). */
+  const unsigned long long idx = (unsigned long long)(pz * g.rows + y) * g.pitch_x + x4;
 #if defined(S2M_K1_COORDS)
   const float cz = __ldg(coord_z + pz);
 #else
@@ -197,10 +207,10 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
 #endif
   float va[4];
   unsigned redo = 0;
-  s2m_k1_eval4(active && in_x, cx, cy_a, cz, va, redo, 0u);
+  s2m_k1_eval4(x4 <= g.res[0], cx, cy_a, cz, va, redo, 0u);
 #if S2M_K1_ROWS == 2
   float vb[4];
-  s2m_k1_eval4(active_b && in_x, cx, cy_b, cz, vb, redo, 2u);
+  s2m_k1_eval4(active_b && x4 <= g.res[0], cx, cy_b, cz, vb, redo, 2u);
 #endif
 #if defined(S2M_K1_PACKED)
   /* Rare (0.3 % of the mandelbulb's pairs at 2048^3): the two lanes of a pair took different paths.
@@ -221,9 +231,9 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   /* slab == nullptr: the slab-free form for cheap SDFs (S2M_MESH_NO_SLAB) -- only the corner classes below are
    * written (0.25 B per corner instead of 4.25) and K4a evaluates all 8 corners of every candidate cell itself. */
   if (opt & 2u) {
-    if (active) *reinterpret_cast<float4*>(slab + row * g.pitch_x + x4) = make_float4(va[0], va[1], va[2], va[3]);
+    if (active) *reinterpret_cast<float4*>(slab + idx) = make_float4(va[0], va[1], va[2], va[3]);
 #if S2M_K1_ROWS == 2
-    if (active_b) *reinterpret_cast<float4*>(slab + (row + 1ull) * g.pitch_x + x4) = make_float4(vb[0], vb[1], vb[2], vb[3]);
+    if (active_b) *reinterpret_cast<float4*>(slab + idx + g.pitch_x) = make_float4(vb[0], vb[1], vb[2], vb[3]);
 #endif
   }
   /* Corner classes for K2: P = value > +tau, N = value < -tau (NaN and the |v| <= tau band are
@@ -233,7 +243,7 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
    * 32-byte sector -- which is 15 instructions per warp less than assembling words with two shuffles and storing
    * them from every fourth lane (5 % of the instructions of a mandelbulb warp outside the fractal). */
   if (opt & 4u) {
-    unsigned char* cb = reinterpret_cast<unsigned char*>(cls) + row * (g.pitch_x >> 2) + (x4 >> 2);
+    unsigned char* cb = reinterpret_cast<unsigned char*>(cls) + (idx >> 2);
     if (active) *cb = (unsigned char)s2m_k1_class_byte(va, tau);
 #if S2M_K1_ROWS == 2
     if (active_b) cb[g.pitch_x >> 2] = (unsigned char)s2m_k1_class_byte(vb, tau);
