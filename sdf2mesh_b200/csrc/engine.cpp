@@ -1020,16 +1020,19 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
       // (>= 0.15 G voxels per chunk) for the two-stream overlap and the early output copies to pay:
       // up to 4 with a slab, up to 8 without one (nothing is resident per chunk but the class planes)
       const double voxels = (double)g.res[0] * g.res[1] * r->nz;
-      const uint32_t want = (uint32_t)std::min(no_slab ? 8.0 : 4.0, voxels / 1.5e8);
+      uint32_t want = (uint32_t)std::min(no_slab ? 8.0 : 4.0, voxels / 1.5e8);
+      if (const char* e = getenv("S2M_CHUNKS_WANT")) want = (uint32_t)std::max(1, atoi(e));  // experiment knob
       n_chunks = std::max(n_chunks, std::min(want, r->nz));
     }
     const uint32_t even = (r->nz + n_chunks - 1) / n_chunks;  // equal chunks instead of a short last one
     for (uint32_t z0 = 0; z0 < r->nz; z0 += even) chunks.push_back({z0, std::min(even, r->nz - z0)});
-    // Taper: what follows the LAST K1 launch -- K2, K3, K4a, K4b and the copy of the last chunk -- overlaps nothing, and
-    // it is proportional to that chunk's thickness (2 ms of a 25 ms slab at N = 2, 0.5 of 6 ms at N = 8).  The last
-    // chunk is therefore cut into 1/2, 1/4, 1/8, 1/8 of its thickness; every extra chunk costs five launches that run
-    // beside the next K1.  S2M_CHUNK_TAPER=0 keeps equal chunks.
-    static const bool taper = [] { const char* e = getenv("S2M_CHUNK_TAPER"); return !e || atoi(e) != 0; }();
+    // Taper (S2M_CHUNK_TAPER=1, off by default): what follows the LAST K1 launch -- K2, K3, K4a, K4b and the copy of the
+    // last chunk -- overlaps nothing and is proportional to that chunk's thickness, so the last chunk can be cut into
+    // 1/2, 1/4, 1/8, 1/8 of its thickness; every extra chunk costs five launches and two host waits.  It paid while a
+    // chunk cost three host waits and K2 ran between two K1 launches; with the final pipeline equal chunks are as fast
+    // or faster everywhere (2048^3 mandelbulb 40.03 vs 40.12 ms, 1024^3 6.32 vs 6.61, torus 2048^3 9.74 vs 10.08,
+    // p_key 1024^3 6.93 vs 7.08; profiles/r02_k1_ab.jsonl).
+    const bool taper = [] { const char* e = getenv("S2M_CHUNK_TAPER"); return e && atoi(e) != 0; }();
     if (taper && !dense && chunks.size() > 1 && chunks.back().nzc >= 32 && !getenv("S2M_NO_CHUNK_OVERLAP")) {
       const Chunk last = chunks.back();
       chunks.pop_back();
