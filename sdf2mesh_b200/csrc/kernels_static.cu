@@ -157,42 +157,47 @@ k2_classify_bits(const uint2* __restrict__ cls, uint32_t cls_words, uint32_t row
   const uint32_t y = blockIdx.y * 8u + (threadIdx.x >> 5);
   const uint32_t zt0 = blockIdx.z * K2_ZT;
   const bool live = xw < words_x && y < res_y;
+  const bool has_next = xw + 1u < cls_words;
   unsigned count = 0;
   unsigned long long prev = 0;
-  for (uint32_t k = 0; k <= (uint32_t)K2_ZT; ++k) {
-    const uint32_t plane = zt0 + k;
-    if (plane > nz_chunk) break;
+  // the thread's words of plane zt0 and where slice zt0's results go; every plane / slice further is one stride on
+  // (the addresses were a quarter of K2's instructions when they were computed from the indices in every iteration)
+  const uint2* r0 = cls + ((unsigned long long)zt0 * rows + y) * cls_words + xw;
+  const unsigned long long plane_step = (unsigned long long)rows * cls_words;
+  uint32_t* out = cand_mask + ((unsigned long long)zt0 * res_y + y) * words_x + xw;
+  const unsigned long long out_step = (unsigned long long)res_y * words_x;
+  uint32_t* seg = seg_count != nullptr ? seg_count + ((unsigned long long)zt0 * res_y + y) * gridDim.x + blockIdx.x : nullptr;
+  const unsigned long long seg_step = (unsigned long long)res_y * gridDim.x;
+  const uint32_t xb = xw * 32u;
+  const uint32_t edge = xb + 32u > res_x ? (xb < res_x ? (1u << (res_x - xb)) - 1u : 0u) : 0xffffffffu;   // cells beyond the grid
+  const uint32_t n_planes = min((uint32_t)K2_ZT, nz_chunk - min(zt0, nz_chunk)) + 1u;   // planes zt0 .. zt0 + n_planes - 1 <= nz_chunk
+  for (uint32_t k = 0; k < n_planes; ++k) {
     unsigned long long cur = 0;
     unsigned pc = 0;
     if (live) {
-      const uint2* r0 = cls + ((unsigned long long)plane * rows + y) * cls_words + xw;
       const uint2* r1 = r0 + cls_words;
-      const bool has_next = xw + 1u < cls_words;
       const unsigned long long a = ld_u64(r0), c = ld_u64(r1);
       const unsigned long long b = has_next ? ld_u64(r0 + 1) : 0ull, d = has_next ? ld_u64(r1 + 1) : 0ull;
-      // P nibbles: all 4 corners of this plane > tau; N nibbles: all < -tau.  Away from the surface -- 99 % of the words --
-      // both corner rows are uniformly P (or uniformly N) and so is the first corner of the next word: the pairing of
-      // such a word is the word itself (K2 is issue-bound; the two pairings are a third of its instructions)
-      const unsigned long long ac = a & c, bd = b & d;
-      if (ac == 0x0f0f0f0f0f0f0f0full && (a | c) == ac && (bd & 0x01ull)) cur = ac;
-      else if (ac == 0xf0f0f0f0f0f0f0f0ull && (a | c) == ac && (bd & 0x10ull)) cur = ac;
-      else cur = cls_pair_x(a, b) & cls_pair_x(c, d);
+      // P nibbles: all 4 corners of this plane > tau; N nibbles: all < -tau.  AND the two corner rows first, then pair in
+      // x once: the shift inside the pairing distributes over AND, so pair(a, b) & pair(c, d) == pair(a & c, b & d).
+      cur = cls_pair_x(a & c, b & d);
       if (k >= 1) {
-        const uint32_t z = plane - 1u;
-        uint32_t cand = cls_candidates(prev, cur);
-        const uint32_t xb = xw * 32u;
-        if (xb + 32u > res_x) cand &= (1u << (res_x - xb)) - 1u;
-        cand_mask[((unsigned long long)z * res_y + y) * words_x + xw] = cand;
+        const uint32_t cand = cls_candidates(prev, cur) & edge;
+        *out = cand;
         pc = (unsigned)__popc(cand);
         count += pc;
       }
     }
     // a warp is one segment (32 consecutive words of one cell row): its candidate count, for K3's scan
-    if (seg_count != nullptr && k >= 1) {
-      const unsigned sc = __reduce_add_sync(0xffffffffu, pc);
-      if ((threadIdx.x & 31u) == 0 && y < res_y)
-        seg_count[((unsigned long long)(plane - 1u) * res_y + y) * gridDim.x + blockIdx.x] = sc;
+    if (k >= 1) {
+      if (seg != nullptr) {
+        const unsigned sc = __reduce_add_sync(0xffffffffu, pc);
+        if ((threadIdx.x & 31u) == 0 && y < res_y) *seg = sc;
+        seg += seg_step;
+      }
+      out += out_step;
     }
+    r0 += plane_step;
     prev = cur;
   }
   for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);

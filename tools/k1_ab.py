@@ -71,6 +71,7 @@ def main():
             piped = run(ctx, mod, params, 4)
             print(json.dumps({"workload": wl, "S2M_K1_PACKED": v, "knobs": knobs, "packed": mod.packed, "jit_ms": round(jit, 1),
                               "k1_alone_ms": round(alone["k1_slab_ms"], 3), "k4a_alone_ms": round(alone["k4_vertices_ms"], 3),
+                              "k2_k3_k4b_alone_ms": [round(alone.get(k, 0.0), 3) for k in ("k2_classify_ms", "k3_compact_ms", "k4_quads_ms")],
                               "device_alone_ms": round(alone["device_ms"], 3), "wall_alone_ms": round(alone["wall_ms"], 3), "chunks": piped.get("chunks"), "chunks_alone": alone.get("chunks"),
                               "device_ms": round(piped["device_ms"], 3), "wall_ms": round(piped["wall_ms"], 3),
                               "Gvoxel_per_s": round(res ** 3 / piped["wall_ms"] / 1e6, 1), "counts": piped["counts"]}), flush=True)
