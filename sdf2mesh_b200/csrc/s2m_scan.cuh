@@ -26,18 +26,24 @@ __device__ __forceinline__ void s2m_st_relaxed(unsigned long long* p, unsigned l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-/* Called by every thread of warp 0 of the block (all 32 lanes converged).  `aggregate` is the
- * block's total (same value in all lanes).  Returns the exclusive prefix of this tile, i.e. `base`
- * plus the aggregates of all earlier tiles. */
-__device__ __forceinline__ unsigned long long s2m_lookback_warp(unsigned long long* status, unsigned tile,
-                                                                unsigned long long aggregate,
-                                                                unsigned long long base) {
+/* The look-back in two halves, for kernels that know their tile's total long before they need its prefix (K4a: the
+ * vertex count is known after the corner evaluations, the prefix is needed after the normal taps): publish early, look
+ * back late -- by then the predecessors have published too and nobody spins.
+ *
+ * s2m_publish_aggregate: lane 0 of warp 0 (any one thread) announces the tile's total. */
+__device__ __forceinline__ void s2m_publish_aggregate(unsigned long long* status, unsigned tile, unsigned long long aggregate,
+                                                      unsigned long long base) {
+  if (tile == 0) s2m_st_relaxed(status, (S2M_SCAN_PREFIX << 62) | (base + aggregate));
+  else s2m_st_relaxed(status + tile, (S2M_SCAN_AGGREGATE << 62) | aggregate);
+}
+/* s2m_lookback_published: called by every thread of warp 0 of the block (all 32 lanes converged) after
+ * s2m_publish_aggregate.  `aggregate` is the block's total (same value in all lanes).  Returns the exclusive prefix of
+ * this tile, i.e. `base` plus the aggregates of all earlier tiles, and upgrades the tile's status to that prefix. */
+__device__ __forceinline__ unsigned long long s2m_lookback_published(unsigned long long* status, unsigned tile,
+                                                                     unsigned long long aggregate,
+                                                                     unsigned long long base) {
   const unsigned lane = threadIdx.x & 31u;
-  if (tile == 0) {
-    if (lane == 0) s2m_st_relaxed(status, (S2M_SCAN_PREFIX << 62) | (base + aggregate));
-    return base;
-  }
-  if (lane == 0) s2m_st_relaxed(status + tile, (S2M_SCAN_AGGREGATE << 62) | aggregate);
+  if (tile == 0) return base;
   unsigned long long exclusive = 0;
   int look = (int)tile - 1;  /* nearest predecessor handled by lane 0 */
   for (;;) {
@@ -60,6 +66,13 @@ __device__ __forceinline__ unsigned long long s2m_lookback_warp(unsigned long lo
   }
   if (lane == 0) s2m_st_relaxed(status + tile, (S2M_SCAN_PREFIX << 62) | (exclusive + aggregate));
   return exclusive;
+}
+/* Both halves back to back.  Called by every thread of warp 0 of the block (all 32 lanes converged). */
+__device__ __forceinline__ unsigned long long s2m_lookback_warp(unsigned long long* status, unsigned tile,
+                                                                unsigned long long aggregate,
+                                                                unsigned long long base) {
+  if ((threadIdx.x & 31u) == 0) s2m_publish_aggregate(status, tile, aggregate, base);
+  return s2m_lookback_published(status, tile, aggregate, base);
 }
 
 /* Block-wide exclusive scan of one unsigned per thread (blockDim.x multiple of 32, <= 1024).
