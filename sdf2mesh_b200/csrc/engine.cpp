@@ -575,9 +575,10 @@ int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uin
   std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo",
                                    (flags & S2M_COMPILE_ALLOW_FMA) ? "--fmad=true" : "--fmad=false"};
   // Launch shape by the size of the SDF (measured on B200, profiles/r02_k1_ab.jsonl; every variant gives the same bits):
-  //  * heavy packed (>= 4 transcendental calls; mandelbulb): one row and one plane per thread, 64-register cap (4 resident
-  //    blocks).  (5 blocks / 48 registers won by 1 % before the round-2 instruction diet; after it 4 blocks do:
-  //    K1 36.75 vs 36.99 ms at 2048^3, 6 blocks 37.6.)
+  //  * heavy packed (>= 4 transcendental calls; mandelbulb): one row per thread, 16 planes marched per thread with the
+  //    coordinates from the run's table, 64-register cap (4 resident blocks).  (5 blocks / 48 registers and one plane
+  //    per thread won by 1-2 % before the round-2 instruction diet; after it: K1 35.5 ms at one plane, 34.3 at 2,
+  //    33.2 at 4, 32.8 at 8, 32.6 at 16, 32.8 at 32.)
   //  * tiny (<= 64 expression nodes; torus): two rows per thread and 16 planes marched per thread -- index, coordinate
   //    and class overhead is a third of its instructions (K1 11.4 -> 8.7 ms at 2048^3)
   //  * in between (p_key 206 nodes, martin_cube 683): one row per thread with a 64-register cap (two rows need 111 / 240
@@ -589,13 +590,13 @@ int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uin
   m->k1_rows = (packed_heavy || mid) ? 1u : kK1RowsDefault;
   if (const char* e = getenv("S2M_K1_ROWS")) m->k1_rows = atoi(e) == 2 ? 2u : 1u;  // experiment knob
   opts.push_back("-DS2M_K1_ROWS=" + std::to_string(m->k1_rows));
-  m->k1_zpt = tiny ? 16u : ((mid && plan.size > 0 && plan.size <= 400) ? 8u : 1u);
+  m->k1_zpt = (tiny || packed_heavy) ? 16u : ((mid && plan.size > 0 && plan.size <= 400) ? 8u : 1u);
   if (const char* e = getenv("S2M_K1_ZPT")) m->k1_zpt = (unsigned)std::max(1, std::min(64, atoi(e)));  // experiment knob
   opts.push_back("-DS2M_K1_ZPT=" + std::to_string(m->k1_zpt));
   // Corner coordinates from the run's table instead of i2f + mul + add per coordinate (kernels_jit.cuh): the mandelbulb's
   // K1 40.0 -> 38.5 ms at 2048^3, the others within noise (profiles/r02_k1_ab.jsonl); a thread that marches through
   // planes computes its x and y once anyway.
-  m->k1_coords = m->k1_zpt == 1;
+  m->k1_coords = m->k1_zpt == 1 || packed_heavy;
   if (const char* e = getenv("S2M_K1_COORDS")) m->k1_coords = atoi(e) != 0;  // experiment knob
   if (m->k1_coords) opts.push_back("-DS2M_K1_COORDS=1");
   if (const char* e = getenv("S2M_K1_UNROLL"))  // experiment knob, see kernels_jit.cuh
@@ -607,7 +608,7 @@ int build_cubins(s2m_module* m, const std::string& user, const K1Plan& plan, uin
   else if (packed_heavy || mid)
     opts.push_back("-DS2M_K1_MINBLOCKS=4");
   if (const char* e = getenv("S2M_K1_GUARD")) { if (atoi(e) != 0) opts.push_back("-DS2M_K1_GUARD=1"); }  // experiment knob
-  else if (packed_heavy) opts.push_back("-DS2M_K1_GUARD=1");   // see s2m_k1_eval4
+  // (no policy sets it any more: the heavy packed kernel kept the guard until it got its plane loop; see s2m_k1_eval4)
 
   const char* split = getenv("S2M_JIT_SPLIT");
   const int n_parts = (split && atoi(split) == 0) ? 1 : s2m_module::kMaxParts;
@@ -1117,10 +1118,14 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
     float tau_arg = tau;
     const float* coord_z = coord[2] ? coord[2] + first_plane : nullptr;
     unsigned opt = ((carry_slab || carry_cls) ? 1u : 0u) | (slab ? 2u : 0u) | (cls ? 4u : 0u);
-    void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw, &carry_slab, &carry_cls, &coord[0], &coord[1], &coord_z, &opt};
     unsigned bx, by;
     k1_block_shape(&bx, &by);
-    dim3 grid1((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), (n_planes + m->k1_zpt - 1u) / m->k1_zpt);
+    const unsigned gx = (g.pitch_x + 4u * bx - 1u) / (4u * bx), gy = (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows);
+    // planes a thread marches through: the module's maximum where the grid is large, fewer where that would leave the
+    // launch with less than ~8 waves of blocks (148 SMs x 4 resident blocks): a 256^3 grid gets 4, a 128^3 grid 1
+    unsigned zpt = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(m->k1_zpt, (unsigned long long)gx * gy * n_planes / 4736ull));
+    void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw, &carry_slab, &carry_cls, &coord[0], &coord[1], &coord_z, &opt, &zpt};
+    dim3 grid1(gx, gy, (n_planes + zpt - 1u) / zpt);
     {
       SPAN_BEGIN(0, ps);
       if ((st2 = launch(m->k1, grid1, dim3(bx, by, 1), ps, a1, "s2m_k1_slab"))) return st2;
@@ -1499,7 +1504,8 @@ extern "C" int s2m_debug_slab_plane(s2m_ctx* c, s2m_module* m, const s2m_mesh_pa
   if ((st = prepare_coords(c, m, g, bx, by, c->stream, coord))) return st;
   const float* coord_z = coord[2] ? coord[2] + first_plane : nullptr;
   unsigned opt = 2u;   // the slab only
-  void* a1[] = {&g, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words, &carry_slab, &carry_cls, &coord[0], &coord[1], &coord_z, &opt};
+  unsigned zpt = 1;
+  void* a1[] = {&g, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cls_words, &carry_slab, &carry_cls, &coord[0], &coord[1], &coord_z, &opt, &zpt};
   if ((st = launch(m->k1, dim3((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), 1), dim3(bx, by, 1), c->stream, a1, "s2m_k1_slab"))) return st;
   CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)(g.res[0] + 1) * 4, slab, (size_t)g.pitch_x * 4, (size_t)(g.res[0] + 1) * 4, g.rows,
                              cudaMemcpyDeviceToHost, c->stream));

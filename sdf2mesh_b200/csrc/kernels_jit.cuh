@@ -69,8 +69,9 @@ __device__ __forceinline__ void s2m_k1_eval4(bool on, const float cx[4], float c
    * the last corner (x4 > res; their coordinates continue the grid) and, with two rows per thread, a row past the last
    * one -- they sit in warps that run for their in-grid lanes anyway, nobody reads what they produce (K2 masks the cells
    * beyond the grid), and the guard with its zero fill is 6 instructions per warp (torus 2048^3 K1 7.5 -> 6.95 ms).
-   * The heavy packed kernel keeps the guard: without it the compiler pairs registers differently and K1 of the
-   * mandelbulb is 1 ms slower at 2048^3 (profiles/r02_k1_ab.jsonl). */
+   * S2M_K1_GUARD=1 is an experiment knob: with one plane per thread the mandelbulb's K1 was 1 ms slower without the
+   * guard (the compiler paired registers differently), with its plane loop it is 0.4 ms faster
+   * (profiles/r02_k1_ab.jsonl). */
 #if defined(S2M_K1_GUARD)
   v[0] = 0.0f; v[1] = 0.0f; v[2] = 0.0f; v[3] = 0.0f;
   if (on)
@@ -112,7 +113,7 @@ __device__ __forceinline__ unsigned s2m_k1_class_byte(const float v[4], float ta
 }
 
 #ifndef S2M_K1_ZPT
-#define S2M_K1_ZPT 1   /* planes a thread marches through (grid.z = ceil(planes / S2M_K1_ZPT)) */
+#define S2M_K1_ZPT 1   /* > 1: a thread marches through `zpt` planes (a launch parameter <= S2M_K1_ZPT; grid.z = ceil(planes / zpt)) */
 #endif
 #ifndef S2M_K1_MINBLOCKS
 #define S2M_K1_MINBLOCKS 1   /* resident 256-thread blocks per SM the register allocator must allow (8 = at most 32 registers) */
@@ -143,7 +144,7 @@ extern "C" __global__ void __launch_bounds__(256, S2M_K1_MINBLOCKS)
 s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned n_planes,
             float tau, uint2* __restrict__ cls, unsigned cls_words,
             const float* __restrict__ carry_slab, const uint2* __restrict__ carry_cls,
-            const float* __restrict__ coord_x, const float* __restrict__ coord_y, const float* __restrict__ coord_z, unsigned opt) {
+            const float* __restrict__ coord_x, const float* __restrict__ coord_y, const float* __restrict__ coord_z, unsigned opt, unsigned zpt) {
   /* opt: what the pointer arguments say, as bits (one 32-bit test each instead of 64-bit pointer compares per thread):
    * 1 = carry_slab or carry_cls is set, 2 = slab is set, 4 = cls is set.  coord_z points at first_plane's entry. */
   const unsigned x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
@@ -181,8 +182,9 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   /* For a tiny SDF a thread marches through S2M_K1_ZPT consecutive planes: its x and y coordinates, its indices and its
    * activity are computed once (they are a third of the instructions of a torus evaluation), only z changes.  Not
    * unrolled: one inlined copy of the SDF per row either way.  The plane range is the same for the whole block.
-   * Measured on B200 (profiles/r02_k1_ab.jsonl): torus 2048^3 K1 11.4 -> 8.7 ms at 16 planes; the mandelbulb and the
-   * primitive compositions lose 1-2 % (fewer, longer blocks), so they keep one plane per thread. */
+   * Measured on B200 (profiles/r02_k1_ab.jsonl): torus 2048^3 K1 11.4 -> 8.7 ms at 16 planes.  The mandelbulb lost
+   * 1-2 % while its per-thread overhead was hidden among 48-register spills and shuffles; after the round-2 diet it
+   * gains 8 % (K1 35.5 -> 32.6 ms at 16 planes).  The large primitive compositions keep one plane per thread. */
   const bool carry = blockIdx.z == 0u && (opt & 1u) != 0u;   /* uniform over the block */
 #if S2M_K1_ROWS == 2
   if (carry) s2m_k1_carry_plane(g.pitch_x, slab, cls, carry_slab, carry_cls, x4, y, active, active_b);
@@ -190,10 +192,11 @@ s2m_k1_slab(S2mGrid g, float* __restrict__ slab, unsigned first_plane, unsigned 
   if (carry) s2m_k1_carry_plane(g.pitch_x, slab, cls, carry_slab, carry_cls, x4, y, active, false);
 #endif
 #if S2M_K1_ZPT > 1
-  const unsigned pz_end = min(n_planes, (blockIdx.z + 1u) * (unsigned)S2M_K1_ZPT);
+  const unsigned pz_end = min(n_planes, (blockIdx.z + 1u) * zpt);
 #pragma unroll 1
-  for (unsigned pz = blockIdx.z * (unsigned)S2M_K1_ZPT + (carry ? 1u : 0u); pz < pz_end; ++pz) {
+  for (unsigned pz = blockIdx.z * zpt + (carry ? 1u : 0u); pz < pz_end; ++pz) {
 #else
+  (void)zpt;
   if (!carry) {  /* one plane per thread: no loop (a loop of one iteration still costs the larger kernels registers) */
   const unsigned pz = blockIdx.z;
 #endif

@@ -4,7 +4,7 @@
     ncu --metrics <METRICS below> --clock-control none -k regex:s2m_k1_slab --csv --log-file gpurun_out/k1cnt_<wl>.csv \\
         python bench.py --workload <wl> --steps 1 --warmup 1 --no-verify --no-cpu-baseline --no-other-workloads
 
-    python tools/ncu_k1_counters.py <wl>=gpurun_out/k1cnt_<wl>.csv:<K1 launches per step> ...
+    python tools/ncu_k1_counters.py <wl>=gpurun_out/k1cnt_<wl>.csv[:<K1 launches per step>] ...
 
 That bench command runs 5 meshing steps (warm-up, timed, one with event spans, two serialised); the launches of the
 SECOND step are summed.  <K1 launches per step> = z-chunks of a pipelined step = gpu_launches / (5 * steps) of a
@@ -42,7 +42,11 @@ def main():
         wl, path = spec.split("=", 1)
         path, _, per_s = path.partition(":")
         ls = parse(path)
-        per = int(per_s)          # z-chunks (= K1 launches) of a pipelined step: gpu_launches / (5 * steps) of the bench line
+        if per_s:
+            per = int(per_s)      # z-chunks (= K1 launches) of a pipelined step: gpu_launches / (5 * steps) of the bench line
+        else:                     # ... or found here: the first three steps are pipelined alike, so their grid sequence repeats
+            grids = [l["grid"] for l in ls]
+            per = next((q for q in range(1, len(grids) // 3 + 1) if grids[:q] == grids[q:2 * q] == grids[2 * q:3 * q] and (3 * q == len(grids) or grids[3 * q:4 * q] != grids[:q])), max(1, len(grids) // 5))
         step = ls[per:2 * per]    # the second step (the first pipelined step after the warm-up)
         tot = lambda m: sum(l.get(m, 0.0) for l in step)
         op = lambda o: tot(f"sm__sass_thread_inst_executed_op_{o}_pred_on.sum")
