@@ -44,9 +44,11 @@ def main():
         ls = parse(path)
         if per_s:
             per = int(per_s)      # z-chunks (= K1 launches) of a pipelined step: gpu_launches / (5 * steps) of the bench line
-        else:                     # ... or found here: the first three steps are pipelined alike, so their grid sequence repeats
-            grids = [l["grid"] for l in ls]
-            per = next((q for q in range(1, len(grids) // 3 + 1) if grids[:q] == grids[q:2 * q] == grids[2 * q:3 * q] and (3 * q == len(grids) or grids[3 * q:4 * q] != grids[:q])), max(1, len(grids) // 5))
+        else:                     # ... or found here: the first three steps are pipelined alike (their grid sequence repeats
+            grids = [l["grid"] for l in ls]   # three times), the two serialised steps that follow are alike too
+            ok = [q for q in range(1, len(grids) // 3 + 1)
+                  if grids[:q] == grids[q:2 * q] == grids[2 * q:3 * q] and len(grids) > 3 * q and (len(grids) - 3 * q) % 2 == 0]
+            per = max(ok) if ok else max(1, len(grids) // 5)
         step = ls[per:2 * per]    # the second step (the first pipelined step after the warm-up)
         tot = lambda m: sum(l.get(m, 0.0) for l in step)
         op = lambda o: tot(f"sm__sass_thread_inst_executed_op_{o}_pred_on.sum")
