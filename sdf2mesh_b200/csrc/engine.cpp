@@ -1027,13 +1027,18 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
     }
     const uint32_t even = (r->nz + n_chunks - 1) / n_chunks;  // equal chunks instead of a short last one
     for (uint32_t z0 = 0; z0 < r->nz; z0 += even) chunks.push_back({z0, std::min(even, r->nz - z0)});
-    // Taper (S2M_CHUNK_TAPER=1, off by default): what follows the LAST K1 launch -- K2, K3, K4a, K4b and the copy of the
-    // last chunk -- overlaps nothing and is proportional to that chunk's thickness, so the last chunk can be cut into
-    // 1/2, 1/4, 1/8, 1/8 of its thickness; every extra chunk costs five launches and two host waits.  It paid while a
-    // chunk cost three host waits and K2 ran between two K1 launches; with the final pipeline equal chunks are as fast
-    // or faster everywhere (2048^3 mandelbulb 40.03 vs 40.12 ms, 1024^3 6.32 vs 6.61, torus 2048^3 9.74 vs 10.08,
-    // p_key 1024^3 6.93 vs 7.08; profiles/r02_k1_ab.jsonl).
-    const bool taper = [] { const char* e = getenv("S2M_CHUNK_TAPER"); return e && atoi(e) != 0; }();
+    // Taper: what follows the LAST K1 launch -- K2, K3, K4a, K4b and the copy of the last chunk -- overlaps nothing and is
+    // proportional to what that chunk holds, so the last chunk is cut into 1/2, 1/4, 1/8, 1/8 of its thickness; every
+    // extra chunk costs five launches and two host waits.  It pays where the last chunk is full of surface: a slab that
+    // ends inside the grid (N = 2: the lower slab of the mandelbulb ends in its densest slices, 2.2 ms of a 19.6 ms step
+    // were that tail).  A slab that reaches the top of the grid usually ends in empty space, and there equal chunks are
+    // as fast or faster (2048^3 mandelbulb 40.03 vs 40.12 ms, 1024^3 6.32 vs 6.61, torus 2048^3 9.74 vs 10.08, p_key
+    // 1024^3 6.93 vs 7.08; profiles/r02_k1_ab.jsonl).  S2M_CHUNK_TAPER=0 / 1 forces it off / on.
+    const bool taper = [&] {
+      if (const char* e = getenv("S2M_CHUNK_TAPER")) return atoi(e) != 0;
+      if (no_slab) return false;   // a cheap SDF's tail is short: torus 2048^3 at N = 2 5.14 ms with equal chunks, 5.70 tapered
+      return r->z_first + r->nz < g.res[2] - ((p->flags & S2M_MESH_ALL_SLICES) ? 0u : 1u);
+    }();
     if (taper && !dense && chunks.size() > 1 && chunks.back().nzc >= 32 && !getenv("S2M_NO_CHUNK_OVERLAP")) {
       const Chunk last = chunks.back();
       chunks.pop_back();
