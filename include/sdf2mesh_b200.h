@@ -311,7 +311,8 @@ int s2m_eval_pairs(s2m_ctx* ctx, s2m_module* m, const float* xyz_a, const float*
                    uint8_t* disagreed);
 /* one corner plane of K1's slab: (dims[1]+1) x (dims[0]+1) floats, row-major */
 int s2m_debug_slab_plane(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, uint32_t plane, float* out);
-/* relative K1 cost of `planes` equal-thickness z bands (for balancing z-slabs across GPUs) */
+/* relative K1 cost of `planes` equal-thickness z bands (for balancing z-slabs across GPUs): the module's K1 on the middle
+ * corner plane of every band, timed with events (S2M_COST_PROBE=lattice: the round-1 lattice of scalar evaluations) */
 int s2m_cost_probe(s2m_ctx* ctx, s2m_module* m, const s2m_mesh_params* p, uint32_t planes, double* cost_out);
 
 #ifdef __cplusplus

@@ -107,7 +107,7 @@ struct DevBuf {
   int ensure(size_t bytes) {
     if (bytes <= cap) return S2M_OK;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
-    size_t want = bytes + (bytes >> 4) + 256;
+    size_t want = bytes + (bytes >> 2) + 256;   // 25 % slack: a z-slab whose boundaries are refined between runs grows without a new allocation
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
       cudaGetLastError();
@@ -1529,21 +1529,21 @@ extern "C" int s2m_read_device_words(s2m_ctx* c, const void* device_words, uint3
   return S2M_OK;
 }
 
-extern "C" int s2m_cost_probe(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, uint32_t planes, double* cost_out) {
-  if (!c || !m || !p || !cost_out || planes == 0) return fail(S2M_ERR_INVALID_ARG, "bad argument");
-  if (!m->k1 || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
-  GridDev g;
-  int st = make_grid(p, &g);
-  if (st) return st;
-  CUDA_TRY(cudaSetDevice(c->device));
+// Relative cost of the z-bands of a grid, for cutting it into slabs of equal work: K1 itself -- the module's own kernel,
+// launch shape and output buffers -- on ONE corner plane in the middle of every band, timed with events.  (Until round 2
+// a lattice of scalar evaluations timed with clock64, s2m_k_cost_probe: once K1's per-thread overhead had been cut it
+// overrated the cheap bands, and the first partition needed two refinements to recover.  S2M_COST_PROBE=lattice keeps it.)
+static int cost_probe_lattice(s2m_ctx* c, s2m_module* m, const GridDev& g, uint32_t planes, double* cost_out) {
   DevBuf buf;
+  int st;
   if ((st = buf.ensure((size_t)planes * 8 + 64))) return st;
   cudaStream_t s = c->stream;
   cudaError_t e = cudaMemsetAsync(buf.p, 0, (size_t)planes * 8 + 64, s);
   unsigned probe = 128, pl = planes;
   unsigned long long* cyc = buf.as<unsigned long long>();
   float* sink = reinterpret_cast<float*>(cyc + planes);
-  void* args[] = {&g, &probe, &pl, &cyc, &sink};
+  GridDev gd = g;
+  void* args[] = {&gd, &probe, &pl, &cyc, &sink};
   if (e == cudaSuccess) st = launch(m->k_probe, dim3(planes), dim3(256), s, args, "s2m_k_cost_probe");
   std::vector<unsigned long long> h(planes);
   if (e == cudaSuccess && !st) e = cudaMemcpyAsync(h.data(), cyc, (size_t)planes * 8, cudaMemcpyDeviceToHost, s);
@@ -1552,5 +1552,56 @@ extern "C" int s2m_cost_probe(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* 
   if (st) return st;
   if (e != cudaSuccess) return fail(S2M_ERR_CUDA, std::string("s2m_cost_probe: ") + cudaGetErrorString(e));
   for (uint32_t i = 0; i < planes; ++i) cost_out[i] = (double)h[i];
+  return S2M_OK;
+}
+
+extern "C" int s2m_cost_probe(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, uint32_t planes, double* cost_out) {
+  if (!c || !m || !p || !cost_out || planes == 0) return fail(S2M_ERR_INVALID_ARG, "bad argument");
+  if (!m->k1 || m->ctx != c) return fail(S2M_ERR_STATE, "module was not compiled for this ctx");
+  if (c->busy) return fail(S2M_ERR_STATE, "ctx is busy");
+  GridDev g;
+  int st = make_grid(p, &g);
+  if (st) return st;
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (const char* e = getenv("S2M_COST_PROBE")) if (!strcmp(e, "lattice")) return cost_probe_lattice(c, m, g, planes, cost_out);
+  cudaStream_t s = c->stream;
+  const bool no_slab = ((p->flags & S2M_MESH_NO_SLAB) || m->slab_free_default) && !(p->flags & (S2M_MESH_CLASSIFY_FROM_SLAB | S2M_MESH_EXACT_DENSE));
+  const unsigned cls_words = g.pitch_x / 32u;
+  DevBuf slab_buf, cls_buf;
+  if (!no_slab && (st = slab_buf.ensure(g.plane_stride * 4))) return st;
+  if ((st = cls_buf.ensure((size_t)g.rows * cls_words * 8 + 64))) return st;
+  unsigned bx, by;
+  k1_block_shape(&bx, &by);
+  const float* coord[3];
+  if ((st = prepare_coords(c, m, g, bx, by, s, coord))) return st;
+  std::vector<cudaEvent_t> ev(planes + 1, nullptr);
+  cudaError_t e = cudaSuccess;
+  for (auto& x : ev) if (e == cudaSuccess) e = cudaEventCreate(&x);
+  const dim3 grid((g.pitch_x + 4u * bx - 1u) / (4u * bx), (g.rows + by * m->k1_rows - 1u) / (by * m->k1_rows), 1), block(bx, by, 1);
+  float* slab = no_slab ? nullptr : slab_buf.as<float>();
+  void* cls = cls_buf.p;
+  unsigned n_planes = 1, cw = cls_words, opt = (slab ? 2u : 0u) | 4u, zpt = 1;
+  float tau_arg = 0.0f;
+  const float* carry_slab = nullptr;
+  const void* carry_cls = nullptr;
+  GridDev gd = g;
+  for (uint32_t i = 0; i <= planes && e == cudaSuccess && !st; ++i) {   // launch 0 warms the instruction cache up and is not timed
+    const uint32_t band = i == 0 ? 0u : i - 1u;
+    unsigned first_plane = (unsigned)std::min<unsigned long long>(g.res[2], ((2ull * band + 1ull) * (g.res[2] + 1ull)) / (2ull * planes));
+    const float* coord_z = coord[2] ? coord[2] + first_plane : nullptr;
+    void* a1[] = {&gd, &slab, &first_plane, &n_planes, &tau_arg, &cls, &cw, &carry_slab, &carry_cls, &coord[0], &coord[1], &coord_z, &opt, &zpt};
+    st = launch(m->k1, grid, block, s, a1, "s2m_k1_slab");
+    if (!st) e = cudaEventRecord(ev[i], s);
+  }
+  if (e == cudaSuccess && !st) e = cudaStreamSynchronize(s);
+  for (uint32_t i = 0; i < planes && e == cudaSuccess && !st; ++i) {
+    float ms = 0.0f;
+    e = cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+    cost_out[i] = (double)ms;
+  }
+  for (auto& x : ev) if (x) cudaEventDestroy(x);
+  slab_buf.release(); cls_buf.release();
+  if (st) return st;
+  if (e != cudaSuccess) return fail(S2M_ERR_CUDA, std::string("s2m_cost_probe: ") + cudaGetErrorString(e));
   return S2M_OK;
 }
