@@ -407,6 +407,31 @@ def test_continue_to_break_rewrite(built, monkeypatch):
     assert "break;" in load_example_shader("mandelbulb").lower_to_cuda()
 
 
+def test_guarded_loop_rotation(built, monkeypatch):
+    """IR optimisation (frontend/optimize.cpp: rotate_guarded_loop): `for (..) { P; if (c) break; R }` with a prefix of plain
+    assignments becomes `P; if (!c) for (;;) { R; step; if (!cond) break; P; if (c) break; }` -- what the compiler hoists
+    out of the loop for R's sake then sits behind the first test.  Loops whose rest `continue`s, whose prefix declares a
+    variable, or that have no prefix are left alone; the values never change (NaN and all)"""
+    rot = "fn sdf3d(p: vec3f) -> f32 { var r = 0.0; var z = p; var d = 1.0; for (var i = 0; i < 6; i++) { r = length(z); if (r > 2.0) { break; } d = d * r * 2.0 + 1.0; z = z * 1.7 + p; } return 0.5 * log(r) * r / d; }"
+    cont = "fn sdf3d(p: vec3f) -> f32 { var r = 0.0; var z = p; for (var i = 0; i < 6; i++) { r = length(z); if (r > 2.0) { break; } if (z.x > 1.0) { z = z * 0.5; continue; } z = z * 1.7 + p; } return r; }"
+    decl = "fn sdf3d(p: vec3f) -> f32 { var r = 0.0; var z = p; for (var i = 0; i < 6; i++) { let q = length(z); if (q > 2.0) { break; } r = r + q; z = z * 1.7 + p; } return r; }"
+    bare = "fn sdf3d(p: vec3f) -> f32 { var r = 0.0; var z = p; for (var i = 0; i < 6; i++) { if (r > 2.0) { break; } r = r + length(z); z = z * 1.7 + p; } return r; }"
+    nested = "fn sdf3d(p: vec3f) -> f32 { var r = 0.0; var z = p; for (var i = 0; i < 4; i++) { r = length(z); if (r > 3.0) { break; } for (var j = 0; j < 3; j++) { if (z.y > 0.5) { continue; } z.y = z.y + 0.3; } z = z * 1.3 + p; } return r; }"
+    zero = "fn sdf3d(p: vec3f) -> f32 { var r = 7.0; var z = p; for (var i = 0; i < i32(p.x); i++) { r = length(z); if (r > 2.0) { break; } z = z * 1.7 + p; } return r; }"
+    pts = points(4.0, 5000)
+    for src, rotated in ((rot, True), (cont, False), (decl, False), (bare, False), (nested, True), (zero, True)):
+        monkeypatch.delenv("S2M_NO_LOOP_ROTATION", raising=False)
+        opt = s2m.Sdf3DShader.from_source(src).lower_to_cuda()
+        monkeypatch.setenv("S2M_NO_LOOP_ROTATION", "1")
+        plain = s2m.Sdf3DShader.from_source(src).lower_to_cuda()
+        assert "for (; ; )" not in plain
+        assert ("for (; ; )" in opt) == rotated, src
+        assert f32_equal(host_eval.eval_points(opt, pts), host_eval.eval_points(plain, pts)).all(), src
+    monkeypatch.delenv("S2M_NO_LOOP_ROTATION", raising=False)
+    sh = load_example_shader("mandelbulb")
+    assert "for (; ; )" in sh.lower_to_cuda() and "for (; ; )" in sh.lower_to_cuda_packed()
+
+
 def test_sin_cos_pairing(built, monkeypatch):
     """IR optimisation (frontend/optimize.cpp: pair_sin_cos): sin(e) / cos(e) of the same pure argument
     become one sincos_pair(e) unless a variable of e is written in between; values never change"""

@@ -66,6 +66,29 @@ def test_packed_device_bits(ctx, name, tmp_path, monkeypatch):
         assert f32_equal(lo, h_lo).all() and (f32_equal(hi, h_hi) | dv).all()
 
 
+def test_packed_division_by_one(ctx, monkeypatch):
+    """s2m_pvec.h p_div: a divisor pair of exactly (1, 1) takes one packed multiplication by 1 instead of two IEEE
+    divisions.  Same bits as the scalar quotient for every numerator -- -0, denormals, infinities, NaN (canonical either
+    way), huge and tiny values -- and for divisor pairs of which only one lane is 1"""
+    monkeypatch.setenv("S2M_K1_PACKED", VARIANT)
+    src = ("fn sdf3d(p: vec3f) -> f32 { var d = 1.0; if (p.z > 0.5) { d = p.z; } let num = p.x * p.y; let a = num / d; "
+           "let b = (p.x / p.y) / d; let c = (num - num) / (p.y - p.y) / d; return a + b * 0.5 + c; }")
+    mod = s2m.Sdf3DShader.from_source(src).create_shader_module(ctx)
+    assert mod.packed, mod.log
+    special = np.array([0.0, -0.0, 1.0, -1.0, 1e-45, -1e-45, 1e-38, 3e38, -3e38, np.inf, -np.inf, np.nan, 1e-20, 1e20, 0.5, 2.0], np.float32)
+    xs, ys, zs = np.meshgrid(special, special, np.array([0.0, 0.25, 0.5, 1.0, 1.0000001, 3.0, np.nan], np.float32), indexing="ij")
+    a = np.stack([xs.ravel(), ys.ravel(), zs.ravel()], 1).astype(np.float32)
+    want_a = mod.eval_points(a)
+    for shift in (1, 7, 16 * 7 + 3):   # partners with the same and with another divisor
+        b = np.roll(a, shift, axis=0)
+        want_b = mod.eval_points(b)
+        lo, hi, dv = mod.eval_pairs(a, b)
+        assert f32_equal(lo, want_a).all()
+        agree = dv == 0
+        assert agree.mean() > 0.3 and f32_equal(hi[agree], want_b[agree]).all()
+    assert np.isnan(want_a).any() and np.isinf(want_a).any() and (want_a == 0).any()
+
+
 @pytest.mark.parametrize("name,res,bounds", [("torus", 128, 2.0), ("martin_cube", 128, 2.0), ("p_key", 128, 20.0), ("mandelbulb", 128, 5.0)])
 def test_mesh_with_packed_k1_matches_oracle(ctx, name, res, bounds, monkeypatch):
     monkeypatch.setenv("S2M_K1_PACKED", VARIANT)
