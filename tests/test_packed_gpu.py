@@ -79,13 +79,15 @@ def test_packed_division_by_one(ctx, monkeypatch):
     xs, ys, zs = np.meshgrid(special, special, np.array([0.0, 0.25, 0.5, 1.0, 1.0000001, 3.0, np.nan], np.float32), indexing="ij")
     a = np.stack([xs.ravel(), ys.ravel(), zs.ravel()], 1).astype(np.float32)
     want_a = mod.eval_points(a)
-    for shift in (1, 7, 16 * 7 + 3):   # partners with the same and with another divisor
+    for shift in (7, 16 * 7, 3 * 16 * 7 + 5 * 7, 1, 3):   # z is the fastest index: multiples of 7 pair points with the same divisor
         b = np.roll(a, shift, axis=0)
         want_b = mod.eval_points(b)
         lo, hi, dv = mod.eval_pairs(a, b)
         assert f32_equal(lo, want_a).all()
         agree = dv == 0
-        assert agree.mean() > 0.3 and f32_equal(hi[agree], want_b[agree]).all()
+        assert f32_equal(hi[agree], want_b[agree]).all()
+        if shift % 7 == 0:
+            assert agree.mean() > 0.8   # only NaN z compares differently from itself... it does not: same branch in both lanes
     assert np.isnan(want_a).any() and np.isinf(want_a).any() and (want_a == 0).any()
 
 
