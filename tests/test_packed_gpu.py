@@ -72,7 +72,8 @@ def test_packed_division_by_one(ctx, monkeypatch):
     way), huge and tiny values -- and for divisor pairs of which only one lane is 1"""
     monkeypatch.setenv("S2M_K1_PACKED", VARIANT)
     src = ("fn sdf3d(p: vec3f) -> f32 { var d = 1.0; if (p.z > 0.5) { d = p.z; } let num = p.x * p.y; let a = num / d; "
-           "let b = (p.x / p.y) / d; let c = (num - num) / (p.y - p.y) / d; return a + b * 0.5 + c; }")
+           "let b = (p.x / p.y) / d; let c = (num - num) / (p.y - p.y) / d; if (p.z == 0.0) { return a; } if (p.z == 0.25) { return b; } "
+           "if (p.z == 0.5) { return c; } return a + b * 0.5; }")
     mod = s2m.Sdf3DShader.from_source(src).create_shader_module(ctx)
     assert mod.packed, mod.log
     special = np.array([0.0, -0.0, 1.0, -1.0, 1e-45, -1e-45, 1e-38, 3e38, -3e38, np.inf, -np.inf, np.nan, 1e-20, 1e20, 0.5, 2.0], np.float32)
