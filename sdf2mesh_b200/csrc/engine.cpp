@@ -1002,7 +1002,10 @@ int mesh_begin_impl(s2m_ctx* c, s2m_module* m, const s2m_mesh_params* p, s2m_res
   std::vector<Chunk> chunks;
   const unsigned long long plane_bytes = g.plane_stride * 4ull;
   if (r->nz > 0) {
-    unsigned long long budget = p->slab_budget_bytes ? p->slab_budget_bytes : (4ull << 30);
+    // default 8 GiB per slab buffer (two of them when pipelined, of 180 GB): 2048^3 in 5 chunks, 25 launches; 4 GiB (9 chunks)
+    // was 0.6 % slower, 3 GiB (11 chunks) 1.3 % (profiles/r02_k1_ab.jsonl)
+    unsigned long long budget = p->slab_budget_bytes ? p->slab_budget_bytes : (8ull << 30);
+    if (!p->slab_budget_bytes) if (const char* e = getenv("S2M_SLAB_BUDGET_GB")) budget = (unsigned long long)(std::max(0.01, atof(e)) * (double)(1ull << 30));  // experiment knob
     uint32_t zc = r->nz;
     if (!no_slab || p->slab_budget_bytes) {
       for (;;) {
