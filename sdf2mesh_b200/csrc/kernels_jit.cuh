@@ -12,7 +12,8 @@
  *                      the sign nibble :57-69 -- and the host pixel scan + VertexList::insert
  *                      (main.rs:327-344, mesh.rs:237) by a stable single-pass compaction.
  *     s2m_k_eval       evaluates the SDF at caller-supplied points (diagnostics / parity tests).
- *     s2m_k_cost_probe per-z-plane evaluation cost estimate used to balance multi-GPU z-slabs.
+ *     s2m_k_cost_probe per-z-plane evaluation cost from a lattice of scalar evaluations (S2M_COST_PROBE=lattice; by default
+ *                      s2m_cost_probe times K1 itself on one plane per z-band, engine.cpp).
  */
 
 /* The module is compiled as three independent NVRTC programs, concurrently on three host threads
