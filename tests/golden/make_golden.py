@@ -31,7 +31,8 @@ CASES = [
 BIG = [("torus", 512, 2.0, 0), ("martin_cube", 512, 2.0, 0), ("mandelbulb", 512, 5.0, 0), ("p_key", 512, 20.0, 0)]
 # headline sizes: minutes of CPU on 16 cores; run on the GPU box's host (`--huge`), output copied back
 HUGE = [("mandelbulb", 1024, 5.0, 0), ("mandelbulb", 2048, 5.0, 0), ("p_key", 1024, 20.0, 0),
-        ("p_key", 1024, 2.0, 0)]   # BASELINE config 3 as literally stated: --resolution 1024, default --bounds 2 (main.rs:150)
+        ("p_key", 1024, 2.0, 0),   # BASELINE config 3 as literally stated: --resolution 1024, default --bounds 2 (main.rs:150)
+        ("torus", 2048, 2.0, 0)]   # bench.py's torus2048 entry (315 s on 8 cores)
 
 
 # BASELINE config 5 in full: 68.7 G cells, 8 SDF evaluations each (~35 minutes on 8 cores, 5 GB); `--giant`
